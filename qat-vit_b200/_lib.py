@@ -1,0 +1,87 @@
+"""ctypes loader for libqatvit_b200.so (the C-ABI in include/qatvit_b200.h).
+
+There is NO fallback: if the shared library is missing, importing this module raises, and every compute
+entry point fails without a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libqatvit_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "qatvit_b200.h")
+
+
+def build(verbose: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a with nvcc (cross-compiles without a GPU)."""
+    cmd = ["make", "-C", os.path.join(_HERE, "csrc"), "-j8"]
+    res = subprocess.run(cmd, capture_output=not verbose, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("building libqatvit_b200.so failed:\n" + (res.stdout or "") + (res.stderr or ""))
+    return LIB_PATH
+
+
+class GemmArgs(ctypes.Structure):
+    """struct qv_gemm_args (include/qatvit_b200.h)."""
+    _fields_ = [
+        ("a", c_void_p), ("lda", c_int64), ("a_plane_stride", c_int64), ("a_mn_major", c_int32),
+        ("b", c_void_p), ("ldb", c_int64), ("b_plane_stride", c_int64), ("b_mn_major", c_int32),
+        ("npairs", c_int32), ("pair_a", c_int32 * 4), ("pair_b", c_int32 * 4),
+        ("M", c_int64), ("N", c_int64), ("K", c_int64),
+        ("d", c_void_p), ("ldd", c_int64),
+        ("col_scale", c_void_p), ("col_rscale", c_void_p), ("alpha", c_void_p), ("bias", c_void_p),
+        ("minmax", c_void_p),
+        ("splits", c_int32), ("workspace", c_void_p),
+    ]
+
+
+_P = c_void_p
+_SIGNATURES = {
+    "qv_version": (c_int, []),
+    "qv_last_error": (c_char_p, []),
+    "qv_device_sm_count": (c_int, []),
+    "qv_launch_count": (c_int64, []),
+    "qv_minmax_reset": (c_int, [_P, c_int, _P]),
+    "qv_minmax_accumulate": (c_int, [_P, c_int64, _P, _P]),
+    "qv_obs_update": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_float, c_int32, c_int32, c_int32, _P]),
+    "qv_fq_apply": (c_int, [_P, c_int64, _P, _P, _P, c_int32, c_int32, _P, _P, _P]),
+    "qv_fq_weight": (c_int, [_P, c_int64, c_int64, c_int32, _P, _P, _P, _P, _P, _P, c_float, c_int32, c_int32,
+                             c_int32, _P, _P, _P, _P, _P, _P]),
+    "qv_fq_bwd": (c_int, [_P, _P, c_int64, _P, _P]),
+    "qv_split_planes": (c_int, [_P, c_int64, _P, _P, _P]),
+    "qv_kd_ce_loss": (c_int, [_P, _P, _P, c_int32, c_int32, c_float, c_float, c_float, _P, _P, c_int32, c_int32,
+                              _P, _P, _P]),
+    "qv_gemm_bf16": (c_int, [POINTER(GemmArgs), _P]),
+    "qv_splitk_reduce": (c_int, [_P, c_int32, c_int64, c_int64, _P, _P, _P, _P, c_int32, _P]),
+}
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(qatvit_b200 has no CPU / PyTorch fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().qv_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"qatvit_b200 {what} failed (code {rc}): {msg}")

@@ -1,0 +1,389 @@
+// fakequant.cu -- observer + fake-quant kernels (HBM-bound, vectorised, SM-count sized grids).
+//
+// Replaces the single ATen op behind FusedMovingAvgObsFakeQuantize.forward
+// (torch/ao/quantization/fake_quantize.py:423-438 -> fused_moving_avg_obs_fake_quant), i.e. torch's
+// aminmax + MovingAverageMinMax + ChooseQuantizationParamsKernelImpl + FakeQuantizeCore launches
+// (SURVEY.md §2.4 K1-K6).  Arithmetic contract: the CPU path:
+//   EMA fp32 mul-then-add, fbgemm ChooseQuantizationParams (float scale, double zero-point math),
+//   q = rint(x * (1/s)) + zp, clamp, (q - zp) * s.
+#include <stdio.h>
+
+#include "qv_common.cuh"
+
+namespace {
+
+// ---------------- ChooseQuantizationParams (fbgemm flavour; see oracle/fq_oracle.c) ----------------
+__device__ void qv_choose_qparams(float mn, float mx, int qmin, int qmax, bool preserve_sparsity, float* scale_out,
+                                  int32_t* zp_out) {
+  if (mn < 0.f && mx > 0.f && preserve_sparsity) {
+    const int sqmin = -((qmax - qmin) / 2 + 1);
+    const int sqmax = (qmax - qmin) / 2;
+    const float a = __fdiv_rn(mn, (float)sqmin);
+    const float b = __fdiv_rn(mx, (float)sqmax);
+    const double ms = fmax(fabs((double)a), fabs((double)b));
+    mn = (float)__dmul_rn(ms, (double)sqmin);
+    mx = (float)__dmul_rn(ms, (double)sqmax);
+  }
+  mn = fminf(mn, 0.f);
+  mx = fmaxf(mx, 0.f);
+  float scale = (float)__ddiv_rn(__dsub_rn((double)mx, (double)mn), (double)(qmax - qmin));
+  if (scale == 0.0f || isinf(__fdiv_rn(1.0f, scale))) scale = 0.1f;
+  const float kSmall = 6.1e-5f;
+  if (scale < kSmall) {
+    const float org = scale;
+    scale = kSmall;
+    if (mn == 0.0f) {
+      mx = __fmul_rn(kSmall, (float)(qmax - qmin));
+    } else if (mx == 0.0f) {
+      mn = __fmul_rn(-kSmall, (float)(qmax - qmin));
+    } else {
+      const float amp = __fdiv_rn(kSmall, org);
+      mn = __fmul_rn(mn, amp);
+      mx = __fmul_rn(mx, amp);
+    }
+  }
+  const double ds = (double)scale;
+  const double mn_s = __ddiv_rn((double)mn, ds), mx_s = __ddiv_rn((double)mx, ds);
+  const double zp_from_min = __dsub_rn((double)qmin, mn_s);
+  const double zp_from_max = __dsub_rn((double)qmax, mx_s);
+  const double err_min = __dadd_rn((double)abs(qmin), fabs(mn_s));
+  const double err_max = __dadd_rn((double)abs(qmax), fabs(mx_s));
+  double zp0 = err_min < err_max ? zp_from_min : zp_from_max;
+  if (mn < 0.f && mx > 0.f && preserve_sparsity) zp0 = (double)(qmin + qmax) / 2.0;
+  int32_t zp;
+  if (zp0 < (double)qmin) zp = qmin;
+  else if (zp0 > (double)qmax) zp = qmax;
+  else zp = (int32_t)rint(zp0);
+  *scale_out = scale;
+  *zp_out = zp;
+}
+
+__device__ __forceinline__ float qv_ema(float r, float cur, float c) {
+  if (isinf(r)) return cur;
+  return __fadd_rn(r, __fmul_rn(c, __fsub_rn(cur, r)));
+}
+
+// ---------------- min/max accumulation ----------------
+__global__ void qv_minmax_reset_kernel(uint32_t* acc, int count) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) {
+    acc[2 * i] = QV_ORD_MIN_INIT;
+    acc[2 * i + 1] = QV_ORD_MAX_INIT;
+  }
+}
+
+__device__ __forceinline__ void qv_block_minmax_commit(float mn, float mx, uint32_t* acc) {
+  __shared__ float smn[32], smx[32];
+  mn = qv_warp_min(mn);
+  mx = qv_warp_max(mx);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  if (lane == 0) { smn[warp] = mn; smx[warp] = mx; }
+  __syncthreads();
+  if (warp == 0) {
+    mn = lane < nw ? smn[lane] : INFINITY;
+    mx = lane < nw ? smx[lane] : -INFINITY;
+    mn = qv_warp_min(mn);
+    mx = qv_warp_max(mx);
+    if (lane == 0 && mn <= mx) {
+      atomicMin(acc, qv_f2ord(mn));
+      atomicMax(acc + 1, qv_f2ord(mx));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) qv_minmax_kernel(const float* __restrict__ x, int64_t n, uint32_t* acc) {
+  float mn = INFINITY, mx = -INFINITY;
+  const int64_t n4 = n >> 2;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  // 4 independent 16-byte loads in flight per thread
+  for (; i + 3 * stride < n4; i += 4 * stride) {
+    float4 a = __ldg(x4 + i), b = __ldg(x4 + i + stride), c = __ldg(x4 + i + 2 * stride), d = __ldg(x4 + i + 3 * stride);
+    mn = fminf(mn, fminf(fminf(fminf(a.x, a.y), fminf(a.z, a.w)), fminf(fminf(b.x, b.y), fminf(b.z, b.w))));
+    mn = fminf(mn, fminf(fminf(fminf(c.x, c.y), fminf(c.z, c.w)), fminf(fminf(d.x, d.y), fminf(d.z, d.w))));
+    mx = fmaxf(mx, fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)), fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w))));
+    mx = fmaxf(mx, fmaxf(fmaxf(fmaxf(c.x, c.y), fmaxf(c.z, c.w)), fmaxf(fmaxf(d.x, d.y), fmaxf(d.z, d.w))));
+  }
+  for (; i < n4; i += stride) {
+    float4 a = __ldg(x4 + i);
+    mn = fminf(mn, fminf(fminf(a.x, a.y), fminf(a.z, a.w)));
+    mx = fmaxf(mx, fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    float v = x[(n4 << 2) + threadIdx.x];
+    mn = fminf(mn, v);
+    mx = fmaxf(mx, v);
+  }
+  qv_block_minmax_commit(mn, mx, acc);
+}
+
+// ---------------- per-tensor observer update (1 thread) ----------------
+__global__ void qv_obs_update_kernel(const uint32_t* acc, const int64_t* obs_on, const int64_t* fq_on, float* min_val,
+                                     float* max_val, float* scale, int32_t* zp, float c, int qmin, int qmax,
+                                     int symmetric) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (*obs_on == 0) return;
+  const uint32_t emn = acc[0], emx = acc[1];
+  if (emn == QV_ORD_MIN_INIT && emx == QV_ORD_MAX_INIT) return;   // empty tensor: nothing observed
+  const float cur_min = qv_ord2f(emn), cur_max = qv_ord2f(emx);
+  const float rmin = qv_ema(*min_val, cur_min, c);
+  const float rmax = qv_ema(*max_val, cur_max, c);
+  *min_val = rmin;
+  *max_val = rmax;
+  if (*fq_on != 0) {
+    float s;
+    int32_t z;
+    qv_choose_qparams(rmin, rmax, qmin, qmax, symmetric != 0, &s, &z);
+    *scale = s;
+    *zp = z;
+  }
+}
+
+// ---------------- elementwise fake-quant ----------------
+__global__ void __launch_bounds__(256) qv_fq_apply_kernel(const float* __restrict__ x, int64_t n,
+                                                          const float* __restrict__ scale,
+                                                          const int32_t* __restrict__ zp,
+                                                          const int64_t* __restrict__ fq_on, int qmin, int qmax,
+                                                          float* __restrict__ y, uint8_t* __restrict__ mask) {
+  const bool on = (*fq_on != 0);
+  const QvQParams q = qv_load_qparams(scale, zp, qmin, qmax);
+  const int64_t n4 = n >> 2;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    float4 o;
+    uchar4 m;
+    if (on) {
+      bool b0, b1, b2, b3;
+      o.x = qv_fq(v.x, q, &b0, nullptr);
+      o.y = qv_fq(v.y, q, &b1, nullptr);
+      o.z = qv_fq(v.z, q, &b2, nullptr);
+      o.w = qv_fq(v.w, q, &b3, nullptr);
+      m = make_uchar4(b0, b1, b2, b3);
+    } else {
+      o = v;
+      m = make_uchar4(1, 1, 1, 1);
+    }
+    reinterpret_cast<float4*>(y)[i] = o;
+    if (mask) reinterpret_cast<uchar4*>(mask)[i] = m;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    bool b = true;
+    y[i] = on ? qv_fq(x[i], q, &b, nullptr) : x[i];
+    if (mask) mask[i] = b;
+  }
+}
+
+__global__ void __launch_bounds__(256) qv_fq_bwd_kernel(const float* __restrict__ gy, const uint8_t* __restrict__ mask,
+                                                        int64_t n, float* __restrict__ gx) {
+  const int64_t n4 = n >> 2;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4; i += stride) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gy) + i);
+    const uchar4 m = __ldg(reinterpret_cast<const uchar4*>(mask) + i);
+    reinterpret_cast<float4*>(gx)[i] = make_float4(m.x ? g.x : 0.f, m.y ? g.y : 0.f, m.z ? g.z : 0.f, m.w ? g.w : 0.f);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    gx[i] = mask[i] ? gy[i] : 0.f;
+  }
+}
+
+// ---------------- weight flavour: one block per row ----------------
+// PER_CHANNEL: row min/max -> EMA -> qparams inside the block; else qparams were produced by
+// qv_minmax_kernel + qv_obs_update_kernel and are read from element 0.
+template <bool PER_CHANNEL>
+__global__ void __launch_bounds__(128) qv_fq_weight_kernel(const float* __restrict__ w, int64_t rows, int64_t cols,
+                                                           const int64_t* obs_on, const int64_t* fq_on, float* min_val,
+                                                           float* max_val, float* scale, int32_t* zp, float c, int qmin,
+                                                           int qmax, int symmetric, float* __restrict__ y,
+                                                           uint8_t* __restrict__ mask, __nv_bfloat16* __restrict__ codes,
+                                                           __nv_bfloat16* __restrict__ codes_t) {
+  const int64_t r = blockIdx.x;
+  const float* wr = w + r * cols;
+  __shared__ float s_scale;
+  __shared__ int32_t s_zp;
+  __shared__ float smn[4], smx[4];
+  const bool fq = (*fq_on != 0);
+  if (PER_CHANNEL) {
+    if (*obs_on != 0) {
+      float mn = INFINITY, mx = -INFINITY;
+      for (int64_t k = threadIdx.x; k < cols; k += blockDim.x) {
+        const float v = __ldg(wr + k);
+        mn = fminf(mn, v);
+        mx = fmaxf(mx, v);
+      }
+      mn = qv_warp_min(mn);
+      mx = qv_warp_max(mx);
+      if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        mn = fminf(fminf(smn[0], smn[1]), fminf(smn[2], smn[3]));
+        mx = fmaxf(fmaxf(smx[0], smx[1]), fmaxf(smx[2], smx[3]));
+        const float rmin = qv_ema(min_val[r], mn, c), rmax = qv_ema(max_val[r], mx, c);
+        min_val[r] = rmin;
+        max_val[r] = rmax;
+        if (fq) {
+          float s;
+          int32_t z;
+          qv_choose_qparams(rmin, rmax, qmin, qmax, symmetric != 0, &s, &z);
+          scale[r] = s;
+          zp[r] = z;
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { s_scale = scale[r]; s_zp = zp[r]; }
+  } else {
+    if (threadIdx.x == 0) { s_scale = scale[0]; s_zp = zp[0]; }
+  }
+  __syncthreads();
+  QvQParams q;
+  q.scale = s_scale;
+  q.inv = __fdiv_rn(1.0f, q.scale);
+  q.zp = (float)s_zp;
+  q.qmin = (float)qmin;
+  q.qmax = (float)qmax;
+  for (int64_t k = threadIdx.x; k < cols; k += blockDim.x) {
+    const float v = __ldg(wr + k);
+    bool in = true;
+    float cc = 0.f;
+    const float o = fq ? qv_fq(v, q, &in, &cc) : v;
+    const int64_t idx = r * cols + k;
+    if (y) y[idx] = o;
+    if (mask) mask[idx] = in;
+    if (codes) codes[idx] = __float2bfloat16_rn(cc);
+    if (codes_t) codes_t[k * rows + r] = __float2bfloat16_rn(cc);
+  }
+}
+
+// ---------------- fp32 -> bf16 hi/lo planes ----------------
+__global__ void __launch_bounds__(256) qv_split_planes_kernel(const float* __restrict__ x, int64_t n,
+                                                              __nv_bfloat16* __restrict__ hi,
+                                                              __nv_bfloat16* __restrict__ lo) {
+  const int64_t n4 = n >> 2;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    __nv_bfloat16 h[4], l[4];
+    qv_split_bf16(v.x, h[0], l[0]);
+    qv_split_bf16(v.y, h[1], l[1]);
+    qv_split_bf16(v.z, h[2], l[2]);
+    qv_split_bf16(v.w, h[3], l[3]);
+    reinterpret_cast<uint2*>(hi)[i] = *reinterpret_cast<uint2*>(h);
+    reinterpret_cast<uint2*>(lo)[i] = *reinterpret_cast<uint2*>(l);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    qv_split_bf16(x[i], hi[i], lo[i]);
+  }
+}
+
+inline int ew_blocks(int64_t n4) {
+  const int sms = qv_num_sms();
+  int64_t b = (n4 + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(sms > 0 ? sms : 1) * 8;   // 8 resident 256-thread CTAs per SM
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+}  // namespace
+
+extern "C" int qv_minmax_reset(uint32_t* acc, int count, void* stream) {
+  QV_REQUIRE(acc && count > 0, QV_ERR_INVALID, "bad minmax_reset arguments");
+  qv_minmax_reset_kernel<<<(count + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(acc, count);
+  return qv_check_launch("qv_minmax_reset");
+}
+
+extern "C" int qv_minmax_accumulate(const float* x, int64_t n, uint32_t* acc, void* stream) {
+  QV_REQUIRE(acc != nullptr && n >= 0, QV_ERR_INVALID, "bad minmax arguments");
+  if (n == 0) return QV_OK;
+  QV_REQUIRE(x && qv_aligned16(x), QV_ERR_INVALID, "x must be a 16-byte aligned device pointer");
+  QV_REQUIRE(qv_num_sms() > 0, QV_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  qv_minmax_kernel<<<ew_blocks((n >> 2) / 4 + 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, acc);
+  return qv_check_launch("qv_minmax_accumulate");
+}
+
+extern "C" int qv_obs_update(const uint32_t* acc, const int64_t* observer_enabled, const int64_t* fake_quant_enabled,
+                             float* min_val, float* max_val, float* scale, int32_t* zero_point, float averaging_const,
+                             int32_t qmin, int32_t qmax, int32_t symmetric, void* stream) {
+  QV_REQUIRE(acc && observer_enabled && fake_quant_enabled && min_val && max_val && scale && zero_point,
+             QV_ERR_INVALID, "null observer state pointer");
+  QV_REQUIRE(qmin < qmax, QV_ERR_INVALID, "qmin must be < qmax");
+  qv_obs_update_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(acc, observer_enabled, fake_quant_enabled,
+                                                                       min_val, max_val, scale, zero_point,
+                                                                       averaging_const, qmin, qmax, symmetric);
+  return qv_check_launch("qv_obs_update");
+}
+
+extern "C" int qv_fq_apply(const float* x, int64_t n, const float* scale, const int32_t* zero_point,
+                           const int64_t* fake_quant_enabled, int32_t qmin, int32_t qmax, float* y, uint8_t* mask,
+                           void* stream) {
+  QV_REQUIRE(n >= 0 && scale && zero_point && fake_quant_enabled, QV_ERR_INVALID, "bad fq_apply arguments");
+  if (n == 0) return QV_OK;
+  QV_REQUIRE(x && y && qv_aligned16(x) && qv_aligned16(y), QV_ERR_INVALID, "x / y must be 16-byte aligned");
+  QV_REQUIRE(mask == nullptr || (reinterpret_cast<uintptr_t>(mask) & 3) == 0, QV_ERR_INVALID, "mask must be 4-byte aligned");
+  QV_REQUIRE(qv_num_sms() > 0, QV_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  qv_fq_apply_kernel<<<ew_blocks(n >> 2), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, scale, zero_point,
+                                                                                      fake_quant_enabled, qmin, qmax, y,
+                                                                                      mask);
+  return qv_check_launch("qv_fq_apply");
+}
+
+extern "C" int qv_fq_bwd(const float* gy, const uint8_t* mask, int64_t n, float* gx, void* stream) {
+  QV_REQUIRE(n >= 0, QV_ERR_INVALID, "bad fq_bwd arguments");
+  if (n == 0) return QV_OK;
+  QV_REQUIRE(gy && gx && mask && qv_aligned16(gy) && qv_aligned16(gx), QV_ERR_INVALID, "gy / gx must be 16-byte aligned");
+  QV_REQUIRE(qv_num_sms() > 0, QV_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  qv_fq_bwd_kernel<<<ew_blocks(n >> 2), 256, 0, static_cast<cudaStream_t>(stream)>>>(gy, mask, n, gx);
+  return qv_check_launch("qv_fq_bwd");
+}
+
+extern "C" int qv_fq_weight(const float* w, int64_t rows, int64_t cols, int32_t per_channel,
+                            const int64_t* observer_enabled, const int64_t* fake_quant_enabled, float* min_val,
+                            float* max_val, float* scale, int32_t* zero_point, float averaging_const, int32_t qmin,
+                            int32_t qmax, int32_t symmetric, float* y, uint8_t* mask, uint16_t* codes, uint16_t* codes_t,
+                            uint32_t* scratch, void* stream) {
+  QV_REQUIRE(w && rows > 0 && cols > 0, QV_ERR_INVALID, "bad weight shape");
+  QV_REQUIRE(observer_enabled && fake_quant_enabled && min_val && max_val && scale && zero_point, QV_ERR_INVALID,
+             "null observer state pointer");
+  QV_REQUIRE(qv_num_sms() > 0, QV_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(codes);
+  __nv_bfloat16* ct = reinterpret_cast<__nv_bfloat16*>(codes_t);
+  if (per_channel) {
+    qv_fq_weight_kernel<true><<<static_cast<unsigned>(rows), 128, 0, st>>>(w, rows, cols, observer_enabled,
+                                                                          fake_quant_enabled, min_val, max_val, scale,
+                                                                          zero_point, averaging_const, qmin, qmax,
+                                                                          symmetric, y, mask, c, ct);
+    return qv_check_launch("qv_fq_weight");
+  }
+  QV_REQUIRE(scratch != nullptr, QV_ERR_INVALID, "per-tensor weight fake-quant needs a uint32[2] scratch");
+  int rc = qv_minmax_reset(scratch, 1, stream);
+  if (rc) return rc;
+  rc = qv_minmax_accumulate(w, rows * cols, scratch, stream);
+  if (rc) return rc;
+  rc = qv_obs_update(scratch, observer_enabled, fake_quant_enabled, min_val, max_val, scale, zero_point, averaging_const,
+                     qmin, qmax, symmetric, stream);
+  if (rc) return rc;
+  qv_fq_weight_kernel<false><<<static_cast<unsigned>(rows), 128, 0, st>>>(w, rows, cols, observer_enabled,
+                                                                         fake_quant_enabled, min_val, max_val, scale,
+                                                                         zero_point, averaging_const, qmin, qmax,
+                                                                         symmetric, y, mask, c, ct);
+  return qv_check_launch("qv_fq_weight");
+}
+
+extern "C" int qv_split_planes(const float* x, int64_t n, uint16_t* hi, uint16_t* lo, void* stream) {
+  QV_REQUIRE(n >= 0, QV_ERR_INVALID, "bad split_planes arguments");
+  if (n == 0) return QV_OK;
+  QV_REQUIRE(x && hi && lo && qv_aligned16(x) && (reinterpret_cast<uintptr_t>(hi) & 7) == 0 &&
+                 (reinterpret_cast<uintptr_t>(lo) & 7) == 0,
+             QV_ERR_INVALID, "split_planes pointers must be aligned (x:16, planes:8)");
+  QV_REQUIRE(qv_num_sms() > 0, QV_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  qv_split_planes_kernel<<<ew_blocks(n >> 2), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, n, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo));
+  return qv_check_launch("qv_split_planes");
+}
