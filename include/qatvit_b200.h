@@ -82,28 +82,40 @@ int qv_kd_ce_loss(const float* s_raw, const float* t, const int64_t* labels, int
                   int32_t qmax, float* out3, float* grad, void* stream);
 
 /* ---- tcgen05 GEMM family (replaces F.linear inside torch.ao.nn.qat.Linear.forward,
- *      torch/ao/nn/qat/modules/linear.py:50-51, its autograd dgrad/wgrad, and the teacher's nn.Linear)
+ *      torch/ao/nn/qat/modules/linear.py:50-51, its autograd dgrad/wgrad, the teacher's nn.Linear, and --
+ *      batched per (image, head) -- the matmuls inside F.scaled_dot_product_attention and its backward)
  *
  * D[M,N] (fp32) = sum over `npairs` plane pairs (pa, pb) of  A[pa] * B[pb]^T , then the epilogue
  *   d = acc * (col_scale ? col_scale[n] : 1) * (alpha ? *alpha : 1) * (col_rscale ? 1/col_rscale[n] : 1)
  *       + (bias ? bias[n] : 0)
- * A, B are bf16 "plane stacks": plane p starts at base + p*plane_stride elements.  An fp32 tensor is
- * represented as hi/lo planes (x ~= hi + lo); integer codes as one exact plane.
- *   a_mn_major = 0: A plane is [M rows, K cols] (row pitch lda), K contiguous.
- *   a_mn_major = 1: A plane is [K rows, M cols] (row pitch lda), M contiguous  (wgrad: A = gy^T).
- *   same for B with N in place of M.
- * splits > 1 (split-K): partial sums go to workspace[splits][M][N] fp32 and `d` is not written; call
- * qv_splitk_reduce afterwards.  minmax (uint32[2], may be NULL): ordered min/max of the stored d
- * values are atomically merged (fused output observer, phase 1).                                  */
+ * A, B are bf16 "plane stacks": an fp32 tensor is represented as hi/lo planes (x ~= hi + lo), integer
+ * fake-quant codes as ONE exact plane.  Per operand (qv_operand):
+ *   mn_major = 0: each matrix is [rows = M (or N), cols >= K], K contiguous (row pitch ld);
+ *   mn_major = 1: each matrix is [rows = K, cols >= M (or N)], M/N contiguous (wgrad: A = gy^T);
+ *   rows/cols: extent of ONE matrix -- reads outside are zero-filled by TMA (ragged tiles, batch edges);
+ *   nb, batch_stride: number of / element distance between consecutive matrices of the tensor;
+ *   batch item bt -> (bo, bi) = (bt / batch_inner, bt % batch_inner) selects matrix bo*c2_outer + bi*c2_inner
+ *   and column offset col0 + bi*col_inner (a head's 64 columns inside a [tokens, 3*D] tensor);
+ *   plane p starts p*plane_stride elements after ptr.
+ * Output of item bt starts at d + bo*d_off_outer + bi*d_off_inner (row pitch ldd).
+ * splits > 1 (split-K, unbatched only): raw partial sums go to workspace[splits][M][N] fp32, `d` and the
+ * epilogue terms are ignored; call qv_splitk_reduce afterwards.  minmax (uint32[2], may be NULL): ordered
+ * min/max of the stored d values are atomically merged (fused output observer, phase 1).            */
+typedef struct qv_operand {
+  const void* ptr; int64_t ld; int64_t plane_stride; int32_t mn_major;
+  int64_t rows, cols;
+  int64_t nb, batch_stride;
+  int32_t c2_outer, c2_inner, col0, col_inner;
+} qv_operand;
 typedef struct qv_gemm_args {
-  const void* a; int64_t lda; int64_t a_plane_stride; int32_t a_mn_major;
-  const void* b; int64_t ldb; int64_t b_plane_stride; int32_t b_mn_major;
+  qv_operand a, b;
   int32_t npairs; int32_t pair_a[4]; int32_t pair_b[4];
   int64_t M, N, K;
   float* d; int64_t ldd;
   const float* col_scale; const float* col_rscale; const float* alpha; const float* bias;
   uint32_t* minmax;
   int32_t splits; float* workspace;
+  int32_t nbatch, batch_inner; int64_t d_off_outer, d_off_inner;
 } qv_gemm_args;
 int qv_gemm_bf16(const qv_gemm_args* args, void* stream);
 
@@ -112,6 +124,55 @@ int qv_gemm_bf16(const qv_gemm_args* args, void* stream);
  * into out (gradient arena). */
 int qv_splitk_reduce(const float* workspace, int32_t splits, int64_t M, int64_t N, const float* row_rscale,
                      const float* alpha, const uint8_t* mask, float* out, int32_t accumulate, void* stream);
+
+/* ---- row / elementwise kernels around the GEMMs (LayerNorm, residual, GELU, embeddings, attention softmax) ----
+ * They replace ATen native_layer_norm / add / gelu / softmax and their backward nodes inside the timm blocks the
+ * reference trains; the activation fake-quant of the PRODUCING Linear is applied on load from
+ * its raw output and (scale, zero_point), so the hook of torch/ao/quantization/quantize.py:150-152 costs no pass. */
+
+/* x_out = x_in + FQ(y_raw) ; h = LayerNorm(x_out)*gamma+beta.  Row r reads input row r*in_row_stride.  Any of
+ * x_in / y_raw / x_out / h_planes (bf16 [2][R][D]) / h_f32 / mean / rstd may be NULL; y_scale NULL = no fake-quant. */
+int qv_resid_ln_fwd(const float* x_in, const float* y_raw, const float* y_scale, const int32_t* y_zp, int32_t qmin,
+                    int32_t qmax, const float* gamma, const float* beta, float eps, int64_t R, int32_t D,
+                    int64_t in_row_stride, float* x_out, uint16_t* h_planes, int64_t plane_stride, float* h_f32,
+                    float* mean, float* rstd, void* stream);
+/* g_x[r*out_row_stride] = g_res[r] + LayerNormBackward(g_h, x, mean, rstd, gamma)[r]; partials: fp32
+ * [ceil(R/rows_per_block)][2][D] per-block dgamma / dbeta sums (reduce with qv_colsum_reduce). */
+int qv_ln_bwd(const float* g_h, const float* x, const float* mean, const float* rstd, const float* gamma,
+              const float* g_res, int64_t R, int32_t D, int64_t out_row_stride, float* g_x, float* partials,
+              int32_t rows_per_block, void* stream);
+int qv_colsum_reduce(const float* partials, int32_t nblk, int64_t ncols, float* out, int32_t accumulate, void* stream);
+int qv_colsum_rows(const float* x, int64_t R, int64_t N, int64_t ld, float* out, int32_t accumulate, void* stream);
+/* gp'[r,n] = g[r',n] * [gelu'(FQ(y))] * STEmask(y_raw[r,n]) * w_scale[n] -> bf16 hi/lo planes [2][R][N], plus per-block
+ * column sums of the unscaled masked gradient (bias grad partials [ceil(R/rows_per_block)][N]).
+ * remap_P/T != 0: output row b*P+i reads g row b*T+i+1 (patch-embed: drop the cls row). */
+int qv_gp_planes(const float* g, const float* y_raw, const float* y_scale, const int32_t* y_zp, int32_t qmin, int32_t qmax,
+                 const float* w_scale, int32_t w_scale_per_channel, int32_t gelu, int64_t R, int64_t N, int32_t remap_P,
+                 int32_t remap_T, uint16_t* out_planes, int64_t plane_stride, float* bias_partials, int32_t rows_per_block,
+                 void* stream);
+/* out planes = [GELU](FQ(y_raw)) elementwise (n % 4 == 0). */
+int qv_act_planes(const float* y_raw, const float* y_scale, const int32_t* y_zp, int32_t qmin, int32_t qmax, int32_t gelu,
+                  int64_t n, uint16_t* out_planes, int64_t plane_stride, void* stream);
+/* x0 = cat(cls, FQ(p_raw)) + pos  ->  [B*(P+1), D] fp32 (timm VisionTransformer._pos_embed). */
+int qv_embed_fwd(const float* p_raw, const float* p_scale, const int32_t* p_zp, int32_t qmin, int32_t qmax, const float* cls,
+                 const float* pos, int64_t B, int32_t P, int32_t D, float* x0, void* stream);
+/* im2col for the patch x patch / patch conv (nnqat.Conv2d, torch/ao/nn/qat/modules/conv.py:55-56, as a GEMM):
+ * rows = B*(HW/patch)^2 patches, cols = C*patch*patch.  With (scale, zp): the image is fake-quantised on load and
+ * out_plane holds the centred integer codes (one exact bf16 plane; out_lo_plane must be NULL).  With scale NULL
+ * (teacher): raw fp32 pixels as bf16 hi (out_plane) / lo (out_lo_plane) planes. */
+int qv_im2col_fq(const float* img, const float* scale, const int32_t* zp, int32_t qmin, int32_t qmax, int64_t B, int32_t C,
+                 int32_t HW, int32_t patch, uint16_t* out_plane, uint16_t* out_lo_plane, void* stream);
+/* P = softmax(S[:, :T] * scale) per row -> bf16 hi/lo planes (row pitch ldP, zero padded); T <= 256. */
+int qv_softmax_planes(const float* S, int64_t ldS, int64_t rows, int32_t T, float scale, uint16_t* P, int64_t ldP,
+                      int64_t plane_stride, void* stream);
+/* dS = P * (dP - rowsum(dP*P)) * scale -> bf16 hi/lo planes. */
+int qv_attn_ds(const uint16_t* P, int64_t ldP, int64_t p_plane_stride, const float* dP, int64_t lddP, int64_t rows, int32_t T,
+               float scale, uint16_t* dS, int64_t ldS, int64_t s_plane_stride, void* stream);
+/* classifier head (D -> num_classes), exact fp32: out = x wq^T + bias (+ fused output-observer min/max). */
+int qv_head_fwd(const float* x, const float* wq, const float* bias, int32_t B, int32_t K, int32_t N, float* out,
+                uint32_t* minmax, void* stream);
+int qv_head_bwd(const float* g, const float* x, const float* wq, const uint8_t* wmask, int32_t B, int32_t K, int32_t N,
+                float* gx, float* gw, float* gb, int32_t accumulate, void* stream);
 
 #ifdef __cplusplus
 }

@@ -24,17 +24,26 @@ def build(verbose: bool = False) -> str:
     return LIB_PATH
 
 
+class Operand(ctypes.Structure):
+    """struct qv_operand (include/qatvit_b200.h)."""
+    _fields_ = [
+        ("ptr", c_void_p), ("ld", c_int64), ("plane_stride", c_int64), ("mn_major", c_int32),
+        ("rows", c_int64), ("cols", c_int64), ("nb", c_int64), ("batch_stride", c_int64),
+        ("c2_outer", c_int32), ("c2_inner", c_int32), ("col0", c_int32), ("col_inner", c_int32),
+    ]
+
+
 class GemmArgs(ctypes.Structure):
     """struct qv_gemm_args (include/qatvit_b200.h)."""
     _fields_ = [
-        ("a", c_void_p), ("lda", c_int64), ("a_plane_stride", c_int64), ("a_mn_major", c_int32),
-        ("b", c_void_p), ("ldb", c_int64), ("b_plane_stride", c_int64), ("b_mn_major", c_int32),
+        ("a", Operand), ("b", Operand),
         ("npairs", c_int32), ("pair_a", c_int32 * 4), ("pair_b", c_int32 * 4),
         ("M", c_int64), ("N", c_int64), ("K", c_int64),
         ("d", c_void_p), ("ldd", c_int64),
         ("col_scale", c_void_p), ("col_rscale", c_void_p), ("alpha", c_void_p), ("bias", c_void_p),
         ("minmax", c_void_p),
         ("splits", c_int32), ("workspace", c_void_p),
+        ("nbatch", c_int32), ("batch_inner", c_int32), ("d_off_outer", c_int64), ("d_off_inner", c_int64),
     ]
 
 
@@ -56,6 +65,20 @@ _SIGNATURES = {
                               _P, _P, _P]),
     "qv_gemm_bf16": (c_int, [POINTER(GemmArgs), _P]),
     "qv_splitk_reduce": (c_int, [_P, c_int32, c_int64, c_int64, _P, _P, _P, _P, c_int32, _P]),
+    "qv_resid_ln_fwd": (c_int, [_P, _P, _P, _P, c_int32, c_int32, _P, _P, c_float, c_int64, c_int32, c_int64, _P, _P,
+                                c_int64, _P, _P, _P, _P]),
+    "qv_ln_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int32, c_int64, _P, _P, c_int32, _P]),
+    "qv_colsum_reduce": (c_int, [_P, c_int32, c_int64, _P, c_int32, _P]),
+    "qv_colsum_rows": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int32, _P]),
+    "qv_gp_planes": (c_int, [_P, _P, _P, _P, c_int32, c_int32, _P, c_int32, c_int32, c_int64, c_int64, c_int32, c_int32,
+                             _P, c_int64, _P, c_int32, _P]),
+    "qv_act_planes": (c_int, [_P, _P, _P, c_int32, c_int32, c_int32, c_int64, _P, c_int64, _P]),
+    "qv_embed_fwd": (c_int, [_P, _P, _P, c_int32, c_int32, _P, _P, c_int64, c_int32, c_int32, _P, _P]),
+    "qv_im2col_fq": (c_int, [_P, _P, _P, c_int32, c_int32, c_int64, c_int32, c_int32, c_int32, _P, _P, _P]),
+    "qv_softmax_planes": (c_int, [_P, c_int64, c_int64, c_int32, c_float, _P, c_int64, c_int64, _P]),
+    "qv_attn_ds": (c_int, [_P, c_int64, c_int64, _P, c_int64, c_int64, c_int32, c_float, _P, c_int64, c_int64, _P]),
+    "qv_head_fwd": (c_int, [_P, _P, _P, c_int32, c_int32, c_int32, _P, _P, _P]),
+    "qv_head_bwd": (c_int, [_P, _P, _P, _P, c_int32, c_int32, c_int32, _P, _P, _P, c_int32, _P]),
 }
 
 _lib = None

@@ -1,0 +1,632 @@
+// elementwise.cu -- HBM-bound row / elementwise kernels around the fake-quant GEMMs.
+//
+// The reference keeps every one of these as a separate ATen launch with fp32 tensors in between
+// (SURVEY.md §2.4 K4/K6/K9/K11/K12).  Here the activation fake-quant is applied ON LOAD by the consumer
+// (residual add, LayerNorm, GELU, attention pre-pass, loss) from the raw GEMM output and the step's
+// (scale, zero_point); the STE mask is recomputed in backward from the same raw tensor, so no mask or
+// fake-quantised copy ever goes to HBM.  Tensors that feed a tensor-core GEMM are written directly as
+// bf16 hi/lo planes.
+#include "qv_common.cuh"
+
+namespace {
+
+struct OptQ {          // optional per-tensor fake-quant applied on load
+  bool on;
+  QvQParams q;
+};
+
+__device__ __forceinline__ OptQ load_optq(const float* scale, const int32_t* zp, int qmin, int qmax) {
+  OptQ o;
+  o.on = (scale != nullptr);
+  if (o.on) o.q = qv_load_qparams(scale, zp, qmin, qmax);
+  return o;
+}
+
+__device__ __forceinline__ float gelu_fwd(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_grad(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+__device__ __forceinline__ void store_planes4(__nv_bfloat16* hi, __nv_bfloat16* lo, int64_t idx, float a, float b,
+                                              float c, float d) {
+  __nv_bfloat16 h[4], l[4];
+  qv_split_bf16(a, h[0], l[0]);
+  qv_split_bf16(b, h[1], l[1]);
+  qv_split_bf16(c, h[2], l[2]);
+  qv_split_bf16(d, h[3], l[3]);
+  *reinterpret_cast<uint2*>(hi + idx) = *reinterpret_cast<uint2*>(h);
+  *reinterpret_cast<uint2*>(lo + idx) = *reinterpret_cast<uint2*>(l);
+}
+
+// ------------------------------------------------------------------------------------------------
+// x_out = x_in + FQ(y_raw);  h = LayerNorm(x_out) -> bf16 hi/lo planes (and/or fp32);  one warp per row.
+// VPL = float4 vectors per lane (D = 128 * VPL).
+// ------------------------------------------------------------------------------------------------
+template <int VPL>
+__global__ void __launch_bounds__(256) resid_ln_fwd_kernel(const float* __restrict__ x_in, const float* __restrict__ y_raw,
+                                                           const float* y_scale, const int32_t* y_zp, int qmin, int qmax,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           float eps, int64_t R, int64_t in_row_stride,
+                                                           float* __restrict__ x_out, __nv_bfloat16* __restrict__ h_planes,
+                                                           int64_t plane_stride, float* __restrict__ h_f32,
+                                                           float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  constexpr int D = 128 * VPL;
+  const int lane = threadIdx.x & 31;
+  const int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= R) return;
+  const OptQ oq = load_optq(y_scale, y_zp, qmin, qmax);
+  const int64_t src = r * in_row_stride * D;
+  float4 v[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    float4 a = x_in ? __ldg(reinterpret_cast<const float4*>(x_in + src + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (y_raw) {
+      float4 y = __ldg(reinterpret_cast<const float4*>(y_raw + src + c));
+      if (oq.on) {
+        y.x = qv_fq(y.x, oq.q, nullptr, nullptr);
+        y.y = qv_fq(y.y, oq.q, nullptr, nullptr);
+        y.z = qv_fq(y.z, oq.q, nullptr, nullptr);
+        y.w = qv_fq(y.w, oq.q, nullptr, nullptr);
+      }
+      a.x += y.x; a.y += y.y; a.z += y.z; a.w += y.w;
+    }
+    v[i] = a;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = qv_warp_sum(s) * (1.0f / D);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    ss += (a * a + b * b) + (c * c + d * d);
+  }
+  const float var = qv_warp_sum(ss) * (1.0f / D);
+  const float rstd = rsqrtf(var + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[r] = mean;
+    if (rstd_out) rstd_out[r] = rstd;
+  }
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (x_out) *reinterpret_cast<float4*>(x_out + r * D + c) = v[i];
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+    const float o0 = (v[i].x - mean) * rstd * g.x + b.x;
+    const float o1 = (v[i].y - mean) * rstd * g.y + b.y;
+    const float o2 = (v[i].z - mean) * rstd * g.z + b.z;
+    const float o3 = (v[i].w - mean) * rstd * g.w + b.w;
+    if (h_planes) store_planes4(h_planes, h_planes + plane_stride, r * D + c, o0, o1, o2, o3);
+    if (h_f32) *reinterpret_cast<float4*>(h_f32 + r * D + c) = make_float4(o0, o1, o2, o3);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward fused with the residual-gradient add.  One warp per row, a block walks
+// `rows_per_block` rows and emits partial dgamma / dbeta column sums (deterministic two-stage reduce).
+//   g_x[r*out_row_stride] = (g_res ? g_res[r] : 0) + rstd * (gy - mean(gy) - xhat * mean(gy * xhat)),  gy = g_h * gamma
+// ------------------------------------------------------------------------------------------------
+template <int VPL>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ g_h, const float* __restrict__ x,
+                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                     const float* __restrict__ gamma, const float* __restrict__ g_res,
+                                                     int64_t R, int64_t out_row_stride, float* __restrict__ g_x,
+                                                     float* __restrict__ partials, int rows_per_block) {
+  constexpr int D = 128 * VPL;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  float4 dg[VPL], db[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) dg[i] = db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 gm[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) gm[i] = __ldg(reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 4));
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_block;
+  for (int rr = warp; rr < rows_per_block; rr += nwarps) {
+    const int64_t r = r0 + rr;
+    if (r >= R) break;
+    const float mu = __ldg(mean + r), rs = __ldg(rstd + r);
+    float4 gh[VPL], xh[VPL];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      gh[i] = __ldg(reinterpret_cast<const float4*>(g_h + r * D + c));
+      const float4 xv = __ldg(reinterpret_cast<const float4*>(x + r * D + c));
+      xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+      dg[i].x += gh[i].x * xh[i].x; dg[i].y += gh[i].y * xh[i].y; dg[i].z += gh[i].z * xh[i].z; dg[i].w += gh[i].w * xh[i].w;
+      db[i].x += gh[i].x; db[i].y += gh[i].y; db[i].z += gh[i].z; db[i].w += gh[i].w;
+      gh[i].x *= gm[i].x; gh[i].y *= gm[i].y; gh[i].z *= gm[i].z; gh[i].w *= gm[i].w;
+      s1 += (gh[i].x + gh[i].y) + (gh[i].z + gh[i].w);
+      s2 += (gh[i].x * xh[i].x + gh[i].y * xh[i].y) + (gh[i].z * xh[i].z + gh[i].w * xh[i].w);
+    }
+    s1 = qv_warp_sum(s1) * (1.0f / D);
+    s2 = qv_warp_sum(s2) * (1.0f / D);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      float4 o = make_float4(rs * (gh[i].x - s1 - xh[i].x * s2), rs * (gh[i].y - s1 - xh[i].y * s2),
+                             rs * (gh[i].z - s1 - xh[i].z * s2), rs * (gh[i].w - s1 - xh[i].w * s2));
+      if (g_res) {
+        const float4 gr = __ldg(reinterpret_cast<const float4*>(g_res + r * D + c));
+        o.x += gr.x; o.y += gr.y; o.z += gr.z; o.w += gr.w;
+      }
+      *reinterpret_cast<float4*>(g_x + r * out_row_stride * D + c) = o;
+    }
+  }
+  // block reduce of the per-warp column partials (fixed order)
+  __shared__ float4 sm[8][2][VPL * 32];
+  if (partials) {
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) { sm[warp][0][i * 32 + lane] = dg[i]; sm[warp][1][i * 32 + lane] = db[i]; }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 2 * VPL * 32; idx += blockDim.x) {
+      const int which = idx / (VPL * 32), c4 = idx % (VPL * 32);
+      float4 a = sm[0][which][c4];
+      for (int w = 1; w < nwarps; ++w) {
+        const float4 b = sm[w][which][c4];
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      *reinterpret_cast<float4*>(partials + (static_cast<int64_t>(blockIdx.x) * 2 + which) * D + c4 * 4) = a;
+    }
+  }
+}
+
+// out[c] (+)= sum_b partials[b][c]
+__global__ void colsum_reduce_kernel(const float* __restrict__ partials, int nblk, int64_t ncols, float* __restrict__ out,
+                                     int accumulate) {
+  const int64_t c = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (c >= ncols) return;
+  float s = 0.f;
+  for (int b = 0; b < nblk; ++b) s += partials[static_cast<int64_t>(b) * ncols + c];
+  out[c] = accumulate ? out[c] + s : s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward "gradient planes":  gp'[r,n] = g[r',n] * [gelu'(FQ(y))] * mask(y[r,n]) * w_scale[n]  -> bf16 hi/lo planes
+// and per-block partial column sums of the UNSCALED masked gradient (bias grad).
+// blockDim.x = N/4 threads, each owns 4 consecutive columns; a block walks rows_per_block rows.
+// Row remap (patch embed): output row r = b*P + i reads g row b*T + i + 1 (drops the cls token).
+// ------------------------------------------------------------------------------------------------
+__global__ void gp_planes_kernel(const float* __restrict__ g, const float* __restrict__ y_raw, const float* y_scale,
+                                 const int32_t* y_zp, int qmin, int qmax, const float* __restrict__ w_scale,
+                                 int w_scale_stride, int gelu, int64_t R, int64_t N, int remap_P, int remap_T,
+                                 __nv_bfloat16* __restrict__ out, int64_t plane_stride, float* __restrict__ partials,
+                                 int rows_per_block) {
+  const int64_t c = static_cast<int64_t>(threadIdx.x) * 4;
+  if (c >= N) return;
+  const OptQ oq = load_optq(y_scale, y_zp, qmin, qmax);
+  float4 ws = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (w_scale) {
+    if (w_scale_stride) ws = __ldg(reinterpret_cast<const float4*>(w_scale + c));
+    else { const float s = __ldg(w_scale); ws = make_float4(s, s, s, s); }
+  }
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_block;
+  const int64_t r1 = min(R, r0 + rows_per_block);
+  for (int64_t r = r0; r < r1; ++r) {
+    const int64_t gr = remap_P ? (r / remap_P) * remap_T + (r % remap_P) + 1 : r;
+    float4 gv = __ldg(reinterpret_cast<const float4*>(g + gr * N + c));
+    if (y_raw) {
+      const float4 yv = __ldg(reinterpret_cast<const float4*>(y_raw + r * N + c));
+      float yq[4] = {yv.x, yv.y, yv.z, yv.w};
+      float gg[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        bool in = true;
+        float v = yq[j];
+        if (oq.on) v = qv_fq(v, oq.q, &in, nullptr);
+        float f = gg[j];
+        if (gelu) f *= gelu_grad(v);
+        gg[j] = in ? f : 0.f;
+      }
+      gv = make_float4(gg[0], gg[1], gg[2], gg[3]);
+    }
+    acc.x += gv.x; acc.y += gv.y; acc.z += gv.z; acc.w += gv.w;
+    store_planes4(out, out + plane_stride, r * N + c, gv.x * ws.x, gv.y * ws.y, gv.z * ws.z, gv.w * ws.w);
+  }
+  if (partials) *reinterpret_cast<float4*>(partials + static_cast<int64_t>(blockIdx.x) * N + c) = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// out planes = [GELU]( FQ(y_raw) )   (fc1 -> fc2 operand; qkv pre-pass with gelu = 0; teacher without FQ)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) act_planes_kernel(const float* __restrict__ y_raw, const float* y_scale,
+                                                         const int32_t* y_zp, int qmin, int qmax, int gelu, int64_t n,
+                                                         __nv_bfloat16* __restrict__ out, int64_t plane_stride) {
+  const OptQ oq = load_optq(y_scale, y_zp, qmin, qmax);
+  const int64_t n4 = n >> 2;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(y_raw) + i);
+    float a[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (oq.on) a[j] = qv_fq(a[j], oq.q, nullptr, nullptr);
+      if (gelu) a[j] = gelu_fwd(a[j]);
+    }
+    store_planes4(out, out + plane_stride, i * 4, a[0], a[1], a[2], a[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// x0[b, 0, :] = cls + pos[0];  x0[b, 1+i, :] = FQ(p_raw[b*P+i, :]) + pos[1+i]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) embed_fwd_kernel(const float* __restrict__ p_raw, const float* p_scale,
+                                                        const int32_t* p_zp, int qmin, int qmax,
+                                                        const float* __restrict__ cls, const float* __restrict__ pos,
+                                                        int64_t B, int P, int D, float* __restrict__ x0) {
+  const OptQ oq = load_optq(p_scale, p_zp, qmin, qmax);
+  const int T = P + 1;
+  const int d4 = D >> 2;
+  const int64_t total = B * T * d4;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total; i += stride) {
+    const int c4 = static_cast<int>(i % d4);
+    const int64_t row = i / d4;
+    const int t = static_cast<int>(row % T);
+    const int64_t b = row / T;
+    const float4 pe = __ldg(reinterpret_cast<const float4*>(pos) + static_cast<int64_t>(t) * d4 + c4);
+    float4 v;
+    if (t == 0) {
+      v = __ldg(reinterpret_cast<const float4*>(cls) + c4);
+    } else {
+      v = __ldg(reinterpret_cast<const float4*>(p_raw) + (b * P + (t - 1)) * d4 + c4);
+      if (oq.on) {
+        v.x = qv_fq(v.x, oq.q, nullptr, nullptr);
+        v.y = qv_fq(v.y, oq.q, nullptr, nullptr);
+        v.z = qv_fq(v.z, oq.q, nullptr, nullptr);
+        v.w = qv_fq(v.w, oq.q, nullptr, nullptr);
+      }
+    }
+    reinterpret_cast<float4*>(x0)[i] = make_float4(v.x + pe.x, v.y + pe.y, v.z + pe.z, v.w + pe.w);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// im2col of the fake-quantised input image for the 16x16/16 patch-embed conv:
+//   out[b*P + py*G + px][c*ps*ps + ky*ps + kx] = bf16( clamp(rint(x*inv)+zp) - zp )   (exact integer)
+// One thread per 4 consecutive kx (float4 load along the image row, 8-byte store).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) im2col_fq_kernel(const float* __restrict__ img, const float* scale,
+                                                        const int32_t* zp, int qmin, int qmax, int64_t B, int C, int HW,
+                                                        int ps, __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_lo, int fq_on) {
+  QvQParams q;
+  if (fq_on) q = qv_load_qparams(scale, zp, qmin, qmax);
+  const int G = HW / ps;
+  const int w4 = HW >> 2;
+  const int64_t total = B * C * HW * w4;
+  const int64_t K = static_cast<int64_t>(C) * ps * ps;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total; i += stride) {
+    const int xw = static_cast<int>(i % w4) * 4;
+    int64_t rest = i / w4;
+    const int yh = static_cast<int>(rest % HW);
+    rest /= HW;
+    const int c = static_cast<int>(rest % C);
+    const int64_t b = rest / C;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(img) + i);
+    float a[4] = {v.x, v.y, v.z, v.w};
+    __nv_bfloat16 o[4], ol[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float cc = a[j];
+      if (fq_on) qv_fq(a[j], q, nullptr, &cc);
+      qv_split_bf16(cc, o[j], ol[j]);     // integer codes: lo == 0 and is not stored
+    }
+    const int py = yh / ps, ky = yh % ps, px = xw / ps, kx = xw % ps;
+    const int64_t row = b * G * G + static_cast<int64_t>(py) * G + px;
+    const int64_t col = static_cast<int64_t>(c) * ps * ps + ky * ps + kx;
+    *reinterpret_cast<uint2*>(out + row * K + col) = *reinterpret_cast<uint2*>(o);
+    if (out_lo) *reinterpret_cast<uint2*>(out_lo + row * K + col) = *reinterpret_cast<uint2*>(ol);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// softmax over the first T entries of each score row (scaled), written as bf16 hi/lo planes.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) softmax_planes_kernel(const float* __restrict__ S, int64_t ldS, int64_t rows, int T,
+                                                             float scale, __nv_bfloat16* __restrict__ P, int64_t ldP,
+                                                             int64_t plane_stride) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const float* s = S + r * ldS;
+  float v[8];                                  // T <= 256
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int j = i * 32 + lane;
+    v[i] = j < T ? __ldg(s + j) * scale : -INFINITY;
+    mx = fmaxf(mx, v[i]);
+  }
+  mx = qv_warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int j = i * 32 + lane;
+    v[i] = j < T ? expf(v[i] - mx) : 0.f;
+    sum += v[i];
+  }
+  sum = qv_warp_sum(sum);
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int j = i * 32 + lane;
+    if (j < ldP) {
+      __nv_bfloat16 h, l;
+      qv_split_bf16(j < T ? v[i] * inv : 0.f, h, l);
+      P[r * ldP + j] = h;
+      P[plane_stride + r * ldP + j] = l;
+    }
+  }
+}
+
+// dS = P * (dP - sum_j dP*P) * scale  -> planes  (softmax backward, one warp per row)
+__global__ void __launch_bounds__(256) attn_ds_kernel(const __nv_bfloat16* __restrict__ P, int64_t ldP, int64_t p_plane_stride,
+                                                      const float* __restrict__ dP, int64_t lddP, int64_t rows, int T,
+                                                      float scale, __nv_bfloat16* __restrict__ dS, int64_t ldS,
+                                                      int64_t s_plane_stride) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  float p[8], d[8];
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int j = i * 32 + lane;
+    if (j < T) {
+      p[i] = __bfloat162float(P[r * ldP + j]) + __bfloat162float(P[p_plane_stride + r * ldP + j]);
+      d[i] = __ldg(dP + r * lddP + j);
+    } else {
+      p[i] = 0.f;
+      d[i] = 0.f;
+    }
+    dot += p[i] * d[i];
+  }
+  dot = qv_warp_sum(dot);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int j = i * 32 + lane;
+    if (j < ldS) {
+      __nv_bfloat16 h, l;
+      qv_split_bf16(j < T ? p[i] * (d[i] - dot) * scale : 0.f, h, l);
+      dS[r * ldS + j] = h;
+      dS[s_plane_stride + r * ldS + j] = l;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// classifier head (384 -> 10): tiny, exact fp32 FMA.  One warp per (b, n) output.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wq,
+                                                       const float* __restrict__ bias, int B, int K, int N,
+                                                       float* __restrict__ out, uint32_t* minmax) {
+  const int lane = threadIdx.x & 31;
+  const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (o >= B * N) return;
+  const int b = o / N, n = o % N;
+  float s = 0.f;
+  for (int k = lane; k < K; k += 32) s = fmaf(x[static_cast<int64_t>(b) * K + k], wq[static_cast<int64_t>(n) * K + k], s);
+  s = qv_warp_sum(s);
+  if (lane == 0) {
+    s += bias ? bias[n] : 0.f;
+    out[o] = s;
+    if (minmax) {
+      atomicMin(minmax, qv_f2ord(s));
+      atomicMax(minmax + 1, qv_f2ord(s));
+    }
+  }
+}
+
+// gx[b,k] = sum_n g[b,n] wq[n,k];  gw[n,k] (+)= mask * sum_b g[b,n] x[b,k];  gb[n] (+)= sum_b g[b,n]
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x,
+                                                       const float* __restrict__ wq, const uint8_t* __restrict__ wmask,
+                                                       int B, int K, int N, float* __restrict__ gx, float* __restrict__ gw,
+                                                       float* __restrict__ gb, int accumulate) {
+  const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t n_gx = static_cast<int64_t>(B) * K, n_gw = static_cast<int64_t>(N) * K;
+  if (tid < n_gx) {
+    const int b = static_cast<int>(tid / K), k = static_cast<int>(tid % K);
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s = fmaf(g[b * N + n], wq[static_cast<int64_t>(n) * K + k], s);
+    gx[tid] = s;
+  } else if (tid < n_gx + n_gw) {
+    const int64_t i = tid - n_gx;
+    const int n = static_cast<int>(i / K), k = static_cast<int>(i % K);
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s = fmaf(g[b * N + n], x[static_cast<int64_t>(b) * K + k], s);
+    if (wmask && !wmask[i]) s = 0.f;
+    gw[i] = accumulate ? gw[i] + s : s;
+  } else if (tid < n_gx + n_gw + N) {
+    const int n = static_cast<int>(tid - n_gx - n_gw);
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += g[b * N + n];
+    gb[n] = accumulate ? gb[n] + s : s;
+  }
+}
+
+// out[c] (+)= sum_r x[r][c]   (thread per column; for many columns / few rows: pos_embed & cls grads)
+__global__ void __launch_bounds__(256) colsum_rows_kernel(const float* __restrict__ x, int64_t R, int64_t N, int64_t ld,
+                                                          float* __restrict__ out, int accumulate) {
+  const int64_t c = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (c >= N) return;
+  float s = 0.f;
+  for (int64_t r = 0; r < R; ++r) s += __ldg(x + r * ld + c);
+  out[c] = accumulate ? out[c] + s : s;
+}
+
+inline int ew_blocks(int64_t n_items, int per_sm = 8) {
+  const int sms = qv_num_sms();
+  int64_t b = (n_items + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(sms > 0 ? sms : 1) * per_sm;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+}  // namespace
+
+#define QV_NEED_GPU() QV_REQUIRE(qv_num_sms() > 0, QV_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)")
+
+extern "C" int qv_resid_ln_fwd(const float* x_in, const float* y_raw, const float* y_scale, const int32_t* y_zp,
+                               int32_t qmin, int32_t qmax, const float* gamma, const float* beta, float eps, int64_t R,
+                               int32_t D, int64_t in_row_stride, float* x_out, uint16_t* h_planes, int64_t plane_stride,
+                               float* h_f32, float* mean, float* rstd, void* stream) {
+  QV_REQUIRE((x_in || y_raw) && gamma && beta && R > 0, QV_ERR_INVALID, "bad resid_ln_fwd arguments");
+  QV_REQUIRE(D % 128 == 0 && D >= 128 && D <= 1024, QV_ERR_UNSUPPORTED, "LayerNorm width must be a multiple of 128 <= 1024 (got %d)", D);
+  QV_REQUIRE((y_scale == nullptr) == (y_zp == nullptr), QV_ERR_INVALID, "y_scale and y_zp go together");
+  QV_NEED_GPU();
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int rows_per_block = 8;
+  const unsigned grid = static_cast<unsigned>((R + rows_per_block - 1) / rows_per_block);
+  __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(h_planes);
+  if (in_row_stride < 1) in_row_stride = 1;
+#define LAUNCH(V)                                                                                                        \
+  resid_ln_fwd_kernel<V><<<grid, 256, 0, st>>>(x_in, y_raw, y_scale, y_zp, qmin, qmax, gamma, beta, eps, R, in_row_stride, \
+                                               x_out, hp, plane_stride, h_f32, mean, rstd)
+  switch (D / 128) {
+    case 1: LAUNCH(1); break;
+    case 2: LAUNCH(2); break;
+    case 3: LAUNCH(3); break;
+    case 4: LAUNCH(4); break;
+    case 6: LAUNCH(6); break;
+    case 8: LAUNCH(8); break;
+    default: return qv_set_error(QV_ERR_UNSUPPORTED, "LayerNorm width %d not instantiated", D);
+  }
+#undef LAUNCH
+  return qv_check_launch("qv_resid_ln_fwd");
+}
+
+extern "C" int qv_ln_bwd(const float* g_h, const float* x, const float* mean, const float* rstd, const float* gamma,
+                         const float* g_res, int64_t R, int32_t D, int64_t out_row_stride, float* g_x, float* partials,
+                         int32_t rows_per_block, void* stream) {
+  QV_REQUIRE(g_h && x && mean && rstd && gamma && g_x && R > 0 && rows_per_block > 0, QV_ERR_INVALID, "bad ln_bwd arguments");
+  QV_REQUIRE(D % 128 == 0 && D >= 128 && D <= 1024, QV_ERR_UNSUPPORTED, "LayerNorm width must be a multiple of 128 <= 1024 (got %d)", D);
+  QV_NEED_GPU();
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned grid = static_cast<unsigned>((R + rows_per_block - 1) / rows_per_block);
+  if (out_row_stride < 1) out_row_stride = 1;
+#define LAUNCH(V) ln_bwd_kernel<V><<<grid, 256, 0, st>>>(g_h, x, mean, rstd, gamma, g_res, R, out_row_stride, g_x, partials, rows_per_block)
+  switch (D / 128) {
+    case 1: LAUNCH(1); break;
+    case 2: LAUNCH(2); break;
+    case 3: LAUNCH(3); break;
+    case 4: LAUNCH(4); break;
+    case 6: LAUNCH(6); break;
+    default: return qv_set_error(QV_ERR_UNSUPPORTED, "LayerNorm backward width %d not instantiated", D);
+  }
+#undef LAUNCH
+  return qv_check_launch("qv_ln_bwd");
+}
+
+extern "C" int qv_colsum_reduce(const float* partials, int32_t nblk, int64_t ncols, float* out, int32_t accumulate,
+                                void* stream) {
+  QV_REQUIRE(partials && out && nblk > 0 && ncols > 0, QV_ERR_INVALID, "bad colsum_reduce arguments");
+  QV_NEED_GPU();
+  colsum_reduce_kernel<<<static_cast<unsigned>((ncols + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      partials, nblk, ncols, out, accumulate);
+  return qv_check_launch("qv_colsum_reduce");
+}
+
+extern "C" int qv_colsum_rows(const float* x, int64_t R, int64_t N, int64_t ld, float* out, int32_t accumulate,
+                              void* stream) {
+  QV_REQUIRE(x && out && R > 0 && N > 0 && ld >= N, QV_ERR_INVALID, "bad colsum_rows arguments");
+  QV_NEED_GPU();
+  colsum_rows_kernel<<<static_cast<unsigned>((N + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, R, N, ld,
+                                                                                                           out, accumulate);
+  return qv_check_launch("qv_colsum_rows");
+}
+
+extern "C" int qv_gp_planes(const float* g, const float* y_raw, const float* y_scale, const int32_t* y_zp, int32_t qmin,
+                            int32_t qmax, const float* w_scale, int32_t w_scale_per_channel, int32_t gelu, int64_t R,
+                            int64_t N, int32_t remap_P, int32_t remap_T, uint16_t* out_planes, int64_t plane_stride,
+                            float* bias_partials, int32_t rows_per_block, void* stream) {
+  QV_REQUIRE(g && out_planes && R > 0 && N > 0 && rows_per_block > 0, QV_ERR_INVALID, "bad gp_planes arguments");
+  QV_REQUIRE(N % 4 == 0 && N / 4 <= 1024, QV_ERR_UNSUPPORTED, "gp_planes needs N %% 4 == 0 and N <= 4096 (got %lld)", (long long)N);
+  QV_REQUIRE((y_scale == nullptr) == (y_zp == nullptr), QV_ERR_INVALID, "y_scale and y_zp go together");
+  QV_NEED_GPU();
+  const unsigned grid = static_cast<unsigned>((R + rows_per_block - 1) / rows_per_block);
+  const unsigned threads = static_cast<unsigned>(((N / 4) + 31) / 32 * 32);
+  gp_planes_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      g, y_raw, y_scale, y_zp, qmin, qmax, w_scale, w_scale_per_channel, gelu, R, N, remap_P, remap_T,
+      reinterpret_cast<__nv_bfloat16*>(out_planes), plane_stride, bias_partials, rows_per_block);
+  return qv_check_launch("qv_gp_planes");
+}
+
+extern "C" int qv_act_planes(const float* y_raw, const float* y_scale, const int32_t* y_zp, int32_t qmin, int32_t qmax,
+                             int32_t gelu, int64_t n, uint16_t* out_planes, int64_t plane_stride, void* stream) {
+  QV_REQUIRE(y_raw && out_planes && n > 0 && n % 4 == 0, QV_ERR_INVALID, "bad act_planes arguments (n must be a multiple of 4)");
+  QV_REQUIRE((y_scale == nullptr) == (y_zp == nullptr), QV_ERR_INVALID, "y_scale and y_zp go together");
+  QV_NEED_GPU();
+  act_planes_kernel<<<ew_blocks(n >> 2), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      y_raw, y_scale, y_zp, qmin, qmax, gelu, n, reinterpret_cast<__nv_bfloat16*>(out_planes), plane_stride);
+  return qv_check_launch("qv_act_planes");
+}
+
+extern "C" int qv_embed_fwd(const float* p_raw, const float* p_scale, const int32_t* p_zp, int32_t qmin, int32_t qmax,
+                            const float* cls, const float* pos, int64_t B, int32_t P, int32_t D, float* x0, void* stream) {
+  QV_REQUIRE(p_raw && cls && pos && x0 && B > 0 && P > 0 && D > 0 && D % 4 == 0, QV_ERR_INVALID, "bad embed_fwd arguments");
+  QV_REQUIRE((p_scale == nullptr) == (p_zp == nullptr), QV_ERR_INVALID, "p_scale and p_zp go together");
+  QV_NEED_GPU();
+  embed_fwd_kernel<<<ew_blocks(B * (P + 1) * (D / 4)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      p_raw, p_scale, p_zp, qmin, qmax, cls, pos, B, P, D, x0);
+  return qv_check_launch("qv_embed_fwd");
+}
+
+extern "C" int qv_im2col_fq(const float* img, const float* scale, const int32_t* zp, int32_t qmin, int32_t qmax, int64_t B,
+                            int32_t C, int32_t HW, int32_t patch, uint16_t* out_plane, uint16_t* out_lo_plane, void* stream) {
+  QV_REQUIRE(img && out_plane && B > 0 && C > 0 && HW > 0 && patch > 0, QV_ERR_INVALID, "bad im2col arguments");
+  QV_REQUIRE(HW % patch == 0 && patch % 4 == 0, QV_ERR_UNSUPPORTED, "im2col needs HW %% patch == 0 and patch %% 4 == 0");
+  QV_REQUIRE((scale == nullptr) == (zp == nullptr), QV_ERR_INVALID, "scale and zp go together");
+  QV_NEED_GPU();
+  const int64_t total = B * C * HW * (HW / 4);
+  im2col_fq_kernel<<<ew_blocks(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      img, scale, zp, qmin, qmax, B, C, HW, patch, reinterpret_cast<__nv_bfloat16*>(out_plane),
+      reinterpret_cast<__nv_bfloat16*>(out_lo_plane), scale != nullptr);
+  return qv_check_launch("qv_im2col_fq");
+}
+
+extern "C" int qv_softmax_planes(const float* S, int64_t ldS, int64_t rows, int32_t T, float scale, uint16_t* P, int64_t ldP,
+                                 int64_t plane_stride, void* stream) {
+  QV_REQUIRE(S && P && rows > 0 && T > 0 && T <= 256 && ldP >= T && ldP <= 256 && ldS >= T, QV_ERR_INVALID,
+             "bad softmax_planes arguments (T <= 256)");
+  QV_NEED_GPU();
+  softmax_planes_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      S, ldS, rows, T, scale, reinterpret_cast<__nv_bfloat16*>(P), ldP, plane_stride);
+  return qv_check_launch("qv_softmax_planes");
+}
+
+extern "C" int qv_attn_ds(const uint16_t* P, int64_t ldP, int64_t p_plane_stride, const float* dP, int64_t lddP, int64_t rows,
+                          int32_t T, float scale, uint16_t* dS, int64_t ldS, int64_t s_plane_stride, void* stream) {
+  QV_REQUIRE(P && dP && dS && rows > 0 && T > 0 && T <= 256 && ldS <= 256 && ldS >= T && ldP >= T && lddP >= T, QV_ERR_INVALID,
+             "bad attn_ds arguments (T <= 256)");
+  QV_NEED_GPU();
+  attn_ds_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(P), ldP, p_plane_stride, dP, lddP, rows, T, scale,
+      reinterpret_cast<__nv_bfloat16*>(dS), ldS, s_plane_stride);
+  return qv_check_launch("qv_attn_ds");
+}
+
+extern "C" int qv_head_fwd(const float* x, const float* wq, const float* bias, int32_t B, int32_t K, int32_t N, float* out,
+                           uint32_t* minmax, void* stream) {
+  QV_REQUIRE(x && wq && out && B > 0 && K > 0 && N > 0, QV_ERR_INVALID, "bad head_fwd arguments");
+  QV_NEED_GPU();
+  head_fwd_kernel<<<(B * N + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, wq, bias, B, K, N, out, minmax);
+  return qv_check_launch("qv_head_fwd");
+}
+
+extern "C" int qv_head_bwd(const float* g, const float* x, const float* wq, const uint8_t* wmask, int32_t B, int32_t K,
+                           int32_t N, float* gx, float* gw, float* gb, int32_t accumulate, void* stream) {
+  QV_REQUIRE(g && x && wq && gx && gw && gb && B > 0 && K > 0 && N > 0, QV_ERR_INVALID, "bad head_bwd arguments");
+  QV_NEED_GPU();
+  const int64_t total = static_cast<int64_t>(B) * K + static_cast<int64_t>(N) * K + N;
+  head_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      g, x, wq, wmask, B, K, N, gx, gw, gb, accumulate);
+  return qv_check_launch("qv_head_bwd");
+}

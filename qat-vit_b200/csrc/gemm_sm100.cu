@@ -46,6 +46,11 @@ struct GemmKParams {
   const float* bias;
   uint32_t* minmax;
   float* workspace;
+  // batching: item -> (outer index bt) -> (bo, bi) = (bt / batch_inner, bt % batch_inner)
+  int32_t nbatch, batch_inner;
+  int32_t a_c2_outer, a_c2_inner, a_col0, a_col_inner;
+  int32_t b_c2_outer, b_c2_inner, b_col0, b_col_inner;
+  int64_t d_off_outer, d_off_inner;
 };
 
 template <int BN>
@@ -96,7 +101,7 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_items = p.tiles_m * p.tiles_n * p.splits;
+  const int num_items = p.tiles_m * p.tiles_n * (p.nbatch > 1 ? p.nbatch : p.splits);
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
@@ -106,7 +111,12 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         const int n_blk = item % p.tiles_n;
         const int m_blk = (item / p.tiles_n) % p.tiles_m;
-        const int z = item / (p.tiles_n * p.tiles_m);
+        const int outer = item / (p.tiles_n * p.tiles_m);
+        const int z = p.nbatch > 1 ? 0 : outer;
+        const int bt = p.nbatch > 1 ? outer : 0;
+        const int bo = bt / p.batch_inner, bi = bt % p.batch_inner;
+        const int a_c2 = bo * p.a_c2_outer + bi * p.a_c2_inner, a_col = p.a_col0 + bi * p.a_col_inner;
+        const int b_c2 = bo * p.b_c2_outer + bi * p.b_c2_inner, b_col = p.b_col0 + bi * p.b_col_inner;
         const int kb0 = z * p.kb_per_split;
         const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
         for (int pr = 0; pr < p.npairs; ++pr) {
@@ -117,18 +127,18 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
             uint8_t* sb = smem_b + stage * C::B_STAGE_BYTES;
             if (!A_MN) {
-              tma_load_3d(sa, &map_a, &full_bar[stage], kb * BK, m_blk * BM, pa);
+              tma_load_4d(sa, &map_a, &full_bar[stage], a_col + kb * BK, m_blk * BM, a_c2, pa);
             } else {
 #pragma unroll
               for (int j = 0; j < BM / 64; ++j)
-                tma_load_3d(sa + j * 8192, &map_a, &full_bar[stage], m_blk * BM + j * 64, kb * BK, pa);
+                tma_load_4d(sa + j * 8192, &map_a, &full_bar[stage], a_col + m_blk * BM + j * 64, kb * BK, a_c2, pa);
             }
             if (!B_MN) {
-              tma_load_3d(sb, &map_b, &full_bar[stage], kb * BK, n_blk * BN, pb);
+              tma_load_4d(sb, &map_b, &full_bar[stage], b_col + kb * BK, n_blk * BN, b_c2, pb);
             } else {
 #pragma unroll
               for (int j = 0; j < BN / 64; ++j)
-                tma_load_3d(sb + j * 8192, &map_b, &full_bar[stage], n_blk * BN + j * 64, kb * BK, pb);
+                tma_load_4d(sb + j * 8192, &map_b, &full_bar[stage], b_col + n_blk * BN + j * 64, kb * BK, b_c2, pb);
             }
             if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
           }
@@ -146,7 +156,7 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       uint32_t phase = 0;
       int local = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
-        const int z = item / (p.tiles_n * p.tiles_m);
+        const int z = p.nbatch > 1 ? 0 : item / (p.tiles_n * p.tiles_m);
         const int kb0 = z * p.kb_per_split;
         const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
         const int iters = p.npairs * (kb1 - kb0);
@@ -184,7 +194,9 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
       const int n_blk = item % p.tiles_n;
       const int m_blk = (item / p.tiles_n) % p.tiles_m;
-      const int z = item / (p.tiles_n * p.tiles_m);
+      const int outer = item / (p.tiles_n * p.tiles_m);
+      const int z = p.nbatch > 1 ? 0 : outer;
+      const int bt = p.nbatch > 1 ? outer : 0;
       const int buf = local & 1;
       const uint32_t use = static_cast<uint32_t>(local >> 1);
       mbar_wait(&tmem_full[buf], use & 1);
@@ -197,7 +209,7 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         out = p.workspace + static_cast<int64_t>(z) * p.M * p.N;
         ldo = p.N;
       } else {
-        out = p.d;
+        out = p.d + (bt / p.batch_inner) * p.d_off_outer + (bt % p.batch_inner) * p.d_off_inner;
         ldo = p.ldd;
       }
 #pragma unroll 1
@@ -298,20 +310,26 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-// bf16 plane stack [planes][rows][ld] viewed as a 3-D tensor (cols, rows, planes); box = (64, box_rows, 1)
-int make_map(CUtensorMap* m, const void* base, int64_t cols, int64_t rows, int64_t ld, int planes,
-             int64_t plane_stride, int box_rows) {
+// bf16 plane stack [planes][nb][rows][ld] viewed as a 4-D tensor (cols, rows, nb, planes); box = (64, box_rows, 1, 1).
+// Out-of-range rows / cols (per batch matrix) are zero-filled by TMA, which is what makes ragged M/N/K and
+// per-(image, head) batching safe in the contraction dimension.
+int make_map(CUtensorMap* m, const qv_operand& op, int planes, int box_rows) {
   EncodeTiledFn enc = get_encode();
   QV_REQUIRE(enc != nullptr, QV_ERR_CUDA, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
-  QV_REQUIRE(qv_aligned16(base), QV_ERR_INVALID, "gemm operand base must be 16-byte aligned");
-  QV_REQUIRE(ld % 8 == 0, QV_ERR_INVALID, "gemm operand row pitch must be a multiple of 8 bf16 (got %lld)", (long long)ld);
-  if (planes > 1) QV_REQUIRE(plane_stride % 8 == 0, QV_ERR_INVALID, "plane stride must be a multiple of 8 bf16");
-  if (plane_stride <= 0) plane_stride = rows * ld;
-  cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(planes)};
-  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(plane_stride) * 2};
-  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+  QV_REQUIRE(op.ptr && qv_aligned16(op.ptr), QV_ERR_INVALID, "gemm operand base must be a 16-byte aligned device pointer");
+  QV_REQUIRE(op.rows > 0 && op.cols > 0, QV_ERR_INVALID, "gemm operand extent must be positive");
+  QV_REQUIRE(op.ld % 8 == 0 && op.ld >= op.cols, QV_ERR_INVALID, "gemm operand row pitch must be >= cols and a multiple of 8 bf16 (got %lld)", (long long)op.ld);
+  int64_t nb = op.nb > 0 ? op.nb : 1;
+  int64_t bstride = op.batch_stride > 0 ? op.batch_stride : op.rows * op.ld;
+  int64_t pstride = op.plane_stride > 0 ? op.plane_stride : bstride * nb;
+  QV_REQUIRE(bstride % 8 == 0 && pstride % 8 == 0, QV_ERR_INVALID, "batch / plane strides must be multiples of 8 bf16");
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(op.cols), static_cast<cuuint64_t>(op.rows), static_cast<cuuint64_t>(nb),
+                        static_cast<cuuint64_t>(planes)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(op.ld) * 2, static_cast<cuuint64_t>(bstride) * 2,
+                           static_cast<cuuint64_t>(pstride) * 2};
+  cuuint32_t box[4] = {64, static_cast<cuuint32_t>(box_rows), 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(op.ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   QV_REQUIRE(r == CUDA_SUCCESS, QV_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -339,8 +357,9 @@ extern "C" int qv_gemm_bf16(const qv_gemm_args* a, void* stream) {
   QV_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, QV_ERR_INVALID, "empty gemm (M=%lld N=%lld K=%lld)", (long long)a->M,
              (long long)a->N, (long long)a->K);
   QV_REQUIRE(a->npairs >= 1 && a->npairs <= 4, QV_ERR_INVALID, "npairs must be 1..4");
-  QV_REQUIRE(a->a && a->b, QV_ERR_INVALID, "null operand");
   const int splits = a->splits > 1 ? a->splits : 1;
+  const int nbatch = a->nbatch > 1 ? a->nbatch : 1;
+  QV_REQUIRE(!(splits > 1 && nbatch > 1), QV_ERR_UNSUPPORTED, "split-K and batching are mutually exclusive");
   if (splits > 1) QV_REQUIRE(a->workspace != nullptr, QV_ERR_INVALID, "split-K needs a workspace");
   else QV_REQUIRE(a->d != nullptr, QV_ERR_INVALID, "null output");
   int pa_max = 0, pb_max = 0;
@@ -350,14 +369,12 @@ extern "C" int qv_gemm_bf16(const qv_gemm_args* a, void* stream) {
     pa_max = a->pair_a[i] > pa_max ? a->pair_a[i] : pa_max;
     pb_max = a->pair_b[i] > pb_max ? a->pair_b[i] : pb_max;
   }
+  QV_REQUIRE(qv_num_sms() > 0, QV_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
   const int BN = 128;
   CUtensorMap ma, mb;
-  int rc;
-  if (!a->a_mn_major) rc = make_map(&ma, a->a, a->K, a->M, a->lda, pa_max + 1, a->a_plane_stride, BM);
-  else rc = make_map(&ma, a->a, a->M, a->K, a->lda, pa_max + 1, a->a_plane_stride, 64);
+  int rc = make_map(&ma, a->a, pa_max + 1, a->a.mn_major ? 64 : BM);
   if (rc) return rc;
-  if (!a->b_mn_major) rc = make_map(&mb, a->b, a->K, a->N, a->ldb, pb_max + 1, a->b_plane_stride, BN);
-  else rc = make_map(&mb, a->b, a->N, a->K, a->ldb, pb_max + 1, a->b_plane_stride, 64);
+  rc = make_map(&mb, a->b, pb_max + 1, a->b.mn_major ? 64 : BN);
   if (rc) return rc;
 
   GemmKParams kp;
@@ -383,14 +400,21 @@ extern "C" int qv_gemm_bf16(const qv_gemm_args* a, void* stream) {
   kp.bias = a->bias;
   kp.minmax = a->minmax;
   kp.workspace = a->workspace;
-  const int64_t items = static_cast<int64_t>(kp.tiles_m) * kp.tiles_n * kp.splits;
+  kp.nbatch = nbatch;
+  kp.batch_inner = a->batch_inner > 0 ? a->batch_inner : 1;
+  kp.a_c2_outer = a->a.c2_outer; kp.a_c2_inner = a->a.c2_inner; kp.a_col0 = a->a.col0; kp.a_col_inner = a->a.col_inner;
+  kp.b_c2_outer = a->b.c2_outer; kp.b_c2_inner = a->b.c2_inner; kp.b_col0 = a->b.col0; kp.b_col_inner = a->b.col_inner;
+  kp.d_off_outer = a->d_off_outer;
+  kp.d_off_inner = a->d_off_inner;
+  const int64_t items = static_cast<int64_t>(kp.tiles_m) * kp.tiles_n * (nbatch > 1 ? nbatch : kp.splits);
+  QV_REQUIRE(items < (1LL << 31), QV_ERR_UNSUPPORTED, "too many tiles");
   const int sms = qv_num_sms();
-  QV_REQUIRE(sms > 0, QV_ERR_CUDA, "no CUDA device");
   const int grid = static_cast<int>(items < sms ? items : sms);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (!a->a_mn_major && !a->b_mn_major) return launch<128, false, false>(ma, mb, kp, grid, st);
-  if (a->a_mn_major && a->b_mn_major) return launch<128, true, true>(ma, mb, kp, grid, st);
-  if (a->a_mn_major && !a->b_mn_major) return launch<128, true, false>(ma, mb, kp, grid, st);
+  const bool amn = a->a.mn_major != 0, bmn = a->b.mn_major != 0;
+  if (!amn && !bmn) return launch<128, false, false>(ma, mb, kp, grid, st);
+  if (amn && bmn) return launch<128, true, true>(ma, mb, kp, grid, st);
+  if (amn && !bmn) return launch<128, true, false>(ma, mb, kp, grid, st);
   return launch<128, false, true>(ma, mb, kp, grid, st);
 }
 

@@ -1,0 +1,529 @@
+"""Fused QAT-distillation step executor (the hot path of bdina9/qat-vit on B200).
+
+Replaces, for one training iteration, everything between ``images.to(device)`` and ``optimizer.step()`` in
+ref/src/training/qat_trainer.py:337-361:
+
+    teacher(images)  (no_grad)                      -> TeacherEngine.forward
+    ddp_model(images)  [QATWrapper -> prepared ViT] -> StudentEngine.forward
+    KL + CE loss                                    -> qv_kd_ce_loss (inside StudentEngine.forward)
+    loss.backward()                                 -> StudentEngine.backward  (hand-written backward, no autograd)
+
+The module tree is NOT modified: parameters stay the torch Parameters of the prepared ``QATWrapper`` (their
+``.grad`` become views into one flat gradient arena), observer state stays in the buffers of the
+``FusedMovingAvgObsFakeQuantize`` modules ``prepare_qat`` created, so ``state_dict()`` (best_qat.pth),
+``convert()`` (best_converted.pth), DDP-style gradient all-reduce and the torch optimizer keep working unchanged.
+
+All arithmetic runs in the sm_100a kernels behind the C-ABI (``ops``); this file only sequences launches on
+the current CUDA stream (it is CUDA-graph capturable: no host sync, no allocation after construction).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .ops import Op, PAIRS_EXACT_B, PAIRS_FP32, PAIRS_SINGLE
+
+_INF = float("inf")
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class FQRef:
+    """The buffers of one FusedMovingAvgObsFakeQuantize module (SURVEY.md §8b 'state ownership')."""
+
+    def __init__(self, mod: nn.Module, channels: Optional[int] = None):
+        from torch.ao.quantization.fake_quantize import FusedMovingAvgObsFakeQuantize
+        if not isinstance(mod, FusedMovingAvgObsFakeQuantize):
+            raise TypeError(f"expected FusedMovingAvgObsFakeQuantize, got {type(mod)}")
+        obs = mod.activation_post_process
+        self.mod = mod
+        self.qmin, self.qmax = int(obs.quant_min), int(obs.quant_max)
+        self.symmetric = bool(mod.is_symmetric_quant)
+        self.per_channel = bool(mod.is_per_channel)
+        self.c = float(obs.averaging_constant)
+        if self.per_channel:
+            if channels is None:
+                raise ValueError("per-channel fake-quant needs the channel count")
+            if obs.min_val.numel() != channels:     # what the ATen op does on its first call
+                obs.min_val.resize_(channels).fill_(_INF)
+                obs.max_val.resize_(channels).fill_(-_INF)
+                mod.scale.resize_(channels).fill_(1.0)
+                mod.zero_point.resize_(channels).fill_(0)
+        self.min_val, self.max_val = obs.min_val, obs.max_val
+        self.scale, self.zero_point = mod.scale, mod.zero_point
+        self.observer_enabled, self.fake_quant_enabled = mod.observer_enabled, mod.fake_quant_enabled
+        for t in (self.min_val, self.max_val, self.scale, self.zero_point, self.observer_enabled, self.fake_quant_enabled):
+            if not t.is_cuda:
+                raise RuntimeError("qatvit_b200: move the prepared model to the GPU before building the engine")
+
+    @property
+    def q(self):
+        """(scale, zero_point, qmin, qmax) for kernels that fake-quantise on load."""
+        return (self.scale, self.zero_point, self.qmin, self.qmax)
+
+    def update_from(self, acc: torch.Tensor) -> None:
+        ops.obs_update(acc, self.observer_enabled, self.fake_quant_enabled, self.min_val, self.max_val, self.scale,
+                       self.zero_point, self.c, self.qmin, self.qmax, self.symmetric)
+
+
+class _QLinear:
+    """One fake-quant Linear / Conv2d-as-GEMM of the student: parameters, observer state, per-step derived operands."""
+
+    def __init__(self, mod: nn.Module, dev, acc: torch.Tensor, small: bool = False):
+        self.mod = mod
+        self.weight, self.bias = mod.weight, mod.bias
+        self.N = mod.weight.shape[0]
+        self.K = mod.weight.numel() // self.N
+        self.wfq = FQRef(mod.weight_fake_quant, channels=self.N)
+        self.afq = FQRef(mod.activation_post_process)
+        if self.afq.per_channel:
+            raise NotImplementedError("per-channel activation fake-quant is not part of the reference path")
+        self.acc = acc                                    # uint32[2] slot of the output observer
+        self.small = small
+        self.wmask = torch.empty(self.N, self.K, dtype=torch.uint8, device=dev)
+        if small:
+            self.wq = torch.empty(self.N, self.K, dtype=torch.float32, device=dev)
+        else:
+            self.codes = torch.empty(1, self.N, self.K, dtype=torch.bfloat16, device=dev)
+            self.codes_t = torch.empty(1, self.K, self.N, dtype=torch.bfloat16, device=dev)
+        self.scratch = torch.zeros(2, dtype=torch.int32, device=dev)
+        # per-output-channel scale vector for the GEMM epilogues (aliases the module buffer when per-channel)
+        self.wscale_vec = self.wfq.scale if self.wfq.per_channel else torch.ones(self.N, device=dev)
+
+    def quantize_weight(self) -> None:
+        f = self.wfq
+        w = self.weight.detach()
+        if self.small:
+            ops.fq_weight(w, f.per_channel, f.observer_enabled, f.fake_quant_enabled, f.min_val, f.max_val, f.scale,
+                          f.zero_point, f.c, f.qmin, f.qmax, f.symmetric, y=self.wq, mask=self.wmask, scratch=self.scratch)
+        else:
+            ops.fq_weight(w, f.per_channel, f.observer_enabled, f.fake_quant_enabled, f.min_val, f.max_val, f.scale,
+                          f.zero_point, f.c, f.qmin, f.qmax, f.symmetric, mask=self.wmask, codes=self.codes[0],
+                          codes_t=self.codes_t[0], scratch=self.scratch)
+        if not f.per_channel:
+            self.wscale_vec.copy_(f.scale.expand(self.N))
+
+
+def _splits_for(tiles: int, kblocks: int, sms: int) -> int:
+    s = max(1, min(kblocks, 32, -(-2 * sms // max(tiles, 1))))
+    kbp = -(-kblocks // s)
+    return -(-kblocks // kbp)
+
+
+class _ViTDims:
+    def __init__(self, vit: nn.Module, batch: int):
+        pe = vit.patch_embed
+        self.B = batch
+        self.D = vit.embed_dim
+        self.L = len(vit.blocks)
+        self.H = vit.blocks[0].attn.num_heads
+        self.hd = self.D // self.H
+        if self.hd != 64:
+            raise NotImplementedError("attention kernels are specialised for head_dim 64 (timm ViT-S/B)")
+        self.F = vit.blocks[0].mlp.fc1.weight.shape[0]
+        self.C = vit.head.weight.shape[0]
+        self.ps = pe.proj.kernel_size[0]
+        self.in_ch = pe.proj.in_channels
+        self.HW = pe.img_size[0] if hasattr(pe, "img_size") else None
+        self.P = pe.num_patches
+        self.T = self.P + 1
+        self.M = batch * self.T
+        self.Kc = self.in_ch * self.ps * self.ps
+        self.ldS = _round_up(self.T, 4)
+        self.ldP = _round_up(self.T, 8)
+        if self.T > 256:
+            raise NotImplementedError("softmax kernels support at most 256 tokens")
+        self.eps = float(vit.blocks[0].norm1.eps)
+        self.attn_scale = float(vit.blocks[0].attn.scale)
+
+
+def _attention_forward(d: _ViTDims, qkvp: torch.Tensor, S: torch.Tensor, Pp: torch.Tensor, o: torch.Tensor) -> None:
+    """softmax(Q K^T / 8) V per (image, head) as two batched tcgen05 GEMMs + one row-softmax kernel
+    (replaces F.scaled_dot_product_attention in timm Attention.forward)."""
+    B, H, T, D = d.B, d.H, d.T, d.D
+    BH = B * H
+    q_op = Op.tokens(qkvp, B, T, 0, 64)
+    k_op = Op.tokens(qkvp, B, T, D, 64)
+    ops.gemm(q_op, k_op, T, T, 64, PAIRS_FP32, out=S, ldd=d.ldS, nbatch=BH, batch_inner=H,
+             d_off_outer=H * T * d.ldS, d_off_inner=T * d.ldS)
+    ops.softmax_planes(S, d.ldS, BH * T, T, d.attn_scale, Pp)
+    p_op = Op.per_head(Pp, BH, H, T, T)
+    v_op = Op.tokens(qkvp, B, T, 2 * D, 64, mn_major=True)
+    ops.gemm(p_op, v_op, T, 64, T, PAIRS_FP32, out=o, ldd=D, nbatch=BH, batch_inner=H, d_off_outer=T * D, d_off_inner=64)
+
+
+class TeacherEngine:
+    """Frozen fp32 ViT forward (ref qat_trainer.py:337-338) on the tcgen05 GEMMs: weights and activations as bf16
+    hi/lo planes, three MMAs per product (hi*hi + hi*lo + lo*hi), fp32 accumulation."""
+
+    def __init__(self, vit: nn.Module, batch: int):
+        self.vit = vit
+        dev = next(vit.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("qatvit_b200: the teacher must live on a CUDA device (there is no CPU fallback)")
+        self.dev = dev
+        d = self.d = _ViTDims(vit, batch)
+        M, D, F = d.M, d.D, d.F
+        bf, f32 = torch.bfloat16, torch.float32
+
+        def planes_of(w: torch.Tensor) -> torch.Tensor:
+            w2 = w.detach().reshape(w.shape[0], -1).contiguous()
+            return ops.split_planes(w2)
+
+        self.w_conv = planes_of(vit.patch_embed.proj.weight)
+        self.blocks = []
+        for blk in vit.blocks:
+            self.blocks.append(dict(
+                n1=(blk.norm1.weight.detach(), blk.norm1.bias.detach()), n2=(blk.norm2.weight.detach(), blk.norm2.bias.detach()),
+                qkv=(planes_of(blk.attn.qkv.weight), blk.attn.qkv.bias.detach()),
+                proj=(planes_of(blk.attn.proj.weight), blk.attn.proj.bias.detach()),
+                fc1=(planes_of(blk.mlp.fc1.weight), blk.mlp.fc1.bias.detach()),
+                fc2=(planes_of(blk.mlp.fc2.weight), blk.mlp.fc2.bias.detach())))
+        e = lambda *s, dt=f32: torch.empty(*s, dtype=dt, device=dev)  # noqa: E731
+        self.img_planes = e(2, d.B * d.P, d.Kc, dt=bf)
+        self.p_raw = e(d.B * d.P, D)
+        self.x = [e(M, D), e(M, D)]
+        self.hp = e(2, M, D, dt=bf)
+        self.qkv_raw = e(M, 3 * D)
+        self.qkvp = e(2, M, 3 * D, dt=bf)
+        self.S = e(d.B * d.H * d.T, d.ldS)
+        self.Pp = torch.zeros(2, d.B * d.H * d.T, d.ldP, dtype=bf, device=dev)
+        self.o = e(M, D)
+        self.op = e(2, M, D, dt=bf)
+        self.y = e(M, D)
+        self.f_raw = e(M, F)
+        self.fp = e(2, M, F, dt=bf)
+        self.xn = e(d.B, D)
+        self.logits = e(d.B, d.C)
+
+    @torch.no_grad()
+    def forward(self, images: torch.Tensor) -> torch.Tensor:
+        d, v = self.d, self.vit
+        B, T, D, F, M = d.B, d.T, d.D, d.F, d.M
+        if tuple(images.shape) != (B, d.in_ch, d.HW, d.HW):
+            raise RuntimeError(f"teacher engine built for batch {B}, got {tuple(images.shape)}")
+        ops.im2col_fq(images, None, B, d.in_ch, d.HW, d.ps, self.img_planes)
+        ops.gemm(Op.full(self.img_planes), Op.full(self.w_conv), B * d.P, D, d.Kc, PAIRS_FP32, out=self.p_raw,
+                 bias=v.patch_embed.proj.bias.detach())
+        ops.embed_fwd(self.p_raw, None, v.cls_token.detach().reshape(-1), v.pos_embed.detach().reshape(T, D), B, d.P, D,
+                      self.x[0])
+        cur = 0
+        x_in, y_prev = self.x[0], None
+        for li, blk in enumerate(self.blocks):
+            g, b = blk["n1"]
+            if li == 0:
+                ops.resid_ln_fwd(x_in, None, None, g, b, d.eps, M, D, h_planes=self.hp)
+            else:
+                ops.resid_ln_fwd(x_in, y_prev, None, g, b, d.eps, M, D, x_out=self.x[cur ^ 1], h_planes=self.hp)
+                cur ^= 1
+                x_in = self.x[cur]
+            w, bias = blk["qkv"]
+            ops.gemm(Op.full(self.hp), Op.full(w), M, 3 * D, D, PAIRS_FP32, out=self.qkv_raw, bias=bias)
+            ops.act_planes(self.qkv_raw, None, False, self.qkvp)
+            _attention_forward(d, self.qkvp, self.S, self.Pp, self.o)
+            ops.split_planes(self.o, self.op)
+            w, bias = blk["proj"]
+            ops.gemm(Op.full(self.op), Op.full(w), M, D, D, PAIRS_FP32, out=self.y, bias=bias)
+            g, b = blk["n2"]
+            ops.resid_ln_fwd(x_in, self.y, None, g, b, d.eps, M, D, x_out=self.x[cur ^ 1], h_planes=self.hp)
+            cur ^= 1
+            x_in = self.x[cur]
+            w, bias = blk["fc1"]
+            ops.gemm(Op.full(self.hp), Op.full(w), M, F, D, PAIRS_FP32, out=self.f_raw, bias=bias)
+            ops.act_planes(self.f_raw, None, True, self.fp)
+            w, bias = blk["fc2"]
+            ops.gemm(Op.full(self.fp), Op.full(w), M, D, F, PAIRS_FP32, out=self.y, bias=bias)
+            y_prev = self.y
+        ops.resid_ln_fwd(x_in, y_prev, None, v.norm.weight.detach(), v.norm.bias.detach(), d.eps, B, D, in_row_stride=T,
+                         h_f32=self.xn)
+        ops.head_fwd(self.xn, v.head.weight.detach(), v.head.bias.detach(), B, D, d.C, self.logits)
+        return self.logits
+
+
+class StudentEngine:
+    """Forward + hand-written backward of the prepared (torch.ao eager-mode QAT) ``QATWrapper`` student."""
+
+    def __init__(self, student: nn.Module, batch: int, hparams: Dict):
+        self.student = student
+        vit = self.vit = student.model
+        dev = next(student.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("qatvit_b200: the student must live on a CUDA device (there is no CPU fallback)")
+        self.dev = dev
+        self.hp_ = dict(hparams)
+        d = self.d = _ViTDims(vit, batch)
+        for blk in vit.blocks:
+            if hasattr(blk.norm1, "activation_post_process") or hasattr(vit.norm, "activation_post_process"):
+                raise NotImplementedError(
+                    "observed LayerNorm (plain nn.LayerNorm, 126 fake-quant modules) is not on the fused path yet; "
+                    "use the timm.layers.LayerNorm variant (SURVEY.md §0.6)")
+        self.sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        L, M, D, F, B, T = d.L, d.M, d.D, d.F, d.B, d.T
+        bf, f32 = torch.bfloat16, torch.float32
+        e = lambda *s, dt=f32: torch.empty(*s, dtype=dt, device=dev)  # noqa: E731
+
+        # ---- observer slots: input, conv out, 4 per block, head ----
+        n_act = 2 + 4 * L + 1
+        self.acc = torch.empty(n_act, 2, dtype=torch.int32, device=dev)
+        self.fq_in = FQRef(student.quant.activation_post_process)
+        self.conv = _QLinear(vit.patch_embed.proj, dev, self.acc[1])
+        self.lin: List[Dict[str, _QLinear]] = []
+        for i, blk in enumerate(vit.blocks):
+            base = 2 + 4 * i
+            self.lin.append(dict(qkv=_QLinear(blk.attn.qkv, dev, self.acc[base]), proj=_QLinear(blk.attn.proj, dev, self.acc[base + 1]),
+                                 fc1=_QLinear(blk.mlp.fc1, dev, self.acc[base + 2]), fc2=_QLinear(blk.mlp.fc2, dev, self.acc[base + 3])))
+        self.head = _QLinear(vit.head, dev, self.acc[n_act - 1], small=True)
+        self.all_linears = [self.conv] + [q for blk in self.lin for q in blk.values()] + [self.head]
+
+        # ---- flat gradient arena (the buffer a DDP-style all-reduce runs over) ----
+        self.params = [p for p in student.parameters() if p.requires_grad]
+        total = sum(p.numel() for p in self.params)
+        self.grad_arena = torch.zeros(total, dtype=f32, device=dev)
+        self._grad_views = []
+        off = 0
+        self._goff = {}
+        for p in self.params:
+            self._grad_views.append(self.grad_arena[off:off + p.numel()].view_as(p))
+            self._goff[id(p)] = off
+            off += p.numel()
+        self.attach_grads()
+
+        # ---- forward activations (saved for backward) ----
+        self.img_codes = e(1, B * d.P, d.Kc, dt=bf)
+        self.p_raw = e(B * d.P, D)
+        self.x_in = [e(M, D) for _ in range(L)]
+        self.x_mid = [e(M, D) for _ in range(L)]
+        self.h1p = [e(2, M, D, dt=bf) for _ in range(L)]
+        self.h2p = [e(2, M, D, dt=bf) for _ in range(L)]
+        self.qkv_raw = [e(M, 3 * D) for _ in range(L)]
+        self.qkvp = [e(2, M, 3 * D, dt=bf) for _ in range(L)]
+        self.Pp = [torch.zeros(2, B * d.H * T, d.ldP, dtype=bf, device=dev) for _ in range(L)]
+        self.op = [e(2, M, D, dt=bf) for _ in range(L)]
+        self.a_raw = [e(M, D) for _ in range(L)]
+        self.f_raw = [e(M, F) for _ in range(L)]
+        self.gelp = [e(2, M, F, dt=bf) for _ in range(L)]
+        self.m_raw = [e(M, D) for _ in range(L)]
+        self.stats1 = [(e(M), e(M)) for _ in range(L)]
+        self.stats2 = [(e(M), e(M)) for _ in range(L)]
+        self.S = e(B * d.H * T, d.ldS)
+        self.o = e(M, D)
+        self.xcls = e(B, D)
+        self.xn = e(B, D)
+        self.statsF = (e(B), e(B))
+        self.logits_raw = e(B, d.C)
+        self.loss3 = e(3)
+        self.g_logits = e(B, d.C)
+
+        # ---- backward scratch ----
+        self.gx = [e(M, D), e(M, D)]
+        self.g_xn = e(B, D)
+        self.gpD = e(2, M, D, dt=bf)
+        self.gpF = e(2, M, F, dt=bf)
+        self.gp3 = e(2, M, 3 * D, dt=bf)
+        self.gpP = e(2, B * d.P, D, dt=bf)
+        self.g_big = e(M, F)
+        self.g_h = e(M, D)
+        self.g_o = e(M, D)
+        self.g_op = e(2, M, D, dt=bf)
+        self.g_qkv = e(M, 3 * D)
+        self.dP = e(B * d.H * T, d.ldS)
+        self.dSp = torch.zeros(2, B * d.H * T, d.ldP, dtype=bf, device=dev)
+        self.rpb_gp = 32
+        self.rpb_ln = 64
+        self.bias_part = e(-(-M // self.rpb_gp), max(F, 3 * D))
+        self.ln_part = e(-(-M // self.rpb_ln), 2, D)
+        max_ws = 0
+        self._splits = {}
+        for (n, k, kdim) in [(3 * D, D, M), (D, D, M), (F, D, M), (D, F, M), (D, d.Kc, B * d.P)]:
+            tiles = (-(-n // 128)) * (-(-k // 128))
+            s = _splits_for(tiles, -(-kdim // 64), self.sms)
+            self._splits[(n, k)] = s
+            max_ws = max(max_ws, s * n * k)
+        self.ws = e(max_ws)
+
+    # ------------------------------------------------------------------------------------------
+    def attach_grads(self) -> None:
+        """(Re)point every parameter's .grad at its slice of the arena (optimizer.zero_grad(set_to_none) drops them)."""
+        for p, g in zip(self.params, self._grad_views):
+            p.grad = g
+
+    def _grad(self, p: torch.Tensor) -> torch.Tensor:
+        off = self._goff[id(p)]
+        return self.grad_arena[off:off + p.numel()]
+
+    def _ln_param_grads(self, norm: nn.Module, nblk: int) -> None:
+        D = self.d.D
+        gw, gb = self._goff[id(norm.weight)], self._goff[id(norm.bias)]
+        if gb == gw + D:
+            ops.colsum_reduce(self.ln_part, nblk, 2 * D, self.grad_arena[gw:gw + 2 * D])
+        else:  # not adjacent in the arena: reduce into scratch, then copy
+            tmp = torch.empty(2 * D, device=self.dev)
+            ops.colsum_reduce(self.ln_part, nblk, 2 * D, tmp)
+            self._grad(norm.weight).copy_(tmp[:D])
+            self._grad(norm.bias).copy_(tmp[D:])
+
+    # ------------------------------------------------------------------------------------------
+    def _linear_fwd(self, ql: _QLinear, a_planes: torch.Tensor, M: int, out: torch.Tensor, pairs=PAIRS_EXACT_B, alpha=None):
+        """y_raw = x @ (codes*scale)^T + b with the output observer's min/max fused in the epilogue, then EMA + qparams."""
+        ops.gemm(Op.full(a_planes), Op.full(ql.codes), M, ql.N, ql.K, pairs, out=out, col_scale=ql.wscale_vec, alpha=alpha,
+                 bias=ql.bias.detach(), minmax=ql.acc)
+        ql.afq.update_from(ql.acc)
+
+    def forward(self, images: torch.Tensor, labels: torch.Tensor, teacher_logits: torch.Tensor) -> torch.Tensor:
+        d, v = self.d, self.vit
+        B, T, D, F, M, L = d.B, d.T, d.D, d.F, d.M, d.L
+        if tuple(images.shape) != (B, d.in_ch, d.HW, d.HW):
+            raise RuntimeError(f"student engine built for batch {B}, got {tuple(images.shape)}")
+        ops.minmax_reset(self.acc)
+        for ql in self.all_linears:
+            ql.quantize_weight()
+        # input fake-quant (QuantStub hook) fused into im2col; patch-embed conv as an exact-integer GEMM
+        ops.minmax_accumulate(images, self.acc[0])
+        self.fq_in.update_from(self.acc[0])
+        ops.im2col_fq(images, self.fq_in.q, B, d.in_ch, d.HW, d.ps, self.img_codes)
+        self._linear_fwd(self.conv, self.img_codes, B * d.P, self.p_raw, pairs=PAIRS_SINGLE, alpha=self.fq_in.scale)
+        ops.embed_fwd(self.p_raw, self.conv.afq.q, v.cls_token.detach().reshape(-1), v.pos_embed.detach().reshape(T, D), B,
+                      d.P, D, self.x_in[0])
+        for l, blk in enumerate(v.blocks):
+            ql = self.lin[l]
+            if l == 0:
+                ops.resid_ln_fwd(self.x_in[0], None, None, blk.norm1.weight.detach(), blk.norm1.bias.detach(), d.eps, M, D,
+                                 h_planes=self.h1p[0], mean=self.stats1[0][0], rstd=self.stats1[0][1])
+            self._linear_fwd(ql["qkv"], self.h1p[l], M, self.qkv_raw[l])
+            ops.act_planes(self.qkv_raw[l], ql["qkv"].afq.q, False, self.qkvp[l])
+            _attention_forward(d, self.qkvp[l], self.S, self.Pp[l], self.o)
+            ops.split_planes(self.o, self.op[l])
+            self._linear_fwd(ql["proj"], self.op[l], M, self.a_raw[l])
+            ops.resid_ln_fwd(self.x_in[l], self.a_raw[l], ql["proj"].afq.q, blk.norm2.weight.detach(), blk.norm2.bias.detach(),
+                             d.eps, M, D, x_out=self.x_mid[l], h_planes=self.h2p[l], mean=self.stats2[l][0],
+                             rstd=self.stats2[l][1])
+            self._linear_fwd(ql["fc1"], self.h2p[l], M, self.f_raw[l])
+            ops.act_planes(self.f_raw[l], ql["fc1"].afq.q, True, self.gelp[l])
+            self._linear_fwd(ql["fc2"], self.gelp[l], M, self.m_raw[l])
+            if l + 1 < L:
+                nb = v.blocks[l + 1]
+                ops.resid_ln_fwd(self.x_mid[l], self.m_raw[l], ql["fc2"].afq.q, nb.norm1.weight.detach(), nb.norm1.bias.detach(),
+                                 d.eps, M, D, x_out=self.x_in[l + 1], h_planes=self.h1p[l + 1], mean=self.stats1[l + 1][0],
+                                 rstd=self.stats1[l + 1][1])
+            else:   # final norm: only the cls rows reach the head
+                ops.resid_ln_fwd(self.x_mid[l], self.m_raw[l], ql["fc2"].afq.q, v.norm.weight.detach(), v.norm.bias.detach(),
+                                 d.eps, B, D, in_row_stride=T, x_out=self.xcls, h_f32=self.xn, mean=self.statsF[0],
+                                 rstd=self.statsF[1])
+        hd = self.head
+        ops.head_fwd(self.xn, hd.wq, hd.bias.detach(), B, D, d.C, self.logits_raw, minmax=hd.acc)
+        hd.afq.update_from(hd.acc)
+        hp = self.hp_
+        check_grad = self.g_logits
+        out3, _ = _kd_ce(self.logits_raw, teacher_logits, labels, hp, hd.afq, self.loss3, check_grad)
+        return out3
+
+    # ------------------------------------------------------------------------------------------
+    def _wgrad(self, ql: _QLinear, gp: torch.Tensor, x_planes: torch.Tensor, kdim: int, pairs, alpha=None) -> None:
+        """weight.grad[N,K] = mask * (gp'^T @ x) / scale[n]  (split-K over the token dimension, deterministic reduce)."""
+        s = self._splits[(ql.N, ql.K)]
+        ops.gemm(Op.full(gp, mn_major=True), Op.full(x_planes, mn_major=True), ql.N, ql.K, kdim, pairs, splits=s,
+                 workspace=self.ws)
+        ops.splitk_reduce(self.ws, s, ql.N, ql.K, self._grad(ql.weight), row_rscale=ql.wscale_vec, alpha=alpha, mask=ql.wmask)
+
+    def _dgrad(self, ql: _QLinear, gp: torch.Tensor, M: int, out: torch.Tensor) -> None:
+        ops.gemm(Op.full(gp), Op.full(ql.codes_t), M, ql.K, ql.N, PAIRS_EXACT_B, out=out)
+
+    def _gp(self, g, y_raw, ql: _QLinear, gelu: bool, R: int, out_planes, remap=(0, 0)) -> None:
+        nblk = -(-R // self.rpb_gp)
+        part = self.bias_part.view(-1)[:nblk * ql.N].view(nblk, ql.N)
+        ops.gp_planes(g, y_raw, ql.afq.q, ql.wscale_vec, True, gelu, R, ql.N, out_planes, part, self.rpb_gp, remap[0], remap[1])
+        ops.colsum_reduce(part, nblk, ql.N, self._grad(ql.bias))
+
+    def backward(self) -> None:
+        d, v = self.d, self.vit
+        B, T, D, F, M, L, H = d.B, d.T, d.D, d.F, d.M, d.L, d.H
+        BH = B * H
+        hd = self.head
+        ops.head_bwd(self.g_logits, self.xn, hd.wq, hd.wmask, B, D, d.C, self.g_xn, self._grad(hd.weight), self._grad(hd.bias))
+        gx, gx2 = self.gx
+        gx.zero_()
+        nblk_ln = -(-B // self.rpb_ln)
+        ops.ln_bwd(self.g_xn, self.xcls, self.statsF[0], self.statsF[1], v.norm.weight.detach(), None, B, D, gx, self.ln_part,
+                   self.rpb_ln, out_row_stride=T)
+        self._ln_param_grads(v.norm, nblk_ln)
+        nblk_ln = -(-M // self.rpb_ln)
+        for l in range(L - 1, -1, -1):
+            blk, ql = v.blocks[l], self.lin[l]
+            # ---- MLP ----
+            self._gp(gx, self.m_raw[l], ql["fc2"], False, M, self.gpD)
+            self._dgrad(ql["fc2"], self.gpD, M, self.g_big)
+            self._wgrad(ql["fc2"], self.gpD, self.gelp[l], M, PAIRS_FP32)
+            self._gp(self.g_big, self.f_raw[l], ql["fc1"], True, M, self.gpF)
+            self._dgrad(ql["fc1"], self.gpF, M, self.g_h)
+            self._wgrad(ql["fc1"], self.gpF, self.h2p[l], M, PAIRS_FP32)
+            ops.ln_bwd(self.g_h, self.x_mid[l], self.stats2[l][0], self.stats2[l][1], blk.norm2.weight.detach(), gx, M, D, gx2,
+                       self.ln_part, self.rpb_ln)
+            self._ln_param_grads(blk.norm2, nblk_ln)
+            # ---- attention ----
+            self._gp(gx2, self.a_raw[l], ql["proj"], False, M, self.gpD)
+            self._dgrad(ql["proj"], self.gpD, M, self.g_o)
+            self._wgrad(ql["proj"], self.gpD, self.op[l], M, PAIRS_FP32)
+            ops.split_planes(self.g_o, self.g_op)
+            qkvp, Pp = self.qkvp[l], self.Pp[l]
+            # dP = dO V^T
+            ops.gemm(Op.tokens(self.g_op, B, T, 0, 64), Op.tokens(qkvp, B, T, 2 * D, 64), T, T, 64, PAIRS_FP32, out=self.dP,
+                     ldd=d.ldS, nbatch=BH, batch_inner=H, d_off_outer=H * T * d.ldS, d_off_inner=T * d.ldS)
+            ops.attn_ds(Pp, self.dP, d.ldS, BH * T, T, d.attn_scale, self.dSp)
+            # dQ = dS K ; dK = dS^T Q ; dV = P^T dO   -> column blocks of g_qkv
+            ops.gemm(Op.per_head(self.dSp, BH, H, T, T), Op.tokens(qkvp, B, T, D, 64, mn_major=True), T, 64, T, PAIRS_FP32,
+                     out=self.g_qkv, ldd=3 * D, nbatch=BH, batch_inner=H, d_off_outer=T * 3 * D, d_off_inner=64)
+            ops.gemm(Op.per_head(self.dSp, BH, H, T, T, mn_major=True), Op.tokens(qkvp, B, T, 0, 64, mn_major=True), T, 64, T,
+                     PAIRS_FP32, out=self.g_qkv[:, D:], ldd=3 * D, nbatch=BH, batch_inner=H, d_off_outer=T * 3 * D,
+                     d_off_inner=64)
+            ops.gemm(Op.per_head(Pp, BH, H, T, T, mn_major=True), Op.tokens(self.g_op, B, T, 0, 64, mn_major=True), T, 64, T,
+                     PAIRS_FP32, out=self.g_qkv[:, 2 * D:], ldd=3 * D, nbatch=BH, batch_inner=H, d_off_outer=T * 3 * D,
+                     d_off_inner=64)
+            self._gp(self.g_qkv, self.qkv_raw[l], ql["qkv"], False, M, self.gp3)
+            self._dgrad(ql["qkv"], self.gp3, M, self.g_h)
+            self._wgrad(ql["qkv"], self.gp3, self.h1p[l], M, PAIRS_FP32)
+            ops.ln_bwd(self.g_h, self.x_in[l], self.stats1[l][0], self.stats1[l][1], blk.norm1.weight.detach(), gx2, M, D, gx,
+                       self.ln_part, self.rpb_ln)
+            self._ln_param_grads(blk.norm1, nblk_ln)
+        # ---- embeddings: pos_embed, cls_token, patch-embed conv ----
+        ops.colsum_rows(gx, B, T * D, T * D, self._grad(v.pos_embed))
+        ops.colsum_rows(gx, B, D, T * D, self._grad(v.cls_token))
+        self._gp(gx, self.p_raw, self.conv, False, B * d.P, self.gpP, remap=(d.P, T))
+        self._wgrad(self.conv, self.gpP, self.img_codes, B * d.P, PAIRS_EXACT_B, alpha=self.fq_in.scale)
+
+
+def _kd_ce(logits_raw, teacher_logits, labels, hp, afq: FQRef, out3, grad):
+    from . import _lib
+    import ctypes
+    B, C = logits_raw.shape
+    _lib.check(_lib.lib().qv_kd_ce_loss(
+        ops._p(logits_raw, torch.float32), ops._p(teacher_logits, torch.float32), ops._p(labels, torch.int64), B, C,
+        float(hp["kd_temp"]), float(hp["kd_alpha"]), float(hp["label_smoothing"]), ops._p(afq.scale, torch.float32),
+        ops._p(afq.zero_point, torch.int32), afq.qmin, afq.qmax, ops._p(out3, torch.float32), ops._p(grad, torch.float32),
+        ops._stream()), "kd_ce_loss")
+    return out3, grad
+
+
+class QATDistillStep:
+    """One object per (student, teacher, batch size): ``loss = step(images, labels)`` runs teacher forward, student
+    forward, loss and backward on the current stream and leaves gradients in ``student`` parameters' ``.grad``."""
+
+    def __init__(self, student: nn.Module, teacher: nn.Module, batch: int, hparams: Dict):
+        self.student_engine = StudentEngine(student, batch, hparams)
+        self.teacher_engine = TeacherEngine(teacher, batch)
+        self.grad_arena = self.student_engine.grad_arena
+
+    def __call__(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        t_logits = self.teacher_engine.forward(images)
+        out3 = self.student_engine.forward(images, labels, t_logits)
+        self.student_engine.backward()
+        return out3
+
+    @property
+    def student_logits_raw(self) -> torch.Tensor:
+        return self.student_engine.logits_raw

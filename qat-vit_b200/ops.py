@@ -112,20 +112,64 @@ def kd_ce_loss(s_raw, t, labels, T, alpha, eps, s_scale=None, s_zp=None, qmin=0,
     return out3, grad
 
 
-def gemm(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, pairs: Sequence[Tuple[int, int]], *,
-         a_mn_major: bool = False, b_mn_major: bool = False, out: Optional[torch.Tensor] = None,
-         col_scale=None, col_rscale=None, alpha=None, bias=None, minmax=None, splits: int = 1,
-         workspace: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
-    """D[M,N] = sum_pairs A[pa] @ B[pb]^T on tcgen05.  a, b: bf16 plane stacks [planes, rows, ld]."""
-    if a.dim() != 3 or b.dim() != 3:
-        raise RuntimeError("gemm operands must be [planes, rows, cols] bf16 plane stacks")
+class Op:
+    """One GEMM operand: a bf16 plane stack plus how batch items map onto it (struct qv_operand)."""
+    __slots__ = ("t", "ptr", "ld", "plane_stride", "mn_major", "rows", "cols", "nb", "batch_stride", "c2_outer",
+                 "c2_inner", "col0", "col_inner")
+
+    def __init__(self, t: torch.Tensor, rows: int, cols: int, ld: int, plane_stride: int, mn_major: bool = False,
+                 nb: int = 1, batch_stride: int = 0, c2_outer: int = 0, c2_inner: int = 0, col0: int = 0,
+                 col_inner: int = 0):
+        if t.dtype != torch.bfloat16 or not t.is_cuda:
+            raise RuntimeError("qatvit_b200: GEMM operands must be CUDA bf16 plane stacks (no CPU fallback)")
+        self.t = t
+        self.ptr = t.data_ptr()
+        self.rows, self.cols, self.ld, self.plane_stride = rows, cols, ld, plane_stride
+        self.mn_major = mn_major
+        self.nb, self.batch_stride = nb, batch_stride
+        self.c2_outer, self.c2_inner, self.col0, self.col_inner = c2_outer, c2_inner, col0, col_inner
+
+    @staticmethod
+    def full(t: torch.Tensor, mn_major: bool = False) -> "Op":
+        """t: [planes, rows, cols] -- one unbatched matrix per plane."""
+        assert t.dim() == 3 and t.stride(2) == 1
+        return Op(t, t.shape[1], t.shape[2], t.stride(1), t.stride(0), mn_major)
+
+    @staticmethod
+    def tokens(t: torch.Tensor, B: int, T: int, col0: int, col_inner: int, mn_major: bool = False) -> "Op":
+        """t: [planes, B*T, W] token tensor; batch item (b, h) = rows of image b, columns col0 + h*col_inner."""
+        assert t.dim() == 3 and t.stride(2) == 1 and t.shape[1] == B * T
+        W = t.shape[2]
+        return Op(t, T, W, t.stride(1), t.stride(0), mn_major, nb=B, batch_stride=T * t.stride(1), c2_outer=1,
+                  c2_inner=0, col0=col0, col_inner=col_inner)
+
+    @staticmethod
+    def per_head(t: torch.Tensor, BH: int, H: int, T: int, cols: int, mn_major: bool = False) -> "Op":
+        """t: [planes, B*H*T, ld] -- one [T, cols] matrix per (image, head)."""
+        assert t.dim() == 3 and t.stride(2) == 1 and t.shape[1] == BH * T
+        return Op(t, T, cols, t.stride(1), t.stride(0), mn_major, nb=BH, batch_stride=T * t.stride(1), c2_outer=H,
+                  c2_inner=1)
+
+    def fill(self, o: "_lib.Operand") -> None:
+        o.ptr = self.ptr
+        o.ld, o.plane_stride, o.mn_major = self.ld, self.plane_stride, int(self.mn_major)
+        o.rows, o.cols, o.nb, o.batch_stride = self.rows, self.cols, self.nb, self.batch_stride
+        o.c2_outer, o.c2_inner, o.col0, o.col_inner = self.c2_outer, self.c2_inner, self.col0, self.col_inner
+
+
+PAIRS_EXACT_B = ((0, 0), (1, 0))            # A = fp32 as hi/lo, B = exact integer codes
+PAIRS_FP32 = ((0, 0), (0, 1), (1, 0))       # both operands fp32 as hi/lo (drops lo*lo, ~2^-16 relative)
+PAIRS_SINGLE = ((0, 0),)
+
+
+def gemm(a: Op, b: Op, M: int, N: int, K: int, pairs: Sequence[Tuple[int, int]], *, out: Optional[torch.Tensor] = None,
+         ldd: Optional[int] = None, col_scale=None, col_rscale=None, alpha=None, bias=None, minmax=None,
+         splits: int = 1, workspace: Optional[torch.Tensor] = None, nbatch: int = 1, batch_inner: int = 1,
+         d_off_outer: int = 0, d_off_inner: int = 0) -> Optional[torch.Tensor]:
+    """D[M,N] = sum_pairs A[pa] @ B[pb]^T on tcgen05 (include/qatvit_b200.h: qv_gemm_bf16)."""
     args = GemmArgs()
-    args.a = a.data_ptr(); args.lda = a.stride(1); args.a_plane_stride = a.stride(0); args.a_mn_major = int(a_mn_major)
-    args.b = b.data_ptr(); args.ldb = b.stride(1); args.b_plane_stride = b.stride(0); args.b_mn_major = int(b_mn_major)
-    if a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16 or not a.is_cuda or not b.is_cuda:
-        raise RuntimeError("gemm operands must be CUDA bf16")
-    if a.stride(2) != 1 or b.stride(2) != 1:
-        raise RuntimeError("gemm operand inner stride must be 1")
+    a.fill(args.a)
+    b.fill(args.b)
     args.npairs = len(pairs)
     for i, (pa, pb) in enumerate(pairs):
         args.pair_a[i] = pa
@@ -133,11 +177,14 @@ def gemm(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, pairs: Sequen
     args.M, args.N, args.K = M, N, K
     if splits <= 1:
         if out is None:
-            out = torch.empty(M, N, dtype=torch.float32, device=a.device)
-        args.d = out.data_ptr(); args.ldd = out.stride(0)
+            out = torch.empty(M, N, dtype=torch.float32, device=a.t.device)
+        if out.dtype != torch.float32 or not out.is_cuda:
+            raise RuntimeError("qatvit_b200: GEMM output must be CUDA fp32")
+        args.d = out.data_ptr()
+        args.ldd = ldd if ldd is not None else out.stride(-2)
     else:
         if workspace is None:
-            workspace = torch.empty(splits, M, N, dtype=torch.float32, device=a.device)
+            workspace = torch.empty(splits, M, N, dtype=torch.float32, device=a.t.device)
         args.workspace = workspace.data_ptr()
     args.col_scale = None if col_scale is None else col_scale.data_ptr()
     args.col_rscale = None if col_rscale is None else col_rscale.data_ptr()
@@ -145,6 +192,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, pairs: Sequen
     args.bias = None if bias is None else bias.data_ptr()
     args.minmax = None if minmax is None else minmax.data_ptr()
     args.splits = splits
+    args.nbatch, args.batch_inner = nbatch, batch_inner
+    args.d_off_outer, args.d_off_inner = d_off_outer, d_off_inner
     check(_lib.lib().qv_gemm_bf16(ctypes.byref(args), _stream()), "gemm_bf16")
     return out if splits <= 1 else workspace
 
@@ -158,3 +207,86 @@ def splitk_reduce(workspace, splits, M, N, out, row_rscale=None, alpha=None, mas
 
 def launch_count() -> int:
     return int(_lib.lib().qv_launch_count())
+
+
+def resid_ln_fwd(x_in, y_raw, fq, gamma, beta, eps, R, D, *, in_row_stride=1, x_out=None, h_planes=None, h_f32=None,
+                 mean=None, rstd=None):
+    """x_out = x_in + FQ(y_raw); h = LN(x_out).  fq = (scale, zero_point, qmin, qmax) or None."""
+    sc, zp, qmin, qmax = fq if fq is not None else (None, None, 0, 0)
+    check(_lib.lib().qv_resid_ln_fwd(_p(x_in, torch.float32), _p(y_raw, torch.float32), _p(sc, torch.float32),
+                                     _p(zp, torch.int32), qmin, qmax, _p(gamma, torch.float32), _p(beta, torch.float32),
+                                     float(eps), R, D, in_row_stride, _p(x_out, torch.float32),
+                                     _p(h_planes, torch.bfloat16), 0 if h_planes is None else h_planes.stride(0),
+                                     _p(h_f32, torch.float32), _p(mean, torch.float32), _p(rstd, torch.float32),
+                                     _stream()), "resid_ln_fwd")
+
+
+def ln_bwd(g_h, x, mean, rstd, gamma, g_res, R, D, g_x, partials, rows_per_block, out_row_stride=1):
+    check(_lib.lib().qv_ln_bwd(_p(g_h, torch.float32), _p(x, torch.float32), _p(mean, torch.float32),
+                               _p(rstd, torch.float32), _p(gamma, torch.float32), _p(g_res, torch.float32), R, D,
+                               out_row_stride, _p(g_x, torch.float32), _p(partials, torch.float32), rows_per_block,
+                               _stream()), "ln_bwd")
+
+
+def colsum_reduce(partials, nblk, ncols, out, accumulate=False):
+    check(_lib.lib().qv_colsum_reduce(_p(partials, torch.float32), nblk, ncols, _p(out, torch.float32),
+                                      int(bool(accumulate)), _stream()), "colsum_reduce")
+
+
+def colsum_rows(x, R, N, ld, out, accumulate=False):
+    check(_lib.lib().qv_colsum_rows(_p(x, torch.float32), R, N, ld, _p(out, torch.float32), int(bool(accumulate)),
+                                    _stream()), "colsum_rows")
+
+
+def gp_planes(g, y_raw, fq, w_scale, per_channel, gelu, R, N, out_planes, bias_partials, rows_per_block, remap_P=0,
+              remap_T=0):
+    sc, zp, qmin, qmax = fq if fq is not None else (None, None, 0, 0)
+    check(_lib.lib().qv_gp_planes(_p(g, torch.float32), _p(y_raw, torch.float32), _p(sc, torch.float32),
+                                  _p(zp, torch.int32), qmin, qmax, _p(w_scale, torch.float32), int(bool(per_channel)),
+                                  int(bool(gelu)), R, N, remap_P, remap_T, _p(out_planes, torch.bfloat16),
+                                  out_planes.stride(0), _p(bias_partials, torch.float32), rows_per_block, _stream()),
+          "gp_planes")
+
+
+def act_planes(y_raw, fq, gelu, out_planes):
+    sc, zp, qmin, qmax = fq if fq is not None else (None, None, 0, 0)
+    check(_lib.lib().qv_act_planes(_p(y_raw, torch.float32), _p(sc, torch.float32), _p(zp, torch.int32), qmin, qmax,
+                                   int(bool(gelu)), y_raw.numel(), _p(out_planes, torch.bfloat16), out_planes.stride(0),
+                                   _stream()), "act_planes")
+
+
+def embed_fwd(p_raw, fq, cls, pos, B, P, D, x0):
+    sc, zp, qmin, qmax = fq if fq is not None else (None, None, 0, 0)
+    check(_lib.lib().qv_embed_fwd(_p(p_raw, torch.float32), _p(sc, torch.float32), _p(zp, torch.int32), qmin, qmax,
+                                  _p(cls, torch.float32), _p(pos, torch.float32), B, P, D, _p(x0, torch.float32),
+                                  _stream()), "embed_fwd")
+
+
+def im2col_fq(img, fq, B, C, HW, patch, out_planes):
+    """fq given: out_planes [1, B*P, K] integer codes; fq None: out_planes [2, B*P, K] hi/lo of the raw pixels."""
+    sc, zp, qmin, qmax = fq if fq is not None else (None, None, 0, 0)
+    lo = None if fq is not None else out_planes[1]
+    check(_lib.lib().qv_im2col_fq(_p(img, torch.float32), _p(sc, torch.float32), _p(zp, torch.int32), qmin, qmax, B, C, HW,
+                                  patch, _p(out_planes[0], torch.bfloat16), _p(lo, torch.bfloat16), _stream()), "im2col_fq")
+
+
+def softmax_planes(S, ldS, rows, T, scale, P_planes):
+    check(_lib.lib().qv_softmax_planes(_p(S, torch.float32), ldS, rows, T, float(scale), _p(P_planes, torch.bfloat16),
+                                       P_planes.stride(1), P_planes.stride(0), _stream()), "softmax_planes")
+
+
+def attn_ds(P_planes, dP, lddP, rows, T, scale, dS_planes):
+    check(_lib.lib().qv_attn_ds(_p(P_planes, torch.bfloat16), P_planes.stride(1), P_planes.stride(0),
+                                _p(dP, torch.float32), lddP, rows, T, float(scale), _p(dS_planes, torch.bfloat16),
+                                dS_planes.stride(1), dS_planes.stride(0), _stream()), "attn_ds")
+
+
+def head_fwd(x, wq, bias, B, K, N, out, minmax=None):
+    check(_lib.lib().qv_head_fwd(_p(x, torch.float32), _p(wq, torch.float32), _p(bias, torch.float32), B, K, N,
+                                 _p(out, torch.float32), _p(minmax, torch.int32), _stream()), "head_fwd")
+
+
+def head_bwd(g, x, wq, wmask, B, K, N, gx, gw, gb, accumulate=False):
+    check(_lib.lib().qv_head_bwd(_p(g, torch.float32), _p(x, torch.float32), _p(wq, torch.float32),
+                                 _p(wmask, torch.uint8), B, K, N, _p(gx, torch.float32), _p(gw, torch.float32),
+                                 _p(gb, torch.float32), int(bool(accumulate)), _stream()), "head_bwd")
