@@ -427,8 +427,12 @@ class StudentEngine:
     def _wgrad(self, ql: _QLinear, gp: torch.Tensor, x_planes: torch.Tensor, kdim: int, pairs, alpha=None) -> None:
         """weight.grad[N,K] = mask * (gp'^T @ x) / scale[n]  (split-K over the token dimension, deterministic reduce)."""
         s = self._splits[(ql.N, ql.K)]
-        ops.gemm(Op.full(gp, mn_major=True), Op.full(x_planes, mn_major=True), ql.N, ql.K, kdim, pairs, splits=s,
-                 workspace=self.ws)
+        if s > 1:
+            ops.gemm(Op.full(gp, mn_major=True), Op.full(x_planes, mn_major=True), ql.N, ql.K, kdim, pairs, splits=s,
+                     workspace=self.ws)
+        else:   # a single split writes its (raw) sums straight into slice 0 of the workspace
+            ops.gemm(Op.full(gp, mn_major=True), Op.full(x_planes, mn_major=True), ql.N, ql.K, kdim, pairs,
+                     out=self.ws[:ql.N * ql.K].view(ql.N, ql.K))
         ops.splitk_reduce(self.ws, s, ql.N, ql.K, self._grad(ql.weight), row_rscale=ql.wscale_vec, alpha=alpha, mask=ql.wmask)
 
     def _dgrad(self, ql: _QLinear, gp: torch.Tensor, M: int, out: torch.Tensor) -> None:

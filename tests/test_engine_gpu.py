@@ -1,101 +1,126 @@
-"""GPU parity (tier 2, <= 1e-3 relative): the fused QAT-distillation step vs the reference path on CPU
-(stock torch.ao prepare_qat + restated timm ViT + restated step body, oracle/vit_ref.py) on identical
-inputs and weights.  Weight observers / codes are compared bit-exactly (identical inputs), activation
-observers to 1e-5 relative (GEMM summation order differs)."""
+"""GPU parity of the fused QAT-distillation step (teacher fwd + student fwd + KL/CE + hand-written backward)
+against the reference path on CPU: stock torch.ao prepare_qat + restated timm ViT + restated step body
+(oracle/vit_ref.py, following ref/src/training/qat_trainer.py:300-316,337-361).
+
+Tolerances (north_star): bit-exact observer scale / zero-point / integer codes on identical inputs,
+<= 1e-3 relative on loss, logits and every gradient.  See tests/parity_utils.py for the forcing protocol."""
 import copy
 
 import pytest
 import torch
 
+from parity_utils import build_models, engine_raw_tensors, install_forcing_hooks, rel_l2, rel_max
+
 pytestmark = pytest.mark.gpu
 
-
-def _rel(a, b):
-    a, b = a.detach().double().cpu(), b.detach().double().cpu()
-    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
-
-
-def _build(backend, batch, student_name, teacher_name, img, seed=0):
-    from oracle import vit_ref as vr
-    torch.manual_seed(seed)
-    kw = dict(img_size=img) if img != 224 else {}
-    student = vr.qat_wrapper_cls(prefer_reference=False)(vr.create_model(student_name, num_classes=10, **kw))
-    torch.manual_seed(seed + 1)
-    teacher = vr.create_model(teacher_name, num_classes=10, **kw)
-    with torch.no_grad():
-        teacher.head.weight.mul_(8.0)
-        # a random-init ViT has almost no signal: widen a few things so every path carries gradient
-        for p in student.parameters():
-            if p.dim() == 1:
-                p.add_(0.02 * torch.randn_like(p))
-    teacher.eval()
-    for p in teacher.parameters():
-        p.requires_grad = False
-    prepared = vr.enable_qat(student, backend)
-    images, labels = vr.synthetic_batch(batch, seed=3, img=img)
-    return vr, prepared, teacher, images, labels
+CASES = [
+    # (backend, student, teacher, img, batch)
+    ("fbgemm", "vit_test_tiny", "vit_test_teacher", 64, 4),
+    ("qnnpack", "vit_test_tiny", "vit_test_teacher", 64, 3),
+    ("fbgemm", "vit_test_tiny", "vit_test_teacher", 96, 5),          # 37 tokens: ragged everything
+    ("fbgemm", "vit_small_patch16_224", "vit_base_patch16_224", 224, 8),   # BASELINE.json config 1
+]
 
 
-@pytest.mark.parametrize("backend", ["fbgemm", "qnnpack"])
-def test_tiny_step_matches_reference(cuda_dev, backend):
+@pytest.mark.parametrize("backend,sname,tname,img,B", CASES)
+def test_forced_parity_with_reference(cuda_dev, backend, sname, tname, img, B):
     from qatvit_b200.engine import QATDistillStep
-    vr, prepared, teacher, images, labels = _build(backend, 4, "vit_test_tiny", "vit_test_teacher", 64)
+    vr, prepared, teacher = build_models(backend, sname, tname, img)
+    images, labels = vr.synthetic_batch(B, seed=3, img=img)
     hp = dict(vr.DEFAULT_HPARAMS)
     gpu_student = copy.deepcopy(prepared).to(cuda_dev)
-    gpu_teacher = copy.deepcopy(teacher).to(cuda_dev)
-    step = QATDistillStep(gpu_student, gpu_teacher, 4, hp)
-    for it in range(2):     # second iteration exercises the EMA branch of every observer
-        loss_ref, s_ref, t_ref = vr.distill_step(prepared, teacher, images, labels, None, hp, clip=False)
-        ref_grads = {n: p.grad.clone() for n, p in prepared.named_parameters()}
-        prepared.zero_grad(set_to_none=True)
+    step = QATDistillStep(gpu_student, copy.deepcopy(teacher).to(cuda_dev), B, hp)
+    for it in range(2):                       # 2nd iteration: EMA branch of every observer, new images
+        if it == 1:
+            images, labels = vr.synthetic_batch(B, seed=11, img=img)
+            images = images * 1.3 + 0.2
         out3 = step(images.to(cuda_dev), labels.to(cuda_dev))
         torch.cuda.synchronize()
-        # teacher logits (fp32 path on bf16x3 tensor cores)
-        assert _rel(step.teacher_engine.logits, t_ref) < 1e-3
-        assert abs(float(out3[0]) - float(loss_ref)) <= 1e-3 * abs(float(loss_ref))
-        # student logits = fake-quantised head output
-        hd = step.student_engine.head
+        se = step.student_engine
+        stage_err = {}
+        handles = install_forcing_hooks(prepared, engine_raw_tensors(se), stage_err)
+        loss_ref, s_ref, t_ref = vr.distill_step(prepared, teacher, images, labels, None, hp, clip=False)
+        for h in handles:
+            h.remove()
+        # teacher: plain fp32 forward (bf16x3 tensor-core GEMMs on our side)
+        assert rel_max(step.teacher_engine.logits, t_ref) < 1e-3
+        # every stage of the student forward, given identical upstream codes
+        worst = max(stage_err, key=stage_err.get)
+        assert stage_err[worst] < 1e-4, (worst, stage_err[worst])
+        assert abs(float(out3[0]) - float(loss_ref)) <= 1e-4 * abs(float(loss_ref))
+        # student logits after the head's fake-quant: identical codes -> identical values up to the scale's last bit
         from qatvit_b200 import ops
-        s_gpu, _ = ops.fq_apply(step.student_logits_raw, hd.afq.scale, hd.afq.zero_point, hd.afq.fake_quant_enabled,
-                                hd.afq.qmin, hd.afq.qmax)
-        assert _rel(s_gpu, s_ref) < 1e-3 + 1.01 * float(hd.afq.scale) / float(s_ref.abs().max())   # <= one code step
-        # every parameter gradient
-        worst = ("", 0.0)
+        hd = se.head
+        s_gpu, _ = ops.fq_apply(se.logits_raw, hd.afq.scale, hd.afq.zero_point, hd.afq.fake_quant_enabled, hd.afq.qmin,
+                                hd.afq.qmax)
+        assert rel_max(s_gpu, s_ref) < 1e-5
+        # every parameter gradient (max-norm AND l2) within 1e-3
         for n, p in gpu_student.named_parameters():
-            r = _rel(p.grad, ref_grads[n])
-            if r > worst[1]:
-                worst = (n, r)
-        assert worst[1] < 2e-3, f"iteration {it}: gradient mismatch {worst}"
-        # observer state
+            ref_g = dict(prepared.named_parameters())[n].grad
+            assert rel_max(p.grad, ref_g) < 1e-3 and rel_l2(p.grad, ref_g) < 1e-3, (it, n, rel_max(p.grad, ref_g))
+        prepared.zero_grad(set_to_none=True)
+        # observer state: weights bit-exact (identical inputs); activations decided on (near-)identical raw tensors
         ref_sd, gpu_sd = prepared.state_dict(), gpu_student.state_dict()
         assert list(ref_sd.keys()) == list(gpu_sd.keys())
         for k in ref_sd:
             a, b = gpu_sd[k].cpu(), ref_sd[k]
             assert a.shape == b.shape and a.dtype == b.dtype, k
-            if "weight_fake_quant" in k:
-                assert torch.equal(a, b), f"weight observer state differs: {k}"
+            if "weight_fake_quant" in k or k.startswith("quant."):
+                assert torch.equal(a, b), f"observer state differs: {k}"
             elif k.endswith(("min_val", "max_val", "scale")):
-                assert _rel(a, b) < 1e-4, k
+                assert rel_max(a, b) < 1e-6, k
             elif k.endswith("zero_point"):
-                assert (a.long() - b.long()).abs().max() <= 1, k
+                assert torch.equal(a, b), k
+
+
+def test_free_running_divergence_is_at_reference_noise_floor(cuda_dev):
+    """Without forcing, our path vs torch-CPU must not diverge more than torch-CUDA (the reference's own GPU path)
+    diverges from torch-CPU on the same model -- that is the reproducibility floor of eager-mode QAT."""
+    from qatvit_b200.engine import QATDistillStep
+    vr, prepared, teacher = build_models("fbgemm", "vit_test_tiny", "vit_test_teacher", 64)
+    B = 8
+    images, labels = vr.synthetic_batch(B, seed=5, img=64)
+    hp = dict(vr.DEFAULT_HPARAMS)
+    ref_cpu, ref_gpu, ours = copy.deepcopy(prepared), copy.deepcopy(prepared).to(cuda_dev), copy.deepcopy(prepared).to(cuda_dev)
+    t_gpu = copy.deepcopy(teacher).to(cuda_dev)
+    l_cpu, s_cpu, _ = vr.distill_step(ref_cpu, teacher, images, labels, None, hp, clip=False)
+    l_gpu, s_gpu, _ = vr.distill_step(ref_gpu, t_gpu, images.to(cuda_dev), labels.to(cuda_dev), None, hp, clip=False)
+    step = QATDistillStep(ours, t_gpu, B, hp)
+    out3 = step(images.to(cuda_dev), labels.to(cuda_dev))
+    torch.cuda.synchronize()
+    g_cpu = torch.cat([p.grad.flatten() for p in ref_cpu.parameters()])
+    g_gpu = torch.cat([p.grad.flatten().cpu() for p in ref_gpu.parameters()])
+    g_ours = torch.cat([p.grad.flatten().cpu() for p in ours.parameters()])
+    floor = rel_l2(g_gpu, g_cpu)
+    mine = rel_l2(g_ours, g_cpu)
+    assert mine < max(3.0 * floor, 2e-2), (mine, floor)
+    assert abs(float(out3[0]) - float(l_cpu)) < max(3.0 * abs(float(l_gpu) - float(l_cpu)), 1e-2 * abs(float(l_cpu)))
 
 
 def test_state_dict_and_convert_flow_unchanged(cuda_dev):
     """best_qat.pth / convert() flow (ref qat_trainer.py:376-388) still works on a model trained by the engine."""
     from torch.ao.quantization import convert
     from qatvit_b200.engine import QATDistillStep
-    vr, prepared, teacher, images, labels = _build("fbgemm", 2, "vit_test_tiny", "vit_test_teacher", 64)
+    vr, prepared, teacher = build_models("fbgemm", "vit_test_tiny", "vit_test_teacher", 64)
+    images, labels = vr.synthetic_batch(2, seed=3, img=64)
     ref_keys = list(prepared.state_dict().keys())
     gpu_student = copy.deepcopy(prepared).to(cuda_dev)
     step = QATDistillStep(gpu_student, copy.deepcopy(teacher).to(cuda_dev), 2, dict(vr.DEFAULT_HPARAMS))
-    step(images.to(cuda_dev), labels.to(cuda_dev))
+    opt = vr.make_optimizer(gpu_student.parameters(), vr.DEFAULT_HPARAMS, 0.5)
+    w0 = gpu_student.model.blocks[0].attn.qkv.weight.detach().clone()
+    for _ in range(2):
+        step(images.to(cuda_dev), labels.to(cuda_dev))
+        torch.nn.utils.clip_grad_norm_(gpu_student.parameters(), 1.0)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        step.student_engine.attach_grads()
     torch.cuda.synchronize()
+    assert not torch.equal(w0, gpu_student.model.blocks[0].attn.qkv.weight.detach())
     sd = gpu_student.state_dict()
     assert list(sd.keys()) == ref_keys
     base = copy.deepcopy(gpu_student).cpu().eval()
     converted = convert(base, inplace=False)
     csd = converted.state_dict()
     assert any(k.endswith("_packed_params._packed_params") for k in csd)
-    # the converted int8 weights come from the observer state our kernels produced
     w, _ = csd["model.blocks.0.attn.qkv._packed_params._packed_params"]
     assert w.dtype == torch.qint8 and w.int_repr().abs().max() > 0
