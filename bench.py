@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- QAT-distillation train throughput (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]           # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] --steps K --warmup W   # the reference's CPU path on host cores
+
+A "step" = teacher ViT-B/16 forward + prepared (torch.ao QAT, fbgemm qconfig) ViT-S/16 student forward, KL+CE loss,
+backward, gradient all-reduce (N > 1), clip-norm 1.0 and AdamW -- ref/src/training/qat_trainer.py:337-361 -- on one
+synthetic batch.  N = 1: batch 256 (BASELINE configs[1]); N > 1: global batch 1024 (configs[2]).
+One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "ViT-S/16 QAT-distill train img/s"
+HP = {"lr": 1.5e-4, "weight_decay": 1e-3, "label_smoothing": 0.1, "kd_temp": 4.0, "kd_alpha": 0.5}   # ref DEFAULT_HPARAMS
+STUDENT, TEACHER = "vit_small_patch16_224", "vit_base_patch16_224"
+# algorithmic FLOPs per image of one step: student fwd+bwd 27.6 G + teacher fwd 35.1 G
+FLOP_PER_IMG = 62.7e9
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=d.get("hbm_gbs", 6650.0), tf_burst=d.get("bf16_tflops", 1590.0),
+                    tf_sustained=d.get("bf16_tflops_sustained", 1400.0), src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's own torch.ao CPU path (restated step over the live torch CPU ops)
+# --------------------------------------------------------------------------------------------------------------------
+def cpu_reference_rate(steps: int, warmup: int, batch: int = 8, budget_s: float = 25.0):
+    """img/s of the reference CPU path on a bounded sample: `steps` distill steps at batch 8 (BASELINE configs[0])."""
+    import torch
+    from oracle import vit_ref as vr     # checker / baseline only -- never on the product path
+    torch.set_num_threads(os.cpu_count() or 1)
+    hp = dict(vr.DEFAULT_HPARAMS)
+    student = vr.enable_qat(vr.make_student(prefer_reference=False), "fbgemm")
+    teacher = vr.make_teacher()
+    opt = vr.make_optimizer(student.parameters(), hp, 0.5)
+    images, labels = vr.synthetic_batch(batch, seed=0)
+    for _ in range(warmup):
+        vr.distill_step(student, teacher, images, labels, opt, hp)
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        vr.distill_step(student, teacher, images, labels, opt, hp)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return dict(value=batch * done / dt, unit="img/s", cores=torch.get_num_threads(), kind="port",
+                sample=f"{done} full distill steps (ViT-B teacher fwd + ViT-S fbgemm-QAT student fwd/bwd + clip + AdamW) at "
+                       f"batch {batch}, fp32, stock torch {torch.__version__} CPU ops, {dt / done * 1e3:.0f} ms/step"), dt / done
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base, ms = cpu_reference_rate(max(args.steps, 1), max(args.warmup, 0), budget_s=150.0)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "img/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "ViT-B/16 teacher -> ViT-S/16 QAT student distillation step (KL+CE), bounded sample: batch 8 "
+                                   "per step on the host CPU", "qconfig": "fbgemm"},
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# this repo's arm
+# --------------------------------------------------------------------------------------------------------------------
+def build_models(batch, dev, seed=0):
+    import warnings
+    import torch
+    from torch.ao.quantization import get_default_qat_qconfig, prepare_qat
+    from qatvit_b200 import vit
+    torch.manual_seed(seed)
+    student = vit.QATWrapper(vit.create_model(STUDENT, num_classes=10))
+    torch.manual_seed(seed + 1)
+    teacher = vit.create_model(TEACHER, num_classes=10).eval()
+    for p in teacher.parameters():
+        p.requires_grad = False
+    # QAT enable block, ref qat_trainer.py:304-308 (fbgemm qconfig = per-channel symmetric weights: north_star)
+    student.train()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        student.qconfig = get_default_qat_qconfig("fbgemm")
+        prepared = prepare_qat(student, inplace=False)
+    return prepared.to(dev).train(), teacher.to(dev)
+
+
+def clip_arena_(arena, max_norm: float, grad_scale: float = 1.0):
+    """torch.nn.utils.clip_grad_norm_(params, max_norm) on the flat gradient arena (same math, 2 launches);
+    grad_scale folds the 1/world of the DDP gradient mean into the same pass."""
+    import torch
+    total = torch.linalg.vector_norm(arena) * grad_scale
+    coef = (max_norm / (total + 1e-6)).clamp(max=1.0) * grad_scale
+    arena.mul_(coef)
+    return total
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import qatvit_b200  # noqa: F401  -- raises if libqatvit_b200.so is missing (no fallback)
+    from qatvit_b200 import ops
+    from qatvit_b200.engine import QATDistillStep
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- qatvit_b200 has no CPU fallback (use --impl reference for the CPU path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = max(world, 1)
+    global_batch = 256 if n == 1 else 1024
+    batch = global_batch // n
+
+    student, teacher = build_models(batch, dev)
+    step = QATDistillStep(student, teacher, batch, HP)
+    opt = torch.optim.AdamW(student.parameters(), lr=HP["lr"] * 0.5, weight_decay=HP["weight_decay"])   # ref :315
+    arena = step.grad_arena
+
+    g = torch.Generator().manual_seed(1234 + rank)
+    host_images = torch.randn(batch, 3, 224, 224, generator=g).pin_memory()
+    host_labels = torch.randint(0, 10, (batch,), generator=g).pin_memory()
+    images = host_images.to(dev)
+    labels = host_labels.to(dev)
+    host_loss = torch.zeros(3).pin_memory()
+
+    def train_step(img, lab):
+        out3 = step(img, lab)                                  # teacher fwd, student fwd, loss, bwd  (our kernels)
+        if world > 1:
+            dist.all_reduce(arena)                             # the one collective of the path (NCCL over NVLink)
+        clip_arena_(arena, 1.0, 1.0 / world)                   # ref :360 (+ DDP mean)
+        opt.step()                                             # ref :361
+        return out3
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        train_step(images, labels)
+    barrier()
+
+    # ---- device-resident timing (value) ----
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = ops.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        train_step(images, labels)
+    ev1.record()
+    barrier()
+    launches = ops.launch_count() - l0
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms)
+    clocks = sampler.stop() if sampler else None
+
+    # ---- end to end through the public step API: pinned host inputs, H2D every step, loss D2H every step ----
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        images.copy_(host_images, non_blocking=True)
+        labels.copy_(host_labels, non_blocking=True)
+        out3 = train_step(images, labels)
+        host_loss.copy_(out3, non_blocking=True)
+        torch.cuda.current_stream().synchronize()              # the reference's loss.item() (ref :363)
+    ev1.record()
+    barrier()
+    ms2 = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_ms = float(ms2)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel-family breakdown of ONE step (CUDA events around every launch) -> roofline of the dominant kernel ----
+    ops.profile_begin()
+    step(images, labels)
+    prof = ops.profile_end()
+    peaks = _peaks()
+    fam = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])
+    step_kernel_ms = sum(v["ms"] for v in prof.values())
+    gemm_ms = sum(v["ms"] for k, v in prof.items() if k.startswith("gemm"))
+    gemm_flop = sum(v["work"] for k, v in prof.items() if k.startswith("gemm"))
+    gemm_cnt = sum(v["count"] for k, v in prof.items() if k.startswith("gemm"))
+    achieved = gemm_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    roofline = {"kernel": "qv_gemm_kernel (tcgen05 fake-quant GEMM family: fwd/dgrad/wgrad/attention)", "bound": "tensor",
+                "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"],
+                "traffic": None, "peak_source": peaks["src"] + ", bf16 dense sustained",
+                "note": "achieved = algorithmic fp32-equivalent FLOPs (2MNK per product, hi/lo bf16 passes not counted) / "
+                        "CUDA-event time of all %d GEMM launches of one step (avg %.1f us/launch); share of step kernel time %.0f%%"
+                        % (gemm_cnt, gemm_ms * 1e3 / max(gemm_cnt, 1), 100.0 * gemm_ms / max(step_kernel_ms, 1e-9)),
+                "breakdown_ms": {k: round(v["ms"], 3) for k, v in fam}}
+
+    cpu_base = None
+    if n == 1 and not args.no_cpu_baseline:
+        cpu_base, _ = cpu_reference_rate(steps=1000, warmup=2, budget_s=18.0)
+
+    value = global_batch * args.steps / (ms_total * 1e-3)
+    e2e_value = global_batch * args.steps / (e2e_ms * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": n, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32 (tcgen05 bf16 hi/lo planes, fp32 accumulate; integer fake-quant codes exact)", "data": "synthetic",
+        "config": {"workload": "ViT-B/16 teacher -> ViT-S/16 QAT student distillation step (KL+CE), batch 256, 1x B200"
+                   if n == 1 else f"same distillation step data-parallel, global batch 1024 at {n} B200 with NCCL gradient allreduce",
+                   "global_batch": global_batch, "per_gpu_batch": batch, "qconfig": "fbgemm", "image": "3x224x224",
+                   "parallelism": f"dp{n}", "l2": "per-step working set (~20 GB of activations) >> 126 MB L2; no flush needed",
+                   "optimizer": "torch AdamW + clip-norm on the flat gradient arena (host stays PyTorch)"},
+        "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": host_images.numel() * 4 + host_labels.numel() * 8,
+                "d2h_bytes_per_step": 12, "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "model_tflops": FLOP_PER_IMG * value / 1e12,
+    }
+    if cpu_base is not None:
+        line["cpu_baseline"] = cpu_base
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -419,9 +419,10 @@ class StudentEngine:
         ops.head_fwd(self.xn, hd.wq, hd.bias.detach(), B, D, d.C, self.logits_raw, minmax=hd.acc)
         hd.afq.update_from(hd.acc)
         hp = self.hp_
-        check_grad = self.g_logits
-        out3, _ = _kd_ce(self.logits_raw, teacher_logits, labels, hp, hd.afq, self.loss3, check_grad)
-        return out3
+        ops.kd_ce_loss(self.logits_raw, teacher_logits, labels, hp["kd_temp"], hp["kd_alpha"], hp["label_smoothing"],
+                       s_scale=hd.afq.scale, s_zp=hd.afq.zero_point, qmin=hd.afq.qmin, qmax=hd.afq.qmax, out3=self.loss3,
+                       grad=self.g_logits)
+        return self.loss3
 
     # ------------------------------------------------------------------------------------------
     def _wgrad(self, ql: _QLinear, gp: torch.Tensor, x_planes: torch.Tensor, kdim: int, pairs, alpha=None) -> None:
@@ -499,18 +500,6 @@ class StudentEngine:
         ops.colsum_rows(gx, B, D, T * D, self._grad(v.cls_token))
         self._gp(gx, self.p_raw, self.conv, False, B * d.P, self.gpP, remap=(d.P, T))
         self._wgrad(self.conv, self.gpP, self.img_codes, B * d.P, PAIRS_EXACT_B, alpha=self.fq_in.scale)
-
-
-def _kd_ce(logits_raw, teacher_logits, labels, hp, afq: FQRef, out3, grad):
-    from . import _lib
-    import ctypes
-    B, C = logits_raw.shape
-    _lib.check(_lib.lib().qv_kd_ce_loss(
-        ops._p(logits_raw, torch.float32), ops._p(teacher_logits, torch.float32), ops._p(labels, torch.int64), B, C,
-        float(hp["kd_temp"]), float(hp["kd_alpha"]), float(hp["label_smoothing"]), ops._p(afq.scale, torch.float32),
-        ops._p(afq.zero_point, torch.int32), afq.qmin, afq.qmax, ops._p(out3, torch.float32), ops._p(grad, torch.float32),
-        ops._stream()), "kd_ce_loss")
-    return out3, grad
 
 
 class QATDistillStep:

@@ -101,10 +101,13 @@ def split_planes(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.T
     return out
 
 
-def kd_ce_loss(s_raw, t, labels, T, alpha, eps, s_scale=None, s_zp=None, qmin=0, qmax=255, want_grad=True):
+def kd_ce_loss(s_raw, t, labels, T, alpha, eps, s_scale=None, s_zp=None, qmin=0, qmax=255, want_grad=True, out3=None,
+               grad=None):
     B, C = s_raw.shape
-    out3 = torch.empty(3, dtype=torch.float32, device=s_raw.device)
-    grad = torch.empty_like(s_raw) if want_grad else None
+    if out3 is None:
+        out3 = torch.empty(3, dtype=torch.float32, device=s_raw.device)
+    if grad is None and want_grad:
+        grad = torch.empty_like(s_raw)
     check(_lib.lib().qv_kd_ce_loss(_p(s_raw, torch.float32, "s"), _p(t, torch.float32, "t"),
                                    _p(labels, torch.int64, "labels"), B, C, float(T), float(alpha), float(eps),
                                    _p(s_scale, torch.float32), _p(s_zp, torch.int32), int(qmin), int(qmax),
@@ -290,3 +293,58 @@ def head_bwd(g, x, wq, wmask, B, K, N, gx, gw, gb, accumulate=False):
     check(_lib.lib().qv_head_bwd(_p(g, torch.float32), _p(x, torch.float32), _p(wq, torch.float32),
                                  _p(wmask, torch.uint8), B, K, N, _p(gx, torch.float32), _p(gw, torch.float32),
                                  _p(gb, torch.float32), int(bool(accumulate)), _stream()), "head_bwd")
+
+
+# ------------------------------------------------------------------------------------------------
+# optional per-op CUDA-event profiling (bench.py's roofline section; off by default, zero overhead when off)
+# ------------------------------------------------------------------------------------------------
+_prof = None
+
+
+def _gemm_tag(args, kw):
+    a, b, M, N, K = args[0], args[1], args[2], args[3], args[4]
+    nb = kw.get("nbatch", 1)
+    kind = "attn" if nb > 1 else ("wgrad" if a.mn_major else "fwd/dgrad")
+    return f"gemm[{kind}]", 2.0 * M * N * K * nb
+
+
+def _wrap(name, fn, tag_fn=None):
+    def inner(*a, **k):
+        if _prof is None:
+            return fn(*a, **k)
+        tag, work = tag_fn(a, k) if tag_fn else (name, 0.0)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        r = fn(*a, **k)
+        e.record()
+        _prof.append((tag, work, s, e))
+        return r
+    inner.__name__ = name
+    inner.__doc__ = fn.__doc__
+    return inner
+
+
+for _n in ("minmax_reset", "minmax_accumulate", "obs_update", "fq_apply", "fq_weight", "fq_bwd", "split_planes",
+           "kd_ce_loss", "splitk_reduce", "resid_ln_fwd", "ln_bwd", "colsum_reduce", "colsum_rows", "gp_planes",
+           "act_planes", "embed_fwd", "im2col_fq", "softmax_planes", "attn_ds", "head_fwd", "head_bwd"):
+    globals()[_n] = _wrap(_n, globals()[_n])
+gemm = _wrap("gemm", gemm, _gemm_tag)
+
+
+def profile_begin() -> None:
+    global _prof
+    _prof = []
+
+
+def profile_end():
+    """-> {tag: dict(count, ms, work)} with CUDA-event durations of every op since profile_begin()."""
+    global _prof
+    torch.cuda.synchronize()
+    out = {}
+    for tag, work, s, e in _prof:
+        d = out.setdefault(tag, dict(count=0, ms=0.0, work=0.0))
+        d["count"] += 1
+        d["ms"] += s.elapsed_time(e)
+        d["work"] += work
+    _prof = None
+    return out
