@@ -85,7 +85,7 @@ int qv_kd_ce_loss(const float* s_raw, const float* t, const int64_t* labels, int
  *      torch/ao/nn/qat/modules/linear.py:50-51, its autograd dgrad/wgrad, the teacher's nn.Linear, and --
  *      batched per (image, head) -- the matmuls inside F.scaled_dot_product_attention and its backward)
  *
- * D[M,N] (fp32) = sum over `npairs` plane pairs (pa, pb) of  A[pa] * B[pb]^T , then the epilogue
+ * D[M,N] (fp32) = sum over plane pairs (pa, pb) of  A[pa] * B[pb]^T  (see a_planes / b_planes), then the epilogue
  *   d = acc * (col_scale ? col_scale[n] : 1) * (alpha ? *alpha : 1) * (col_rscale ? 1/col_rscale[n] : 1)
  *       + (bias ? bias[n] : 0)
  * A, B are bf16 "plane stacks": an fp32 tensor is represented as hi/lo planes (x ~= hi + lo), integer
@@ -97,7 +97,6 @@ int qv_kd_ce_loss(const float* s_raw, const float* t, const int64_t* labels, int
  *   batch item bt -> (bo, bi) = (bt / batch_inner, bt % batch_inner) selects matrix bo*c2_outer + bi*c2_inner
  *   and column offset col0 + bi*col_inner (a head's 64 columns inside a [tokens, 3*D] tensor);
  *   plane p starts p*plane_stride elements after ptr.
- * Output of item bt starts at d + bo*d_off_outer + bi*d_off_inner (row pitch ldd).
  * splits > 1 (split-K, unbatched only): raw partial sums go to workspace[splits][M][N] fp32, `d` and the
  * epilogue terms are ignored; call qv_splitk_reduce afterwards.  minmax (uint32[2], may be NULL): ordered
  * min/max of the stored d values are atomically merged (fused output observer, phase 1).            */
@@ -107,15 +106,24 @@ typedef struct qv_operand {
   int64_t nb, batch_stride;
   int32_t c2_outer, c2_inner, col0, col_inner;
 } qv_operand;
+/* fp32 output tensor [nb][rows][ld]; batch item (bo, bi) is written at matrix bo*c2_outer + bi*c2_inner, columns
+ * col0 + bi*col_inner + [0, N); rows >= `rows` and columns >= `cols` are clipped by the TMA store. */
+typedef struct qv_out {
+  float* ptr; int64_t ld;
+  int64_t rows, cols;
+  int64_t nb, batch_stride;
+  int32_t c2_outer, c2_inner, col0, col_inner;
+} qv_out;
 typedef struct qv_gemm_args {
   qv_operand a, b;
-  int32_t npairs; int32_t pair_a[4]; int32_t pair_b[4];
+  int32_t a_planes, b_planes;   /* (1,1): A*B ; (2,1): (A0+A1)*B ; (2,2): A0*B0 + A0*B1 + A1*B0 */
   int64_t M, N, K;
-  float* d; int64_t ldd;
+  qv_out out;
   const float* col_scale; const float* col_rscale; const float* alpha; const float* bias;
   uint32_t* minmax;
   int32_t splits; float* workspace;
-  int32_t nbatch, batch_inner; int64_t d_off_outer, d_off_inner;
+  int32_t nbatch, batch_inner;
+  int32_t tile_n;               /* 0 = auto; else 64 / 128 / 192 */
 } qv_gemm_args;
 int qv_gemm_bf16(const qv_gemm_args* args, void* stream);
 

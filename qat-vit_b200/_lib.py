@@ -33,17 +33,25 @@ class Operand(ctypes.Structure):
     ]
 
 
+class Out(ctypes.Structure):
+    """struct qv_out (include/qatvit_b200.h)."""
+    _fields_ = [
+        ("ptr", c_void_p), ("ld", c_int64), ("rows", c_int64), ("cols", c_int64), ("nb", c_int64),
+        ("batch_stride", c_int64), ("c2_outer", c_int32), ("c2_inner", c_int32), ("col0", c_int32), ("col_inner", c_int32),
+    ]
+
+
 class GemmArgs(ctypes.Structure):
     """struct qv_gemm_args (include/qatvit_b200.h)."""
     _fields_ = [
         ("a", Operand), ("b", Operand),
-        ("npairs", c_int32), ("pair_a", c_int32 * 4), ("pair_b", c_int32 * 4),
+        ("a_planes", c_int32), ("b_planes", c_int32),
         ("M", c_int64), ("N", c_int64), ("K", c_int64),
-        ("d", c_void_p), ("ldd", c_int64),
+        ("out", Out),
         ("col_scale", c_void_p), ("col_rscale", c_void_p), ("alpha", c_void_p), ("bias", c_void_p),
         ("minmax", c_void_p),
         ("splits", c_int32), ("workspace", c_void_p),
-        ("nbatch", c_int32), ("batch_inner", c_int32), ("d_off_outer", c_int64), ("d_off_inner", c_int64),
+        ("nbatch", c_int32), ("batch_inner", c_int32), ("tile_n", c_int32),
     ]
 
 

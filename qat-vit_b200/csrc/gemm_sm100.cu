@@ -1,22 +1,23 @@
 // gemm_sm100.cu -- persistent, warp-specialised tcgen05 GEMM for the fake-quant Linear family.
 //
-//   D[M,N] = sum_pairs A[pa] (bf16 planes) x B[pb]^T (bf16 planes), fp32 accumulation in TMEM.
+//   D[M,N] (fp32) = sum over plane pairs of A[pa] (bf16) x B[pb]^T (bf16), fp32 accumulation in TMEM.
 //
-// Replaces F.linear inside torch.ao.nn.qat.Linear.forward (torch/ao/nn/qat/modules/linear.py:50-51),
-// its autograd dgrad / wgrad mm's, and the teacher's nn.Linear (ref qat_trainer.py:337-341).
-// fp32 tensors reach the tensor cores as bf16 hi/lo plane stacks; fake-quantised weights as ONE exact
-// plane of integer codes with the per-channel scale applied in the epilogue (SURVEY.md §7 "hard parts").
+// Replaces F.linear inside torch.ao.nn.qat.Linear.forward (torch/ao/nn/qat/modules/linear.py:50-51), its autograd
+// dgrad / wgrad mm's, the teacher's nn.Linear (ref qat_trainer.py:337-341) and -- batched per (image, head) -- the
+// matmuls of F.scaled_dot_product_attention and its backward.  fp32 tensors reach the tensor cores as bf16 hi/lo plane
+// stacks; fake-quantised weights as ONE exact plane of integer codes with the per-channel scale in the epilogue.
 //
 // Structure (one CTA per SM, static round-robin over 128 x BN output tiles):
-//   warp 0      : TMA producer  -- cp.async.bulk.tensor into a STAGES-deep 128B-swizzled smem ring
-//   warp 1      : tcgen05.mma issuer (one thread) -- accumulators double-buffered in TMEM
-//   warps 2..5  : epilogue -- tcgen05.ld -> scale/bias -> fused observer min/max -> coalesced fp32 stores
-// so the epilogue of tile i overlaps the main loop of tile i+1 (the student GEMMs have K = 384 and are
-// close to HBM-bound on the fp32 output write).
+//   warp 0      : TMA producer.  One pipeline stage holds ALL planes of one 64-deep k-block (NA A-planes + NB B-planes),
+//                 so the hi/lo passes re-use the B (or A) tile from shared memory instead of re-fetching it from L2.
+//   warp 1      : tcgen05.mma issuer (one thread): for each stage, every (pa, pb) pair x 4 UMMA_K steps into the same
+//                 TMEM accumulator; accumulators are double-buffered in TMEM.
+//   warps 2..5  : epilogue: tcgen05.ld (32 lanes x 32 columns) -> scale / bias -> fused observer min/max ->
+//                 128B-swizzled smem staging -> per-warp TMA store (cp.async.bulk.tensor), double-buffered, so the
+//                 epilogue of tile i overlaps the main loop of tile i+1 and global writes are full 128-byte lines.
 #include <cuda.h>
 #include <stdio.h>
 #include <string.h>
-#include <atomic>
 #include <mutex>
 
 #include "qv_common.cuh"
@@ -30,49 +31,50 @@ constexpr int BM = 128;
 constexpr int BK = 64;            // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 192;
-constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int A_PLANE_BYTES = BM * BK * 2;
+constexpr int EPI_WARP_BYTES = 2 * 32 * 128;   // two 32-row x 128-byte staging buffers per epilogue warp
+constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;
+constexpr int SMEM_LIMIT = 232448;             // 227 KB
 
 struct GemmKParams {
   int64_t M, N;
-  int32_t kblocks;        // ceil(K / BK) per plane pair
-  int32_t npairs;
-  int32_t pair_a[4], pair_b[4];
+  int32_t kblocks;        // ceil(K / BK)
   int32_t tiles_m, tiles_n, splits, kb_per_split;
-  float* d;
-  int64_t ldd;
   const float* col_scale;
   const float* col_rscale;
   const float* alpha;
   const float* bias;
   uint32_t* minmax;
-  float* workspace;
-  // batching: item -> (outer index bt) -> (bo, bi) = (bt / batch_inner, bt % batch_inner)
+  // batching: outer index bt -> (bo, bi) = (bt / batch_inner, bt % batch_inner)
   int32_t nbatch, batch_inner;
   int32_t a_c2_outer, a_c2_inner, a_col0, a_col_inner;
   int32_t b_c2_outer, b_c2_inner, b_col0, b_col_inner;
-  int64_t d_off_outer, d_off_inner;
+  int32_t o_c2_outer, o_c2_inner, o_col0, o_col_inner;
 };
 
-template <int BN>
+template <int BN, int NA, int NB>
 struct Cfg {
-  static constexpr int B_STAGE_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (BN == 128) ? 6 : 4;
-  static constexpr int TMEM_COLS = 2 * BN;                 // 256 or 512 (power of two)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int B_PLANE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = NA * A_PLANE_BYTES + NB * B_PLANE_BYTES;
+  static constexpr int MAX_STAGES = (SMEM_LIMIT - 1024 - 256 - EPI_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = MAX_STAGES > 6 ? 6 : MAX_STAGES;
+  static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int NPAIRS = (NA == 2 && NB == 2) ? 3 : NA * NB;   // (hi,hi) (hi,lo) (lo,hi): lo*lo is dropped
+  static_assert(STAGES >= 2, "pipeline needs at least two stages");
+  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN must be a multiple of 32 up to 256");
 };
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, int NA, int NB, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const GemmKParams p) {
-  using C = Cfg<BN>;
+               const __grid_constant__ CUtensorMap map_o, const GemmKParams p) {
+  using C = Cfg<BN, NA, NB>;
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle atoms need 1024-byte aligned tile bases
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + C::STAGES * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint8_t* smem_epi = smem + C::STAGES * C::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + EPI_BYTES);
   uint64_t* full_bar = bars;                       // [STAGES]
   uint64_t* empty_bar = bars + C::STAGES;          // [STAGES]
   uint64_t* tmem_full = bars + 2 * C::STAGES;      // [2]
@@ -85,6 +87,7 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (threadIdx.x == 0) {
     prefetch_tensormap(&map_a);
     prefetch_tensormap(&map_b);
+    prefetch_tensormap(&map_o);
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -119,29 +122,34 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int b_c2 = bo * p.b_c2_outer + bi * p.b_c2_inner, b_col = p.b_col0 + bi * p.b_col_inner;
         const int kb0 = z * p.kb_per_split;
         const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
-        for (int pr = 0; pr < p.npairs; ++pr) {
-          const int pa = p.pair_a[pr], pb = p.pair_b[pr];
-          for (int kb = kb0; kb < kb1; ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-            uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
-            uint8_t* sb = smem_b + stage * C::B_STAGE_BYTES;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          uint8_t* sb = sa + NA * A_PLANE_BYTES;
+#pragma unroll
+          for (int pa = 0; pa < NA; ++pa) {
             if (!A_MN) {
-              tma_load_4d(sa, &map_a, &full_bar[stage], a_col + kb * BK, m_blk * BM, a_c2, pa);
+              tma_load_4d(sa + pa * A_PLANE_BYTES, &map_a, &full_bar[stage], a_col + kb * BK, m_blk * BM, a_c2, pa);
             } else {
 #pragma unroll
               for (int j = 0; j < BM / 64; ++j)
-                tma_load_4d(sa + j * 8192, &map_a, &full_bar[stage], a_col + m_blk * BM + j * 64, kb * BK, a_c2, pa);
+                tma_load_4d(sa + pa * A_PLANE_BYTES + j * 8192, &map_a, &full_bar[stage], a_col + m_blk * BM + j * 64,
+                            kb * BK, a_c2, pa);
             }
+          }
+#pragma unroll
+          for (int pb = 0; pb < NB; ++pb) {
             if (!B_MN) {
-              tma_load_4d(sb, &map_b, &full_bar[stage], b_col + kb * BK, n_blk * BN, b_c2, pb);
+              tma_load_4d(sb + pb * C::B_PLANE_BYTES, &map_b, &full_bar[stage], b_col + kb * BK, n_blk * BN, b_c2, pb);
             } else {
 #pragma unroll
               for (int j = 0; j < BN / 64; ++j)
-                tma_load_4d(sb + j * 8192, &map_b, &full_bar[stage], b_col + n_blk * BN + j * 64, kb * BK, b_c2, pb);
+                tma_load_4d(sb + pb * C::B_PLANE_BYTES + j * 8192, &map_b, &full_bar[stage], b_col + n_blk * BN + j * 64,
+                            kb * BK, b_c2, pb);
             }
-            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
           }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -159,22 +167,27 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int z = p.nbatch > 1 ? 0 : item / (p.tiles_n * p.tiles_m);
         const int kb0 = z * p.kb_per_split;
         const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
-        const int iters = p.npairs * (kb1 - kb0);
         const int buf = local & 1;
         const uint32_t use = static_cast<uint32_t>(local >> 1);      // n-th use of this TMEM buffer
         mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * BN);
-        for (int it = 0; it < iters; ++it) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem_a + stage * A_STAGE_BYTES);
-          const uint32_t sb = smem_u32(smem_b + stage * C::B_STAGE_BYTES);
+          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t sb = sa + NA * A_PLANE_BYTES;
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t da = umma_smem_desc(sa + k * a_kadv, a_lbo, 1024u);
-            const uint64_t db = umma_smem_desc(sb + k * b_kadv, b_lbo, 1024u);
-            umma_bf16(d_tmem, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+          for (int pr = 0; pr < C::NPAIRS; ++pr) {
+            // pair order: (0,0) [,(0,1)] [,(1,0)]  -- for NB == 1 the second pair is (1,0)
+            const int pa = (NB == 1) ? pr : (pr == 2 ? 1 : 0);
+            const int pb = (NB == 1) ? 0 : (pr == 1 ? 1 : 0);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t da = umma_smem_desc(sa + pa * A_PLANE_BYTES + k * a_kadv, a_lbo, 1024u);
+              const uint64_t db = umma_smem_desc(sb + pb * C::B_PLANE_BYTES + k * b_kadv, b_lbo, 1024u);
+              umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || pr > 0 || k > 0) ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);       // frees this smem stage once the MMAs have read it
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -183,76 +196,88 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else {
-    // =============================== epilogue (128 threads) ===============================
+    // =============================== epilogue (4 warps) ===============================
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
-    const int row_in_tile = q * 32 + lane;
+    uint8_t* my_epi = smem_epi + q * EPI_WARP_BYTES;
     float mn = INFINITY, mx = -INFINITY;
     const float alpha = p.alpha ? __ldg(p.alpha) : 1.0f;
-    const bool vec_ok = p.splits > 1 ? (p.N % 4 == 0 && (reinterpret_cast<uintptr_t>(p.workspace) & 15) == 0)
-                                     : (p.ldd % 4 == 0 && (reinterpret_cast<uintptr_t>(p.d) & 15) == 0);
+    const bool raw = p.splits > 1;
+    uint32_t chunk_ctr = 0;
     int local = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
       const int n_blk = item % p.tiles_n;
       const int m_blk = (item / p.tiles_n) % p.tiles_m;
       const int outer = item / (p.tiles_n * p.tiles_m);
-      const int z = p.nbatch > 1 ? 0 : outer;
       const int bt = p.nbatch > 1 ? outer : 0;
+      const int bo = bt / p.batch_inner, bi = bt % p.batch_inner;
+      const int o_c2 = raw ? outer : bo * p.o_c2_outer + bi * p.o_c2_inner;
+      const int o_col = raw ? 0 : p.o_col0 + bi * p.o_col_inner;
       const int buf = local & 1;
       const uint32_t use = static_cast<uint32_t>(local >> 1);
       mbar_wait(&tmem_full[buf], use & 1);
       tc_fence_after();
-      const int64_t m = static_cast<int64_t>(m_blk) * BM + row_in_tile;
-      float* out;
-      int64_t ldo;
-      const bool raw = p.splits > 1;
-      if (raw) {
-        out = p.workspace + static_cast<int64_t>(z) * p.M * p.N;
-        ldo = p.N;
-      } else {
-        out = p.d + (bt / p.batch_inner) * p.d_off_outer + (bt % p.batch_inner) * p.d_off_inner;
-        ldo = p.ldd;
-      }
+      const int row0 = m_blk * BM + q * 32;                     // first row of this warp's 32-row slab
+      const bool row_ok = static_cast<int64_t>(row0 + lane) < p.M;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN + c0), r);
         tmem_ld_wait();
+        if (c0 + 32 >= BN) {                                    // accumulator fully read: hand TMEM back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[buf]);
+        }
         const int64_t n0 = static_cast<int64_t>(n_blk) * BN + c0;
-        if (m < p.M && n0 < p.N) {
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float a = __uint_as_float(r[j]);
-            if (!raw) {
-              const int64_t n = n0 + j;
-              if (n < p.N) {
-                float mult = alpha;
-                if (p.col_scale) mult *= __ldg(p.col_scale + n);
-                if (p.col_rscale) mult = __fdiv_rn(mult, __ldg(p.col_rscale + n));
-                a *= mult;
-                if (p.bias) a += __ldg(p.bias + n);
-                mn = fminf(mn, a);
-                mx = fmaxf(mx, a);
-              }
-            }
-            v[j] = a;
-          }
-          float* dst = out + m * ldo + n0;
-          if (vec_ok && n0 + 32 <= p.N) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.N) dst[j] = v[j];
+        if (n0 >= p.N || static_cast<int64_t>(row0) >= p.M) continue;      // warp-uniform: nothing to store
+        uint8_t* sbuf = my_epi + (chunk_ctr & 1) * 4096;
+        if (lane == 0) tma_store_wait_read<1>();                // the store that last used this buffer has read it
+        __syncwarp();
+        // per-column epilogue terms: lane j owns column n0 + j (two coalesced loads), broadcast by shuffle below
+        float my_mult = 1.0f, my_bias = 0.0f;
+        if (!raw) {
+          const int64_t n = n0 + lane;
+          if (n < p.N) {
+            my_mult = alpha;
+            if (p.col_scale) my_mult *= __ldg(p.col_scale + n);
+            if (p.col_rscale) my_mult = __fdiv_rn(my_mult, __ldg(p.col_rscale + n));
+            if (p.bias) my_bias = __ldg(p.bias + n);
           }
         }
+        const int ncols = static_cast<int>(min(static_cast<int64_t>(32), p.N - n0));   // valid columns of this chunk
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float a = __uint_as_float(r[j]);
+          if (!raw) {
+            const float m_j = __shfl_sync(0xffffffffu, my_mult, j);
+            const float b_j = __shfl_sync(0xffffffffu, my_bias, j);
+            a = a * m_j + b_j;
+            const bool ok = row_ok && (j < ncols);
+            mn = ok ? fminf(mn, a) : mn;
+            mx = ok ? fmaxf(mx, a) : mx;
+          }
+          v[j] = a;
+        }
+        // 128B-swizzled staging: 16-byte chunk j of row `lane` lives at chunk (j ^ (lane & 7))
+        const uint32_t srow = smem_u32(sbuf) + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t addr = srow + (static_cast<uint32_t>(j ^ (lane & 7)) << 4);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[4 * j]), "f"(v[4 * j + 1]),
+                       "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                       : "memory");
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&map_o, sbuf, o_col + static_cast<int>(n0), row0, o_c2);
+          tma_store_commit();
+        }
+        ++chunk_ctr;
       }
-      tc_fence_before();
-      mbar_arrive(&tmem_empty[buf]);
     }
-    if (p.minmax && p.splits == 1) {
+    if (lane == 0) tma_store_wait_read<0>();
+    if (p.minmax && !raw) {
       mn = qv_warp_min(mn);
       mx = qv_warp_max(mx);
       if (lane == 0 && mn <= mx) {
@@ -318,7 +343,8 @@ int make_map(CUtensorMap* m, const qv_operand& op, int planes, int box_rows) {
   QV_REQUIRE(enc != nullptr, QV_ERR_CUDA, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
   QV_REQUIRE(op.ptr && qv_aligned16(op.ptr), QV_ERR_INVALID, "gemm operand base must be a 16-byte aligned device pointer");
   QV_REQUIRE(op.rows > 0 && op.cols > 0, QV_ERR_INVALID, "gemm operand extent must be positive");
-  QV_REQUIRE(op.ld % 8 == 0 && op.ld >= op.cols, QV_ERR_INVALID, "gemm operand row pitch must be >= cols and a multiple of 8 bf16 (got %lld)", (long long)op.ld);
+  QV_REQUIRE(op.ld % 8 == 0 && op.ld >= op.cols, QV_ERR_INVALID,
+             "gemm operand row pitch must be >= cols and a multiple of 8 bf16 (got %lld)", (long long)op.ld);
   int64_t nb = op.nb > 0 ? op.nb : 1;
   int64_t bstride = op.batch_stride > 0 ? op.batch_stride : op.rows * op.ld;
   int64_t pstride = op.plane_stride > 0 ? op.plane_stride : bstride * nb;
@@ -332,22 +358,71 @@ int make_map(CUtensorMap* m, const qv_operand& op, int planes, int box_rows) {
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(op.ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  QV_REQUIRE(r == CUDA_SUCCESS, QV_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  QV_REQUIRE(r == CUDA_SUCCESS, QV_ERR_CUDA, "cuTensorMapEncodeTiled(operand) failed (%d)", (int)r);
   return 0;
 }
 
-template <int BN, bool A_MN, bool B_MN>
-int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmKParams& kp, int grid, cudaStream_t st) {
-  using C = Cfg<BN>;
+// fp32 output [nb][rows][ld] as a 3-D tensor (cols, rows, nb); store box = (32 cols = 128 B, 32 rows, 1), 128B swizzle.
+int make_out_map(CUtensorMap* m, float* ptr, int64_t cols, int64_t rows, int64_t ld, int64_t nb, int64_t bstride) {
+  EncodeTiledFn enc = get_encode();
+  QV_REQUIRE(enc != nullptr, QV_ERR_CUDA, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  QV_REQUIRE(ptr && qv_aligned16(ptr), QV_ERR_INVALID, "gemm output base must be a 16-byte aligned device pointer");
+  QV_REQUIRE(rows > 0 && cols > 0 && ld >= cols && ld % 4 == 0, QV_ERR_INVALID,
+             "gemm output row pitch must be >= cols and a multiple of 4 floats (got %lld)", (long long)ld);
+  if (nb < 1) nb = 1;
+  if (bstride <= 0) bstride = rows * ld;
+  QV_REQUIRE(bstride % 4 == 0, QV_ERR_INVALID, "gemm output batch stride must be a multiple of 4 floats");
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(nb)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 4, static_cast<cuuint64_t>(bstride) * 4};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  QV_REQUIRE(r == CUDA_SUCCESS, QV_ERR_CUDA, "cuTensorMapEncodeTiled(output) failed (%d)", (int)r);
+  return 0;
+}
+
+template <int BN, int NA, int NB, bool A_MN, bool B_MN>
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const GemmKParams& kp, int grid,
+           cudaStream_t st) {
+  using C = Cfg<BN, NA, NB>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(qv_gemm_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    attr_err = cudaFuncSetAttribute(qv_gemm_kernel<BN, NA, NB, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     C::SMEM_BYTES);
   });
   QV_REQUIRE(attr_err == cudaSuccess, QV_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
-  qv_gemm_kernel<BN, A_MN, B_MN><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mb, kp);
+  qv_gemm_kernel<BN, NA, NB, A_MN, B_MN><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mb, mo, kp);
   return qv_check_launch("qv_gemm_bf16");
+}
+
+template <int BN, int NA, int NB>
+int launch_major(bool amn, bool bmn, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo,
+                 const GemmKParams& kp, int grid, cudaStream_t st) {
+  if (!amn && !bmn) return launch<BN, NA, NB, false, false>(ma, mb, mo, kp, grid, st);
+  if (amn && bmn) return launch<BN, NA, NB, true, true>(ma, mb, mo, kp, grid, st);
+  if (!amn && bmn) return launch<BN, NA, NB, false, true>(ma, mb, mo, kp, grid, st);
+  return qv_set_error(QV_ERR_UNSUPPORTED, "operand layout (A MN-major, B K-major) is not instantiated");
+}
+
+template <int BN>
+int launch_planes(int na, int nb, bool amn, bool bmn, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo,
+                  const GemmKParams& kp, int grid, cudaStream_t st) {
+  if (na == 1 && nb == 1) return launch_major<BN, 1, 1>(amn, bmn, ma, mb, mo, kp, grid, st);
+  if (na == 2 && nb == 1) return launch_major<BN, 2, 1>(amn, bmn, ma, mb, mo, kp, grid, st);
+  if (na == 2 && nb == 2) return launch_major<BN, 2, 2>(amn, bmn, ma, mb, mo, kp, grid, st);
+  return qv_set_error(QV_ERR_UNSUPPORTED, "plane combination (%d A planes, %d B planes) is not instantiated", na, nb);
+}
+
+// N-tile choice: 192 divides every ViT-S/B projection width (384 .. 3072) with the best operand re-use; small or odd
+// widths (attention head slices, score matrices) take 64 / 128.
+int pick_bn(int64_t N) {
+  if (N <= 64) return 64;
+  if (N % 192 == 0) return 192;
+  if (N <= 128) return 128;
+  if (N % 128 == 0) return 128;
+  return (N > 1024) ? 192 : 128;
 }
 
 }  // namespace
@@ -356,25 +431,31 @@ extern "C" int qv_gemm_bf16(const qv_gemm_args* a, void* stream) {
   QV_REQUIRE(a != nullptr, QV_ERR_INVALID, "null args");
   QV_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, QV_ERR_INVALID, "empty gemm (M=%lld N=%lld K=%lld)", (long long)a->M,
              (long long)a->N, (long long)a->K);
-  QV_REQUIRE(a->npairs >= 1 && a->npairs <= 4, QV_ERR_INVALID, "npairs must be 1..4");
+  QV_REQUIRE(a->a_planes >= 1 && a->a_planes <= 2 && a->b_planes >= 1 && a->b_planes <= 2, QV_ERR_INVALID,
+             "a_planes / b_planes must be 1 or 2");
   const int splits = a->splits > 1 ? a->splits : 1;
   const int nbatch = a->nbatch > 1 ? a->nbatch : 1;
   QV_REQUIRE(!(splits > 1 && nbatch > 1), QV_ERR_UNSUPPORTED, "split-K and batching are mutually exclusive");
-  if (splits > 1) QV_REQUIRE(a->workspace != nullptr, QV_ERR_INVALID, "split-K needs a workspace");
-  else QV_REQUIRE(a->d != nullptr, QV_ERR_INVALID, "null output");
-  int pa_max = 0, pb_max = 0;
-  for (int i = 0; i < a->npairs; ++i) {
-    QV_REQUIRE(a->pair_a[i] >= 0 && a->pair_b[i] >= 0 && a->pair_a[i] < 8 && a->pair_b[i] < 8, QV_ERR_INVALID,
-               "bad plane index");
-    pa_max = a->pair_a[i] > pa_max ? a->pair_a[i] : pa_max;
-    pb_max = a->pair_b[i] > pb_max ? a->pair_b[i] : pb_max;
-  }
   QV_REQUIRE(qv_num_sms() > 0, QV_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
-  const int BN = 128;
-  CUtensorMap ma, mb;
-  int rc = make_map(&ma, a->a, pa_max + 1, a->a.mn_major ? 64 : BM);
+  const int BN = a->tile_n > 0 ? a->tile_n : pick_bn(a->N);
+  QV_REQUIRE(BN == 64 || BN == 128 || BN == 192, QV_ERR_UNSUPPORTED, "tile_n must be 64, 128 or 192");
+  CUtensorMap ma, mb, mo;
+  int rc = make_map(&ma, a->a, a->a_planes, a->a.mn_major ? 64 : BM);
   if (rc) return rc;
-  rc = make_map(&mb, a->b, pb_max + 1, a->b.mn_major ? 64 : BN);
+  rc = make_map(&mb, a->b, a->b_planes, a->b.mn_major ? 64 : BN);
+  if (rc) return rc;
+  if (splits > 1) {
+    QV_REQUIRE(a->workspace != nullptr, QV_ERR_INVALID, "split-K needs a workspace");
+    QV_REQUIRE(a->N % 4 == 0, QV_ERR_UNSUPPORTED, "split-K needs N to be a multiple of 4");
+    rc = make_out_map(&mo, a->workspace, a->N, a->M, a->N, splits, a->M * a->N);
+  } else {
+    const qv_out& o = a->out;
+    QV_REQUIRE(o.ptr != nullptr, QV_ERR_INVALID, "null output");
+    // a tile edge that is not the tensor edge must fall on a 32-column store box
+    QV_REQUIRE(a->N % 32 == 0 || (o.col_inner == 0 && o.col0 + a->N == o.cols), QV_ERR_UNSUPPORTED,
+               "N must be a multiple of 32 unless the output tile ends at the tensor edge");
+    rc = make_out_map(&mo, o.ptr, o.cols, o.rows, o.ld, o.nb, o.batch_stride);
+  }
   if (rc) return rc;
 
   GemmKParams kp;
@@ -382,8 +463,6 @@ extern "C" int qv_gemm_bf16(const qv_gemm_args* a, void* stream) {
   kp.M = a->M;
   kp.N = a->N;
   kp.kblocks = static_cast<int32_t>((a->K + BK - 1) / BK);
-  kp.npairs = a->npairs;
-  for (int i = 0; i < a->npairs; ++i) { kp.pair_a[i] = a->pair_a[i]; kp.pair_b[i] = a->pair_b[i]; }
   kp.tiles_m = static_cast<int32_t>((a->M + BM - 1) / BM);
   kp.tiles_n = static_cast<int32_t>((a->N + BN - 1) / BN);
   int sp = splits > kp.kblocks ? kp.kblocks : splits;
@@ -392,35 +471,33 @@ extern "C" int qv_gemm_bf16(const qv_gemm_args* a, void* stream) {
   QV_REQUIRE(splits == 1 || sp == splits, QV_ERR_INVALID,
              "split-K: %d splits over %d k-blocks leaves empty splits (use %d)", splits, kp.kblocks, sp);
   kp.splits = sp;
-  kp.d = a->d;
-  kp.ldd = a->ldd;
   kp.col_scale = a->col_scale;
   kp.col_rscale = a->col_rscale;
   kp.alpha = a->alpha;
   kp.bias = a->bias;
   kp.minmax = a->minmax;
-  kp.workspace = a->workspace;
   kp.nbatch = nbatch;
   kp.batch_inner = a->batch_inner > 0 ? a->batch_inner : 1;
   kp.a_c2_outer = a->a.c2_outer; kp.a_c2_inner = a->a.c2_inner; kp.a_col0 = a->a.col0; kp.a_col_inner = a->a.col_inner;
   kp.b_c2_outer = a->b.c2_outer; kp.b_c2_inner = a->b.c2_inner; kp.b_col0 = a->b.col0; kp.b_col_inner = a->b.col_inner;
-  kp.d_off_outer = a->d_off_outer;
-  kp.d_off_inner = a->d_off_inner;
+  kp.o_c2_outer = a->out.c2_outer; kp.o_c2_inner = a->out.c2_inner; kp.o_col0 = a->out.col0; kp.o_col_inner = a->out.col_inner;
   const int64_t items = static_cast<int64_t>(kp.tiles_m) * kp.tiles_n * (nbatch > 1 ? nbatch : kp.splits);
   QV_REQUIRE(items < (1LL << 31), QV_ERR_UNSUPPORTED, "too many tiles");
   const int sms = qv_num_sms();
   const int grid = static_cast<int>(items < sms ? items : sms);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool amn = a->a.mn_major != 0, bmn = a->b.mn_major != 0;
-  if (!amn && !bmn) return launch<128, false, false>(ma, mb, kp, grid, st);
-  if (amn && bmn) return launch<128, true, true>(ma, mb, kp, grid, st);
-  if (amn && !bmn) return launch<128, true, false>(ma, mb, kp, grid, st);
-  return launch<128, false, true>(ma, mb, kp, grid, st);
+  switch (BN) {
+    case 64: return launch_planes<64>(a->a_planes, a->b_planes, amn, bmn, ma, mb, mo, kp, grid, st);
+    case 128: return launch_planes<128>(a->a_planes, a->b_planes, amn, bmn, ma, mb, mo, kp, grid, st);
+    default: return launch_planes<192>(a->a_planes, a->b_planes, amn, bmn, ma, mb, mo, kp, grid, st);
+  }
 }
 
 extern "C" int qv_splitk_reduce(const float* workspace, int32_t splits, int64_t M, int64_t N, const float* row_rscale,
                                 const float* alpha, const uint8_t* mask, float* out, int32_t accumulate, void* stream) {
   QV_REQUIRE(workspace && out && splits >= 1 && M > 0 && N > 0, QV_ERR_INVALID, "bad splitk_reduce arguments");
+  QV_REQUIRE(qv_num_sms() > 0, QV_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
   const int64_t total = M * N;
   int blocks = static_cast<int>((total + 255) / 256);
   const int cap = qv_num_sms() * 8;

@@ -25,7 +25,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .ops import Op, PAIRS_EXACT_B, PAIRS_FP32, PAIRS_SINGLE
+from .ops import Op, Out, PAIRS_EXACT_B, PAIRS_FP32, PAIRS_SINGLE
 
 _INF = float("inf")
 
@@ -150,12 +150,11 @@ def _attention_forward(d: _ViTDims, qkvp: torch.Tensor, S: torch.Tensor, Pp: tor
     BH = B * H
     q_op = Op.tokens(qkvp, B, T, 0, 64)
     k_op = Op.tokens(qkvp, B, T, D, 64)
-    ops.gemm(q_op, k_op, T, T, 64, PAIRS_FP32, out=S, ldd=d.ldS, nbatch=BH, batch_inner=H,
-             d_off_outer=H * T * d.ldS, d_off_inner=T * d.ldS)
+    ops.gemm(q_op, k_op, T, T, 64, PAIRS_FP32, out=Out.per_head(S, BH, H, T, T), nbatch=BH, batch_inner=H)
     ops.softmax_planes(S, d.ldS, BH * T, T, d.attn_scale, Pp)
     p_op = Op.per_head(Pp, BH, H, T, T)
     v_op = Op.tokens(qkvp, B, T, 2 * D, 64, mn_major=True)
-    ops.gemm(p_op, v_op, T, 64, T, PAIRS_FP32, out=o, ldd=D, nbatch=BH, batch_inner=H, d_off_outer=T * D, d_off_inner=64)
+    ops.gemm(p_op, v_op, T, 64, T, PAIRS_FP32, out=Out.tokens(o, B, T, 0, 64), nbatch=BH, batch_inner=H)
 
 
 class TeacherEngine:
@@ -426,6 +425,7 @@ class StudentEngine:
 
     # ------------------------------------------------------------------------------------------
     def _wgrad(self, ql: _QLinear, gp: torch.Tensor, x_planes: torch.Tensor, kdim: int, pairs, alpha=None) -> None:
+        # pairs: (2,2) -> gp hi/lo x x hi/lo ; (2,1) -> gp hi/lo x exact codes
         """weight.grad[N,K] = mask * (gp'^T @ x) / scale[n]  (split-K over the token dimension, deterministic reduce)."""
         s = self._splits[(ql.N, ql.K)]
         if s > 1:
@@ -477,18 +477,16 @@ class StudentEngine:
             ops.split_planes(self.g_o, self.g_op)
             qkvp, Pp = self.qkvp[l], self.Pp[l]
             # dP = dO V^T
-            ops.gemm(Op.tokens(self.g_op, B, T, 0, 64), Op.tokens(qkvp, B, T, 2 * D, 64), T, T, 64, PAIRS_FP32, out=self.dP,
-                     ldd=d.ldS, nbatch=BH, batch_inner=H, d_off_outer=H * T * d.ldS, d_off_inner=T * d.ldS)
+            ops.gemm(Op.tokens(self.g_op, B, T, 0, 64), Op.tokens(qkvp, B, T, 2 * D, 64), T, T, 64, PAIRS_FP32,
+                     out=Out.per_head(self.dP, BH, H, T, T), nbatch=BH, batch_inner=H)
             ops.attn_ds(Pp, self.dP, d.ldS, BH * T, T, d.attn_scale, self.dSp)
             # dQ = dS K ; dK = dS^T Q ; dV = P^T dO   -> column blocks of g_qkv
             ops.gemm(Op.per_head(self.dSp, BH, H, T, T), Op.tokens(qkvp, B, T, D, 64, mn_major=True), T, 64, T, PAIRS_FP32,
-                     out=self.g_qkv, ldd=3 * D, nbatch=BH, batch_inner=H, d_off_outer=T * 3 * D, d_off_inner=64)
+                     out=Out.tokens(self.g_qkv, B, T, 0, 64), nbatch=BH, batch_inner=H)
             ops.gemm(Op.per_head(self.dSp, BH, H, T, T, mn_major=True), Op.tokens(qkvp, B, T, 0, 64, mn_major=True), T, 64, T,
-                     PAIRS_FP32, out=self.g_qkv[:, D:], ldd=3 * D, nbatch=BH, batch_inner=H, d_off_outer=T * 3 * D,
-                     d_off_inner=64)
+                     PAIRS_FP32, out=Out.tokens(self.g_qkv, B, T, D, 64), nbatch=BH, batch_inner=H)
             ops.gemm(Op.per_head(Pp, BH, H, T, T, mn_major=True), Op.tokens(self.g_op, B, T, 0, 64, mn_major=True), T, 64, T,
-                     PAIRS_FP32, out=self.g_qkv[:, 2 * D:], ldd=3 * D, nbatch=BH, batch_inner=H, d_off_outer=T * 3 * D,
-                     d_off_inner=64)
+                     PAIRS_FP32, out=Out.tokens(self.g_qkv, B, T, 2 * D, 64), nbatch=BH, batch_inner=H)
             self._gp(self.g_qkv, self.qkv_raw[l], ql["qkv"], False, M, self.gp3)
             self._dgrad(ql["qkv"], self.gp3, M, self.g_h)
             self._wgrad(ql["qkv"], self.gp3, self.h1p[l], M, PAIRS_FP32)

@@ -160,35 +160,67 @@ class Op:
         o.c2_outer, o.c2_inner, o.col0, o.col_inner = self.c2_outer, self.c2_inner, self.col0, self.col_inner
 
 
-PAIRS_EXACT_B = ((0, 0), (1, 0))            # A = fp32 as hi/lo, B = exact integer codes
-PAIRS_FP32 = ((0, 0), (0, 1), (1, 0))       # both operands fp32 as hi/lo (drops lo*lo, ~2^-16 relative)
-PAIRS_SINGLE = ((0, 0),)
+class Out:
+    """Where a GEMM writes: an fp32 tensor plus the batch-item mapping (struct qv_out)."""
+    __slots__ = ("t", "ptr", "ld", "rows", "cols", "nb", "batch_stride", "c2_outer", "c2_inner", "col0", "col_inner")
+
+    def __init__(self, t, rows, cols, ld, nb=1, batch_stride=0, c2_outer=0, c2_inner=0, col0=0, col_inner=0):
+        if t.dtype != torch.float32 or not t.is_cuda:
+            raise RuntimeError("qatvit_b200: GEMM output must be a CUDA fp32 tensor (no CPU fallback)")
+        self.t, self.ptr = t, t.data_ptr()
+        self.rows, self.cols, self.ld, self.nb, self.batch_stride = rows, cols, ld, nb, batch_stride
+        self.c2_outer, self.c2_inner, self.col0, self.col_inner = c2_outer, c2_inner, col0, col_inner
+
+    @staticmethod
+    def full(t: torch.Tensor) -> "Out":
+        assert t.dim() == 2 and t.stride(1) == 1
+        return Out(t, t.shape[0], t.shape[1], t.stride(0))
+
+    @staticmethod
+    def tokens(t: torch.Tensor, B: int, T: int, col0: int, col_inner: int) -> "Out":
+        """t: [B*T, W]; item (b, h) -> rows of image b, columns col0 + h*col_inner."""
+        assert t.dim() == 2 and t.stride(1) == 1 and t.shape[0] == B * T
+        return Out(t, T, t.shape[1], t.stride(0), nb=B, batch_stride=T * t.stride(0), c2_outer=1, c2_inner=0, col0=col0,
+                   col_inner=col_inner)
+
+    @staticmethod
+    def per_head(t: torch.Tensor, BH: int, H: int, T: int, cols: int) -> "Out":
+        """t: [B*H*T, ld]; one [T, cols] matrix per (image, head)."""
+        assert t.dim() == 2 and t.stride(1) == 1 and t.shape[0] == BH * T
+        return Out(t, T, cols, t.stride(0), nb=BH, batch_stride=T * t.stride(0), c2_outer=H, c2_inner=1)
+
+    def fill(self, o) -> None:
+        o.ptr, o.ld, o.rows, o.cols, o.nb, o.batch_stride = self.ptr, self.ld, self.rows, self.cols, self.nb, self.batch_stride
+        o.c2_outer, o.c2_inner, o.col0, o.col_inner = self.c2_outer, self.c2_inner, self.col0, self.col_inner
 
 
-def gemm(a: Op, b: Op, M: int, N: int, K: int, pairs: Sequence[Tuple[int, int]], *, out: Optional[torch.Tensor] = None,
-         ldd: Optional[int] = None, col_scale=None, col_rscale=None, alpha=None, bias=None, minmax=None,
-         splits: int = 1, workspace: Optional[torch.Tensor] = None, nbatch: int = 1, batch_inner: int = 1,
-         d_off_outer: int = 0, d_off_inner: int = 0) -> Optional[torch.Tensor]:
-    """D[M,N] = sum_pairs A[pa] @ B[pb]^T on tcgen05 (include/qatvit_b200.h: qv_gemm_bf16)."""
+# (a_planes, b_planes): which hi/lo plane products the tensor cores accumulate
+PAIRS_SINGLE = (1, 1)        # exact integer codes on both sides (patch-embed conv forward)
+PAIRS_EXACT_B = (2, 1)       # A = fp32 as hi/lo, B = exact integer codes: A0*B + A1*B
+PAIRS_FP32 = (2, 2)          # both fp32 as hi/lo: A0*B0 + A0*B1 + A1*B0 (lo*lo dropped, ~2^-16 relative)
+
+
+def gemm(a: Op, b: Op, M: int, N: int, K: int, planes: Tuple[int, int], *, out=None, col_scale=None, col_rscale=None,
+         alpha=None, bias=None, minmax=None, splits: int = 1, workspace: Optional[torch.Tensor] = None, nbatch: int = 1,
+         batch_inner: int = 1, tile_n: int = 0):
+    """D[M,N] = sum_pairs A[pa] @ B[pb]^T on tcgen05 (include/qatvit_b200.h: qv_gemm_bf16).
+    out: an ``Out`` descriptor, a 2-D fp32 tensor, or None (allocated)."""
     args = GemmArgs()
     a.fill(args.a)
     b.fill(args.b)
-    args.npairs = len(pairs)
-    for i, (pa, pb) in enumerate(pairs):
-        args.pair_a[i] = pa
-        args.pair_b[i] = pb
+    args.a_planes, args.b_planes = planes
     args.M, args.N, args.K = M, N, K
+    ret = None
     if splits <= 1:
         if out is None:
             out = torch.empty(M, N, dtype=torch.float32, device=a.t.device)
-        if out.dtype != torch.float32 or not out.is_cuda:
-            raise RuntimeError("qatvit_b200: GEMM output must be CUDA fp32")
-        args.d = out.data_ptr()
-        args.ldd = ldd if ldd is not None else out.stride(-2)
+        ret = out.t if isinstance(out, Out) else out
+        (out if isinstance(out, Out) else Out.full(out)).fill(args.out)
     else:
         if workspace is None:
             workspace = torch.empty(splits, M, N, dtype=torch.float32, device=a.t.device)
         args.workspace = workspace.data_ptr()
+        ret = workspace
     args.col_scale = None if col_scale is None else col_scale.data_ptr()
     args.col_rscale = None if col_rscale is None else col_rscale.data_ptr()
     args.alpha = None if alpha is None else alpha.data_ptr()
@@ -196,9 +228,9 @@ def gemm(a: Op, b: Op, M: int, N: int, K: int, pairs: Sequence[Tuple[int, int]],
     args.minmax = None if minmax is None else minmax.data_ptr()
     args.splits = splits
     args.nbatch, args.batch_inner = nbatch, batch_inner
-    args.d_off_outer, args.d_off_inner = d_off_outer, d_off_inner
+    args.tile_n = tile_n
     check(_lib.lib().qv_gemm_bf16(ctypes.byref(args), _stream()), "gemm_bf16")
-    return out if splits <= 1 else workspace
+    return ret
 
 
 def splitk_reduce(workspace, splits, M, N, out, row_rscale=None, alpha=None, mask=None, accumulate=False):

@@ -5,6 +5,7 @@ import sys
 import os
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TILE_N = int(os.environ.get("QV_TILE_N", "0"))
 
 CASES = {
     # name: (M, N, K, a_mn, b_mn, planes_a, planes_b, pairs, splits)
@@ -12,12 +13,18 @@ CASES = {
     "kk_mid": (1024, 384, 384, 0, 0, 1, 1, [(0, 0)], 1),
     "kk_ragged": (1576, 1152, 384, 0, 0, 2, 1, [(0, 0), (1, 0)], 1),
     "kk_3pair": (1000, 768, 768, 0, 0, 2, 2, [(0, 0), (0, 1), (1, 0)], 1),
-    "kk_big": (50432, 1152, 384, 0, 0, 2, 1, [(0, 0), (1, 0)], 1),
+    "kk_n64": (333, 64, 197, 0, 0, 2, 2, [(0, 0), (0, 1), (1, 0)], 1),
+    "kk_n197": (197, 197, 64, 0, 0, 2, 2, [(0, 0), (0, 1), (1, 0)], 1),
+    "qkv_fwd": (50432, 1152, 384, 0, 0, 2, 1, [(0, 0), (1, 0)], 1),
+    "fc1_fwd": (50432, 1536, 384, 0, 0, 2, 1, [(0, 0), (1, 0)], 1),
+    "fc2_fwd": (50432, 384, 1536, 0, 0, 2, 1, [(0, 0), (1, 0)], 1),
+    "t_qkv": (50432, 2304, 768, 0, 0, 2, 2, [(0, 0), (0, 1), (1, 0)], 1),
+    "t_fc2": (50432, 768, 3072, 0, 0, 2, 2, [(0, 0), (0, 1), (1, 0)], 1),
     "mn_small": (128, 128, 64, 1, 1, 1, 1, [(0, 0)], 1),
     "mn_mid": (384, 1536, 1576, 1, 1, 2, 2, [(0, 0), (0, 1), (1, 0)], 1),
-    "mn_split": (1152, 384, 50432, 1, 1, 2, 2, [(0, 0), (0, 1), (1, 0)], 8),
-    "a_mn_only": (256, 256, 256, 1, 0, 1, 1, [(0, 0)], 1),
-    "b_mn_only": (256, 256, 256, 0, 1, 1, 1, [(0, 0)], 1),
+    "wgrad_qkv": (1152, 384, 50432, 1, 1, 2, 2, [(0, 0), (0, 1), (1, 0)], 11),
+    "wgrad_fc1": (1536, 384, 50432, 1, 1, 2, 2, [(0, 0), (0, 1), (1, 0)], 8),
+    "b_mn_only": (256, 256, 256, 0, 1, 2, 2, [(0, 0), (0, 1), (1, 0)], 1),
 }
 
 
@@ -49,11 +56,11 @@ def run_case(name):
     mm = ops.new_minmax(dev)
     torch.cuda.synchronize()
     if splits == 1:
-        out = ops.gemm(a_in, b_in, M, N, K, pairs, a_mn_major=bool(a_mn), b_mn_major=bool(b_mn), col_scale=cs, bias=bias,
-                       minmax=mm)
+        out = ops.gemm(ops.Op.full(a_in, bool(a_mn)), ops.Op.full(b_in, bool(b_mn)), M, N, K, (pa, pb), col_scale=cs, bias=bias,
+                       minmax=mm, tile_n=TILE_N)
         ref = ref * cs.double()[None, :] + bias.double()[None, :]
     else:
-        ws = ops.gemm(a_in, b_in, M, N, K, pairs, a_mn_major=bool(a_mn), b_mn_major=bool(b_mn), splits=splits)
+        ws = ops.gemm(ops.Op.full(a_in, bool(a_mn)), ops.Op.full(b_in, bool(b_mn)), M, N, K, (pa, pb), splits=splits, tile_n=TILE_N)
         out = torch.empty(M, N, device=dev)
         ops.splitk_reduce(ws, splits, M, N, out)
     torch.cuda.synchronize()
@@ -72,18 +79,18 @@ def run_case(name):
     if M * N * K > 1e9:
         st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for _ in range(3):
-            ops.gemm(a_in, b_in, M, N, K, pairs, a_mn_major=bool(a_mn), b_mn_major=bool(b_mn), splits=splits,
-                     workspace=ws if splits > 1 else None, out=out if splits == 1 else None)
+            ops.gemm(ops.Op.full(a_in, bool(a_mn)), ops.Op.full(b_in, bool(b_mn)), M, N, K, (pa, pb), splits=splits,
+                     workspace=ws if splits > 1 else None, out=out if splits == 1 else None, tile_n=TILE_N)
         st.record()
         for _ in range(10):
-            ops.gemm(a_in, b_in, M, N, K, pairs, a_mn_major=bool(a_mn), b_mn_major=bool(b_mn), splits=splits,
-                     workspace=ws if splits > 1 else None, out=out if splits == 1 else None)
+            ops.gemm(ops.Op.full(a_in, bool(a_mn)), ops.Op.full(b_in, bool(b_mn)), M, N, K, (pa, pb), splits=splits,
+                     workspace=ws if splits > 1 else None, out=out if splits == 1 else None, tile_n=TILE_N)
         en.record()
         torch.cuda.synchronize()
         ms = st.elapsed_time(en) / 10
         fl = 2.0 * M * N * K * len(pairs)
-        msg += f" time={ms*1e3:.1f}us bf16_TFLOPs={fl/ms/1e9:.1f}"
-    print(msg, "OK" if rel < 2e-5 else "FAIL", flush=True)
+        msg += f" time={ms*1e3:.1f}us bf16_TFLOPs={fl/ms/1e9:.1f} alg_TFLOPs={2.0*M*N*K/ms/1e9:.1f} tile_n={TILE_N}"
+    print(msg, "OK" if rel < 5e-5 else "FAIL", flush=True)
 
 
 if __name__ == "__main__":
