@@ -190,7 +190,22 @@ def run_ours(args):
     batch = global_batch // n
 
     student, teacher = build_models(batch, dev)
-    step = QATDistillStep(student, teacher, batch, HP)
+    sync = None
+    if world > 1:
+        from qatvit_b200.ddp import GradSync
+        # every rank starts from rank 0's weights, like DDP's constructor broadcast (ref :311)
+        for t in list(student.parameters()) + list(student.buffers()):
+            dist.broadcast(t.data, src=0)
+        # one flat buffer: [gradients | activation-observer min/max tail]; built before the engine so .grad views alias it
+        n_grad = QATDistillStep.count_trainable(student)
+        n_obs = 2 + 4 * len(student.model.blocks) + 1
+        sync = GradSync(n_grad, [], dev)
+        sync.flat = torch.zeros(n_grad + 2 * n_obs, device=dev)
+        sync.n_tail = 2 * n_obs
+        step = QATDistillStep(student, teacher, batch, HP, grad_buffer=sync.grad_arena)
+        sync.observers = step.activation_observers()
+    else:
+        step = QATDistillStep(student, teacher, batch, HP)
     opt = torch.optim.AdamW(student.parameters(), lr=HP["lr"] * 0.5, weight_decay=HP["weight_decay"])   # ref :315
     arena = step.grad_arena
 
@@ -203,8 +218,9 @@ def run_ours(args):
 
     def train_step(img, lab):
         out3 = step(img, lab)                                  # teacher fwd, student fwd, loss, bwd  (our kernels)
-        if world > 1:
-            dist.all_reduce(arena)                             # the one collective of the path (NCCL over NVLink)
+        if sync is not None:
+            sync.all_reduce()                                  # the one exchange of the path: NCCL SUM over NVLink of
+                                                               # [grads | rank-0 observer state] (qatvit_b200/ddp.py)
         clip_arena_(arena, 1.0, 1.0 / world)                   # ref :360 (+ DDP mean)
         opt.step()                                             # ref :361
         return out3

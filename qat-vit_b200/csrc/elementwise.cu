@@ -176,14 +176,24 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ g
   }
 }
 
-// out[c] (+)= sum_b partials[b][c]
-__global__ void colsum_reduce_kernel(const float* __restrict__ partials, int nblk, int64_t ncols, float* __restrict__ out,
-                                     int accumulate) {
-  const int64_t c = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  if (c >= ncols) return;
+// out[c] (+)= sum_b partials[b][c].  Block = 32 columns x 8 row slices (128-byte coalesced row reads), fixed-order
+// combine so the result is deterministic.
+__global__ void __launch_bounds__(256) colsum_reduce_kernel(const float* __restrict__ partials, int nblk, int64_t ncols,
+                                                            float* __restrict__ out, int accumulate) {
+  __shared__ float sm[8][32];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int64_t c = blockIdx.x * 32LL + cx;
   float s = 0.f;
-  for (int b = 0; b < nblk; ++b) s += partials[static_cast<int64_t>(b) * ncols + c];
-  out[c] = accumulate ? out[c] + s : s;
+  if (c < ncols)
+    for (int b = ry; b < nblk; b += 8) s += __ldg(partials + static_cast<int64_t>(b) * ncols + c);
+  sm[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0 && c < ncols) {
+    float t = sm[0][cx];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) t += sm[k][cx];
+    out[c] = accumulate ? out[c] + t : t;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -529,7 +539,7 @@ extern "C" int qv_colsum_reduce(const float* partials, int32_t nblk, int64_t nco
                                 void* stream) {
   QV_REQUIRE(partials && out && nblk > 0 && ncols > 0, QV_ERR_INVALID, "bad colsum_reduce arguments");
   QV_NEED_GPU();
-  colsum_reduce_kernel<<<static_cast<unsigned>((ncols + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  colsum_reduce_kernel<<<static_cast<unsigned>((ncols + 31) / 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       partials, nblk, ncols, out, accumulate);
   return qv_check_launch("qv_colsum_reduce");
 }

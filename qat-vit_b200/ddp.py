@@ -1,0 +1,86 @@
+"""Data-parallel glue for the fused step: ONE exchange per iteration.
+
+The reference wraps the prepared student in ``DistributedDataParallel`` (ref/src/training/qat_trainer.py:310-313), which
+(a) averages gradients with bucketed NCCL all-reduces during backward and (b) broadcasts every buffer -- i.e. the
+observer state -- from rank 0 at each forward entry (torch/nn/parallel/distributed.py:1590-1591).
+
+Here the engine writes all gradients into one flat fp32 arena; ``GradSync`` all-reduces it (SUM; the 1/world is folded
+into the clip pass) and piggy-backs rank 0's activation-observer running min/max in the tail of the same buffer:
+rank 0 contributes its values, every other rank contributes zeros, so after the SUM every rank holds rank 0's state
+exactly -- the DDP buffer-broadcast semantics without a second collective.  (scale / zero_point are a deterministic
+function of min/max and are recomputed on the next forward; weight observers see identical weights on every rank.)
+Works with any torch.distributed backend (nccl on the B200 box, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+class GradSync:
+    def __init__(self, n_grad: int, observers: Sequence[Tuple[torch.Tensor, torch.Tensor]], device, dtype=torch.float32,
+                 bucket_bytes: int = 32 << 20):
+        """observers: [(min_val, max_val)] tensors (0-dim or [1]) of the activation fake-quant modules."""
+        self.n_grad = n_grad
+        self.observers = list(observers)
+        self.n_tail = 2 * len(self.observers)
+        self.flat = torch.zeros(n_grad + self.n_tail, dtype=dtype, device=device)
+        self.bucket_elems = max(1, bucket_bytes // 4)
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+
+    @property
+    def grad_arena(self) -> torch.Tensor:
+        return self.flat[:self.n_grad]
+
+    @property
+    def tail(self) -> torch.Tensor:
+        return self.flat[self.n_grad:]
+
+    def pack_observers(self) -> None:
+        if self.n_tail == 0:
+            return
+        if self.rank == 0:
+            vals = [t.reshape(1) for pair in self.observers for t in pair]
+            torch.cat(vals, out=self.tail)
+        else:
+            self.tail.zero_()
+
+    def unpack_observers(self) -> None:
+        if self.n_tail == 0 or self.world == 1:
+            return
+        t = self.tail
+        for i, (mn, mx) in enumerate(self.observers):
+            mn.copy_(t[2 * i].reshape(mn.shape))
+            mx.copy_(t[2 * i + 1].reshape(mx.shape))
+
+    def buckets(self) -> List[Tuple[int, int]]:
+        """[start, end) element ranges, last bucket first (gradients are produced head -> patch-embed)."""
+        total = self.flat.numel()
+        out, end = [], total
+        while end > 0:
+            start = max(0, end - self.bucket_elems)
+            out.append((start, end))
+            end = start
+        return out
+
+    def all_reduce(self, async_op: bool = False):
+        """SUM over ranks of gradients + observer tail.  Returns the list of work handles when async."""
+        if self.world == 1:
+            return []
+        self.pack_observers()
+        works = []
+        for (s, e) in self.buckets():
+            w = dist.all_reduce(self.flat[s:e], op=dist.ReduceOp.SUM, async_op=async_op)
+            if async_op:
+                works.append(w)
+        if not async_op:
+            self.unpack_observers()
+        return works
+
+    def finish(self, works) -> None:
+        for w in works:
+            w.wait()
+        self.unpack_observers()

@@ -248,7 +248,7 @@ class TeacherEngine:
 class StudentEngine:
     """Forward + hand-written backward of the prepared (torch.ao eager-mode QAT) ``QATWrapper`` student."""
 
-    def __init__(self, student: nn.Module, batch: int, hparams: Dict):
+    def __init__(self, student: nn.Module, batch: int, hparams: Dict, grad_buffer: Optional[torch.Tensor] = None):
         self.student = student
         vit = self.vit = student.model
         dev = next(student.parameters()).device
@@ -283,7 +283,12 @@ class StudentEngine:
         # ---- flat gradient arena (the buffer a DDP-style all-reduce runs over) ----
         self.params = [p for p in student.parameters() if p.requires_grad]
         total = sum(p.numel() for p in self.params)
-        self.grad_arena = torch.zeros(total, dtype=f32, device=dev)
+        if grad_buffer is not None:      # e.g. the head of a ddp.GradSync buffer (gradients + observer tail)
+            if grad_buffer.numel() != total or grad_buffer.dtype != f32 or grad_buffer.device != dev:
+                raise ValueError("grad_buffer must be a flat fp32 tensor with one element per trainable parameter")
+            self.grad_arena = grad_buffer
+        else:
+            self.grad_arena = torch.zeros(total, dtype=f32, device=dev)
         self._grad_views = []
         off = 0
         self._goff = {}
@@ -333,7 +338,7 @@ class StudentEngine:
         self.g_qkv = e(M, 3 * D)
         self.dP = e(B * d.H * T, d.ldS)
         self.dSp = torch.zeros(2, B * d.H * T, d.ldP, dtype=bf, device=dev)
-        self.rpb_gp = 32
+        self.rpb_gp = 64
         self.rpb_ln = 64
         self.bias_part = e(-(-M // self.rpb_gp), max(F, 3 * D))
         self.ln_part = e(-(-M // self.rpb_ln), 2, D)
@@ -504,8 +509,9 @@ class QATDistillStep:
     """One object per (student, teacher, batch size): ``loss = step(images, labels)`` runs teacher forward, student
     forward, loss and backward on the current stream and leaves gradients in ``student`` parameters' ``.grad``."""
 
-    def __init__(self, student: nn.Module, teacher: nn.Module, batch: int, hparams: Dict):
-        self.student_engine = StudentEngine(student, batch, hparams)
+    def __init__(self, student: nn.Module, teacher: nn.Module, batch: int, hparams: Dict,
+                 grad_buffer: Optional[torch.Tensor] = None):
+        self.student_engine = StudentEngine(student, batch, hparams, grad_buffer=grad_buffer)
         self.teacher_engine = TeacherEngine(teacher, batch)
         self.grad_arena = self.student_engine.grad_arena
 
@@ -518,3 +524,13 @@ class QATDistillStep:
     @property
     def student_logits_raw(self) -> torch.Tensor:
         return self.student_engine.logits_raw
+
+    def activation_observers(self):
+        """[(min_val, max_val)] of every activation fake-quant, in forward order (for ddp.GradSync)."""
+        se = self.student_engine
+        fqs = [se.fq_in, se.conv.afq] + [ql[k].afq for ql in se.lin for k in ("qkv", "proj", "fc1", "fc2")] + [se.head.afq]
+        return [(f.min_val, f.max_val) for f in fqs]
+
+    @staticmethod
+    def count_trainable(student: nn.Module) -> int:
+        return sum(p.numel() for p in student.parameters() if p.requires_grad)

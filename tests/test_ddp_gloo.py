@@ -1,0 +1,49 @@
+"""CPU, world_size 2, gloo: the one exchange step of the data-parallel path (qatvit_b200/ddp.py) -- gradient SUM over
+ranks plus rank-0-authoritative observer state piggy-backed on the same buffer."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, async_op, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import qatvit_b200  # noqa: F401
+    from qatvit_b200.ddp import GradSync
+    torch.manual_seed(100 + rank)
+    obs = [(torch.tensor(float(-1 - rank - i)), torch.tensor(float(1 + rank + i))) for i in range(5)]
+    gs = GradSync(1000, obs, device="cpu", bucket_bytes=1024)      # several buckets
+    g = torch.randn(1000)
+    gs.grad_arena.copy_(g)
+    works = gs.all_reduce(async_op=async_op)
+    if async_op:
+        gs.finish(works)
+    q.put((rank, g, gs.grad_arena.clone(), [(float(a), float(b)) for a, b in obs]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("async_op", [False, True])
+def test_gradient_sum_and_rank0_observer_state(async_op):
+    world, port = 2, 29000 + os.getpid() % 2000 + (1 if async_op else 0)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, async_op, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    total = res[0][1] + res[1][1]
+    for rank, _, reduced, obs in res:
+        assert torch.allclose(reduced, total, atol=1e-6)                  # SUM; the 1/world is applied in the clip pass
+        assert obs == [(float(-1 - i), float(1 + i)) for i in range(5)]   # everyone ends with rank 0's running min/max
