@@ -195,15 +195,14 @@ def run_ours(args):
         from qatvit_b200.ddp import GradSync
         # every rank starts from rank 0's weights, like DDP's constructor broadcast (ref :311)
         for t in list(student.parameters()) + list(student.buffers()):
-            dist.broadcast(t.data, src=0)
+            if t.numel() > 0:
+                dist.broadcast(t.data, src=0)
         # one flat buffer: [gradients | activation-observer min/max tail]; built before the engine so .grad views alias it
         n_grad = QATDistillStep.count_trainable(student)
         n_obs = 2 + 4 * len(student.model.blocks) + 1
-        sync = GradSync(n_grad, [], dev)
-        sync.flat = torch.zeros(n_grad + 2 * n_obs, device=dev)
-        sync.n_tail = 2 * n_obs
+        sync = GradSync(n_grad, n_obs, dev)
         step = QATDistillStep(student, teacher, batch, HP, grad_buffer=sync.grad_arena)
-        sync.observers = step.activation_observers()
+        sync.bind_observers(step.activation_observers())
     else:
         step = QATDistillStep(student, teacher, batch, HP)
     opt = torch.optim.AdamW(student.parameters(), lr=HP["lr"] * 0.5, weight_decay=HP["weight_decay"])   # ref :315

@@ -20,16 +20,22 @@ import torch.distributed as dist
 
 
 class GradSync:
-    def __init__(self, n_grad: int, observers: Sequence[Tuple[torch.Tensor, torch.Tensor]], device, dtype=torch.float32,
-                 bucket_bytes: int = 32 << 20):
-        """observers: [(min_val, max_val)] tensors (0-dim or [1]) of the activation fake-quant modules."""
+    def __init__(self, n_grad: int, n_observers: int, device, dtype=torch.float32, bucket_bytes: int = 32 << 20):
+        """One flat buffer [n_grad gradients | 2*n_observers running min/max].  Build the engine on ``grad_arena`` and
+        then ``bind_observers`` the (min_val, max_val) buffers of the activation fake-quant modules."""
         self.n_grad = n_grad
-        self.observers = list(observers)
-        self.n_tail = 2 * len(self.observers)
+        self.observers: List[Tuple[torch.Tensor, torch.Tensor]] = []
+        self.n_tail = 2 * n_observers
         self.flat = torch.zeros(n_grad + self.n_tail, dtype=dtype, device=device)
         self.bucket_elems = max(1, bucket_bytes // 4)
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.rank = dist.get_rank() if dist.is_initialized() else 0
+
+    def bind_observers(self, observers: Sequence[Tuple[torch.Tensor, torch.Tensor]]) -> None:
+        observers = list(observers)
+        if 2 * len(observers) != self.n_tail:
+            raise ValueError(f"expected {self.n_tail // 2} observers, got {len(observers)}")
+        self.observers = observers
 
     @property
     def grad_arena(self) -> torch.Tensor:
@@ -42,6 +48,8 @@ class GradSync:
     def pack_observers(self) -> None:
         if self.n_tail == 0:
             return
+        if len(self.observers) * 2 != self.n_tail:
+            raise RuntimeError("GradSync.bind_observers() has not been called")
         if self.rank == 0:
             vals = [t.reshape(1) for pair in self.observers for t in pair]
             torch.cat(vals, out=self.tail)

@@ -20,7 +20,8 @@ def _worker(rank, world, port, async_op, q):
     from qatvit_b200.ddp import GradSync
     torch.manual_seed(100 + rank)
     obs = [(torch.tensor(float(-1 - rank - i)), torch.tensor(float(1 + rank + i))) for i in range(5)]
-    gs = GradSync(1000, obs, device="cpu", bucket_bytes=1024)      # several buckets
+    gs = GradSync(1000, len(obs), device="cpu", bucket_bytes=1024)      # several buckets
+    gs.bind_observers(obs)
     g = torch.randn(1000)
     gs.grad_arena.copy_(g)
     works = gs.all_reduce(async_op=async_op)
