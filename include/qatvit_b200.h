@@ -124,6 +124,11 @@ typedef struct qv_gemm_args {
   int32_t splits; float* workspace;
   int32_t nbatch, batch_inner;
   int32_t tile_n;               /* 0 = auto; else 64 / 128 / 192 */
+  /* out_kind = 1: `out.ptr` is a bf16 hi/lo plane stack [2][nb][rows][ld] (ld in bf16 elements, planes out_plane_stride
+   * elements apart) -- the operand format of the next GEMM -- written straight from the epilogue, so a producer/consumer
+   * pair of Linears with no observer in between (the teacher) never round-trips fp32 through HBM.
+   * act = 1: exact-erf GELU after scale/bias (timm Mlp.act fused into fc1's epilogue); needs out_kind = 1. */
+  int32_t out_kind; int32_t act; int64_t out_plane_stride;
 } qv_gemm_args;
 int qv_gemm_bf16(const qv_gemm_args* args, void* stream);
 

@@ -52,6 +52,7 @@ class GemmArgs(ctypes.Structure):
         ("minmax", c_void_p),
         ("splits", c_int32), ("workspace", c_void_p),
         ("nbatch", c_int32), ("batch_inner", c_int32), ("tile_n", c_int32),
+        ("out_kind", c_int32), ("act", c_int32), ("out_plane_stride", c_int64),
     ]
 
 

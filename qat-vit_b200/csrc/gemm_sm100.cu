@@ -32,8 +32,9 @@ constexpr int BK = 64;            // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 192;
 constexpr int A_PLANE_BYTES = BM * BK * 2;
-constexpr int EPI_WARP_BYTES = 2 * 32 * 128;   // two 32-row x 128-byte staging buffers per epilogue warp
-constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;
+// epilogue staging per warp: 32-row x 128-byte buffers, double-buffered.  fp32 output: one buffer per 32-column chunk;
+// bf16 hi/lo plane output: a hi and a lo buffer per 64-column chunk.
+constexpr int epi_warp_bytes(int epi) { return (epi == 1 ? 4 : 2) * 32 * 128; }
 constexpr int SMEM_LIMIT = 232448;             // 227 KB
 
 struct GemmKParams {
@@ -50,12 +51,15 @@ struct GemmKParams {
   int32_t a_c2_outer, a_c2_inner, a_col0, a_col_inner;
   int32_t b_c2_outer, b_c2_inner, b_col0, b_col_inner;
   int32_t o_c2_outer, o_c2_inner, o_col0, o_col_inner;
+  int32_t act;            // 0 = none, 1 = exact-erf GELU (applied after scale / bias)
 };
 
-template <int BN, int NA, int NB>
+template <int BN, int NA, int NB, int EPI = 0>
 struct Cfg {
   static constexpr int B_PLANE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = NA * A_PLANE_BYTES + NB * B_PLANE_BYTES;
+  static constexpr int EPI_WARP_BYTES = epi_warp_bytes(EPI);
+  static constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;
   static constexpr int MAX_STAGES = (SMEM_LIMIT - 1024 - 256 - EPI_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = MAX_STAGES > 6 ? 6 : MAX_STAGES;
   static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
@@ -63,13 +67,23 @@ struct Cfg {
   static constexpr int NPAIRS = (NA == 2 && NB == 2) ? 3 : NA * NB;   // (hi,hi) (hi,lo) (lo,hi): lo*lo is dropped
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN must be a multiple of 32 up to 256");
+  static_assert(EPI == 0 || BN % 64 == 0, "plane output works on 64-column chunks");
 };
 
-template <int BN, int NA, int NB, bool A_MN, bool B_MN>
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return static_cast<uint32_t>(__bfloat16_as_ushort(a)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
+}
+
+// EPI = 0: fp32 output;  EPI = 1: bf16 hi/lo plane output (the operand format of the next GEMM), optional GELU.
+template <int BN, int NA, int NB, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_o, const GemmKParams p) {
-  using C = Cfg<BN, NA, NB>;
+  using C = Cfg<BN, NA, NB, EPI>;
+  constexpr int EPI_WARP_BYTES = C::EPI_WARP_BYTES;
+  constexpr int EPI_BYTES = C::EPI_BYTES;
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle atoms need 1024-byte aligned tile bases
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -218,6 +232,71 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tc_fence_after();
       const int row0 = m_blk * BM + q * 32;                     // first row of this warp's 32-row slab
       const bool row_ok = static_cast<int64_t>(row0 + lane) < p.M;
+      if constexpr (EPI == 1) {
+        // ---- bf16 hi/lo plane output: 64 columns per step -> one 32x128B hi box and one lo box ----
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 64) {
+          const int64_t n0 = static_cast<int64_t>(n_blk) * BN + c0;
+          const bool live = n0 < p.N && static_cast<int64_t>(row0) < p.M;       // warp-uniform
+          uint8_t* sbuf = my_epi + (chunk_ctr & 1) * 8192;                       // [hi 4 KB][lo 4 KB]
+          if (live) {
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+          }
+          const uint32_t srow_hi = smem_u32(sbuf) + lane * 128, srow_lo = srow_hi + 4096;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN + c0 + half * 32), r);
+            tmem_ld_wait();
+            if (half == 1 && c0 + 64 >= BN) {
+              tc_fence_before();
+              mbar_arrive(&tmem_empty[buf]);
+            }
+            if (!live) continue;
+            float my_mult = 1.0f, my_bias = 0.0f;
+            {
+              const int64_t n = n0 + half * 32 + lane;
+              if (n < p.N) {
+                my_mult = alpha;
+                if (p.col_scale) my_mult *= __ldg(p.col_scale + n);
+                if (p.col_rscale) my_mult = __fdiv_rn(my_mult, __ldg(p.col_rscale + n));
+                if (p.bias) my_bias = __ldg(p.bias + n);
+              }
+            }
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              float a0 = __uint_as_float(r[j]) * __shfl_sync(0xffffffffu, my_mult, j) + __shfl_sync(0xffffffffu, my_bias, j);
+              float a1 = __uint_as_float(r[j + 1]) * __shfl_sync(0xffffffffu, my_mult, j + 1) +
+                         __shfl_sync(0xffffffffu, my_bias, j + 1);
+              if (p.act == 1) { a0 = gelu_erf(a0); a1 = gelu_erf(a1); }
+              __nv_bfloat16 h0, l0, h1, l1;
+              qv_split_bf16(a0, h0, l0);
+              qv_split_bf16(a1, h1, l1);
+              hi[j >> 1] = pack_bf16x2(h0, h1);
+              lo[j >> 1] = pack_bf16x2(l0, l1);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t sw = (static_cast<uint32_t>((half * 4 + j) ^ (lane & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow_hi + sw), "r"(hi[4 * j]), "r"(hi[4 * j + 1]),
+                           "r"(hi[4 * j + 2]), "r"(hi[4 * j + 3]) : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow_lo + sw), "r"(lo[4 * j]), "r"(lo[4 * j + 1]),
+                           "r"(lo[4 * j + 2]), "r"(lo[4 * j + 3]) : "memory");
+            }
+          }
+          if (!live) continue;
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&map_o, sbuf, o_col + static_cast<int>(n0), row0, o_c2, 0);
+            tma_store_4d(&map_o, sbuf + 4096, o_col + static_cast<int>(n0), row0, o_c2, 1);
+            tma_store_commit();
+          }
+          ++chunk_ctr;
+        }
+      } else {
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
@@ -274,6 +353,7 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           tma_store_commit();
         }
         ++chunk_ctr;
+      }
       }
     }
     if (lane == 0) tma_store_wait_read<0>();
@@ -382,18 +462,41 @@ int make_out_map(CUtensorMap* m, float* ptr, int64_t cols, int64_t rows, int64_t
   return 0;
 }
 
-template <int BN, int NA, int NB, bool A_MN, bool B_MN>
+// bf16 hi/lo plane output [2][nb][rows][ld] as a 4-D tensor (cols, rows, nb, plane); store box = (64 cols = 128 B, 32 rows).
+int make_out_planes_map(CUtensorMap* m, void* ptr, int64_t cols, int64_t rows, int64_t ld, int64_t nb, int64_t bstride,
+                        int64_t pstride) {
+  EncodeTiledFn enc = get_encode();
+  QV_REQUIRE(enc != nullptr, QV_ERR_CUDA, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  QV_REQUIRE(ptr && qv_aligned16(ptr), QV_ERR_INVALID, "gemm plane output base must be a 16-byte aligned device pointer");
+  QV_REQUIRE(rows > 0 && cols > 0 && ld >= cols && ld % 8 == 0, QV_ERR_INVALID,
+             "gemm plane output row pitch must be >= cols and a multiple of 8 bf16 (got %lld)", (long long)ld);
+  if (nb < 1) nb = 1;
+  if (bstride <= 0) bstride = rows * ld;
+  if (pstride <= 0) pstride = bstride * nb;
+  QV_REQUIRE(bstride % 8 == 0 && pstride % 8 == 0, QV_ERR_INVALID, "plane output batch / plane strides must be multiples of 8 bf16");
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(nb), 2};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(bstride) * 2,
+                           static_cast<cuuint64_t>(pstride) * 2};
+  cuuint32_t box[4] = {64, 32, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  QV_REQUIRE(r == CUDA_SUCCESS, QV_ERR_CUDA, "cuTensorMapEncodeTiled(plane output) failed (%d)", (int)r);
+  return 0;
+}
+
+template <int BN, int NA, int NB, bool A_MN, bool B_MN, int EPI = 0>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const GemmKParams& kp, int grid,
            cudaStream_t st) {
-  using C = Cfg<BN, NA, NB>;
+  using C = Cfg<BN, NA, NB, EPI>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(qv_gemm_kernel<BN, NA, NB, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    attr_err = cudaFuncSetAttribute(qv_gemm_kernel<BN, NA, NB, A_MN, B_MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     C::SMEM_BYTES);
   });
   QV_REQUIRE(attr_err == cudaSuccess, QV_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
-  qv_gemm_kernel<BN, NA, NB, A_MN, B_MN><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mb, mo, kp);
+  qv_gemm_kernel<BN, NA, NB, A_MN, B_MN, EPI><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mb, mo, kp);
   return qv_check_launch("qv_gemm_bf16");
 }
 
@@ -439,6 +542,14 @@ extern "C" int qv_gemm_bf16(const qv_gemm_args* a, void* stream) {
   QV_REQUIRE(qv_num_sms() > 0, QV_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
   const int BN = a->tile_n > 0 ? a->tile_n : pick_bn(a->N);
   QV_REQUIRE(BN == 64 || BN == 128 || BN == 192, QV_ERR_UNSUPPORTED, "tile_n must be 64, 128 or 192");
+  const bool planes_out = a->out_kind == 1;
+  QV_REQUIRE(a->out_kind == 0 || a->out_kind == 1, QV_ERR_INVALID, "out_kind must be 0 (fp32) or 1 (bf16 hi/lo planes)");
+  QV_REQUIRE(a->act == 0 || (a->act == 1 && planes_out), QV_ERR_UNSUPPORTED, "act = GELU needs out_kind = 1 (plane output)");
+  if (planes_out) {
+    QV_REQUIRE(splits == 1 && a->a_planes == 2 && a->b_planes == 2 && !a->a.mn_major && !a->b.mn_major && BN >= 128,
+               QV_ERR_UNSUPPORTED, "plane output is instantiated for unsplit K-major (2,2)-plane GEMMs with tile_n 128/192");
+    QV_REQUIRE(a->N % 64 == 0, QV_ERR_UNSUPPORTED, "plane output needs N to be a multiple of 64");
+  }
   CUtensorMap ma, mb, mo;
   int rc = make_map(&ma, a->a, a->a_planes, a->a.mn_major ? 64 : BM);
   if (rc) return rc;
@@ -454,7 +565,10 @@ extern "C" int qv_gemm_bf16(const qv_gemm_args* a, void* stream) {
     // a tile edge that is not the tensor edge must fall on a 32-column store box
     QV_REQUIRE(a->N % 32 == 0 || (o.col_inner == 0 && o.col0 + a->N == o.cols), QV_ERR_UNSUPPORTED,
                "N must be a multiple of 32 unless the output tile ends at the tensor edge");
-    rc = make_out_map(&mo, o.ptr, o.cols, o.rows, o.ld, o.nb, o.batch_stride);
+    if (planes_out)
+      rc = make_out_planes_map(&mo, o.ptr, o.cols, o.rows, o.ld, o.nb, o.batch_stride, a->out_plane_stride);
+    else
+      rc = make_out_map(&mo, o.ptr, o.cols, o.rows, o.ld, o.nb, o.batch_stride);
   }
   if (rc) return rc;
 
@@ -481,12 +595,17 @@ extern "C" int qv_gemm_bf16(const qv_gemm_args* a, void* stream) {
   kp.a_c2_outer = a->a.c2_outer; kp.a_c2_inner = a->a.c2_inner; kp.a_col0 = a->a.col0; kp.a_col_inner = a->a.col_inner;
   kp.b_c2_outer = a->b.c2_outer; kp.b_c2_inner = a->b.c2_inner; kp.b_col0 = a->b.col0; kp.b_col_inner = a->b.col_inner;
   kp.o_c2_outer = a->out.c2_outer; kp.o_c2_inner = a->out.c2_inner; kp.o_col0 = a->out.col0; kp.o_col_inner = a->out.col_inner;
+  kp.act = a->act;
   const int64_t items = static_cast<int64_t>(kp.tiles_m) * kp.tiles_n * (nbatch > 1 ? nbatch : kp.splits);
   QV_REQUIRE(items < (1LL << 31), QV_ERR_UNSUPPORTED, "too many tiles");
   const int sms = qv_num_sms();
   const int grid = static_cast<int>(items < sms ? items : sms);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool amn = a->a.mn_major != 0, bmn = a->b.mn_major != 0;
+  if (planes_out) {
+    if (BN == 128) return launch<128, 2, 2, false, false, 1>(ma, mb, mo, kp, grid, st);
+    return launch<192, 2, 2, false, false, 1>(ma, mb, mo, kp, grid, st);
+  }
   switch (BN) {
     case 64: return launch_planes<64>(a->a_planes, a->b_planes, amn, bmn, ma, mb, mo, kp, grid, st);
     case 128: return launch_planes<128>(a->a_planes, a->b_planes, amn, bmn, ma, mb, mo, kp, grid, st);

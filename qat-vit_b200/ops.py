@@ -202,16 +202,24 @@ PAIRS_FP32 = (2, 2)          # both fp32 as hi/lo: A0*B0 + A0*B1 + A1*B0 (lo*lo 
 
 def gemm(a: Op, b: Op, M: int, N: int, K: int, planes: Tuple[int, int], *, out=None, col_scale=None, col_rscale=None,
          alpha=None, bias=None, minmax=None, splits: int = 1, workspace: Optional[torch.Tensor] = None, nbatch: int = 1,
-         batch_inner: int = 1, tile_n: int = 0):
+         batch_inner: int = 1, tile_n: int = 0, out_planes: Optional[torch.Tensor] = None, gelu: bool = False):
     """D[M,N] = sum_pairs A[pa] @ B[pb]^T on tcgen05 (include/qatvit_b200.h: qv_gemm_bf16).
-    out: an ``Out`` descriptor, a 2-D fp32 tensor, or None (allocated)."""
+    out: an ``Out`` descriptor, a 2-D fp32 tensor, or None (allocated).
+    out_planes: bf16 [2, M, N] -- write [GELU](D) as hi/lo planes straight from the epilogue instead of fp32."""
     args = GemmArgs()
     a.fill(args.a)
     b.fill(args.b)
     args.a_planes, args.b_planes = planes
     args.M, args.N, args.K = M, N, K
     ret = None
-    if splits <= 1:
+    if out_planes is not None:
+        if out_planes.dtype != torch.bfloat16 or not out_planes.is_cuda or out_planes.dim() != 3 or out_planes.stride(2) != 1:
+            raise RuntimeError("qatvit_b200: out_planes must be a CUDA bf16 [2, M, N] plane stack (no CPU fallback)")
+        o = args.out
+        o.ptr, o.ld, o.rows, o.cols, o.nb, o.batch_stride = out_planes.data_ptr(), out_planes.stride(1), M, N, 1, 0
+        args.out_kind, args.act, args.out_plane_stride = 1, int(bool(gelu)), out_planes.stride(0)
+        ret = out_planes
+    elif splits <= 1:
         if out is None:
             out = torch.empty(M, N, dtype=torch.float32, device=a.t.device)
         ret = out.t if isinstance(out, Out) else out
