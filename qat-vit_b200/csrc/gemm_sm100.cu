@@ -30,11 +30,13 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;            // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;           // TMA warp, MMA warp, 8 epilogue warps
 constexpr int A_PLANE_BYTES = BM * BK * 2;
-// epilogue staging per warp: 32-row x 128-byte buffers, double-buffered.  fp32 output: one buffer per 32-column chunk;
-// bf16 hi/lo plane output: a hi and a lo buffer per 64-column chunk.
-constexpr int epi_warp_bytes(int epi) { return (epi == 1 ? 4 : 2) * 32 * 128; }
+// epilogue staging per warp: 32-row x 128-byte buffers.  fp32 output: one buffer per 32-column chunk; bf16 hi/lo plane
+// output: a hi and a lo buffer per 64-column chunk.  Two warps alternate on each TMEM lane quarter, so per-warp single
+// buffering already overlaps one warp's TMA store with the other's math.
+constexpr int epi_warp_bytes(int epi) { return (epi == 1 ? 2 : 1) * 32 * 128; }
+constexpr int epi_terms_bytes(int epi) { return epi == 1 ? 0 : 8 * 2 * 32 * 4; }   // per-warp [mult][bias] column terms
 constexpr int SMEM_LIMIT = 232448;             // 227 KB
 
 struct GemmKParams {
@@ -59,7 +61,7 @@ struct Cfg {
   static constexpr int B_PLANE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = NA * A_PLANE_BYTES + NB * B_PLANE_BYTES;
   static constexpr int EPI_WARP_BYTES = epi_warp_bytes(EPI);
-  static constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;
+  static constexpr int EPI_BYTES = 8 * EPI_WARP_BYTES + epi_terms_bytes(EPI);
   static constexpr int MAX_STAGES = (SMEM_LIMIT - 1024 - 256 - EPI_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = MAX_STAGES > 6 ? 6 : MAX_STAGES;
   static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
@@ -71,10 +73,6 @@ struct Cfg {
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
-
-__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
-  return static_cast<uint32_t>(__bfloat16_as_ushort(a)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
-}
 
 // EPI = 0: fp32 output;  EPI = 1: bf16 hi/lo plane output (the operand format of the next GEMM), optional GELU.
 template <int BN, int NA, int NB, bool A_MN, bool B_MN, int EPI>
@@ -108,7 +106,7 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
-      mbar_init(&tmem_empty[b], 128);
+      mbar_init(&tmem_empty[b], 256);
     }
     fence_barrier_init();
   }
@@ -210,13 +208,22 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else {
-    // =============================== epilogue (4 warps) ===============================
+    // =============================== epilogue (8 warps) ===============================
+    // Two warps per TMEM lane quarter: warp (q, par) takes the column chunks whose index has parity `par`, so every SM
+    // sub-partition always has a second epilogue warp to switch to while the other waits on TMEM / TMA latencies.
+    // Per chunk: tcgen05.ld (the next chunk's load is issued before this one is processed) -> per-column scale / bias
+    // (staged once per chunk in smem, read back as broadcast LDS.128) -> [GELU] -> observer min/max ->
+    // 128B-swizzled smem staging -> TMA store.
+    const int ew = warp - 2;
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
-    uint8_t* my_epi = smem_epi + q * EPI_WARP_BYTES;
+    const int par = ew >> 2;                     // chunk parity owned by this warp
+    constexpr int CW = (EPI == 1) ? 64 : 32;     // columns per chunk (one 128-byte row of fp32 / of each bf16 plane)
+    constexpr int NCHUNK = BN / CW;
+    uint8_t* my_epi = smem_epi + ew * EPI_WARP_BYTES;
+    float* my_terms = reinterpret_cast<float*>(smem_epi + 8 * EPI_WARP_BYTES) + ew * 64;   // EPI 0: [mult 32][bias 32]
     float mn = INFINITY, mx = -INFINITY;
     const float alpha = p.alpha ? __ldg(p.alpha) : 1.0f;
     const bool raw = p.splits > 1;
-    uint32_t chunk_ctr = 0;
     int local = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
       const int n_blk = item % p.tiles_n;
@@ -232,128 +239,115 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tc_fence_after();
       const int row0 = m_blk * BM + q * 32;                     // first row of this warp's 32-row slab
       const bool row_ok = static_cast<int64_t>(row0 + lane) < p.M;
-      if constexpr (EPI == 1) {
-        // ---- bf16 hi/lo plane output: 64 columns per step -> one 32x128B hi box and one lo box ----
+      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN);
+      // register double buffer: `nxt` receives the next chunk's tcgen05.ld while `rr` is processed.  The chunk loop is NOT
+      // unrolled (the body is ~3 K instructions; unrolling it thrashed the instruction cache: ncu `no_instruction` stalls).
+      uint32_t rr[CW], nxt[CW];
+      tmem_ld_cols<CW>(t_base + par * CW, nxt);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 64) {
-          const int64_t n0 = static_cast<int64_t>(n_blk) * BN + c0;
-          const bool live = n0 < p.N && static_cast<int64_t>(row0) < p.M;       // warp-uniform
-          uint8_t* sbuf = my_epi + (chunk_ctr & 1) * 8192;                       // [hi 4 KB][lo 4 KB]
-          if (live) {
-            if (lane == 0) tma_store_wait_read<1>();
-            __syncwarp();
-          }
-          const uint32_t srow_hi = smem_u32(sbuf) + lane * 128, srow_lo = srow_hi + 4096;
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            uint32_t r[32];
-            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN + c0 + half * 32), r);
-            tmem_ld_wait();
-            if (half == 1 && c0 + 64 >= BN) {
-              tc_fence_before();
-              mbar_arrive(&tmem_empty[buf]);
-            }
-            if (!live) continue;
-            float my_mult = 1.0f, my_bias = 0.0f;
-            {
-              const int64_t n = n0 + half * 32 + lane;
-              if (n < p.N) {
-                my_mult = alpha;
-                if (p.col_scale) my_mult *= __ldg(p.col_scale + n);
-                if (p.col_rscale) my_mult = __fdiv_rn(my_mult, __ldg(p.col_rscale + n));
-                if (p.bias) my_bias = __ldg(p.bias + n);
-              }
-            }
-            uint32_t hi[16], lo[16];
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              float a0 = __uint_as_float(r[j]) * __shfl_sync(0xffffffffu, my_mult, j) + __shfl_sync(0xffffffffu, my_bias, j);
-              float a1 = __uint_as_float(r[j + 1]) * __shfl_sync(0xffffffffu, my_mult, j + 1) +
-                         __shfl_sync(0xffffffffu, my_bias, j + 1);
-              if (p.act == 1) { a0 = gelu_erf(a0); a1 = gelu_erf(a1); }
-              __nv_bfloat16 h0, l0, h1, l1;
-              qv_split_bf16(a0, h0, l0);
-              qv_split_bf16(a1, h1, l1);
-              hi[j >> 1] = pack_bf16x2(h0, h1);
-              lo[j >> 1] = pack_bf16x2(l0, l1);
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t sw = (static_cast<uint32_t>((half * 4 + j) ^ (lane & 7)) << 4);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow_hi + sw), "r"(hi[4 * j]), "r"(hi[4 * j + 1]),
-                           "r"(hi[4 * j + 2]), "r"(hi[4 * j + 3]) : "memory");
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow_lo + sw), "r"(lo[4 * j]), "r"(lo[4 * j + 1]),
-                           "r"(lo[4 * j + 2]), "r"(lo[4 * j + 3]) : "memory");
-            }
-          }
-          if (!live) continue;
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_4d(&map_o, sbuf, o_col + static_cast<int>(n0), row0, o_c2, 0);
-            tma_store_4d(&map_o, sbuf + 4096, o_col + static_cast<int>(n0), row0, o_c2, 1);
-            tma_store_commit();
-          }
-          ++chunk_ctr;
-        }
-      } else {
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN + c0), r);
+      for (int ch = par; ch < NCHUNK; ch += 2) {
+        const int c0 = ch * CW;
         tmem_ld_wait();
-        if (c0 + 32 >= BN) {                                    // accumulator fully read: hand TMEM back to the MMA warp
+#pragma unroll
+        for (int j = 0; j < CW; ++j) rr[j] = nxt[j];
+        if (ch + 2 < NCHUNK) {
+          tmem_ld_cols<CW>(t_base + (ch + 2) * CW, nxt);
+        } else {                                                // this warp's last chunk is in registers
           tc_fence_before();
           mbar_arrive(&tmem_empty[buf]);
         }
         const int64_t n0 = static_cast<int64_t>(n_blk) * BN + c0;
         if (n0 >= p.N || static_cast<int64_t>(row0) >= p.M) continue;      // warp-uniform: nothing to store
-        uint8_t* sbuf = my_epi + (chunk_ctr & 1) * 4096;
-        if (lane == 0) tma_store_wait_read<1>();                // the store that last used this buffer has read it
+        if (lane == 0) tma_store_wait_read<0>();                // this warp's previous store has read the staging buffer
         __syncwarp();
-        // per-column epilogue terms: lane j owns column n0 + j (two coalesced loads), broadcast by shuffle below
-        float my_mult = 1.0f, my_bias = 0.0f;
-        if (!raw) {
-          const int64_t n = n0 + lane;
-          if (n < p.N) {
-            my_mult = alpha;
-            if (p.col_scale) my_mult *= __ldg(p.col_scale + n);
-            if (p.col_rscale) my_mult = __fdiv_rn(my_mult, __ldg(p.col_rscale + n));
-            if (p.bias) my_bias = __ldg(p.bias + n);
+        if constexpr (EPI == 0) {
+          if (!raw) {                                           // lane j fetches the terms of column n0 + j; smem broadcast
+            const int64_t n = n0 + lane;
+            float m_ = 1.0f, b_ = 0.0f;
+            if (n < p.N) {
+              m_ = alpha;
+              if (p.col_scale) m_ *= __ldg(p.col_scale + n);
+              if (p.col_rscale) m_ = __fdiv_rn(m_, __ldg(p.col_rscale + n));
+              if (p.bias) b_ = __ldg(p.bias + n);
+            }
+            my_terms[lane] = m_;
+            my_terms[CW + lane] = b_;
+            __syncwarp();
           }
         }
-        const int ncols = static_cast<int>(min(static_cast<int64_t>(32), p.N - n0));   // valid columns of this chunk
-        float v[32];
+        if constexpr (EPI == 0) {
+          const int ncols = static_cast<int>(min(static_cast<int64_t>(32), p.N - n0));   // valid columns of this chunk
+          const uint32_t srow = smem_u32(my_epi) + lane * 128;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float a = __uint_as_float(r[j]);
-          if (!raw) {
-            const float m_j = __shfl_sync(0xffffffffu, my_mult, j);
-            const float b_j = __shfl_sync(0xffffffffu, my_bias, j);
-            a = a * m_j + b_j;
-            const bool ok = row_ok && (j < ncols);
-            mn = ok ? fminf(mn, a) : mn;
-            mx = ok ? fmaxf(mx, a) : mx;
+          for (int j = 0; j < 8; ++j) {
+            float4 v = make_float4(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1]), __uint_as_float(rr[4 * j + 2]),
+                                   __uint_as_float(rr[4 * j + 3]));
+            if (!raw) {
+              const float4 m4 = *reinterpret_cast<const float4*>(my_terms + 4 * j);
+              const float4 b4 = *reinterpret_cast<const float4*>(my_terms + CW + 4 * j);
+              v.x = v.x * m4.x + b4.x; v.y = v.y * m4.y + b4.y; v.z = v.z * m4.z + b4.z; v.w = v.w * m4.w + b4.w;
+              if (p.minmax) {
+                const float big = INFINITY;
+                const float lo0 = (row_ok && 4 * j + 0 < ncols) ? v.x : big, hi0 = (row_ok && 4 * j + 0 < ncols) ? v.x : -big;
+                const float lo1 = (row_ok && 4 * j + 1 < ncols) ? v.y : big, hi1 = (row_ok && 4 * j + 1 < ncols) ? v.y : -big;
+                const float lo2 = (row_ok && 4 * j + 2 < ncols) ? v.z : big, hi2 = (row_ok && 4 * j + 2 < ncols) ? v.z : -big;
+                const float lo3 = (row_ok && 4 * j + 3 < ncols) ? v.w : big, hi3 = (row_ok && 4 * j + 3 < ncols) ? v.w : -big;
+                mn = fminf(mn, fminf(fminf(lo0, lo1), fminf(lo2, lo3)));
+                mx = fmaxf(mx, fmaxf(fmaxf(hi0, hi1), fmaxf(hi2, hi3)));
+              }
+            }
+            // 128B-swizzled staging: 16-byte chunk j of row `lane` lives at chunk (j ^ (lane & 7))
+            const uint32_t addr = srow + (static_cast<uint32_t>(j ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
           }
-          v[j] = a;
-        }
-        // 128B-swizzled staging: 16-byte chunk j of row `lane` lives at chunk (j ^ (lane & 7))
-        const uint32_t srow = smem_u32(sbuf) + lane * 128;
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&map_o, my_epi, o_col + static_cast<int>(n0), row0, o_c2);
+            tma_store_commit();
+          }
+        } else {
+          // bf16 hi/lo plane output: 64 columns -> one 32-row x 128-byte hi box and one lo box
+          const uint32_t srow_hi = smem_u32(my_epi) + lane * 128, srow_lo = srow_hi + 4096;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t addr = srow + (static_cast<uint32_t>(j ^ (lane & 7)) << 4);
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[4 * j]), "f"(v[4 * j + 1]),
-                       "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
-                       : "memory");
+          for (int j = 0; j < 8; ++j) {
+            // plane output takes bias only (checked on the host); every lane reads the same 32 bytes: broadcast LDG.128
+            float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba;
+            if (p.bias) {
+              ba = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 8 * j));
+              bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 8 * j + 4));
+            }
+            float a[8] = {__uint_as_float(rr[8 * j]) + ba.x,     __uint_as_float(rr[8 * j + 1]) + ba.y,
+                          __uint_as_float(rr[8 * j + 2]) + ba.z, __uint_as_float(rr[8 * j + 3]) + ba.w,
+                          __uint_as_float(rr[8 * j + 4]) + bb.x, __uint_as_float(rr[8 * j + 5]) + bb.y,
+                          __uint_as_float(rr[8 * j + 6]) + bb.z, __uint_as_float(rr[8 * j + 7]) + bb.w};
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float a0 = a[2 * e], a1 = a[2 * e + 1];
+              if (p.act == 1) { a0 = gelu_erf(a0); a1 = gelu_erf(a1); }
+              // packed split: one F2FP for the hi pair, exact residuals, one F2FP for the lo pair
+              const __nv_bfloat162 h2 = __floats2bfloat162_rn(a0, a1);
+              const uint32_t hbits = *reinterpret_cast<const uint32_t*>(&h2);
+              const float r0 = a0 - __uint_as_float(hbits << 16), r1 = a1 - __uint_as_float(hbits & 0xffff0000u);
+              const __nv_bfloat162 l2 = __floats2bfloat162_rn(r0, r1);
+              hi[e] = hbits;
+              lo[e] = *reinterpret_cast<const uint32_t*>(&l2);
+            }
+            const uint32_t sw = (static_cast<uint32_t>(j ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow_hi + sw), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]),
+                         "r"(hi[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow_lo + sw), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]),
+                         "r"(lo[3]) : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&map_o, my_epi, o_col + static_cast<int>(n0), row0, o_c2, 0);
+            tma_store_4d(&map_o, my_epi + 4096, o_col + static_cast<int>(n0), row0, o_c2, 1);
+            tma_store_commit();
+          }
         }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_3d(&map_o, sbuf, o_col + static_cast<int>(n0), row0, o_c2);
-          tma_store_commit();
-        }
-        ++chunk_ctr;
-      }
       }
     }
     if (lane == 0) tma_store_wait_read<0>();
@@ -549,6 +543,9 @@ extern "C" int qv_gemm_bf16(const qv_gemm_args* a, void* stream) {
     QV_REQUIRE(splits == 1 && a->a_planes == 2 && a->b_planes == 2 && !a->a.mn_major && !a->b.mn_major && BN >= 128,
                QV_ERR_UNSUPPORTED, "plane output is instantiated for unsplit K-major (2,2)-plane GEMMs with tile_n 128/192");
     QV_REQUIRE(a->N % 64 == 0, QV_ERR_UNSUPPORTED, "plane output needs N to be a multiple of 64");
+    QV_REQUIRE(!a->col_scale && !a->col_rscale && !a->alpha && !a->minmax, QV_ERR_UNSUPPORTED,
+               "plane output takes a bias term only (no scale / alpha / observer)");
+    QV_REQUIRE(!a->bias || qv_aligned16(a->bias), QV_ERR_INVALID, "plane output needs a 16-byte aligned bias");
   }
   CUtensorMap ma, mb, mo;
   int rc = make_map(&ma, a->a, a->a_planes, a->a.mn_major ? 64 : BM);

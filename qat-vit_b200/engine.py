@@ -189,14 +189,12 @@ class TeacherEngine:
         self.p_raw = e(d.B * d.P, D)
         self.x = [e(M, D), e(M, D)]
         self.hp = e(2, M, D, dt=bf)
-        self.qkv_raw = e(M, 3 * D)
         self.qkvp = e(2, M, 3 * D, dt=bf)
         self.S = e(d.B * d.H * d.T, d.ldS)
         self.Pp = torch.zeros(2, d.B * d.H * d.T, d.ldP, dtype=bf, device=dev)
         self.o = e(M, D)
         self.op = e(2, M, D, dt=bf)
         self.y = e(M, D)
-        self.f_raw = e(M, F)
         self.fp = e(2, M, F, dt=bf)
         self.xn = e(d.B, D)
         self.logits = e(d.B, d.C)
@@ -223,8 +221,8 @@ class TeacherEngine:
                 cur ^= 1
                 x_in = self.x[cur]
             w, bias = blk["qkv"]
-            ops.gemm(Op.full(self.hp), Op.full(w), M, 3 * D, D, PAIRS_FP32, out=self.qkv_raw, bias=bias)
-            ops.act_planes(self.qkv_raw, None, False, self.qkvp)
+            # no observer sits between the teacher's Linears: epilogues emit the next operand's bf16 planes directly
+            ops.gemm(Op.full(self.hp), Op.full(w), M, 3 * D, D, PAIRS_FP32, bias=bias, out_planes=self.qkvp)
             _attention_forward(d, self.qkvp, self.S, self.Pp, self.o)
             ops.split_planes(self.o, self.op)
             w, bias = blk["proj"]
@@ -234,8 +232,7 @@ class TeacherEngine:
             cur ^= 1
             x_in = self.x[cur]
             w, bias = blk["fc1"]
-            ops.gemm(Op.full(self.hp), Op.full(w), M, F, D, PAIRS_FP32, out=self.f_raw, bias=bias)
-            ops.act_planes(self.f_raw, None, True, self.fp)
+            ops.gemm(Op.full(self.hp), Op.full(w), M, F, D, PAIRS_FP32, bias=bias, out_planes=self.fp, gelu=True)
             w, bias = blk["fc2"]
             ops.gemm(Op.full(self.fp), Op.full(w), M, D, F, PAIRS_FP32, out=self.y, bias=bias)
             y_prev = self.y
