@@ -181,6 +181,17 @@ int qv_softmax_planes(const float* S, int64_t ldS, int64_t rows, int32_t T, floa
 /* dS = P * (dP - rowsum(dP*P)) * scale -> bf16 hi/lo planes. */
 int qv_attn_ds(const uint16_t* P, int64_t ldP, int64_t p_plane_stride, const float* dP, int64_t lddP, int64_t rows, int32_t T,
                float scale, uint16_t* dS, int64_t ldS, int64_t s_plane_stride, void* stream);
+/* Fused softmax attention forward, one (image, head) per work item on tcgen05 / TMEM (replaces
+ * F.scaled_dot_product_attention in timm Attention.forward):  O = softmax(Q K^T * scale) V, head_dim 64,
+ * T <= 224 tokens; scores / probabilities stay in tensor memory.
+ * qkv_planes: bf16 plane stack [n_planes][B*T][ld] holding Q | K | V column blocks (H*64 columns each).
+ *   n_planes = 2: fp32 values as hi/lo planes;  n_planes = 1: exact integer fake-quant codes, with the observer's scale
+ *   passed as device scalars: logits *= (*qk_scale)^2, output *= *v_scale (either may be NULL).
+ * out_planes: bf16 hi/lo planes [2][B*T][out_ld]; head h fills columns h*64..h*64+63 (the proj GEMM's A operand).
+ * lse (may be NULL): fp32 [B*H*T] natural-log logsumexp of the scaled logits (saved for a recomputing backward). */
+int qv_attn_fwd(const uint16_t* qkv_planes, int32_t n_planes, int64_t plane_stride, int64_t ld, int32_t B, int32_t T,
+                int32_t H, float scale, const float* qk_scale, const float* v_scale, uint16_t* out_planes,
+                int64_t out_plane_stride, int64_t out_ld, float* lse, void* stream);
 /* classifier head (D -> num_classes), exact fp32: out = x wq^T + bias (+ fused output-observer min/max). */
 int qv_head_fwd(const float* x, const float* wq, const float* bias, int32_t B, int32_t K, int32_t N, float* out,
                 uint32_t* minmax, void* stream);

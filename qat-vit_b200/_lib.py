@@ -86,6 +86,8 @@ _SIGNATURES = {
     "qv_im2col_fq": (c_int, [_P, _P, _P, c_int32, c_int32, c_int64, c_int32, c_int32, c_int32, _P, _P, _P]),
     "qv_softmax_planes": (c_int, [_P, c_int64, c_int64, c_int32, c_float, _P, c_int64, c_int64, _P]),
     "qv_attn_ds": (c_int, [_P, c_int64, c_int64, _P, c_int64, c_int64, c_int32, c_float, _P, c_int64, c_int64, _P]),
+    "qv_attn_fwd": (c_int, [_P, c_int32, c_int64, c_int64, c_int32, c_int32, c_int32, c_float, _P, _P, _P, c_int64, c_int64,
+                            _P, _P]),
     "qv_head_fwd": (c_int, [_P, _P, _P, c_int32, c_int32, c_int32, _P, _P, _P]),
     "qv_head_bwd": (c_int, [_P, _P, _P, _P, c_int32, c_int32, c_int32, _P, _P, _P, c_int32, _P]),
 }

@@ -324,6 +324,18 @@ def attn_ds(P_planes, dP, lddP, rows, T, scale, dS_planes):
                                 dS_planes.stride(1), dS_planes.stride(0), _stream()), "attn_ds")
 
 
+def attn_fwd(qkv_planes, B, T, H, scale, out_planes, qk_scale=None, v_scale=None, lse=None):
+    """Fused softmax(Q K^T * scale) V per (image, head): qkv_planes bf16 [1 or 2, B*T, 3*H*64] -> out_planes bf16
+    [2, B*T, H*64] (include/qatvit_b200.h: qv_attn_fwd)."""
+    if qkv_planes.dim() != 3 or qkv_planes.stride(2) != 1 or out_planes.dim() != 3 or out_planes.stride(2) != 1:
+        raise RuntimeError("qatvit_b200: attn_fwd takes [planes, tokens, cols] plane stacks")
+    check(_lib.lib().qv_attn_fwd(_p(qkv_planes, torch.bfloat16, "qkv_planes"), qkv_planes.shape[0], qkv_planes.stride(0),
+                                 qkv_planes.stride(1), B, T, H, float(scale), _p(qk_scale, torch.float32),
+                                 _p(v_scale, torch.float32), _p(out_planes, torch.bfloat16, "out_planes"),
+                                 out_planes.stride(0), out_planes.stride(1), _p(lse, torch.float32), _stream()), "attn_fwd")
+    return out_planes
+
+
 def head_fwd(x, wq, bias, B, K, N, out, minmax=None):
     check(_lib.lib().qv_head_fwd(_p(x, torch.float32), _p(wq, torch.float32), _p(bias, torch.float32), B, K, N,
                                  _p(out, torch.float32), _p(minmax, torch.int32), _stream()), "head_fwd")
@@ -366,7 +378,7 @@ def _wrap(name, fn, tag_fn=None):
 
 for _n in ("minmax_reset", "minmax_accumulate", "obs_update", "fq_apply", "fq_weight", "fq_bwd", "split_planes",
            "kd_ce_loss", "splitk_reduce", "resid_ln_fwd", "ln_bwd", "colsum_reduce", "colsum_rows", "gp_planes",
-           "act_planes", "embed_fwd", "im2col_fq", "softmax_planes", "attn_ds", "head_fwd", "head_bwd"):
+           "act_planes", "embed_fwd", "im2col_fq", "softmax_planes", "attn_ds", "head_fwd", "head_bwd", "attn_fwd"):
     globals()[_n] = _wrap(_n, globals()[_n])
 gemm = _wrap("gemm", gemm, _gemm_tag)
 
