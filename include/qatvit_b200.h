@@ -187,16 +187,39 @@ int qv_attn_ds(const uint16_t* P, int64_t ldP, int64_t p_plane_stride, const flo
  * qkv_planes: bf16 plane stack [n_planes][B*T][ld] holding Q | K | V column blocks (H*64 columns each).
  *   n_planes = 2: fp32 values as hi/lo planes;  n_planes = 1: exact integer fake-quant codes, with the observer's scale
  *   passed as device scalars: logits *= (*qk_scale)^2, output *= *v_scale (either may be NULL).
- * out_planes: bf16 hi/lo planes [2][B*T][out_ld]; head h fills columns h*64..h*64+63 (the proj GEMM's A operand).
+ * out_planes: bf16 hi/lo planes [2][B*T][out_ld]; head h fills columns h*64..h*64+63 (the proj GEMM's A operand);
+ * out_f32: fp32 [B*T][H*64] copy of the output (either output may be NULL, not both).
  * lse (may be NULL): fp32 [B*H*T] natural-log logsumexp of the scaled logits (saved for a recomputing backward). */
 int qv_attn_fwd(const uint16_t* qkv_planes, int32_t n_planes, int64_t plane_stride, int64_t ld, int32_t B, int32_t T,
                 int32_t H, float scale, const float* qk_scale, const float* v_scale, uint16_t* out_planes,
-                int64_t out_plane_stride, int64_t out_ld, float* lse, void* stream);
+                int64_t out_plane_stride, int64_t out_ld, float* out_f32, float* lse, void* stream);
 /* classifier head (D -> num_classes), exact fp32: out = x wq^T + bias (+ fused output-observer min/max). */
 int qv_head_fwd(const float* x, const float* wq, const float* bias, int32_t B, int32_t K, int32_t N, float* out,
                 uint32_t* minmax, void* stream);
 int qv_head_bwd(const float* g, const float* x, const float* wq, const uint8_t* wmask, int32_t B, int32_t K, int32_t N,
                 float* gx, float* gw, float* gb, int32_t accumulate, void* stream);
+
+/* ---- converted int8 student (replaces torch.ops.quantized.linear behind the nnq.Linear / nnq.Conv2d modules stock
+ *      convert() builds: ref/src/training/qat_trainer.py:377-388; torch/ao/nn/quantized/modules/linear.py:187-190) ----
+ * acc = sum_k (q_x - z_x) q_w on tcgen05 kind::i8 (u8 x s8 -> s32 in TMEM), then the engine's requantisation:
+ *   bias_int = 0 (x86 / fbgemm, torch's default CPU engine): q_y = clamp(rint((float(acc) + b/(s_x s_w)) * (s_x s_w/s_y)) + z_y, 0, 255)
+ *   bias_int = 1 (qnnpack engine):                           q_y = clamp(rint(float(acc + rint(b/(s_x s_w))) * (s_x s_w/s_y)) + z_y, 0, 255)  qx uint8 [M,K]; qw int8 [N,K] (symmetric: weight zero point 0); sx / zx: DEVICE scalars (the
+ * input's qparams, possibly computed on device); sw fp32 [N] (per_channel) or [1]; wsum int32 [N] = sum_k qw[n,k];
+ * bias fp32 [N] or NULL; (sy, zy) the module's output qparams.  Outputs (either may be NULL): qy uint8 [M,N] codes,
+ * y fp32 [M,N] = (qy - zy) * sy (what DeQuantize / the float glue consumes).  K % 16 == 0. */
+int qv_int8_linear(const uint8_t* qx, int64_t M, int64_t K, const float* sx, const int32_t* zx, const int8_t* qw, int64_t N,
+                   const float* sw, int32_t per_channel, const int32_t* wsum, const float* bias, float sy, int32_t zy,
+                   int32_t bias_int, uint8_t* qy, float* y, void* stream);
+/* q = clamp(rint(x * (1/scale)) + zero_point, 0, 255) with device-scalar qparams (torch.quantize_per_tensor / nnq.Quantize). */
+int qv_quantize_u8(const float* x, int64_t n, const float* scale, const int32_t* zero_point, uint8_t* q, void* stream);
+/* Affine qparams from an ordered min/max accumulator (qv_minmax_accumulate), Python-observer formula
+ * (torch/ao/quantization/observer.py:349-427): scale = max((max+ - min-)/(qmax-qmin), eps), zp = clamp(qmin - rint(min-/scale)). */
+int qv_qparams_from_minmax(const uint32_t* acc, int32_t qmin, int32_t qmax, float* scale, int32_t* zero_point, void* stream);
+/* Quantise the input image and gather 16x16 patches in one pass (nnq.Quantize + the im2col of nnq.Conv2d): uint8 [B*P, C*p*p]. */
+int qv_im2col_u8(const float* img, const float* scale, const int32_t* zp, int64_t B, int32_t C, int32_t HW, int32_t patch,
+                 uint8_t* out, void* stream);
+/* y = GELU_erf(x) in fp32, with the min / max of y merged into acc (may be NULL): the float glue between fc1 and fc2. */
+int qv_gelu_minmax(const float* x, int64_t n, float* y, uint32_t* acc, void* stream);
 
 #ifdef __cplusplus
 }

@@ -130,8 +130,9 @@ def distill_loss(s: np.ndarray, t: np.ndarray, labels: np.ndarray, T: float, alp
     return float(out[0]), float(out[1]), float(out[2]), g
 
 
-def int8_linear(qx, sx, zx, qw, sw, bias, sy, zy):
-    """quantized::linear restatement (SURVEY.md §8 a12); qx uint8 [M,K], qw int8 [N,K]."""
+def int8_linear(qx, sx, zx, qw, sw, bias, sy, zy, engine="x86"):
+    """quantized::linear restatement (SURVEY.md §8 a12); qx uint8 [M,K], qw int8 [N,K].  engine: "x86"/"fbgemm" (float bias,
+    the default CPU engine) or "qnnpack" (int32-quantised bias)."""
     qx = np.ascontiguousarray(qx, np.uint8)
     qw = np.ascontiguousarray(qw, np.int8)
     sw = np.ascontiguousarray(np.atleast_1d(sw), np.float32)
@@ -141,5 +142,5 @@ def int8_linear(qx, sx, zx, qw, sw, bias, sy, zy):
     qy = np.empty((M, N), np.uint8)
     lib().qo_int8_linear(_p(qx), ctypes.c_int64(M), ctypes.c_int64(K), ctypes.c_float(sx), ctypes.c_int32(zx),
                          _p(qw), ctypes.c_int64(N), _p(sw), int(sw.size > 1), _p(bias), ctypes.c_float(sy),
-                         ctypes.c_int32(zy), _p(qy))
+                         ctypes.c_int32(zy), int(engine == "qnnpack"), _p(qy))
     return qy

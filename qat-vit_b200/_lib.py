@@ -87,7 +87,13 @@ _SIGNATURES = {
     "qv_softmax_planes": (c_int, [_P, c_int64, c_int64, c_int32, c_float, _P, c_int64, c_int64, _P]),
     "qv_attn_ds": (c_int, [_P, c_int64, c_int64, _P, c_int64, c_int64, c_int32, c_float, _P, c_int64, c_int64, _P]),
     "qv_attn_fwd": (c_int, [_P, c_int32, c_int64, c_int64, c_int32, c_int32, c_int32, c_float, _P, _P, _P, c_int64, c_int64,
-                            _P, _P]),
+                            _P, _P, _P]),
+    "qv_int8_linear": (c_int, [_P, c_int64, c_int64, _P, _P, _P, c_int64, _P, c_int32, _P, _P, c_float, c_int32, c_int32, _P, _P,
+                               _P]),
+    "qv_quantize_u8": (c_int, [_P, c_int64, _P, _P, _P, _P]),
+    "qv_qparams_from_minmax": (c_int, [_P, c_int32, c_int32, _P, _P, _P]),
+    "qv_im2col_u8": (c_int, [_P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P, _P]),
+    "qv_gelu_minmax": (c_int, [_P, c_int64, _P, _P, _P]),
     "qv_head_fwd": (c_int, [_P, _P, _P, c_int32, c_int32, c_int32, _P, _P, _P]),
     "qv_head_bwd": (c_int, [_P, _P, _P, _P, c_int32, c_int32, c_int32, _P, _P, _P, c_int32, _P]),
 }

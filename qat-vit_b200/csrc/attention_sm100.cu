@@ -59,8 +59,9 @@ struct AttnParams {
   float scale;           // softmax scale (head_dim^-0.5)
   const float* qk_scale; // optional device scalar s: logits are multiplied by s*s (integer-code operands)
   const float* v_scale;  // optional device scalar s: output is multiplied by s
-  __nv_bfloat16* out;    // [2][B*T][out_ld] hi/lo planes; head h writes columns h*64 .. h*64+63
+  __nv_bfloat16* out;    // [2][B*T][out_ld] hi/lo planes; head h writes columns h*64 .. h*64+63 (may be null)
   int64_t out_plane_stride, out_ld;
+  float* out_f32;        // optional fp32 copy of the output, [B*T][H*64]
   float* lse;            // optional [B*H*T]: scale' * rowmax + ln(rowsum)   (natural-log logsumexp of the scaled logits)
 };
 
@@ -309,16 +310,25 @@ qv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         if (t < p.T) {
           const float inv = vs / sum;
           const int64_t row = static_cast<int64_t>(b) * p.T + t;
-          __nv_bfloat16* dst_hi = p.out + row * p.out_ld + h * HD;
-          __nv_bfloat16* dst_lo = dst_hi + p.out_plane_stride;
+          if (p.out) {
+            __nv_bfloat16* dst_hi = p.out + row * p.out_ld + h * HD;
+            __nv_bfloat16* dst_lo = dst_hi + p.out_plane_stride;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            uint32_t hi[4], lo[4];
+            for (int j = 0; j < 8; ++j) {
+              uint32_t hi[4], lo[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-              split_pack2(__uint_as_float(o[8 * j + 2 * e]) * inv, __uint_as_float(o[8 * j + 2 * e + 1]) * inv, hi[e], lo[e]);
-            *reinterpret_cast<uint4*>(dst_hi + 8 * j) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(dst_lo + 8 * j) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              for (int e = 0; e < 4; ++e)
+                split_pack2(__uint_as_float(o[8 * j + 2 * e]) * inv, __uint_as_float(o[8 * j + 2 * e + 1]) * inv, hi[e], lo[e]);
+              *reinterpret_cast<uint4*>(dst_hi + 8 * j) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4*>(dst_lo + 8 * j) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+          }
+          if (p.out_f32) {
+            float* dst = p.out_f32 + row * (static_cast<int64_t>(p.H) * HD) + h * HD;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(__uint_as_float(o[4 * j]) * inv, __uint_as_float(o[4 * j + 1]) * inv,
+                                                                    __uint_as_float(o[4 * j + 2]) * inv, __uint_as_float(o[4 * j + 3]) * inv);
           }
           if (p.lse) p.lse[(static_cast<int64_t>(b) * p.H + h) * p.T + t] = mx * sc + logf(sum);
         }
@@ -352,13 +362,16 @@ int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap&
 
 extern "C" int qv_attn_fwd(const uint16_t* qkv_planes, int32_t n_planes, int64_t plane_stride, int64_t ld, int32_t B,
                            int32_t T, int32_t H, float scale, const float* qk_scale, const float* v_scale,
-                           uint16_t* out_planes, int64_t out_plane_stride, int64_t out_ld, float* lse, void* stream) {
-  QV_REQUIRE(qkv_planes && out_planes && B > 0 && T > 0 && H > 0, QV_ERR_INVALID, "bad attn_fwd arguments");
+                           uint16_t* out_planes, int64_t out_plane_stride, int64_t out_ld, float* out_f32, float* lse,
+                           void* stream) {
+  QV_REQUIRE(qkv_planes && (out_planes || out_f32) && B > 0 && T > 0 && H > 0, QV_ERR_INVALID, "bad attn_fwd arguments");
   QV_REQUIRE(n_planes == 1 || n_planes == 2, QV_ERR_INVALID, "n_planes must be 1 (integer codes) or 2 (fp32 hi/lo)");
   QV_REQUIRE(T <= 224, QV_ERR_UNSUPPORTED, "fused attention holds all keys in one tile: T <= 224 (got %d)", T);
   QV_REQUIRE(ld >= 3LL * H * HD, QV_ERR_INVALID, "qkv row pitch must cover Q | K | V (3 * H * 64 columns)");
-  QV_REQUIRE(out_ld >= static_cast<int64_t>(H) * HD && out_ld % 8 == 0 && out_plane_stride % 8 == 0 && qv_aligned16(out_planes),
+  QV_REQUIRE(!out_planes || (out_ld >= static_cast<int64_t>(H) * HD && out_ld % 8 == 0 && out_plane_stride % 8 == 0 &&
+                             qv_aligned16(out_planes)),
              QV_ERR_INVALID, "output planes must be 16-byte aligned with pitches that are multiples of 8 bf16");
+  QV_REQUIRE(!out_f32 || qv_aligned16(out_f32), QV_ERR_INVALID, "fp32 output must be 16-byte aligned");
   QV_REQUIRE(qv_num_sms() > 0, QV_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
   AttnParams ap;
   memset(&ap, 0, sizeof(ap));
@@ -371,6 +384,7 @@ extern "C" int qv_attn_fwd(const uint16_t* qkv_planes, int32_t n_planes, int64_t
   ap.out = reinterpret_cast<__nv_bfloat16*>(out_planes);
   ap.out_plane_stride = out_plane_stride;
   ap.out_ld = out_ld;
+  ap.out_f32 = out_f32;
   ap.lse = lse;
   // one tensor, three box shapes: per-image matrices [T rows, ld cols]; rows >= T are zero-filled by TMA
   qv_operand op;

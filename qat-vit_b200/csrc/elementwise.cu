@@ -471,6 +471,63 @@ __global__ void __launch_bounds__(256) colsum_rows_kernel(const float* __restric
   out[c] = accumulate ? out[c] + s : s;
 }
 
+// im2col of the QUANTISED input image (converted model: nnq.Quantize followed by nnq.Conv2d 16x16/16 as an int8 GEMM):
+//   out[b*P + py*G + px][c*ps*ps + ky*ps + kx] = clamp(rint(x * (1/s)) + z, 0, 255)   (uint8)
+__global__ void __launch_bounds__(256) im2col_u8_kernel(const float* __restrict__ img, const float* scale, const int32_t* zp,
+                                                        int64_t B, int C, int HW, int ps, uint8_t* __restrict__ out) {
+  const float inv = __fdiv_rn(1.0f, __ldg(scale));
+  const float z = static_cast<float>(__ldg(zp));
+  const int G = HW / ps;
+  const int w4 = HW >> 2;
+  const int64_t total = B * C * HW * w4;
+  const int64_t K = static_cast<int64_t>(C) * ps * ps;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total; i += stride) {
+    const int xw = static_cast<int>(i % w4) * 4;
+    int64_t rest = i / w4;
+    const int yh = static_cast<int>(rest % HW);
+    rest /= HW;
+    const int c = static_cast<int>(rest % C);
+    const int64_t b = rest / C;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(img) + i);
+    const float a[4] = {v.x, v.y, v.z, v.w};
+    uint32_t w = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float f = __fadd_rn(nearbyintf(__fmul_rn(a[j], inv)), z);
+      f = fminf(fmaxf(f, 0.0f), 255.0f);
+      w |= static_cast<uint32_t>(f) << (8 * j);
+    }
+    const int py = yh / ps, ky = yh % ps, px = xw / ps, kx = xw % ps;
+    const int64_t row = b * G * G + static_cast<int64_t>(py) * G + px;
+    const int64_t col = static_cast<int64_t>(c) * ps * ps + ky * ps + kx;
+    *reinterpret_cast<uint32_t*>(out + row * K + col) = w;
+  }
+}
+
+// y = GELU(x) (exact erf), fp32 -> fp32, fused with the min / max of y (dynamic quantisation of the next int8 Linear)
+__global__ void __launch_bounds__(256) gelu_minmax_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ y,
+                                                          uint32_t* acc) {
+  float mn = INFINITY, mx = -INFINITY;
+  const int64_t n4 = n >> 2;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    const float4 o = make_float4(gelu_fwd(v.x), gelu_fwd(v.y), gelu_fwd(v.z), gelu_fwd(v.w));
+    reinterpret_cast<float4*>(y)[i] = o;
+    mn = fminf(mn, fminf(fminf(o.x, o.y), fminf(o.z, o.w)));
+    mx = fmaxf(mx, fmaxf(fmaxf(o.x, o.y), fmaxf(o.z, o.w)));
+  }
+  if (acc) {
+    mn = qv_warp_min(mn);
+    mx = qv_warp_max(mx);
+    if ((threadIdx.x & 31) == 0 && mn <= mx) {
+      atomicMin(acc, qv_f2ord(mn));
+      atomicMax(acc + 1, qv_f2ord(mx));
+    }
+  }
+}
+
 inline int ew_blocks(int64_t n_items, int per_sm = 8) {
   const int sms = qv_num_sms();
   int64_t b = (n_items + 255) / 256;
@@ -600,6 +657,23 @@ extern "C" int qv_im2col_fq(const float* img, const float* scale, const int32_t*
       img, scale, zp, qmin, qmax, B, C, HW, patch, reinterpret_cast<__nv_bfloat16*>(out_plane),
       reinterpret_cast<__nv_bfloat16*>(out_lo_plane), scale != nullptr);
   return qv_check_launch("qv_im2col_fq");
+}
+
+extern "C" int qv_im2col_u8(const float* img, const float* scale, const int32_t* zp, int64_t B, int32_t C, int32_t HW,
+                            int32_t patch, uint8_t* out, void* stream) {
+  QV_REQUIRE(img && scale && zp && out && B > 0 && C > 0 && HW > 0 && patch > 0, QV_ERR_INVALID, "bad im2col_u8 arguments");
+  QV_REQUIRE(HW % patch == 0 && patch % 4 == 0, QV_ERR_UNSUPPORTED, "im2col needs HW %% patch == 0 and patch %% 4 == 0");
+  QV_NEED_GPU();
+  const int64_t total = B * C * HW * (HW / 4);
+  im2col_u8_kernel<<<ew_blocks(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(img, scale, zp, B, C, HW, patch, out);
+  return qv_check_launch("qv_im2col_u8");
+}
+
+extern "C" int qv_gelu_minmax(const float* x, int64_t n, float* y, uint32_t* acc, void* stream) {
+  QV_REQUIRE(x && y && n > 0 && n % 4 == 0, QV_ERR_INVALID, "bad gelu_minmax arguments (n must be a multiple of 4)");
+  QV_NEED_GPU();
+  gelu_minmax_kernel<<<ew_blocks(n >> 2), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, y, acc);
+  return qv_check_launch("qv_gelu_minmax");
 }
 
 extern "C" int qv_softmax_planes(const float* S, int64_t ldS, int64_t rows, int32_t T, float scale, uint16_t* P, int64_t ldP,

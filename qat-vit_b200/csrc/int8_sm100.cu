@@ -1,0 +1,365 @@
+// int8_sm100.cu -- converted-student inference: quantized Linear on the tcgen05 integer tensor cores.
+//
+// Replaces torch.ops.quantized.linear, the forward of torch.ao.nn.quantized.Linear that stock convert() produces from
+// every nnqat.Linear (ref/src/training/qat_trainer.py:377-388; torch/ao/nn/quantized/modules/linear.py:187-190):
+//
+//   acc[m,n] = sum_k (q_x[m,k] - z_x) * q_w[n,k]                                                (int32, exact)
+//   q_y[m,n] = clamp(rint((float(acc) + b[n] / (s_x s_w[n])) * (s_x s_w[n] / s_y)) + z_y, 0, 255)   (x86 / fbgemm engine)
+//   q_y[m,n] = clamp(rint(float(acc + rint(b[n] / (s_x s_w[n]))) * (s_x s_w[n] / s_y)) + z_y, 0, 255) (qnnpack engine)
+//
+// q_x is uint8, q_w int8: `tcgen05.mma.kind::i8` (u8 x s8 -> s32 accumulators in TMEM) computes sum_k q_x q_w; the
+// zero-point term z_x * sum_k q_w[n,k] is removed in the epilogue from a per-channel weight row sum.  Results are
+// bit-identical to the fbgemm / x86 engines of the reference (tests/test_int8_gpu.py; oracle: oracle/fq_oracle.c qo_int8_linear).
+//
+// Structure: persistent 128 x BN tiles; warp 0 TMA producer (128-byte rows of 128 int8, 128B swizzle, OOB zero fill),
+// warp 1 MMA issuer (4 x K=32 steps per stage, double-buffered TMEM accumulators), warps 2-5 requantising epilogue.
+#include <cuda.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "qv_common.cuh"
+#include "qv_ptx.cuh"
+#include "qv_tma.cuh"
+
+using namespace qvptx;
+
+namespace {
+
+constexpr int I8_BM = 128;
+constexpr int I8_BK = 128;          // 128 int8 = one 128-byte swizzle row
+constexpr int I8_UMMA_K = 32;
+constexpr int I8_THREADS = 192;
+constexpr int I8_A_BYTES = I8_BM * I8_BK;
+
+template <int BN>
+struct I8Cfg {
+  static constexpr int B_BYTES = BN * I8_BK;
+  static constexpr int STAGE_BYTES = I8_A_BYTES + B_BYTES;
+  static constexpr int STAGES = 6;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : 256;
+};
+
+struct I8Params {
+  int64_t M, N, K;
+  int32_t kblocks, tiles_m, tiles_n;
+  const float* sx;        // device scalar: input scale
+  const int32_t* zx;      // device scalar: input zero point
+  const float* sw;        // [N] (per channel) or [1]
+  int32_t per_channel;
+  const int32_t* wsum;    // [N] sum_k q_w[n,k]
+  const float* bias;      // [N] fp32 or null
+  float sy;
+  int32_t zy;
+  int32_t bias_int;       // 0: float bias added to float(acc) (x86 / fbgemm); 1: bias pre-quantised to int32 (qnnpack)
+  uint8_t* qy;            // [M,N] quint8 codes (may be null)
+  float* y;               // [M,N] dequantised (q_y - z_y) * s_y (may be null)
+};
+
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// kind::i8 instruction descriptor: A unsigned 8-bit, B signed 8-bit, D int32, both K-major
+__host__ __device__ constexpr uint32_t umma_idesc_u8s8(int M, int N) {
+  return (2u << 4) | (0u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(I8_THREADS, 1)
+qv_int8_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const I8Params p) {
+  using C = I8Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C::STAGES;
+  uint64_t* tmem_full = bars + 2 * C::STAGES;
+  uint64_t* tmem_empty = bars + 2 * C::STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&map_a);
+    prefetch_tensormap(&map_b);
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int num_items = p.tiles_m * p.tiles_n;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int n_blk = item % p.tiles_n, m_blk = item / p.tiles_n;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          tma_load_2d(sa, &map_a, &full_bar[stage], kb * I8_BK, m_blk * I8_BM);
+          tma_load_2d(sa + I8_A_BYTES, &map_b, &full_bar[stage], kb * I8_BK, n_blk * BN);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_u8s8(I8_BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
+        const int buf = local & 1;
+        mbar_wait(&tmem_empty[buf], ((local >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * BN);
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t sb = sa + I8_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < I8_BK / I8_UMMA_K; ++k) {
+            const uint64_t da = umma_smem_desc(sa + k * I8_UMMA_K, 16u, 1024u);
+            const uint64_t db = umma_smem_desc(sb + k * I8_UMMA_K, 16u, 1024u);
+            umma_i8(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[buf]);
+      }
+    }
+  } else {
+    // =============================== requantising epilogue ===============================
+    const int q = warp & 3;
+    const float sx = __ldg(p.sx);
+    const int32_t zx = __ldg(p.zx);
+    const float zyf = static_cast<float>(p.zy);
+    const bool vec_ok = (p.N % 16 == 0);
+    int local = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
+      const int n_blk = item % p.tiles_n, m_blk = item / p.tiles_n;
+      const int buf = local & 1;
+      mbar_wait(&tmem_full[buf], (local >> 1) & 1);
+      tc_fence_after();
+      const int64_t row = static_cast<int64_t>(m_blk) * I8_BM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN + c0), r);
+        tmem_ld_wait();
+        if (c0 + 32 >= BN) {
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[buf]);
+        }
+        const int64_t n0 = static_cast<int64_t>(n_blk) * BN + c0;
+        if (n0 >= p.N) continue;
+        // per-column terms: lane j owns column n0 + j
+        int32_t my_add = 0;          // - z_x * sum_k q_w  (+ rint(b / (s_x s_w)) in qnnpack mode)
+        float my_badd = 0.f;         // b / (s_x s_w)  (x86 / fbgemm mode)
+        float my_mult = 0.f;         // s_x s_w / s_y
+        {
+          const int64_t n = n0 + lane;
+          if (n < p.N) {
+            const float bs = __fmul_rn(sx, __ldg(p.sw + (p.per_channel ? n : 0)));
+            my_mult = __fdiv_rn(bs, p.sy);
+            my_add = -zx * __ldg(p.wsum + n);
+            if (p.bias) {
+              const float bq = __fdiv_rn(__ldg(p.bias + n), bs);
+              if (p.bias_int) my_add += static_cast<int32_t>(nearbyintf(bq));
+              else my_badd = bq;
+            }
+          }
+        }
+        const int ncols = static_cast<int>(min(static_cast<int64_t>(32), p.N - n0));
+        uint32_t packed[8];
+        float deq[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int32_t add_j = __shfl_sync(0xffffffffu, my_add, j);
+          const float mult_j = __shfl_sync(0xffffffffu, my_mult, j);
+          const float badd_j = __shfl_sync(0xffffffffu, my_badd, j);
+          const int32_t acc = static_cast<int32_t>(r[j]) + add_j;
+          float f = __fadd_rn(nearbyintf(__fmul_rn(__fadd_rn(static_cast<float>(acc), badd_j), mult_j)), zyf);
+          f = fminf(fmaxf(f, 0.0f), 255.0f);
+          const uint32_t code = static_cast<uint32_t>(f);
+          deq[j] = __fmul_rn(__fsub_rn(f, zyf), p.sy);
+          if ((j & 3) == 0) packed[j >> 2] = code;
+          else packed[j >> 2] |= code << (8 * (j & 3));
+        }
+        if (!row_ok) continue;
+        if (p.qy) {
+          uint8_t* dst = p.qy + row * p.N + n0;
+          if (vec_ok && ncols == 32) {
+            *reinterpret_cast<uint4*>(dst) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            *reinterpret_cast<uint4*>(dst + 16) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) dst[j] = static_cast<uint8_t>((packed[j >> 2] >> (8 * (j & 3))) & 0xffu);
+          }
+        }
+        if (p.y) {
+          float* dst = p.y + row * p.N + n0;
+          if (p.N % 4 == 0 && ncols == 32) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(deq[4 * j], deq[4 * j + 1], deq[4 * j + 2], deq[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) dst[j] = deq[j];
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// uint8 / int8 matrix [rows][K] as a 2-D tensor (K, rows); box = (128 bytes, box_rows), 128B swizzle, OOB zero fill
+int make_map_i8(CUtensorMap* m, const void* ptr, int64_t rows, int64_t K, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  QV_REQUIRE(enc != nullptr, QV_ERR_CUDA, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  QV_REQUIRE(ptr && qv_aligned16(ptr), QV_ERR_INVALID, "int8 operand base must be a 16-byte aligned device pointer");
+  QV_REQUIRE(K % 16 == 0, QV_ERR_UNSUPPORTED, "int8 linear needs K to be a multiple of 16 (got %lld)", (long long)K);
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(K)};
+  cuuint32_t box[2] = {128, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  QV_REQUIRE(r == CUDA_SUCCESS, QV_ERR_CUDA, "cuTensorMapEncodeTiled(int8 operand) failed (%d)", (int)r);
+  return 0;
+}
+
+template <int BN>
+int launch_i8(const CUtensorMap& ma, const CUtensorMap& mb, const I8Params& kp, int grid, cudaStream_t st) {
+  using C = I8Cfg<BN>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(qv_int8_linear_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+  });
+  QV_REQUIRE(attr_err == cudaSuccess, QV_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+  qv_int8_linear_kernel<BN><<<grid, I8_THREADS, C::SMEM_BYTES, st>>>(ma, mb, kp);
+  return qv_check_launch("qv_int8_linear");
+}
+
+// x -> quint8 codes with the scale / zero point in device scalars: clamp(rint(x * (1/s)) + z, 0, 255)
+// (torch.quantize_per_tensor; the nnq.Quantize module convert() puts in place of QuantStub)
+__global__ void __launch_bounds__(256) quantize_u8_kernel(const float* __restrict__ x, int64_t n, const float* scale,
+                                                          const int32_t* zp, uint8_t* __restrict__ q) {
+  const float inv = __fdiv_rn(1.0f, __ldg(scale));
+  const float z = static_cast<float>(__ldg(zp));
+  const int64_t n4 = n >> 2;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    const float a[4] = {v.x, v.y, v.z, v.w};
+    uint32_t w = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float f = __fadd_rn(nearbyintf(__fmul_rn(a[j], inv)), z);
+      f = fminf(fmaxf(f, 0.0f), 255.0f);
+      w |= static_cast<uint32_t>(f) << (8 * j);
+    }
+    reinterpret_cast<uint32_t*>(q)[i] = w;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (int64_t i = n4 * 4; i < n; ++i) {
+      float f = __fadd_rn(nearbyintf(__fmul_rn(x[i], inv)), z);
+      q[i] = static_cast<uint8_t>(fminf(fmaxf(f, 0.0f), 255.0f));
+    }
+}
+
+// Affine quint8 qparams from an observed min / max (torch/ao/quantization/observer.py:349-427, the convert-time Python
+// formula; also what the float-glue executor uses for dynamically quantised inputs): fp32 arithmetic.
+__global__ void qparams_from_minmax_kernel(const uint32_t* acc, int32_t qmin, int32_t qmax, float* scale, int32_t* zp) {
+  const float mn = fminf(qv_ord2f(acc[0]), 0.0f), mx = fmaxf(qv_ord2f(acc[1]), 0.0f);
+  float s = __fdiv_rn(__fsub_rn(mx, mn), static_cast<float>(qmax - qmin));
+  s = fmaxf(s, 1.1920928955078125e-07f);
+  float z = __fsub_rn(static_cast<float>(qmin), nearbyintf(__fdiv_rn(mn, s)));
+  z = fminf(fmaxf(z, static_cast<float>(qmin)), static_cast<float>(qmax));
+  *scale = s;
+  *zp = static_cast<int32_t>(z);
+}
+
+}  // namespace
+
+extern "C" int qv_int8_linear(const uint8_t* qx, int64_t M, int64_t K, const float* sx, const int32_t* zx, const int8_t* qw,
+                              int64_t N, const float* sw, int32_t per_channel, const int32_t* wsum, const float* bias, float sy,
+                              int32_t zy, int32_t bias_int, uint8_t* qy, float* y, void* stream) {
+  QV_REQUIRE(qx && qw && sx && zx && sw && wsum && (qy || y), QV_ERR_INVALID, "null pointer in int8_linear");
+  QV_REQUIRE(M > 0 && N > 0 && K > 0 && sy > 0.f, QV_ERR_INVALID, "bad int8_linear shape (M=%lld N=%lld K=%lld)", (long long)M,
+             (long long)N, (long long)K);
+  QV_REQUIRE(qv_num_sms() > 0, QV_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  const int BN = N <= 64 ? 64 : 128;
+  CUtensorMap ma, mb;
+  int rc = make_map_i8(&ma, qx, M, K, I8_BM);
+  if (rc) return rc;
+  rc = make_map_i8(&mb, qw, N, K, BN);
+  if (rc) return rc;
+  I8Params kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.M = M; kp.N = N; kp.K = K;
+  kp.kblocks = static_cast<int32_t>((K + I8_BK - 1) / I8_BK);
+  kp.tiles_m = static_cast<int32_t>((M + I8_BM - 1) / I8_BM);
+  kp.tiles_n = static_cast<int32_t>((N + BN - 1) / BN);
+  kp.sx = sx; kp.zx = zx; kp.sw = sw; kp.per_channel = per_channel; kp.wsum = wsum; kp.bias = bias;
+  kp.sy = sy; kp.zy = zy; kp.bias_int = bias_int; kp.qy = qy; kp.y = y;
+  const int64_t items = static_cast<int64_t>(kp.tiles_m) * kp.tiles_n;
+  const int sms = qv_num_sms();
+  const int grid = static_cast<int>(items < sms ? items : sms);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (BN == 64) return launch_i8<64>(ma, mb, kp, grid, st);
+  return launch_i8<128>(ma, mb, kp, grid, st);
+}
+
+extern "C" int qv_quantize_u8(const float* x, int64_t n, const float* scale, const int32_t* zero_point, uint8_t* q, void* stream) {
+  QV_REQUIRE(x && scale && zero_point && q && n > 0, QV_ERR_INVALID, "bad quantize_u8 arguments");
+  QV_REQUIRE(qv_aligned16(x) && (reinterpret_cast<uintptr_t>(q) & 3u) == 0, QV_ERR_INVALID, "quantize_u8 needs aligned buffers");
+  QV_REQUIRE(qv_num_sms() > 0, QV_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  int64_t blocks = ((n >> 2) + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(qv_num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  quantize_u8_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, scale, zero_point, q);
+  return qv_check_launch("qv_quantize_u8");
+}
+
+extern "C" int qv_qparams_from_minmax(const uint32_t* acc, int32_t qmin, int32_t qmax, float* scale, int32_t* zero_point,
+                                      void* stream) {
+  QV_REQUIRE(acc && scale && zero_point && qmax > qmin, QV_ERR_INVALID, "bad qparams_from_minmax arguments");
+  QV_REQUIRE(qv_num_sms() > 0, QV_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  qparams_from_minmax_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(acc, qmin, qmax, scale, zero_point);
+  return qv_check_launch("qv_qparams_from_minmax");
+}

@@ -324,16 +324,53 @@ def attn_ds(P_planes, dP, lddP, rows, T, scale, dS_planes):
                                 dS_planes.stride(1), dS_planes.stride(0), _stream()), "attn_ds")
 
 
-def attn_fwd(qkv_planes, B, T, H, scale, out_planes, qk_scale=None, v_scale=None, lse=None):
+def attn_fwd(qkv_planes, B, T, H, scale, out_planes, qk_scale=None, v_scale=None, lse=None, out_f32=None):
     """Fused softmax(Q K^T * scale) V per (image, head): qkv_planes bf16 [1 or 2, B*T, 3*H*64] -> out_planes bf16
     [2, B*T, H*64] (include/qatvit_b200.h: qv_attn_fwd)."""
-    if qkv_planes.dim() != 3 or qkv_planes.stride(2) != 1 or out_planes.dim() != 3 or out_planes.stride(2) != 1:
+    if qkv_planes.dim() != 3 or qkv_planes.stride(2) != 1 or (out_planes is not None and (out_planes.dim() != 3 or out_planes.stride(2) != 1)):
         raise RuntimeError("qatvit_b200: attn_fwd takes [planes, tokens, cols] plane stacks")
+    ops_, opl = (out_planes.stride(0), out_planes.stride(1)) if out_planes is not None else (0, 0)
     check(_lib.lib().qv_attn_fwd(_p(qkv_planes, torch.bfloat16, "qkv_planes"), qkv_planes.shape[0], qkv_planes.stride(0),
                                  qkv_planes.stride(1), B, T, H, float(scale), _p(qk_scale, torch.float32),
-                                 _p(v_scale, torch.float32), _p(out_planes, torch.bfloat16, "out_planes"),
-                                 out_planes.stride(0), out_planes.stride(1), _p(lse, torch.float32), _stream()), "attn_fwd")
-    return out_planes
+                                 _p(v_scale, torch.float32), _p(out_planes, torch.bfloat16, "out_planes"), ops_, opl,
+                                 _p(out_f32, torch.float32, "out_f32"), _p(lse, torch.float32), _stream()), "attn_fwd")
+    return out_planes if out_planes is not None else out_f32
+
+
+def int8_linear(qx, sx, zx, qw, sw, wsum, bias, sy, zy, qy=None, y=None, engine="x86"):
+    """quantized::linear on the integer tensor cores (include/qatvit_b200.h: qv_int8_linear).  qx uint8 [M,K], qw int8 [N,K]."""
+    M, K = qx.shape
+    N = qw.shape[0]
+    if qy is None and y is None:
+        qy = torch.empty(M, N, dtype=torch.uint8, device=qx.device)
+    check(_lib.lib().qv_int8_linear(_p(qx, torch.uint8, "qx"), M, K, _p(sx, torch.float32, "sx"), _p(zx, torch.int32, "zx"),
+                                    _p(qw, torch.int8, "qw"), N, _p(sw, torch.float32, "sw"), int(sw.numel() > 1),
+                                    _p(wsum, torch.int32, "wsum"), _p(bias, torch.float32, "bias"), float(sy), int(zy),
+                                    int(engine == "qnnpack"), _p(qy, torch.uint8, "qy"), _p(y, torch.float32, "y"), _stream()), "int8_linear")
+    return qy if qy is not None else y
+
+
+def quantize_u8(x, scale, zero_point, out=None):
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    check(_lib.lib().qv_quantize_u8(_p(x, torch.float32, "x"), x.numel(), _p(scale, torch.float32), _p(zero_point, torch.int32),
+                                    _p(out, torch.uint8, "out"), _stream()), "quantize_u8")
+    return out
+
+
+def qparams_from_minmax(acc, qmin, qmax, scale, zero_point):
+    check(_lib.lib().qv_qparams_from_minmax(_p(acc, torch.int32, "acc"), int(qmin), int(qmax), _p(scale, torch.float32),
+                                            _p(zero_point, torch.int32), _stream()), "qparams_from_minmax")
+
+
+def im2col_u8(img, scale, zero_point, B, C, HW, patch, out):
+    check(_lib.lib().qv_im2col_u8(_p(img, torch.float32, "img"), _p(scale, torch.float32), _p(zero_point, torch.int32), B, C, HW,
+                                  patch, _p(out, torch.uint8, "out"), _stream()), "im2col_u8")
+
+
+def gelu_minmax(x, y, acc=None):
+    check(_lib.lib().qv_gelu_minmax(_p(x, torch.float32, "x"), x.numel(), _p(y, torch.float32, "y"), _p(acc, torch.int32),
+                                    _stream()), "gelu_minmax")
 
 
 def head_fwd(x, wq, bias, B, K, N, out, minmax=None):
@@ -378,7 +415,8 @@ def _wrap(name, fn, tag_fn=None):
 
 for _n in ("minmax_reset", "minmax_accumulate", "obs_update", "fq_apply", "fq_weight", "fq_bwd", "split_planes",
            "kd_ce_loss", "splitk_reduce", "resid_ln_fwd", "ln_bwd", "colsum_reduce", "colsum_rows", "gp_planes",
-           "act_planes", "embed_fwd", "im2col_fq", "softmax_planes", "attn_ds", "head_fwd", "head_bwd", "attn_fwd"):
+           "act_planes", "embed_fwd", "im2col_fq", "softmax_planes", "attn_ds", "head_fwd", "head_bwd", "attn_fwd",
+           "int8_linear", "quantize_u8", "qparams_from_minmax", "im2col_u8", "gelu_minmax"):
     globals()[_n] = _wrap(_n, globals()[_n])
 gemm = _wrap("gemm", gemm, _gemm_tag)
 

@@ -1,0 +1,150 @@
+"""GPU parity of the converted-int8 path (BASELINE.json configs[4]; SURVEY.md §8 a12 / §8c config-5 oracle).
+
+Tier 1 (bit-exact): qv_int8_linear codes == torch.ops.quantized.linear codes (the reference's CPU engine) on identical quint8
+inputs -- the committed golden vectors, live random cases at ViT shapes, and EVERY quantized module of a converted student fed
+the CPU run's own inputs; qv_quantize_u8 == torch.quantize_per_tensor; dynamic qparams == the Python observer formula.
+Tier 2: end-to-end logits of the float-glue executor vs the same glue on CPU with stock ops (oracle/int8_ref.py): the glue's
+fp32 LayerNorm / softmax differ in the last bits between CPU and GPU, which can flip a dynamic-quantisation code, so the bound
+is a few output quantisation steps (tolerance written below)."""
+import copy
+import os
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from parity_utils import build_models
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _run_ours(dev, qx, sx, zx, qw_int, sw, bias, sy, zy):
+    from qatvit_b200 import ops
+    qw = qw_int.to(torch.int8).contiguous().to(dev)
+    wsum = qw_int.to(torch.int32).sum(1).to(torch.int32).contiguous().to(dev)
+    M, N = qx.shape[0], qw.shape[0]
+    qy = torch.empty(M, N, dtype=torch.uint8, device=dev)
+    y = torch.empty(M, N, device=dev)
+    sxd = torch.tensor([sx], dtype=torch.float32, device=dev)
+    zxd = torch.tensor([zx], dtype=torch.int32, device=dev)
+    args = (qx.contiguous().to(dev), sxd, zxd, qw, sw.to(torch.float32).contiguous().to(dev), wsum,
+            None if bias is None else bias.to(dev), float(sy), int(zy))
+    ops.int8_linear(*args, qy=qy)
+    ops.int8_linear(*args, y=y)
+    torch.cuda.synchronize()
+    return qy.cpu(), y.cpu()
+
+
+def test_int8_linear_golden_vectors(cuda_dev):
+    z = np.load(os.path.join(GOLDEN, "qlinear_cases.npz"))
+    for i in range(2):
+        sx, zx, sy, zy = z[f"q{i}_p"]
+        qy, y = _run_ours(cuda_dev, torch.from_numpy(z[f"q{i}_qx"]), float(sx), int(zx), torch.from_numpy(z[f"q{i}_qw"]),
+                          torch.from_numpy(z[f"q{i}_sw"]), torch.from_numpy(z[f"q{i}_b"]), float(sy), int(zy))
+        ref = torch.from_numpy(z[f"q{i}_qy"])
+        assert torch.equal(qy, ref)
+        assert torch.equal(y, (ref.float() - float(zy)) * np.float32(sy))
+
+
+@pytest.mark.parametrize("M,N,K", [(197 * 4, 1152, 384), (197 * 4, 384, 1536), (197 * 2, 1536, 384), (196 * 2, 384, 768),
+                                   (8, 10, 384), (130, 24, 96), (1, 16, 16), (300, 200, 144)])
+@pytest.mark.parametrize("per_channel", [True, False])
+def test_int8_linear_vs_quantized_linear(cuda_dev, M, N, K, per_channel):
+    g = torch.Generator().manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=g) * 2
+    w = torch.randn(N, K, generator=g) * 0.05
+    b = torch.randn(N, generator=g) * 0.1
+    sx, zx, sy, zy = 0.0313, 131, 0.0471, 117
+    qx = torch.quantize_per_tensor(x, sx, zx, torch.quint8)
+    if per_channel:
+        sw = (w.abs().amax(1) / 127.0).clamp_min(1e-8)
+        qw = torch.quantize_per_channel(w, sw, torch.zeros(N, dtype=torch.int64), 0, torch.qint8)
+    else:
+        sw = (w.abs().max() / 127.0).reshape(1)
+        qw = torch.quantize_per_tensor(w, float(sw), 0, torch.qint8)
+    ref = torch.ops.quantized.linear(qx, torch.ops.quantized.linear_prepack(qw, b), sy, zy)
+    qy, y = _run_ours(cuda_dev, qx.int_repr(), sx, zx, qw.int_repr(), sw, b, sy, zy)
+    assert torch.equal(qy, ref.int_repr())
+    assert torch.equal(y, ref.dequantize())
+
+
+@pytest.mark.parametrize("shape", [(4, 197, 384), (3, 5, 7), (1, 3, 64, 64)])
+def test_quantize_and_dynamic_qparams(cuda_dev, shape):
+    from qatvit_b200 import ops
+    from oracle import int8_ref
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(shape, generator=g) * 3 + 0.7
+    acc = ops.new_minmax(cuda_dev)
+    xd = x.to(cuda_dev)
+    ops.minmax_accumulate(xd, acc)
+    s = torch.empty(1, device=cuda_dev)
+    zp = torch.empty(1, dtype=torch.int32, device=cuda_dev)
+    ops.qparams_from_minmax(acc[0], 0, 255, s, zp)
+    s_ref, z_ref = int8_ref.dynamic_qparams(x)
+    assert float(s) == np.float32(s_ref) and int(zp) == z_ref
+    q = ops.quantize_u8(xd, s, zp)
+    ref = torch.quantize_per_tensor(x, s_ref, z_ref, torch.quint8).int_repr()
+    assert torch.equal(q.cpu(), ref)
+
+
+def _converted(backend, sname, tname, img, B):
+    from torch.ao.quantization import convert
+    vr, prepared, teacher = build_models(backend, sname, tname, img)
+    images, labels = vr.synthetic_batch(B, seed=3, img=img)
+    hp = dict(vr.DEFAULT_HPARAMS)
+    for _ in range(2):                                   # give the observers a couple of EMA steps
+        vr.distill_step(prepared, teacher, images, labels, None, hp, clip=False)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        conv = convert(copy.deepcopy(prepared).eval(), inplace=False)      # ref qat_trainer.py:377-379
+    return conv, images
+
+
+@pytest.mark.parametrize("backend,sname,img,B", [("fbgemm", "vit_test_tiny", 64, 4), ("qnnpack", "vit_test_tiny", 64, 3),
+                                                 ("fbgemm", "vit_small_patch16_224", 224, 2)])
+def test_converted_student_per_layer_and_end_to_end(cuda_dev, backend, sname, img, B):
+    from qatvit_b200 import ops
+    from qatvit_b200.int8 import ConvertedStudent
+    from oracle import int8_ref
+    conv, images = _converted(backend, sname, "vit_test_teacher", img, B)
+    trace = {}
+    ref_logits = int8_ref.converted_forward(conv, images, trace)
+    ex = ConvertedStudent(conv, B, cuda_dev)
+    # tier 1: every quantized module, on the CPU run's own quint8 input, gives bit-identical codes
+    qlins = {"head": ex.head}
+    for i, blk in enumerate(ex.blocks):
+        qlins.update({f"blocks.{i}.attn.qkv": blk["qkv"], f"blocks.{i}.attn.proj": blk["proj"],
+                      f"blocks.{i}.mlp.fc1": blk["fc1"], f"blocks.{i}.mlp.fc2": blk["fc2"]})
+    assert set(qlins) | {"patch_embed.proj"} == set(trace)
+    for name, ql in qlins.items():
+        qx, qy = trace[name]
+        x2 = qx.int_repr().reshape(-1, ql.K).contiguous().to(cuda_dev)
+        sx = torch.tensor([qx.q_scale()], dtype=torch.float32, device=cuda_dev)
+        zx = torch.tensor([qx.q_zero_point()], dtype=torch.int32, device=cuda_dev)
+        got = ops.int8_linear(x2, sx, zx, ql.qw, ql.sw, ql.wsum, ql.bias, ql.sy, ql.zy)
+        assert torch.equal(got.cpu(), qy.int_repr().reshape(-1, ql.N)), name
+    # the conv: quantise + im2col on device from the float image, then the same int8 GEMM
+    qx, qy = trace["patch_embed.proj"]
+    ops.im2col_u8(images.to(cuda_dev), ex.in_scale, ex.in_zp, B, 3, ex.HW, ex.ps, ex.q_img)
+    got = ops.int8_linear(ex.q_img, ex.in_scale, ex.in_zp, ex.conv.qw, ex.conv.sw, ex.conv.wsum, ex.conv.bias, ex.conv.sy,
+                          ex.conv.zy)
+    assert torch.equal(got.cpu().view(B, ex.P, ex.D), qy.int_repr().flatten(2).transpose(1, 2))
+    # tier 2: end to end through the float glue
+    ours = {}
+    logits = ex(images.to(cuda_dev), ours)
+    torch.cuda.synchronize()
+    # (a) up to the first dynamic quantisation everything is decided on identical inputs: same qparams, and the codes differ
+    #     only where the fp32 LayerNorm of the two sides rounds differently across a .5 boundary (<= 1 code on < 0.1 %)
+    qh, s, z = ours["blocks.0.attn.qkv"]
+    ref_qx = trace["blocks.0.attn.qkv"][0]
+    assert abs(float(s) - ref_qx.q_scale()) <= 1e-6 * ref_qx.q_scale() and int(z) == ref_qx.q_zero_point()
+    d = (qh.cpu().int() - ref_qx.int_repr().reshape(qh.shape).int()).abs()
+    assert int(d.max()) <= 1 and float((d > 0).float().mean()) < 1e-3
+    # (b) logits: a flipped code perturbs everything downstream (12 blocks x 4 dynamic re-quantisations), so the bound is a
+    #     few output quantisation steps of the head (128-level grid): 6 steps max, relative L2 < 8e-2
+    step = conv.model.head.scale
+    diff = logits.cpu() - ref_logits
+    assert float(diff.abs().max()) <= 6.0 * step + 1e-6
+    assert float(diff.norm() / ref_logits.norm()) < 8e-2
