@@ -163,9 +163,10 @@ int qv_gp_planes(const float* g, const float* y_raw, const float* y_scale, const
                  const float* w_scale, int32_t w_scale_per_channel, int32_t gelu, int64_t R, int64_t N, int32_t remap_P,
                  int32_t remap_T, uint16_t* out_planes, int64_t plane_stride, float* bias_partials, int32_t rows_per_block,
                  void* stream);
-/* out planes = [GELU](FQ(y_raw)) elementwise (n % 4 == 0). */
+/* out planes = [GELU](FQ(y_raw)) elementwise (n % 4 == 0).  codes_only != 0: ONE plane of centred integer codes (q - zp),
+ * exact in bf16 -- FQ(y) = code * scale with the scale applied by the consumer (integer-code attention kernels). */
 int qv_act_planes(const float* y_raw, const float* y_scale, const int32_t* y_zp, int32_t qmin, int32_t qmax, int32_t gelu,
-                  int64_t n, uint16_t* out_planes, int64_t plane_stride, void* stream);
+                  int32_t codes_only, int64_t n, uint16_t* out_planes, int64_t plane_stride, void* stream);
 /* x0 = cat(cls, FQ(p_raw)) + pos  ->  [B*(P+1), D] fp32 (timm VisionTransformer._pos_embed). */
 int qv_embed_fwd(const float* p_raw, const float* p_scale, const int32_t* p_zp, int32_t qmin, int32_t qmax, const float* cls,
                  const float* pos, int64_t B, int32_t P, int32_t D, float* x0, void* stream);
@@ -193,6 +194,12 @@ int qv_attn_ds(const uint16_t* P, int64_t ldP, int64_t p_plane_stride, const flo
 int qv_attn_fwd(const uint16_t* qkv_planes, int32_t n_planes, int64_t plane_stride, int64_t ld, int32_t B, int32_t T,
                 int32_t H, float scale, const float* qk_scale, const float* v_scale, uint16_t* out_planes,
                 int64_t out_plane_stride, int64_t out_ld, float* out_f32, float* lse, void* stream);
+/* Fused attention backward for integer-code operands (the QAT student; autograd of F.scaled_dot_product_attention):
+ * recomputes P from the codes and the forward's lse on the tensor cores and writes dQ | dK | dV (gradients w.r.t. the
+ * fake-quantised q, k, v = s * codes) into g_qkv fp32 [B*T][3*H*64].  qkv_codes: ONE bf16 plane [B*T][ld]; do_planes: bf16
+ * hi/lo planes [2][B*T][do_ld] of dL/dO; lse: fp32 [B*H*T] (qv_attn_fwd); qscale: device scalar s (NULL = 1).  T <= 224. */
+int qv_attn_bwd(const uint16_t* qkv_codes, int64_t ld, const float* qscale, const uint16_t* do_planes, int64_t do_plane_stride,
+                int64_t do_ld, const float* lse, int32_t B, int32_t T, int32_t H, float scale, float* g_qkv, void* stream);
 /* classifier head (D -> num_classes), exact fp32: out = x wq^T + bias (+ fused output-observer min/max). */
 int qv_head_fwd(const float* x, const float* wq, const float* bias, int32_t B, int32_t K, int32_t N, float* out,
                 uint32_t* minmax, void* stream);

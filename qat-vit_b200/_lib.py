@@ -81,13 +81,14 @@ _SIGNATURES = {
     "qv_colsum_rows": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int32, _P]),
     "qv_gp_planes": (c_int, [_P, _P, _P, _P, c_int32, c_int32, _P, c_int32, c_int32, c_int64, c_int64, c_int32, c_int32,
                              _P, c_int64, _P, c_int32, _P]),
-    "qv_act_planes": (c_int, [_P, _P, _P, c_int32, c_int32, c_int32, c_int64, _P, c_int64, _P]),
+    "qv_act_planes": (c_int, [_P, _P, _P, c_int32, c_int32, c_int32, c_int32, c_int64, _P, c_int64, _P]),
     "qv_embed_fwd": (c_int, [_P, _P, _P, c_int32, c_int32, _P, _P, c_int64, c_int32, c_int32, _P, _P]),
     "qv_im2col_fq": (c_int, [_P, _P, _P, c_int32, c_int32, c_int64, c_int32, c_int32, c_int32, _P, _P, _P]),
     "qv_softmax_planes": (c_int, [_P, c_int64, c_int64, c_int32, c_float, _P, c_int64, c_int64, _P]),
     "qv_attn_ds": (c_int, [_P, c_int64, c_int64, _P, c_int64, c_int64, c_int32, c_float, _P, c_int64, c_int64, _P]),
     "qv_attn_fwd": (c_int, [_P, c_int32, c_int64, c_int64, c_int32, c_int32, c_int32, c_float, _P, _P, _P, c_int64, c_int64,
                             _P, _P, _P]),
+    "qv_attn_bwd": (c_int, [_P, c_int64, _P, _P, c_int64, c_int64, _P, c_int32, c_int32, c_int32, c_float, _P, _P]),
     "qv_int8_linear": (c_int, [_P, c_int64, c_int64, _P, _P, _P, c_int64, _P, c_int32, _P, _P, c_float, c_int32, c_int32, _P, _P,
                                _P]),
     "qv_quantize_u8": (c_int, [_P, c_int64, _P, _P, _P, _P]),

@@ -358,6 +358,309 @@ int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap&
   return qv_check_launch("qv_attn_fwd");
 }
 
+
+// ====================================================================================================================
+// Fused attention BACKWARD for integer-code operands (the QAT student: Q, K, V = s * codes), one (image, head) per item.
+//
+// Given dO (bf16 hi/lo planes), the codes and the forward's logsumexp, recomputes the probabilities on the tensor cores and
+// produces dQ, dK, dV (fp32) without ever writing scores to HBM.  Replaces the autograd of F.scaled_dot_product_attention
+// (4 batched GEMMs + softmax-backward passes in the unfused path).  With z = scale * Q K^T, P = softmax(z):
+//     dP = dO V^T,  delta_i = sum_j P_ij dP_ij,  dz = P o (dP - delta),  dQ = scale dz K,  dK = scale dz^T Q,  dV = P^T dO.
+// TMEM accumulators are row-per-lane, so the kernel runs two kinds of sub-pass per 128-row tile:
+//   pass A (lanes = queries):  R0 = Q K^T, R1 = dO V^T  -> threads: delta_i, dz (bf16 hi/lo, in place over R1) -> dQ = dz K
+//   pass B (lanes = keys):     R0 = K Q^T, R1 = V dO^T  -> threads: P^T, dz^T (in place)  -> dV = P^T dO, dK = dz^T Q
+// (recomputing S / dP transposed costs two small extra MMAs and saves staging dz through shared memory).  All second-stage
+// products are TS-mode MMAs (A from TMEM); the same [tokens x 64] shared-memory tiles serve as K-major operands of the first
+// stage and MN-major operands of the second.
+// TMEM: R0 [0,224) | R1 [224,448) | ACC0 [448,512) (dQ / dV) ; dK re-uses [0,64) once P^T has been consumed.
+// Warps: 0 TMA, 1 MMA, 2-9 compute (two warps per TMEM lane quarter, alternating 32-column chunks).
+// ====================================================================================================================
+constexpr int BW_TILE_BYTES = 256 * HD * 2;     // 32 KB: up to 256 token rows x 64 bf16 (rows >= T zero-filled by TMA)
+constexpr int BW_SMEM_BYTES = 5 * BW_TILE_BYTES + 4096 /*lse, delta, partials*/ + 1024 /*align*/ + 256 /*barriers*/;
+
+struct AttnBwdParams {
+  int32_t B, T, H;
+  int32_t n_keys, m_tiles;
+  float scale;
+  const float* qscale;      // device scalar s (Q = K = V scale); may be null (= 1)
+  const float* lse;         // [B*H*T] from the forward
+  float* g_qkv;             // [B*T][3*D]: dQ | dK | dV column blocks
+};
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
+                   const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + BW_TILE_BYTES;
+  uint8_t* sV = sK + BW_TILE_BYTES;
+  uint8_t* sDOh = sV + BW_TILE_BYTES;
+  uint8_t* sDOl = sDOh + BW_TILE_BYTES;
+  float* lse2_s = reinterpret_cast<float*>(sDOl + BW_TILE_BYTES);   // [256] lse * log2(e)
+  float* delta_s = lse2_s + 256;                                     // [256] sum_j P_ij dP_raw_ij
+  float* part_s = delta_s + 256;                                     // [2 sub-pass parities][2 warps of a pair][128 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(part_s + 512);
+  uint64_t* ld_full = bars + 0;
+  uint64_t* ld_empty = bars + 1;
+  uint64_t* mma1_done = bars + 2;
+  uint64_t* cmp_done = bars + 3;
+  uint64_t* acc_done = bars + 4;
+  uint64_t* acc2_done = bars + 5;
+  uint64_t* epi_done = bars + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int D = p.H * HD;
+  const int num_items = p.B * p.H;
+  const int n_keys = p.n_keys;
+  const int mt = p.m_tiles;
+  const int ksteps = n_keys >> 4;
+  constexpr uint32_t R1_COL = S_COLS, ACC0_COL = O0_COL;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&map_qkv);
+    prefetch_tensormap(&map_do);
+    mbar_init(ld_full, 1);
+    mbar_init(ld_empty, 1);
+    mbar_init(mma1_done, 1);
+    mbar_init(cmp_done, 256);
+    mbar_init(acc_done, 1);
+    mbar_init(acc2_done, 1);
+    mbar_init(epi_done, 256);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      int local = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
+        const int b = item / p.H, h = item % p.H;
+        mbar_wait(ld_empty, static_cast<uint32_t>(local & 1) ^ 1);
+        mbar_expect_tx(ld_full, 5 * BW_TILE_BYTES);
+        tma_load_4d(sQ, &map_qkv, ld_full, h * HD, 0, b, 0);
+        tma_load_4d(sK, &map_qkv, ld_full, D + h * HD, 0, b, 0);
+        tma_load_4d(sV, &map_qkv, ld_full, 2 * D + h * HD, 0, b, 0);
+        tma_load_4d(sDOh, &map_do, ld_full, h * HD, 0, b, 0);
+        tma_load_4d(sDOl, &map_do, ld_full, h * HD, 0, b, 1);
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      const uint32_t idesc_ss = umma_idesc_bf16(128, n_keys, false, false);
+      const uint32_t idesc_ts = umma_idesc_bf16(128, HD, false, true);
+      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aDh = smem_u32(sDOh), aDl = smem_u32(sDOl);
+      const uint32_t r0 = tmem_base, r1 = tmem_base + R1_COL, acc0 = tmem_base + ACC0_COL, acc1 = tmem_base;
+      // first-stage SS product: D[tmem] (+)= A[rows tile*128.., K-major] * B[rows 0..n_keys, K-major]^T over d = 64
+      auto ss = [&](uint32_t d_tmem, uint32_t a_tile, int tile, uint32_t b_tile, bool accumulate) {
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) {
+          const uint64_t da = umma_smem_desc(a_tile + tile * (128 * 128) + k * 32, 16u, 1024u);
+          const uint64_t db = umma_smem_desc(b_tile + k * 32, 16u, 1024u);
+          umma_bf16(d_tmem, da, db, idesc_ss, (accumulate || k > 0) ? 1u : 0u);
+        }
+      };
+      // second-stage TS product: D[tmem] (+)= A[tmem region, plane] * B[[tokens x 64] tile, MN-major] over the tokens
+      auto ts = [&](uint32_t d_tmem, uint32_t a_region, int plane, uint32_t b_tile, bool accumulate) {
+        for (int kk = 0; kk < ksteps; ++kk) {
+          const uint32_t a_tmem = a_region + static_cast<uint32_t>((kk >> 1) * 32 + plane * 16 + (kk & 1) * 8);
+          const uint64_t db = umma_smem_desc(b_tile + kk * 2048, 8192u, 1024u);
+          umma_bf16_ts(d_tmem, a_tmem, db, idesc_ts, (accumulate || kk > 0) ? 1u : 0u);
+        }
+      };
+      uint32_t sp = 0;          // running sub-pass counter (phase of mma1_done / cmp_done / acc_done / epi_done)
+      uint32_t spb = 0;         // running pass-B counter (phase of acc2_done)
+      int local = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
+        mbar_wait(ld_full, static_cast<uint32_t>(local & 1));
+        tc_fence_after();
+        for (int g = 0; g < mt; ++g, ++sp) {                     // ---- pass A: lanes = queries of tile g ----
+          mbar_wait(epi_done, (sp & 1) ^ 1);
+          tc_fence_after();
+          ss(r0, aQ, g, aK, false);                              // S = Q K^T
+          ss(r1, aDh, g, aV, false);                             // dP = dO V^T (hi + lo)
+          ss(r1, aDl, g, aV, true);
+          umma_commit(mma1_done);
+          mbar_wait(cmp_done, sp & 1);
+          tc_fence_after();
+          ts(acc0, r1, 0, aK, false);                            // dQ = dz K
+          ts(acc0, r1, 1, aK, true);
+          umma_commit(acc_done);
+        }
+        for (int kt = 0; kt < mt; ++kt, ++sp, ++spb) {           // ---- pass B: lanes = keys of tile kt ----
+          mbar_wait(epi_done, (sp & 1) ^ 1);
+          tc_fence_after();
+          ss(r0, aK, kt, aQ, false);                             // S^T = K Q^T
+          ss(r1, aV, kt, aDh, false);                            // dP^T = V dO^T (hi + lo)
+          ss(r1, aV, kt, aDl, true);
+          umma_commit(mma1_done);
+          mbar_wait(cmp_done, sp & 1);
+          tc_fence_after();
+          ts(acc0, r0, 0, aDh, false);                           // dV = P^T dO : (hi,hi) (hi,lo) (lo,hi)
+          ts(acc0, r0, 0, aDl, true);
+          ts(acc0, r0, 1, aDh, true);
+          umma_commit(acc_done);
+          mbar_wait(acc_done, sp & 1);                           // P^T consumed: [0,64) may now hold dK
+          tc_fence_after();
+          ts(acc1, r1, 0, aQ, false);                            // dK = dz^T Q
+          ts(acc1, r1, 1, aQ, true);
+          umma_commit(acc2_done);
+        }
+        umma_commit(ld_empty);                                   // every MMA that reads this item's tiles has completed
+      }
+    }
+  } else {
+    // =============================== compute warps ===============================
+    const int cw = warp - 2;
+    const int q = warp & 3;
+    const int par = cw >> 2;
+    const int row = q * 32 + lane;               // row inside the 128-row tile == TMEM lane
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t r0 = tmem_base + lane_addr, r1 = r0 + R1_COL, acc0 = r0 + ACC0_COL, acc1 = r0;
+    const int nch = (n_keys + 31) >> 5;
+    const float s = p.qscale ? __ldg(p.qscale) : 1.0f;
+    const float c2 = p.scale * s * s * 1.4426950408889634f;
+    const float gscale = p.scale * s * s;        // dQ, dK factor (see header comment)
+    const int ctid = threadIdx.x - 64;           // 0..255
+    uint32_t sp = 0, spb = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int b = item / p.H, h = item % p.H;
+      const float* lse_bh = p.lse + (static_cast<int64_t>(b) * p.H + h) * p.T;
+      asm volatile("bar.sync 9, 256;" ::: "memory");            // previous item's pass B has finished reading lse2_s / delta_s
+      lse2_s[ctid] = (ctid < p.T) ? __ldg(lse_bh + ctid) * 1.4426950408889634f : 0.0f;
+      float* grow_base = p.g_qkv + static_cast<int64_t>(b) * p.T * (3 * D) + h * HD + par * 32;
+      // ------------------------------ pass A ------------------------------
+      for (int g = 0; g < mt; ++g, ++sp) {
+        const int i = g * 128 + row;
+        const float Li = (i < p.T) ? __ldg(lse_bh + i) * 1.4426950408889634f : 0.0f;
+        mbar_wait(mma1_done, sp & 1);
+        tc_fence_after();
+        float dpart = 0.f;
+#pragma unroll 1
+        for (int c = par; c < nch; c += 2) {
+          uint32_t sv[32], dv[32];
+          tmem_ld_32x32(r0 + c * 32, sv);
+          tmem_ld_32x32(r1 + c * 32, dv);
+          tmem_ld_wait();
+          const int nvalid = p.T - c * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float pj = (j < nvalid) ? ex2_approx(fmaf(__uint_as_float(sv[j]), c2, -Li)) : 0.f;
+            dpart = fmaf(pj, __uint_as_float(dv[j]), dpart);
+          }
+        }
+        float* part = part_s + (sp & 1) * 256;
+        part[par * 128 + row] = dpart;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+        const float delta = part[row] + part[128 + row];
+        if (par == 0) delta_s[g * 128 + row] = delta;
+#pragma unroll 1
+        for (int c = par; c < nch; c += 2) {
+          uint32_t sv[32], dv[32], pk[32];
+          tmem_ld_32x32(r0 + c * 32, sv);
+          tmem_ld_32x32(r1 + c * 32, dv);
+          tmem_ld_wait();
+          const int nvalid = p.T - c * 32;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float p0 = (2 * j < nvalid) ? ex2_approx(fmaf(__uint_as_float(sv[2 * j]), c2, -Li)) : 0.f;
+            const float p1 = (2 * j + 1 < nvalid) ? ex2_approx(fmaf(__uint_as_float(sv[2 * j + 1]), c2, -Li)) : 0.f;
+            split_pack2(p0 * (__uint_as_float(dv[2 * j]) - delta), p1 * (__uint_as_float(dv[2 * j + 1]) - delta), pk[j], pk[16 + j]);
+          }
+          tmem_st_32x32(r1 + c * 32, pk);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(cmp_done);
+        // dQ tile: this warp stores columns par*32 .. par*32+31 of its 32 rows
+        mbar_wait(acc_done, sp & 1);
+        tc_fence_after();
+        uint32_t o[32];
+        tmem_ld_32x32(acc0 + par * 32, o);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(epi_done);
+        if (i < p.T) {
+          float* dst = grow_base + static_cast<int64_t>(i) * (3 * D);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(__uint_as_float(o[4 * j]) * gscale, __uint_as_float(o[4 * j + 1]) * gscale,
+                                                                  __uint_as_float(o[4 * j + 2]) * gscale, __uint_as_float(o[4 * j + 3]) * gscale);
+        }
+      }
+      asm volatile("bar.sync 9, 256;" ::: "memory");            // lse2_s and delta_s complete for every query row
+      // ------------------------------ pass B ------------------------------
+      for (int kt = 0; kt < mt; ++kt, ++sp, ++spb) {
+        const int jrow = kt * 128 + row;                          // key index of this lane
+        mbar_wait(mma1_done, sp & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = par; c < nch; c += 2) {
+          uint32_t sv[32], dv[32], pp[32], pz[32];
+          tmem_ld_32x32(r0 + c * 32, sv);
+          tmem_ld_32x32(r1 + c * 32, dv);
+          tmem_ld_wait();
+          const int nvalid = p.T - c * 32;                        // valid query columns of this chunk
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float2 L = *reinterpret_cast<const float2*>(lse2_s + c * 32 + 2 * j);      // broadcast reads
+            const float2 dl = *reinterpret_cast<const float2*>(delta_s + c * 32 + 2 * j);
+            const float p0 = (2 * j < nvalid) ? ex2_approx(fmaf(__uint_as_float(sv[2 * j]), c2, -L.x)) : 0.f;
+            const float p1 = (2 * j + 1 < nvalid) ? ex2_approx(fmaf(__uint_as_float(sv[2 * j + 1]), c2, -L.y)) : 0.f;
+            split_pack2(p0, p1, pp[j], pp[16 + j]);
+            split_pack2(p0 * (__uint_as_float(dv[2 * j]) - dl.x), p1 * (__uint_as_float(dv[2 * j + 1]) - dl.y), pz[j], pz[16 + j]);
+          }
+          tmem_st_32x32(r0 + c * 32, pp);
+          tmem_st_32x32(r1 + c * 32, pz);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(cmp_done);
+        uint32_t o[32];
+        mbar_wait(acc_done, sp & 1);                              // dV
+        tc_fence_after();
+        tmem_ld_32x32(acc0 + par * 32, o);
+        tmem_ld_wait();
+        if (jrow < p.T) {
+          float* dst = grow_base + static_cast<int64_t>(jrow) * (3 * D) + 2 * D;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(__uint_as_float(o[4 * j]), __uint_as_float(o[4 * j + 1]),
+                                                                  __uint_as_float(o[4 * j + 2]), __uint_as_float(o[4 * j + 3]));
+        }
+        mbar_wait(acc2_done, spb & 1);                            // dK
+        tc_fence_after();
+        tmem_ld_32x32(acc1 + par * 32, o);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(epi_done);
+        if (jrow < p.T) {
+          float* dst = grow_base + static_cast<int64_t>(jrow) * (3 * D) + D;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(__uint_as_float(o[4 * j]) * gscale, __uint_as_float(o[4 * j + 1]) * gscale,
+                                                                  __uint_as_float(o[4 * j + 2]) * gscale, __uint_as_float(o[4 * j + 3]) * gscale);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace
 
 extern "C" int qv_attn_fwd(const uint16_t* qkv_planes, int32_t n_planes, int64_t plane_stride, int64_t ld, int32_t B,
@@ -404,4 +707,45 @@ extern "C" int qv_attn_fwd(const uint16_t* qkv_planes, int32_t n_planes, int64_t
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (n_planes == 2) return launch_attn<2>(mq, mk, mv, ap, grid, st);
   return launch_attn<1>(mq, mk, mv, ap, grid, st);
+}
+
+extern "C" int qv_attn_bwd(const uint16_t* qkv_codes, int64_t ld, const float* qscale, const uint16_t* do_planes,
+                           int64_t do_plane_stride, int64_t do_ld, const float* lse, int32_t B, int32_t T, int32_t H, float scale,
+                           float* g_qkv, void* stream) {
+  QV_REQUIRE(qkv_codes && do_planes && lse && g_qkv && B > 0 && T > 0 && H > 0, QV_ERR_INVALID, "bad attn_bwd arguments");
+  QV_REQUIRE(T <= 224, QV_ERR_UNSUPPORTED, "fused attention holds all keys in one tile: T <= 224 (got %d)", T);
+  QV_REQUIRE(ld >= 3LL * H * HD && do_ld >= static_cast<int64_t>(H) * HD, QV_ERR_INVALID, "row pitches too small");
+  QV_REQUIRE(qv_aligned16(g_qkv), QV_ERR_INVALID, "g_qkv must be 16-byte aligned");
+  QV_REQUIRE(qv_num_sms() > 0, QV_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  AttnBwdParams ap;
+  memset(&ap, 0, sizeof(ap));
+  ap.B = B; ap.T = T; ap.H = H;
+  ap.n_keys = (T + 15) / 16 * 16;
+  ap.m_tiles = (T + 127) / 128;
+  ap.scale = scale;
+  ap.qscale = qscale;
+  ap.lse = lse;
+  ap.g_qkv = g_qkv;
+  qv_operand op;
+  memset(&op, 0, sizeof(op));
+  op.ptr = qkv_codes; op.ld = ld; op.plane_stride = 0; op.rows = T; op.cols = 3LL * H * HD;
+  op.nb = B; op.batch_stride = static_cast<int64_t>(T) * ld;
+  CUtensorMap mq, md;
+  int rc = make_map(&mq, op, 1, 256);
+  if (rc) return rc;
+  op.ptr = do_planes; op.ld = do_ld; op.plane_stride = do_plane_stride; op.cols = static_cast<int64_t>(H) * HD;
+  op.batch_stride = static_cast<int64_t>(T) * do_ld;
+  rc = make_map(&md, op, 2, 256);
+  if (rc) return rc;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(qv_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM_BYTES);
+  });
+  QV_REQUIRE(attr_err == cudaSuccess, QV_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+  const int items = B * H;
+  const int sms = qv_num_sms();
+  const int grid = items < sms ? items : sms;
+  qv_attn_bwd_kernel<<<grid, AT_THREADS, BW_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(mq, md, ap);
+  return qv_check_launch("qv_attn_bwd");
 }

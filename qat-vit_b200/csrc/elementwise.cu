@@ -245,15 +245,28 @@ __global__ void gp_planes_kernel(const float* __restrict__ g, const float* __res
 // ------------------------------------------------------------------------------------------------
 // out planes = [GELU]( FQ(y_raw) )   (fc1 -> fc2 operand; qkv pre-pass with gelu = 0; teacher without FQ)
 // ------------------------------------------------------------------------------------------------
+// codes_only: write ONE plane holding the centred integer code (q - zp), exact in bf16 (|code| <= 255): the operand format
+// of the integer-code attention kernels (FQ(x) = code * scale, the scale is applied by the consumer).
 __global__ void __launch_bounds__(256) act_planes_kernel(const float* __restrict__ y_raw, const float* y_scale,
-                                                         const int32_t* y_zp, int qmin, int qmax, int gelu, int64_t n,
-                                                         __nv_bfloat16* __restrict__ out, int64_t plane_stride) {
+                                                         const int32_t* y_zp, int qmin, int qmax, int gelu, int codes_only,
+                                                         int64_t n, __nv_bfloat16* __restrict__ out, int64_t plane_stride) {
   const OptQ oq = load_optq(y_scale, y_zp, qmin, qmax);
   const int64_t n4 = n >> 2;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4; i += stride) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(y_raw) + i);
     float a[4] = {v.x, v.y, v.z, v.w};
+    if (codes_only) {
+      __nv_bfloat16 c[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float cc;
+        qv_fq(a[j], oq.q, nullptr, &cc);
+        c[j] = __float2bfloat16_rn(cc);
+      }
+      *reinterpret_cast<uint2*>(out + i * 4) = *reinterpret_cast<uint2*>(c);
+      continue;
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (oq.on) a[j] = qv_fq(a[j], oq.q, nullptr, nullptr);
@@ -627,12 +640,14 @@ extern "C" int qv_gp_planes(const float* g, const float* y_raw, const float* y_s
 }
 
 extern "C" int qv_act_planes(const float* y_raw, const float* y_scale, const int32_t* y_zp, int32_t qmin, int32_t qmax,
-                             int32_t gelu, int64_t n, uint16_t* out_planes, int64_t plane_stride, void* stream) {
+                             int32_t gelu, int32_t codes_only, int64_t n, uint16_t* out_planes, int64_t plane_stride,
+                             void* stream) {
   QV_REQUIRE(y_raw && out_planes && n > 0 && n % 4 == 0, QV_ERR_INVALID, "bad act_planes arguments (n must be a multiple of 4)");
   QV_REQUIRE((y_scale == nullptr) == (y_zp == nullptr), QV_ERR_INVALID, "y_scale and y_zp go together");
+  QV_REQUIRE(!codes_only || (y_scale && !gelu), QV_ERR_INVALID, "codes_only needs quantisation parameters and no GELU");
   QV_NEED_GPU();
   act_planes_kernel<<<ew_blocks(n >> 2), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      y_raw, y_scale, y_zp, qmin, qmax, gelu, n, reinterpret_cast<__nv_bfloat16*>(out_planes), plane_stride);
+      y_raw, y_scale, y_zp, qmin, qmax, gelu, codes_only, n, reinterpret_cast<__nv_bfloat16*>(out_planes), plane_stride);
   return qv_check_launch("qv_act_planes");
 }
 

@@ -491,14 +491,15 @@ extern "C" int qv_gemm_bf16(const qv_gemm_args* a, void* stream) {
   const int nbatch = a->nbatch > 1 ? a->nbatch : 1;
   QV_REQUIRE(!(splits > 1 && nbatch > 1), QV_ERR_UNSUPPORTED, "split-K and batching are mutually exclusive");
   QV_REQUIRE(qv_num_sms() > 0, QV_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
-  const int BN = a->tile_n > 0 ? a->tile_n : pick_bn(a->N);
-  QV_REQUIRE(BN == 64 || BN == 128 || BN == 192, QV_ERR_UNSUPPORTED, "tile_n must be 64, 128 or 192");
   const bool planes_out = a->out_kind == 1;
+  int BN = a->tile_n > 0 ? a->tile_n : pick_bn(a->N);
+  if (planes_out && a->tile_n <= 0 && BN < 128) BN = 128;      // plane output is instantiated for 128 / 192 wide tiles
+  QV_REQUIRE(BN == 64 || BN == 128 || BN == 192, QV_ERR_UNSUPPORTED, "tile_n must be 64, 128 or 192");
   QV_REQUIRE(a->out_kind == 0 || a->out_kind == 1, QV_ERR_INVALID, "out_kind must be 0 (fp32) or 1 (bf16 hi/lo planes)");
   QV_REQUIRE(a->act == 0 || (a->act == 1 && planes_out), QV_ERR_UNSUPPORTED, "act = GELU needs out_kind = 1 (plane output)");
   if (planes_out) {
-    QV_REQUIRE(splits == 1 && a->a_planes == 2 && a->b_planes == 2 && !a->a.mn_major && !a->b.mn_major && BN >= 128,
-               QV_ERR_UNSUPPORTED, "plane output is instantiated for unsplit K-major (2,2)-plane GEMMs with tile_n 128/192");
+    QV_REQUIRE(splits == 1 && a->a_planes == 2 && !a->a.mn_major && !a->b.mn_major && BN >= 128, QV_ERR_UNSUPPORTED,
+               "plane output is instantiated for unsplit K-major (2,1)- and (2,2)-plane GEMMs with tile_n 128/192");
     QV_REQUIRE(a->N % 64 == 0, QV_ERR_UNSUPPORTED, "plane output needs N to be a multiple of 64");
     QV_REQUIRE(!a->col_scale && !a->col_rscale && !a->alpha && !a->minmax, QV_ERR_UNSUPPORTED,
                "plane output takes a bias term only (no scale / alpha / observer)");
@@ -557,6 +558,10 @@ extern "C" int qv_gemm_bf16(const qv_gemm_args* a, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool amn = a->a.mn_major != 0, bmn = a->b.mn_major != 0;
   if (planes_out) {
+    if (a->b_planes == 1) {
+      if (BN == 128) return launch<128, 2, 1, false, false, 1>(ma, mb, mo, kp, grid, st);
+      return launch<192, 2, 1, false, false, 1>(ma, mb, mo, kp, grid, st);
+    }
     if (BN == 128) return launch<128, 2, 2, false, false, 1>(ma, mb, mo, kp, grid, st);
     return launch<192, 2, 2, false, false, 1>(ma, mb, mo, kp, grid, st);
   }

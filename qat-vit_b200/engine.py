@@ -242,7 +242,8 @@ class TeacherEngine:
 class StudentEngine:
     """Forward + hand-written backward of the prepared (torch.ao eager-mode QAT) ``QATWrapper`` student."""
 
-    def __init__(self, student: nn.Module, batch: int, hparams: Dict, grad_buffer: Optional[torch.Tensor] = None):
+    def __init__(self, student: nn.Module, batch: int, hparams: Dict, grad_buffer: Optional[torch.Tensor] = None,
+                 fused_attention: Optional[bool] = None):
         self.student = student
         vit = self.vit = student.model
         dev = next(student.parameters()).device
@@ -292,6 +293,14 @@ class StudentEngine:
             off += p.numel()
         self.attach_grads()
 
+        # Fused attention works on the integer codes of the fake-quantised q, k, v (FQ(x) = code * scale): one exact bf16
+        # plane instead of hi/lo planes, scores never leave tensor memory, backward recomputes P from the saved logsumexp.
+        # It needs fake-quant to be ON for every qkv output observer (the reference never turns it off); the flags are read
+        # once here -- if any is off, fall back to the unfused hi/lo-plane kernels.
+        if fused_attention is None:
+            fused_attention = all(int(ql["qkv"].afq.fake_quant_enabled.item()) != 0 for ql in self.lin)
+        self.fused_attn = bool(fused_attention)
+
         # ---- forward activations (saved for backward) ----
         self.img_codes = e(1, B * d.P, d.Kc, dt=bf)
         self.p_raw = e(B * d.P, D)
@@ -300,8 +309,12 @@ class StudentEngine:
         self.h1p = [e(2, M, D, dt=bf) for _ in range(L)]
         self.h2p = [e(2, M, D, dt=bf) for _ in range(L)]
         self.qkv_raw = [e(M, 3 * D) for _ in range(L)]
-        self.qkvp = [e(2, M, 3 * D, dt=bf) for _ in range(L)]
-        self.Pp = [torch.zeros(2, B * d.H * T, d.ldP, dtype=bf, device=dev) for _ in range(L)]
+        if self.fused_attn:
+            self.qkvc = [e(1, M, 3 * D, dt=bf) for _ in range(L)]
+            self.lse = [e(B * d.H * T) for _ in range(L)]
+        else:
+            self.qkvp = [e(2, M, 3 * D, dt=bf) for _ in range(L)]
+            self.Pp = [torch.zeros(2, B * d.H * T, d.ldP, dtype=bf, device=dev) for _ in range(L)]
         self.op = [e(2, M, D, dt=bf) for _ in range(L)]
         self.a_raw = [e(M, D) for _ in range(L)]
         self.f_raw = [e(M, F) for _ in range(L)]
@@ -309,8 +322,9 @@ class StudentEngine:
         self.m_raw = [e(M, D) for _ in range(L)]
         self.stats1 = [(e(M), e(M)) for _ in range(L)]
         self.stats2 = [(e(M), e(M)) for _ in range(L)]
-        self.S = e(B * d.H * T, d.ldS)
-        self.o = e(M, D)
+        if not self.fused_attn:
+            self.S = e(B * d.H * T, d.ldS)
+            self.o = e(M, D)
         self.xcls = e(B, D)
         self.xn = e(B, D)
         self.statsF = (e(B), e(B))
@@ -327,11 +341,12 @@ class StudentEngine:
         self.gpP = e(2, B * d.P, D, dt=bf)
         self.g_big = e(M, F)
         self.g_h = e(M, D)
-        self.g_o = e(M, D)
         self.g_op = e(2, M, D, dt=bf)
         self.g_qkv = e(M, 3 * D)
-        self.dP = e(B * d.H * T, d.ldS)
-        self.dSp = torch.zeros(2, B * d.H * T, d.ldP, dtype=bf, device=dev)
+        if not self.fused_attn:
+            self.g_o = e(M, D)
+            self.dP = e(B * d.H * T, d.ldS)
+            self.dSp = torch.zeros(2, B * d.H * T, d.ldP, dtype=bf, device=dev)
         self.rpb_gp = 64
         self.rpb_ln = 64
         self.bias_part = e(-(-M // self.rpb_gp), max(F, 3 * D))
@@ -394,9 +409,14 @@ class StudentEngine:
                 ops.resid_ln_fwd(self.x_in[0], None, None, blk.norm1.weight.detach(), blk.norm1.bias.detach(), d.eps, M, D,
                                  h_planes=self.h1p[0], mean=self.stats1[0][0], rstd=self.stats1[0][1])
             self._linear_fwd(ql["qkv"], self.h1p[l], M, self.qkv_raw[l])
-            ops.act_planes(self.qkv_raw[l], ql["qkv"].afq.q, False, self.qkvp[l])
-            _attention_forward(d, self.qkvp[l], self.S, self.Pp[l], self.o)
-            ops.split_planes(self.o, self.op[l])
+            if self.fused_attn:
+                qs = ql["qkv"].afq.scale
+                ops.act_planes(self.qkv_raw[l], ql["qkv"].afq.q, False, self.qkvc[l], codes_only=True)
+                ops.attn_fwd(self.qkvc[l], B, T, d.H, d.attn_scale, self.op[l], qk_scale=qs, v_scale=qs, lse=self.lse[l])
+            else:
+                ops.act_planes(self.qkv_raw[l], ql["qkv"].afq.q, False, self.qkvp[l])
+                _attention_forward(d, self.qkvp[l], self.S, self.Pp[l], self.o)
+                ops.split_planes(self.o, self.op[l])
             self._linear_fwd(ql["proj"], self.op[l], M, self.a_raw[l])
             ops.resid_ln_fwd(self.x_in[l], self.a_raw[l], ql["proj"].afq.q, blk.norm2.weight.detach(), blk.norm2.bias.detach(),
                              d.eps, M, D, x_out=self.x_mid[l], h_planes=self.h2p[l], mean=self.stats2[l][0],
@@ -471,21 +491,27 @@ class StudentEngine:
             self._ln_param_grads(blk.norm2, nblk_ln)
             # ---- attention ----
             self._gp(gx2, self.a_raw[l], ql["proj"], False, M, self.gpD)
-            self._dgrad(ql["proj"], self.gpD, M, self.g_o)
-            self._wgrad(ql["proj"], self.gpD, self.op[l], M, PAIRS_FP32)
-            ops.split_planes(self.g_o, self.g_op)
-            qkvp, Pp = self.qkvp[l], self.Pp[l]
-            # dP = dO V^T
-            ops.gemm(Op.tokens(self.g_op, B, T, 0, 64), Op.tokens(qkvp, B, T, 2 * D, 64), T, T, 64, PAIRS_FP32,
-                     out=Out.per_head(self.dP, BH, H, T, T), nbatch=BH, batch_inner=H)
-            ops.attn_ds(Pp, self.dP, d.ldS, BH * T, T, d.attn_scale, self.dSp)
-            # dQ = dS K ; dK = dS^T Q ; dV = P^T dO   -> column blocks of g_qkv
-            ops.gemm(Op.per_head(self.dSp, BH, H, T, T), Op.tokens(qkvp, B, T, D, 64, mn_major=True), T, 64, T, PAIRS_FP32,
-                     out=Out.tokens(self.g_qkv, B, T, 0, 64), nbatch=BH, batch_inner=H)
-            ops.gemm(Op.per_head(self.dSp, BH, H, T, T, mn_major=True), Op.tokens(qkvp, B, T, 0, 64, mn_major=True), T, 64, T,
-                     PAIRS_FP32, out=Out.tokens(self.g_qkv, B, T, D, 64), nbatch=BH, batch_inner=H)
-            ops.gemm(Op.per_head(Pp, BH, H, T, T, mn_major=True), Op.tokens(self.g_op, B, T, 0, 64, mn_major=True), T, 64, T,
-                     PAIRS_FP32, out=Out.tokens(self.g_qkv, B, T, 2 * D, 64), nbatch=BH, batch_inner=H)
+            if self.fused_attn:
+                # proj dgrad emits dL/dO directly as bf16 hi/lo planes; one fused kernel recomputes P and writes dQ | dK | dV
+                ops.gemm(Op.full(self.gpD), Op.full(ql["proj"].codes_t), M, D, D, PAIRS_EXACT_B, out_planes=self.g_op)
+                self._wgrad(ql["proj"], self.gpD, self.op[l], M, PAIRS_FP32)
+                ops.attn_bwd(self.qkvc[l], ql["qkv"].afq.scale, self.g_op, self.lse[l], B, T, H, d.attn_scale, self.g_qkv)
+            else:
+                self._dgrad(ql["proj"], self.gpD, M, self.g_o)
+                self._wgrad(ql["proj"], self.gpD, self.op[l], M, PAIRS_FP32)
+                ops.split_planes(self.g_o, self.g_op)
+                qkvp, Pp = self.qkvp[l], self.Pp[l]
+                # dP = dO V^T
+                ops.gemm(Op.tokens(self.g_op, B, T, 0, 64), Op.tokens(qkvp, B, T, 2 * D, 64), T, T, 64, PAIRS_FP32,
+                         out=Out.per_head(self.dP, BH, H, T, T), nbatch=BH, batch_inner=H)
+                ops.attn_ds(Pp, self.dP, d.ldS, BH * T, T, d.attn_scale, self.dSp)
+                # dQ = dS K ; dK = dS^T Q ; dV = P^T dO   -> column blocks of g_qkv
+                ops.gemm(Op.per_head(self.dSp, BH, H, T, T), Op.tokens(qkvp, B, T, D, 64, mn_major=True), T, 64, T, PAIRS_FP32,
+                         out=Out.tokens(self.g_qkv, B, T, 0, 64), nbatch=BH, batch_inner=H)
+                ops.gemm(Op.per_head(self.dSp, BH, H, T, T, mn_major=True), Op.tokens(qkvp, B, T, 0, 64, mn_major=True), T, 64, T,
+                         PAIRS_FP32, out=Out.tokens(self.g_qkv, B, T, D, 64), nbatch=BH, batch_inner=H)
+                ops.gemm(Op.per_head(Pp, BH, H, T, T, mn_major=True), Op.tokens(self.g_op, B, T, 0, 64, mn_major=True), T, 64, T,
+                         PAIRS_FP32, out=Out.tokens(self.g_qkv, B, T, 2 * D, 64), nbatch=BH, batch_inner=H)
             self._gp(self.g_qkv, self.qkv_raw[l], ql["qkv"], False, M, self.gp3)
             self._dgrad(ql["qkv"], self.gp3, M, self.g_h)
             self._wgrad(ql["qkv"], self.gp3, self.h1p[l], M, PAIRS_FP32)
@@ -504,8 +530,8 @@ class QATDistillStep:
     forward, loss and backward on the current stream and leaves gradients in ``student`` parameters' ``.grad``."""
 
     def __init__(self, student: nn.Module, teacher: nn.Module, batch: int, hparams: Dict,
-                 grad_buffer: Optional[torch.Tensor] = None):
-        self.student_engine = StudentEngine(student, batch, hparams, grad_buffer=grad_buffer)
+                 grad_buffer: Optional[torch.Tensor] = None, fused_attention: Optional[bool] = None):
+        self.student_engine = StudentEngine(student, batch, hparams, grad_buffer=grad_buffer, fused_attention=fused_attention)
         self.teacher_engine = TeacherEngine(teacher, batch)
         self.grad_arena = self.student_engine.grad_arena
 

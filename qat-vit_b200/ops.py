@@ -291,11 +291,12 @@ def gp_planes(g, y_raw, fq, w_scale, per_channel, gelu, R, N, out_planes, bias_p
           "gp_planes")
 
 
-def act_planes(y_raw, fq, gelu, out_planes):
+def act_planes(y_raw, fq, gelu, out_planes, codes_only=False):
+    """out_planes [2, ...] <- hi/lo planes of [GELU](FQ(y_raw)); codes_only: out_planes [1, ...] <- centred integer codes."""
     sc, zp, qmin, qmax = fq if fq is not None else (None, None, 0, 0)
     check(_lib.lib().qv_act_planes(_p(y_raw, torch.float32), _p(sc, torch.float32), _p(zp, torch.int32), qmin, qmax,
-                                   int(bool(gelu)), y_raw.numel(), _p(out_planes, torch.bfloat16), out_planes.stride(0),
-                                   _stream()), "act_planes")
+                                   int(bool(gelu)), int(bool(codes_only)), y_raw.numel(), _p(out_planes, torch.bfloat16),
+                                   out_planes.stride(0), _stream()), "act_planes")
 
 
 def embed_fwd(p_raw, fq, cls, pos, B, P, D, x0):
@@ -335,6 +336,17 @@ def attn_fwd(qkv_planes, B, T, H, scale, out_planes, qk_scale=None, v_scale=None
                                  _p(v_scale, torch.float32), _p(out_planes, torch.bfloat16, "out_planes"), ops_, opl,
                                  _p(out_f32, torch.float32, "out_f32"), _p(lse, torch.float32), _stream()), "attn_fwd")
     return out_planes if out_planes is not None else out_f32
+
+
+def attn_bwd(qkv_codes, qscale, do_planes, lse, B, T, H, scale, g_qkv):
+    """Fused attention backward on integer codes: g_qkv fp32 [B*T, 3*H*64] <- dQ | dK | dV (include/qatvit_b200.h: qv_attn_bwd)."""
+    if qkv_codes.dim() != 3 or qkv_codes.shape[0] != 1 or do_planes.dim() != 3 or do_planes.shape[0] != 2:
+        raise RuntimeError("qatvit_b200: attn_bwd takes a [1, tokens, 3D] code plane and [2, tokens, D] gradient planes")
+    check(_lib.lib().qv_attn_bwd(_p(qkv_codes, torch.bfloat16, "qkv_codes"), qkv_codes.stride(1), _p(qscale, torch.float32),
+                                 _p(do_planes, torch.bfloat16, "do_planes"), do_planes.stride(0), do_planes.stride(1),
+                                 _p(lse, torch.float32, "lse"), B, T, H, float(scale), _p(g_qkv, torch.float32, "g_qkv"),
+                                 _stream()), "attn_bwd")
+    return g_qkv
 
 
 def int8_linear(qx, sx, zx, qw, sw, wsum, bias, sy, zy, qy=None, y=None, engine="x86"):
@@ -415,7 +427,7 @@ def _wrap(name, fn, tag_fn=None):
 
 for _n in ("minmax_reset", "minmax_accumulate", "obs_update", "fq_apply", "fq_weight", "fq_bwd", "split_planes",
            "kd_ce_loss", "splitk_reduce", "resid_ln_fwd", "ln_bwd", "colsum_reduce", "colsum_rows", "gp_planes",
-           "act_planes", "embed_fwd", "im2col_fq", "softmax_planes", "attn_ds", "head_fwd", "head_bwd", "attn_fwd",
+           "act_planes", "embed_fwd", "im2col_fq", "softmax_planes", "attn_ds", "head_fwd", "head_bwd", "attn_fwd", "attn_bwd",
            "int8_linear", "quantize_u8", "qparams_from_minmax", "im2col_u8", "gelu_minmax"):
     globals()[_n] = _wrap(_n, globals()[_n])
 gemm = _wrap("gemm", gemm, _gemm_tag)

@@ -55,3 +55,31 @@ def test_attn_fwd_integer_codes(cuda_dev, B, H, T):
     o_ref, _ = _ref(codes.to(cuda_dev) * s, B, T, H, 0.125)
     got = out[0].double() + out[1].double()
     assert _rel(got, o_ref) < 1e-4
+
+
+@pytest.mark.parametrize("B,H,T", [(3, 6, 197), (4, 2, 17), (2, 3, 37), (1, 1, 128), (2, 2, 129), (150, 2, 33)])
+def test_attn_bwd_integer_codes(cuda_dev, B, H, T):
+    """fused backward (recomputed P from codes + lse) vs fp64 autograd of softmax(QK^T/8)V."""
+    from qatvit_b200 import ops
+    g = torch.Generator().manual_seed(7 * B + H + T)
+    D = H * 64
+    codes = torch.randint(-60, 68, (B * T, 3 * D), generator=g).float()
+    sval = 0.0437
+    s = torch.tensor([sval], device=cuda_dev)
+    cp = codes.to(cuda_dev).bfloat16()[None].contiguous()
+    out = torch.empty(2, B * T, D, dtype=torch.bfloat16, device=cuda_dev)
+    lse = torch.empty(B * H * T, device=cuda_dev)
+    ops.attn_fwd(cp, B, T, H, 0.125, out, qk_scale=s, v_scale=s, lse=lse)
+    dO = torch.randn(B * T, D, generator=g)
+    dOp = ops.split_planes(dO.to(cuda_dev))
+    g_qkv = torch.full((B * T, 3 * D), float("nan"), device=cuda_dev)
+    for _ in range(2):
+        ops.attn_bwd(cp, s, dOp, lse, B, T, H, 0.125, g_qkv)
+    torch.cuda.synchronize()
+    x = (codes.double() * sval).requires_grad_(True)
+    xv = x.view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
+    o = torch.softmax((xv[0] @ xv[1].transpose(-1, -2)) * 0.125, dim=-1) @ xv[2]
+    o.permute(0, 2, 1, 3).reshape(B * T, D).backward(dO.double())
+    ref = x.grad
+    for blk, name in enumerate(("dQ", "dK", "dV")):
+        assert _rel(g_qkv[:, blk * D:(blk + 1) * D], ref[:, blk * D:(blk + 1) * D]) < 1e-4, name

@@ -14,22 +14,24 @@ from parity_utils import build_models, engine_raw_tensors, install_forcing_hooks
 pytestmark = pytest.mark.gpu
 
 CASES = [
-    # (backend, student, teacher, img, batch)
-    ("fbgemm", "vit_test_tiny", "vit_test_teacher", 64, 4),
-    ("qnnpack", "vit_test_tiny", "vit_test_teacher", 64, 3),
-    ("fbgemm", "vit_test_tiny", "vit_test_teacher", 96, 5),          # 37 tokens: ragged everything
-    ("fbgemm", "vit_small_patch16_224", "vit_base_patch16_224", 224, 8),   # BASELINE.json config 1
+    # (backend, student, teacher, img, batch, fused attention (integer-code tcgen05 kernels) or the unfused fallback)
+    ("fbgemm", "vit_test_tiny", "vit_test_teacher", 64, 4, True),
+    ("qnnpack", "vit_test_tiny", "vit_test_teacher", 64, 3, True),
+    ("fbgemm", "vit_test_tiny", "vit_test_teacher", 96, 5, True),          # 37 tokens: ragged everything
+    ("fbgemm", "vit_test_tiny", "vit_test_teacher", 96, 3, False),
+    ("fbgemm", "vit_small_patch16_224", "vit_base_patch16_224", 224, 8, True),   # BASELINE.json config 1
 ]
 
 
-@pytest.mark.parametrize("backend,sname,tname,img,B", CASES)
-def test_forced_parity_with_reference(cuda_dev, backend, sname, tname, img, B):
+@pytest.mark.parametrize("backend,sname,tname,img,B,fused", CASES)
+def test_forced_parity_with_reference(cuda_dev, backend, sname, tname, img, B, fused):
     from qatvit_b200.engine import QATDistillStep
     vr, prepared, teacher = build_models(backend, sname, tname, img)
     images, labels = vr.synthetic_batch(B, seed=3, img=img)
     hp = dict(vr.DEFAULT_HPARAMS)
     gpu_student = copy.deepcopy(prepared).to(cuda_dev)
-    step = QATDistillStep(gpu_student, copy.deepcopy(teacher).to(cuda_dev), B, hp)
+    step = QATDistillStep(gpu_student, copy.deepcopy(teacher).to(cuda_dev), B, hp, fused_attention=fused)
+    assert step.student_engine.fused_attn == fused
     for it in range(2):                       # 2nd iteration: EMA branch of every observer, new images
         if it == 1:
             images, labels = vr.synthetic_batch(B, seed=11, img=img)
