@@ -218,26 +218,40 @@ __global__ void gp_planes_kernel(const float* __restrict__ g, const float* __res
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   const int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_block;
   const int64_t r1 = min(R, r0 + rows_per_block);
-  for (int64_t r = r0; r < r1; ++r) {
-    const int64_t gr = remap_P ? (r / remap_P) * remap_T + (r % remap_P) + 1 : r;
-    float4 gv = __ldg(reinterpret_cast<const float4*>(g + gr * N + c));
-    if (y_raw) {
-      const float4 yv = __ldg(reinterpret_cast<const float4*>(y_raw + r * N + c));
-      float yq[4] = {yv.x, yv.y, yv.z, yv.w};
-      float gg[4] = {gv.x, gv.y, gv.z, gv.w};
+  constexpr int U = 4;                       // rows in flight per thread: 8 independent 16-byte loads before the first use
+  for (int64_t rb = r0; rb < r1; rb += U) {
+    float4 gv[U], yv[U];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        bool in = true;
-        float v = yq[j];
-        if (oq.on) v = qv_fq(v, oq.q, &in, nullptr);
-        float f = gg[j];
-        if (gelu) f *= gelu_grad(v);
-        gg[j] = in ? f : 0.f;
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = rb + u;
+      if (r < r1) {
+        const int64_t gr = remap_P ? (r / remap_P) * remap_T + (r % remap_P) + 1 : r;
+        gv[u] = __ldg(reinterpret_cast<const float4*>(g + gr * N + c));
+        if (y_raw) yv[u] = __ldg(reinterpret_cast<const float4*>(y_raw + r * N + c));
       }
-      gv = make_float4(gg[0], gg[1], gg[2], gg[3]);
     }
-    acc.x += gv.x; acc.y += gv.y; acc.z += gv.z; acc.w += gv.w;
-    store_planes4(out, out + plane_stride, r * N + c, gv.x * ws.x, gv.y * ws.y, gv.z * ws.z, gv.w * ws.w);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = rb + u;
+      if (r >= r1) break;
+      float4 gq = gv[u];
+      if (y_raw) {
+        float yq[4] = {yv[u].x, yv[u].y, yv[u].z, yv[u].w};
+        float gg[4] = {gq.x, gq.y, gq.z, gq.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          bool in = true;
+          float v = yq[j];
+          if (oq.on) v = qv_fq(v, oq.q, &in, nullptr);
+          float f = gg[j];
+          if (gelu) f *= gelu_grad(v);
+          gg[j] = in ? f : 0.f;
+        }
+        gq = make_float4(gg[0], gg[1], gg[2], gg[3]);
+      }
+      acc.x += gq.x; acc.y += gq.y; acc.z += gq.z; acc.w += gq.w;
+      store_planes4(out, out + plane_stride, r * N + c, gq.x * ws.x, gq.y * ws.y, gq.z * ws.z, gq.w * ws.w);
+    }
   }
   if (partials) *reinterpret_cast<float4*>(partials + static_cast<int64_t>(blockIdx.x) * N + c) = acc;
 }

@@ -403,10 +403,46 @@ _prof = None
 
 
 def _gemm_tag(args, kw):
-    a, b, M, N, K = args[0], args[1], args[2], args[3], args[4]
+    """profile tag + algorithmic FLOPs (2 M N K per product of the ORIGINAL fp32 / integer operands; the hi/lo bf16 passes
+    that realise an fp32 product on the tensor cores are not counted)."""
+    a, b, M, N, K, planes = args[0], args[1], args[2], args[3], args[4], args[5]
     nb = kw.get("nbatch", 1)
-    kind = "attn" if nb > 1 else ("wgrad" if a.mn_major else "fwd/dgrad")
+    if nb > 1:
+        kind = "attn (unfused)"
+    elif a.mn_major:
+        kind = "wgrad"
+    elif tuple(planes) == (2, 2):
+        kind = "teacher linear"
+    elif tuple(planes) == (2, 1):
+        kind = "student fwd/dgrad"
+    else:
+        kind = "patch-embed"
     return f"gemm[{kind}]", 2.0 * M * N * K * nb
+
+
+def _n(t):
+    return 0 if t is None else t.numel()
+
+
+def _bytes_act_planes(a, k):
+    n = a[0].numel()
+    return "act_planes", 4.0 * n + (2.0 * n if k.get("codes_only", False) else 4.0 * n)
+
+
+def _bytes_gp_planes(a, k):
+    R, N = a[6], a[7]
+    return "gp_planes", (12.0 if a[1] is not None else 8.0) * R * N
+
+
+def _bytes_resid_ln(a, k):
+    R, D = a[6], a[7]
+    n = sum(1 for t in (a[0], a[1], k.get("x_out"), k.get("h_planes"), k.get("h_f32")) if t is not None)
+    return "resid_ln_fwd", 4.0 * n * R * D
+
+
+def _bytes_ln_bwd(a, k):
+    R, D = a[6], a[7]
+    return "ln_bwd", (16.0 if a[5] is not None else 12.0) * R * D
 
 
 def _wrap(name, fn, tag_fn=None):
@@ -425,12 +461,16 @@ def _wrap(name, fn, tag_fn=None):
     return inner
 
 
-for _n in ("minmax_reset", "minmax_accumulate", "obs_update", "fq_apply", "fq_weight", "fq_bwd", "split_planes",
-           "kd_ce_loss", "splitk_reduce", "resid_ln_fwd", "ln_bwd", "colsum_reduce", "colsum_rows", "gp_planes",
-           "act_planes", "embed_fwd", "im2col_fq", "softmax_planes", "attn_ds", "head_fwd", "head_bwd", "attn_fwd", "attn_bwd",
+for _nm in ("minmax_reset", "minmax_accumulate", "obs_update", "fq_apply", "fq_weight", "fq_bwd", "split_planes",
+           "kd_ce_loss", "splitk_reduce", "colsum_reduce", "colsum_rows",
+           "embed_fwd", "im2col_fq", "softmax_planes", "attn_ds", "head_fwd", "head_bwd", "attn_fwd", "attn_bwd",
            "int8_linear", "quantize_u8", "qparams_from_minmax", "im2col_u8", "gelu_minmax"):
-    globals()[_n] = _wrap(_n, globals()[_n])
+    globals()[_nm] = _wrap(_nm, globals()[_nm])
 gemm = _wrap("gemm", gemm, _gemm_tag)
+act_planes = _wrap("act_planes", act_planes, _bytes_act_planes)
+gp_planes = _wrap("gp_planes", gp_planes, _bytes_gp_planes)
+resid_ln_fwd = _wrap("resid_ln_fwd", resid_ln_fwd, _bytes_resid_ln)
+ln_bwd = _wrap("ln_bwd", ln_bwd, _bytes_ln_bwd)
 
 
 def profile_begin() -> None:
