@@ -124,10 +124,9 @@ class _QATLinearFn(torch.autograd.Function):
             ops.colsum_reduce(part, nblk, N, gb)
         gx = torch.empty(M, K, dtype=torch.float32, device=dev)
         ops.gemm(Op.full(gp), Op.full(codes_t), M, K, N, PAIRS_EXACT_B, out=gx)
-        from .engine import _splits_for
+        from .engine import wgrad_splits
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        tiles = (-(-N // 128)) * (-(-K // 128))
-        s = _splits_for(tiles, -(-M // 64), sms)
+        s = wgrad_splits(N, K, M, sms)
         gw = torch.empty(N, K, dtype=torch.float32, device=dev)
         if s > 1:
             ws = ops.gemm(Op.full(gp, mn_major=True), Op.full(xp, mn_major=True), N, K, M, PAIRS_FP32, splits=s)

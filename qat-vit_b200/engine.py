@@ -110,10 +110,41 @@ class _QLinear:
             self.wscale_vec.copy_(f.scale.expand(self.N))
 
 
-def _splits_for(tiles: int, kblocks: int, sms: int) -> int:
-    s = max(1, min(kblocks, 32, -(-2 * sms // max(tiles, 1))))
-    kbp = -(-kblocks // s)
-    return -(-kblocks // kbp)
+def gemm_tile_n(N: int) -> int:
+    """N-tile width qv_gemm_bf16 picks for an output width N (mirrors pick_bn in csrc/gemm_sm100.cu)."""
+    if N <= 64:
+        return 64
+    if N % 192 == 0:
+        return 192
+    if N <= 128 or N % 128 == 0:
+        return 128
+    return 192 if N > 1024 else 128
+
+
+def _splits_for(tiles: int, kblocks: int, sms: int, max_splits: int = 64) -> int:
+    """Split-K factor for a persistent GEMM with `tiles` output tiles and `kblocks` 64-deep k-blocks on `sms` SMs.
+    Work items are dealt round-robin to one CTA per SM, so the kernel lasts  ceil(tiles*s / sms) * ceil(kblocks / s)
+    k-block times: pick the smallest s within 5 % of the best such cost (a 2-wave choice that leaves the second wave a
+    third full wastes ~30 %), never leaving a split empty."""
+    tiles = max(tiles, 1)
+    best_cost, cands = None, []
+    for s in range(1, min(kblocks, max_splits) + 1):
+        per = -(-kblocks // s)
+        if -(-kblocks // per) != s:          # would leave an empty split
+            continue
+        cost = -(-(tiles * s) // sms) * per
+        cands.append((s, cost))
+        best_cost = cost if best_cost is None else min(best_cost, cost)
+    for s, cost in cands:
+        if cost <= 1.05 * best_cost:
+            return s
+    return 1
+
+
+def wgrad_splits(n_out: int, k_in: int, tokens: int, sms: int) -> int:
+    """Split-K factor for weight.grad[n_out, k_in] = gy^T x over `tokens` rows (128 x gemm_tile_n(k_in) output tiles)."""
+    tiles = (-(-n_out // 128)) * (-(-k_in // gemm_tile_n(k_in)))
+    return _splits_for(tiles, -(-tokens // 64), sms)
 
 
 class _ViTDims:
@@ -354,8 +385,7 @@ class StudentEngine:
         max_ws = 0
         self._splits = {}
         for (n, k, kdim) in [(3 * D, D, M), (D, D, M), (F, D, M), (D, F, M), (D, d.Kc, B * d.P)]:
-            tiles = (-(-n // 128)) * (-(-k // 128))
-            s = _splits_for(tiles, -(-kdim // 64), self.sms)
+            s = wgrad_splits(n, k, kdim, self.sms)
             self._splits[(n, k)] = s
             max_ws = max(max_ws, s * n * k)
         self.ws = e(max_ws)

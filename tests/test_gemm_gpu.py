@@ -83,14 +83,14 @@ def test_gemm_plane_output(cuda_dev, M, N, K, gelu):
 def test_gemm_wgrad_splitk(cuda_dev, N, K, Mtok):
     """weight.grad[N,K] = mask * (gy^T @ x) / scale: MN-major operands, split-K over tokens, deterministic reduce."""
     from qatvit_b200 import ops
-    from qatvit_b200.engine import _splits_for
+    from qatvit_b200.engine import wgrad_splits
     from qatvit_b200.ops import Op, PAIRS_FP32
     g = torch.Generator().manual_seed(N + K)
     gy, x = torch.randn(Mtok, N, generator=g).to(cuda_dev), torch.randn(Mtok, K, generator=g).to(cuda_dev)
     rscale = (torch.rand(N, generator=g) + 0.5).to(cuda_dev)
     mask = (torch.rand(N, K, generator=g) > 0.1).to(torch.uint8).to(cuda_dev)
     sms = torch.cuda.get_device_properties(cuda_dev).multi_processor_count
-    s = _splits_for((-(-N // 128)) * (-(-K // 128)), -(-Mtok // 64), sms)
+    s = wgrad_splits(N, K, Mtok, sms)
     gyp, xp = _planes(gy), _planes(x)
     out = torch.empty(N, K, device=cuda_dev)
     res = []
