@@ -205,8 +205,12 @@ def run_ours(args):
         sync.bind_observers(step.activation_observers())
     else:
         step = QATDistillStep(student, teacher, batch, HP)
-    opt = torch.optim.AdamW(student.parameters(), lr=HP["lr"] * 0.5, weight_decay=HP["weight_decay"])   # ref :315
     arena = step.grad_arena
+    if args.torch_optimizer:
+        opt = torch.optim.AdamW(student.parameters(), lr=HP["lr"] * 0.5, weight_decay=HP["weight_decay"])   # ref :315
+    else:   # same arithmetic, two launches over flat arenas (qatvit_b200/optim.py)
+        from qatvit_b200.optim import FusedClipAdamW
+        opt = FusedClipAdamW(student.parameters(), arena, lr=HP["lr"] * 0.5, weight_decay=HP["weight_decay"], max_norm=1.0)
 
     g = torch.Generator().manual_seed(1234 + rank)
     host_images = torch.randn(batch, 3, 224, 224, generator=g).pin_memory()
@@ -220,8 +224,11 @@ def run_ours(args):
         if sync is not None:
             sync.all_reduce()                                  # the one exchange of the path: NCCL SUM over NVLink of
                                                                # [grads | rank-0 observer state] (qatvit_b200/ddp.py)
-        clip_arena_(arena, 1.0, 1.0 / world)                   # ref :360 (+ DDP mean)
-        opt.step()                                             # ref :361
+        if args.torch_optimizer:
+            clip_arena_(arena, 1.0, 1.0 / world)               # ref :360 (+ DDP mean)
+            opt.step()                                         # ref :361
+        else:
+            opt.step(grad_scale=1.0 / world)                   # ref :360-361 fused: clip-norm 1.0 + AdamW (+ DDP mean)
         return out3
 
     def barrier():
@@ -330,7 +337,8 @@ def run_ours(args):
                    if n == 1 else f"same distillation step data-parallel, global batch 1024 at {n} B200 with NCCL gradient allreduce",
                    "global_batch": global_batch, "per_gpu_batch": batch, "qconfig": "fbgemm", "image": "3x224x224",
                    "parallelism": f"dp{n}", "l2": "per-step working set (~20 GB of activations) >> 126 MB L2; no flush needed",
-                   "optimizer": "torch AdamW + clip-norm on the flat gradient arena (host stays PyTorch)",
+                   "optimizer": "torch AdamW + clip-norm on the flat gradient arena" if args.torch_optimizer else
+                                "fused clip-norm + AdamW on flat arenas (qv_clip_adamw, 2 launches)",
                    "attention": "fused tcgen05 (integer-code student fwd+bwd, hi/lo teacher fwd)"},
         "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": host_images.numel() * 4 + host_labels.numel() * 8,
                 "d2h_bytes_per_step": 12, "ms_per_step": e2e_ms / args.steps},
@@ -354,6 +362,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--torch-optimizer", action="store_true", help="torch AdamW + clip on the arena instead of qv_clip_adamw")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -228,6 +228,16 @@ int qv_im2col_u8(const float* img, const float* scale, const int32_t* zp, int64_
 /* y = GELU_erf(x) in fp32, with the min / max of y merged into acc (may be NULL): the float glue between fc1 and fc2. */
 int qv_gelu_minmax(const float* x, int64_t n, float* y, uint32_t* acc, void* stream);
 
+/* ---- clip_grad_norm_ + AdamW on flat arenas (replaces ref/src/training/qat_trainer.py:360-361; torch.optim.AdamW foreach
+ *      arithmetic, single parameter group) ----
+ * params / grads / exp_avg / exp_avg_sq: fp32 [n] arenas in the same order; partials: fp32 [n_partials] scratch.
+ * total = ||grads * grad_scale||_2 (written to norm_out if not NULL); grads are scaled by grad_scale * min(1, max_norm /
+ * (total + 1e-6)) (max_norm <= 0: no clipping) before the AdamW update of step `step` (1-based); write_back_grad != 0 stores the
+ * clipped gradients back (what clip_grad_norm_ leaves in .grad).  Deterministic; two launches; no host sync. */
+int qv_clip_adamw(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float* partials, int32_t n_partials,
+                  float grad_scale, float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                  float* norm_out, int32_t write_back_grad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -89,6 +89,8 @@ _SIGNATURES = {
     "qv_attn_fwd": (c_int, [_P, c_int32, c_int64, c_int64, c_int32, c_int32, c_int32, c_float, _P, _P, _P, c_int64, c_int64,
                             _P, _P, _P]),
     "qv_attn_bwd": (c_int, [_P, c_int64, _P, _P, c_int64, c_int64, _P, c_int32, c_int32, c_int32, c_float, _P, _P]),
+    "qv_clip_adamw": (c_int, [_P, _P, _P, _P, c_int64, _P, c_int32, c_float, c_float, c_float, c_float, c_float, c_float, c_float,
+                              c_int64, _P, c_int32, _P]),
     "qv_int8_linear": (c_int, [_P, c_int64, c_int64, _P, _P, _P, c_int64, _P, c_int32, _P, _P, c_float, c_int32, c_int32, _P, _P,
                                _P]),
     "qv_quantize_u8": (c_int, [_P, c_int64, _P, _P, _P, _P]),
