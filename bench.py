@@ -139,13 +139,13 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------------------------
 # this repo's arm
 # --------------------------------------------------------------------------------------------------------------------
-def build_models(batch, dev, seed=0):
+def build_models(batch, dev, seed=0, ln_variant="subclass"):
     import warnings
     import torch
     from torch.ao.quantization import get_default_qat_qconfig, prepare_qat
     from qatvit_b200 import vit
     torch.manual_seed(seed)
-    student = vit.QATWrapper(vit.create_model(STUDENT, num_classes=10))
+    student = vit.QATWrapper(vit.create_model(STUDENT, num_classes=10, ln_variant=ln_variant))
     torch.manual_seed(seed + 1)
     teacher = vit.create_model(TEACHER, num_classes=10).eval()
     for p in teacher.parameters():
@@ -189,7 +189,7 @@ def run_ours(args):
     global_batch = 256 if n == 1 else 1024
     batch = global_batch // n
 
-    student, teacher = build_models(batch, dev)
+    student, teacher = build_models(batch, dev, ln_variant=args.ln_variant)
     sync = None
     if world > 1:
         from qatvit_b200.ddp import GradSync
@@ -199,7 +199,7 @@ def run_ours(args):
                 dist.broadcast(t.data, src=0)
         # one flat buffer: [gradients | activation-observer min/max tail]; built before the engine so .grad views alias it
         n_grad = QATDistillStep.count_trainable(student)
-        n_obs = 2 + 4 * len(student.model.blocks) + 1
+        n_obs = QATDistillStep.count_activation_observers(student)
         sync = GradSync(n_grad, n_obs, dev)
         step = QATDistillStep(student, teacher, batch, HP, grad_buffer=sync.grad_arena)
         sync.bind_observers(step.activation_observers())
@@ -335,7 +335,7 @@ def run_ours(args):
         "dtype": "f32 (tcgen05 bf16 hi/lo planes, fp32 accumulate; integer fake-quant codes exact)", "data": "synthetic",
         "config": {"workload": "ViT-B/16 teacher -> ViT-S/16 QAT student distillation step (KL+CE), batch 256, 1x B200"
                    if n == 1 else f"same distillation step data-parallel, global batch 1024 at {n} B200 with NCCL gradient allreduce",
-                   "global_batch": global_batch, "per_gpu_batch": batch, "qconfig": "fbgemm", "image": "3x224x224",
+                   "global_batch": global_batch, "per_gpu_batch": batch, "qconfig": "fbgemm", "layernorm": args.ln_variant, "image": "3x224x224",
                    "parallelism": f"dp{n}", "l2": "per-step working set (~20 GB of activations) >> 126 MB L2; no flush needed",
                    "optimizer": "torch AdamW + clip-norm on the flat gradient arena" if args.torch_optimizer else
                                 "fused clip-norm + AdamW on flat arenas (qv_clip_adamw, 2 launches)",
@@ -362,6 +362,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ln-variant", default="subclass", choices=["subclass", "plain"],
+                    help="timm LayerNorm flavour: 'subclass' (timm.layers.LayerNorm, not observed: 101 fake-quant modules, the "
+                         "primary target) or 'plain' (nn.LayerNorm, observed by prepare_qat: 126) -- SURVEY.md section 0.6")
     ap.add_argument("--torch-optimizer", action="store_true", help="torch AdamW + clip on the arena instead of qv_clip_adamw")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -144,16 +144,21 @@ int qv_splitk_reduce(const float* workspace, int32_t splits, int64_t M, int64_t 
  * its raw output and (scale, zero_point), so the hook of torch/ao/quantization/quantize.py:150-152 costs no pass. */
 
 /* x_out = x_in + FQ(y_raw) ; h = LayerNorm(x_out)*gamma+beta.  Row r reads input row r*in_row_stride.  Any of
- * x_in / y_raw / x_out / h_planes (bf16 [2][R][D]) / h_f32 / mean / rstd may be NULL; y_scale NULL = no fake-quant. */
+ * x_in / y_raw / x_out / h_planes (bf16 [2][R][D]) / h_f32 / mean / rstd may be NULL; y_scale NULL = no fake-quant.
+ * minmax (uint32[2], may be NULL): ordered min / max of h merged atomically -- the output observer of an OBSERVED LayerNorm
+ * (plain nn.LayerNorm under prepare_qat), phase 1. */
 int qv_resid_ln_fwd(const float* x_in, const float* y_raw, const float* y_scale, const int32_t* y_zp, int32_t qmin,
                     int32_t qmax, const float* gamma, const float* beta, float eps, int64_t R, int32_t D,
                     int64_t in_row_stride, float* x_out, uint16_t* h_planes, int64_t plane_stride, float* h_f32,
-                    float* mean, float* rstd, void* stream);
+                    float* mean, float* rstd, uint32_t* minmax, void* stream);
 /* g_x[r*out_row_stride] = g_res[r] + LayerNormBackward(g_h, x, mean, rstd, gamma)[r]; partials: fp32
- * [ceil(R/rows_per_block)][2][D] per-block dgamma / dbeta sums (reduce with qv_colsum_reduce). */
+ * [ceil(R/rows_per_block)][2][D] per-block dgamma / dbeta sums (reduce with qv_colsum_reduce).
+ * h_raw (may be NULL): the raw LayerNorm output of an observed LayerNorm; g_h then passes the STE mask of its fake-quant
+ * (h_scale, h_zp, qmin, qmax) on load. */
 int qv_ln_bwd(const float* g_h, const float* x, const float* mean, const float* rstd, const float* gamma,
               const float* g_res, int64_t R, int32_t D, int64_t out_row_stride, float* g_x, float* partials,
-              int32_t rows_per_block, void* stream);
+              int32_t rows_per_block, const float* h_raw, const float* h_scale, const int32_t* h_zp, int32_t qmin, int32_t qmax,
+              void* stream);
 int qv_colsum_reduce(const float* partials, int32_t nblk, int64_t ncols, float* out, int32_t accumulate, void* stream);
 int qv_colsum_rows(const float* x, int64_t R, int64_t N, int64_t ld, float* out, int32_t accumulate, void* stream);
 /* gp'[r,n] = g[r',n] * [gelu'(FQ(y))] * STEmask(y_raw[r,n]) * w_scale[n] -> bf16 hi/lo planes [2][R][N], plus per-block

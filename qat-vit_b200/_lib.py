@@ -75,8 +75,8 @@ _SIGNATURES = {
     "qv_gemm_bf16": (c_int, [POINTER(GemmArgs), _P]),
     "qv_splitk_reduce": (c_int, [_P, c_int32, c_int64, c_int64, _P, _P, _P, _P, c_int32, _P]),
     "qv_resid_ln_fwd": (c_int, [_P, _P, _P, _P, c_int32, c_int32, _P, _P, c_float, c_int64, c_int32, c_int64, _P, _P,
-                                c_int64, _P, _P, _P, _P]),
-    "qv_ln_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int32, c_int64, _P, _P, c_int32, _P]),
+                                c_int64, _P, _P, _P, _P, _P]),
+    "qv_ln_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int32, c_int64, _P, _P, c_int32, _P, _P, _P, c_int32, c_int32, _P]),
     "qv_colsum_reduce": (c_int, [_P, c_int32, c_int64, _P, c_int32, _P]),
     "qv_colsum_rows": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int32, _P]),
     "qv_gp_planes": (c_int, [_P, _P, _P, _P, c_int32, c_int32, _P, c_int32, c_int32, c_int64, c_int64, c_int32, c_int32,

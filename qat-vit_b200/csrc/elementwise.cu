@@ -51,11 +51,14 @@ __global__ void __launch_bounds__(256) resid_ln_fwd_kernel(const float* __restri
                                                            float eps, int64_t R, int64_t in_row_stride,
                                                            float* __restrict__ x_out, __nv_bfloat16* __restrict__ h_planes,
                                                            int64_t plane_stride, float* __restrict__ h_f32,
-                                                           float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+                                                           float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                           uint32_t* minmax) {
   constexpr int D = 128 * VPL;
   const int lane = threadIdx.x & 31;
   const int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (r >= R) return;
+  __shared__ float s_mn[8], s_mx[8];
+  float omn = INFINITY, omx = -INFINITY;
+  if (r < R) {
   const OptQ oq = load_optq(y_scale, y_zp, qmin, qmax);
   const int64_t src = r * in_row_stride * D;
   float4 v[VPL];
@@ -103,6 +106,22 @@ __global__ void __launch_bounds__(256) resid_ln_fwd_kernel(const float* __restri
     const float o3 = (v[i].w - mean) * rstd * g.w + b.w;
     if (h_planes) store_planes4(h_planes, h_planes + plane_stride, r * D + c, o0, o1, o2, o3);
     if (h_f32) *reinterpret_cast<float4*>(h_f32 + r * D + c) = make_float4(o0, o1, o2, o3);
+    omn = fminf(omn, fminf(fminf(o0, o1), fminf(o2, o3)));
+    omx = fmaxf(omx, fmaxf(fmaxf(o0, o1), fmaxf(o2, o3)));
+  }
+  }
+  if (minmax) {                       // observed-LayerNorm variant: min / max of the LN output, one atomic pair per block
+    omn = qv_warp_min(omn);
+    omx = qv_warp_max(omx);
+    if (lane == 0) { s_mn[threadIdx.x >> 5] = omn; s_mx[threadIdx.x >> 5] = omx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < static_cast<int>(blockDim.x >> 5); ++w) { omn = fminf(omn, s_mn[w]); omx = fmaxf(omx, s_mx[w]); }
+      if (omn <= omx) {
+        atomicMin(minmax, qv_f2ord(omn));
+        atomicMax(minmax + 1, qv_f2ord(omx));
+      }
+    }
   }
 }
 
@@ -116,9 +135,12 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ g
                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                                      const float* __restrict__ gamma, const float* __restrict__ g_res,
                                                      int64_t R, int64_t out_row_stride, float* __restrict__ g_x,
-                                                     float* __restrict__ partials, int rows_per_block) {
+                                                     float* __restrict__ partials, int rows_per_block,
+                                                     const float* __restrict__ h_raw, const float* h_scale,
+                                                     const int32_t* h_zp, int qmin, int qmax) {
   constexpr int D = 128 * VPL;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const OptQ hq = load_optq(h_raw ? h_scale : nullptr, h_zp, qmin, qmax);   // observed LN output: g_h passes its STE mask
   float4 dg[VPL], db[VPL];
 #pragma unroll
   for (int i = 0; i < VPL; ++i) dg[i] = db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -136,6 +158,13 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ g
     for (int i = 0; i < VPL; ++i) {
       const int c = (i * 32 + lane) * 4;
       gh[i] = __ldg(reinterpret_cast<const float4*>(g_h + r * D + c));
+      if (hq.on) {
+        const float4 hv = __ldg(reinterpret_cast<const float4*>(h_raw + r * D + c));
+        bool in0, in1, in2, in3;
+        qv_fq(hv.x, hq.q, &in0, nullptr); qv_fq(hv.y, hq.q, &in1, nullptr);
+        qv_fq(hv.z, hq.q, &in2, nullptr); qv_fq(hv.w, hq.q, &in3, nullptr);
+        gh[i].x = in0 ? gh[i].x : 0.f; gh[i].y = in1 ? gh[i].y : 0.f; gh[i].z = in2 ? gh[i].z : 0.f; gh[i].w = in3 ? gh[i].w : 0.f;
+      }
       const float4 xv = __ldg(reinterpret_cast<const float4*>(x + r * D + c));
       xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
       dg[i].x += gh[i].x * xh[i].x; dg[i].y += gh[i].y * xh[i].y; dg[i].z += gh[i].z * xh[i].z; dg[i].w += gh[i].w * xh[i].w;
@@ -571,7 +600,7 @@ inline int ew_blocks(int64_t n_items, int per_sm = 8) {
 extern "C" int qv_resid_ln_fwd(const float* x_in, const float* y_raw, const float* y_scale, const int32_t* y_zp,
                                int32_t qmin, int32_t qmax, const float* gamma, const float* beta, float eps, int64_t R,
                                int32_t D, int64_t in_row_stride, float* x_out, uint16_t* h_planes, int64_t plane_stride,
-                               float* h_f32, float* mean, float* rstd, void* stream) {
+                               float* h_f32, float* mean, float* rstd, uint32_t* minmax, void* stream) {
   QV_REQUIRE((x_in || y_raw) && gamma && beta && R > 0, QV_ERR_INVALID, "bad resid_ln_fwd arguments");
   QV_REQUIRE(D % 128 == 0 && D >= 128 && D <= 1024, QV_ERR_UNSUPPORTED, "LayerNorm width must be a multiple of 128 <= 1024 (got %d)", D);
   QV_REQUIRE((y_scale == nullptr) == (y_zp == nullptr), QV_ERR_INVALID, "y_scale and y_zp go together");
@@ -583,7 +612,7 @@ extern "C" int qv_resid_ln_fwd(const float* x_in, const float* y_raw, const floa
   if (in_row_stride < 1) in_row_stride = 1;
 #define LAUNCH(V)                                                                                                        \
   resid_ln_fwd_kernel<V><<<grid, 256, 0, st>>>(x_in, y_raw, y_scale, y_zp, qmin, qmax, gamma, beta, eps, R, in_row_stride, \
-                                               x_out, hp, plane_stride, h_f32, mean, rstd)
+                                               x_out, hp, plane_stride, h_f32, mean, rstd, minmax)
   switch (D / 128) {
     case 1: LAUNCH(1); break;
     case 2: LAUNCH(2); break;
@@ -599,14 +628,17 @@ extern "C" int qv_resid_ln_fwd(const float* x_in, const float* y_raw, const floa
 
 extern "C" int qv_ln_bwd(const float* g_h, const float* x, const float* mean, const float* rstd, const float* gamma,
                          const float* g_res, int64_t R, int32_t D, int64_t out_row_stride, float* g_x, float* partials,
-                         int32_t rows_per_block, void* stream) {
+                         int32_t rows_per_block, const float* h_raw, const float* h_scale, const int32_t* h_zp, int32_t qmin,
+                         int32_t qmax, void* stream) {
   QV_REQUIRE(g_h && x && mean && rstd && gamma && g_x && R > 0 && rows_per_block > 0, QV_ERR_INVALID, "bad ln_bwd arguments");
   QV_REQUIRE(D % 128 == 0 && D >= 128 && D <= 1024, QV_ERR_UNSUPPORTED, "LayerNorm width must be a multiple of 128 <= 1024 (got %d)", D);
+  QV_REQUIRE(!h_raw || (h_scale && h_zp), QV_ERR_INVALID, "h_raw needs h_scale and h_zp");
   QV_NEED_GPU();
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const unsigned grid = static_cast<unsigned>((R + rows_per_block - 1) / rows_per_block);
   if (out_row_stride < 1) out_row_stride = 1;
-#define LAUNCH(V) ln_bwd_kernel<V><<<grid, 256, 0, st>>>(g_h, x, mean, rstd, gamma, g_res, R, out_row_stride, g_x, partials, rows_per_block)
+#define LAUNCH(V) ln_bwd_kernel<V><<<grid, 256, 0, st>>>(g_h, x, mean, rstd, gamma, g_res, R, out_row_stride, g_x, partials, \
+                                                         rows_per_block, h_raw, h_scale, h_zp, qmin, qmax)
   switch (D / 128) {
     case 1: LAUNCH(1); break;
     case 2: LAUNCH(2); break;

@@ -283,11 +283,12 @@ class StudentEngine:
         self.dev = dev
         self.hp_ = dict(hparams)
         d = self.d = _ViTDims(vit, batch)
-        for blk in vit.blocks:
-            if hasattr(blk.norm1, "activation_post_process") or hasattr(vit.norm, "activation_post_process"):
-                raise NotImplementedError(
-                    "observed LayerNorm (plain nn.LayerNorm, 126 fake-quant modules) is not on the fused path yet; "
-                    "use the timm.layers.LayerNorm variant (SURVEY.md §0.6)")
+        # with plain nn.LayerNorm blocks (older timm) prepare_qat also observes every LayerNorm output (126
+        # fake-quant modules instead of 101).  The LN outputs are then exact integer codes, so qkv / fc1 become single-pass
+        # integer GEMMs (codes x codes) and their wgrads two-pass.
+        self.ln_obs = hasattr(vit.blocks[0].norm1, "activation_post_process")
+        if self.ln_obs != hasattr(vit.norm, "activation_post_process"):
+            raise NotImplementedError("mixed observed / unobserved LayerNorm modules")
         self.sms = torch.cuda.get_device_properties(dev).multi_processor_count
         L, M, D, F, B, T = d.L, d.M, d.D, d.F, d.B, d.T
         bf, f32 = torch.bfloat16, torch.float32
@@ -295,7 +296,8 @@ class StudentEngine:
 
         # ---- observer slots: input, conv out, 4 per block, head ----
         n_act = 2 + 4 * L + 1
-        self.acc = torch.empty(n_act, 2, dtype=torch.int32, device=dev)
+        n_ln = (2 * L + 1) if self.ln_obs else 0
+        self.acc = torch.empty(n_act + n_ln, 2, dtype=torch.int32, device=dev)
         self.fq_in = FQRef(student.quant.activation_post_process)
         self.conv = _QLinear(vit.patch_embed.proj, dev, self.acc[1])
         self.lin: List[Dict[str, _QLinear]] = []
@@ -305,6 +307,14 @@ class StudentEngine:
                                  fc1=_QLinear(blk.mlp.fc1, dev, self.acc[base + 2]), fc2=_QLinear(blk.mlp.fc2, dev, self.acc[base + 3])))
         self.head = _QLinear(vit.head, dev, self.acc[n_act - 1], small=True)
         self.all_linears = [self.conv] + [q for blk in self.lin for q in blk.values()] + [self.head]
+        self.ln_fq: List[FQRef] = []          # [norm1_0, norm2_0, norm1_1, ..., final norm] (observed-LN variant only)
+        self.ln_acc = [self.acc[n_act + i] for i in range(n_ln)]
+        if self.ln_obs:
+            for blk in vit.blocks:
+                self.ln_fq += [FQRef(blk.norm1.activation_post_process), FQRef(blk.norm2.activation_post_process)]
+            self.ln_fq.append(FQRef(vit.norm.activation_post_process))
+            if not all(int(f.fake_quant_enabled.item()) != 0 for f in self.ln_fq):
+                raise NotImplementedError("observed LayerNorm with fake-quant disabled is not on the fused path")
 
         # ---- flat gradient arena (the buffer a DDP-style all-reduce runs over) ----
         self.params = [p for p in student.parameters() if p.requires_grad]
@@ -337,8 +347,16 @@ class StudentEngine:
         self.p_raw = e(B * d.P, D)
         self.x_in = [e(M, D) for _ in range(L)]
         self.x_mid = [e(M, D) for _ in range(L)]
-        self.h1p = [e(2, M, D, dt=bf) for _ in range(L)]
-        self.h2p = [e(2, M, D, dt=bf) for _ in range(L)]
+        # A operand of qkv / fc1: LayerNorm output as hi/lo planes, or (observed LN) one plane of codes + the raw output
+        npl = 1 if self.ln_obs else 2
+        self.h1p = [e(npl, M, D, dt=bf) for _ in range(L)]
+        self.h2p = [e(npl, M, D, dt=bf) for _ in range(L)]
+        if self.ln_obs:
+            self.h1_raw = [e(M, D) for _ in range(L)]
+            self.h2_raw = [e(M, D) for _ in range(L)]
+            self.hN_raw = e(M, D)
+            self.xn_raw = e(B, D)
+            self.xn_mask = e(B, D, dt=torch.uint8)
         self.qkv_raw = [e(M, 3 * D) for _ in range(L)]
         if self.fused_attn:
             self.qkvc = [e(1, M, 3 * D, dt=bf) for _ in range(L)]
@@ -418,6 +436,25 @@ class StudentEngine:
                  bias=ql.bias.detach(), minmax=ql.acc)
         ql.afq.update_from(ql.acc)
 
+    def _ln_fwd(self, slot: int, norm: nn.Module, x_in, y_raw, fq, x_out, h_out, h_raw, stats) -> None:
+        """x_out = x_in + FQ(y_raw); LayerNorm -> the A operand of the next Linear: bf16 hi/lo planes, or (observed LN) raw
+        output + fused observer + one plane of integer codes."""
+        d = self.d
+        g, b = norm.weight.detach(), norm.bias.detach()
+        if not self.ln_obs:
+            ops.resid_ln_fwd(x_in, y_raw, fq, g, b, d.eps, d.M, d.D, x_out=x_out, h_planes=h_out, mean=stats[0], rstd=stats[1])
+            return
+        f, acc = self.ln_fq[slot], self.ln_acc[slot]
+        ops.resid_ln_fwd(x_in, y_raw, fq, g, b, d.eps, d.M, d.D, x_out=x_out, h_f32=h_raw, mean=stats[0], rstd=stats[1], minmax=acc)
+        f.update_from(acc)
+        ops.act_planes(h_raw, f.q, False, h_out, codes_only=True)
+
+    def _lin_after_ln(self, ql: _QLinear, slot: int, a, M: int, out) -> None:
+        if self.ln_obs:     # codes x codes, the activation scale rides in alpha
+            self._linear_fwd(ql, a, M, out, pairs=PAIRS_SINGLE, alpha=self.ln_fq[slot].scale)
+        else:
+            self._linear_fwd(ql, a, M, out)
+
     def forward(self, images: torch.Tensor, labels: torch.Tensor, teacher_logits: torch.Tensor) -> torch.Tensor:
         d, v = self.d, self.vit
         B, T, D, F, M, L = d.B, d.T, d.D, d.F, d.M, d.L
@@ -436,9 +473,9 @@ class StudentEngine:
         for l, blk in enumerate(v.blocks):
             ql = self.lin[l]
             if l == 0:
-                ops.resid_ln_fwd(self.x_in[0], None, None, blk.norm1.weight.detach(), blk.norm1.bias.detach(), d.eps, M, D,
-                                 h_planes=self.h1p[0], mean=self.stats1[0][0], rstd=self.stats1[0][1])
-            self._linear_fwd(ql["qkv"], self.h1p[l], M, self.qkv_raw[l])
+                self._ln_fwd(0, blk.norm1, self.x_in[0], None, None, None, self.h1p[0], self.h1_raw[0] if self.ln_obs else None,
+                             self.stats1[0])
+            self._lin_after_ln(ql["qkv"], 2 * l, self.h1p[l], M, self.qkv_raw[l])
             if self.fused_attn:
                 qs = ql["qkv"].afq.scale
                 ops.act_planes(self.qkv_raw[l], ql["qkv"].afq.q, False, self.qkvc[l], codes_only=True)
@@ -448,21 +485,29 @@ class StudentEngine:
                 _attention_forward(d, self.qkvp[l], self.S, self.Pp[l], self.o)
                 ops.split_planes(self.o, self.op[l])
             self._linear_fwd(ql["proj"], self.op[l], M, self.a_raw[l])
-            ops.resid_ln_fwd(self.x_in[l], self.a_raw[l], ql["proj"].afq.q, blk.norm2.weight.detach(), blk.norm2.bias.detach(),
-                             d.eps, M, D, x_out=self.x_mid[l], h_planes=self.h2p[l], mean=self.stats2[l][0],
-                             rstd=self.stats2[l][1])
-            self._linear_fwd(ql["fc1"], self.h2p[l], M, self.f_raw[l])
+            self._ln_fwd(2 * l + 1, blk.norm2, self.x_in[l], self.a_raw[l], ql["proj"].afq.q, self.x_mid[l], self.h2p[l],
+                         self.h2_raw[l] if self.ln_obs else None, self.stats2[l])
+            self._lin_after_ln(ql["fc1"], 2 * l + 1, self.h2p[l], M, self.f_raw[l])
             ops.act_planes(self.f_raw[l], ql["fc1"].afq.q, True, self.gelp[l])
             self._linear_fwd(ql["fc2"], self.gelp[l], M, self.m_raw[l])
             if l + 1 < L:
                 nb = v.blocks[l + 1]
-                ops.resid_ln_fwd(self.x_mid[l], self.m_raw[l], ql["fc2"].afq.q, nb.norm1.weight.detach(), nb.norm1.bias.detach(),
-                                 d.eps, M, D, x_out=self.x_in[l + 1], h_planes=self.h1p[l + 1], mean=self.stats1[l + 1][0],
-                                 rstd=self.stats1[l + 1][1])
+                self._ln_fwd(2 * l + 2, nb.norm1, self.x_mid[l], self.m_raw[l], ql["fc2"].afq.q, self.x_in[l + 1], self.h1p[l + 1],
+                             self.h1_raw[l + 1] if self.ln_obs else None, self.stats1[l + 1])
             else:   # final norm: only the cls rows reach the head
-                ops.resid_ln_fwd(self.x_mid[l], self.m_raw[l], ql["fc2"].afq.q, v.norm.weight.detach(), v.norm.bias.detach(),
-                                 d.eps, B, D, in_row_stride=T, x_out=self.xcls, h_f32=self.xn, mean=self.statsF[0],
-                                 rstd=self.statsF[1])
+                gN, bN = v.norm.weight.detach(), v.norm.bias.detach()
+                if self.ln_obs:
+                    # the reference normalises (and OBSERVES) all tokens before taking x[:, 0]: min / max over every row
+                    fN, accN = self.ln_fq[2 * L], self.ln_acc[2 * L]
+                    ops.resid_ln_fwd(self.x_mid[l], self.m_raw[l], ql["fc2"].afq.q, gN, bN, d.eps, M, D, h_f32=self.hN_raw, minmax=accN)
+                    fN.update_from(accN)
+                    ops.resid_ln_fwd(self.x_mid[l], self.m_raw[l], ql["fc2"].afq.q, gN, bN, d.eps, B, D, in_row_stride=T,
+                                     x_out=self.xcls, h_f32=self.xn_raw, mean=self.statsF[0], rstd=self.statsF[1])
+                    ops.fq_apply(self.xn_raw, fN.scale, fN.zero_point, fN.fake_quant_enabled, fN.qmin, fN.qmax, y=self.xn,
+                                 mask=self.xn_mask)
+                else:
+                    ops.resid_ln_fwd(self.x_mid[l], self.m_raw[l], ql["fc2"].afq.q, gN, bN, d.eps, B, D, in_row_stride=T,
+                                     x_out=self.xcls, h_f32=self.xn, mean=self.statsF[0], rstd=self.statsF[1])
         hd = self.head
         ops.head_fwd(self.xn, hd.wq, hd.bias.detach(), B, D, d.C, self.logits_raw, minmax=hd.acc)
         hd.afq.update_from(hd.acc)
@@ -500,6 +545,8 @@ class StudentEngine:
         BH = B * H
         hd = self.head
         ops.head_bwd(self.g_logits, self.xn, hd.wq, hd.wmask, B, D, d.C, self.g_xn, self._grad(hd.weight), self._grad(hd.bias))
+        if self.ln_obs:     # STE mask of the final norm's output fake-quant
+            ops.fq_bwd(self.g_xn, self.xn_mask, gx=self.g_xn)
         gx, gx2 = self.gx
         gx.zero_()
         nblk_ln = -(-B // self.rpb_ln)
@@ -515,9 +562,15 @@ class StudentEngine:
             self._wgrad(ql["fc2"], self.gpD, self.gelp[l], M, PAIRS_FP32)
             self._gp(self.g_big, self.f_raw[l], ql["fc1"], True, M, self.gpF)
             self._dgrad(ql["fc1"], self.gpF, M, self.g_h)
-            self._wgrad(ql["fc1"], self.gpF, self.h2p[l], M, PAIRS_FP32)
-            ops.ln_bwd(self.g_h, self.x_mid[l], self.stats2[l][0], self.stats2[l][1], blk.norm2.weight.detach(), gx, M, D, gx2,
-                       self.ln_part, self.rpb_ln)
+            if self.ln_obs:
+                f2 = self.ln_fq[2 * l + 1]
+                self._wgrad(ql["fc1"], self.gpF, self.h2p[l], M, PAIRS_EXACT_B, alpha=f2.scale)
+                ops.ln_bwd(self.g_h, self.x_mid[l], self.stats2[l][0], self.stats2[l][1], blk.norm2.weight.detach(), gx, M, D, gx2,
+                           self.ln_part, self.rpb_ln, h_raw=self.h2_raw[l], h_fq=f2.q)
+            else:
+                self._wgrad(ql["fc1"], self.gpF, self.h2p[l], M, PAIRS_FP32)
+                ops.ln_bwd(self.g_h, self.x_mid[l], self.stats2[l][0], self.stats2[l][1], blk.norm2.weight.detach(), gx, M, D, gx2,
+                           self.ln_part, self.rpb_ln)
             self._ln_param_grads(blk.norm2, nblk_ln)
             # ---- attention ----
             self._gp(gx2, self.a_raw[l], ql["proj"], False, M, self.gpD)
@@ -544,9 +597,15 @@ class StudentEngine:
                          PAIRS_FP32, out=Out.tokens(self.g_qkv, B, T, 2 * D, 64), nbatch=BH, batch_inner=H)
             self._gp(self.g_qkv, self.qkv_raw[l], ql["qkv"], False, M, self.gp3)
             self._dgrad(ql["qkv"], self.gp3, M, self.g_h)
-            self._wgrad(ql["qkv"], self.gp3, self.h1p[l], M, PAIRS_FP32)
-            ops.ln_bwd(self.g_h, self.x_in[l], self.stats1[l][0], self.stats1[l][1], blk.norm1.weight.detach(), gx2, M, D, gx,
-                       self.ln_part, self.rpb_ln)
+            if self.ln_obs:
+                f1 = self.ln_fq[2 * l]
+                self._wgrad(ql["qkv"], self.gp3, self.h1p[l], M, PAIRS_EXACT_B, alpha=f1.scale)
+                ops.ln_bwd(self.g_h, self.x_in[l], self.stats1[l][0], self.stats1[l][1], blk.norm1.weight.detach(), gx2, M, D, gx,
+                           self.ln_part, self.rpb_ln, h_raw=self.h1_raw[l], h_fq=f1.q)
+            else:
+                self._wgrad(ql["qkv"], self.gp3, self.h1p[l], M, PAIRS_FP32)
+                ops.ln_bwd(self.g_h, self.x_in[l], self.stats1[l][0], self.stats1[l][1], blk.norm1.weight.detach(), gx2, M, D, gx,
+                           self.ln_part, self.rpb_ln)
             self._ln_param_grads(blk.norm1, nblk_ln)
         # ---- embeddings: pos_embed, cls_token, patch-embed conv ----
         ops.colsum_rows(gx, B, T * D, T * D, self._grad(v.pos_embed))
@@ -579,7 +638,16 @@ class QATDistillStep:
         """[(min_val, max_val)] of every activation fake-quant, in forward order (for ddp.GradSync)."""
         se = self.student_engine
         fqs = [se.fq_in, se.conv.afq] + [ql[k].afq for ql in se.lin for k in ("qkv", "proj", "fc1", "fc2")] + [se.head.afq]
+        fqs += se.ln_fq
         return [(f.min_val, f.max_val) for f in fqs]
+
+    @staticmethod
+    def count_activation_observers(student: nn.Module) -> int:
+        """activation fake-quant modules of the prepared student (51, or 76 with observed LayerNorms) -- the length of
+        activation_observers(), needed to size ddp.GradSync before the engine exists."""
+        from torch.ao.quantization.fake_quantize import FusedMovingAvgObsFakeQuantize
+        return sum(1 for n, m in student.named_modules()
+                   if isinstance(m, FusedMovingAvgObsFakeQuantize) and n.endswith("activation_post_process"))
 
     @staticmethod
     def count_trainable(student: nn.Module) -> int:

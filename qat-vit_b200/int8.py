@@ -147,11 +147,12 @@ class ConvertedStudent:
         for li, blk in enumerate(self.blocks):
             g, b = blk["n1"]
             if y_prev is None:
-                ops.resid_ln_fwd(self.x[cur], None, None, g, b, self.eps, M, D, h_f32=self.h)
+                ops.resid_ln_fwd(self.x[cur], None, None, g, b, self.eps, M, D, h_f32=self.h, minmax=self.acc[slot])
             else:
-                ops.resid_ln_fwd(self.x[cur], y_prev, None, g, b, self.eps, M, D, x_out=self.x[cur ^ 1], h_f32=self.h)
+                ops.resid_ln_fwd(self.x[cur], y_prev, None, g, b, self.eps, M, D, x_out=self.x[cur ^ 1], h_f32=self.h,
+                                 minmax=self.acc[slot])
                 cur ^= 1
-            s, z = self._dyn_quant(slot, self.h, self.qh); slot += 1
+            s, z = self._dyn_quant(slot, self.h, self.qh, have_minmax=True); slot += 1
             if trace is not None:
                 trace[f"blocks.{li}.attn.qkv"] = (self.qh.clone(), s.clone(), z.clone())
             self._lin(blk["qkv"], self.qh, s, z, self.qkv)
@@ -160,9 +161,10 @@ class ConvertedStudent:
             s, z = self._dyn_quant(slot, self.o, self.qh); slot += 1
             self._lin(blk["proj"], self.qh, s, z, self.y)
             g, b = blk["n2"]
-            ops.resid_ln_fwd(self.x[cur], self.y, None, g, b, self.eps, M, D, x_out=self.x[cur ^ 1], h_f32=self.h)
+            ops.resid_ln_fwd(self.x[cur], self.y, None, g, b, self.eps, M, D, x_out=self.x[cur ^ 1], h_f32=self.h,
+                             minmax=self.acc[slot])
             cur ^= 1
-            s, z = self._dyn_quant(slot, self.h, self.qh); slot += 1
+            s, z = self._dyn_quant(slot, self.h, self.qh, have_minmax=True); slot += 1
             self._lin(blk["fc1"], self.qh, s, z, self.f)
             ops.gelu_minmax(self.f, self.g, self.acc[slot])
             s, z = self._dyn_quant(slot, self.g, self.qg, have_minmax=True); slot += 1

@@ -253,7 +253,7 @@ def launch_count() -> int:
 
 
 def resid_ln_fwd(x_in, y_raw, fq, gamma, beta, eps, R, D, *, in_row_stride=1, x_out=None, h_planes=None, h_f32=None,
-                 mean=None, rstd=None):
+                 mean=None, rstd=None, minmax=None):
     """x_out = x_in + FQ(y_raw); h = LN(x_out).  fq = (scale, zero_point, qmin, qmax) or None."""
     sc, zp, qmin, qmax = fq if fq is not None else (None, None, 0, 0)
     check(_lib.lib().qv_resid_ln_fwd(_p(x_in, torch.float32), _p(y_raw, torch.float32), _p(sc, torch.float32),
@@ -261,14 +261,17 @@ def resid_ln_fwd(x_in, y_raw, fq, gamma, beta, eps, R, D, *, in_row_stride=1, x_
                                      float(eps), R, D, in_row_stride, _p(x_out, torch.float32),
                                      _p(h_planes, torch.bfloat16), 0 if h_planes is None else h_planes.stride(0),
                                      _p(h_f32, torch.float32), _p(mean, torch.float32), _p(rstd, torch.float32),
-                                     _stream()), "resid_ln_fwd")
+                                     _p(minmax, torch.int32), _stream()), "resid_ln_fwd")
 
 
-def ln_bwd(g_h, x, mean, rstd, gamma, g_res, R, D, g_x, partials, rows_per_block, out_row_stride=1):
+def ln_bwd(g_h, x, mean, rstd, gamma, g_res, R, D, g_x, partials, rows_per_block, out_row_stride=1, h_raw=None, h_fq=None):
+    """h_raw + h_fq = (scale, zero_point, qmin, qmax): g_h first passes the STE mask of an observed LayerNorm's fake-quant."""
+    sc, zp, qmin, qmax = h_fq if (h_raw is not None and h_fq is not None) else (None, None, 0, 0)
     check(_lib.lib().qv_ln_bwd(_p(g_h, torch.float32), _p(x, torch.float32), _p(mean, torch.float32),
                                _p(rstd, torch.float32), _p(gamma, torch.float32), _p(g_res, torch.float32), R, D,
                                out_row_stride, _p(g_x, torch.float32), _p(partials, torch.float32), rows_per_block,
-                               _stream()), "ln_bwd")
+                               _p(h_raw if sc is not None else None, torch.float32), _p(sc, torch.float32), _p(zp, torch.int32),
+                               qmin, qmax, _stream()), "ln_bwd")
 
 
 def colsum_reduce(partials, nblk, ncols, out, accumulate=False):

@@ -54,6 +54,11 @@ def engine_raw_tensors(se):
         forced[pre + "attn.proj.activation_post_process"] = se.a_raw[i].view(B, T, -1).cpu()
         forced[pre + "mlp.fc1.activation_post_process"] = se.f_raw[i].view(B, T, -1).cpu()
         forced[pre + "mlp.fc2.activation_post_process"] = se.m_raw[i].view(B, T, -1).cpu()
+        if se.ln_obs:
+            forced[pre + "norm1.activation_post_process"] = se.h1_raw[i].view(B, T, -1).cpu()
+            forced[pre + "norm2.activation_post_process"] = se.h2_raw[i].view(B, T, -1).cpu()
+    if se.ln_obs:
+        forced["model.norm.activation_post_process"] = se.hN_raw.view(B, T, -1).cpu()
     return forced
 
 

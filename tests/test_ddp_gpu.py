@@ -32,7 +32,7 @@ def _worker(rank, world, port, q):
     hp = dict(vr.DEFAULT_HPARAMS)
     student = copy.deepcopy(prepared).to(dev)
     n_grad = QATDistillStep.count_trainable(student)
-    n_obs = 2 + 4 * len(student.model.blocks) + 1
+    n_obs = QATDistillStep.count_activation_observers(student)
     sync = GradSync(n_grad, n_obs, dev)
     step = QATDistillStep(student, copy.deepcopy(teacher).to(dev), B, hp, grad_buffer=sync.grad_arena)
     sync.bind_observers(step.activation_observers())

@@ -14,24 +14,32 @@ from parity_utils import build_models, engine_raw_tensors, install_forcing_hooks
 pytestmark = pytest.mark.gpu
 
 CASES = [
-    # (backend, student, teacher, img, batch, fused attention (integer-code tcgen05 kernels) or the unfused fallback)
-    ("fbgemm", "vit_test_tiny", "vit_test_teacher", 64, 4, True),
-    ("qnnpack", "vit_test_tiny", "vit_test_teacher", 64, 3, True),
-    ("fbgemm", "vit_test_tiny", "vit_test_teacher", 96, 5, True),          # 37 tokens: ragged everything
-    ("fbgemm", "vit_test_tiny", "vit_test_teacher", 96, 3, False),
-    ("fbgemm", "vit_small_patch16_224", "vit_base_patch16_224", 224, 8, True),   # BASELINE.json config 1
+    # (backend, student, teacher, img, batch, fused attention (integer-code tcgen05 kernels) or the unfused fallback,
+    #  LayerNorm variant: "subclass" = timm.layers.LayerNorm, not observed (101 fake-quant modules);
+    #                     "plain" = nn.LayerNorm, observed by prepare_qat (126 fake-quant modules) -- SURVEY.md §0.6)
+    ("fbgemm", "vit_test_tiny", "vit_test_teacher", 64, 4, True, "subclass"),
+    ("qnnpack", "vit_test_tiny", "vit_test_teacher", 64, 3, True, "subclass"),
+    ("fbgemm", "vit_test_tiny", "vit_test_teacher", 96, 5, True, "subclass"),          # 37 tokens: ragged everything
+    ("fbgemm", "vit_test_tiny", "vit_test_teacher", 96, 3, False, "subclass"),
+    ("fbgemm", "vit_test_tiny", "vit_test_teacher", 64, 4, True, "plain"),
+    ("qnnpack", "vit_test_tiny", "vit_test_teacher", 96, 3, True, "plain"),
+    ("fbgemm", "vit_small_patch16_224", "vit_base_patch16_224", 224, 8, True, "subclass"),   # BASELINE.json config 1
+    ("fbgemm", "vit_small_patch16_224", "vit_base_patch16_224", 224, 4, True, "plain"),
 ]
 
 
-@pytest.mark.parametrize("backend,sname,tname,img,B,fused", CASES)
-def test_forced_parity_with_reference(cuda_dev, backend, sname, tname, img, B, fused):
+@pytest.mark.parametrize("backend,sname,tname,img,B,fused,ln_variant", CASES)
+def test_forced_parity_with_reference(cuda_dev, backend, sname, tname, img, B, fused, ln_variant):
     from qatvit_b200.engine import QATDistillStep
-    vr, prepared, teacher = build_models(backend, sname, tname, img)
+    vr, prepared, teacher = build_models(backend, sname, tname, img, ln_variant=ln_variant)
+    n_fq = sum(1 for m in prepared.modules() if type(m).__name__ == "FusedMovingAvgObsFakeQuantize")
+    L = len(prepared.model.blocks)
+    assert n_fq == (8 * L + 5 if ln_variant == "subclass" else 10 * L + 6)       # 101 / 126 at depth 12
     images, labels = vr.synthetic_batch(B, seed=3, img=img)
     hp = dict(vr.DEFAULT_HPARAMS)
     gpu_student = copy.deepcopy(prepared).to(cuda_dev)
     step = QATDistillStep(gpu_student, copy.deepcopy(teacher).to(cuda_dev), B, hp, fused_attention=fused)
-    assert step.student_engine.fused_attn == fused
+    assert step.student_engine.fused_attn == fused and step.student_engine.ln_obs == (ln_variant == "plain")
     for it in range(2):                       # 2nd iteration: EMA branch of every observer, new images
         if it == 1:
             images, labels = vr.synthetic_batch(B, seed=11, img=img)
