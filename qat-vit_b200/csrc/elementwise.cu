@@ -228,15 +228,17 @@ __global__ void __launch_bounds__(256) colsum_reduce_kernel(const float* __restr
 // ------------------------------------------------------------------------------------------------
 // Backward "gradient planes":  gp'[r,n] = g[r',n] * [gelu'(FQ(y))] * mask(y[r,n]) * w_scale[n]  -> bf16 hi/lo planes
 // and per-block partial column sums of the UNSCALED masked gradient (bias grad).
-// blockDim.x = N/4 threads, each owns 4 consecutive columns; a block walks rows_per_block rows.
+// Each thread owns 4 consecutive columns (blockDim.x <= 256 threads, blockIdx.y walks the column groups); a block walks
+// rows_per_block rows.
 // Row remap (patch embed): output row r = b*P + i reads g row b*T + i + 1 (drops the cls token).
 // ------------------------------------------------------------------------------------------------
-__global__ void gp_planes_kernel(const float* __restrict__ g, const float* __restrict__ y_raw, const float* y_scale,
+template <int U>   // rows in flight per thread: 2 U independent 16-byte loads before the first use
+__global__ void __launch_bounds__(256) gp_planes_kernel(const float* __restrict__ g, const float* __restrict__ y_raw, const float* y_scale,
                                  const int32_t* y_zp, int qmin, int qmax, const float* __restrict__ w_scale,
                                  int w_scale_stride, int gelu, int64_t R, int64_t N, int remap_P, int remap_T,
                                  __nv_bfloat16* __restrict__ out, int64_t plane_stride, float* __restrict__ partials,
                                  int rows_per_block) {
-  const int64_t c = static_cast<int64_t>(threadIdx.x) * 4;
+  const int64_t c = (static_cast<int64_t>(blockIdx.y) * blockDim.x + threadIdx.x) * 4;
   if (c >= N) return;
   const OptQ oq = load_optq(y_scale, y_zp, qmin, qmax);
   float4 ws = make_float4(1.f, 1.f, 1.f, 1.f);
@@ -247,7 +249,6 @@ __global__ void gp_planes_kernel(const float* __restrict__ g, const float* __res
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   const int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_block;
   const int64_t r1 = min(R, r0 + rows_per_block);
-  constexpr int U = 4;                       // rows in flight per thread: 8 independent 16-byte loads before the first use
   for (int64_t rb = r0; rb < r1; rb += U) {
     float4 gv[U], yv[U];
 #pragma unroll
@@ -674,12 +675,15 @@ extern "C" int qv_gp_planes(const float* g, const float* y_raw, const float* y_s
                             int64_t N, int32_t remap_P, int32_t remap_T, uint16_t* out_planes, int64_t plane_stride,
                             float* bias_partials, int32_t rows_per_block, void* stream) {
   QV_REQUIRE(g && out_planes && R > 0 && N > 0 && rows_per_block > 0, QV_ERR_INVALID, "bad gp_planes arguments");
-  QV_REQUIRE(N % 4 == 0 && N / 4 <= 1024, QV_ERR_UNSUPPORTED, "gp_planes needs N %% 4 == 0 and N <= 4096 (got %lld)", (long long)N);
+  QV_REQUIRE(N % 4 == 0, QV_ERR_UNSUPPORTED, "gp_planes needs N %% 4 == 0 (got %lld)", (long long)N);
   QV_REQUIRE((y_scale == nullptr) == (y_zp == nullptr), QV_ERR_INVALID, "y_scale and y_zp go together");
   QV_NEED_GPU();
-  const unsigned grid = static_cast<unsigned>((R + rows_per_block - 1) / rows_per_block);
-  const unsigned threads = static_cast<unsigned>(((N / 4) + 31) / 32 * 32);
-  gp_planes_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+  const unsigned gridx = static_cast<unsigned>((R + rows_per_block - 1) / rows_per_block);
+  const unsigned groups = static_cast<unsigned>(N / 4);
+  const unsigned ny = (groups + 255) / 256;                              // column groups per row block, balanced
+  const unsigned threads = ((groups + ny - 1) / ny + 31) / 32 * 32;
+  const dim3 grid(gridx, ny);
+  gp_planes_kernel<4><<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(
       g, y_raw, y_scale, y_zp, qmin, qmax, w_scale, w_scale_per_channel, gelu, R, N, remap_P, remap_T,
       reinterpret_cast<__nv_bfloat16*>(out_planes), plane_stride, bias_partials, rows_per_block);
   return qv_check_launch("qv_gp_planes");
