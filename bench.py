@@ -220,10 +220,9 @@ def run_ours(args):
     host_loss = torch.zeros(3).pin_memory()
 
     def train_step(img, lab):
-        out3 = step(img, lab)                                  # teacher fwd, student fwd, loss, bwd  (our kernels)
-        if sync is not None:
-            sync.all_reduce()                                  # the one exchange of the path: NCCL SUM over NVLink of
-                                                               # [grads | rank-0 observer state] (qatvit_b200/ddp.py)
+        # teacher fwd, student fwd, loss, bwd (our kernels); with N > 1 the one exchange of the path -- NCCL SUM over NVLink of
+        # [grads | rank-0 observer state] (qatvit_b200/ddp.py) -- is issued layer by layer during the backward
+        out3 = step(img, lab, grad_sync=sync)
         if args.torch_optimizer:
             clip_arena_(arena, 1.0, 1.0 / world)               # ref :360 (+ DDP mean)
             opt.step()                                         # ref :361

@@ -92,3 +92,32 @@ class GradSync:
         for w in works:
             w.wait()
         self.unpack_observers()
+
+    # ---- overlapped mode: the engine reports, layer by layer, how much of the arena is final -------------------------
+    def begin_step(self, min_bucket_bytes: int = 4 << 20) -> None:
+        """Call before backward.  Gradients are produced from the END of the arena (head, last block, ...) towards its start
+        (embeddings), like DDP's reverse-order buckets (torch/nn/parallel/distributed.py:831-833): ``grads_final_from(lo)``
+        all-reduces the newly completed suffix asynchronously so the transfer overlaps the remaining backward GEMMs."""
+        self._hi = self.flat.numel()
+        self._works = []
+        self._min_bucket = max(1, min_bucket_bytes // 4)
+        if self.world > 1:
+            self.pack_observers()          # rank 0's running min/max are final after the forward; they ride in the first bucket
+
+    def grads_final_from(self, lo: int) -> None:
+        """Every gradient with arena offset >= lo is final.  lo == 0 flushes what is left."""
+        if self.world == 1:
+            return
+        if lo > 0 and self._hi - lo < self._min_bucket:
+            return
+        if self._hi > lo:
+            self._works.append(dist.all_reduce(self.flat[lo:self._hi], op=dist.ReduceOp.SUM, async_op=True))
+            self._hi = lo
+
+    def end_step(self) -> None:
+        """Wait for the outstanding all-reduces (stream-ordered for NCCL) and adopt rank 0's observer state."""
+        if self.world == 1:
+            return
+        self.grads_final_from(0)
+        self.finish(self._works)
+        self._works = []

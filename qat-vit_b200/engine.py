@@ -333,6 +333,12 @@ class StudentEngine:
             self._goff[id(p)] = off
             off += p.numel()
         self.attach_grads()
+        # arena offset below which nothing belongs to block l or later (parameters are laid out in module order)
+        self._block_lo = [min(self._goff[id(p)] for p in blk.parameters()) for blk in vit.blocks]
+        order_ok = all(self._block_lo[i] < self._block_lo[i + 1] for i in range(L - 1)) and \
+            all(self._goff[id(p)] > self._block_lo[-1] for p in list(vit.norm.parameters()) + list(vit.head.parameters()))
+        if not order_ok:
+            raise RuntimeError("unexpected parameter order: blocks / norm / head must follow each other in the gradient arena")
 
         # Fused attention works on the integer codes of the fake-quantised q, k, v (FQ(x) = code * scale): one exact bf16
         # plane instead of hi/lo planes, scores never leave tensor memory, backward recomputes P from the saved logsumexp.
@@ -539,7 +545,9 @@ class StudentEngine:
         ops.gp_planes(g, y_raw, ql.afq.q, ql.wscale_vec, True, gelu, R, ql.N, out_planes, part, self.rpb_gp, remap[0], remap[1])
         ops.colsum_reduce(part, nblk, ql.N, self._grad(ql.bias))
 
-    def backward(self) -> None:
+    def backward(self, grads_final_from=None) -> None:
+        """grads_final_from(lo): optional callback, called as soon as every gradient with arena offset >= lo is final (after
+        the head, after each block, after the embeddings) -- ddp.GradSync uses it to overlap the all-reduce with backward."""
         d, v = self.d, self.vit
         B, T, D, F, M, L, H = d.B, d.T, d.D, d.F, d.M, d.L, d.H
         BH = B * H
@@ -553,6 +561,8 @@ class StudentEngine:
         ops.ln_bwd(self.g_xn, self.xcls, self.statsF[0], self.statsF[1], v.norm.weight.detach(), None, B, D, gx, self.ln_part,
                    self.rpb_ln, out_row_stride=T)
         self._ln_param_grads(v.norm, nblk_ln)
+        if grads_final_from is not None:
+            grads_final_from(min(self._goff[id(p)] for p in list(v.norm.parameters()) + list(v.head.parameters())))
         nblk_ln = -(-M // self.rpb_ln)
         for l in range(L - 1, -1, -1):
             blk, ql = v.blocks[l], self.lin[l]
@@ -607,11 +617,15 @@ class StudentEngine:
                 ops.ln_bwd(self.g_h, self.x_in[l], self.stats1[l][0], self.stats1[l][1], blk.norm1.weight.detach(), gx2, M, D, gx,
                            self.ln_part, self.rpb_ln)
             self._ln_param_grads(blk.norm1, nblk_ln)
+            if grads_final_from is not None:
+                grads_final_from(self._block_lo[l])
         # ---- embeddings: pos_embed, cls_token, patch-embed conv ----
         ops.colsum_rows(gx, B, T * D, T * D, self._grad(v.pos_embed))
         ops.colsum_rows(gx, B, D, T * D, self._grad(v.cls_token))
         self._gp(gx, self.p_raw, self.conv, False, B * d.P, self.gpP, remap=(d.P, T))
         self._wgrad(self.conv, self.gpP, self.img_codes, B * d.P, PAIRS_EXACT_B, alpha=self.fq_in.scale)
+        if grads_final_from is not None:
+            grads_final_from(0)
 
 
 class QATDistillStep:
@@ -624,10 +638,16 @@ class QATDistillStep:
         self.teacher_engine = TeacherEngine(teacher, batch)
         self.grad_arena = self.student_engine.grad_arena
 
-    def __call__(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    def __call__(self, images: torch.Tensor, labels: torch.Tensor, grad_sync=None) -> torch.Tensor:
+        """grad_sync: a ddp.GradSync whose buffer holds the gradient arena -- its all-reduce then overlaps the backward."""
         t_logits = self.teacher_engine.forward(images)
         out3 = self.student_engine.forward(images, labels, t_logits)
-        self.student_engine.backward()
+        if grad_sync is None:
+            self.student_engine.backward()
+        else:
+            grad_sync.begin_step()
+            self.student_engine.backward(grads_final_from=grad_sync.grads_final_from)
+            grad_sync.end_step()
         return out3
 
     @property

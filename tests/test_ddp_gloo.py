@@ -24,17 +24,23 @@ def _worker(rank, world, port, async_op, q):
     gs.bind_observers(obs)
     g = torch.randn(1000)
     gs.grad_arena.copy_(g)
-    works = gs.all_reduce(async_op=async_op)
-    if async_op:
-        gs.finish(works)
+    if async_op == "overlapped":        # layer-by-layer suffixes, as the engine's backward reports them
+        gs.begin_step(min_bucket_bytes=512)
+        for lo in (900, 870, 600, 590, 300, 0):
+            gs.grads_final_from(lo)
+        gs.end_step()
+    else:
+        works = gs.all_reduce(async_op=async_op)
+        if async_op:
+            gs.finish(works)
     q.put((rank, g, gs.grad_arena.clone(), [(float(a), float(b)) for a, b in obs]))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("async_op", [False, True])
+@pytest.mark.parametrize("async_op", [False, True, "overlapped"])
 def test_gradient_sum_and_rank0_observer_state(async_op):
-    world, port = 2, 29000 + os.getpid() % 2000 + (1 if async_op else 0)
+    world, port = 2, 29000 + os.getpid() % 2000 + [False, True, "overlapped"].index(async_op)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, world, port, async_op, q)) for r in range(world)]

@@ -42,6 +42,17 @@ def _worker(rank, world, port, q):
     local_obs = [(float(a), float(b)) for a, b in step.activation_observers()]
     sync.all_reduce()
     torch.cuda.synchronize()
+    reduced_blocking = sync.grad_arena.clone()
+    # the overlapped mode (all-reduce issued layer by layer during backward) must give the same sums: rerun the same step on a
+    # fresh copy of the model / observer state
+    student2 = copy.deepcopy(prepared).to(dev)
+    sync2 = GradSync(n_grad, n_obs, dev)
+    step2 = QATDistillStep(student2, copy.deepcopy(teacher).to(dev), B, hp, grad_buffer=sync2.grad_arena)
+    sync2.bind_observers(step2.activation_observers())
+    step2(images[sl].to(dev), labels[sl].to(dev), grad_sync=sync2)
+    torch.cuda.synchronize()
+    assert torch.equal(sync2.grad_arena, reduced_blocking), "overlapped all-reduce differs from the blocking one"
+    assert [(float(a), float(b)) for a, b in step2.activation_observers()] == [(float(a), float(b)) for a, b in step.activation_observers()]
     q.put((rank, local.cpu(), sync.grad_arena.cpu().clone(), local_obs, [(float(a), float(b)) for a, b in step.activation_observers()]))
     dist.barrier()
     dist.destroy_process_group()
