@@ -129,6 +129,14 @@ typedef struct qv_gemm_args {
    * pair of Linears with no observer in between (the teacher) never round-trips fp32 through HBM.
    * act = 1: exact-erf GELU after scale/bias (timm Mlp.act fused into fc1's epilogue); needs out_kind = 1. */
   int32_t out_kind; int32_t act; int64_t out_plane_stride;
+  /* act = 2 (needs out_kind = 1, (2,1) planes): the dgrad GEMM that produces dL/d(out of a fake-quantised Linear [+ GELU])
+   * applies that Linear's backward prologue in its epilogue -- qv_gp_planes fused (STE of torch's
+   * FusedMovingAvgObsFqHelperBackward0 and GeluBackward0):
+   *   gq[m,n] = acc[m,n] * (ep_gelu ? gelu'(FQ(y[m,n])) : 1) * STEmask(y[m,n]),   y = ep_raw (row pitch ep_raw_ld floats),
+   *   out planes = hi/lo split of gq * col_scale[n];  ep_colsum (may be NULL): fp32 [ceil(M/32)][N], row s = column sums
+   *   of gq over token rows 32 s .. 32 s + 31 (bias-grad partials; reduce with qv_colsum_reduce). */
+  const float* ep_raw; int64_t ep_raw_ld; const float* ep_scale; const int32_t* ep_zp;
+  int32_t ep_qmin, ep_qmax, ep_gelu; float* ep_colsum;
 } qv_gemm_args;
 int qv_gemm_bf16(const qv_gemm_args* args, void* stream);
 
@@ -159,6 +167,15 @@ int qv_ln_bwd(const float* g_h, const float* x, const float* mean, const float* 
               const float* g_res, int64_t R, int32_t D, int64_t out_row_stride, float* g_x, float* partials,
               int32_t rows_per_block, const float* h_raw, const float* h_scale, const int32_t* h_zp, int32_t qmin, int32_t qmax,
               void* stream);
+/* qv_ln_bwd (out_row_stride 1) that also emits the gradient planes of the Linear whose fake-quantised output gp_y was added
+ * into the residual stream this LayerNorm reads (attn.proj for norm2, the previous block's mlp.fc2 for norm1):
+ * gp_out = hi/lo planes [2][R][D] of g_x * STEmask(gp_y) * gp_wscale[col]; gp_partials (may be NULL) fp32
+ * [ceil(R/rows_per_block)][D]: per-block column sums of g_x * mask (that Linear's bias grad; reduce with qv_colsum_reduce). */
+int qv_ln_bwd_gp(const float* g_h, const float* x, const float* mean, const float* rstd, const float* gamma, const float* g_res,
+                 int64_t R, int32_t D, float* g_x, float* partials, int32_t rows_per_block, const float* h_raw,
+                 const float* h_scale, const int32_t* h_zp, int32_t qmin, int32_t qmax, const float* gp_y, const float* gp_scale,
+                 const int32_t* gp_zp, int32_t gp_qmin, int32_t gp_qmax, const float* gp_wscale, uint16_t* gp_out,
+                 int64_t gp_plane_stride, float* gp_partials, void* stream);
 int qv_colsum_reduce(const float* partials, int32_t nblk, int64_t ncols, float* out, int32_t accumulate, void* stream);
 int qv_colsum_rows(const float* x, int64_t R, int64_t N, int64_t ld, float* out, int32_t accumulate, void* stream);
 /* gp'[r,n] = g[r',n] * [gelu'(FQ(y))] * STEmask(y_raw[r,n]) * w_scale[n] -> bf16 hi/lo planes [2][R][N], plus per-block
@@ -205,6 +222,15 @@ int qv_attn_fwd(const uint16_t* qkv_planes, int32_t n_planes, int64_t plane_stri
  * hi/lo planes [2][B*T][do_ld] of dL/dO; lse: fp32 [B*H*T] (qv_attn_fwd); qscale: device scalar s (NULL = 1).  T <= 224. */
 int qv_attn_bwd(const uint16_t* qkv_codes, int64_t ld, const float* qscale, const uint16_t* do_planes, int64_t do_plane_stride,
                 int64_t do_ld, const float* lse, int32_t B, int32_t T, int32_t H, float scale, float* g_qkv, void* stream);
+/* qv_attn_bwd with the qkv Linear's backward prologue (qv_gp_planes) fused into its output stage: instead of fp32 dQ | dK | dV,
+ * writes gp = g * STEmask(y_raw) * w_scale[col] as bf16 hi/lo planes [2][B*T][3*H*64] (the A operand of the qkv dgrad / wgrad
+ * GEMMs) and colsum fp32 [B * ceil(T/128) * 4][3*H*64]: per 32-token slab column sums of g * mask (bias-grad partials, reduce
+ * with qv_colsum_reduce).  y_raw: the qkv Linear's raw output fp32 [B*T][3*H*64]; (y_scale, y_zp, qmin, qmax): its output
+ * fake-quant; w_scale: fp32 [3*H*64] per-output-channel weight scale. */
+int qv_attn_bwd_gp(const uint16_t* qkv_codes, int64_t ld, const float* qscale, const uint16_t* do_planes,
+                   int64_t do_plane_stride, int64_t do_ld, const float* lse, int32_t B, int32_t T, int32_t H, float scale,
+                   const float* y_raw, const float* y_scale, const int32_t* y_zp, int32_t qmin, int32_t qmax,
+                   const float* w_scale, uint16_t* gp_planes, int64_t gp_plane_stride, float* colsum, void* stream);
 /* classifier head (D -> num_classes), exact fp32: out = x wq^T + bias (+ fused output-observer min/max). */
 int qv_head_fwd(const float* x, const float* wq, const float* bias, int32_t B, int32_t K, int32_t N, float* out,
                 uint32_t* minmax, void* stream);

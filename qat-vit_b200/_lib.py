@@ -53,6 +53,8 @@ class GemmArgs(ctypes.Structure):
         ("splits", c_int32), ("workspace", c_void_p),
         ("nbatch", c_int32), ("batch_inner", c_int32), ("tile_n", c_int32),
         ("out_kind", c_int32), ("act", c_int32), ("out_plane_stride", c_int64),
+        ("ep_raw", c_void_p), ("ep_raw_ld", c_int64), ("ep_scale", c_void_p), ("ep_zp", c_void_p),
+        ("ep_qmin", c_int32), ("ep_qmax", c_int32), ("ep_gelu", c_int32), ("ep_colsum", c_void_p),
     ]
 
 
@@ -77,6 +79,8 @@ _SIGNATURES = {
     "qv_resid_ln_fwd": (c_int, [_P, _P, _P, _P, c_int32, c_int32, _P, _P, c_float, c_int64, c_int32, c_int64, _P, _P,
                                 c_int64, _P, _P, _P, _P, _P]),
     "qv_ln_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int32, c_int64, _P, _P, c_int32, _P, _P, _P, c_int32, c_int32, _P]),
+    "qv_ln_bwd_gp": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int32, _P, _P, c_int32, _P, _P, _P, c_int32, c_int32,
+                             _P, _P, _P, c_int32, c_int32, _P, _P, c_int64, _P, _P]),
     "qv_colsum_reduce": (c_int, [_P, c_int32, c_int64, _P, c_int32, _P]),
     "qv_colsum_rows": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int32, _P]),
     "qv_gp_planes": (c_int, [_P, _P, _P, _P, c_int32, c_int32, _P, c_int32, c_int32, c_int64, c_int64, c_int32, c_int32,
@@ -89,6 +93,8 @@ _SIGNATURES = {
     "qv_attn_fwd": (c_int, [_P, c_int32, c_int64, c_int64, c_int32, c_int32, c_int32, c_float, _P, _P, _P, c_int64, c_int64,
                             _P, _P, _P]),
     "qv_attn_bwd": (c_int, [_P, c_int64, _P, _P, c_int64, c_int64, _P, c_int32, c_int32, c_int32, c_float, _P, _P]),
+    "qv_attn_bwd_gp": (c_int, [_P, c_int64, _P, _P, c_int64, c_int64, _P, c_int32, c_int32, c_int32, c_float,
+                               _P, _P, _P, c_int32, c_int32, _P, _P, c_int64, _P, _P]),
     "qv_clip_adamw": (c_int, [_P, _P, _P, _P, c_int64, _P, c_int32, c_float, c_float, c_float, c_float, c_float, c_float, c_float,
                               c_int64, _P, c_int32, _P]),
     "qv_int8_linear": (c_int, [_P, c_int64, c_int64, _P, _P, _P, c_int64, _P, c_int32, _P, _P, c_float, c_int32, c_int32, _P, _P,

@@ -385,8 +385,19 @@ struct AttnBwdParams {
   const float* qscale;      // device scalar s (Q = K = V scale); may be null (= 1)
   const float* lse;         // [B*H*T] from the forward
   float* g_qkv;             // [B*T][3*D]: dQ | dK | dV column blocks
+  // FUSED: the qkv Linear's backward prologue (qv_gp_planes) applied on the way out -- gq = g * STEmask(y_raw),
+  // planes = hi/lo split of gq * w_scale[col], per-slab column sums of gq (bias grad partials)
+  const float* y_raw;       // [B*T][3*D] raw qkv output
+  const float* y_scale;
+  const int32_t* y_zp;
+  int32_t qmin, qmax;
+  const float* w_scale;     // [3*D]
+  __nv_bfloat16* gp;        // [2][B*T][3*D]
+  int64_t gp_plane_stride;
+  float* colsum;            // [B * m_tiles * 4][3*D]
 };
 
+template <bool FUSED>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
                    const AttnBwdParams p) {
@@ -530,6 +541,48 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
     const float c2 = p.scale * s * s * 1.4426950408889634f;
     const float gscale = p.scale * s * s;        // dQ, dK factor (see header comment)
     const int ctid = threadIdx.x - 64;           // 0..255
+    QvQParams yq;
+    if constexpr (FUSED) yq = qv_load_qparams(p.y_scale, p.y_zp, p.qmin, p.qmax);
+    const int D3 = 3 * D;
+    // FUSED output of one 32-row x 32-column block: lane = token `tok` of image b, columns col .. col+31 of the [., 3D] row
+    auto load_y = [&](float4 (&yv)[8], int b, int tok, int col) {
+      const float4* yp = reinterpret_cast<const float4*>(p.y_raw + (static_cast<int64_t>(b) * p.T + tok) * D3 + col);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) yv[j] = (tok < p.T) ? __ldg(yp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    auto emit = [&](const uint32_t (&o)[32], const float4 (&yv)[8], float mult, int b, int tok, int col, int slab) {
+      const bool ok = tok < p.T;
+      float gq[32];
+      __nv_bfloat16* dst = p.gp + (static_cast<int64_t>(b) * p.T + tok) * D3 + col;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {                                // 8 columns per step: one 16-byte store per plane
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int hlf = 0; hlf < 2; ++hlf) {
+          const float4 ws = __ldg(reinterpret_cast<const float4*>(p.w_scale + col) + 2 * j + hlf);
+          const float4 y4 = yv[2 * j + hlf];
+          const float yy[4] = {y4.x, y4.y, y4.z, y4.w};
+          const float wv[4] = {ws.x, ws.y, ws.z, ws.w};
+          float a[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float r = __fadd_rn(rintf(__fmul_rn(yy[e], yq.inv)), yq.zp);
+            const bool in = (yq.qmin <= r) && (r <= yq.qmax);
+            const float f = (ok && in) ? __uint_as_float(o[8 * j + 4 * hlf + e]) * mult : 0.f;
+            gq[8 * j + 4 * hlf + e] = f;
+            a[e] = f * wv[e];
+          }
+          split_pack2(a[0], a[1], hi[2 * hlf], lo[2 * hlf]);
+          split_pack2(a[2], a[3], hi[2 * hlf + 1], lo[2 * hlf + 1]);
+        }
+        if (ok) {
+          *reinterpret_cast<uint4*>(dst + 8 * j) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(dst + p.gp_plane_stride + 8 * j) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      }
+      const float cs = qv_warp_colsum32(gq, lane);
+      p.colsum[static_cast<int64_t>(slab) * D3 + col + lane] = cs;
+    };
     uint32_t sp = 0, spb = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       const int b = item / p.H, h = item % p.H;
@@ -581,6 +634,8 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         tc_fence_before();
         mbar_arrive(cmp_done);
         // dQ tile: this warp stores columns par*32 .. par*32+31 of its 32 rows
+        float4 yv[FUSED ? 8 : 1];
+        if constexpr (FUSED) load_y(yv, b, i, h * HD + par * 32);       // in flight while the dQ MMAs finish
         mbar_wait(acc_done, sp & 1);
         tc_fence_after();
         uint32_t o[32];
@@ -588,7 +643,9 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(epi_done);
-        if (i < p.T) {
+        if constexpr (FUSED) {
+          emit(o, yv, gscale, b, i, h * HD + par * 32, (b * mt + g) * 4 + q);
+        } else if (i < p.T) {
           float* dst = grow_base + static_cast<int64_t>(i) * (3 * D);
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -625,11 +682,16 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         tc_fence_before();
         mbar_arrive(cmp_done);
         uint32_t o[32];
+        float4 yv[FUSED ? 8 : 1];
+        if constexpr (FUSED) load_y(yv, b, jrow, 2 * D + h * HD + par * 32);
         mbar_wait(acc_done, sp & 1);                              // dV
         tc_fence_after();
         tmem_ld_32x32(acc0 + par * 32, o);
         tmem_ld_wait();
-        if (jrow < p.T) {
+        if constexpr (FUSED) {
+          emit(o, yv, 1.0f, b, jrow, 2 * D + h * HD + par * 32, (b * mt + kt) * 4 + q);
+          load_y(yv, b, jrow, D + h * HD + par * 32);
+        } else if (jrow < p.T) {
           float* dst = grow_base + static_cast<int64_t>(jrow) * (3 * D) + 2 * D;
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -642,7 +704,9 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(epi_done);
-        if (jrow < p.T) {
+        if constexpr (FUSED) {
+          emit(o, yv, gscale, b, jrow, D + h * HD + par * 32, (b * mt + kt) * 4 + q);
+        } else if (jrow < p.T) {
           float* dst = grow_base + static_cast<int64_t>(jrow) * (3 * D) + D;
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -709,16 +773,45 @@ extern "C" int qv_attn_fwd(const uint16_t* qkv_planes, int32_t n_planes, int64_t
   return launch_attn<1>(mq, mk, mv, ap, grid, st);
 }
 
+namespace {
+int attn_bwd_impl(const uint16_t* qkv_codes, int64_t ld, const float* qscale, const uint16_t* do_planes, int64_t do_plane_stride,
+                  int64_t do_ld, const float* lse, int32_t B, int32_t T, int32_t H, float scale, float* g_qkv,
+                  const AttnBwdParams* fused, void* stream);
+}
+
 extern "C" int qv_attn_bwd(const uint16_t* qkv_codes, int64_t ld, const float* qscale, const uint16_t* do_planes,
                            int64_t do_plane_stride, int64_t do_ld, const float* lse, int32_t B, int32_t T, int32_t H, float scale,
                            float* g_qkv, void* stream) {
-  QV_REQUIRE(qkv_codes && do_planes && lse && g_qkv && B > 0 && T > 0 && H > 0, QV_ERR_INVALID, "bad attn_bwd arguments");
+  QV_REQUIRE(g_qkv && qv_aligned16(g_qkv), QV_ERR_INVALID, "g_qkv must be a 16-byte aligned device pointer");
+  return attn_bwd_impl(qkv_codes, ld, qscale, do_planes, do_plane_stride, do_ld, lse, B, T, H, scale, g_qkv, nullptr, stream);
+}
+
+extern "C" int qv_attn_bwd_gp(const uint16_t* qkv_codes, int64_t ld, const float* qscale, const uint16_t* do_planes,
+                              int64_t do_plane_stride, int64_t do_ld, const float* lse, int32_t B, int32_t T, int32_t H,
+                              float scale, const float* y_raw, const float* y_scale, const int32_t* y_zp, int32_t qmin,
+                              int32_t qmax, const float* w_scale, uint16_t* gp_planes, int64_t gp_plane_stride,
+                              float* colsum, void* stream) {
+  QV_REQUIRE(y_raw && y_scale && y_zp && w_scale && gp_planes && colsum, QV_ERR_INVALID, "bad attn_bwd_gp arguments");
+  QV_REQUIRE(qv_aligned16(y_raw) && qv_aligned16(w_scale) && qv_aligned16(gp_planes) && gp_plane_stride % 8 == 0, QV_ERR_INVALID,
+             "y_raw / w_scale / gp_planes must be 16-byte aligned (plane stride a multiple of 8 bf16)");
+  AttnBwdParams f;
+  memset(&f, 0, sizeof(f));
+  f.y_raw = y_raw; f.y_scale = y_scale; f.y_zp = y_zp; f.qmin = qmin; f.qmax = qmax; f.w_scale = w_scale;
+  f.gp = reinterpret_cast<__nv_bfloat16*>(gp_planes); f.gp_plane_stride = gp_plane_stride; f.colsum = colsum;
+  return attn_bwd_impl(qkv_codes, ld, qscale, do_planes, do_plane_stride, do_ld, lse, B, T, H, scale, nullptr, &f, stream);
+}
+
+namespace {
+int attn_bwd_impl(const uint16_t* qkv_codes, int64_t ld, const float* qscale, const uint16_t* do_planes, int64_t do_plane_stride,
+                  int64_t do_ld, const float* lse, int32_t B, int32_t T, int32_t H, float scale, float* g_qkv,
+                  const AttnBwdParams* fused, void* stream) {
+  QV_REQUIRE(qkv_codes && do_planes && lse && (g_qkv || fused) && B > 0 && T > 0 && H > 0, QV_ERR_INVALID, "bad attn_bwd arguments");
   QV_REQUIRE(T <= 224, QV_ERR_UNSUPPORTED, "fused attention holds all keys in one tile: T <= 224 (got %d)", T);
   QV_REQUIRE(ld >= 3LL * H * HD && do_ld >= static_cast<int64_t>(H) * HD, QV_ERR_INVALID, "row pitches too small");
-  QV_REQUIRE(qv_aligned16(g_qkv), QV_ERR_INVALID, "g_qkv must be 16-byte aligned");
   QV_REQUIRE(qv_num_sms() > 0, QV_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
   AttnBwdParams ap;
   memset(&ap, 0, sizeof(ap));
+  if (fused) ap = *fused;
   ap.B = B; ap.T = T; ap.H = H;
   ap.n_keys = (T + 15) / 16 * 16;
   ap.m_tiles = (T + 127) / 128;
@@ -740,12 +833,16 @@ extern "C" int qv_attn_bwd(const uint16_t* qkv_codes, int64_t ld, const float* q
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(qv_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM_BYTES);
+    attr_err = cudaFuncSetAttribute(qv_attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM_BYTES);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(qv_attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM_BYTES);
   });
   QV_REQUIRE(attr_err == cudaSuccess, QV_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
   const int items = B * H;
   const int sms = qv_num_sms();
   const int grid = items < sms ? items : sms;
-  qv_attn_bwd_kernel<<<grid, AT_THREADS, BW_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(mq, md, ap);
+  if (fused) qv_attn_bwd_kernel<true><<<grid, AT_THREADS, BW_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(mq, md, ap);
+  else qv_attn_bwd_kernel<false><<<grid, AT_THREADS, BW_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(mq, md, ap);
   return qv_check_launch("qv_attn_bwd");
 }
+}  // namespace

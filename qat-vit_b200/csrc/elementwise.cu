@@ -22,12 +22,8 @@ __device__ __forceinline__ OptQ load_optq(const float* scale, const int32_t* zp,
   return o;
 }
 
-__device__ __forceinline__ float gelu_fwd(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
-__device__ __forceinline__ float gelu_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-  const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
-  return cdf + x * pdf;
-}
+__device__ __forceinline__ float gelu_fwd(float x) { return qv_gelu_fwd(x); }
+__device__ __forceinline__ float gelu_grad(float x) { return qv_gelu_grad(x); }
 
 __device__ __forceinline__ void store_planes4(__nv_bfloat16* hi, __nv_bfloat16* lo, int64_t idx, float a, float b,
                                               float c, float d) {
@@ -137,13 +133,23 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ g
                                                      int64_t R, int64_t out_row_stride, float* __restrict__ g_x,
                                                      float* __restrict__ partials, int rows_per_block,
                                                      const float* __restrict__ h_raw, const float* h_scale,
-                                                     const int32_t* h_zp, int qmin, int qmax) {
+                                                     const int32_t* h_zp, int qmin, int qmax,
+                                                     const float* __restrict__ gp_y, const float* gp_scale, const int32_t* gp_zp,
+                                                     int gp_qmin, int gp_qmax, const float* __restrict__ gp_wscale,
+                                                     __nv_bfloat16* __restrict__ gp_out, int64_t gp_plane_stride,
+                                                     float* __restrict__ gp_partials) {
   constexpr int D = 128 * VPL;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const OptQ hq = load_optq(h_raw ? h_scale : nullptr, h_zp, qmin, qmax);   // observed LN output: g_h passes its STE mask
-  float4 dg[VPL], db[VPL];
+  // fused gradient planes of the Linear whose (fake-quantised) output y was added into this residual stream:
+  // gp = g_x * STEmask(y) * w_scale -> hi/lo planes, per-block column sums of g_x * mask (its bias grad)
+  const OptQ gq_ = load_optq(gp_y ? gp_scale : nullptr, gp_zp, gp_qmin, gp_qmax);
+  float4 dg[VPL], db[VPL], dbias[VPL], wsv[VPL];
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) dg[i] = db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < VPL; ++i) {
+    dg[i] = db[i] = dbias[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    wsv[i] = gq_.on ? __ldg(reinterpret_cast<const float4*>(gp_wscale + (i * 32 + lane) * 4)) : make_float4(1.f, 1.f, 1.f, 1.f);
+  }
   float4 gm[VPL];
 #pragma unroll
   for (int i = 0; i < VPL; ++i) gm[i] = __ldg(reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 4));
@@ -185,6 +191,15 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ g
         o.x += gr.x; o.y += gr.y; o.z += gr.z; o.w += gr.w;
       }
       *reinterpret_cast<float4*>(g_x + r * out_row_stride * D + c) = o;
+      if (gq_.on) {
+        const float4 yv = __ldg(reinterpret_cast<const float4*>(gp_y + r * D + c));
+        bool in0, in1, in2, in3;
+        qv_fq(yv.x, gq_.q, &in0, nullptr); qv_fq(yv.y, gq_.q, &in1, nullptr);
+        qv_fq(yv.z, gq_.q, &in2, nullptr); qv_fq(yv.w, gq_.q, &in3, nullptr);
+        o.x = in0 ? o.x : 0.f; o.y = in1 ? o.y : 0.f; o.z = in2 ? o.z : 0.f; o.w = in3 ? o.w : 0.f;
+        dbias[i].x += o.x; dbias[i].y += o.y; dbias[i].z += o.z; dbias[i].w += o.w;
+        store_planes4(gp_out, gp_out + gp_plane_stride, r * D + c, o.x * wsv[i].x, o.y * wsv[i].y, o.z * wsv[i].z, o.w * wsv[i].w);
+      }
     }
   }
   // block reduce of the per-warp column partials (fixed order)
@@ -203,25 +218,65 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ g
       *reinterpret_cast<float4*>(partials + (static_cast<int64_t>(blockIdx.x) * 2 + which) * D + c4 * 4) = a;
     }
   }
+  if (gq_.on && gp_partials) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) sm[warp][0][i * 32 + lane] = dbias[i];
+    __syncthreads();
+    for (int c4 = threadIdx.x; c4 < VPL * 32; c4 += blockDim.x) {
+      float4 a = sm[0][0][c4];
+      for (int w = 1; w < nwarps; ++w) {
+        const float4 b = sm[w][0][c4];
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      *reinterpret_cast<float4*>(gp_partials + static_cast<int64_t>(blockIdx.x) * D + c4 * 4) = a;
+    }
+  }
 }
 
-// out[c] (+)= sum_b partials[b][c].  Block = 32 columns x 8 row slices (128-byte coalesced row reads), fixed-order
-// combine so the result is deterministic.
-__global__ void __launch_bounds__(256) colsum_reduce_kernel(const float* __restrict__ partials, int nblk, int64_t ncols,
-                                                            float* __restrict__ out, int accumulate) {
-  __shared__ float sm[8][32];
-  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
-  const int64_t c = blockIdx.x * 32LL + cx;
-  float s = 0.f;
-  if (c < ncols)
-    for (int b = ry; b < nblk; b += 8) s += __ldg(partials + static_cast<int64_t>(b) * ncols + c);
-  sm[ry][cx] = s;
+// out[c] (+)= sum_b partials[b][c].  Block = 32 columns (8 lanes x float4) x 128 row slices: every thread's loads are
+// independent 16-byte reads (all in flight at once), rows are read as full 128-byte lines; fixed-order combine in shared
+// memory so the result is deterministic.  ncols % 4 == 0 takes the vector path.
+__global__ void __launch_bounds__(1024) colsum_reduce_kernel(const float* __restrict__ partials, int nblk, int64_t ncols,
+                                                             float* __restrict__ out, int accumulate, int vec) {
+  __shared__ float sm[128][33];
+  const int c4 = threadIdx.x & 7, slice = threadIdx.x >> 3;
+  const int64_t c = blockIdx.x * 32LL + c4 * 4;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (vec) {
+    if (c < ncols) {
+#pragma unroll 4
+      for (int b = slice; b < nblk; b += 128) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(partials + static_cast<int64_t>(b) * ncols + c));
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+    }
+  } else {
+    for (int b = slice; b < nblk; b += 128) {
+      const float* row = partials + static_cast<int64_t>(b) * ncols;
+      if (c + 0 < ncols) s.x += __ldg(row + c + 0);
+      if (c + 1 < ncols) s.y += __ldg(row + c + 1);
+      if (c + 2 < ncols) s.z += __ldg(row + c + 2);
+      if (c + 3 < ncols) s.w += __ldg(row + c + 3);
+    }
+  }
+  sm[slice][c4 * 4 + 0] = s.x; sm[slice][c4 * 4 + 1] = s.y; sm[slice][c4 * 4 + 2] = s.z; sm[slice][c4 * 4 + 3] = s.w;
   __syncthreads();
-  if (ry == 0 && c < ncols) {
-    float t = sm[0][cx];
-#pragma unroll
-    for (int k = 1; k < 8; ++k) t += sm[k][cx];
-    out[c] = accumulate ? out[c] + t : t;
+  // 128 slices -> 4 partial sums per column (threads 0..127), then one thread per column adds the four in order
+  if (threadIdx.x < 128) {
+    const int col = threadIdx.x & 31, part = threadIdx.x >> 5;
+    float t = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) t += sm[part * 32 + k][col];
+    sm[part * 32][col] = t;         // slot (part*32, col) was read only by this thread
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int64_t cc = blockIdx.x * 32LL + threadIdx.x;
+    if (cc < ncols) {
+      const float t = ((sm[0][threadIdx.x] + sm[32][threadIdx.x]) + sm[64][threadIdx.x]) + sm[96][threadIdx.x];
+      out[cc] = accumulate ? out[cc] + t : t;
+    }
   }
 }
 
@@ -627,10 +682,12 @@ extern "C" int qv_resid_ln_fwd(const float* x_in, const float* y_raw, const floa
   return qv_check_launch("qv_resid_ln_fwd");
 }
 
-extern "C" int qv_ln_bwd(const float* g_h, const float* x, const float* mean, const float* rstd, const float* gamma,
-                         const float* g_res, int64_t R, int32_t D, int64_t out_row_stride, float* g_x, float* partials,
-                         int32_t rows_per_block, const float* h_raw, const float* h_scale, const int32_t* h_zp, int32_t qmin,
-                         int32_t qmax, void* stream) {
+namespace {
+int ln_bwd_impl(const float* g_h, const float* x, const float* mean, const float* rstd, const float* gamma, const float* g_res,
+                int64_t R, int32_t D, int64_t out_row_stride, float* g_x, float* partials, int32_t rows_per_block,
+                const float* h_raw, const float* h_scale, const int32_t* h_zp, int32_t qmin, int32_t qmax, const float* gp_y,
+                const float* gp_scale, const int32_t* gp_zp, int32_t gp_qmin, int32_t gp_qmax, const float* gp_wscale,
+                uint16_t* gp_out, int64_t gp_plane_stride, float* gp_partials, void* stream) {
   QV_REQUIRE(g_h && x && mean && rstd && gamma && g_x && R > 0 && rows_per_block > 0, QV_ERR_INVALID, "bad ln_bwd arguments");
   QV_REQUIRE(D % 128 == 0 && D >= 128 && D <= 1024, QV_ERR_UNSUPPORTED, "LayerNorm width must be a multiple of 128 <= 1024 (got %d)", D);
   QV_REQUIRE(!h_raw || (h_scale && h_zp), QV_ERR_INVALID, "h_raw needs h_scale and h_zp");
@@ -639,7 +696,9 @@ extern "C" int qv_ln_bwd(const float* g_h, const float* x, const float* mean, co
   const unsigned grid = static_cast<unsigned>((R + rows_per_block - 1) / rows_per_block);
   if (out_row_stride < 1) out_row_stride = 1;
 #define LAUNCH(V) ln_bwd_kernel<V><<<grid, 256, 0, st>>>(g_h, x, mean, rstd, gamma, g_res, R, out_row_stride, g_x, partials, \
-                                                         rows_per_block, h_raw, h_scale, h_zp, qmin, qmax)
+                                                         rows_per_block, h_raw, h_scale, h_zp, qmin, qmax, gp_y, gp_scale, gp_zp, \
+                                                         gp_qmin, gp_qmax, gp_wscale, reinterpret_cast<__nv_bfloat16*>(gp_out),   \
+                                                         gp_plane_stride, gp_partials)
   switch (D / 128) {
     case 1: LAUNCH(1); break;
     case 2: LAUNCH(2); break;
@@ -651,13 +710,34 @@ extern "C" int qv_ln_bwd(const float* g_h, const float* x, const float* mean, co
 #undef LAUNCH
   return qv_check_launch("qv_ln_bwd");
 }
+}  // namespace
+
+extern "C" int qv_ln_bwd(const float* g_h, const float* x, const float* mean, const float* rstd, const float* gamma,
+                         const float* g_res, int64_t R, int32_t D, int64_t out_row_stride, float* g_x, float* partials,
+                         int32_t rows_per_block, const float* h_raw, const float* h_scale, const int32_t* h_zp, int32_t qmin,
+                         int32_t qmax, void* stream) {
+  return ln_bwd_impl(g_h, x, mean, rstd, gamma, g_res, R, D, out_row_stride, g_x, partials, rows_per_block, h_raw, h_scale, h_zp,
+                     qmin, qmax, nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr, 0, nullptr, stream);
+}
+
+extern "C" int qv_ln_bwd_gp(const float* g_h, const float* x, const float* mean, const float* rstd, const float* gamma,
+                            const float* g_res, int64_t R, int32_t D, float* g_x, float* partials, int32_t rows_per_block,
+                            const float* h_raw, const float* h_scale, const int32_t* h_zp, int32_t qmin, int32_t qmax,
+                            const float* gp_y, const float* gp_scale, const int32_t* gp_zp, int32_t gp_qmin, int32_t gp_qmax,
+                            const float* gp_wscale, uint16_t* gp_out, int64_t gp_plane_stride, float* gp_partials, void* stream) {
+  QV_REQUIRE(gp_y && gp_scale && gp_zp && gp_wscale && gp_out, QV_ERR_INVALID, "bad ln_bwd_gp arguments");
+  QV_REQUIRE(qv_aligned16(gp_y) && qv_aligned16(gp_wscale) && qv_aligned16(gp_out) && gp_plane_stride % 4 == 0, QV_ERR_INVALID,
+             "gp_y / gp_wscale / gp_out must be 16-byte aligned");
+  return ln_bwd_impl(g_h, x, mean, rstd, gamma, g_res, R, D, 1, g_x, partials, rows_per_block, h_raw, h_scale, h_zp, qmin, qmax,
+                     gp_y, gp_scale, gp_zp, gp_qmin, gp_qmax, gp_wscale, gp_out, gp_plane_stride, gp_partials, stream);
+}
 
 extern "C" int qv_colsum_reduce(const float* partials, int32_t nblk, int64_t ncols, float* out, int32_t accumulate,
                                 void* stream) {
   QV_REQUIRE(partials && out && nblk > 0 && ncols > 0, QV_ERR_INVALID, "bad colsum_reduce arguments");
   QV_NEED_GPU();
-  colsum_reduce_kernel<<<static_cast<unsigned>((ncols + 31) / 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      partials, nblk, ncols, out, accumulate);
+  colsum_reduce_kernel<<<static_cast<unsigned>((ncols + 31) / 32), 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+      partials, nblk, ncols, out, accumulate, (ncols % 4 == 0 && qv_aligned16(partials)) ? 1 : 0);
   return qv_check_launch("qv_colsum_reduce");
 }
 

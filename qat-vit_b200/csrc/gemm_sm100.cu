@@ -36,8 +36,8 @@ constexpr int A_PLANE_BYTES = BM * BK * 2;
 // epilogue staging per warp: 32-row x 128-byte buffers.  fp32 output: one buffer per 32-column chunk; bf16 hi/lo plane
 // output: a hi and a lo buffer per 64-column chunk.  Two warps alternate on each TMEM lane quarter, so per-warp single
 // buffering already overlaps one warp's TMA store with the other's math.
-constexpr int epi_warp_bytes(int epi) { return (epi == 1 ? 2 : 1) * 32 * 128; }
-constexpr int epi_terms_bytes(int epi) { return epi == 1 ? 0 : 8 * 2 * 32 * 4; }   // per-warp [mult][bias] column terms
+constexpr int epi_warp_bytes(int epi) { return (epi >= 1 ? 2 : 1) * 32 * 128; }
+constexpr int epi_terms_bytes(int epi) { return epi >= 1 ? 0 : 8 * 2 * 32 * 4; }   // per-warp [mult][bias] column terms
 constexpr int SMEM_LIMIT = 232448;             // 227 KB
 
 struct GemmKParams {
@@ -55,6 +55,13 @@ struct GemmKParams {
   int32_t b_c2_outer, b_c2_inner, b_col0, b_col_inner;
   int32_t o_c2_outer, o_c2_inner, o_col0, o_col_inner;
   int32_t act;            // 0 = none, 1 = exact-erf GELU (applied after scale / bias)
+  // EPI 2 ("gradient planes"): gq = acc * [gelu'(FQ(y))] * STEmask(y), planes = split(gq * col_scale[n]), column sums of gq
+  const float* ep_raw;    // y: raw output [M, N] of the Linear whose output fake-quant the gradient passes through
+  int64_t ep_raw_ld;
+  const float* ep_scale;
+  const int32_t* ep_zp;
+  int32_t ep_qmin, ep_qmax, ep_gelu;
+  float* ep_colsum;       // [ceil(M/32)][N] per-32-row-slab column sums of gq (bias-grad partials), may be NULL
 };
 
 template <int BN, int NA, int NB, int EPI = 0>
@@ -75,11 +82,14 @@ struct Cfg {
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-// EPI = 0: fp32 output;  EPI = 1: bf16 hi/lo plane output (the operand format of the next GEMM), optional GELU.
+// EPI = 0: fp32 output;  EPI = 1: bf16 hi/lo plane output (the operand format of the next GEMM), optional GELU;
+// EPI = 2: dgrad producing the NEXT layer's gradient planes: the accumulator (dL/d FQ(y) or dL/d GELU(FQ(y))) is multiplied by
+// gelu'(FQ(y)) -- a 256-entry table over the integer codes, built per CTA -- and the STE mask recomputed from the raw y tile,
+// folded with the per-channel weight scale and written as hi/lo planes; bias-grad column sums leave as per-slab partials.
 template <int BN, int NA, int NB, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const __grid_constant__ CUtensorMap map_o, const GemmKParams p) {
+               const __grid_constant__ CUtensorMap map_o, const __grid_constant__ CUtensorMap map_y, const GemmKParams p) {
   using C = Cfg<BN, NA, NB, EPI>;
   constexpr int EPI_WARP_BYTES = C::EPI_WARP_BYTES;
   constexpr int EPI_BYTES = C::EPI_BYTES;
@@ -93,9 +103,19 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* tmem_full = bars + 2 * C::STAGES;      // [2]
   uint64_t* tmem_empty = bars + 2 * C::STAGES + 2; // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+  uint64_t* raw_bar = bars + 2 * C::STAGES + 5;    // [8] EPI 2: one per epilogue warp (raw y tile landed)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+
+  __shared__ float gelu_lut[EPI == 2 ? 256 : 1];
+  if constexpr (EPI == 2) {
+    if (p.ep_gelu) {     // FQ(y) takes at most qmax - qmin + 1 <= 256 distinct values: gelu'(FQ(y)) by table lookup on the code
+      const QvQParams yq = qv_load_qparams(p.ep_scale, p.ep_zp, p.ep_qmin, p.ep_qmax);
+      for (int k = threadIdx.x; k <= p.ep_qmax - p.ep_qmin && k < 256; k += NUM_THREADS)
+        gelu_lut[k] = qv_gelu_grad(__fmul_rn(__fsub_rn(static_cast<float>(p.ep_qmin + k), yq.zp), yq.scale));
+    }
+  }
 
   if (threadIdx.x == 0) {
     prefetch_tensormap(&map_a);
@@ -108,6 +128,10 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
       mbar_init(&tmem_empty[b], 256);
+    }
+    if constexpr (EPI == 2) {
+      prefetch_tensormap(&map_y);
+      for (int w = 0; w < 8; ++w) mbar_init(&raw_bar[w], 1);
     }
     fence_barrier_init();
   }
@@ -218,6 +242,128 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int ew = warp - 2;
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
     const int par = ew >> 2;                     // chunk parity owned by this warp
+    if constexpr (EPI == 2) {
+      // ---- gradient-planes epilogue, in units of 32 columns (the two warps of a lane quarter take alternate units).
+      // The raw y tile of a unit (32 rows x 32 fp32) arrives by TMA in the warp's staging buffer -- coalesced, off the LSU
+      // path -- one unit ahead: as soon as the lanes have copied their row to registers the next unit's load is issued, for
+      // an item's first unit before its accumulator is even complete.  Planes leave through 64-byte-swizzled staging and TMA.
+      constexpr int NU = BN / 32;
+      uint8_t* my_raw = smem_epi + ew * EPI_WARP_BYTES;          // 4 KB: y tile in (128B-swizzled rows of 32 fp32)
+      uint8_t* my_out = my_raw + 4096;                            // 2 KB hi + 2 KB lo: 32 rows x 64 B, 64B swizzle
+      uint64_t* my_bar = &raw_bar[ew];
+      const QvQParams yq = qv_load_qparams(p.ep_scale, p.ep_zp, p.ep_qmin, p.ep_qmax);
+      const bool use_lut = p.ep_gelu != 0;
+      auto issue_raw = [&](int item, int u) {                     // lane 0 only
+        const int n_blk = item % p.tiles_n;
+        const int m_blk = (item / p.tiles_n) % p.tiles_m;
+        mbar_expect_tx(my_bar, 4096);
+        tma_load_3d(my_raw, &map_y, my_bar, n_blk * BN + u * 32, m_blk * BM + q * 32, 0);
+      };
+      uint32_t raw_phase = 0;
+      int local = 0;
+      if (static_cast<int>(blockIdx.x) < num_items && lane == 0) issue_raw(blockIdx.x, par);
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
+        const int n_blk = item % p.tiles_n;
+        const int m_blk = (item / p.tiles_n) % p.tiles_m;
+        const int buf = local & 1;
+        const uint32_t use = static_cast<uint32_t>(local >> 1);
+        const int row0 = m_blk * BM + q * 32;
+        const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN);
+        bool acc_ready = false;
+#pragma unroll 1
+        for (int u = par; u < NU; u += 2) {
+          // ---- this unit's y values: smem -> registers, then hand the buffer to the next unit's load ----
+          mbar_wait(my_bar, raw_phase);
+          raw_phase ^= 1;
+          float4 yv[8];
+          {
+            const uint32_t srow = smem_u32(my_raw) + lane * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t addr = srow + (static_cast<uint32_t>(j ^ (lane & 7)) << 4);
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(yv[j].x), "=f"(yv[j].y), "=f"(yv[j].z), "=f"(yv[j].w)
+                           : "r"(addr) : "memory");
+            }
+          }
+          __syncwarp();
+          const bool last = u + 2 >= NU;
+          if (lane == 0) {
+            if (!last) issue_raw(item, u + 2);
+            else if (item + static_cast<int>(gridDim.x) < num_items) issue_raw(item + gridDim.x, par);
+          }
+          if (!acc_ready) {
+            mbar_wait(&tmem_full[buf], use & 1);
+            tc_fence_after();
+            acc_ready = true;
+          }
+          uint32_t rr[32];
+          tmem_ld_cols<32>(t_base + u * 32, rr);
+          tmem_ld_wait();
+          if (last) {                                             // this warp's last TMEM read of the buffer
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[buf]);
+          }
+          const int64_t n0 = static_cast<int64_t>(n_blk) * BN + u * 32;
+          if (n0 >= p.N || static_cast<int64_t>(row0) >= p.M) continue;          // warp-uniform
+          if (lane == 0) tma_store_wait_read<0>();                // previous planes have left the staging buffer
+          __syncwarp();
+          float gq[32];
+          const uint32_t srow_hi = smem_u32(my_out) + lane * 64, srow_lo = srow_hi + 2048;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {                           // 8 columns per step
+            float4 sa = make_float4(1.f, 1.f, 1.f, 1.f), sb = sa;
+            if (p.col_scale) {
+              sa = __ldg(reinterpret_cast<const float4*>(p.col_scale + n0 + 8 * j));
+              sb = __ldg(reinterpret_cast<const float4*>(p.col_scale + n0 + 8 * j + 4));
+            }
+            const float4 ya = yv[2 * j], yb = yv[2 * j + 1];
+            const float yy[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+            const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+            float a[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float r = __fadd_rn(rintf(__fmul_rn(yy[e], yq.inv)), yq.zp);
+              const float c = fminf(fmaxf(r, yq.qmin), yq.qmax);
+              const bool in = (yq.qmin <= r) && (r <= yq.qmax);
+              float f = __uint_as_float(rr[8 * j + e]);
+              if (use_lut) f *= gelu_lut[static_cast<int>(c - yq.qmin)];
+              f = in ? f : 0.f;
+              gq[8 * j + e] = f;
+              a[e] = f * sc[e];
+            }
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float a0 = a[2 * e], a1 = a[2 * e + 1];
+              const __nv_bfloat162 h2 = __floats2bfloat162_rn(a0, a1);
+              const uint32_t hbits = *reinterpret_cast<const uint32_t*>(&h2);
+              const float r0 = a0 - __uint_as_float(hbits << 16), r1 = a1 - __uint_as_float(hbits & 0xffff0000u);
+              const __nv_bfloat162 l2 = __floats2bfloat162_rn(r0, r1);
+              hi[e] = hbits;
+              lo[e] = *reinterpret_cast<const uint32_t*>(&l2);
+            }
+            // 64B swizzle: 16-byte chunk j of row `lane` lives at chunk j ^ ((lane >> 1) & 3)
+            const uint32_t sw = (static_cast<uint32_t>(j ^ ((lane >> 1) & 3)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow_hi + sw), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]),
+                         "r"(hi[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow_lo + sw), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]),
+                         "r"(lo[3]) : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&map_o, my_out, static_cast<int>(n0), row0, 0, 0);
+            tma_store_4d(&map_o, my_out + 2048, static_cast<int>(n0), row0, 0, 1);
+            tma_store_commit();
+          }
+          if (p.ep_colsum) {
+            const float cs = qv_warp_colsum32(gq, lane);
+            p.ep_colsum[(static_cast<int64_t>(m_blk) * 4 + q) * p.N + n0 + lane] = cs;
+          }
+        }
+      }
+      if (lane == 0) tma_store_wait_read<0>();
+    } else {
     constexpr int CW = (EPI == 1) ? 64 : 32;     // columns per chunk (one 128-byte row of fp32 / of each bf16 plane)
     constexpr int NCHUNK = BN / CW;
     uint8_t* my_epi = smem_epi + ew * EPI_WARP_BYTES;
@@ -360,6 +506,7 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         atomicMax(p.minmax + 1, qv_f2ord(mx));
       }
     }
+    }   // EPI != 2
   }
 
   tc_fence_before();
@@ -414,8 +561,9 @@ int make_out_map(CUtensorMap* m, float* ptr, int64_t cols, int64_t rows, int64_t
 }
 
 // bf16 hi/lo plane output [2][nb][rows][ld] as a 4-D tensor (cols, rows, nb, plane); store box = (64 cols = 128 B, 32 rows).
+// box_cols = 32: 64-byte rows, 64B swizzle (the gradient-planes epilogue works in 32-column units).
 int make_out_planes_map(CUtensorMap* m, void* ptr, int64_t cols, int64_t rows, int64_t ld, int64_t nb, int64_t bstride,
-                        int64_t pstride) {
+                        int64_t pstride, int box_cols = 64) {
   EncodeTiledFn enc = get_encode();
   QV_REQUIRE(enc != nullptr, QV_ERR_CUDA, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
   QV_REQUIRE(ptr && qv_aligned16(ptr), QV_ERR_INVALID, "gemm plane output base must be a 16-byte aligned device pointer");
@@ -428,17 +576,18 @@ int make_out_planes_map(CUtensorMap* m, void* ptr, int64_t cols, int64_t rows, i
   cuuint64_t dims[4] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(nb), 2};
   cuuint64_t strides[3] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(bstride) * 2,
                            static_cast<cuuint64_t>(pstride) * 2};
-  cuuint32_t box[4] = {64, 32, 1, 1};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(box_cols), 32, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   QV_REQUIRE(r == CUDA_SUCCESS, QV_ERR_CUDA, "cuTensorMapEncodeTiled(plane output) failed (%d)", (int)r);
   return 0;
 }
 
 template <int BN, int NA, int NB, bool A_MN, bool B_MN, int EPI = 0>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const GemmKParams& kp, int grid,
-           cudaStream_t st) {
+           cudaStream_t st, const CUtensorMap* my = nullptr) {
   using C = Cfg<BN, NA, NB, EPI>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
@@ -447,7 +596,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, 
                                     C::SMEM_BYTES);
   });
   QV_REQUIRE(attr_err == cudaSuccess, QV_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
-  qv_gemm_kernel<BN, NA, NB, A_MN, B_MN, EPI><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mb, mo, kp);
+  qv_gemm_kernel<BN, NA, NB, A_MN, B_MN, EPI><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mb, mo, my ? *my : mo, kp);
   return qv_check_launch("qv_gemm_bf16");
 }
 
@@ -496,8 +645,24 @@ extern "C" int qv_gemm_bf16(const qv_gemm_args* a, void* stream) {
   if (planes_out && a->tile_n <= 0 && BN < 128) BN = 128;      // plane output is instantiated for 128 / 192 wide tiles
   QV_REQUIRE(BN == 64 || BN == 128 || BN == 192, QV_ERR_UNSUPPORTED, "tile_n must be 64, 128 or 192");
   QV_REQUIRE(a->out_kind == 0 || a->out_kind == 1, QV_ERR_INVALID, "out_kind must be 0 (fp32) or 1 (bf16 hi/lo planes)");
-  QV_REQUIRE(a->act == 0 || (a->act == 1 && planes_out), QV_ERR_UNSUPPORTED, "act = GELU needs out_kind = 1 (plane output)");
-  if (planes_out) {
+  QV_REQUIRE(a->act == 0 || ((a->act == 1 || a->act == 2) && planes_out), QV_ERR_UNSUPPORTED,
+             "act = GELU / gradient-planes epilogue needs out_kind = 1 (plane output)");
+  const bool grad_epi = a->act == 2;
+  if (grad_epi) {
+    QV_REQUIRE(splits == 1 && nbatch == 1 && a->a_planes == 2 && a->b_planes == 1 && !a->a.mn_major && !a->b.mn_major,
+               QV_ERR_UNSUPPORTED, "gradient-planes epilogue is instantiated for unsplit, unbatched K-major (2,1)-plane GEMMs");
+    QV_REQUIRE(a->N % 64 == 0, QV_ERR_UNSUPPORTED, "plane output needs N to be a multiple of 64");
+    QV_REQUIRE(a->ep_raw && a->ep_scale && a->ep_zp, QV_ERR_INVALID, "gradient-planes epilogue needs ep_raw, ep_scale and ep_zp");
+    QV_REQUIRE(qv_aligned16(a->ep_raw) && a->ep_raw_ld >= a->N && a->ep_raw_ld % 4 == 0, QV_ERR_INVALID,
+               "ep_raw must be 16-byte aligned with a row pitch >= N that is a multiple of 4 floats");
+    QV_REQUIRE(a->ep_qmax >= a->ep_qmin && a->ep_qmax - a->ep_qmin <= 255, QV_ERR_INVALID, "ep_qmin / ep_qmax span more than 256 codes");
+    QV_REQUIRE(!a->bias && !a->col_rscale && !a->alpha && !a->minmax, QV_ERR_UNSUPPORTED,
+               "gradient-planes epilogue takes col_scale only (no bias / alpha / observer)");
+    QV_REQUIRE(!a->col_scale || qv_aligned16(a->col_scale), QV_ERR_INVALID, "col_scale must be 16-byte aligned");
+    QV_REQUIRE(a->out.nb <= 1 && a->out.col0 == 0, QV_ERR_UNSUPPORTED, "gradient-planes epilogue writes a plain [2][M][N] plane stack");
+    if (a->tile_n <= 0 && BN < 128) BN = 128;
+    QV_REQUIRE(BN >= 128, QV_ERR_UNSUPPORTED, "gradient-planes epilogue needs tile_n 128 / 192");
+  } else if (planes_out) {
     QV_REQUIRE(splits == 1 && a->a_planes == 2 && !a->a.mn_major && !a->b.mn_major && BN >= 128, QV_ERR_UNSUPPORTED,
                "plane output is instantiated for unsplit K-major (2,1)- and (2,2)-plane GEMMs with tile_n 128/192");
     QV_REQUIRE(a->N % 64 == 0, QV_ERR_UNSUPPORTED, "plane output needs N to be a multiple of 64");
@@ -505,7 +670,7 @@ extern "C" int qv_gemm_bf16(const qv_gemm_args* a, void* stream) {
                "plane output takes a bias term only (no scale / alpha / observer)");
     QV_REQUIRE(!a->bias || qv_aligned16(a->bias), QV_ERR_INVALID, "plane output needs a 16-byte aligned bias");
   }
-  CUtensorMap ma, mb, mo;
+  CUtensorMap ma, mb, mo, my;
   int rc = make_map(&ma, a->a, a->a_planes, a->a.mn_major ? 64 : BM);
   if (rc) return rc;
   rc = make_map(&mb, a->b, a->b_planes, a->b.mn_major ? 64 : BN);
@@ -520,7 +685,12 @@ extern "C" int qv_gemm_bf16(const qv_gemm_args* a, void* stream) {
     // a tile edge that is not the tensor edge must fall on a 32-column store box
     QV_REQUIRE(a->N % 32 == 0 || (o.col_inner == 0 && o.col0 + a->N == o.cols), QV_ERR_UNSUPPORTED,
                "N must be a multiple of 32 unless the output tile ends at the tensor edge");
-    if (planes_out)
+    if (grad_epi) {
+      rc = make_out_planes_map(&mo, o.ptr, o.cols, o.rows, o.ld, o.nb, o.batch_stride, a->out_plane_stride, 32);
+      if (rc) return rc;
+      // the raw y tile comes in through the fp32 store-map geometry used as a load map: box = 32 cols x 32 rows, 128B swizzle
+      rc = make_out_map(&my, const_cast<float*>(a->ep_raw), a->N, a->M, a->ep_raw_ld, 1, 0);
+    } else if (planes_out)
       rc = make_out_planes_map(&mo, o.ptr, o.cols, o.rows, o.ld, o.nb, o.batch_stride, a->out_plane_stride);
     else
       rc = make_out_map(&mo, o.ptr, o.cols, o.rows, o.ld, o.nb, o.batch_stride);
@@ -551,12 +721,18 @@ extern "C" int qv_gemm_bf16(const qv_gemm_args* a, void* stream) {
   kp.b_c2_outer = a->b.c2_outer; kp.b_c2_inner = a->b.c2_inner; kp.b_col0 = a->b.col0; kp.b_col_inner = a->b.col_inner;
   kp.o_c2_outer = a->out.c2_outer; kp.o_c2_inner = a->out.c2_inner; kp.o_col0 = a->out.col0; kp.o_col_inner = a->out.col_inner;
   kp.act = a->act;
+  kp.ep_raw = a->ep_raw; kp.ep_raw_ld = a->ep_raw_ld; kp.ep_scale = a->ep_scale; kp.ep_zp = a->ep_zp;
+  kp.ep_qmin = a->ep_qmin; kp.ep_qmax = a->ep_qmax; kp.ep_gelu = a->ep_gelu; kp.ep_colsum = a->ep_colsum;
   const int64_t items = static_cast<int64_t>(kp.tiles_m) * kp.tiles_n * (nbatch > 1 ? nbatch : kp.splits);
   QV_REQUIRE(items < (1LL << 31), QV_ERR_UNSUPPORTED, "too many tiles");
   const int sms = qv_num_sms();
   const int grid = static_cast<int>(items < sms ? items : sms);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool amn = a->a.mn_major != 0, bmn = a->b.mn_major != 0;
+  if (grad_epi) {
+    if (BN == 128) return launch<128, 2, 1, false, false, 2>(ma, mb, mo, kp, grid, st, &my);
+    return launch<192, 2, 1, false, false, 2>(ma, mb, mo, kp, grid, st, &my);
+  }
   if (planes_out) {
     if (a->b_planes == 1) {
       if (BN == 128) return launch<128, 2, 1, false, false, 1>(ma, mb, mo, kp, grid, st);

@@ -75,6 +75,31 @@ __device__ __forceinline__ float qv_fq(float x, const QvQParams& q, bool* in_ran
   return __fmul_rn(cc, q.scale);
 }
 
+// exact-erf GELU (timm Mlp.act = nn.GELU()) and its derivative; shared so that every kernel evaluates the same expression
+__device__ __forceinline__ float qv_gelu_fwd(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float qv_gelu_grad(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+// Column sums across the 32 lanes of a warp for 32 columns at once (lane r holds row r's 32 values in v): a transposing
+// butterfly, 31 shuffles in total; returns the sum of column `lane` over all rows.  Fixed order -> deterministic.  Destroys v.
+__device__ __forceinline__ float qv_warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    const int off = 16 >> s, n = 16 >> s;
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const float send = up ? v[i] : v[i + n];
+      const float keep = up ? v[i + n] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
 // split an fp32 value into bf16 hi + bf16 lo (x ~= hi + lo, relative error <= 2^-17)
 __device__ __forceinline__ void qv_split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(x);

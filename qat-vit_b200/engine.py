@@ -274,7 +274,7 @@ class StudentEngine:
     """Forward + hand-written backward of the prepared (torch.ao eager-mode QAT) ``QATWrapper`` student."""
 
     def __init__(self, student: nn.Module, batch: int, hparams: Dict, grad_buffer: Optional[torch.Tensor] = None,
-                 fused_attention: Optional[bool] = None):
+                 fused_attention: Optional[bool] = None, fused_gp: bool = True):
         self.student = student
         vit = self.vit = student.model
         dev = next(student.parameters()).device
@@ -347,6 +347,11 @@ class StudentEngine:
         if fused_attention is None:
             fused_attention = all(int(ql["qkv"].afq.fake_quant_enabled.item()) != 0 for ql in self.lin)
         self.fused_attn = bool(fused_attention)
+        # The backward prologue of every block Linear (gradient x STE mask of its output fake-quant [x gelu'] x weight scale ->
+        # bf16 planes, bias-grad partial sums; qv_gp_planes) runs inside the kernel that PRODUCES the gradient: the fc2 dgrad
+        # GEMM epilogue (for fc1), the attention backward's output stage (for qkv) and the LayerNorm backward (for proj and the
+        # previous block's fc2).  fused_gp=False keeps the standalone kernel (parity reference for the fused forms).
+        self.fused_gp = bool(fused_gp)
 
         # ---- forward activations (saved for backward) ----
         self.img_codes = e(1, B * d.P, d.Kc, dt=bf)
@@ -394,17 +399,21 @@ class StudentEngine:
         self.gpF = e(2, M, F, dt=bf)
         self.gp3 = e(2, M, 3 * D, dt=bf)
         self.gpP = e(2, B * d.P, D, dt=bf)
-        self.g_big = e(M, F)
+        if not self.fused_gp:
+            self.g_big = e(M, F)
         self.g_h = e(M, D)
         self.g_op = e(2, M, D, dt=bf)
-        self.g_qkv = e(M, 3 * D)
+        if not (self.fused_gp and self.fused_attn):
+            self.g_qkv = e(M, 3 * D)
         if not self.fused_attn:
             self.g_o = e(M, D)
             self.dP = e(B * d.H * T, d.ldS)
             self.dSp = torch.zeros(2, B * d.H * T, d.ldP, dtype=bf, device=dev)
         self.rpb_gp = 64
         self.rpb_ln = 64
-        self.bias_part = e(-(-M // self.rpb_gp), max(F, 3 * D))
+        # bias-grad partial sums: standalone gp_planes [M/64][N]; GEMM epilogue [M/32][F]; attention backward [B*mt*4][3D]
+        self.slabs_attn = B * (-(-T // 128)) * 4
+        self.bias_part = e(max(-(-M // self.rpb_gp) * max(F, 3 * D), -(-M // 32) * F, self.slabs_attn * 3 * D))
         self.ln_part = e(-(-M // self.rpb_ln), 2, D)
         max_ws = 0
         self._splits = {}
@@ -539,9 +548,12 @@ class StudentEngine:
     def _dgrad(self, ql: _QLinear, gp: torch.Tensor, M: int, out: torch.Tensor) -> None:
         ops.gemm(Op.full(gp), Op.full(ql.codes_t), M, ql.K, ql.N, PAIRS_EXACT_B, out=out)
 
+    def _part(self, nblk: int, N: int) -> torch.Tensor:
+        return self.bias_part[:nblk * N].view(nblk, N)
+
     def _gp(self, g, y_raw, ql: _QLinear, gelu: bool, R: int, out_planes, remap=(0, 0)) -> None:
         nblk = -(-R // self.rpb_gp)
-        part = self.bias_part.view(-1)[:nblk * ql.N].view(nblk, ql.N)
+        part = self._part(nblk, ql.N)
         ops.gp_planes(g, y_raw, ql.afq.q, ql.wscale_vec, True, gelu, R, ql.N, out_planes, part, self.rpb_gp, remap[0], remap[1])
         ops.colsum_reduce(part, nblk, ql.N, self._grad(ql.bias))
 
@@ -567,28 +579,51 @@ class StudentEngine:
         for l in range(L - 1, -1, -1):
             blk, ql = v.blocks[l], self.lin[l]
             # ---- MLP ----
-            self._gp(gx, self.m_raw[l], ql["fc2"], False, M, self.gpD)
-            self._dgrad(ql["fc2"], self.gpD, M, self.g_big)
-            self._wgrad(ql["fc2"], self.gpD, self.gelp[l], M, PAIRS_FP32)
-            self._gp(self.g_big, self.f_raw[l], ql["fc1"], True, M, self.gpF)
+            if not (self.fused_gp and l < L - 1):     # else: emitted by the LayerNorm backward of block l + 1
+                self._gp(gx, self.m_raw[l], ql["fc2"], False, M, self.gpD)
+            if self.fused_gp:
+                # fc2 dgrad with fc1's backward prologue in its epilogue: gelu'(FQ(f_raw)) * STE mask * fc1 weight scale
+                nslab = -(-M // 32)
+                part = self._part(nslab, F)
+                ops.gemm(Op.full(self.gpD), Op.full(ql["fc2"].codes_t), M, F, D, PAIRS_EXACT_B, out_planes=self.gpF,
+                         col_scale=ql["fc1"].wscale_vec, grad_of=(self.f_raw[l], ql["fc1"].afq.q, True, part))
+                ops.colsum_reduce(part, nslab, F, self._grad(ql["fc1"].bias))
+                self._wgrad(ql["fc2"], self.gpD, self.gelp[l], M, PAIRS_FP32)
+            else:
+                self._dgrad(ql["fc2"], self.gpD, M, self.g_big)
+                self._wgrad(ql["fc2"], self.gpD, self.gelp[l], M, PAIRS_FP32)
+                self._gp(self.g_big, self.f_raw[l], ql["fc1"], True, M, self.gpF)
             self._dgrad(ql["fc1"], self.gpF, M, self.g_h)
+            # norm2 backward (+ residual grad) also emits proj's gradient planes
+            nblk_gp = -(-M // self.rpb_ln)
+            part = self._part(nblk_gp, D)
+            gp_proj = (self.a_raw[l], ql["proj"].afq.q, ql["proj"].wscale_vec, self.gpD, part) if self.fused_gp else None
             if self.ln_obs:
                 f2 = self.ln_fq[2 * l + 1]
                 self._wgrad(ql["fc1"], self.gpF, self.h2p[l], M, PAIRS_EXACT_B, alpha=f2.scale)
                 ops.ln_bwd(self.g_h, self.x_mid[l], self.stats2[l][0], self.stats2[l][1], blk.norm2.weight.detach(), gx, M, D, gx2,
-                           self.ln_part, self.rpb_ln, h_raw=self.h2_raw[l], h_fq=f2.q)
+                           self.ln_part, self.rpb_ln, h_raw=self.h2_raw[l], h_fq=f2.q, gp=gp_proj)
             else:
                 self._wgrad(ql["fc1"], self.gpF, self.h2p[l], M, PAIRS_FP32)
                 ops.ln_bwd(self.g_h, self.x_mid[l], self.stats2[l][0], self.stats2[l][1], blk.norm2.weight.detach(), gx, M, D, gx2,
-                           self.ln_part, self.rpb_ln)
+                           self.ln_part, self.rpb_ln, gp=gp_proj)
             self._ln_param_grads(blk.norm2, nblk_ln)
             # ---- attention ----
-            self._gp(gx2, self.a_raw[l], ql["proj"], False, M, self.gpD)
+            if self.fused_gp:
+                ops.colsum_reduce(part, nblk_gp, D, self._grad(ql["proj"].bias))
+            else:
+                self._gp(gx2, self.a_raw[l], ql["proj"], False, M, self.gpD)
             if self.fused_attn:
                 # proj dgrad emits dL/dO directly as bf16 hi/lo planes; one fused kernel recomputes P and writes dQ | dK | dV
                 ops.gemm(Op.full(self.gpD), Op.full(ql["proj"].codes_t), M, D, D, PAIRS_EXACT_B, out_planes=self.g_op)
                 self._wgrad(ql["proj"], self.gpD, self.op[l], M, PAIRS_FP32)
-                ops.attn_bwd(self.qkvc[l], ql["qkv"].afq.scale, self.g_op, self.lse[l], B, T, H, d.attn_scale, self.g_qkv)
+                if self.fused_gp:   # ... with qkv's backward prologue applied on the way out
+                    part = self._part(self.slabs_attn, 3 * D)
+                    ops.attn_bwd_gp(self.qkvc[l], ql["qkv"].afq.scale, self.g_op, self.lse[l], B, T, H, d.attn_scale,
+                                    self.qkv_raw[l], ql["qkv"].afq.q, ql["qkv"].wscale_vec, self.gp3, part)
+                    ops.colsum_reduce(part, self.slabs_attn, 3 * D, self._grad(ql["qkv"].bias))
+                else:
+                    ops.attn_bwd(self.qkvc[l], ql["qkv"].afq.scale, self.g_op, self.lse[l], B, T, H, d.attn_scale, self.g_qkv)
             else:
                 self._dgrad(ql["proj"], self.gpD, M, self.g_o)
                 self._wgrad(ql["proj"], self.gpD, self.op[l], M, PAIRS_FP32)
@@ -605,18 +640,27 @@ class StudentEngine:
                          PAIRS_FP32, out=Out.tokens(self.g_qkv, B, T, D, 64), nbatch=BH, batch_inner=H)
                 ops.gemm(Op.per_head(Pp, BH, H, T, T, mn_major=True), Op.tokens(self.g_op, B, T, 0, 64, mn_major=True), T, 64, T,
                          PAIRS_FP32, out=Out.tokens(self.g_qkv, B, T, 2 * D, 64), nbatch=BH, batch_inner=H)
-            self._gp(self.g_qkv, self.qkv_raw[l], ql["qkv"], False, M, self.gp3)
+            if not (self.fused_gp and self.fused_attn):
+                self._gp(self.g_qkv, self.qkv_raw[l], ql["qkv"], False, M, self.gp3)
             self._dgrad(ql["qkv"], self.gp3, M, self.g_h)
+            # norm1 backward also emits the gradient planes of the PREVIOUS block's fc2 (its output joined this residual stream)
+            gp_fc2 = None
+            if self.fused_gp and l > 0:
+                pf = self.lin[l - 1]["fc2"]
+                part = self._part(nblk_gp, D)
+                gp_fc2 = (self.m_raw[l - 1], pf.afq.q, pf.wscale_vec, self.gpD, part)
             if self.ln_obs:
                 f1 = self.ln_fq[2 * l]
                 self._wgrad(ql["qkv"], self.gp3, self.h1p[l], M, PAIRS_EXACT_B, alpha=f1.scale)
                 ops.ln_bwd(self.g_h, self.x_in[l], self.stats1[l][0], self.stats1[l][1], blk.norm1.weight.detach(), gx2, M, D, gx,
-                           self.ln_part, self.rpb_ln, h_raw=self.h1_raw[l], h_fq=f1.q)
+                           self.ln_part, self.rpb_ln, h_raw=self.h1_raw[l], h_fq=f1.q, gp=gp_fc2)
             else:
                 self._wgrad(ql["qkv"], self.gp3, self.h1p[l], M, PAIRS_FP32)
                 ops.ln_bwd(self.g_h, self.x_in[l], self.stats1[l][0], self.stats1[l][1], blk.norm1.weight.detach(), gx2, M, D, gx,
-                           self.ln_part, self.rpb_ln)
+                           self.ln_part, self.rpb_ln, gp=gp_fc2)
             self._ln_param_grads(blk.norm1, nblk_ln)
+            if gp_fc2 is not None:
+                ops.colsum_reduce(part, nblk_gp, D, self._grad(self.lin[l - 1]["fc2"].bias))
             if grads_final_from is not None:
                 grads_final_from(self._block_lo[l])
         # ---- embeddings: pos_embed, cls_token, patch-embed conv ----
@@ -633,8 +677,9 @@ class QATDistillStep:
     forward, loss and backward on the current stream and leaves gradients in ``student`` parameters' ``.grad``."""
 
     def __init__(self, student: nn.Module, teacher: nn.Module, batch: int, hparams: Dict,
-                 grad_buffer: Optional[torch.Tensor] = None, fused_attention: Optional[bool] = None):
-        self.student_engine = StudentEngine(student, batch, hparams, grad_buffer=grad_buffer, fused_attention=fused_attention)
+                 grad_buffer: Optional[torch.Tensor] = None, fused_attention: Optional[bool] = None, fused_gp: bool = True):
+        self.student_engine = StudentEngine(student, batch, hparams, grad_buffer=grad_buffer, fused_attention=fused_attention,
+                                            fused_gp=fused_gp)
         self.teacher_engine = TeacherEngine(teacher, batch)
         self.grad_arena = self.student_engine.grad_arena
 

@@ -202,10 +202,13 @@ PAIRS_FP32 = (2, 2)          # both fp32 as hi/lo: A0*B0 + A0*B1 + A1*B0 (lo*lo 
 
 def gemm(a: Op, b: Op, M: int, N: int, K: int, planes: Tuple[int, int], *, out=None, col_scale=None, col_rscale=None,
          alpha=None, bias=None, minmax=None, splits: int = 1, workspace: Optional[torch.Tensor] = None, nbatch: int = 1,
-         batch_inner: int = 1, tile_n: int = 0, out_planes: Optional[torch.Tensor] = None, gelu: bool = False):
+         batch_inner: int = 1, tile_n: int = 0, out_planes: Optional[torch.Tensor] = None, gelu: bool = False,
+         grad_of=None):
     """D[M,N] = sum_pairs A[pa] @ B[pb]^T on tcgen05 (include/qatvit_b200.h: qv_gemm_bf16).
     out: an ``Out`` descriptor, a 2-D fp32 tensor, or None (allocated).
-    out_planes: bf16 [2, M, N] -- write [GELU](D) as hi/lo planes straight from the epilogue instead of fp32."""
+    out_planes: bf16 [2, M, N] -- write [GELU](D) as hi/lo planes straight from the epilogue instead of fp32.
+    grad_of = (y_raw [M,N], (scale, zp, qmin, qmax), gelu: bool, colsum [ceil(M/32), N] | None): with out_planes, the
+    gradient-planes epilogue (act = 2): D * [gelu'(FQ(y))] * STEmask(y) * col_scale -> planes, bias-grad slab sums."""
     args = GemmArgs()
     a.fill(args.a)
     b.fill(args.b)
@@ -218,6 +221,18 @@ def gemm(a: Op, b: Op, M: int, N: int, K: int, planes: Tuple[int, int], *, out=N
         o = args.out
         o.ptr, o.ld, o.rows, o.cols, o.nb, o.batch_stride = out_planes.data_ptr(), out_planes.stride(1), M, N, 1, 0
         args.out_kind, args.act, args.out_plane_stride = 1, int(bool(gelu)), out_planes.stride(0)
+        if grad_of is not None:
+            y_raw, fq, g_gelu, colsum = grad_of
+            if y_raw.dtype != torch.float32 or not y_raw.is_cuda or y_raw.dim() != 2 or y_raw.stride(1) != 1:
+                raise RuntimeError("qatvit_b200: grad_of[0] must be a CUDA fp32 [M, N] tensor (no CPU fallback)")
+            args.act = 2
+            args.ep_raw, args.ep_raw_ld = y_raw.data_ptr(), y_raw.stride(0)
+            args.ep_scale, args.ep_zp = _p(fq[0], torch.float32, "scale"), _p(fq[1], torch.int32, "zero_point")
+            args.ep_qmin, args.ep_qmax, args.ep_gelu = int(fq[2]), int(fq[3]), int(bool(g_gelu))
+            if colsum is not None:
+                if colsum.dtype != torch.float32 or colsum.numel() < -(-M // 32) * N or not colsum.is_contiguous():
+                    raise RuntimeError("qatvit_b200: colsum must be a contiguous fp32 buffer of at least ceil(M/32) * N elements")
+                args.ep_colsum = colsum.data_ptr()
         ret = out_planes
     elif splits <= 1:
         if out is None:
@@ -264,9 +279,25 @@ def resid_ln_fwd(x_in, y_raw, fq, gamma, beta, eps, R, D, *, in_row_stride=1, x_
                                      _p(minmax, torch.int32), _stream()), "resid_ln_fwd")
 
 
-def ln_bwd(g_h, x, mean, rstd, gamma, g_res, R, D, g_x, partials, rows_per_block, out_row_stride=1, h_raw=None, h_fq=None):
-    """h_raw + h_fq = (scale, zero_point, qmin, qmax): g_h first passes the STE mask of an observed LayerNorm's fake-quant."""
+def ln_bwd(g_h, x, mean, rstd, gamma, g_res, R, D, g_x, partials, rows_per_block, out_row_stride=1, h_raw=None, h_fq=None,
+           gp=None):
+    """h_raw + h_fq = (scale, zero_point, qmin, qmax): g_h first passes the STE mask of an observed LayerNorm's fake-quant.
+    gp = (y_raw [R, D], (scale, zp, qmin, qmax), w_scale [D], out_planes bf16 [2, R, D], bias_partials | None): also emit the
+    gradient planes g_x * STEmask(y_raw) * w_scale of the Linear whose output y_raw fed this residual stream (qv_ln_bwd_gp)."""
     sc, zp, qmin, qmax = h_fq if (h_raw is not None and h_fq is not None) else (None, None, 0, 0)
+    if gp is not None:
+        if out_row_stride != 1:
+            raise RuntimeError("qatvit_b200: ln_bwd with fused gradient planes needs out_row_stride == 1")
+        y_raw, fq, w_scale, out_planes, bias_part = gp
+        check(_lib.lib().qv_ln_bwd_gp(_p(g_h, torch.float32), _p(x, torch.float32), _p(mean, torch.float32),
+                                      _p(rstd, torch.float32), _p(gamma, torch.float32), _p(g_res, torch.float32), R, D,
+                                      _p(g_x, torch.float32), _p(partials, torch.float32), rows_per_block,
+                                      _p(h_raw if sc is not None else None, torch.float32), _p(sc, torch.float32),
+                                      _p(zp, torch.int32), qmin, qmax, _p(y_raw, torch.float32, "gp y_raw"),
+                                      _p(fq[0], torch.float32), _p(fq[1], torch.int32), int(fq[2]), int(fq[3]),
+                                      _p(w_scale, torch.float32), _p(out_planes, torch.bfloat16, "gp out_planes"),
+                                      out_planes.stride(0), _p(bias_part, torch.float32), _stream()), "ln_bwd_gp")
+        return
     check(_lib.lib().qv_ln_bwd(_p(g_h, torch.float32), _p(x, torch.float32), _p(mean, torch.float32),
                                _p(rstd, torch.float32), _p(gamma, torch.float32), _p(g_res, torch.float32), R, D,
                                out_row_stride, _p(g_x, torch.float32), _p(partials, torch.float32), rows_per_block,
@@ -352,6 +383,23 @@ def attn_bwd(qkv_codes, qscale, do_planes, lse, B, T, H, scale, g_qkv):
     return g_qkv
 
 
+def attn_bwd_gp(qkv_codes, qscale, do_planes, lse, B, T, H, scale, y_raw, fq, w_scale, gp_planes, colsum):
+    """attn_bwd with the qkv Linear's gradient prologue fused: gp_planes bf16 [2, B*T, 3*H*64] <- (dQ|dK|dV) * STEmask(y_raw) *
+    w_scale; colsum fp32 [B * ceil(T/128) * 4, 3*H*64] <- per-slab bias-grad partials (include/qatvit_b200.h: qv_attn_bwd_gp)."""
+    if qkv_codes.dim() != 3 or qkv_codes.shape[0] != 1 or do_planes.dim() != 3 or do_planes.shape[0] != 2:
+        raise RuntimeError("qatvit_b200: attn_bwd takes a [1, tokens, 3D] code plane and [2, tokens, D] gradient planes")
+    nslab = B * (-(-T // 128)) * 4
+    if colsum.numel() < nslab * 3 * H * 64 or gp_planes.dim() != 3 or gp_planes.stride(1) != 3 * H * 64:
+        raise RuntimeError("qatvit_b200: attn_bwd_gp needs dense [2, B*T, 3D] planes and a [B*ceil(T/128)*4, 3D] colsum buffer")
+    check(_lib.lib().qv_attn_bwd_gp(_p(qkv_codes, torch.bfloat16, "qkv_codes"), qkv_codes.stride(1), _p(qscale, torch.float32),
+                                    _p(do_planes, torch.bfloat16, "do_planes"), do_planes.stride(0), do_planes.stride(1),
+                                    _p(lse, torch.float32, "lse"), B, T, H, float(scale), _p(y_raw, torch.float32, "y_raw"),
+                                    _p(fq[0], torch.float32), _p(fq[1], torch.int32), int(fq[2]), int(fq[3]),
+                                    _p(w_scale, torch.float32), _p(gp_planes, torch.bfloat16, "gp_planes"), gp_planes.stride(0),
+                                    _p(colsum, torch.float32), _stream()), "attn_bwd_gp")
+    return nslab
+
+
 def int8_linear(qx, sx, zx, qw, sw, wsum, bias, sy, zy, qy=None, y=None, engine="x86"):
     """quantized::linear on the integer tensor cores (include/qatvit_b200.h: qv_int8_linear).  qx uint8 [M,K], qw int8 [N,K]."""
     M, K = qx.shape
@@ -416,6 +464,8 @@ def _gemm_tag(args, kw):
         kind = "wgrad"
     elif tuple(planes) == (2, 2):
         kind = "teacher linear"
+    elif kw.get("grad_of") is not None:
+        kind = "student dgrad+gp"
     elif tuple(planes) == (2, 1):
         kind = "student fwd/dgrad"
     else:
@@ -445,7 +495,7 @@ def _bytes_resid_ln(a, k):
 
 def _bytes_ln_bwd(a, k):
     R, D = a[6], a[7]
-    return "ln_bwd", (16.0 if a[5] is not None else 12.0) * R * D
+    return "ln_bwd", ((16.0 if a[5] is not None else 12.0) + (8.0 if k.get("gp") is not None else 0.0)) * R * D
 
 
 def _wrap(name, fn, tag_fn=None):
@@ -466,7 +516,7 @@ def _wrap(name, fn, tag_fn=None):
 
 for _nm in ("minmax_reset", "minmax_accumulate", "obs_update", "fq_apply", "fq_weight", "fq_bwd", "split_planes",
            "kd_ce_loss", "splitk_reduce", "colsum_reduce", "colsum_rows",
-           "embed_fwd", "im2col_fq", "softmax_planes", "attn_ds", "head_fwd", "head_bwd", "attn_fwd", "attn_bwd",
+           "embed_fwd", "im2col_fq", "softmax_planes", "attn_ds", "head_fwd", "head_bwd", "attn_fwd", "attn_bwd", "attn_bwd_gp",
            "int8_linear", "quantize_u8", "qparams_from_minmax", "im2col_u8", "gelu_minmax"):
     globals()[_nm] = _wrap(_nm, globals()[_nm])
 gemm = _wrap("gemm", gemm, _gemm_tag)

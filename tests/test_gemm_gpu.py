@@ -123,3 +123,44 @@ def test_gemm_batched_per_head(cuda_dev, B, H, T):
     k = qkv[:, D:2 * D].view(B, T, H, 64).permute(0, 2, 1, 3).double()
     ref = (q @ k.transpose(-1, -2)).reshape(B * H * T, T)
     assert _rel(S[:, :T], ref) < 1e-4
+
+
+@pytest.mark.parametrize("M,N,K,gelu", [(197 * 8, 1536, 384, True), (197 * 8, 384, 384, False), (197 * 8 + 5, 1152, 384, False),
+                                        (130, 128, 72, True), (33, 192, 64, True), (197 * 32, 1536, 384, True)])
+@pytest.mark.parametrize("qrange", [(0, 127), (0, 255)])
+def test_gemm_gradient_planes_epilogue(cuda_dev, M, N, K, gelu, qrange):
+    """act = 2: the dgrad GEMM applies gelu'(FQ(y)) * STE mask * w_scale in its epilogue and emits hi/lo planes plus bias-grad
+    slab sums.  Must equal the unfused chain (fp32 GEMM -> qv_gp_planes -> qv_colsum_reduce) bit for bit on the planes (same
+    accumulator, same expression) and to fp32 summation-order noise on the column sums."""
+    from qatvit_b200 import ops
+    from qatvit_b200.ops import Op, PAIRS_EXACT_B
+    g = torch.Generator().manual_seed(M + N + K + qrange[1])
+    dev = cuda_dev
+    a = torch.randn(M, K, generator=g).to(dev)
+    b = _codes((N, K), dev, g)
+    ap, bp = _planes(a), b.bfloat16()[None].contiguous()
+    y = (torch.randn(M, N, generator=g) * 2.0).to(dev)
+    scale = torch.tensor([4.0 / (qrange[1] - qrange[0])], device=dev)       # clips ~5 % of y on either side
+    zp = torch.tensor([(qrange[0] + qrange[1]) // 2], dtype=torch.int32, device=dev)
+    fq = (scale, zp, qrange[0], qrange[1])
+    wsc = (torch.rand(N, generator=g) * 0.02 + 0.001).to(dev)
+    # unfused
+    gmat = ops.gemm(Op.full(ap), Op.full(bp), M, N, K, PAIRS_EXACT_B)
+    rpb = 64
+    nblk = -(-M // rpb)
+    part = torch.empty(nblk, N, device=dev)
+    ref_planes = torch.empty(2, M, N, dtype=torch.bfloat16, device=dev)
+    ops.gp_planes(gmat, y, fq, wsc, True, gelu, M, N, ref_planes, part, rpb)
+    ref_bias = torch.empty(N, device=dev)
+    ops.colsum_reduce(part, nblk, N, ref_bias)
+    # fused
+    out_planes = torch.full((2, M, N), float("nan"), dtype=torch.bfloat16, device=dev)
+    nslab = -(-M // 32)
+    slab = torch.full((nslab, N), float("nan"), device=dev)
+    ops.gemm(Op.full(ap), Op.full(bp), M, N, K, PAIRS_EXACT_B, out_planes=out_planes, col_scale=wsc, grad_of=(y, fq, gelu, slab))
+    bias = torch.empty(N, device=dev)
+    ops.colsum_reduce(slab, nslab, N, bias)
+    torch.cuda.synchronize()
+    assert torch.equal(out_planes.view(torch.int16), ref_planes.view(torch.int16))
+    assert (ref_planes.float().abs().sum(0) == 0).float().mean() > 0.02      # the STE mask really zeroed something
+    assert _rel(bias, ref_bias) < 1e-5
