@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(256) resid_ln_fwd_kernel(const float* __restri
 //   g_x[r*out_row_stride] = (g_res ? g_res[r] : 0) + rstd * (gy - mean(gy) - xhat * mean(gy * xhat)),  gy = g_h * gamma
 // ------------------------------------------------------------------------------------------------
 template <int VPL>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ g_h, const float* __restrict__ x,
+__global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const float* __restrict__ g_h, const float* __restrict__ x,
                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                                      const float* __restrict__ gamma, const float* __restrict__ g_res,
                                                      int64_t R, int64_t out_row_stride, float* __restrict__ g_x,
@@ -144,38 +144,42 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ g
   // fused gradient planes of the Linear whose (fake-quantised) output y was added into this residual stream:
   // gp = g_x * STEmask(y) * w_scale -> hi/lo planes, per-block column sums of g_x * mask (its bias grad)
   const OptQ gq_ = load_optq(gp_y ? gp_scale : nullptr, gp_zp, gp_qmin, gp_qmax);
-  float4 dg[VPL], db[VPL], dbias[VPL], wsv[VPL];
+  float4 dg[VPL], db[VPL], dbias[VPL];
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    dg[i] = db[i] = dbias[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    wsv[i] = gq_.on ? __ldg(reinterpret_cast<const float4*>(gp_wscale + (i * 32 + lane) * 4)) : make_float4(1.f, 1.f, 1.f, 1.f);
-  }
-  float4 gm[VPL];
-#pragma unroll
-  for (int i = 0; i < VPL; ++i) gm[i] = __ldg(reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 4));
+  for (int i = 0; i < VPL; ++i) dg[i] = db[i] = dbias[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   const int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_block;
   for (int rr = warp; rr < rows_per_block; rr += nwarps) {
     const int64_t r = r0 + rr;
     if (r >= R) break;
-    const float mu = __ldg(mean + r), rs = __ldg(rstd + r);
-    float4 gh[VPL], xh[VPL];
-    float s1 = 0.f, s2 = 0.f;
+    // every global read of the row is issued before the first use (gamma / w_scale are L1-resident re-reads, which keeps
+    // them out of the persistent register state): 4-5 independent 16-byte loads per lane and vector in flight
+    float4 gh[VPL], xh[VPL], gr[VPL], yv[VPL], hv[VPL];
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int c = (i * 32 + lane) * 4;
       gh[i] = __ldg(reinterpret_cast<const float4*>(g_h + r * D + c));
+      xh[i] = __ldg(reinterpret_cast<const float4*>(x + r * D + c));
+      if (g_res) gr[i] = __ldg(reinterpret_cast<const float4*>(g_res + r * D + c));
+      if (gq_.on) yv[i] = __ldg(reinterpret_cast<const float4*>(gp_y + r * D + c));
+      if (hq.on) hv[i] = __ldg(reinterpret_cast<const float4*>(h_raw + r * D + c));
+    }
+    const float mu = __ldg(mean + r), rs = __ldg(rstd + r);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * 4;
       if (hq.on) {
-        const float4 hv = __ldg(reinterpret_cast<const float4*>(h_raw + r * D + c));
         bool in0, in1, in2, in3;
-        qv_fq(hv.x, hq.q, &in0, nullptr); qv_fq(hv.y, hq.q, &in1, nullptr);
-        qv_fq(hv.z, hq.q, &in2, nullptr); qv_fq(hv.w, hq.q, &in3, nullptr);
+        qv_fq(hv[i].x, hq.q, &in0, nullptr); qv_fq(hv[i].y, hq.q, &in1, nullptr);
+        qv_fq(hv[i].z, hq.q, &in2, nullptr); qv_fq(hv[i].w, hq.q, &in3, nullptr);
         gh[i].x = in0 ? gh[i].x : 0.f; gh[i].y = in1 ? gh[i].y : 0.f; gh[i].z = in2 ? gh[i].z : 0.f; gh[i].w = in3 ? gh[i].w : 0.f;
       }
-      const float4 xv = __ldg(reinterpret_cast<const float4*>(x + r * D + c));
+      const float4 xv = xh[i];
       xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
       dg[i].x += gh[i].x * xh[i].x; dg[i].y += gh[i].y * xh[i].y; dg[i].z += gh[i].z * xh[i].z; dg[i].w += gh[i].w * xh[i].w;
       db[i].x += gh[i].x; db[i].y += gh[i].y; db[i].z += gh[i].z; db[i].w += gh[i].w;
-      gh[i].x *= gm[i].x; gh[i].y *= gm[i].y; gh[i].z *= gm[i].z; gh[i].w *= gm[i].w;
+      const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      gh[i].x *= gm.x; gh[i].y *= gm.y; gh[i].z *= gm.z; gh[i].w *= gm.w;
       s1 += (gh[i].x + gh[i].y) + (gh[i].z + gh[i].w);
       s2 += (gh[i].x * xh[i].x + gh[i].y * xh[i].y) + (gh[i].z * xh[i].z + gh[i].w * xh[i].w);
     }
@@ -186,19 +190,16 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ g
       const int c = (i * 32 + lane) * 4;
       float4 o = make_float4(rs * (gh[i].x - s1 - xh[i].x * s2), rs * (gh[i].y - s1 - xh[i].y * s2),
                              rs * (gh[i].z - s1 - xh[i].z * s2), rs * (gh[i].w - s1 - xh[i].w * s2));
-      if (g_res) {
-        const float4 gr = __ldg(reinterpret_cast<const float4*>(g_res + r * D + c));
-        o.x += gr.x; o.y += gr.y; o.z += gr.z; o.w += gr.w;
-      }
+      if (g_res) { o.x += gr[i].x; o.y += gr[i].y; o.z += gr[i].z; o.w += gr[i].w; }
       *reinterpret_cast<float4*>(g_x + r * out_row_stride * D + c) = o;
       if (gq_.on) {
-        const float4 yv = __ldg(reinterpret_cast<const float4*>(gp_y + r * D + c));
         bool in0, in1, in2, in3;
-        qv_fq(yv.x, gq_.q, &in0, nullptr); qv_fq(yv.y, gq_.q, &in1, nullptr);
-        qv_fq(yv.z, gq_.q, &in2, nullptr); qv_fq(yv.w, gq_.q, &in3, nullptr);
+        qv_fq(yv[i].x, gq_.q, &in0, nullptr); qv_fq(yv[i].y, gq_.q, &in1, nullptr);
+        qv_fq(yv[i].z, gq_.q, &in2, nullptr); qv_fq(yv[i].w, gq_.q, &in3, nullptr);
         o.x = in0 ? o.x : 0.f; o.y = in1 ? o.y : 0.f; o.z = in2 ? o.z : 0.f; o.w = in3 ? o.w : 0.f;
         dbias[i].x += o.x; dbias[i].y += o.y; dbias[i].z += o.z; dbias[i].w += o.w;
-        store_planes4(gp_out, gp_out + gp_plane_stride, r * D + c, o.x * wsv[i].x, o.y * wsv[i].y, o.z * wsv[i].z, o.w * wsv[i].w);
+        const float4 ws = __ldg(reinterpret_cast<const float4*>(gp_wscale + c));
+        store_planes4(gp_out, gp_out + gp_plane_stride, r * D + c, o.x * ws.x, o.y * ws.y, o.z * ws.z, o.w * ws.w);
       }
     }
   }
@@ -352,10 +353,31 @@ __global__ void __launch_bounds__(256) act_planes_kernel(const float* __restrict
   const OptQ oq = load_optq(y_scale, y_zp, qmin, qmax);
   const int64_t n4 = n >> 2;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4; i += stride) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(y_raw) + i);
+  // GELU(FQ(y)) takes at most qmax - qmin + 1 <= 256 distinct values: a per-block table of packed (hi | lo << 16) bf16 pairs
+  // indexed by the clamped code replaces erff on every element (same expression evaluated once per code -> same bits).
+  __shared__ uint32_t lut[256];
+  const bool use_lut = gelu && oq.on && !codes_only && (qmax - qmin) < 256;
+  if (use_lut) {
+    for (int k = threadIdx.x; k <= qmax - qmin; k += blockDim.x) {
+      const float v = gelu_fwd(__fmul_rn(__fsub_rn(static_cast<float>(qmin + k), oq.q.zp), oq.q.scale));
+      __nv_bfloat16 h, l;
+      qv_split_bf16(v, h, l);
+      lut[k] = static_cast<uint32_t>(__bfloat16_as_ushort(h)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l)) << 16);
+    }
+    __syncthreads();
+  }
+  auto emit = [&](int64_t i, const float4& v) {
     float a[4] = {v.x, v.y, v.z, v.w};
-    if (codes_only) {
+    if (use_lut) {
+      uint32_t e[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float r = __fadd_rn(rintf(__fmul_rn(a[j], oq.q.inv)), oq.q.zp);
+        e[j] = lut[static_cast<int>(fminf(fmaxf(r, oq.q.qmin), oq.q.qmax) - oq.q.qmin)];
+      }
+      *reinterpret_cast<uint2*>(out + i * 4) = make_uint2(__byte_perm(e[0], e[1], 0x5410), __byte_perm(e[2], e[3], 0x5410));
+      *reinterpret_cast<uint2*>(out + plane_stride + i * 4) = make_uint2(__byte_perm(e[0], e[1], 0x7632), __byte_perm(e[2], e[3], 0x7632));
+    } else if (codes_only) {
       __nv_bfloat16 c[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -364,15 +386,24 @@ __global__ void __launch_bounds__(256) act_planes_kernel(const float* __restrict
         c[j] = __float2bfloat16_rn(cc);
       }
       *reinterpret_cast<uint2*>(out + i * 4) = *reinterpret_cast<uint2*>(c);
-      continue;
-    }
+    } else {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (oq.on) a[j] = qv_fq(a[j], oq.q, nullptr, nullptr);
-      if (gelu) a[j] = gelu_fwd(a[j]);
+      for (int j = 0; j < 4; ++j) {
+        if (oq.on) a[j] = qv_fq(a[j], oq.q, nullptr, nullptr);
+        if (gelu) a[j] = gelu_fwd(a[j]);
+      }
+      store_planes4(out, out + plane_stride, i * 4, a[0], a[1], a[2], a[3]);
     }
-    store_planes4(out, out + plane_stride, i * 4, a[0], a[1], a[2], a[3]);
+  };
+  int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  for (; i + 3 * stride < n4; i += 4 * stride) {                 // four independent 16-byte loads in flight per thread
+    const float4 v0 = __ldg(reinterpret_cast<const float4*>(y_raw) + i);
+    const float4 v1 = __ldg(reinterpret_cast<const float4*>(y_raw) + i + stride);
+    const float4 v2 = __ldg(reinterpret_cast<const float4*>(y_raw) + i + 2 * stride);
+    const float4 v3 = __ldg(reinterpret_cast<const float4*>(y_raw) + i + 3 * stride);
+    emit(i, v0); emit(i + stride, v1); emit(i + 2 * stride, v2); emit(i + 3 * stride, v3);
   }
+  for (; i < n4; i += stride) emit(i, __ldg(reinterpret_cast<const float4*>(y_raw) + i));
 }
 
 // ------------------------------------------------------------------------------------------------

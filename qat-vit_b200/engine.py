@@ -409,8 +409,9 @@ class StudentEngine:
             self.g_o = e(M, D)
             self.dP = e(B * d.H * T, d.ldS)
             self.dSp = torch.zeros(2, B * d.H * T, d.ldP, dtype=bf, device=dev)
+        import os
         self.rpb_gp = 64
-        self.rpb_ln = 64
+        self.rpb_ln = int(os.environ.get("QV_RPB_LN", "64"))
         # bias-grad partial sums: standalone gp_planes [M/64][N]; GEMM epilogue [M/32][F]; attention backward [B*mt*4][3D]
         self.slabs_attn = B * (-(-T // 128)) * 4
         self.bias_part = e(max(-(-M // self.rpb_gp) * max(F, 3 * D), -(-M // 32) * F, self.slabs_attn * 3 * D))
