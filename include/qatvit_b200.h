@@ -218,19 +218,22 @@ int qv_attn_fwd(const uint16_t* qkv_planes, int32_t n_planes, int64_t plane_stri
                 int64_t out_plane_stride, int64_t out_ld, float* out_f32, float* lse, void* stream);
 /* Fused attention backward for integer-code operands (the QAT student; autograd of F.scaled_dot_product_attention):
  * recomputes P from the codes and the forward's lse on the tensor cores and writes dQ | dK | dV (gradients w.r.t. the
- * fake-quantised q, k, v = s * codes) into g_qkv fp32 [B*T][3*H*64].  qkv_codes: ONE bf16 plane [B*T][ld]; do_planes: bf16
- * hi/lo planes [2][B*T][do_ld] of dL/dO; lse: fp32 [B*H*T] (qv_attn_fwd); qscale: device scalar s (NULL = 1).  T <= 224. */
-int qv_attn_bwd(const uint16_t* qkv_codes, int64_t ld, const float* qscale, const uint16_t* do_planes, int64_t do_plane_stride,
-                int64_t do_ld, const float* lse, int32_t B, int32_t T, int32_t H, float scale, float* g_qkv, void* stream);
+ * fake-quantised q, k, v = s * codes) into g_qkv fp32 [B*T][3*H*64].  qkv_codes: ONE bf16 plane [B*T][ld]; o_planes: the
+ * forward's output, bf16 hi/lo planes [2][B*T][o_ld] (qv_attn_fwd out_planes; gives delta = dO . O); do_planes: bf16 hi/lo
+ * planes [2][B*T][do_ld] of dL/dO; lse: fp32 [B*H*T] (qv_attn_fwd); qscale: device scalar s (NULL = 1).  T <= 224. */
+int qv_attn_bwd(const uint16_t* qkv_codes, int64_t ld, const float* qscale, const uint16_t* o_planes, int64_t o_plane_stride,
+                int64_t o_ld, const uint16_t* do_planes, int64_t do_plane_stride, int64_t do_ld, const float* lse, int32_t B,
+                int32_t T, int32_t H, float scale, float* g_qkv, void* stream);
 /* qv_attn_bwd with the qkv Linear's backward prologue (qv_gp_planes) fused into its output stage: instead of fp32 dQ | dK | dV,
  * writes gp = g * STEmask(y_raw) * w_scale[col] as bf16 hi/lo planes [2][B*T][3*H*64] (the A operand of the qkv dgrad / wgrad
  * GEMMs) and colsum fp32 [B * ceil(T/128) * 4][3*H*64]: per 32-token slab column sums of g * mask (bias-grad partials, reduce
  * with qv_colsum_reduce).  y_raw: the qkv Linear's raw output fp32 [B*T][3*H*64]; (y_scale, y_zp, qmin, qmax): its output
  * fake-quant; w_scale: fp32 [3*H*64] per-output-channel weight scale. */
-int qv_attn_bwd_gp(const uint16_t* qkv_codes, int64_t ld, const float* qscale, const uint16_t* do_planes,
-                   int64_t do_plane_stride, int64_t do_ld, const float* lse, int32_t B, int32_t T, int32_t H, float scale,
-                   const float* y_raw, const float* y_scale, const int32_t* y_zp, int32_t qmin, int32_t qmax,
-                   const float* w_scale, uint16_t* gp_planes, int64_t gp_plane_stride, float* colsum, void* stream);
+int qv_attn_bwd_gp(const uint16_t* qkv_codes, int64_t ld, const float* qscale, const uint16_t* o_planes, int64_t o_plane_stride,
+                   int64_t o_ld, const uint16_t* do_planes, int64_t do_plane_stride, int64_t do_ld, const float* lse, int32_t B,
+                   int32_t T, int32_t H, float scale, const float* y_raw, const float* y_scale, const int32_t* y_zp,
+                   int32_t qmin, int32_t qmax, const float* w_scale, uint16_t* gp_planes, int64_t gp_plane_stride,
+                   float* colsum, void* stream);
 /* classifier head (D -> num_classes), exact fp32: out = x wq^T + bias (+ fused output-observer min/max). */
 int qv_head_fwd(const float* x, const float* wq, const float* bias, int32_t B, int32_t K, int32_t N, float* out,
                 uint32_t* minmax, void* stream);

@@ -11,7 +11,7 @@ import subprocess
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libqatvit_b200.so")
+LIB_PATH = os.environ.get("QV_LIB") or os.path.join(_HERE, "lib", "libqatvit_b200.so")    # QV_LIB: an instrumented build
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "qatvit_b200.h")
 
 
@@ -92,9 +92,10 @@ _SIGNATURES = {
     "qv_attn_ds": (c_int, [_P, c_int64, c_int64, _P, c_int64, c_int64, c_int32, c_float, _P, c_int64, c_int64, _P]),
     "qv_attn_fwd": (c_int, [_P, c_int32, c_int64, c_int64, c_int32, c_int32, c_int32, c_float, _P, _P, _P, c_int64, c_int64,
                             _P, _P, _P]),
-    "qv_attn_bwd": (c_int, [_P, c_int64, _P, _P, c_int64, c_int64, _P, c_int32, c_int32, c_int32, c_float, _P, _P]),
-    "qv_attn_bwd_gp": (c_int, [_P, c_int64, _P, _P, c_int64, c_int64, _P, c_int32, c_int32, c_int32, c_float,
-                               _P, _P, _P, c_int32, c_int32, _P, _P, c_int64, _P, _P]),
+    "qv_attn_bwd": (c_int, [_P, c_int64, _P, _P, c_int64, c_int64, _P, c_int64, c_int64, _P, c_int32, c_int32, c_int32, c_float,
+                            _P, _P]),
+    "qv_attn_bwd_gp": (c_int, [_P, c_int64, _P, _P, c_int64, c_int64, _P, c_int64, c_int64, _P, c_int32, c_int32, c_int32,
+                               c_float, _P, _P, _P, c_int32, c_int32, _P, _P, c_int64, _P, _P]),
     "qv_clip_adamw": (c_int, [_P, _P, _P, _P, c_int64, _P, c_int32, c_float, c_float, c_float, c_float, c_float, c_float, c_float,
                               c_int64, _P, c_int32, _P]),
     "qv_int8_linear": (c_int, [_P, c_int64, c_int64, _P, _P, _P, c_int64, _P, c_int32, _P, _P, c_float, c_int32, c_int32, _P, _P,

@@ -183,10 +183,14 @@ qv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    // whole warp walks the schedule, one elected lane issues (operands stay in uniform registers; see gemm_sm100.cu)
+    {
       const uint32_t idesc_s = umma_idesc_bf16(128, n_keys, false, false);
       const uint32_t idesc_pv = umma_idesc_bf16(128, HD, false, true);
       const int ksteps_pv = n_keys >> 4;
+      const uint64_t dQ0 = umma_smem_desc(smem_u32(sQ), 16u, 1024u);          // K-major Q tiles / K planes
+      const uint64_t dK0 = umma_smem_desc(smem_u32(sK), 16u, 1024u);
+      const uint64_t dV0 = umma_smem_desc(smem_u32(sV), 8192u, 1024u);        // MN-major V boxes
       int local = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
         const uint32_t ph = static_cast<uint32_t>(local & 1);
@@ -198,22 +202,22 @@ qv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         // ---- S_g = Q_g K^T ----
         for (int g = 0; g < mt; ++g) {
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(g * S_COLS);
+          if (elect_one()) {
 #pragma unroll
-          for (int pr = 0; pr < C::NPAIRS_S; ++pr) {
-            const int pa = (pr == 2) ? 1 : 0;
-            const int pb = (pr == 1) ? 1 : 0;
-            const uint32_t a_base = smem_u32(sQ + (pa * 2 + g) * Q_TILE_BYTES);
-            const uint32_t b_base = smem_u32(sK + pb * K_PLANE_BYTES);
+            for (int pr = 0; pr < C::NPAIRS_S; ++pr) {
+              const int pa = (pr == 2) ? 1 : 0;
+              const int pb = (pr == 1) ? 1 : 0;
+              const uint64_t da = dQ0 + static_cast<uint64_t>((pa * 2 + g) * (Q_TILE_BYTES >> 4));
+              const uint64_t db = dK0 + static_cast<uint64_t>(pb * (K_PLANE_BYTES >> 4));
 #pragma unroll
-            for (int k = 0; k < HD / 16; ++k) {
-              const uint64_t da = umma_smem_desc(a_base + k * 32, 16u, 1024u);
-              const uint64_t db = umma_smem_desc(b_base + k * 32, 16u, 1024u);
-              umma_bf16(d_tmem, da, db, idesc_s, (pr > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < HD / 16; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc_s, (pr > 0 || k > 0) ? 1u : 0u);
             }
+            umma_commit(&s_full[g]);
           }
-          umma_commit(&s_full[g]);
+          __syncwarp();
         }
-        umma_commit(qk_empty);                 // Q / K smem may be refilled once the score MMAs have read it
+        if (elect_one()) umma_commit(qk_empty);  // Q / K smem may be refilled once the score MMAs have read it
+        __syncwarp();
         // ---- O_g = P_g V ----
         mbar_wait(v_full, ph);
         for (int g = 0; g < mt; ++g) {
@@ -222,21 +226,26 @@ qv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(g == 0 ? O0_COL : 0);
           const uint32_t p_tmem = tmem_base + static_cast<uint32_t>(g * S_COLS);
+          if (elect_one()) {
 #pragma unroll
-          for (int pr = 0; pr < C::NPAIRS_PV; ++pr) {
-            // NPL == 2: (P_hi,V_hi) (P_hi,V_lo) (P_lo,V_hi);  NPL == 1: (P_hi,V) (P_lo,V)
-            const int pa = (NPL == 2) ? (pr == 2 ? 1 : 0) : pr;
-            const int pb = (NPL == 2) ? (pr == 1 ? 1 : 0) : 0;
-            for (int kk = 0; kk < ksteps_pv; ++kk) {
-              // 16 keys of P: 8 TMEM columns inside the 32-column chunk kk/2 -- [hi even | hi odd | lo even | lo odd]
-              const uint32_t a_tmem = p_tmem + static_cast<uint32_t>((kk >> 1) * 32 + pa * 16 + (kk & 1) * 8);
-              const uint64_t db = umma_smem_desc(smem_u32(sV + (pb * 4 + (kk >> 2)) * V_BOX_BYTES) + (kk & 3) * 2048, 8192u, 1024u);
-              umma_bf16_ts(d_tmem, a_tmem, db, idesc_pv, (pr > 0 || kk > 0) ? 1u : 0u);
+            for (int pr = 0; pr < C::NPAIRS_PV; ++pr) {
+              // NPL == 2: (P_hi,V_hi) (P_hi,V_lo) (P_lo,V_hi);  NPL == 1: (P_hi,V) (P_lo,V)
+              const int pa = (NPL == 2) ? (pr == 2 ? 1 : 0) : pr;
+              const int pb = (NPL == 2) ? (pr == 1 ? 1 : 0) : 0;
+              const uint64_t dv = dV0 + static_cast<uint64_t>(pb * 4 * (V_BOX_BYTES >> 4));
+              for (int kk = 0; kk < ksteps_pv; ++kk) {
+                // 16 keys of P: 8 TMEM columns inside the 32-column chunk kk/2 -- [hi even | hi odd | lo even | lo odd]
+                const uint32_t a_tmem = p_tmem + static_cast<uint32_t>((kk >> 1) * 32 + pa * 16 + (kk & 1) * 8);
+                // key step kk: box kk/4 (8 KB each), 2048 bytes per step inside the box -> contiguous: kk * 2048 bytes
+                umma_bf16_ts(d_tmem, a_tmem, dv + static_cast<uint64_t>(kk) * 128u, idesc_pv, (pr > 0 || kk > 0) ? 1u : 0u);
+              }
             }
+            umma_commit(&o_full[g]);
           }
-          umma_commit(&o_full[g]);
+          __syncwarp();
         }
-        umma_commit(v_empty);
+        if (elect_one()) umma_commit(v_empty);
+        __syncwarp();
       }
     }
   } else {
@@ -362,21 +371,28 @@ int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap&
 // ====================================================================================================================
 // Fused attention BACKWARD for integer-code operands (the QAT student: Q, K, V = s * codes), one (image, head) per item.
 //
-// Given dO (bf16 hi/lo planes), the codes and the forward's logsumexp, recomputes the probabilities on the tensor cores and
-// produces dQ, dK, dV (fp32) without ever writing scores to HBM.  Replaces the autograd of F.scaled_dot_product_attention
-// (4 batched GEMMs + softmax-backward passes in the unfused path).  With z = scale * Q K^T, P = softmax(z):
-//     dP = dO V^T,  delta_i = sum_j P_ij dP_ij,  dz = P o (dP - delta),  dQ = scale dz K,  dK = scale dz^T Q,  dV = P^T dO.
+// Given dO (bf16 hi/lo planes), O (the forward's output planes), the codes and the forward's logsumexp, recomputes the
+// probabilities on the tensor cores and produces dQ, dK, dV without ever writing scores to HBM.  Replaces the autograd of
+// F.scaled_dot_product_attention (4 batched GEMMs + softmax-backward passes in the unfused path).  With z = scale * Q K^T,
+// P = softmax(z):
+//     dP = dO V^T,  delta_i = sum_j P_ij dP_ij = sum_d dO_id O_id,  dz = P o (dP - delta),
+//     dQ = scale dz K,  dK = scale dz^T Q,  dV = P^T dO.
 // TMEM accumulators are row-per-lane, so the kernel runs two kinds of sub-pass per 128-row tile:
-//   pass A (lanes = queries):  R0 = Q K^T, R1 = dO V^T  -> threads: delta_i, dz (bf16 hi/lo, in place over R1) -> dQ = dz K
-//   pass B (lanes = keys):     R0 = K Q^T, R1 = V dO^T  -> threads: P^T, dz^T (in place)  -> dV = P^T dO, dK = dz^T Q
-// (recomputing S / dP transposed costs two small extra MMAs and saves staging dz through shared memory).  All second-stage
-// products are TS-mode MMAs (A from TMEM); the same [tokens x 64] shared-memory tiles serve as K-major operands of the first
-// stage and MN-major operands of the second.
-// TMEM: R0 [0,224) | R1 [224,448) | ACC0 [448,512) (dQ / dV) ; dK re-uses [0,64) once P^T has been consumed.
-// Warps: 0 TMA, 1 MMA, 2-9 compute (two warps per TMEM lane quarter, alternating 32-column chunks).
+//   pass A (lanes = queries):  S = Q K^T, dP = dO V^T  -> threads: dz (bf16 hi/lo, in place over dP)   -> dQ += dz K
+//   pass B (lanes = keys):     S^T = K Q^T, dP^T = V dO^T -> threads: P^T, dz^T (in place)  -> dV += P^T dO, dK += dz^T Q
+// (recomputing S / dP transposed costs two small extra MMAs and saves staging dz through shared memory).
+// Every sub-pass is cut into CHUNKS of 64 columns (keys in pass A, queries in pass B) with the S / dP accumulators
+// double-buffered in TMEM: while the 8 compute warps turn chunk c into dz / P^T, the tensor pipe already runs the first-stage
+// products of chunk c+1 and the second-stage products of chunk c-1.  delta comes from dO . O (computed per item from global
+// memory while the item's tiles are still in flight), so a chunk needs no row-wide reduction before it can be processed.
+// All second-stage products are TS-mode MMAs (A from TMEM); the same [tokens x 64] shared-memory tiles serve as K-major
+// operands of the first stage and MN-major operands of the second.
+// TMEM: buffer b in {0,1}: S_b [128 b, +64) | R_b [128 b + 64, +64) ;  ACC0 [256,320) (dQ / dV) ;  ACC1 [320,384) (dK).
+// Warps: 0 TMA, 1 MMA, 2-9 compute (two warps per TMEM lane quarter, one 32-column piece of the chunk each).
 // ====================================================================================================================
 constexpr int BW_TILE_BYTES = 256 * HD * 2;     // 32 KB: up to 256 token rows x 64 bf16 (rows >= T zero-filled by TMA)
-constexpr int BW_SMEM_BYTES = 5 * BW_TILE_BYTES + 4096 /*lse, delta, partials*/ + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int BW_SMEM_BYTES = 5 * BW_TILE_BYTES + 4096 /*lse, delta*/ + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t BW_ACC0_COL = 256, BW_ACC1_COL = 320;
 
 struct AttnBwdParams {
   int32_t B, T, H;
@@ -384,6 +400,10 @@ struct AttnBwdParams {
   float scale;
   const float* qscale;      // device scalar s (Q = K = V scale); may be null (= 1)
   const float* lse;         // [B*H*T] from the forward
+  const __nv_bfloat16* o_planes;   // [2][B*T][o_ld]: the forward's output O (hi/lo), head h in columns h*64..
+  int64_t o_plane_stride, o_ld;
+  const __nv_bfloat16* do_planes;  // [2][B*T][do_ld]: dL/dO (also the TMA source of the dO tiles)
+  int64_t do_plane_stride, do_ld;
   float* g_qkv;             // [B*T][3*D]: dQ | dK | dV column blocks
   // FUSED: the qkv Linear's backward prologue (qv_gp_planes) applied on the way out -- gq = g * STEmask(y_raw),
   // planes = hi/lo split of gq * w_scale[col], per-slab column sums of gq (bias grad partials)
@@ -397,6 +417,19 @@ struct AttnBwdParams {
   float* colsum;            // [B * m_tiles * 4][3*D]
 };
 
+#ifdef QV_ATTN_DEBUG
+__device__ unsigned long long qv_dbg_buf[2][8192];
+__device__ __forceinline__ void dbg_event(int who, int& n, int tag) {
+  if (blockIdx.x == 0 && n < 8192) qv_dbg_buf[who][n++] = (static_cast<unsigned long long>(tag) << 48) | (clock64() & 0xffffffffffffULL);
+}
+#define DBG(who, tag) dbg_event(who, dbg_n, tag)
+#else
+#define DBG(who, tag)
+#endif
+
+__device__ __forceinline__ float bf16lo_f(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16hi_f(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
 template <bool FUSED>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
@@ -409,16 +442,14 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
   uint8_t* sDOh = sV + BW_TILE_BYTES;
   uint8_t* sDOl = sDOh + BW_TILE_BYTES;
   float* lse2_s = reinterpret_cast<float*>(sDOl + BW_TILE_BYTES);   // [256] lse * log2(e)
-  float* delta_s = lse2_s + 256;                                     // [256] sum_j P_ij dP_raw_ij
-  float* part_s = delta_s + 256;                                     // [2 sub-pass parities][2 warps of a pair][128 rows]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(part_s + 512);
+  float* delta_s = lse2_s + 256;                                     // [256] (dO . O) / s
+  uint64_t* bars = reinterpret_cast<uint64_t*>(delta_s + 768);
   uint64_t* ld_full = bars + 0;
   uint64_t* ld_empty = bars + 1;
-  uint64_t* mma1_done = bars + 2;
-  uint64_t* cmp_done = bars + 3;
-  uint64_t* acc_done = bars + 4;
-  uint64_t* acc2_done = bars + 5;
-  uint64_t* epi_done = bars + 6;
+  uint64_t* mma1_done = bars + 2;   // [2]
+  uint64_t* cmp_done = bars + 4;    // [2]
+  uint64_t* acc_done = bars + 6;
+  uint64_t* epi_done = bars + 7;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5;
@@ -427,18 +458,19 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
   const int num_items = p.B * p.H;
   const int n_keys = p.n_keys;
   const int mt = p.m_tiles;
-  const int ksteps = n_keys >> 4;
-  constexpr uint32_t R1_COL = S_COLS, ACC0_COL = O0_COL;
+  const int nch = (n_keys + 63) >> 6;          // 64-column chunks per sub-pass
+  const int nsub = 2 * mt;                     // sub-passes per item: pass A tiles, then pass B tiles
 
   if (threadIdx.x == 0) {
     prefetch_tensormap(&map_qkv);
     prefetch_tensormap(&map_do);
     mbar_init(ld_full, 1);
     mbar_init(ld_empty, 1);
-    mbar_init(mma1_done, 1);
-    mbar_init(cmp_done, 256);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&mma1_done[b], 1);
+      mbar_init(&cmp_done[b], 256);
+    }
     mbar_init(acc_done, 1);
-    mbar_init(acc2_done, 1);
     mbar_init(epi_done, 256);
     fence_barrier_init();
   }
@@ -465,67 +497,113 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      const uint32_t idesc_ss = umma_idesc_bf16(128, n_keys, false, false);
+    // The WHOLE warp walks the schedule (waits included) and one elected lane issues: with warp-uniform control flow ptxas
+    // keeps descriptors / TMEM addresses in uniform registers instead of a per-instruction R2UR + ELECT waterfall loop.
+    {
       const uint32_t idesc_ts = umma_idesc_bf16(128, HD, false, true);
-      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aDh = smem_u32(sDOh), aDl = smem_u32(sDOl);
-      const uint32_t r0 = tmem_base, r1 = tmem_base + R1_COL, acc0 = tmem_base + ACC0_COL, acc1 = tmem_base;
-      // first-stage SS product: D[tmem] (+)= A[rows tile*128.., K-major] * B[rows 0..n_keys, K-major]^T over d = 64
-      auto ss = [&](uint32_t d_tmem, uint32_t a_tile, int tile, uint32_t b_tile, bool accumulate) {
+      // Descriptors are built ONCE per tile and mode; every MMA then only adds its byte offset (>> 4) to the start-address
+      // field (tiles sit below 256 KB, so the 14-bit field never carries) -- the single issuing thread is on the critical
+      // path of every chunk-step, and rebuilding a descriptor per instruction cost ~50 ns each.
+      const uint64_t kQ = umma_smem_desc(smem_u32(sQ), 16u, 1024u), kK = umma_smem_desc(smem_u32(sK), 16u, 1024u),
+                     kV = umma_smem_desc(smem_u32(sV), 16u, 1024u), kDh = umma_smem_desc(smem_u32(sDOh), 16u, 1024u),
+                     kDl = umma_smem_desc(smem_u32(sDOl), 16u, 1024u);                       // K-major views
+      const uint64_t mQ = umma_smem_desc(smem_u32(sQ), 8192u, 1024u), mK = umma_smem_desc(smem_u32(sK), 8192u, 1024u),
+                     mDh = umma_smem_desc(smem_u32(sDOh), 8192u, 1024u), mDl = umma_smem_desc(smem_u32(sDOl), 8192u, 1024u);  // MN-major
+      const int w_tail = n_keys - 64 * (nch - 1);
+      const uint32_t idesc_full = umma_idesc_bf16(128, 64, false, false);
+      const uint32_t idesc_tail = umma_idesc_bf16(128, w_tail, false, false);
+      auto mma1 = [&](int sub, int c, uint32_t buf) {
+        const uint32_t idesc = (c == nch - 1) ? idesc_tail : idesc_full;
+        const uint32_t S = tmem_base + buf * 128u, R = S + 64u;
+        const uint64_t rows = static_cast<uint64_t>(c) * 512u;           // 64 token rows x 128 B, in 16-byte units
+        // S and dP are independent accumulators: their MMAs are issued alternately so that consecutive instructions never
+        // accumulate into the same TMEM tile (back-to-back dependent accumulation at N = 64 runs at half rate)
+        const bool pa = sub < mt;                                        // pass A: lanes = queries; pass B: lanes = keys
+        const uint64_t t = static_cast<uint64_t>(pa ? sub : sub - mt) * 1024u;      // 128-row tile: 16384 B
+        const uint64_t sa = (pa ? kQ : kK) + t, sb = (pa ? kK : kQ) + rows;         // S = Q K^T        | S^T = K Q^T
+        const uint64_t r1a = (pa ? kDh : kV) + t, r1b = (pa ? kV : kDh) + rows;     // dP = dO V^T (hi) | dP^T = V dO^T (hi)
+        const uint64_t r2a = (pa ? kDl : kV) + t, r2b = (pa ? kV : kDl) + rows;     //            (lo) |              (lo)
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) {
-          const uint64_t da = umma_smem_desc(a_tile + tile * (128 * 128) + k * 32, 16u, 1024u);
-          const uint64_t db = umma_smem_desc(b_tile + k * 32, 16u, 1024u);
-          umma_bf16(d_tmem, da, db, idesc_ss, (accumulate || k > 0) ? 1u : 0u);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k) {
+            umma_bf16(R, r1a + 2 * k, r1b + 2 * k, idesc, k > 0 ? 1u : 0u);
+            umma_bf16(S, sa + 2 * k, sb + 2 * k, idesc, k > 0 ? 1u : 0u);
+            umma_bf16(R, r2a + 2 * k, r2b + 2 * k, idesc, 1u);
+          }
+          umma_commit(&mma1_done[buf]);
+        }
+        __syncwarp();
+      };
+      auto mma2 = [&](int sub, int c, uint32_t buf) {
+        const int ks = (c == nch - 1) ? (w_tail >> 4) : 4;
+        const uint32_t S = tmem_base + buf * 128u, R = S + 64u;
+        const uint64_t rows = static_cast<uint64_t>(c) * 512u;
+        const uint32_t acc0 = tmem_base + BW_ACC0_COL, acc1 = tmem_base + BW_ACC1_COL;
+        const bool pa = sub < mt;
+        const uint64_t bK = mK + rows, bQ = mQ + rows, bDh = mDh + rows, bDl = mDl + rows;   // operands formed warp-uniformly
+        const uint32_t first0 = c > 0 ? 1u : 0u;
+        if (elect_one()) {
+          if (pa) {                                                      // dQ += dz K (hi, lo)
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              if (kk < ks) {
+                const uint32_t off = static_cast<uint32_t>((kk >> 1) * 32 + (kk & 1) * 8);
+                umma_bf16_ts(acc0, R + off, bK + 128 * kk, idesc_ts, kk > 0 ? 1u : first0);
+                umma_bf16_ts(acc0, R + off + 16, bK + 128 * kk, idesc_ts, 1u);
+              }
+            }
+          } else {                                                       // dV and dK chains interleaved (independent tiles)
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              if (kk < ks) {
+                const uint32_t off = static_cast<uint32_t>((kk >> 1) * 32 + (kk & 1) * 8);
+                const uint32_t first = kk > 0 ? 1u : first0;
+                umma_bf16_ts(acc0, S + off, bDh + 128 * kk, idesc_ts, first);            // dV += P^T dO : (hi,hi)
+                umma_bf16_ts(acc1, R + off, bQ + 128 * kk, idesc_ts, first);             // dK += dz^T Q : hi
+                umma_bf16_ts(acc0, S + off, bDl + 128 * kk, idesc_ts, 1u);               //               (hi,lo)
+                umma_bf16_ts(acc1, R + off + 16, bQ + 128 * kk, idesc_ts, 1u);           //                lo
+                umma_bf16_ts(acc0, S + off + 16, bDh + 128 * kk, idesc_ts, 1u);          //               (lo,hi)
+              }
+            }
+          }
         }
       };
-      // second-stage TS product: D[tmem] (+)= A[tmem region, plane] * B[[tokens x 64] tile, MN-major] over the tokens
-      auto ts = [&](uint32_t d_tmem, uint32_t a_region, int plane, uint32_t b_tile, bool accumulate) {
-        for (int kk = 0; kk < ksteps; ++kk) {
-          const uint32_t a_tmem = a_region + static_cast<uint32_t>((kk >> 1) * 32 + plane * 16 + (kk & 1) * 8);
-          const uint64_t db = umma_smem_desc(b_tile + kk * 2048, 8192u, 1024u);
-          umma_bf16_ts(d_tmem, a_tmem, db, idesc_ts, (accumulate || kk > 0) ? 1u : 0u);
-        }
-      };
-      uint32_t sp = 0;          // running sub-pass counter (phase of mma1_done / cmp_done / acc_done / epi_done)
-      uint32_t spb = 0;         // running pass-B counter (phase of acc2_done)
+      uint32_t st = 0;          // running chunk-step counter: buffer = st & 1, barrier phase = (st >> 1) & 1
+      uint32_t nsp = 0;         // running sub-pass counter (phase of acc_done / epi_done)
       int local = 0;
+#ifdef QV_ATTN_DEBUG
+      int dbg_n = 0;
+#endif
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
+        DBG(0, 1);
         mbar_wait(ld_full, static_cast<uint32_t>(local & 1));
         tc_fence_after();
-        for (int g = 0; g < mt; ++g, ++sp) {                     // ---- pass A: lanes = queries of tile g ----
-          mbar_wait(epi_done, (sp & 1) ^ 1);
-          tc_fence_after();
-          ss(r0, aQ, g, aK, false);                              // S = Q K^T
-          ss(r1, aDh, g, aV, false);                             // dP = dO V^T (hi + lo)
-          ss(r1, aDl, g, aV, true);
-          umma_commit(mma1_done);
-          mbar_wait(cmp_done, sp & 1);
-          tc_fence_after();
-          ts(acc0, r1, 0, aK, false);                            // dQ = dz K
-          ts(acc0, r1, 1, aK, true);
-          umma_commit(acc_done);
+        DBG(0, 2);
+        mma1(0, 0, st & 1);
+        for (int sub = 0; sub < nsub; ++sub) {
+          for (int c = 0; c < nch; ++c, ++st) {
+            // first stage of the NEXT chunk-step goes out before this step's second stage waits for the compute warps
+            if (c + 1 < nch) mma1(sub, c + 1, (st + 1) & 1);
+            else if (sub + 1 < nsub) mma1(sub + 1, 0, (st + 1) & 1);
+            DBG(0, 3);
+            mbar_wait(&cmp_done[st & 1], (st >> 1) & 1);
+            DBG(0, 4);
+            if (c == 0) mbar_wait(epi_done, (nsp & 1) ^ 1);              // accumulators of the previous sub-pass drained
+            tc_fence_after();
+            DBG(0, 5);
+            mma2(sub, c, st & 1);
+            __syncwarp();
+            DBG(0, 6);
+            if (c == nch - 1) {
+              if (elect_one()) umma_commit(acc_done);
+              __syncwarp();
+              ++nsp;
+            }
+          }
         }
-        for (int kt = 0; kt < mt; ++kt, ++sp, ++spb) {           // ---- pass B: lanes = keys of tile kt ----
-          mbar_wait(epi_done, (sp & 1) ^ 1);
-          tc_fence_after();
-          ss(r0, aK, kt, aQ, false);                             // S^T = K Q^T
-          ss(r1, aV, kt, aDh, false);                            // dP^T = V dO^T (hi + lo)
-          ss(r1, aV, kt, aDl, true);
-          umma_commit(mma1_done);
-          mbar_wait(cmp_done, sp & 1);
-          tc_fence_after();
-          ts(acc0, r0, 0, aDh, false);                           // dV = P^T dO : (hi,hi) (hi,lo) (lo,hi)
-          ts(acc0, r0, 0, aDl, true);
-          ts(acc0, r0, 1, aDh, true);
-          umma_commit(acc_done);
-          mbar_wait(acc_done, sp & 1);                           // P^T consumed: [0,64) may now hold dK
-          tc_fence_after();
-          ts(acc1, r1, 0, aQ, false);                            // dK = dz^T Q
-          ts(acc1, r1, 1, aQ, true);
-          umma_commit(acc2_done);
-        }
-        umma_commit(ld_empty);                                   // every MMA that reads this item's tiles has completed
+        if (elect_one()) umma_commit(ld_empty);                          // every MMA that reads this item's tiles has completed
+        __syncwarp();
       }
     }
   } else {
@@ -535,9 +613,9 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
     const int par = cw >> 2;
     const int row = q * 32 + lane;               // row inside the 128-row tile == TMEM lane
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t r0 = tmem_base + lane_addr, r1 = r0 + R1_COL, acc0 = r0 + ACC0_COL, acc1 = r0;
-    const int nch = (n_keys + 31) >> 5;
+    const uint32_t t0 = tmem_base + lane_addr;
     const float s = p.qscale ? __ldg(p.qscale) : 1.0f;
+    const float inv_s = 1.0f / s;
     const float c2 = p.scale * s * s * 1.4426950408889634f;
     const float gscale = p.scale * s * s;        // dQ, dK factor (see header comment)
     const int ctid = threadIdx.x - 64;           // 0..255
@@ -583,136 +661,146 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
       const float cs = qv_warp_colsum32(gq, lane);
       p.colsum[static_cast<int64_t>(slab) * D3 + col + lane] = cs;
     };
-    uint32_t sp = 0, spb = 0;
+    auto store_f32 = [&](const uint32_t (&o)[32], float mult, int b, int tok, int col) {
+      if (tok < p.T) {
+        float* dst = p.g_qkv + (static_cast<int64_t>(b) * p.T + tok) * D3 + col;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(__uint_as_float(o[4 * j]) * mult, __uint_as_float(o[4 * j + 1]) * mult,
+                                                                __uint_as_float(o[4 * j + 2]) * mult, __uint_as_float(o[4 * j + 3]) * mult);
+      }
+    };
+    uint32_t st = 0, nsp = 0;
+#ifdef QV_ATTN_DEBUG
+    int dbg_n = (threadIdx.x == 64) ? 0 : 8192;
+#endif
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       const int b = item / p.H, h = item % p.H;
       const float* lse_bh = p.lse + (static_cast<int64_t>(b) * p.H + h) * p.T;
-      asm volatile("bar.sync 9, 256;" ::: "memory");            // previous item's pass B has finished reading lse2_s / delta_s
+      DBG(1, 10);
+      asm volatile("bar.sync 9, 256;" ::: "memory");            // previous item has finished reading lse2_s / delta_s
       lse2_s[ctid] = (ctid < p.T) ? __ldg(lse_bh + ctid) * 1.4426950408889634f : 0.0f;
-      float* grow_base = p.g_qkv + static_cast<int64_t>(b) * p.T * (3 * D) + h * HD + par * 32;
-      // ------------------------------ pass A ------------------------------
-      for (int g = 0; g < mt; ++g, ++sp) {
-        const int i = g * 128 + row;
-        const float Li = (i < p.T) ? __ldg(lse_bh + i) * 1.4426950408889634f : 0.0f;
-        mbar_wait(mma1_done, sp & 1);
-        tc_fence_after();
-        float dpart = 0.f;
+      // delta_i = (dO_i . O_i) / s from global memory (the item's tiles are still landing): 8 lanes per token row, 8 columns each
 #pragma unroll 1
-        for (int c = par; c < nch; c += 2) {
-          uint32_t sv[32], dv[32];
-          tmem_ld_32x32(r0 + c * 32, sv);
-          tmem_ld_32x32(r1 + c * 32, dv);
-          tmem_ld_wait();
-          const int nvalid = p.T - c * 32;
+      for (int half = 0; half < 2; ++half) {
+        uint4 oh[4], ol[4], dh[4], dl[4];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float pj = (j < nvalid) ? ex2_approx(fmaf(__uint_as_float(sv[j]), c2, -Li)) : 0.f;
-            dpart = fmaf(pj, __uint_as_float(dv[j]), dpart);
+        for (int u = 0; u < 4; ++u) {                              // 16 independent 16-byte loads in flight per lane
+          const int r = (half * 4 + u) * 32 + cw * 4 + (lane >> 3);
+          if (r < p.T) {
+            const int64_t grow = static_cast<int64_t>(b) * p.T + r;
+            const int col = h * HD + (lane & 7) * 8;
+            oh[u] = __ldg(reinterpret_cast<const uint4*>(p.o_planes + grow * p.o_ld + col));
+            ol[u] = __ldg(reinterpret_cast<const uint4*>(p.o_planes + p.o_plane_stride + grow * p.o_ld + col));
+            dh[u] = __ldg(reinterpret_cast<const uint4*>(p.do_planes + grow * p.do_ld + col));
+            dl[u] = __ldg(reinterpret_cast<const uint4*>(p.do_planes + p.do_plane_stride + grow * p.do_ld + col));
+          } else {
+            oh[u] = ol[u] = dh[u] = dl[u] = make_uint4(0u, 0u, 0u, 0u);
           }
         }
-        float* part = part_s + (sp & 1) * 256;
-        part[par * 128 + row] = dpart;
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-        const float delta = part[row] + part[128 + row];
-        if (par == 0) delta_s[g * 128 + row] = delta;
-#pragma unroll 1
-        for (int c = par; c < nch; c += 2) {
-          uint32_t sv[32], dv[32], pk[32];
-          tmem_ld_32x32(r0 + c * 32, sv);
-          tmem_ld_32x32(r1 + c * 32, dv);
-          tmem_ld_wait();
-          const int nvalid = p.T - c * 32;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float p0 = (2 * j < nvalid) ? ex2_approx(fmaf(__uint_as_float(sv[2 * j]), c2, -Li)) : 0.f;
-            const float p1 = (2 * j + 1 < nvalid) ? ex2_approx(fmaf(__uint_as_float(sv[2 * j + 1]), c2, -Li)) : 0.f;
-            split_pack2(p0 * (__uint_as_float(dv[2 * j]) - delta), p1 * (__uint_as_float(dv[2 * j + 1]) - delta), pk[j], pk[16 + j]);
+        for (int u = 0; u < 4; ++u) {
+          const int r = (half * 4 + u) * 32 + cw * 4 + (lane >> 3);
+          const uint32_t ohw[4] = {oh[u].x, oh[u].y, oh[u].z, oh[u].w}, olw[4] = {ol[u].x, ol[u].y, ol[u].z, ol[u].w};
+          const uint32_t dhw[4] = {dh[u].x, dh[u].y, dh[u].z, dh[u].w}, dlw[4] = {dl[u].x, dl[u].y, dl[u].z, dl[u].w};
+          float dot = 0.f;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            dot = fmaf(bf16lo_f(ohw[e]) + bf16lo_f(olw[e]), bf16lo_f(dhw[e]) + bf16lo_f(dlw[e]), dot);
+            dot = fmaf(bf16hi_f(ohw[e]) + bf16hi_f(olw[e]), bf16hi_f(dhw[e]) + bf16hi_f(dlw[e]), dot);
           }
-          tmem_st_32x32(r1 + c * 32, pk);
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(cmp_done);
-        // dQ tile: this warp stores columns par*32 .. par*32+31 of its 32 rows
-        float4 yv[FUSED ? 8 : 1];
-        if constexpr (FUSED) load_y(yv, b, i, h * HD + par * 32);       // in flight while the dQ MMAs finish
-        mbar_wait(acc_done, sp & 1);
-        tc_fence_after();
-        uint32_t o[32];
-        tmem_ld_32x32(acc0 + par * 32, o);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(epi_done);
-        if constexpr (FUSED) {
-          emit(o, yv, gscale, b, i, h * HD + par * 32, (b * mt + g) * 4 + q);
-        } else if (i < p.T) {
-          float* dst = grow_base + static_cast<int64_t>(i) * (3 * D);
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(__uint_as_float(o[4 * j]) * gscale, __uint_as_float(o[4 * j + 1]) * gscale,
-                                                                  __uint_as_float(o[4 * j + 2]) * gscale, __uint_as_float(o[4 * j + 3]) * gscale);
+          dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+          dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+          dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+          if ((lane & 7) == 0) delta_s[r] = dot * inv_s;
         }
       }
-      asm volatile("bar.sync 9, 256;" ::: "memory");            // lse2_s and delta_s complete for every query row
-      // ------------------------------ pass B ------------------------------
-      for (int kt = 0; kt < mt; ++kt, ++sp, ++spb) {
-        const int jrow = kt * 128 + row;                          // key index of this lane
-        mbar_wait(mma1_done, sp & 1);
-        tc_fence_after();
-#pragma unroll 1
-        for (int c = par; c < nch; c += 2) {
-          uint32_t sv[32], dv[32], pp[32], pz[32];
-          tmem_ld_32x32(r0 + c * 32, sv);
-          tmem_ld_32x32(r1 + c * 32, dv);
-          tmem_ld_wait();
-          const int nvalid = p.T - c * 32;                        // valid query columns of this chunk
+      asm volatile("bar.sync 9, 256;" ::: "memory");            // lse2_s and delta_s complete for every token
+      DBG(1, 11);
+      for (int sub = 0; sub < nsub; ++sub, ++nsp) {
+        const bool pass_a = sub < mt;
+        const int tile = pass_a ? sub : sub - mt;
+        const int tok = tile * 128 + row;                         // query (pass A) / key (pass B) of this lane
+        const float Li = lse2_s[tok & 255], di = delta_s[tok & 255];
+        for (int c = 0; c < nch; ++c, ++st) {
+          const uint32_t buf = st & 1;
+          const uint32_t S = t0 + buf * 128u + par * 32u, R = S + 64u;
+          const int col0 = 64 * c + 32 * par;                     // first column (key in pass A, query in pass B) of this piece
+          DBG(1, 12);
+          mbar_wait(&mma1_done[buf], (st >> 1) & 1);
+          tc_fence_after();
+          DBG(1, 13);
+          if (col0 < n_keys) {
+            uint32_t sv[32], dv[32];
+            tmem_ld_32x32(S, sv);
+            tmem_ld_32x32(R, dv);
+            tmem_ld_wait();
+            const int nvalid = p.T - col0;
+            if (pass_a) {
+              uint32_t pk[32];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float2 L = *reinterpret_cast<const float2*>(lse2_s + c * 32 + 2 * j);      // broadcast reads
-            const float2 dl = *reinterpret_cast<const float2*>(delta_s + c * 32 + 2 * j);
-            const float p0 = (2 * j < nvalid) ? ex2_approx(fmaf(__uint_as_float(sv[2 * j]), c2, -L.x)) : 0.f;
-            const float p1 = (2 * j + 1 < nvalid) ? ex2_approx(fmaf(__uint_as_float(sv[2 * j + 1]), c2, -L.y)) : 0.f;
-            split_pack2(p0, p1, pp[j], pp[16 + j]);
-            split_pack2(p0 * (__uint_as_float(dv[2 * j]) - dl.x), p1 * (__uint_as_float(dv[2 * j + 1]) - dl.y), pz[j], pz[16 + j]);
+              for (int j = 0; j < 16; ++j) {
+                const float p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * j]), c2, -Li));
+                const float p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * j + 1]), c2, -Li));
+                const float z0 = (2 * j < nvalid) ? p0 * (__uint_as_float(dv[2 * j]) - di) : 0.f;
+                const float z1 = (2 * j + 1 < nvalid) ? p1 * (__uint_as_float(dv[2 * j + 1]) - di) : 0.f;
+                split_pack2(z0, z1, pk[j], pk[16 + j]);
+              }
+              tmem_st_32x32(R, pk);
+            } else {
+              uint32_t pp[32], pz[32];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float2 L = *reinterpret_cast<const float2*>(lse2_s + col0 + 2 * j);      // broadcast reads
+                const float2 dl = *reinterpret_cast<const float2*>(delta_s + col0 + 2 * j);
+                const float p0 = (2 * j < nvalid) ? ex2_approx(fmaf(__uint_as_float(sv[2 * j]), c2, -L.x)) : 0.f;
+                const float p1 = (2 * j + 1 < nvalid) ? ex2_approx(fmaf(__uint_as_float(sv[2 * j + 1]), c2, -L.y)) : 0.f;
+                const float z0 = (2 * j < nvalid) ? p0 * (__uint_as_float(dv[2 * j]) - dl.x) : 0.f;
+                const float z1 = (2 * j + 1 < nvalid) ? p1 * (__uint_as_float(dv[2 * j + 1]) - dl.y) : 0.f;
+                split_pack2(p0, p1, pp[j], pp[16 + j]);
+                split_pack2(z0, z1, pz[j], pz[16 + j]);
+              }
+              tmem_st_32x32(S, pp);
+              tmem_st_32x32(R, pz);
+            }
+            tmem_st_wait();
           }
-          tmem_st_32x32(r0 + c * 32, pp);
-          tmem_st_32x32(r1 + c * 32, pz);
+          tc_fence_before();
+          mbar_arrive(&cmp_done[buf]);
+          DBG(1, 14);
         }
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(cmp_done);
-        uint32_t o[32];
+        // ---- sub-pass output: this warp stores columns par*32 .. par*32+31 of its 32 rows ----
+        const int slab = (b * mt + tile) * 4 + q;
+        const int ccol = h * HD + par * 32;
         float4 yv[FUSED ? 8 : 1];
-        if constexpr (FUSED) load_y(yv, b, jrow, 2 * D + h * HD + par * 32);
-        mbar_wait(acc_done, sp & 1);                              // dV
+        if constexpr (FUSED) load_y(yv, b, tok, (pass_a ? 0 : 2 * D) + ccol);       // in flight while the last MMAs finish
+        mbar_wait(acc_done, nsp & 1);
         tc_fence_after();
-        tmem_ld_32x32(acc0 + par * 32, o);
+        DBG(1, 15);
+        uint32_t o[32];
+        tmem_ld_32x32(t0 + BW_ACC0_COL + par * 32, o);
         tmem_ld_wait();
-        if constexpr (FUSED) {
-          emit(o, yv, 1.0f, b, jrow, 2 * D + h * HD + par * 32, (b * mt + kt) * 4 + q);
-          load_y(yv, b, jrow, D + h * HD + par * 32);
-        } else if (jrow < p.T) {
-          float* dst = grow_base + static_cast<int64_t>(jrow) * (3 * D) + 2 * D;
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(__uint_as_float(o[4 * j]), __uint_as_float(o[4 * j + 1]),
-                                                                  __uint_as_float(o[4 * j + 2]), __uint_as_float(o[4 * j + 3]));
+        if (pass_a) {
+          tc_fence_before();
+          mbar_arrive(epi_done);
+          if constexpr (FUSED) emit(o, yv, gscale, b, tok, ccol, slab);
+          else store_f32(o, gscale, b, tok, ccol);
+        } else {
+          uint32_t o2[32];
+          tmem_ld_32x32(t0 + BW_ACC1_COL + par * 32, o2);
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(epi_done);
+          if constexpr (FUSED) {
+            emit(o, yv, 1.0f, b, tok, 2 * D + ccol, slab);                         // dV
+            load_y(yv, b, tok, D + ccol);
+            emit(o2, yv, gscale, b, tok, D + ccol, slab);                          // dK
+          } else {
+            store_f32(o, 1.0f, b, tok, 2 * D + ccol);
+            store_f32(o2, gscale, b, tok, D + ccol);
+          }
         }
-        mbar_wait(acc2_done, spb & 1);                            // dK
-        tc_fence_after();
-        tmem_ld_32x32(acc1 + par * 32, o);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(epi_done);
-        if constexpr (FUSED) {
-          emit(o, yv, gscale, b, jrow, D + h * HD + par * 32, (b * mt + kt) * 4 + q);
-        } else if (jrow < p.T) {
-          float* dst = grow_base + static_cast<int64_t>(jrow) * (3 * D) + D;
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(__uint_as_float(o[4 * j]) * gscale, __uint_as_float(o[4 * j + 1]) * gscale,
-                                                                  __uint_as_float(o[4 * j + 2]) * gscale, __uint_as_float(o[4 * j + 3]) * gscale);
-        }
+        DBG(1, 16);
       }
     }
   }
@@ -774,40 +862,16 @@ extern "C" int qv_attn_fwd(const uint16_t* qkv_planes, int32_t n_planes, int64_t
 }
 
 namespace {
-int attn_bwd_impl(const uint16_t* qkv_codes, int64_t ld, const float* qscale, const uint16_t* do_planes, int64_t do_plane_stride,
-                  int64_t do_ld, const float* lse, int32_t B, int32_t T, int32_t H, float scale, float* g_qkv,
-                  const AttnBwdParams* fused, void* stream);
-}
-
-extern "C" int qv_attn_bwd(const uint16_t* qkv_codes, int64_t ld, const float* qscale, const uint16_t* do_planes,
-                           int64_t do_plane_stride, int64_t do_ld, const float* lse, int32_t B, int32_t T, int32_t H, float scale,
-                           float* g_qkv, void* stream) {
-  QV_REQUIRE(g_qkv && qv_aligned16(g_qkv), QV_ERR_INVALID, "g_qkv must be a 16-byte aligned device pointer");
-  return attn_bwd_impl(qkv_codes, ld, qscale, do_planes, do_plane_stride, do_ld, lse, B, T, H, scale, g_qkv, nullptr, stream);
-}
-
-extern "C" int qv_attn_bwd_gp(const uint16_t* qkv_codes, int64_t ld, const float* qscale, const uint16_t* do_planes,
-                              int64_t do_plane_stride, int64_t do_ld, const float* lse, int32_t B, int32_t T, int32_t H,
-                              float scale, const float* y_raw, const float* y_scale, const int32_t* y_zp, int32_t qmin,
-                              int32_t qmax, const float* w_scale, uint16_t* gp_planes, int64_t gp_plane_stride,
-                              float* colsum, void* stream) {
-  QV_REQUIRE(y_raw && y_scale && y_zp && w_scale && gp_planes && colsum, QV_ERR_INVALID, "bad attn_bwd_gp arguments");
-  QV_REQUIRE(qv_aligned16(y_raw) && qv_aligned16(w_scale) && qv_aligned16(gp_planes) && gp_plane_stride % 8 == 0, QV_ERR_INVALID,
-             "y_raw / w_scale / gp_planes must be 16-byte aligned (plane stride a multiple of 8 bf16)");
-  AttnBwdParams f;
-  memset(&f, 0, sizeof(f));
-  f.y_raw = y_raw; f.y_scale = y_scale; f.y_zp = y_zp; f.qmin = qmin; f.qmax = qmax; f.w_scale = w_scale;
-  f.gp = reinterpret_cast<__nv_bfloat16*>(gp_planes); f.gp_plane_stride = gp_plane_stride; f.colsum = colsum;
-  return attn_bwd_impl(qkv_codes, ld, qscale, do_planes, do_plane_stride, do_ld, lse, B, T, H, scale, nullptr, &f, stream);
-}
-
-namespace {
-int attn_bwd_impl(const uint16_t* qkv_codes, int64_t ld, const float* qscale, const uint16_t* do_planes, int64_t do_plane_stride,
-                  int64_t do_ld, const float* lse, int32_t B, int32_t T, int32_t H, float scale, float* g_qkv,
-                  const AttnBwdParams* fused, void* stream) {
-  QV_REQUIRE(qkv_codes && do_planes && lse && (g_qkv || fused) && B > 0 && T > 0 && H > 0, QV_ERR_INVALID, "bad attn_bwd arguments");
+int attn_bwd_impl(const uint16_t* qkv_codes, int64_t ld, const float* qscale, const uint16_t* o_planes, int64_t o_plane_stride,
+                  int64_t o_ld, const uint16_t* do_planes, int64_t do_plane_stride, int64_t do_ld, const float* lse, int32_t B,
+                  int32_t T, int32_t H, float scale, float* g_qkv, const AttnBwdParams* fused, void* stream) {
+  QV_REQUIRE(qkv_codes && o_planes && do_planes && lse && (g_qkv || fused) && B > 0 && T > 0 && H > 0, QV_ERR_INVALID,
+             "bad attn_bwd arguments");
   QV_REQUIRE(T <= 224, QV_ERR_UNSUPPORTED, "fused attention holds all keys in one tile: T <= 224 (got %d)", T);
-  QV_REQUIRE(ld >= 3LL * H * HD && do_ld >= static_cast<int64_t>(H) * HD, QV_ERR_INVALID, "row pitches too small");
+  QV_REQUIRE(ld >= 3LL * H * HD && do_ld >= static_cast<int64_t>(H) * HD && o_ld >= static_cast<int64_t>(H) * HD, QV_ERR_INVALID,
+             "row pitches too small");
+  QV_REQUIRE(qv_aligned16(o_planes) && o_ld % 8 == 0 && o_plane_stride % 8 == 0 && do_ld % 8 == 0 && do_plane_stride % 8 == 0,
+             QV_ERR_INVALID, "O / dO planes must be 16-byte aligned with pitches that are multiples of 8 bf16");
   QV_REQUIRE(qv_num_sms() > 0, QV_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
   AttnBwdParams ap;
   memset(&ap, 0, sizeof(ap));
@@ -818,6 +882,8 @@ int attn_bwd_impl(const uint16_t* qkv_codes, int64_t ld, const float* qscale, co
   ap.scale = scale;
   ap.qscale = qscale;
   ap.lse = lse;
+  ap.o_planes = reinterpret_cast<const __nv_bfloat16*>(o_planes); ap.o_plane_stride = o_plane_stride; ap.o_ld = o_ld;
+  ap.do_planes = reinterpret_cast<const __nv_bfloat16*>(do_planes); ap.do_plane_stride = do_plane_stride; ap.do_ld = do_ld;
   ap.g_qkv = g_qkv;
   qv_operand op;
   memset(&op, 0, sizeof(op));
@@ -846,3 +912,34 @@ int attn_bwd_impl(const uint16_t* qkv_codes, int64_t ld, const float* qscale, co
   return qv_check_launch("qv_attn_bwd");
 }
 }  // namespace
+
+extern "C" int qv_attn_bwd(const uint16_t* qkv_codes, int64_t ld, const float* qscale, const uint16_t* o_planes,
+                           int64_t o_plane_stride, int64_t o_ld, const uint16_t* do_planes, int64_t do_plane_stride,
+                           int64_t do_ld, const float* lse, int32_t B, int32_t T, int32_t H, float scale, float* g_qkv,
+                           void* stream) {
+  QV_REQUIRE(g_qkv && qv_aligned16(g_qkv), QV_ERR_INVALID, "g_qkv must be a 16-byte aligned device pointer");
+  return attn_bwd_impl(qkv_codes, ld, qscale, o_planes, o_plane_stride, o_ld, do_planes, do_plane_stride, do_ld, lse, B, T, H,
+                       scale, g_qkv, nullptr, stream);
+}
+
+extern "C" int qv_attn_bwd_gp(const uint16_t* qkv_codes, int64_t ld, const float* qscale, const uint16_t* o_planes,
+                              int64_t o_plane_stride, int64_t o_ld, const uint16_t* do_planes, int64_t do_plane_stride,
+                              int64_t do_ld, const float* lse, int32_t B, int32_t T, int32_t H, float scale, const float* y_raw,
+                              const float* y_scale, const int32_t* y_zp, int32_t qmin, int32_t qmax, const float* w_scale,
+                              uint16_t* gp_planes, int64_t gp_plane_stride, float* colsum, void* stream) {
+  QV_REQUIRE(y_raw && y_scale && y_zp && w_scale && gp_planes && colsum, QV_ERR_INVALID, "bad attn_bwd_gp arguments");
+  QV_REQUIRE(qv_aligned16(y_raw) && qv_aligned16(w_scale) && qv_aligned16(gp_planes) && gp_plane_stride % 8 == 0, QV_ERR_INVALID,
+             "y_raw / w_scale / gp_planes must be 16-byte aligned (plane stride a multiple of 8 bf16)");
+  AttnBwdParams f;
+  memset(&f, 0, sizeof(f));
+  f.y_raw = y_raw; f.y_scale = y_scale; f.y_zp = y_zp; f.qmin = qmin; f.qmax = qmax; f.w_scale = w_scale;
+  f.gp = reinterpret_cast<__nv_bfloat16*>(gp_planes); f.gp_plane_stride = gp_plane_stride; f.colsum = colsum;
+  return attn_bwd_impl(qkv_codes, ld, qscale, o_planes, o_plane_stride, o_ld, do_planes, do_plane_stride, do_ld, lse, B, T, H,
+                       scale, nullptr, &f, stream);
+}
+
+#ifdef QV_ATTN_DEBUG
+extern "C" int qv_debug_read(unsigned long long* host_out) {   // host_out: [2][8192]
+  return cudaMemcpyFromSymbol(host_out, qv_dbg_buf, sizeof(unsigned long long) * 2 * 8192) == cudaSuccess ? 0 : -1;
+}
+#endif

@@ -36,7 +36,7 @@ constexpr int A_PLANE_BYTES = BM * BK * 2;
 // epilogue staging per warp: 32-row x 128-byte buffers.  fp32 output: one buffer per 32-column chunk; bf16 hi/lo plane
 // output: a hi and a lo buffer per 64-column chunk.  Two warps alternate on each TMEM lane quarter, so per-warp single
 // buffering already overlaps one warp's TMA store with the other's math.
-constexpr int epi_warp_bytes(int epi) { return (epi >= 1 ? 2 : 1) * 32 * 128; }
+constexpr int epi_warp_bytes(int epi) { return (epi == 2 ? 3 : epi == 1 ? 2 : 1) * 32 * 128; }   // EPI 2: y tile x2 + planes
 constexpr int epi_terms_bytes(int epi) { return epi >= 1 ? 0 : 8 * 2 * 32 * 4; }   // per-warp [mult][bias] column terms
 constexpr int SMEM_LIMIT = 232448;             // 227 KB
 
@@ -192,11 +192,17 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    // The whole warp walks the tile / k-block schedule (barrier waits included) and ONE elected lane issues the MMAs and
+    // commits.  With warp-uniform control flow and descriptors formed as "stage base + compile-time offset", ptxas keeps the
+    // operands in uniform registers; under an `if (lane == 0)` region every tcgen05.mma paid an R2UR + ELECT waterfall loop
+    // (~90 cycles of issue per instruction -- as long as a 128 x 192 x 16 MMA takes to execute).
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
       constexpr uint32_t a_lbo = A_MN ? 8192u : 16u, b_lbo = B_MN ? 8192u : 16u;
       constexpr uint32_t a_kadv = A_MN ? (UMMA_K * 128u) : (UMMA_K * 2u);   // bytes per 16-deep k step
       constexpr uint32_t b_kadv = B_MN ? (UMMA_K * 128u) : (UMMA_K * 2u);
+      const uint64_t desc_a0 = umma_smem_desc(smem_u32(smem), a_lbo, 1024u);                          // stage 0, plane 0
+      const uint64_t desc_b0 = umma_smem_desc(smem_u32(smem) + NA * A_PLANE_BYTES, b_lbo, 1024u);
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
@@ -212,24 +218,29 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
-          const uint32_t sb = sa + NA * A_PLANE_BYTES;
+          const uint64_t sa = desc_a0 + static_cast<uint64_t>(stage) * (C::STAGE_BYTES >> 4);
+          const uint64_t sb = desc_b0 + static_cast<uint64_t>(stage) * (C::STAGE_BYTES >> 4);
+          const uint32_t first = (kb > kb0) ? 1u : 0u;
+          if (elect_one()) {
 #pragma unroll
-          for (int pr = 0; pr < C::NPAIRS; ++pr) {
-            // pair order: (0,0) [,(0,1)] [,(1,0)]  -- for NB == 1 the second pair is (1,0)
-            const int pa = (NB == 1) ? pr : (pr == 2 ? 1 : 0);
-            const int pb = (NB == 1) ? 0 : (pr == 1 ? 1 : 0);
+            for (int pr = 0; pr < C::NPAIRS; ++pr) {
+              // pair order: (0,0) [,(0,1)] [,(1,0)]  -- for NB == 1 the second pair is (1,0)
+              const int pa = (NB == 1) ? pr : (pr == 2 ? 1 : 0);
+              const int pb = (NB == 1) ? 0 : (pr == 1 ? 1 : 0);
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              const uint64_t da = umma_smem_desc(sa + pa * A_PLANE_BYTES + k * a_kadv, a_lbo, 1024u);
-              const uint64_t db = umma_smem_desc(sb + pb * C::B_PLANE_BYTES + k * b_kadv, b_lbo, 1024u);
-              umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || pr > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                const uint64_t da = sa + ((pa * A_PLANE_BYTES + k * a_kadv) >> 4);
+                const uint64_t db = sb + ((pb * C::B_PLANE_BYTES + k * b_kadv) >> 4);
+                umma_bf16(d_tmem, da, db, idesc, (pr > 0 || k > 0) ? 1u : first);
+              }
             }
+            umma_commit(&empty_bar[stage]);     // frees this smem stage once the MMAs have read it
           }
-          umma_commit(&empty_bar[stage]);       // frees this smem stage once the MMAs have read it
+          __syncwarp();
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[buf]);           // accumulator complete -> epilogue
+        if (elect_one()) umma_commit(&tmem_full[buf]);   // accumulator complete -> epilogue
+        __syncwarp();
       }
     }
   } else {
@@ -248,20 +259,22 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // path -- one unit ahead: as soon as the lanes have copied their row to registers the next unit's load is issued, for
       // an item's first unit before its accumulator is even complete.  Planes leave through 64-byte-swizzled staging and TMA.
       constexpr int NU = BN / 32;
-      uint8_t* my_raw = smem_epi + ew * EPI_WARP_BYTES;          // 4 KB: y tile in (128B-swizzled rows of 32 fp32)
-      uint8_t* my_out = my_raw + 4096;                            // 2 KB hi + 2 KB lo: 32 rows x 64 B, 64B swizzle
+      // y tile in: 2 x 4 KB (128B-swizzled rows of 32 fp32), alternating, so the TMA write of unit n+1 never lands in the
+      // buffer whose ld.shared reads of unit n may still be in flight (observed as stale last chunks with one buffer)
+      uint8_t* my_raw = smem_epi + ew * EPI_WARP_BYTES;
+      uint8_t* my_out = my_raw + 8192;                            // 2 KB hi + 2 KB lo: 32 rows x 64 B, 64B swizzle
       uint64_t* my_bar = &raw_bar[ew];
       const QvQParams yq = qv_load_qparams(p.ep_scale, p.ep_zp, p.ep_qmin, p.ep_qmax);
       const bool use_lut = p.ep_gelu != 0;
-      auto issue_raw = [&](int item, int u) {                     // lane 0 only
+      auto issue_raw = [&](int item, int u, uint32_t slot) {      // lane 0 only
         const int n_blk = item % p.tiles_n;
         const int m_blk = (item / p.tiles_n) % p.tiles_m;
         mbar_expect_tx(my_bar, 4096);
-        tma_load_3d(my_raw, &map_y, my_bar, n_blk * BN + u * 32, m_blk * BM + q * 32, 0);
+        tma_load_3d(my_raw + slot * 4096u, &map_y, my_bar, n_blk * BN + u * 32, m_blk * BM + q * 32, 0);
       };
-      uint32_t raw_phase = 0;
+      uint32_t raw_phase = 0;             // also the slot of the tile being waited for (loads alternate slots)
       int local = 0;
-      if (static_cast<int>(blockIdx.x) < num_items && lane == 0) issue_raw(blockIdx.x, par);
+      if (static_cast<int>(blockIdx.x) < num_items && lane == 0) issue_raw(blockIdx.x, par, 0);
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
         const int n_blk = item % p.tiles_n;
         const int m_blk = (item / p.tiles_n) % p.tiles_m;
@@ -274,10 +287,9 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int u = par; u < NU; u += 2) {
           // ---- this unit's y values: smem -> registers, then hand the buffer to the next unit's load ----
           mbar_wait(my_bar, raw_phase);
-          raw_phase ^= 1;
           float4 yv[8];
           {
-            const uint32_t srow = smem_u32(my_raw) + lane * 128;
+            const uint32_t srow = smem_u32(my_raw) + raw_phase * 4096u + lane * 128;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const uint32_t addr = srow + (static_cast<uint32_t>(j ^ (lane & 7)) << 4);
@@ -285,11 +297,12 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                            : "r"(addr) : "memory");
             }
           }
+          raw_phase ^= 1;
           __syncwarp();
           const bool last = u + 2 >= NU;
           if (lane == 0) {
-            if (!last) issue_raw(item, u + 2);
-            else if (item + static_cast<int>(gridDim.x) < num_items) issue_raw(item + gridDim.x, par);
+            if (!last) issue_raw(item, u + 2, raw_phase);
+            else if (item + static_cast<int>(gridDim.x) < num_items) issue_raw(item + gridDim.x, par, raw_phase);
           }
           if (!acc_ready) {
             mbar_wait(&tmem_full[buf], use & 1);

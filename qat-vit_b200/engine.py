@@ -620,11 +620,12 @@ class StudentEngine:
                 self._wgrad(ql["proj"], self.gpD, self.op[l], M, PAIRS_FP32)
                 if self.fused_gp:   # ... with qkv's backward prologue applied on the way out
                     part = self._part(self.slabs_attn, 3 * D)
-                    ops.attn_bwd_gp(self.qkvc[l], ql["qkv"].afq.scale, self.g_op, self.lse[l], B, T, H, d.attn_scale,
+                    ops.attn_bwd_gp(self.qkvc[l], ql["qkv"].afq.scale, self.op[l], self.g_op, self.lse[l], B, T, H, d.attn_scale,
                                     self.qkv_raw[l], ql["qkv"].afq.q, ql["qkv"].wscale_vec, self.gp3, part)
                     ops.colsum_reduce(part, self.slabs_attn, 3 * D, self._grad(ql["qkv"].bias))
                 else:
-                    ops.attn_bwd(self.qkvc[l], ql["qkv"].afq.scale, self.g_op, self.lse[l], B, T, H, d.attn_scale, self.g_qkv)
+                    ops.attn_bwd(self.qkvc[l], ql["qkv"].afq.scale, self.op[l], self.g_op, self.lse[l], B, T, H, d.attn_scale,
+                                 self.g_qkv)
             else:
                 self._dgrad(ql["proj"], self.gpD, M, self.g_o)
                 self._wgrad(ql["proj"], self.gpD, self.op[l], M, PAIRS_FP32)

@@ -372,26 +372,33 @@ def attn_fwd(qkv_planes, B, T, H, scale, out_planes, qk_scale=None, v_scale=None
     return out_planes if out_planes is not None else out_f32
 
 
-def attn_bwd(qkv_codes, qscale, do_planes, lse, B, T, H, scale, g_qkv):
-    """Fused attention backward on integer codes: g_qkv fp32 [B*T, 3*H*64] <- dQ | dK | dV (include/qatvit_b200.h: qv_attn_bwd)."""
-    if qkv_codes.dim() != 3 or qkv_codes.shape[0] != 1 or do_planes.dim() != 3 or do_planes.shape[0] != 2:
-        raise RuntimeError("qatvit_b200: attn_bwd takes a [1, tokens, 3D] code plane and [2, tokens, D] gradient planes")
+def _check_attn_bwd_planes(qkv_codes, o_planes, do_planes):
+    if qkv_codes.dim() != 3 or qkv_codes.shape[0] != 1 or do_planes.dim() != 3 or do_planes.shape[0] != 2 or \
+            o_planes.dim() != 3 or o_planes.shape[0] != 2:
+        raise RuntimeError("qatvit_b200: attn_bwd takes a [1, tokens, 3D] code plane and [2, tokens, D] output / gradient planes")
+
+
+def attn_bwd(qkv_codes, qscale, o_planes, do_planes, lse, B, T, H, scale, g_qkv):
+    """Fused attention backward on integer codes: g_qkv fp32 [B*T, 3*H*64] <- dQ | dK | dV (include/qatvit_b200.h: qv_attn_bwd).
+    o_planes: the forward's output planes (attn_fwd out_planes)."""
+    _check_attn_bwd_planes(qkv_codes, o_planes, do_planes)
     check(_lib.lib().qv_attn_bwd(_p(qkv_codes, torch.bfloat16, "qkv_codes"), qkv_codes.stride(1), _p(qscale, torch.float32),
+                                 _p(o_planes, torch.bfloat16, "o_planes"), o_planes.stride(0), o_planes.stride(1),
                                  _p(do_planes, torch.bfloat16, "do_planes"), do_planes.stride(0), do_planes.stride(1),
                                  _p(lse, torch.float32, "lse"), B, T, H, float(scale), _p(g_qkv, torch.float32, "g_qkv"),
                                  _stream()), "attn_bwd")
     return g_qkv
 
 
-def attn_bwd_gp(qkv_codes, qscale, do_planes, lse, B, T, H, scale, y_raw, fq, w_scale, gp_planes, colsum):
+def attn_bwd_gp(qkv_codes, qscale, o_planes, do_planes, lse, B, T, H, scale, y_raw, fq, w_scale, gp_planes, colsum):
     """attn_bwd with the qkv Linear's gradient prologue fused: gp_planes bf16 [2, B*T, 3*H*64] <- (dQ|dK|dV) * STEmask(y_raw) *
     w_scale; colsum fp32 [B * ceil(T/128) * 4, 3*H*64] <- per-slab bias-grad partials (include/qatvit_b200.h: qv_attn_bwd_gp)."""
-    if qkv_codes.dim() != 3 or qkv_codes.shape[0] != 1 or do_planes.dim() != 3 or do_planes.shape[0] != 2:
-        raise RuntimeError("qatvit_b200: attn_bwd takes a [1, tokens, 3D] code plane and [2, tokens, D] gradient planes")
+    _check_attn_bwd_planes(qkv_codes, o_planes, do_planes)
     nslab = B * (-(-T // 128)) * 4
     if colsum.numel() < nslab * 3 * H * 64 or gp_planes.dim() != 3 or gp_planes.stride(1) != 3 * H * 64:
         raise RuntimeError("qatvit_b200: attn_bwd_gp needs dense [2, B*T, 3D] planes and a [B*ceil(T/128)*4, 3D] colsum buffer")
     check(_lib.lib().qv_attn_bwd_gp(_p(qkv_codes, torch.bfloat16, "qkv_codes"), qkv_codes.stride(1), _p(qscale, torch.float32),
+                                    _p(o_planes, torch.bfloat16, "o_planes"), o_planes.stride(0), o_planes.stride(1),
                                     _p(do_planes, torch.bfloat16, "do_planes"), do_planes.stride(0), do_planes.stride(1),
                                     _p(lse, torch.float32, "lse"), B, T, H, float(scale), _p(y_raw, torch.float32, "y_raw"),
                                     _p(fq[0], torch.float32), _p(fq[1], torch.int32), int(fq[2]), int(fq[3]),

@@ -74,7 +74,7 @@ def test_attn_bwd_integer_codes(cuda_dev, B, H, T):
     dOp = ops.split_planes(dO.to(cuda_dev))
     g_qkv = torch.full((B * T, 3 * D), float("nan"), device=cuda_dev)
     for _ in range(2):
-        ops.attn_bwd(cp, s, dOp, lse, B, T, H, 0.125, g_qkv)
+        ops.attn_bwd(cp, s, out, dOp, lse, B, T, H, 0.125, g_qkv)
     torch.cuda.synchronize()
     x = (codes.double() * sval).requires_grad_(True)
     xv = x.view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)

@@ -38,7 +38,7 @@ def test_attn_bwd_gp_matches_unfused(cuda_dev, B, H, T):
     wsc = (torch.rand(3 * D, generator=g) * 0.02 + 0.001).to(dev)
     # unfused: fp32 dQ|dK|dV -> gp_planes -> colsum_reduce
     g_qkv = torch.empty(B * T, 3 * D, device=dev)
-    ops.attn_bwd(cp, s, dOp, lse, B, T, H, 0.125, g_qkv)
+    ops.attn_bwd(cp, s, out, dOp, lse, B, T, H, 0.125, g_qkv)
     rpb = 64
     nblk = -(-(B * T) // rpb)
     part = torch.empty(nblk, 3 * D, device=dev)
@@ -51,7 +51,7 @@ def test_attn_bwd_gp_matches_unfused(cuda_dev, B, H, T):
     nslab = B * (-(-T // 128)) * 4
     slab = torch.full((nslab, 3 * D), float("nan"), device=dev)
     for _ in range(2):
-        assert ops.attn_bwd_gp(cp, s, dOp, lse, B, T, H, 0.125, y_raw, fq, wsc, planes, slab) == nslab
+        assert ops.attn_bwd_gp(cp, s, out, dOp, lse, B, T, H, 0.125, y_raw, fq, wsc, planes, slab) == nslab
     bias = torch.empty(3 * D, device=dev)
     ops.colsum_reduce(slab, nslab, 3 * D, bias)
     torch.cuda.synchronize()

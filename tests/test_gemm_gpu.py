@@ -164,3 +164,30 @@ def test_gemm_gradient_planes_epilogue(cuda_dev, M, N, K, gelu, qrange):
     assert torch.equal(out_planes.view(torch.int16), ref_planes.view(torch.int16))
     assert (ref_planes.float().abs().sum(0) == 0).float().mean() > 0.02      # the STE mask really zeroed something
     assert _rel(bias, ref_bias) < 1e-5
+
+
+def test_gemm_gradient_planes_epilogue_is_race_free(cuda_dev):
+    """Regression: with a single y staging buffer per warp the TMA write of the next unit could land while ld.shared reads of
+    the current unit were still in flight (a few stale 16-byte chunks in ~3 % of launches).  100 launches must all match."""
+    from qatvit_b200 import ops
+    from qatvit_b200.ops import Op, PAIRS_EXACT_B
+    dev = cuda_dev
+    M, N, K = 1576, 384, 384
+    g = torch.Generator().manual_seed(1)
+    a = torch.randn(M, K, generator=g).to(dev)
+    b = _codes((N, K), dev, g)
+    ap, bp = _planes(a), b.bfloat16()[None].contiguous()
+    y = (torch.randn(M, N, generator=g) * 2.0).to(dev)
+    fq = (torch.tensor([4.0 / 127], device=dev), torch.tensor([63], dtype=torch.int32, device=dev), 0, 127)
+    wsc = (torch.rand(N, generator=g) * 0.02 + 0.001).to(dev)
+    gmat = ops.gemm(Op.full(ap), Op.full(bp), M, N, K, PAIRS_EXACT_B)
+    part = torch.empty(-(-M // 64), N, device=dev)
+    ref = torch.empty(2, M, N, dtype=torch.bfloat16, device=dev)
+    ops.gp_planes(gmat, y, fq, wsc, True, False, M, N, ref, part, 64)
+    slab = torch.empty(-(-M // 32), N, device=dev)
+    outs = [torch.empty(2, M, N, dtype=torch.bfloat16, device=dev) for _ in range(100)]
+    for out in outs:
+        ops.gemm(Op.full(ap), Op.full(bp), M, N, K, PAIRS_EXACT_B, out_planes=out, col_scale=wsc, grad_of=(y, fq, False, slab))
+    torch.cuda.synchronize()
+    bad = sum(0 if torch.equal(o.view(torch.int16), ref.view(torch.int16)) else 1 for o in outs)
+    assert bad == 0, f"{bad} of 100 launches differ"
