@@ -55,6 +55,19 @@ int qv_fq_apply(const float* x, int64_t n, const float* scale, const int32_t* ze
                 const int64_t* fake_quant_enabled, int32_t qmin, int32_t qmax, float* y, uint8_t* mask,
                 void* stream);
 
+/* Grouped per-channel weight fake-quant: every weight of the model in ONE launch (same arithmetic as qv_fq_weight with
+ * per_channel = 1; outputs codes, codes_t and mask are all required).  `descs` is a DEVICE array of n_desc descriptors sorted by
+ * block_start; weight i owns blocks [block_start_i, block_start_i + ceil(rows_i / 16)), total_blocks in all; rows must be
+ * 16-byte aligned (cols % 4 == 0) and rows_i % 8 == 0 keeps the transposed stores aligned; max_cols = the largest cols. */
+typedef struct qv_fqw_desc {
+  const float* w; float* min_val; float* max_val; float* scale; int32_t* zero_point;
+  const int64_t* observer_enabled; const int64_t* fake_quant_enabled;
+  uint8_t* mask; uint16_t* codes; uint16_t* codes_t;
+  int32_t rows, cols, block_start, reserved;
+} qv_fqw_desc;
+int qv_fq_weight_grouped(const qv_fqw_desc* descs_device, int32_t n_desc, int32_t total_blocks, int32_t max_cols,
+                         float averaging_const, int32_t qmin, int32_t qmax, int32_t symmetric, void* stream);
+
 /* Weight flavour, one launch: per-row (per_channel=1, ch_axis 0) or whole-tensor (per_channel=0; two
  * internal phases) min/max -> EMA -> qparams -> fake-quant of W[rows, cols].
  * Outputs (each may be NULL): y fp32 [rows,cols]; mask uint8; codes bf16 [rows,cols] holding the

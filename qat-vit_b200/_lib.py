@@ -41,6 +41,16 @@ class Out(ctypes.Structure):
     ]
 
 
+class FqwDesc(ctypes.Structure):
+    """struct qv_fqw_desc (include/qatvit_b200.h)."""
+    _fields_ = [
+        ("w", c_void_p), ("min_val", c_void_p), ("max_val", c_void_p), ("scale", c_void_p), ("zero_point", c_void_p),
+        ("observer_enabled", c_void_p), ("fake_quant_enabled", c_void_p),
+        ("mask", c_void_p), ("codes", c_void_p), ("codes_t", c_void_p),
+        ("rows", c_int32), ("cols", c_int32), ("block_start", c_int32), ("reserved", c_int32),
+    ]
+
+
 class GemmArgs(ctypes.Structure):
     """struct qv_gemm_args (include/qatvit_b200.h)."""
     _fields_ = [
@@ -70,6 +80,7 @@ _SIGNATURES = {
     "qv_fq_apply": (c_int, [_P, c_int64, _P, _P, _P, c_int32, c_int32, _P, _P, _P]),
     "qv_fq_weight": (c_int, [_P, c_int64, c_int64, c_int32, _P, _P, _P, _P, _P, _P, c_float, c_int32, c_int32,
                              c_int32, _P, _P, _P, _P, _P, _P]),
+    "qv_fq_weight_grouped": (c_int, [_P, c_int32, c_int32, c_int32, c_float, c_int32, c_int32, c_int32, _P]),
     "qv_fq_bwd": (c_int, [_P, _P, c_int64, _P, _P]),
     "qv_split_planes": (c_int, [_P, c_int64, _P, _P, _P]),
     "qv_kd_ce_loss": (c_int, [_P, _P, _P, c_int32, c_int32, c_float, c_float, c_float, _P, _P, c_int32, c_int32,

@@ -390,8 +390,12 @@ int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap&
 // TMEM: buffer b in {0,1}: S_b [128 b, +64) | R_b [128 b + 64, +64) ;  ACC0 [256,320) (dQ / dV) ;  ACC1 [320,384) (dK).
 // Warps: 0 TMA, 1 MMA, 2-9 compute (two warps per TMEM lane quarter, one 32-column piece of the chunk each).
 // ====================================================================================================================
-constexpr int BW_TILE_BYTES = 256 * HD * 2;     // 32 KB: up to 256 token rows x 64 bf16 (rows >= T zero-filled by TMA)
-constexpr int BW_SMEM_BYTES = 5 * BW_TILE_BYTES + 4096 /*lse, delta*/ + 1024 /*align*/ + 256 /*barriers*/;
+// 28 KB tiles: 224 token rows x 64 bf16 (T <= 224; rows >= T zero-filled by TMA).  The second 128-row MMA tile reads 32 rows
+// past its end (the next tile's head): those lanes are tokens >= 224 > T, whose results are never stored.
+constexpr int BW_TILE_ROWS = 224;
+constexpr int BW_TILE_BYTES = BW_TILE_ROWS * HD * 2;
+constexpr int BW_STAGE_BYTES = 8 * 2 * 4096;    // per compute warp: two 4 KB staging buffers (y tile in, gradient tile out)
+constexpr int BW_SMEM_BYTES = 5 * BW_TILE_BYTES + 4096 /*lse, delta*/ + BW_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr uint32_t BW_ACC0_COL = 256, BW_ACC1_COL = 320;
 
 struct AttnBwdParams {
@@ -433,6 +437,7 @@ __device__ __forceinline__ float bf16hi_f(uint32_t w) { return __uint_as_float(w
 template <bool FUSED>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
+                   const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_o,
                    const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -443,7 +448,8 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
   uint8_t* sDOl = sDOh + BW_TILE_BYTES;
   float* lse2_s = reinterpret_cast<float*>(sDOl + BW_TILE_BYTES);   // [256] lse * log2(e)
   float* delta_s = lse2_s + 256;                                     // [256] (dO . O) / s
-  uint64_t* bars = reinterpret_cast<uint64_t*>(delta_s + 768);
+  uint8_t* stage_s = reinterpret_cast<uint8_t*>(delta_s + 768);    // [8 warps][2][4 KB], 1024-byte aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_s + BW_STAGE_BYTES);
   uint64_t* ld_full = bars + 0;
   uint64_t* ld_empty = bars + 1;
   uint64_t* mma1_done = bars + 2;   // [2]
@@ -451,6 +457,7 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
   uint64_t* acc_done = bars + 6;
   uint64_t* epi_done = bars + 7;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* y_bar = bars + 9;       // [8 warps][2]: y tile landed in staging buffer k of compute warp w
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -472,6 +479,11 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
     }
     mbar_init(acc_done, 1);
     mbar_init(epi_done, 256);
+    if constexpr (FUSED) {
+      prefetch_tensormap(&map_y);
+      for (int w = 0; w < 16; ++w) mbar_init(&y_bar[w], 1);
+    }
+    prefetch_tensormap(&map_o);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -622,52 +634,84 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
     QvQParams yq;
     if constexpr (FUSED) yq = qv_load_qparams(p.y_scale, p.y_zp, p.qmin, p.qmax);
     const int D3 = 3 * D;
-    // FUSED output of one 32-row x 32-column block: lane = token `tok` of image b, columns col .. col+31 of the [., 3D] row
-    auto load_y = [&](float4 (&yv)[8], int b, int tok, int col) {
-      const float4* yp = reinterpret_cast<const float4*>(p.y_raw + (static_cast<int64_t>(b) * p.T + tok) * D3 + col);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) yv[j] = (tok < p.T) ? __ldg(yp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    // Output of one 32-row x 32-column block (this warp's TMEM lanes x its column half of the 64-wide accumulator), staged
+    // through shared memory so that global traffic is whole 128-byte lines moved by TMA: the y tile (FUSED: the qkv Linear's
+    // raw output under these gradients) comes IN through buffer k, the lanes take their rows to registers, and the finished
+    // tile (fp32, or bf16 hi/lo planes) leaves through the same buffer.  Rows >= T are zero-filled on load and clipped on
+    // store by the per-image tensor maps.
+    uint8_t* my_stage = stage_s + cw * 8192;
+    uint64_t* my_ybar = y_bar + cw * 2;
+    uint32_t yph0 = 0, yph1 = 0;
+    auto request_y = [&](int k, int b, int tok0, int col) {       // lane 0, after tma_store_wait_read<0>()
+      mbar_expect_tx(&my_ybar[k], 4096);
+      tma_load_3d(my_stage + k * 4096, &map_y, &my_ybar[k], col, tok0, b);
     };
-    auto emit = [&](const uint32_t (&o)[32], const float4 (&yv)[8], float mult, int b, int tok, int col, int slab) {
-      const bool ok = tok < p.T;
-      float gq[32];
-      __nv_bfloat16* dst = p.gp + (static_cast<int64_t>(b) * p.T + tok) * D3 + col;
+    auto emit = [&](const uint32_t (&o)[32], int k, uint32_t yph, float mult, int b, int tok0, int col, int slab) {
+      uint8_t* buf = my_stage + k * 4096;
+      const bool ok = tok0 + lane < p.T;
+      if constexpr (FUSED) {
+        mbar_wait(&my_ybar[k], yph);
+        float4 yv[8];
+        const uint32_t srow = smem_u32(buf) + lane * 128;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {                                // 8 columns per step: one 16-byte store per plane
-        uint32_t hi[4], lo[4];
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t addr = srow + (static_cast<uint32_t>(j ^ (lane & 7)) << 4);
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(yv[j].x), "=f"(yv[j].y), "=f"(yv[j].z), "=f"(yv[j].w)
+                       : "r"(addr) : "memory");
+        }
+        float gq[32];
+        uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int hlf = 0; hlf < 2; ++hlf) {
-          const float4 ws = __ldg(reinterpret_cast<const float4*>(p.w_scale + col) + 2 * j + hlf);
-          const float4 y4 = yv[2 * j + hlf];
-          const float yy[4] = {y4.x, y4.y, y4.z, y4.w};
+        for (int j = 0; j < 8; ++j) {
+          const float4 ws = __ldg(reinterpret_cast<const float4*>(p.w_scale + col) + j);
+          const float yy[4] = {yv[j].x, yv[j].y, yv[j].z, yv[j].w};
           const float wv[4] = {ws.x, ws.y, ws.z, ws.w};
           float a[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float r = __fadd_rn(rintf(__fmul_rn(yy[e], yq.inv)), yq.zp);
             const bool in = (yq.qmin <= r) && (r <= yq.qmax);
-            const float f = (ok && in) ? __uint_as_float(o[8 * j + 4 * hlf + e]) * mult : 0.f;
-            gq[8 * j + 4 * hlf + e] = f;
+            const float f = (ok && in) ? __uint_as_float(o[4 * j + e]) * mult : 0.f;
+            gq[4 * j + e] = f;
             a[e] = f * wv[e];
           }
-          split_pack2(a[0], a[1], hi[2 * hlf], lo[2 * hlf]);
-          split_pack2(a[2], a[3], hi[2 * hlf + 1], lo[2 * hlf + 1]);
+          split_pack2(a[0], a[1], hi[2 * j], lo[2 * j]);
+          split_pack2(a[2], a[3], hi[2 * j + 1], lo[2 * j + 1]);
         }
-        if (ok) {
-          *reinterpret_cast<uint4*>(dst + 8 * j) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(dst + p.gp_plane_stride + 8 * j) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        }
-      }
-      const float cs = qv_warp_colsum32(gq, lane);
-      p.colsum[static_cast<int64_t>(slab) * D3 + col + lane] = cs;
-    };
-    auto store_f32 = [&](const uint32_t (&o)[32], float mult, int b, int tok, int col) {
-      if (tok < p.T) {
-        float* dst = p.g_qkv + (static_cast<int64_t>(b) * p.T + tok) * D3 + col;
+        __syncwarp();                                             // every lane holds its y row: the buffer may be overwritten
+        const uint32_t orow = smem_u32(buf) + lane * 64;          // planes: 32 rows x 64 B (hi) | + 2 KB (lo), 64B swizzle
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(__uint_as_float(o[4 * j]) * mult, __uint_as_float(o[4 * j + 1]) * mult,
-                                                                __uint_as_float(o[4 * j + 2]) * mult, __uint_as_float(o[4 * j + 3]) * mult);
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t sw = (static_cast<uint32_t>(j ^ ((lane >> 1) & 3)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(orow + sw), "r"(hi[4 * j]), "r"(hi[4 * j + 1]),
+                       "r"(hi[4 * j + 2]), "r"(hi[4 * j + 3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(orow + 2048 + sw), "r"(lo[4 * j]), "r"(lo[4 * j + 1]),
+                       "r"(lo[4 * j + 2]), "r"(lo[4 * j + 3]) : "memory");
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(&map_o, buf, col, tok0, b, 0);
+          tma_store_4d(&map_o, buf + 2048, col, tok0, b, 1);
+          tma_store_commit();
+        }
+        const float cs = qv_warp_colsum32(gq, lane);
+        p.colsum[static_cast<int64_t>(slab) * D3 + col + lane] = cs;
+      } else {
+        const uint32_t srow = smem_u32(buf) + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t addr = srow + (static_cast<uint32_t>(j ^ (lane & 7)) << 4);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(__uint_as_float(o[4 * j]) * mult),
+                       "f"(__uint_as_float(o[4 * j + 1]) * mult), "f"(__uint_as_float(o[4 * j + 2]) * mult),
+                       "f"(__uint_as_float(o[4 * j + 3]) * mult) : "memory");
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&map_o, buf, col, tok0, b);
+          tma_store_commit();
+        }
       }
     };
     uint32_t st = 0, nsp = 0;
@@ -722,6 +766,16 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         const int tile = pass_a ? sub : sub - mt;
         const int tok = tile * 128 + row;                         // query (pass A) / key (pass B) of this lane
         const float Li = lse2_s[tok & 255], di = delta_s[tok & 255];
+        const int tok0 = tile * 128 + q * 32;                     // first token of this warp's 32-row slab
+        const int ccol = h * HD + par * 32;
+        if (lane == 0) {
+          tma_store_wait_read<0>();                               // the previous sub-pass's tiles have left the staging buffers
+          if constexpr (FUSED) {                                  // y tiles under this sub-pass's outputs: in flight during the chunks
+            request_y(0, b, tok0, (pass_a ? 0 : 2 * D) + ccol);
+            if (!pass_a) request_y(1, b, tok0, D + ccol);
+          }
+        }
+        __syncwarp();
         for (int c = 0; c < nch; ++c, ++st) {
           const uint32_t buf = st & 1;
           const uint32_t S = t0 + buf * 128u + par * 32u, R = S + 64u;
@@ -771,9 +825,6 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         }
         // ---- sub-pass output: this warp stores columns par*32 .. par*32+31 of its 32 rows ----
         const int slab = (b * mt + tile) * 4 + q;
-        const int ccol = h * HD + par * 32;
-        float4 yv[FUSED ? 8 : 1];
-        if constexpr (FUSED) load_y(yv, b, tok, (pass_a ? 0 : 2 * D) + ccol);       // in flight while the last MMAs finish
         mbar_wait(acc_done, nsp & 1);
         tc_fence_after();
         DBG(1, 15);
@@ -783,26 +834,23 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         if (pass_a) {
           tc_fence_before();
           mbar_arrive(epi_done);
-          if constexpr (FUSED) emit(o, yv, gscale, b, tok, ccol, slab);
-          else store_f32(o, gscale, b, tok, ccol);
+          emit(o, 0, yph0, gscale, b, tok0, ccol, slab);                             // dQ
+          yph0 ^= 1;
         } else {
           uint32_t o2[32];
           tmem_ld_32x32(t0 + BW_ACC1_COL + par * 32, o2);
           tmem_ld_wait();
           tc_fence_before();
           mbar_arrive(epi_done);
-          if constexpr (FUSED) {
-            emit(o, yv, 1.0f, b, tok, 2 * D + ccol, slab);                         // dV
-            load_y(yv, b, tok, D + ccol);
-            emit(o2, yv, gscale, b, tok, D + ccol, slab);                          // dK
-          } else {
-            store_f32(o, 1.0f, b, tok, 2 * D + ccol);
-            store_f32(o2, gscale, b, tok, D + ccol);
-          }
+          emit(o, 0, yph0, 1.0f, b, tok0, 2 * D + ccol, slab);                       // dV
+          emit(o2, 1, yph1, gscale, b, tok0, D + ccol, slab);                        // dK
+          yph0 ^= 1;
+          yph1 ^= 1;
         }
         DBG(1, 16);
       }
     }
+    if (lane == 0) tma_store_wait_read<0>();
   }
 
   tc_fence_before();
@@ -890,11 +938,23 @@ int attn_bwd_impl(const uint16_t* qkv_codes, int64_t ld, const float* qscale, co
   op.ptr = qkv_codes; op.ld = ld; op.plane_stride = 0; op.rows = T; op.cols = 3LL * H * HD;
   op.nb = B; op.batch_stride = static_cast<int64_t>(T) * ld;
   CUtensorMap mq, md;
-  int rc = make_map(&mq, op, 1, 256);
+  int rc = make_map(&mq, op, 1, BW_TILE_ROWS);
   if (rc) return rc;
   op.ptr = do_planes; op.ld = do_ld; op.plane_stride = do_plane_stride; op.cols = static_cast<int64_t>(H) * HD;
   op.batch_stride = static_cast<int64_t>(T) * do_ld;
-  rc = make_map(&md, op, 2, 256);
+  rc = make_map(&md, op, 2, BW_TILE_ROWS);
+  if (rc) return rc;
+  // staging maps (per-image: rows >= T are zero-filled on load / clipped on store)
+  CUtensorMap my, mo;
+  const int64_t D3 = 3LL * H * HD;
+  if (fused) {
+    rc = make_out_map(&my, const_cast<float*>(fused->y_raw), D3, T, D3, B, static_cast<int64_t>(T) * D3);
+    if (rc) return rc;
+    rc = make_out_planes_map(&mo, fused->gp, D3, T, D3, B, static_cast<int64_t>(T) * D3, fused->gp_plane_stride, 32);
+  } else {
+    rc = make_out_map(&mo, g_qkv, D3, T, D3, B, static_cast<int64_t>(T) * D3);
+    my = mo;
+  }
   if (rc) return rc;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
@@ -907,8 +967,8 @@ int attn_bwd_impl(const uint16_t* qkv_codes, int64_t ld, const float* qscale, co
   const int items = B * H;
   const int sms = qv_num_sms();
   const int grid = items < sms ? items : sms;
-  if (fused) qv_attn_bwd_kernel<true><<<grid, AT_THREADS, BW_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(mq, md, ap);
-  else qv_attn_bwd_kernel<false><<<grid, AT_THREADS, BW_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(mq, md, ap);
+  if (fused) qv_attn_bwd_kernel<true><<<grid, AT_THREADS, BW_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(mq, md, my, mo, ap);
+  else qv_attn_bwd_kernel<false><<<grid, AT_THREADS, BW_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(mq, md, my, mo, ap);
   return qv_check_launch("qv_attn_bwd");
 }
 }  // namespace

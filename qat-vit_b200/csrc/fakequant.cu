@@ -8,6 +8,8 @@
 //   q = rint(x * (1/s)) + zp, clamp, (q - zp) * s.
 #include <stdio.h>
 
+#include <mutex>
+
 #include "qv_common.cuh"
 
 namespace {
@@ -340,6 +342,126 @@ extern "C" int qv_fq_bwd(const float* gy, const uint8_t* mask, int64_t n, float*
   QV_REQUIRE(qv_num_sms() > 0, QV_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
   qv_fq_bwd_kernel<<<ew_blocks(n >> 2), 256, 0, static_cast<cudaStream_t>(stream)>>>(gy, mask, n, gx);
   return qv_check_launch("qv_fq_bwd");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Grouped per-channel weight fake-quant: ALL fake-quantised weights of the model in one launch (the reference runs the
+// observer + fake-quant of each of its 50 weights as ~4 launches apiece).  A block takes FQW_ROWS consecutive output
+// channels of one weight (descriptor table in device memory, built once by the host side): a warp owns two rows at a
+// time -- row min/max (float4 reads), EMA + qparams by one lane, quantise on the second (L1-resident) read -> codes
+// (row-major), STE mask, and the codes staged in shared memory so that the TRANSPOSED copy (the dgrad operand) leaves as
+// 32-byte runs instead of one scattered 2-byte store per element.
+// ------------------------------------------------------------------------------------------------
+constexpr int FQW_ROWS = 16;
+
+__global__ void __launch_bounds__(256) qv_fq_weight_grouped_kernel(const qv_fqw_desc* __restrict__ descs, int n_desc, float c,
+                                                                   int qmin, int qmax, int symmetric) {
+  extern __shared__ __nv_bfloat16 s_codes[];       // [FQW_ROWS][cols + 8] (row pitch keeps the column reads conflict-light)
+  __shared__ int s_d;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = n_desc - 1;
+    while (lo < hi) {                               // last descriptor whose first block is <= blockIdx.x
+      const int mid = (lo + hi + 1) >> 1;
+      if (descs[mid].block_start <= static_cast<int>(blockIdx.x)) lo = mid; else hi = mid - 1;
+    }
+    s_d = lo;
+  }
+  __syncthreads();
+  const qv_fqw_desc d = descs[s_d];
+  const int r0 = (static_cast<int>(blockIdx.x) - d.block_start) * FQW_ROWS;
+  const int nrows = min(FQW_ROWS, d.rows - r0);
+  const int cols = d.cols, pitch = cols + 8;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool obs = (*d.observer_enabled != 0), fq = (*d.fake_quant_enabled != 0);
+  for (int rr = warp; rr < nrows; rr += 8) {
+    const int r = r0 + rr;
+    const float4* wr = reinterpret_cast<const float4*>(d.w + static_cast<int64_t>(r) * cols);
+    float sc, zpf;
+    if (obs) {
+      float mn = INFINITY, mx = -INFINITY;
+      for (int k = lane; k < cols / 4; k += 32) {
+        const float4 v = __ldg(wr + k);
+        mn = fminf(mn, fminf(fminf(v.x, v.y), fminf(v.z, v.w)));
+        mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+      }
+      mn = qv_warp_min(mn);
+      mx = qv_warp_max(mx);
+      if (lane == 0) {
+        const float rmin = qv_ema(d.min_val[r], mn, c), rmax = qv_ema(d.max_val[r], mx, c);
+        d.min_val[r] = rmin;
+        d.max_val[r] = rmax;
+        if (fq) {
+          float s_;
+          int32_t z_;
+          qv_choose_qparams(rmin, rmax, qmin, qmax, symmetric != 0, &s_, &z_);
+          d.scale[r] = s_;
+          d.zero_point[r] = z_;
+        }
+      }
+      __syncwarp();
+    }
+    if (lane == 0) { sc = d.scale[r]; zpf = static_cast<float>(d.zero_point[r]); }
+    sc = __shfl_sync(0xffffffffu, sc, 0);
+    zpf = __shfl_sync(0xffffffffu, zpf, 0);
+    QvQParams q;
+    q.scale = sc;
+    q.inv = __fdiv_rn(1.0f, sc);
+    q.zp = zpf;
+    q.qmin = static_cast<float>(qmin);
+    q.qmax = static_cast<float>(qmax);
+    for (int k = lane; k < cols / 4; k += 32) {
+      const float4 v = __ldg(wr + k);
+      const float a[4] = {v.x, v.y, v.z, v.w};
+      __nv_bfloat16 cb[4];
+      uint8_t mb[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        bool in = true;
+        float cc = a[j];                            // fake-quant disabled: the "code" plane carries the raw value (not used then)
+        if (fq) qv_fq(a[j], q, &in, &cc);
+        cb[j] = __float2bfloat16_rn(cc);
+        mb[j] = in ? 1 : 0;
+      }
+      const int64_t idx = static_cast<int64_t>(r) * cols + 4 * k;
+      *reinterpret_cast<uint2*>(d.codes + idx) = *reinterpret_cast<uint2*>(cb);
+      *reinterpret_cast<uchar4*>(d.mask + idx) = make_uchar4(mb[0], mb[1], mb[2], mb[3]);
+      *reinterpret_cast<uint2*>(s_codes + rr * pitch + 4 * k) = *reinterpret_cast<uint2*>(cb);
+    }
+  }
+  __syncthreads();
+  // transposed copy: codes_t[k][r0 .. r0 + nrows) -- 32 contiguous bytes per k when the block is full
+  if (nrows == FQW_ROWS) {
+    for (int k = threadIdx.x; k < cols; k += blockDim.x) {
+      __nv_bfloat16 v[FQW_ROWS];
+#pragma unroll
+      for (int rr = 0; rr < FQW_ROWS; ++rr) v[rr] = s_codes[rr * pitch + k];
+      uint4* dst = reinterpret_cast<uint4*>(d.codes_t + static_cast<int64_t>(k) * d.rows + r0);
+      dst[0] = *reinterpret_cast<uint4*>(v);
+      dst[1] = *reinterpret_cast<uint4*>(v + 8);
+    }
+  } else {
+    for (int k = threadIdx.x; k < cols; k += blockDim.x)
+      for (int rr = 0; rr < nrows; ++rr)
+        d.codes_t[static_cast<int64_t>(k) * d.rows + r0 + rr] = __bfloat16_as_ushort(s_codes[rr * pitch + k]);
+  }
+}
+
+extern "C" int qv_fq_weight_grouped(const qv_fqw_desc* descs_device, int32_t n_desc, int32_t total_blocks, int32_t max_cols,
+                                    float averaging_const, int32_t qmin, int32_t qmax, int32_t symmetric, void* stream) {
+  QV_REQUIRE(descs_device && n_desc > 0 && total_blocks > 0 && max_cols > 0 && max_cols % 4 == 0, QV_ERR_INVALID,
+             "bad fq_weight_grouped arguments (cols must be multiples of 4)");
+  QV_REQUIRE(qv_num_sms() > 0, QV_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  const size_t smem = static_cast<size_t>(FQW_ROWS) * (max_cols + 8) * sizeof(__nv_bfloat16);
+  QV_REQUIRE(smem <= 200 * 1024, QV_ERR_UNSUPPORTED, "fq_weight_grouped: rows of %d elements do not fit the staging tile", max_cols);
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(qv_fq_weight_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  });
+  QV_REQUIRE(attr_err == cudaSuccess, QV_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+  qv_fq_weight_grouped_kernel<<<static_cast<unsigned>(total_blocks), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      descs_device, n_desc, averaging_const, qmin, qmax, symmetric);
+  return qv_check_launch("qv_fq_weight_grouped");
 }
 
 extern "C" int qv_fq_weight(const float* w, int64_t rows, int64_t cols, int32_t per_channel,

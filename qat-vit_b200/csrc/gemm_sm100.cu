@@ -192,17 +192,15 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    // The whole warp walks the tile / k-block schedule (barrier waits included) and ONE elected lane issues the MMAs and
-    // commits.  With warp-uniform control flow and descriptors formed as "stage base + compile-time offset", ptxas keeps the
-    // operands in uniform registers; under an `if (lane == 0)` region every tcgen05.mma paid an R2UR + ELECT waterfall loop
-    // (~90 cycles of issue per instruction -- as long as a 128 x 192 x 16 MMA takes to execute).
-    {
+    // (A whole-warp walk with an elected issuing lane -- which keeps operands in uniform registers and removed a per-MMA
+    // R2UR/ELECT waterfall in the attention kernels, where N = 64 instructions are issue-bound -- measured 3-4 % SLOWER here:
+    // a 128 x 192 x 16 MMA executes for as long as its issue sequence takes, and 32 polling lanes steal issue slots from the
+    // two epilogue warps sharing the sub-partition.)
+    if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
       constexpr uint32_t a_lbo = A_MN ? 8192u : 16u, b_lbo = B_MN ? 8192u : 16u;
       constexpr uint32_t a_kadv = A_MN ? (UMMA_K * 128u) : (UMMA_K * 2u);   // bytes per 16-deep k step
       constexpr uint32_t b_kadv = B_MN ? (UMMA_K * 128u) : (UMMA_K * 2u);
-      const uint64_t desc_a0 = umma_smem_desc(smem_u32(smem), a_lbo, 1024u);                          // stage 0, plane 0
-      const uint64_t desc_b0 = umma_smem_desc(smem_u32(smem) + NA * A_PLANE_BYTES, b_lbo, 1024u);
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
@@ -218,29 +216,24 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t sa = desc_a0 + static_cast<uint64_t>(stage) * (C::STAGE_BYTES >> 4);
-          const uint64_t sb = desc_b0 + static_cast<uint64_t>(stage) * (C::STAGE_BYTES >> 4);
-          const uint32_t first = (kb > kb0) ? 1u : 0u;
-          if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t sb = sa + NA * A_PLANE_BYTES;
 #pragma unroll
-            for (int pr = 0; pr < C::NPAIRS; ++pr) {
-              // pair order: (0,0) [,(0,1)] [,(1,0)]  -- for NB == 1 the second pair is (1,0)
-              const int pa = (NB == 1) ? pr : (pr == 2 ? 1 : 0);
-              const int pb = (NB == 1) ? 0 : (pr == 1 ? 1 : 0);
+          for (int pr = 0; pr < C::NPAIRS; ++pr) {
+            // pair order: (0,0) [,(0,1)] [,(1,0)]  -- for NB == 1 the second pair is (1,0)
+            const int pa = (NB == 1) ? pr : (pr == 2 ? 1 : 0);
+            const int pb = (NB == 1) ? 0 : (pr == 1 ? 1 : 0);
 #pragma unroll
-              for (int k = 0; k < BK / UMMA_K; ++k) {
-                const uint64_t da = sa + ((pa * A_PLANE_BYTES + k * a_kadv) >> 4);
-                const uint64_t db = sb + ((pb * C::B_PLANE_BYTES + k * b_kadv) >> 4);
-                umma_bf16(d_tmem, da, db, idesc, (pr > 0 || k > 0) ? 1u : first);
-              }
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t da = umma_smem_desc(sa + pa * A_PLANE_BYTES + k * a_kadv, a_lbo, 1024u);
+              const uint64_t db = umma_smem_desc(sb + pb * C::B_PLANE_BYTES + k * b_kadv, b_lbo, 1024u);
+              umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || pr > 0 || k > 0) ? 1u : 0u);
             }
-            umma_commit(&empty_bar[stage]);     // frees this smem stage once the MMAs have read it
           }
-          __syncwarp();
+          umma_commit(&empty_bar[stage]);       // frees this smem stage once the MMAs have read it
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        if (elect_one()) umma_commit(&tmem_full[buf]);   // accumulator complete -> epilogue
-        __syncwarp();
+        umma_commit(&tmem_full[buf]);           // accumulator complete -> epilogue
       }
     }
   } else {
@@ -553,51 +546,6 @@ __global__ void qv_splitk_reduce_kernel(const float* __restrict__ ws, int splits
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-// fp32 output [nb][rows][ld] as a 3-D tensor (cols, rows, nb); store box = (32 cols = 128 B, 32 rows, 1), 128B swizzle.
-int make_out_map(CUtensorMap* m, float* ptr, int64_t cols, int64_t rows, int64_t ld, int64_t nb, int64_t bstride) {
-  EncodeTiledFn enc = get_encode();
-  QV_REQUIRE(enc != nullptr, QV_ERR_CUDA, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
-  QV_REQUIRE(ptr && qv_aligned16(ptr), QV_ERR_INVALID, "gemm output base must be a 16-byte aligned device pointer");
-  QV_REQUIRE(rows > 0 && cols > 0 && ld >= cols && ld % 4 == 0, QV_ERR_INVALID,
-             "gemm output row pitch must be >= cols and a multiple of 4 floats (got %lld)", (long long)ld);
-  if (nb < 1) nb = 1;
-  if (bstride <= 0) bstride = rows * ld;
-  QV_REQUIRE(bstride % 4 == 0, QV_ERR_INVALID, "gemm output batch stride must be a multiple of 4 floats");
-  cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(nb)};
-  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 4, static_cast<cuuint64_t>(bstride) * 4};
-  cuuint32_t box[3] = {32, 32, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  QV_REQUIRE(r == CUDA_SUCCESS, QV_ERR_CUDA, "cuTensorMapEncodeTiled(output) failed (%d)", (int)r);
-  return 0;
-}
-
-// bf16 hi/lo plane output [2][nb][rows][ld] as a 4-D tensor (cols, rows, nb, plane); store box = (64 cols = 128 B, 32 rows).
-// box_cols = 32: 64-byte rows, 64B swizzle (the gradient-planes epilogue works in 32-column units).
-int make_out_planes_map(CUtensorMap* m, void* ptr, int64_t cols, int64_t rows, int64_t ld, int64_t nb, int64_t bstride,
-                        int64_t pstride, int box_cols = 64) {
-  EncodeTiledFn enc = get_encode();
-  QV_REQUIRE(enc != nullptr, QV_ERR_CUDA, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
-  QV_REQUIRE(ptr && qv_aligned16(ptr), QV_ERR_INVALID, "gemm plane output base must be a 16-byte aligned device pointer");
-  QV_REQUIRE(rows > 0 && cols > 0 && ld >= cols && ld % 8 == 0, QV_ERR_INVALID,
-             "gemm plane output row pitch must be >= cols and a multiple of 8 bf16 (got %lld)", (long long)ld);
-  if (nb < 1) nb = 1;
-  if (bstride <= 0) bstride = rows * ld;
-  if (pstride <= 0) pstride = bstride * nb;
-  QV_REQUIRE(bstride % 8 == 0 && pstride % 8 == 0, QV_ERR_INVALID, "plane output batch / plane strides must be multiples of 8 bf16");
-  cuuint64_t dims[4] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(nb), 2};
-  cuuint64_t strides[3] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(bstride) * 2,
-                           static_cast<cuuint64_t>(pstride) * 2};
-  cuuint32_t box[4] = {static_cast<cuuint32_t>(box_cols), 32, 1, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  QV_REQUIRE(r == CUDA_SUCCESS, QV_ERR_CUDA, "cuTensorMapEncodeTiled(plane output) failed (%d)", (int)r);
-  return 0;
-}
-
 template <int BN, int NA, int NB, bool A_MN, bool B_MN, int EPI = 0>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const GemmKParams& kp, int grid,
            cudaStream_t st, const CUtensorMap* my = nullptr) {

@@ -307,6 +307,19 @@ class StudentEngine:
                                  fc1=_QLinear(blk.mlp.fc1, dev, self.acc[base + 2]), fc2=_QLinear(blk.mlp.fc2, dev, self.acc[base + 3])))
         self.head = _QLinear(vit.head, dev, self.acc[n_act - 1], small=True)
         self.all_linears = [self.conv] + [q for blk in self.lin for q in blk.values()] + [self.head]
+        # every per-channel weight fake-quant with the same qparams in ONE launch; the rest (per-tensor qnnpack weights, the
+        # 10-row head that keeps an fp32 fake-quantised copy) one by one
+        self._wgroup, self._wsingle = [], []
+        for ql in self.all_linears:
+            f = ql.wfq
+            same = not self._wgroup or (f.c, f.qmin, f.qmax, f.symmetric) == self._wgroup_key
+            if f.per_channel and not ql.small and ql.N % 8 == 0 and ql.K % 4 == 0 and same:
+                self._wgroup_key = (f.c, f.qmin, f.qmax, f.symmetric)
+                self._wgroup.append(ql)
+            else:
+                self._wsingle.append(ql)
+        self._wtable = None
+        self._wptrs = None
         self.ln_fq: List[FQRef] = []          # [norm1_0, norm2_0, norm1_1, ..., final norm] (observed-LN variant only)
         self.ln_acc = [self.acc[n_act + i] for i in range(n_ln)]
         if self.ln_obs:
@@ -471,14 +484,31 @@ class StudentEngine:
         else:
             self._linear_fwd(ql, a, M, out)
 
+    def quantize_weights(self) -> None:
+        """Observer + fake-quant of every weight (ref: weight_fake_quant inside each nnqat module's forward)."""
+        if self._wgroup:
+            # the descriptor table holds raw pointers: rebuild it whenever a weight's storage has moved (an optimizer that
+            # re-homes parameters into a flat arena, FusedClipAdamW, does that once after the engine is built)
+            ptrs = [ql.weight.data_ptr() for ql in self._wgroup]
+            if ptrs != self._wptrs:
+                self._wtable, self._wblocks, self._wmaxk = ops.fq_weight_group_table(
+                    [dict(w=ql.weight.detach().reshape(ql.N, ql.K), min_val=ql.wfq.min_val, max_val=ql.wfq.max_val,
+                          scale=ql.wfq.scale, zero_point=ql.wfq.zero_point, observer_enabled=ql.wfq.observer_enabled,
+                          fake_quant_enabled=ql.wfq.fake_quant_enabled, mask=ql.wmask, codes=ql.codes[0], codes_t=ql.codes_t[0])
+                     for ql in self._wgroup], self.dev)
+                self._wptrs = ptrs
+            c, qmin, qmax, sym = self._wgroup_key
+            ops.fq_weight_grouped(self._wtable, len(self._wgroup), self._wblocks, self._wmaxk, c, qmin, qmax, sym)
+        for ql in self._wsingle:
+            ql.quantize_weight()
+
     def forward(self, images: torch.Tensor, labels: torch.Tensor, teacher_logits: torch.Tensor) -> torch.Tensor:
         d, v = self.d, self.vit
         B, T, D, F, M, L = d.B, d.T, d.D, d.F, d.M, d.L
         if tuple(images.shape) != (B, d.in_ch, d.HW, d.HW):
             raise RuntimeError(f"student engine built for batch {B}, got {tuple(images.shape)}")
         ops.minmax_reset(self.acc)
-        for ql in self.all_linears:
-            ql.quantize_weight()
+        self.quantize_weights()
         # input fake-quant (QuantStub hook) fused into im2col; patch-embed conv as an exact-integer GEMM
         ops.minmax_accumulate(images, self.acc[0])
         self.fq_in.update_from(self.acc[0])

@@ -84,6 +84,44 @@ def fq_weight(w, per_channel, observer_enabled, fake_quant_enabled, min_val, max
                                   _p(scratch, torch.int32, "scratch"), _stream()), "fq_weight")
 
 
+FQW_ROWS = 16      # output channels per block of qv_fq_weight_grouped (csrc/fakequant.cu)
+
+
+def fq_weight_group_table(entries, device) -> Tuple[torch.Tensor, int, int]:
+    """Device descriptor table for fq_weight_grouped.  entries: dicts with w [N, K] fp32, min_val / max_val / scale fp32 [N],
+    zero_point int32 [N], observer_enabled / fake_quant_enabled int64 [1], mask uint8 [N, K], codes bf16 [N, K], codes_t bf16 [K, N].
+    -> (uint8 tensor holding the qv_fqw_desc array, total_blocks, max_cols).  The tensors must stay alive and in place."""
+    arr = (_lib.FqwDesc * len(entries))()
+    start, max_cols = 0, 0
+    for d, e in zip(arr, entries):
+        w = e["w"]
+        rows, cols = w.shape[0], w.numel() // w.shape[0]
+        if cols % 4 or rows % 8:
+            raise RuntimeError("qatvit_b200: grouped weight fake-quant needs cols % 4 == 0 and rows % 8 == 0")
+        d.w = _p(w, torch.float32, "weight").value
+        d.min_val, d.max_val = _p(e["min_val"], torch.float32).value, _p(e["max_val"], torch.float32).value
+        d.scale, d.zero_point = _p(e["scale"], torch.float32).value, _p(e["zero_point"], torch.int32).value
+        d.observer_enabled = _p(e["observer_enabled"], torch.int64).value
+        d.fake_quant_enabled = _p(e["fake_quant_enabled"], torch.int64).value
+        d.mask, d.codes, d.codes_t = _p(e["mask"], torch.uint8).value, _p(e["codes"], torch.bfloat16).value, \
+            _p(e["codes_t"], torch.bfloat16).value
+        for t in (e["min_val"], e["max_val"], e["scale"], e["zero_point"]):
+            if t.numel() != rows:
+                raise RuntimeError("qatvit_b200: per-channel observer state must have one entry per output channel")
+        d.rows, d.cols, d.block_start = rows, cols, start
+        start += -(-rows // FQW_ROWS)
+        max_cols = max(max_cols, cols)
+    table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
+    return table, start, max_cols
+
+
+def fq_weight_grouped(table, n_desc, total_blocks, max_cols, averaging_const, qmin, qmax, symmetric):
+    """All per-channel fake-quantised weights in one launch (include/qatvit_b200.h: qv_fq_weight_grouped)."""
+    check(_lib.lib().qv_fq_weight_grouped(_p(table, torch.uint8, "descriptor table"), n_desc, total_blocks, max_cols,
+                                          float(averaging_const), int(qmin), int(qmax), int(bool(symmetric)), _stream()),
+          "fq_weight_grouped")
+
+
 def fq_bwd(gy, mask, gx=None):
     if gx is None:
         gx = torch.empty_like(gy)
@@ -521,7 +559,7 @@ def _wrap(name, fn, tag_fn=None):
     return inner
 
 
-for _nm in ("minmax_reset", "minmax_accumulate", "obs_update", "fq_apply", "fq_weight", "fq_bwd", "split_planes",
+for _nm in ("minmax_reset", "minmax_accumulate", "obs_update", "fq_apply", "fq_weight", "fq_weight_grouped", "fq_bwd", "split_planes",
            "kd_ce_loss", "splitk_reduce", "colsum_reduce", "colsum_rows",
            "embed_fwd", "im2col_fq", "softmax_planes", "attn_ds", "head_fwd", "head_bwd", "attn_fwd", "attn_bwd", "attn_bwd_gp",
            "int8_linear", "quantize_u8", "qparams_from_minmax", "im2col_u8", "gelu_minmax"):

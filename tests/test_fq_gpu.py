@@ -210,3 +210,49 @@ def test_kd_ce_loss(cuda_dev, B, C, fq):
     assert abs(out3[1] - kd.item()) <= 1e-5 * abs(kd.item()) + 1e-7
     assert abs(out3[2] - ce.item()) <= 1e-5 * abs(ce.item())
     assert torch.allclose(grad.cpu(), sq.grad, rtol=1e-4, atol=1e-7)
+
+
+def test_weight_fq_grouped_bit_exact(cuda_dev):
+    """qv_fq_weight_grouped: several per-channel weights (ViT-S shapes, a ragged row count and edge-case rows) in ONE launch,
+    three EMA steps; state, fake-quantised values (codes * scale), STE mask and the transposed code plane must equal the live
+    torch CPU op applied to each weight separately."""
+    from qatvit_b200 import ops
+    dev = cuda_dev
+    gen = torch.Generator().manual_seed(77)
+    shapes = [(1152, 384), (384, 384), (1536, 384), (384, 1536), (384, 768), (40, 64), (8, 4)]
+    qmin, qmax, sym = -128, 127, True
+    w0s = []
+    for shp in shapes:
+        w = torch.randn(shp, generator=gen) * 0.02
+        w[0] = w[0].abs() + 1e-3
+        w[1] = -w[1].abs() - 1e-3
+        w[2] = 0.0
+        w[3] = w[3] * 1e-4              # below the 6.1e-5 scale cut-off
+        w0s.append(w)
+    ref_state = [dict(mn=torch.empty(0), mx=torch.empty(0), s=torch.ones(1), z=torch.zeros(1, dtype=torch.int32)) for _ in shapes]
+    on = torch.ones(1, dtype=torch.int64, device=dev)
+    ent = []
+    for shp in shapes:
+        n, k = shp
+        ent.append(dict(w=torch.empty(n, k, device=dev), min_val=torch.full((n,), float("inf"), device=dev),
+                        max_val=torch.full((n,), float("-inf"), device=dev), scale=torch.ones(n, device=dev),
+                        zero_point=torch.zeros(n, dtype=torch.int32, device=dev), observer_enabled=on, fake_quant_enabled=on,
+                        mask=torch.empty(n, k, dtype=torch.uint8, device=dev), codes=torch.empty(n, k, dtype=torch.bfloat16, device=dev),
+                        codes_t=torch.empty(k, n, dtype=torch.bfloat16, device=dev)))
+    table, blocks, max_cols = ops.fq_weight_group_table(ent, dev)
+    assert blocks == sum(-(-s[0] // ops.FQW_ROWS) for s in shapes) and max_cols == 1536
+    for step in range(3):
+        for w0, e in zip(w0s, ent):
+            e["w"].copy_(w0 * (1.0 + 0.3 * step) + 1e-3 * step)
+        ops.fq_weight_grouped(table, len(ent), blocks, max_cols, 0.01, qmin, qmax, sym)
+        torch.cuda.synchronize()
+        for w0, e, r in zip(w0s, ent, ref_state):
+            wt = (w0 * (1.0 + 0.3 * step) + 1e-3 * step).clone().requires_grad_(True)
+            y_ref = torch.fused_moving_avg_obs_fake_quant(wt, torch.tensor([1]), torch.tensor([1]), r["mn"], r["mx"], r["s"], r["z"],
+                                                          0.01, qmin, qmax, 0, True, sym)
+            y_ref.backward(torch.ones_like(y_ref))
+            assert torch.equal(e["min_val"].cpu(), r["mn"]) and torch.equal(e["max_val"].cpu(), r["mx"])
+            assert torch.equal(e["scale"].cpu(), r["s"]) and torch.equal(e["zero_point"].cpu(), r["z"])
+            assert torch.equal(e["codes"].float().cpu() * e["scale"].cpu().reshape(-1, 1), y_ref.detach())
+            assert torch.equal(e["mask"].cpu().float(), wt.grad)
+            assert torch.equal(e["codes_t"].cpu().t().contiguous(), e["codes"].cpu())
