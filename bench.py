@@ -310,7 +310,7 @@ def run_ours(args):
     peaks = _peaks()
     fam = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])
     step_kernel_ms = sum(v["ms"] for v in prof.values())
-    PASSES = {"gemm[teacher linear]": 3, "gemm[student fwd/dgrad]": 2, "gemm[wgrad]": 3, "gemm[patch-embed]": 1,
+    PASSES = {"gemm[teacher linear]": 3, "gemm[student fwd/dgrad]": 2, "gemm[student dgrad+gp]": 2, "gemm[wgrad]": 3, "gemm[patch-embed]": 1,
               "gemm[attn (unfused)]": 3}
     gemm_fams = {k: v for k, v in prof.items() if k.startswith("gemm") and v["ms"] > 0}
     top = max(gemm_fams, key=lambda k: gemm_fams[k]["ms"])
