@@ -365,6 +365,11 @@ class StudentEngine:
         # GEMM epilogue (for fc1), the attention backward's output stage (for qkv) and the LayerNorm backward (for proj and the
         # previous block's fc2).  fused_gp=False keeps the standalone kernel (parity reference for the fused forms).
         self.fused_gp = bool(fused_gp)
+        import os
+        self._wstream = torch.cuda.Stream(device=dev) if os.environ.get("QV_OVERLAP_WGRAD", "1") != "0" else None
+        self._w_ready = {k: torch.cuda.Event() for k in ("fc2", "fc1", "proj", "qkv", "conv")}
+        self._w_done = {k: torch.cuda.Event() for k in ("fc2", "fc1", "proj", "qkv", "conv")}
+        self._w_pending = set()
 
         # ---- forward activations (saved for backward) ----
         self.img_codes = e(1, B * d.P, d.Kc, dt=bf)
@@ -408,8 +413,9 @@ class StudentEngine:
         # ---- backward scratch ----
         self.gx = [e(M, D), e(M, D)]
         self.g_xn = e(B, D)
-        self.gpD = e(2, M, D, dt=bf)
-        self.gpF = e(2, M, F, dt=bf)
+        self.gpD = e(2, M, D, dt=bf)         # fc2's gradient planes
+        self.gpDp = e(2, M, D, dt=bf)        # proj's (separate, so a weight-gradient GEMM on the side stream can still read one
+        self.gpF = e(2, M, F, dt=bf)         #         while the main chain already writes the other)
         self.gp3 = e(2, M, 3 * D, dt=bf)
         self.gpP = e(2, B * d.P, D, dt=bf)
         if not self.fused_gp:
@@ -502,7 +508,9 @@ class StudentEngine:
         for ql in self._wsingle:
             ql.quantize_weight()
 
-    def forward(self, images: torch.Tensor, labels: torch.Tensor, teacher_logits: torch.Tensor) -> torch.Tensor:
+    def forward(self, images: torch.Tensor, labels: torch.Tensor, teacher_logits: torch.Tensor, teacher_ready=None) -> torch.Tensor:
+        """teacher_ready: optional CUDA event; the current stream waits for it right before the loss (the teacher forward may
+        then run concurrently on another stream)."""
         d, v = self.d, self.vit
         B, T, D, F, M, L = d.B, d.T, d.D, d.F, d.M, d.L
         if tuple(images.shape) != (B, d.in_ch, d.HW, d.HW):
@@ -558,15 +566,42 @@ class StudentEngine:
         ops.head_fwd(self.xn, hd.wq, hd.bias.detach(), B, D, d.C, self.logits_raw, minmax=hd.acc)
         hd.afq.update_from(hd.acc)
         hp = self.hp_
+        if teacher_ready is not None:
+            torch.cuda.current_stream().wait_event(teacher_ready)
         ops.kd_ce_loss(self.logits_raw, teacher_logits, labels, hp["kd_temp"], hp["kd_alpha"], hp["label_smoothing"],
                        s_scale=hd.afq.scale, s_zp=hd.afq.zero_point, qmin=hd.afq.qmin, qmax=hd.afq.qmax, out3=self.loss3,
                        grad=self.g_logits)
         return self.loss3
 
     # ------------------------------------------------------------------------------------------
-    def _wgrad(self, ql: _QLinear, gp: torch.Tensor, x_planes: torch.Tensor, kdim: int, pairs, alpha=None) -> None:
-        # pairs: (2,2) -> gp hi/lo x x hi/lo ; (2,1) -> gp hi/lo x exact codes
-        """weight.grad[N,K] = mask * (gp'^T @ x) / scale[n]  (split-K over the token dimension, deterministic reduce)."""
+    def _wgrad(self, ql: _QLinear, gp: torch.Tensor, x_planes: torch.Tensor, kdim: int, pairs, alpha=None, key=None) -> None:
+        """weight.grad[N,K] = mask * (gp'^T @ x) / scale[n]  (split-K over the token dimension, deterministic reduce).
+        pairs: (2,2) -> gp hi/lo x x hi/lo ; (2,1) -> gp hi/lo x exact codes.
+        Nothing downstream in the backward chain reads a weight gradient, so the GEMM + reduce go to a side stream (ordered
+        after the kernel that wrote `gp`); `key` names the gp buffer so its next writer can wait for this read (_w_wait)."""
+        if self._wstream is None or key is None or ops.profiling():
+            return self._wgrad_now(ql, gp, x_planes, kdim, pairs, alpha)
+        main = torch.cuda.current_stream()
+        self._w_ready[key].record(main)
+        with torch.cuda.stream(self._wstream):
+            self._wstream.wait_event(self._w_ready[key])
+            self._wgrad_now(ql, gp, x_planes, kdim, pairs, alpha)
+            self._w_done[key].record(self._wstream)
+        self._w_pending.add(key)
+
+    def _w_wait(self, key: str) -> None:
+        """The current stream is about to overwrite gp buffer `key`: wait for the side-stream weight-gradient GEMM reading it."""
+        if key in self._w_pending:
+            torch.cuda.current_stream().wait_event(self._w_done[key])
+            self._w_pending.discard(key)
+
+    def _w_join(self) -> None:
+        """Every weight gradient issued so far is complete (before gradients are declared final / the optimizer runs)."""
+        if self._w_pending:
+            torch.cuda.current_stream().wait_stream(self._wstream)
+            self._w_pending.clear()
+
+    def _wgrad_now(self, ql: _QLinear, gp: torch.Tensor, x_planes: torch.Tensor, kdim: int, pairs, alpha=None) -> None:
         s = self._splits[(ql.N, ql.K)]
         if s > 1:
             ops.gemm(Op.full(gp, mn_major=True), Op.full(x_planes, mn_major=True), ql.N, ql.K, kdim, pairs, splits=s,
@@ -611,31 +646,35 @@ class StudentEngine:
             blk, ql = v.blocks[l], self.lin[l]
             # ---- MLP ----
             if not (self.fused_gp and l < L - 1):     # else: emitted by the LayerNorm backward of block l + 1
+                self._w_wait("fc2")
                 self._gp(gx, self.m_raw[l], ql["fc2"], False, M, self.gpD)
             if self.fused_gp:
+                self._w_wait("fc1")
                 # fc2 dgrad with fc1's backward prologue in its epilogue: gelu'(FQ(f_raw)) * STE mask * fc1 weight scale
                 nslab = -(-M // 32)
                 part = self._part(nslab, F)
                 ops.gemm(Op.full(self.gpD), Op.full(ql["fc2"].codes_t), M, F, D, PAIRS_EXACT_B, out_planes=self.gpF,
                          col_scale=ql["fc1"].wscale_vec, grad_of=(self.f_raw[l], ql["fc1"].afq.q, True, part))
                 ops.colsum_reduce(part, nslab, F, self._grad(ql["fc1"].bias))
-                self._wgrad(ql["fc2"], self.gpD, self.gelp[l], M, PAIRS_FP32)
+                self._wgrad(ql["fc2"], self.gpD, self.gelp[l], M, PAIRS_FP32, key="fc2")
             else:
                 self._dgrad(ql["fc2"], self.gpD, M, self.g_big)
-                self._wgrad(ql["fc2"], self.gpD, self.gelp[l], M, PAIRS_FP32)
+                self._wgrad(ql["fc2"], self.gpD, self.gelp[l], M, PAIRS_FP32, key="fc2")
+                self._w_wait("fc1")
                 self._gp(self.g_big, self.f_raw[l], ql["fc1"], True, M, self.gpF)
             self._dgrad(ql["fc1"], self.gpF, M, self.g_h)
             # norm2 backward (+ residual grad) also emits proj's gradient planes
             nblk_gp = -(-M // self.rpb_ln)
             part = self._part(nblk_gp, D)
-            gp_proj = (self.a_raw[l], ql["proj"].afq.q, ql["proj"].wscale_vec, self.gpD, part) if self.fused_gp else None
+            self._w_wait("proj")
+            gp_proj = (self.a_raw[l], ql["proj"].afq.q, ql["proj"].wscale_vec, self.gpDp, part) if self.fused_gp else None
             if self.ln_obs:
                 f2 = self.ln_fq[2 * l + 1]
-                self._wgrad(ql["fc1"], self.gpF, self.h2p[l], M, PAIRS_EXACT_B, alpha=f2.scale)
+                self._wgrad(ql["fc1"], self.gpF, self.h2p[l], M, PAIRS_EXACT_B, alpha=f2.scale, key="fc1")
                 ops.ln_bwd(self.g_h, self.x_mid[l], self.stats2[l][0], self.stats2[l][1], blk.norm2.weight.detach(), gx, M, D, gx2,
                            self.ln_part, self.rpb_ln, h_raw=self.h2_raw[l], h_fq=f2.q, gp=gp_proj)
             else:
-                self._wgrad(ql["fc1"], self.gpF, self.h2p[l], M, PAIRS_FP32)
+                self._wgrad(ql["fc1"], self.gpF, self.h2p[l], M, PAIRS_FP32, key="fc1")
                 ops.ln_bwd(self.g_h, self.x_mid[l], self.stats2[l][0], self.stats2[l][1], blk.norm2.weight.detach(), gx, M, D, gx2,
                            self.ln_part, self.rpb_ln, gp=gp_proj)
             self._ln_param_grads(blk.norm2, nblk_ln)
@@ -643,12 +682,13 @@ class StudentEngine:
             if self.fused_gp:
                 ops.colsum_reduce(part, nblk_gp, D, self._grad(ql["proj"].bias))
             else:
-                self._gp(gx2, self.a_raw[l], ql["proj"], False, M, self.gpD)
+                self._gp(gx2, self.a_raw[l], ql["proj"], False, M, self.gpDp)
             if self.fused_attn:
                 # proj dgrad emits dL/dO directly as bf16 hi/lo planes; one fused kernel recomputes P and writes dQ | dK | dV
-                ops.gemm(Op.full(self.gpD), Op.full(ql["proj"].codes_t), M, D, D, PAIRS_EXACT_B, out_planes=self.g_op)
-                self._wgrad(ql["proj"], self.gpD, self.op[l], M, PAIRS_FP32)
+                ops.gemm(Op.full(self.gpDp), Op.full(ql["proj"].codes_t), M, D, D, PAIRS_EXACT_B, out_planes=self.g_op)
+                self._wgrad(ql["proj"], self.gpDp, self.op[l], M, PAIRS_FP32, key="proj")
                 if self.fused_gp:   # ... with qkv's backward prologue applied on the way out
+                    self._w_wait("qkv")
                     part = self._part(self.slabs_attn, 3 * D)
                     ops.attn_bwd_gp(self.qkvc[l], ql["qkv"].afq.scale, self.op[l], self.g_op, self.lse[l], B, T, H, d.attn_scale,
                                     self.qkv_raw[l], ql["qkv"].afq.q, ql["qkv"].wscale_vec, self.gp3, part)
@@ -657,8 +697,8 @@ class StudentEngine:
                     ops.attn_bwd(self.qkvc[l], ql["qkv"].afq.scale, self.op[l], self.g_op, self.lse[l], B, T, H, d.attn_scale,
                                  self.g_qkv)
             else:
-                self._dgrad(ql["proj"], self.gpD, M, self.g_o)
-                self._wgrad(ql["proj"], self.gpD, self.op[l], M, PAIRS_FP32)
+                self._dgrad(ql["proj"], self.gpDp, M, self.g_o)
+                self._wgrad(ql["proj"], self.gpDp, self.op[l], M, PAIRS_FP32, key="proj")
                 ops.split_planes(self.g_o, self.g_op)
                 qkvp, Pp = self.qkvp[l], self.Pp[l]
                 # dP = dO V^T
@@ -673,33 +713,37 @@ class StudentEngine:
                 ops.gemm(Op.per_head(Pp, BH, H, T, T, mn_major=True), Op.tokens(self.g_op, B, T, 0, 64, mn_major=True), T, 64, T,
                          PAIRS_FP32, out=Out.tokens(self.g_qkv, B, T, 2 * D, 64), nbatch=BH, batch_inner=H)
             if not (self.fused_gp and self.fused_attn):
+                self._w_wait("qkv")
                 self._gp(self.g_qkv, self.qkv_raw[l], ql["qkv"], False, M, self.gp3)
             self._dgrad(ql["qkv"], self.gp3, M, self.g_h)
             # norm1 backward also emits the gradient planes of the PREVIOUS block's fc2 (its output joined this residual stream)
             gp_fc2 = None
             if self.fused_gp and l > 0:
+                self._w_wait("fc2")
                 pf = self.lin[l - 1]["fc2"]
                 part = self._part(nblk_gp, D)
                 gp_fc2 = (self.m_raw[l - 1], pf.afq.q, pf.wscale_vec, self.gpD, part)
             if self.ln_obs:
                 f1 = self.ln_fq[2 * l]
-                self._wgrad(ql["qkv"], self.gp3, self.h1p[l], M, PAIRS_EXACT_B, alpha=f1.scale)
+                self._wgrad(ql["qkv"], self.gp3, self.h1p[l], M, PAIRS_EXACT_B, alpha=f1.scale, key="qkv")
                 ops.ln_bwd(self.g_h, self.x_in[l], self.stats1[l][0], self.stats1[l][1], blk.norm1.weight.detach(), gx2, M, D, gx,
                            self.ln_part, self.rpb_ln, h_raw=self.h1_raw[l], h_fq=f1.q, gp=gp_fc2)
             else:
-                self._wgrad(ql["qkv"], self.gp3, self.h1p[l], M, PAIRS_FP32)
+                self._wgrad(ql["qkv"], self.gp3, self.h1p[l], M, PAIRS_FP32, key="qkv")
                 ops.ln_bwd(self.g_h, self.x_in[l], self.stats1[l][0], self.stats1[l][1], blk.norm1.weight.detach(), gx2, M, D, gx,
                            self.ln_part, self.rpb_ln, gp=gp_fc2)
             self._ln_param_grads(blk.norm1, nblk_ln)
             if gp_fc2 is not None:
                 ops.colsum_reduce(part, nblk_gp, D, self._grad(self.lin[l - 1]["fc2"].bias))
             if grads_final_from is not None:
+                self._w_join()
                 grads_final_from(self._block_lo[l])
         # ---- embeddings: pos_embed, cls_token, patch-embed conv ----
         ops.colsum_rows(gx, B, T * D, T * D, self._grad(v.pos_embed))
         ops.colsum_rows(gx, B, D, T * D, self._grad(v.cls_token))
         self._gp(gx, self.p_raw, self.conv, False, B * d.P, self.gpP, remap=(d.P, T))
-        self._wgrad(self.conv, self.gpP, self.img_codes, B * d.P, PAIRS_EXACT_B, alpha=self.fq_in.scale)
+        self._wgrad(self.conv, self.gpP, self.img_codes, B * d.P, PAIRS_EXACT_B, alpha=self.fq_in.scale, key="conv")
+        self._w_join()
         if grads_final_from is not None:
             grads_final_from(0)
 
@@ -709,16 +753,34 @@ class QATDistillStep:
     forward, loss and backward on the current stream and leaves gradients in ``student`` parameters' ``.grad``."""
 
     def __init__(self, student: nn.Module, teacher: nn.Module, batch: int, hparams: Dict,
-                 grad_buffer: Optional[torch.Tensor] = None, fused_attention: Optional[bool] = None, fused_gp: bool = True):
+                 grad_buffer: Optional[torch.Tensor] = None, fused_attention: Optional[bool] = None, fused_gp: bool = True,
+                 overlap_teacher: Optional[bool] = None):
         self.student_engine = StudentEngine(student, batch, hparams, grad_buffer=grad_buffer, fused_attention=fused_attention,
                                             fused_gp=fused_gp)
         self.teacher_engine = TeacherEngine(teacher, batch)
         self.grad_arena = self.student_engine.grad_arena
+        # The frozen teacher's forward (ref qat_trainer.py:337-338) is independent of the student's until the loss: it runs on a
+        # second stream, so each stream's kernel-boundary bubbles (tails of persistent kernels, small reduces / observer updates)
+        # are filled by the other's work.
+        import os
+        if overlap_teacher is None:
+            overlap_teacher = os.environ.get("QV_OVERLAP_TEACHER", "1") != "0"
+        self.overlap_teacher = bool(overlap_teacher)
+        self._tstream = torch.cuda.Stream(device=self.student_engine.dev) if self.overlap_teacher else None
+        self._tdone = torch.cuda.Event() if self.overlap_teacher else None
 
     def __call__(self, images: torch.Tensor, labels: torch.Tensor, grad_sync=None) -> torch.Tensor:
         """grad_sync: a ddp.GradSync whose buffer holds the gradient arena -- its all-reduce then overlaps the backward."""
-        t_logits = self.teacher_engine.forward(images)
-        out3 = self.student_engine.forward(images, labels, t_logits)
+        if self.overlap_teacher and not ops.profiling():
+            main = torch.cuda.current_stream()
+            self._tstream.wait_stream(main)                      # images are ready; the previous step's loss has read the logits
+            with torch.cuda.stream(self._tstream):
+                t_logits = self.teacher_engine.forward(images)
+                self._tdone.record(self._tstream)
+            out3 = self.student_engine.forward(images, labels, t_logits, teacher_ready=self._tdone)
+        else:
+            t_logits = self.teacher_engine.forward(images)
+            out3 = self.student_engine.forward(images, labels, t_logits)
         if grad_sync is None:
             self.student_engine.backward()
         else:

@@ -571,6 +571,10 @@ resid_ln_fwd = _wrap("resid_ln_fwd", resid_ln_fwd, _bytes_resid_ln)
 ln_bwd = _wrap("ln_bwd", ln_bwd, _bytes_ln_bwd)
 
 
+def profiling() -> bool:
+    return _prof is not None
+
+
 def profile_begin() -> None:
     global _prof
     _prof = []
