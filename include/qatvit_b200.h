@@ -285,6 +285,16 @@ int qv_clip_adamw(float* params, float* grads, float* exp_avg, float* exp_avg_sq
                   float grad_scale, float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
                   float* norm_out, int32_t write_back_grad, void* stream);
 
+/* ---- input transform: ref/src/training/qat_trainer.py:210-216 -------------------------------------
+ * transforms.Compose([Resize(size, BICUBIC), ToTensor(), Normalize(mean, std)]) on a batch of uint8 HWC images
+ * img [B][Hin][Win][C] -> out fp32 [B][C][Hout][Wout].  Pillow's two-pass 8-bit bicubic resample (horizontal, then vertical;
+ * 22-bit fixed-point taps), /255, (x - mean[c]) / std[c]: bit-identical to the CPU pipeline.  bounds_* int32 [n_out][2] =
+ * (first input index, tap count), coef_* int32 [n_out][ksize]: Pillow's precompute_coeffs + normalize_coeffs_8bpc for the
+ * horizontal (Win -> Wout) and vertical (Hin -> Hout) pass (computed by the host side, qatvit_b200/data.py). */
+int qv_resize_normalize_u8(const uint8_t* img, int64_t B, int32_t Hin, int32_t Win, int32_t C, int32_t Hout, int32_t Wout,
+                           const int32_t* bounds_h, const int32_t* coef_h, const int32_t* bounds_v, const int32_t* coef_v,
+                           int32_t ksize, const float* mean, const float* stdv, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -151,8 +151,46 @@ def model_census():
     print("tiny_step loss", float(loss))
 
 
+def resize_cases():
+    """The reference's input transform (ref qat_trainer.py:210-216) run LIVE through Pillow + torchvision on small uint8 images:
+    a random CIFAR-sized image and extreme patterns at 224, random and non-square inputs at smaller target sizes (same code path,
+    smaller fixture).  Stored: inputs, the uint8 images Pillow's bicubic resize returns, and ToTensor + Normalize as the 3 x 256
+    table of the float32 value each uint8 level maps to per channel (the map is pointwise)."""
+    from PIL import Image
+    from torchvision import transforms
+    import torch
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    rng = np.random.default_rng(2024)
+    cases = {"rand224": (rng.integers(0, 256, (32, 32, 3), dtype=np.uint8), 224),
+             "checker224": (np.zeros((32, 32, 3), np.uint8), 224), "white224": (np.full((32, 32, 3), 255, np.uint8), 224),
+             "binary224": ((rng.integers(0, 2, (32, 32, 3)) * 255).astype(np.uint8), 224),
+             "rand96": (rng.integers(0, 256, (32, 32, 3), dtype=np.uint8), 96),
+             "wide64": (rng.integers(0, 256, (32, 48, 3), dtype=np.uint8), 64),
+             "tall80": (rng.integers(0, 256, (40, 32, 3), dtype=np.uint8), 80),
+             "down24": (rng.integers(0, 256, (50, 70, 3), dtype=np.uint8), 24)}
+    cases["checker224"][0][::2, ::2] = 255
+    out = {}
+    for k, (v, size) in cases.items():
+        rz = transforms.Resize(size, interpolation=transforms.InterpolationMode.BICUBIC)
+        pil = rz(Image.fromarray(v))
+        full = transforms.Compose([rz, transforms.ToTensor(), transforms.Normalize(mean=mean, std=std)])(Image.fromarray(v)).numpy()
+        u8 = np.array(pil)
+        out["in_" + k] = v
+        out["u8_" + k] = u8
+        out["size_" + k] = np.array([size])
+        # the float output is a pointwise function of the resized uint8 image: check, then store only the table
+        lut_probe = transforms.Compose([transforms.ToTensor(), transforms.Normalize(mean=mean, std=std)])
+        assert np.array_equal(full, lut_probe(Image.fromarray(u8)).numpy())
+    levels = np.repeat(np.arange(256, dtype=np.uint8)[None, :, None], 3, axis=2)            # [1, 256, 3] image holding every level
+    out["level_table"] = transforms.Compose([transforms.ToTensor(), transforms.Normalize(mean=mean, std=std)])(
+        Image.fromarray(levels)).numpy()[:, 0, :]                                           # [3, 256] float32
+    np.savez_compressed(os.path.join(OUT, "resize.npz"), **out)
+    print("resize cases", {k: v.shape for k, v in out.items() if k.startswith("u8_")})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    resize_cases()
     fq_cases()
     cqp_ties()
     qlinear_cases()

@@ -114,6 +114,8 @@ _SIGNATURES = {
     "qv_quantize_u8": (c_int, [_P, c_int64, _P, _P, _P, _P]),
     "qv_qparams_from_minmax": (c_int, [_P, c_int32, c_int32, _P, _P, _P]),
     "qv_im2col_u8": (c_int, [_P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P, _P]),
+    "qv_resize_normalize_u8": (c_int, [_P, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P, _P, _P, c_int32, _P, _P,
+                                       _P, _P]),
     "qv_gelu_minmax": (c_int, [_P, c_int64, _P, _P, _P]),
     "qv_head_fwd": (c_int, [_P, _P, _P, c_int32, c_int32, c_int32, _P, _P, _P]),
     "qv_head_bwd": (c_int, [_P, _P, _P, _P, c_int32, c_int32, c_int32, _P, _P, _P, c_int32, _P]),

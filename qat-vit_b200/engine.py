@@ -508,9 +508,20 @@ class StudentEngine:
         for ql in self._wsingle:
             ql.quantize_weight()
 
-    def forward(self, images: torch.Tensor, labels: torch.Tensor, teacher_logits: torch.Tensor, teacher_ready=None) -> torch.Tensor:
+    def predict(self, images: torch.Tensor) -> torch.Tensor:
+        """Forward only: the prepared student's output (fake-quantised logits), as ``ddp_model(images)`` returns it -- the call
+        inside ref qat_trainer.py:49-61 (evaluate_fp32).  Like the stock modules, the observers keep following the data unless
+        they were disabled (torch.ao.quantization.disable_observer): FusedMovingAvgObsFakeQuantize ignores train / eval mode."""
+        self.forward(images, None, None)
+        hd = self.head
+        y, _ = ops.fq_apply(self.logits_raw, hd.afq.scale, hd.afq.zero_point, hd.afq.fake_quant_enabled, hd.afq.qmin, hd.afq.qmax,
+                            want_mask=False)
+        return y
+
+    def forward(self, images: torch.Tensor, labels: Optional[torch.Tensor], teacher_logits: Optional[torch.Tensor],
+                teacher_ready=None) -> Optional[torch.Tensor]:
         """teacher_ready: optional CUDA event; the current stream waits for it right before the loss (the teacher forward may
-        then run concurrently on another stream)."""
+        then run concurrently on another stream).  labels = None: stop after the head (predict)."""
         d, v = self.d, self.vit
         B, T, D, F, M, L = d.B, d.T, d.D, d.F, d.M, d.L
         if tuple(images.shape) != (B, d.in_ch, d.HW, d.HW):
@@ -565,6 +576,8 @@ class StudentEngine:
         hd = self.head
         ops.head_fwd(self.xn, hd.wq, hd.bias.detach(), B, D, d.C, self.logits_raw, minmax=hd.acc)
         hd.afq.update_from(hd.acc)
+        if labels is None:
+            return None
         hp = self.hp_
         if teacher_ready is not None:
             torch.cuda.current_stream().wait_event(teacher_ready)
@@ -788,6 +801,10 @@ class QATDistillStep:
             self.student_engine.backward(grads_final_from=grad_sync.grads_final_from)
             grad_sync.end_step()
         return out3
+
+    def predict(self, images: torch.Tensor) -> torch.Tensor:
+        """student(images) without loss / backward (validation loop of ref qat_trainer.py:49-61)."""
+        return self.student_engine.predict(images)
 
     @property
     def student_logits_raw(self) -> torch.Tensor:

@@ -134,3 +134,34 @@ def test_state_dict_and_convert_flow_unchanged(cuda_dev):
     assert any(k.endswith("_packed_params._packed_params") for k in csd)
     w, _ = csd["model.blocks.0.attn.qkv._packed_params._packed_params"]
     assert w.dtype == torch.qint8 and w.int_repr().abs().max() > 0
+
+
+@pytest.mark.parametrize("backend,ln_variant", [("fbgemm", "subclass"), ("qnnpack", "plain")])
+def test_predict_matches_reference_forward(cuda_dev, backend, ln_variant):
+    """Forward only (the reference's evaluate_fp32 loop, qat_trainer.py:49-61): engine.predict(images) == prepared(images) on CPU
+    with identical codes forced; two calls, so the EMA branch of every observer is covered; no gradient is touched."""
+    from qatvit_b200.engine import QATDistillStep
+    vr, prepared, teacher = build_models(backend, "vit_test_tiny", "vit_test_teacher", 64, ln_variant=ln_variant)
+    B = 5
+    gpu_student = copy.deepcopy(prepared).to(cuda_dev)
+    step = QATDistillStep(gpu_student, copy.deepcopy(teacher).to(cuda_dev), B, dict(vr.DEFAULT_HPARAMS))
+    step.grad_arena.fill_(7.0)
+    for it in range(2):
+        images, _ = vr.synthetic_batch(B, seed=20 + it, img=64)
+        y = step.predict(images.to(cuda_dev))
+        torch.cuda.synchronize()
+        stage_err = {}
+        handles = install_forcing_hooks(prepared, engine_raw_tensors(step.student_engine), stage_err)
+        with torch.no_grad():
+            y_ref = prepared(images)
+        for h in handles:
+            h.remove()
+        assert max(stage_err.values()) < 1e-4
+        assert rel_max(y, y_ref) < 1e-5
+    assert bool((step.grad_arena == 7.0).all())
+    ref_sd, gpu_sd = prepared.state_dict(), gpu_student.state_dict()
+    for k in ref_sd:
+        if k.endswith("zero_point"):
+            assert torch.equal(gpu_sd[k].cpu(), ref_sd[k]), k
+        elif k.endswith(("min_val", "max_val", "scale")):
+            assert rel_max(gpu_sd[k].cpu(), ref_sd[k]) < 1e-6, k
