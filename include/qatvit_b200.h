@@ -150,6 +150,14 @@ typedef struct qv_gemm_args {
    *   of gq over token rows 32 s .. 32 s + 31 (bias-grad partials; reduce with qv_colsum_reduce). */
   const float* ep_raw; int64_t ep_raw_ld; const float* ep_scale; const int32_t* ep_zp;
   int32_t ep_qmin, ep_qmax, ep_gelu; float* ep_colsum;
+  /* obs_ticket != NULL (needs minmax, fp32 output, no split-K): the output observer's update -- qv_obs_update on (minmax ->
+   * obs_min_val / obs_max_val EMA with obs_c -> obs_scale / obs_zero_point) -- runs in the kernel's tail, done by the last
+   * epilogue warp of the grid, so the consumer of the fake-quantised output can be launched straight after the GEMM.
+   * obs_ticket: a zero-initialised uint32 the kernel leaves at zero (one per stream). */
+  float* obs_min_val; float* obs_max_val; float* obs_scale; int32_t* obs_zero_point;
+  const int64_t* obs_enabled; const int64_t* obs_fq_enabled;
+  float obs_c; int32_t obs_qmin, obs_qmax, obs_symmetric;
+  uint32_t* obs_ticket;
 } qv_gemm_args;
 int qv_gemm_bf16(const qv_gemm_args* args, void* stream);
 

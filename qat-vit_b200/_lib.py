@@ -65,6 +65,10 @@ class GemmArgs(ctypes.Structure):
         ("out_kind", c_int32), ("act", c_int32), ("out_plane_stride", c_int64),
         ("ep_raw", c_void_p), ("ep_raw_ld", c_int64), ("ep_scale", c_void_p), ("ep_zp", c_void_p),
         ("ep_qmin", c_int32), ("ep_qmax", c_int32), ("ep_gelu", c_int32), ("ep_colsum", c_void_p),
+        ("obs_min_val", c_void_p), ("obs_max_val", c_void_p), ("obs_scale", c_void_p), ("obs_zero_point", c_void_p),
+        ("obs_enabled", c_void_p), ("obs_fq_enabled", c_void_p),
+        ("obs_c", c_float), ("obs_qmin", c_int32), ("obs_qmax", c_int32), ("obs_symmetric", c_int32),
+        ("obs_ticket", c_void_p),
     ]
 
 

@@ -11,59 +11,9 @@
 #include <mutex>
 
 #include "qv_common.cuh"
+#include "qv_observer.cuh"
 
 namespace {
-
-// ---------------- ChooseQuantizationParams (fbgemm flavour; see oracle/fq_oracle.c) ----------------
-__device__ void qv_choose_qparams(float mn, float mx, int qmin, int qmax, bool preserve_sparsity, float* scale_out,
-                                  int32_t* zp_out) {
-  if (mn < 0.f && mx > 0.f && preserve_sparsity) {
-    const int sqmin = -((qmax - qmin) / 2 + 1);
-    const int sqmax = (qmax - qmin) / 2;
-    const float a = __fdiv_rn(mn, (float)sqmin);
-    const float b = __fdiv_rn(mx, (float)sqmax);
-    const double ms = fmax(fabs((double)a), fabs((double)b));
-    mn = (float)__dmul_rn(ms, (double)sqmin);
-    mx = (float)__dmul_rn(ms, (double)sqmax);
-  }
-  mn = fminf(mn, 0.f);
-  mx = fmaxf(mx, 0.f);
-  float scale = (float)__ddiv_rn(__dsub_rn((double)mx, (double)mn), (double)(qmax - qmin));
-  if (scale == 0.0f || isinf(__fdiv_rn(1.0f, scale))) scale = 0.1f;
-  const float kSmall = 6.1e-5f;
-  if (scale < kSmall) {
-    const float org = scale;
-    scale = kSmall;
-    if (mn == 0.0f) {
-      mx = __fmul_rn(kSmall, (float)(qmax - qmin));
-    } else if (mx == 0.0f) {
-      mn = __fmul_rn(-kSmall, (float)(qmax - qmin));
-    } else {
-      const float amp = __fdiv_rn(kSmall, org);
-      mn = __fmul_rn(mn, amp);
-      mx = __fmul_rn(mx, amp);
-    }
-  }
-  const double ds = (double)scale;
-  const double mn_s = __ddiv_rn((double)mn, ds), mx_s = __ddiv_rn((double)mx, ds);
-  const double zp_from_min = __dsub_rn((double)qmin, mn_s);
-  const double zp_from_max = __dsub_rn((double)qmax, mx_s);
-  const double err_min = __dadd_rn((double)abs(qmin), fabs(mn_s));
-  const double err_max = __dadd_rn((double)abs(qmax), fabs(mx_s));
-  double zp0 = err_min < err_max ? zp_from_min : zp_from_max;
-  if (mn < 0.f && mx > 0.f && preserve_sparsity) zp0 = (double)(qmin + qmax) / 2.0;
-  int32_t zp;
-  if (zp0 < (double)qmin) zp = qmin;
-  else if (zp0 > (double)qmax) zp = qmax;
-  else zp = (int32_t)rint(zp0);
-  *scale_out = scale;
-  *zp_out = zp;
-}
-
-__device__ __forceinline__ float qv_ema(float r, float cur, float c) {
-  if (isinf(r)) return cur;
-  return __fadd_rn(r, __fmul_rn(c, __fsub_rn(cur, r)));
-}
 
 // ---------------- min/max accumulation ----------------
 __global__ void qv_minmax_reset_kernel(uint32_t* acc, int count) {
@@ -125,21 +75,7 @@ __global__ void qv_obs_update_kernel(const uint32_t* acc, const int64_t* obs_on,
                                      float* max_val, float* scale, int32_t* zp, float c, int qmin, int qmax,
                                      int symmetric) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  if (*obs_on == 0) return;
-  const uint32_t emn = acc[0], emx = acc[1];
-  if (emn == QV_ORD_MIN_INIT && emx == QV_ORD_MAX_INIT) return;   // empty tensor: nothing observed
-  const float cur_min = qv_ord2f(emn), cur_max = qv_ord2f(emx);
-  const float rmin = qv_ema(*min_val, cur_min, c);
-  const float rmax = qv_ema(*max_val, cur_max, c);
-  *min_val = rmin;
-  *max_val = rmax;
-  if (*fq_on != 0) {
-    float s;
-    int32_t z;
-    qv_choose_qparams(rmin, rmax, qmin, qmax, symmetric != 0, &s, &z);
-    *scale = s;
-    *zp = z;
-  }
+  qv_observer_step(acc[0], acc[1], obs_on, fq_on, min_val, max_val, scale, zp, c, qmin, qmax, symmetric);
 }
 
 // ---------------- elementwise fake-quant ----------------

@@ -23,6 +23,7 @@
 #include "qv_common.cuh"
 #include "qv_ptx.cuh"
 #include "qv_tma.cuh"
+#include "qv_observer.cuh"
 
 using namespace qvptx;
 
@@ -62,6 +63,12 @@ struct GemmKParams {
   const int32_t* ep_zp;
   int32_t ep_qmin, ep_qmax, ep_gelu;
   float* ep_colsum;       // [ceil(M/32)][N] per-32-row-slab column sums of gq (bias-grad partials), may be NULL
+  // observer update in the kernel tail (needs minmax): the grid's last epilogue warp turns the merged min / max into the
+  // module's running range and (scale, zero_point) -- qv_obs_update without a launch
+  float* obs_min_val; float* obs_max_val; float* obs_scale; int32_t* obs_zero_point;
+  const int64_t* obs_enabled; const int64_t* obs_fq_enabled;
+  float obs_c; int32_t obs_qmin, obs_qmax, obs_symmetric;
+  uint32_t* obs_ticket;
 };
 
 template <int BN, int NA, int NB, int EPI = 0>
@@ -511,6 +518,18 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         atomicMin(p.minmax, qv_f2ord(mn));
         atomicMax(p.minmax + 1, qv_f2ord(mx));
       }
+      if (p.obs_ticket && lane == 0) {
+        __threadfence();                                          // this warp's min / max are visible before its ticket
+        const uint32_t t = atomicAdd(p.obs_ticket, 1u);
+        if (t == gridDim.x * 8u - 1u) {                           // every epilogue warp of the grid has merged its range
+          __threadfence();
+          const uint32_t emn = *reinterpret_cast<volatile uint32_t*>(p.minmax);
+          const uint32_t emx = *reinterpret_cast<volatile uint32_t*>(p.minmax + 1);
+          qv_observer_step(emn, emx, p.obs_enabled, p.obs_fq_enabled, p.obs_min_val, p.obs_max_val, p.obs_scale,
+                           p.obs_zero_point, p.obs_c, p.obs_qmin, p.obs_qmax, p.obs_symmetric);
+          *p.obs_ticket = 0u;                                     // re-armed for the next launch on this stream
+        }
+      }
     }
     }   // EPI != 2
   }
@@ -684,6 +703,15 @@ extern "C" int qv_gemm_bf16(const qv_gemm_args* a, void* stream) {
   kp.act = a->act;
   kp.ep_raw = a->ep_raw; kp.ep_raw_ld = a->ep_raw_ld; kp.ep_scale = a->ep_scale; kp.ep_zp = a->ep_zp;
   kp.ep_qmin = a->ep_qmin; kp.ep_qmax = a->ep_qmax; kp.ep_gelu = a->ep_gelu; kp.ep_colsum = a->ep_colsum;
+  if (a->obs_ticket) {
+    QV_REQUIRE(a->minmax && splits == 1 && !planes_out, QV_ERR_INVALID, "a fused observer update needs minmax on an unsplit fp32-output GEMM");
+    QV_REQUIRE(a->obs_min_val && a->obs_max_val && a->obs_scale && a->obs_zero_point && a->obs_enabled && a->obs_fq_enabled,
+               QV_ERR_INVALID, "null observer state pointer");
+    kp.obs_min_val = a->obs_min_val; kp.obs_max_val = a->obs_max_val; kp.obs_scale = a->obs_scale;
+    kp.obs_zero_point = a->obs_zero_point; kp.obs_enabled = a->obs_enabled; kp.obs_fq_enabled = a->obs_fq_enabled;
+    kp.obs_c = a->obs_c; kp.obs_qmin = a->obs_qmin; kp.obs_qmax = a->obs_qmax; kp.obs_symmetric = a->obs_symmetric;
+    kp.obs_ticket = a->obs_ticket;
+  }
   const int64_t items = static_cast<int64_t>(kp.tiles_m) * kp.tiles_n * (nbatch > 1 ? nbatch : kp.splits);
   QV_REQUIRE(items < (1LL << 31), QV_ERR_UNSUPPORTED, "too many tiles");
   const int sms = qv_num_sms();

@@ -298,6 +298,9 @@ class StudentEngine:
         n_act = 2 + 4 * L + 1
         n_ln = (2 * L + 1) if self.ln_obs else 0
         self.acc = torch.empty(n_act + n_ln, 2, dtype=torch.int32, device=dev)
+        self.obs_ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+        import os
+        self._fused_obs = os.environ.get("QV_FUSED_OBS", "1") != "0"
         self.fq_in = FQRef(student.quant.activation_post_process)
         self.conv = _QLinear(vit.patch_embed.proj, dev, self.acc[1])
         self.lin: List[Dict[str, _QLinear]] = []
@@ -467,9 +470,15 @@ class StudentEngine:
     # ------------------------------------------------------------------------------------------
     def _linear_fwd(self, ql: _QLinear, a_planes: torch.Tensor, M: int, out: torch.Tensor, pairs=PAIRS_EXACT_B, alpha=None):
         """y_raw = x @ (codes*scale)^T + b with the output observer's min/max fused in the epilogue, then EMA + qparams."""
+        f = ql.afq      # the observer's EMA + qparams run in the GEMM's tail (last epilogue warp of the grid): no extra launch
+        if not self._fused_obs:
+            ops.gemm(Op.full(a_planes), Op.full(ql.codes), M, ql.N, ql.K, pairs, out=out, col_scale=ql.wscale_vec, alpha=alpha,
+                     bias=ql.bias.detach(), minmax=ql.acc)
+            return ql.afq.update_from(ql.acc)
         ops.gemm(Op.full(a_planes), Op.full(ql.codes), M, ql.N, ql.K, pairs, out=out, col_scale=ql.wscale_vec, alpha=alpha,
-                 bias=ql.bias.detach(), minmax=ql.acc)
-        ql.afq.update_from(ql.acc)
+                 bias=ql.bias.detach(), minmax=ql.acc,
+                 observer=(f.min_val, f.max_val, f.scale, f.zero_point, f.observer_enabled, f.fake_quant_enabled, f.c, f.qmin,
+                           f.qmax, f.symmetric, self.obs_ticket))
 
     def _ln_fwd(self, slot: int, norm: nn.Module, x_in, y_raw, fq, x_out, h_out, h_raw, stats) -> None:
         """x_out = x_in + FQ(y_raw); LayerNorm -> the A operand of the next Linear: bf16 hi/lo planes, or (observed LN) raw

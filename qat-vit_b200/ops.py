@@ -241,12 +241,14 @@ PAIRS_FP32 = (2, 2)          # both fp32 as hi/lo: A0*B0 + A0*B1 + A1*B0 (lo*lo 
 def gemm(a: Op, b: Op, M: int, N: int, K: int, planes: Tuple[int, int], *, out=None, col_scale=None, col_rscale=None,
          alpha=None, bias=None, minmax=None, splits: int = 1, workspace: Optional[torch.Tensor] = None, nbatch: int = 1,
          batch_inner: int = 1, tile_n: int = 0, out_planes: Optional[torch.Tensor] = None, gelu: bool = False,
-         grad_of=None):
+         grad_of=None, observer=None):
     """D[M,N] = sum_pairs A[pa] @ B[pb]^T on tcgen05 (include/qatvit_b200.h: qv_gemm_bf16).
     out: an ``Out`` descriptor, a 2-D fp32 tensor, or None (allocated).
     out_planes: bf16 [2, M, N] -- write [GELU](D) as hi/lo planes straight from the epilogue instead of fp32.
     grad_of = (y_raw [M,N], (scale, zp, qmin, qmax), gelu: bool, colsum [ceil(M/32), N] | None): with out_planes, the
-    gradient-planes epilogue (act = 2): D * [gelu'(FQ(y))] * STEmask(y) * col_scale -> planes, bias-grad slab sums."""
+    gradient-planes epilogue (act = 2): D * [gelu'(FQ(y))] * STEmask(y) * col_scale -> planes, bias-grad slab sums.
+    observer = (min_val, max_val, scale, zero_point, observer_enabled, fake_quant_enabled, c, qmin, qmax, symmetric, ticket):
+    with minmax, the output observer's update (obs_update) runs in the GEMM's tail instead of a separate launch."""
     args = GemmArgs()
     a.fill(args.a)
     b.fill(args.b)
@@ -287,6 +289,13 @@ def gemm(a: Op, b: Op, M: int, N: int, K: int, planes: Tuple[int, int], *, out=N
     args.alpha = None if alpha is None else alpha.data_ptr()
     args.bias = None if bias is None else bias.data_ptr()
     args.minmax = None if minmax is None else minmax.data_ptr()
+    if observer is not None:
+        mn, mx, sc, zp, on, fq_on, c, qmin, qmax, sym, ticket = observer
+        args.obs_min_val, args.obs_max_val = _p(mn, torch.float32, "min_val"), _p(mx, torch.float32, "max_val")
+        args.obs_scale, args.obs_zero_point = _p(sc, torch.float32, "scale"), _p(zp, torch.int32, "zero_point")
+        args.obs_enabled, args.obs_fq_enabled = _p(on, torch.int64, "observer_enabled"), _p(fq_on, torch.int64, "fake_quant_enabled")
+        args.obs_c, args.obs_qmin, args.obs_qmax, args.obs_symmetric = float(c), int(qmin), int(qmax), int(bool(sym))
+        args.obs_ticket = _p(ticket, torch.int32, "observer ticket")
     args.splits = splits
     args.nbatch, args.batch_inner = nbatch, batch_inner
     args.tile_n = tile_n

@@ -191,3 +191,38 @@ def test_gemm_gradient_planes_epilogue_is_race_free(cuda_dev):
     torch.cuda.synchronize()
     bad = sum(0 if torch.equal(o.view(torch.int16), ref.view(torch.int16)) else 1 for o in outs)
     assert bad == 0, f"{bad} of 100 launches differ"
+
+
+@pytest.mark.parametrize("M,N,K", [(197 * 8, 1152, 384), (130, 96, 40), (197 * 64, 384, 1536)])
+def test_gemm_fused_observer_update(cuda_dev, M, N, K):
+    """obs_ticket: the output observer's EMA + qparams run in the GEMM's tail (last epilogue warp of the grid).  Three launches
+    (first call, EMA, EMA) must leave exactly the state that GEMM + qv_obs_update leave, and the ticket back at zero."""
+    from qatvit_b200 import ops
+    from qatvit_b200.ops import Op, PAIRS_EXACT_B
+    dev = cuda_dev
+    g = torch.Generator().manual_seed(M + N)
+    b = _codes((N, K), dev, g)
+    bp = b.bfloat16()[None].contiguous()
+    scale = (torch.rand(N, generator=g) * 0.02 + 0.001).to(dev)
+    bias = torch.randn(N, generator=g).to(dev)
+
+    def fresh():
+        return (torch.full((1,), float("inf"), device=dev).squeeze(0), torch.full((1,), float("-inf"), device=dev).squeeze(0),
+                torch.ones(1, device=dev), torch.zeros(1, dtype=torch.int32, device=dev))
+    on = torch.ones(1, dtype=torch.int64, device=dev)
+    ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+    st_f, st_r = fresh(), fresh()
+    for it in range(3):
+        a = (torch.randn(M, K, generator=g) * (1.0 + it)).to(dev)
+        ap = _planes(a)
+        acc_f, acc_r = ops.new_minmax(dev), ops.new_minmax(dev)
+        out_f = ops.gemm(Op.full(ap), Op.full(bp), M, N, K, PAIRS_EXACT_B, col_scale=scale, bias=bias, minmax=acc_f,
+                         observer=(st_f[0], st_f[1], st_f[2], st_f[3], on, on, 0.01, 0, 127, False, ticket))
+        out_r = ops.gemm(Op.full(ap), Op.full(bp), M, N, K, PAIRS_EXACT_B, col_scale=scale, bias=bias, minmax=acc_r)
+        ops.obs_update(acc_r, on, on, st_r[0], st_r[1], st_r[2], st_r[3], 0.01, 0, 127, False)
+        torch.cuda.synchronize()
+        assert torch.equal(out_f, out_r) and torch.equal(acc_f, acc_r)
+        for x, y in zip(st_f, st_r):
+            assert torch.equal(x, y)
+        assert int(ticket) == 0
+    assert float(st_f[2]) != 1.0
