@@ -87,6 +87,16 @@ struct Cfg {
   static_assert(EPI == 0 || BN % 64 == 0, "plane output works on 64-column chunks");
 };
 
+#ifdef QV_ATTN_DEBUG      // timeline-instrumented build (make debug): clock64 events of CTA 0, read back with qv_gemm_debug_read
+__device__ unsigned long long qv_gemm_dbg[3][4096];
+__device__ __forceinline__ void gdbg(int who, int& n, int tag) {
+  if (blockIdx.x == 0 && n < 4096) qv_gemm_dbg[who][n++] = (static_cast<unsigned long long>(tag) << 48) | (clock64() & 0xffffffffffffULL);
+}
+#define GDBG(who, tag) gdbg(who, gdbg_n, tag)
+#else
+#define GDBG(who, tag)
+#endif
+
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 // EPI = 0: fp32 output;  EPI = 1: bf16 hi/lo plane output (the operand format of the next GEMM), optional GELU;
@@ -155,6 +165,9 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+#ifdef QV_ATTN_DEBUG
+      int gdbg_n = 0;
+#endif
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         const int n_blk = item % p.tiles_n;
         const int m_blk = (item / p.tiles_n) % p.tiles_m;
@@ -167,7 +180,9 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int kb0 = z * p.kb_per_split;
         const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
+          GDBG(0, 1);
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          GDBG(0, 2);
           mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + NA * A_PLANE_BYTES;
@@ -198,16 +213,19 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else if (warp == 1) {
+#ifdef QV_GEMM_UNIFORM_ISSUE
     // =============================== MMA issuer ===============================
-    // (A whole-warp walk with an elected issuing lane -- which keeps operands in uniform registers and removed a per-MMA
-    // R2UR/ELECT waterfall in the attention kernels, where N = 64 instructions are issue-bound -- measured 3-4 % SLOWER here:
-    // a 128 x 192 x 16 MMA executes for as long as its issue sequence takes, and 32 polling lanes steal issue slots from the
-    // two epilogue warps sharing the sub-partition.)
-    if (lane == 0) {
+    // The whole warp walks the tile / k-block schedule (barrier waits included) and ONE elected lane issues the MMAs and
+    // commits.  With warp-uniform control flow and descriptors formed as "stage base + compile-time offset", ptxas keeps the
+    // operands in uniform registers; under an `if (lane == 0)` region every tcgen05.mma paid an R2UR + ELECT waterfall loop
+    // (~90 cycles of issue per instruction -- as long as a 128 x 192 x 16 MMA takes to execute).
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
       constexpr uint32_t a_lbo = A_MN ? 8192u : 16u, b_lbo = B_MN ? 8192u : 16u;
       constexpr uint32_t a_kadv = A_MN ? (UMMA_K * 128u) : (UMMA_K * 2u);   // bytes per 16-deep k step
       constexpr uint32_t b_kadv = B_MN ? (UMMA_K * 128u) : (UMMA_K * 2u);
+      const uint64_t desc_a0 = umma_smem_desc(smem_u32(smem), a_lbo, 1024u);                          // stage 0, plane 0
+      const uint64_t desc_b0 = umma_smem_desc(smem_u32(smem) + NA * A_PLANE_BYTES, b_lbo, 1024u);
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
@@ -222,6 +240,64 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * BN);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t sa = desc_a0 + static_cast<uint64_t>(stage) * (C::STAGE_BYTES >> 4);
+          const uint64_t sb = desc_b0 + static_cast<uint64_t>(stage) * (C::STAGE_BYTES >> 4);
+          const uint32_t first = (kb > kb0) ? 1u : 0u;
+          if (elect_one()) {
+#pragma unroll
+            for (int pr = 0; pr < C::NPAIRS; ++pr) {
+              // pair order: (0,0) [,(0,1)] [,(1,0)]  -- for NB == 1 the second pair is (1,0)
+              const int pa = (NB == 1) ? pr : (pr == 2 ? 1 : 0);
+              const int pb = (NB == 1) ? 0 : (pr == 1 ? 1 : 0);
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                const uint64_t da = sa + ((pa * A_PLANE_BYTES + k * a_kadv) >> 4);
+                const uint64_t db = sb + ((pb * C::B_PLANE_BYTES + k * b_kadv) >> 4);
+                umma_bf16(d_tmem, da, db, idesc, (pr > 0 || k > 0) ? 1u : first);
+              }
+            }
+            umma_commit(&empty_bar[stage]);     // frees this smem stage once the MMAs have read it
+          }
+          __syncwarp();
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (elect_one()) umma_commit(&tmem_full[buf]);   // accumulator complete -> epilogue
+        __syncwarp();
+      }
+    }
+#else
+    // =============================== MMA issuer ===============================
+    // (A whole-warp walk with an elected issuing lane -- which keeps operands in uniform registers and removed a per-MMA
+    // R2UR/ELECT waterfall in the attention kernels, where N = 64 instructions are issue-bound -- measured 3-4 % SLOWER here:
+    // a 128 x 192 x 16 MMA executes for as long as its issue sequence takes, and 32 polling lanes steal issue slots from the
+    // two epilogue warps sharing the sub-partition.)
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+      constexpr uint32_t a_lbo = A_MN ? 8192u : 16u, b_lbo = B_MN ? 8192u : 16u;
+      constexpr uint32_t a_kadv = A_MN ? (UMMA_K * 128u) : (UMMA_K * 2u);   // bytes per 16-deep k step
+      constexpr uint32_t b_kadv = B_MN ? (UMMA_K * 128u) : (UMMA_K * 2u);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+#ifdef QV_ATTN_DEBUG
+      int gdbg_n = 0;
+#endif
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
+        const int z = p.nbatch > 1 ? 0 : item / (p.tiles_n * p.tiles_m);
+        const int kb0 = z * p.kb_per_split;
+        const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
+        const int buf = local & 1;
+        const uint32_t use = static_cast<uint32_t>(local >> 1);      // n-th use of this TMEM buffer
+        GDBG(1, 10);
+        mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);
+        GDBG(1, 11);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          GDBG(1, 12);
+          mbar_wait(&full_bar[stage], phase);
+          GDBG(1, 13);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint32_t sb = sa + NA * A_PLANE_BYTES;
@@ -238,11 +314,13 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
           }
           umma_commit(&empty_bar[stage]);       // frees this smem stage once the MMAs have read it
+          GDBG(1, 14);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full[buf]);           // accumulator complete -> epilogue
       }
     }
+#endif
   } else {
     // =============================== epilogue (8 warps) ===============================
     // Two warps per TMEM lane quarter: warp (q, par) takes the column chunks whose index has parity `par`, so every SM
@@ -385,6 +463,9 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const float alpha = p.alpha ? __ldg(p.alpha) : 1.0f;
     const bool raw = p.splits > 1;
     int local = 0;
+#ifdef QV_ATTN_DEBUG
+    int gdbg_n = (threadIdx.x == 64) ? 0 : 4096;
+#endif
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
       const int n_blk = item % p.tiles_n;
       const int m_blk = (item / p.tiles_n) % p.tiles_m;
@@ -395,7 +476,9 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int o_col = raw ? 0 : p.o_col0 + bi * p.o_col_inner;
       const int buf = local & 1;
       const uint32_t use = static_cast<uint32_t>(local >> 1);
+      GDBG(2, 20);
       mbar_wait(&tmem_full[buf], use & 1);
+      GDBG(2, 21);
       tc_fence_after();
       const int row0 = m_blk * BM + q * 32;                     // first row of this warp's 32-row slab
       const bool row_ok = static_cast<int64_t>(row0 + lane) < p.M;
@@ -415,6 +498,7 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         } else {                                                // this warp's last chunk is in registers
           tc_fence_before();
           mbar_arrive(&tmem_empty[buf]);
+          GDBG(2, 22);
         }
         const int64_t n0 = static_cast<int64_t>(n_blk) * BN + c0;
         if (n0 >= p.N || static_cast<int64_t>(row0) >= p.M) continue;      // warp-uniform: nothing to store
@@ -749,3 +833,13 @@ extern "C" int qv_splitk_reduce(const float* workspace, int32_t splits, int64_t 
                                                                                  alpha, mask, out, accumulate);
   return qv_check_launch("qv_splitk_reduce");
 }
+
+#ifdef QV_ATTN_DEBUG
+extern "C" int qv_gemm_debug_read(unsigned long long* host_out) {   // host_out: [3][4096]
+  return cudaMemcpyFromSymbol(host_out, qv_gemm_dbg, sizeof(unsigned long long) * 3 * 4096) == cudaSuccess ? 0 : -1;
+}
+extern "C" int qv_gemm_debug_clear() {
+  static unsigned long long z[3 * 4096];
+  return cudaMemcpyToSymbol(qv_gemm_dbg, z, sizeof(z)) == cudaSuccess ? 0 : -1;
+}
+#endif
