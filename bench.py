@@ -139,7 +139,7 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------------------------
 # this repo's arm
 # --------------------------------------------------------------------------------------------------------------------
-def build_models(batch, dev, seed=0, ln_variant="subclass"):
+def build_models(batch, dev, seed=0, ln_variant="subclass", prepare=True):
     import warnings
     import torch
     from torch.ao.quantization import get_default_qat_qconfig, prepare_qat
@@ -150,8 +150,10 @@ def build_models(batch, dev, seed=0, ln_variant="subclass"):
     teacher = vit.create_model(TEACHER, num_classes=10).eval()
     for p in teacher.parameters():
         p.requires_grad = False
-    # QAT enable block, ref qat_trainer.py:304-308 (fbgemm qconfig = per-channel symmetric weights: north_star)
     student.train()
+    if not prepare:          # the epochs before qat_start_epoch (ref qat_trainer.py:300-316 not yet taken)
+        return student.to(dev), teacher.to(dev)
+    # QAT enable block, ref qat_trainer.py:304-308 (fbgemm qconfig = per-channel symmetric weights: north_star)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         student.qconfig = get_default_qat_qconfig("fbgemm")
@@ -189,7 +191,10 @@ def run_ours(args):
     global_batch = 256 if n == 1 else 1024
     batch = global_batch // n
 
-    student, teacher = build_models(batch, dev, ln_variant=args.ln_variant)
+    student, teacher = build_models(batch, dev, ln_variant=args.ln_variant, prepare=not args.pre_qat)
+    if args.pre_qat:
+        from qatvit_b200.plain import PlainDistillStep
+        QATDistillStep = PlainDistillStep          # noqa: N806 -- same call surface; no observers to synchronise
     sync = None
     if world > 1:
         from qatvit_b200.ddp import GradSync
@@ -198,11 +203,11 @@ def run_ours(args):
             if t.numel() > 0:
                 dist.broadcast(t.data, src=0)
         # one flat buffer: [gradients | activation-observer min/max tail]; built before the engine so .grad views alias it
-        n_grad = QATDistillStep.count_trainable(student)
-        n_obs = QATDistillStep.count_activation_observers(student)
+        n_grad = sum(p.numel() for p in student.parameters() if p.requires_grad)
+        n_obs = 0 if args.pre_qat else QATDistillStep.count_activation_observers(student)
         sync = GradSync(n_grad, n_obs, dev)
         step = QATDistillStep(student, teacher, batch, HP, grad_buffer=sync.grad_arena)
-        sync.bind_observers(step.activation_observers())
+        sync.bind_observers([] if args.pre_qat else step.activation_observers())
     else:
         step = QATDistillStep(student, teacher, batch, HP)
     arena = step.grad_arena
@@ -354,7 +359,10 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": n, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32 (tcgen05 bf16 hi/lo planes, fp32 accumulate; integer fake-quant codes exact)", "data": "synthetic",
-        "config": {"workload": "ViT-B/16 teacher -> ViT-S/16 QAT student distillation step (KL+CE), batch 256, 1x B200"
+        "config": {"workload": ("PRE-QAT epoch variant (student not yet prepared, no fake-quant; ref qat_trainer.py:333-361 before "
+                                "qat_start_epoch): ViT-B/16 teacher -> ViT-S/16 student distillation step, batch 256, 1x B200")
+                   if (n == 1 and args.pre_qat) else
+                   "ViT-B/16 teacher -> ViT-S/16 QAT student distillation step (KL+CE), batch 256, 1x B200"
                    if n == 1 else f"same distillation step data-parallel, global batch 1024 at {n} B200 with NCCL gradient allreduce",
                    "global_batch": global_batch, "per_gpu_batch": batch, "qconfig": "fbgemm", "layernorm": args.ln_variant, "image": "3x224x224",
                    "parallelism": f"dp{n}", "l2": "per-step working set (~20 GB of activations) >> 126 MB L2; no flush needed",
@@ -387,6 +395,9 @@ def main():
     ap.add_argument("--ln-variant", default="subclass", choices=["subclass", "plain"],
                     help="timm LayerNorm flavour: 'subclass' (timm.layers.LayerNorm, not observed: 101 fake-quant modules, the "
                          "primary target) or 'plain' (nn.LayerNorm, observed by prepare_qat: 126) -- SURVEY.md section 0.6")
+    ap.add_argument("--pre-qat", action="store_true",
+                    help="time the pre-QAT epoch step instead (unprepared student, qatvit_b200.plain.PlainDistillStep) -- not the "
+                         "BASELINE metric, a side measurement of SURVEY.md section 8f item 3")
     ap.add_argument("--torch-optimizer", action="store_true", help="torch AdamW + clip on the arena instead of qv_clip_adamw")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -1,0 +1,301 @@
+"""Pre-QAT epochs on the same kernels (ref/src/training/qat_trainer.py:286,320,333-361 with
+``qat_enabled == False``): before ``qat_start_epoch`` the reference trains the UNPREPARED ``QATWrapper`` student (identity
+Quant/DeQuant stubs, plain nn.Linear / nn.Conv2d, no fake-quant) against the same frozen teacher with the same KL + CE loss.
+
+``PlainDistillStep`` is that step on the tcgen05 GEMM family: every fp32 tensor that feeds a GEMM travels as bf16 hi/lo planes,
+three MMAs per product, fp32 accumulation (fp32-grade results, ~2^-16 relative) -- the reference's non-AMP arithmetic; its
+``--amp`` variant (fp16 autocast + GradScaler) is reproduced to fp16 accuracy, not bit for bit.  Weights are re-split into planes
+every step (they change every step); dgrad reads the same [N, K] planes as an MN-major operand, so no transposed copy exists.
+Attention uses the unfused kernels (scores / probabilities as planes in HBM, saved for backward): the fused integer-code
+kernels need fake-quantised q, k, v.  Gradients land in one flat arena exactly like the QAT engine's, so the optimizer and the
+gradient all-reduce are shared (qatvit_b200.optim.FusedClipAdamW, qatvit_b200.ddp.GradSync).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .engine import TeacherEngine, _ViTDims, _attention_forward, _round_up, wgrad_splits
+from .ops import Op, Out, PAIRS_FP32
+
+
+class _Lin:
+    """One plain Linear / Conv2d-as-GEMM: parameters + the per-step hi/lo planes of its weight."""
+
+    def __init__(self, mod: nn.Module, dev):
+        self.mod = mod
+        self.weight, self.bias = mod.weight, mod.bias
+        self.N = mod.weight.shape[0]
+        self.K = mod.weight.numel() // self.N
+        self.planes = torch.empty(2, self.N, self.K, dtype=torch.bfloat16, device=dev)
+
+    def split(self) -> None:
+        ops.split_planes(self.weight.detach().reshape(self.N, self.K), self.planes)
+
+
+class PlainStudentEngine:
+    """Forward + hand-written backward of the unprepared ``QATWrapper`` student (no fake-quant anywhere)."""
+
+    def __init__(self, student: nn.Module, batch: int, hparams: Dict, grad_buffer: Optional[torch.Tensor] = None):
+        for m in student.modules():
+            if type(m).__name__ == "FusedMovingAvgObsFakeQuantize":
+                raise RuntimeError("qatvit_b200: PlainStudentEngine takes the student BEFORE prepare_qat (use QATDistillStep after)")
+        self.student = student
+        vit = self.vit = student.model
+        dev = next(student.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("qatvit_b200: the student must live on a CUDA device (there is no CPU fallback)")
+        self.dev = dev
+        self.hp_ = dict(hparams)
+        d = self.d = _ViTDims(vit, batch)
+        self.sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        L, M, D, F, B, T = d.L, d.M, d.D, d.F, d.B, d.T
+        bf, f32 = torch.bfloat16, torch.float32
+        e = lambda *s, dt=f32: torch.empty(*s, dtype=dt, device=dev)  # noqa: E731
+        self.conv = _Lin(vit.patch_embed.proj, dev)
+        self.lin: List[Dict[str, _Lin]] = [dict(qkv=_Lin(b.attn.qkv, dev), proj=_Lin(b.attn.proj, dev), fc1=_Lin(b.mlp.fc1, dev),
+                                                fc2=_Lin(b.mlp.fc2, dev)) for b in vit.blocks]
+        self.all_linears = [self.conv] + [q for blk in self.lin for q in blk.values()]
+        # ---- flat gradient arena ----
+        self.params = [p for p in student.parameters() if p.requires_grad]
+        total = sum(p.numel() for p in self.params)
+        if grad_buffer is not None:
+            if grad_buffer.numel() != total or grad_buffer.dtype != f32 or grad_buffer.device != dev:
+                raise ValueError("grad_buffer must be a flat fp32 tensor with one element per trainable parameter")
+            self.grad_arena = grad_buffer
+        else:
+            self.grad_arena = torch.zeros(total, dtype=f32, device=dev)
+        self._goff, self._grad_views, off = {}, [], 0
+        for p in self.params:
+            self._grad_views.append(self.grad_arena[off:off + p.numel()].view_as(p))
+            self._goff[id(p)] = off
+            off += p.numel()
+        self.attach_grads()
+        # ---- forward activations (saved for backward) ----
+        self.img_planes = e(2, B * d.P, d.Kc, dt=bf)
+        self.p_raw = e(B * d.P, D)
+        self.x_in = [e(M, D) for _ in range(L)]
+        self.x_mid = [e(M, D) for _ in range(L)]
+        self.h1p = [e(2, M, D, dt=bf) for _ in range(L)]
+        self.h2p = [e(2, M, D, dt=bf) for _ in range(L)]
+        self.qkvp = [e(2, M, 3 * D, dt=bf) for _ in range(L)]
+        self.Pp = [torch.zeros(2, B * d.H * T, d.ldP, dtype=bf, device=dev) for _ in range(L)]
+        self.op = [e(2, M, D, dt=bf) for _ in range(L)]
+        self.a_raw = e(M, D)
+        self.f_raw = [e(M, F) for _ in range(L)]
+        self.gelp = [e(2, M, F, dt=bf) for _ in range(L)]
+        self.m_raw = e(M, D)
+        self.stats1 = [(e(M), e(M)) for _ in range(L)]
+        self.stats2 = [(e(M), e(M)) for _ in range(L)]
+        self.S = e(B * d.H * T, d.ldS)
+        self.o = e(M, D)
+        self.xcls, self.xn = e(B, D), e(B, D)
+        self.statsF = (e(B), e(B))
+        self.logits = e(B, d.C)
+        self.loss3 = e(3)
+        self.g_logits = e(B, d.C)
+        # ---- backward scratch ----
+        self.gx = [e(M, D), e(M, D)]
+        self.g_xn = e(B, D)
+        self.gpD = e(2, M, D, dt=bf)
+        self.gpF = e(2, M, F, dt=bf)
+        self.gp3 = e(2, M, 3 * D, dt=bf)
+        self.gpP = e(2, B * d.P, D, dt=bf)
+        self.g_big = e(M, F)
+        self.g_h = e(M, D)
+        self.g_o = e(M, D)
+        self.g_op = e(2, M, D, dt=bf)
+        self.g_qkv = e(M, 3 * D)
+        self.dP = e(B * d.H * T, d.ldS)
+        self.dSp = torch.zeros(2, B * d.H * T, d.ldP, dtype=bf, device=dev)
+        self.rpb = 64
+        self.bias_part = e(-(-M // self.rpb) * max(F, 3 * D))
+        self.ln_part = e(-(-M // self.rpb), 2, D)
+        self._splits, max_ws = {}, 0
+        for (n, k, kdim) in [(3 * D, D, M), (D, D, M), (F, D, M), (D, F, M), (D, d.Kc, B * d.P)]:
+            s = wgrad_splits(n, k, kdim, self.sms)
+            self._splits[(n, k)] = s
+            max_ws = max(max_ws, s * n * k)
+        self.ws = e(max_ws)
+
+    # ------------------------------------------------------------------------------------------
+    def attach_grads(self) -> None:
+        for p, g in zip(self.params, self._grad_views):
+            p.grad = g
+
+    def _grad(self, p: torch.Tensor) -> torch.Tensor:
+        off = self._goff[id(p)]
+        return self.grad_arena[off:off + p.numel()]
+
+    def _ln_param_grads(self, norm: nn.Module, nblk: int) -> None:
+        D = self.d.D
+        tmp = torch.empty(2 * D, device=self.dev)
+        ops.colsum_reduce(self.ln_part, nblk, 2 * D, tmp)
+        self._grad(norm.weight).copy_(tmp[:D])
+        self._grad(norm.bias).copy_(tmp[D:])
+
+    def _fwd(self, ql: _Lin, a_planes, M, out=None, out_planes=None) -> None:
+        ops.gemm(Op.full(a_planes), Op.full(ql.planes), M, ql.N, ql.K, PAIRS_FP32, out=out, out_planes=out_planes,
+                 bias=ql.bias.detach())
+
+    def forward(self, images: torch.Tensor, labels: Optional[torch.Tensor], teacher_logits: Optional[torch.Tensor],
+                teacher_ready=None) -> Optional[torch.Tensor]:
+        d, v = self.d, self.vit
+        B, T, D, F, M, L = d.B, d.T, d.D, d.F, d.M, d.L
+        if tuple(images.shape) != (B, d.in_ch, d.HW, d.HW):
+            raise RuntimeError(f"student engine built for batch {B}, got {tuple(images.shape)}")
+        for ql in self.all_linears:
+            ql.split()
+        ops.im2col_fq(images, None, B, d.in_ch, d.HW, d.ps, self.img_planes)
+        self._fwd(self.conv, self.img_planes, B * d.P, out=self.p_raw)
+        ops.embed_fwd(self.p_raw, None, v.cls_token.detach().reshape(-1), v.pos_embed.detach().reshape(T, D), B, d.P, D, self.x_in[0])
+        for l, blk in enumerate(v.blocks):
+            ql = self.lin[l]
+            if l == 0:
+                ops.resid_ln_fwd(self.x_in[0], None, None, blk.norm1.weight.detach(), blk.norm1.bias.detach(), d.eps, M, D,
+                                 h_planes=self.h1p[0], mean=self.stats1[0][0], rstd=self.stats1[0][1])
+            self._fwd(ql["qkv"], self.h1p[l], M, out_planes=self.qkvp[l])
+            _attention_forward(d, self.qkvp[l], self.S, self.Pp[l], self.o)
+            ops.split_planes(self.o, self.op[l])
+            self._fwd(ql["proj"], self.op[l], M, out=self.a_raw)
+            ops.resid_ln_fwd(self.x_in[l], self.a_raw, None, blk.norm2.weight.detach(), blk.norm2.bias.detach(), d.eps, M, D,
+                             x_out=self.x_mid[l], h_planes=self.h2p[l], mean=self.stats2[l][0], rstd=self.stats2[l][1])
+            self._fwd(ql["fc1"], self.h2p[l], M, out=self.f_raw[l])
+            ops.act_planes(self.f_raw[l], None, True, self.gelp[l])
+            self._fwd(ql["fc2"], self.gelp[l], M, out=self.m_raw)
+            if l + 1 < L:
+                nb = v.blocks[l + 1]
+                ops.resid_ln_fwd(self.x_mid[l], self.m_raw, None, nb.norm1.weight.detach(), nb.norm1.bias.detach(), d.eps, M, D,
+                                 x_out=self.x_in[l + 1], h_planes=self.h1p[l + 1], mean=self.stats1[l + 1][0],
+                                 rstd=self.stats1[l + 1][1])
+            else:
+                ops.resid_ln_fwd(self.x_mid[l], self.m_raw, None, v.norm.weight.detach(), v.norm.bias.detach(), d.eps, B, D,
+                                 in_row_stride=T, x_out=self.xcls, h_f32=self.xn, mean=self.statsF[0], rstd=self.statsF[1])
+        ops.head_fwd(self.xn, v.head.weight.detach(), v.head.bias.detach(), B, D, d.C, self.logits)
+        if labels is None:
+            return None
+        hp = self.hp_
+        if teacher_ready is not None:
+            torch.cuda.current_stream().wait_event(teacher_ready)
+        ops.kd_ce_loss(self.logits, teacher_logits, labels, hp["kd_temp"], hp["kd_alpha"], hp["label_smoothing"], out3=self.loss3,
+                       grad=self.g_logits)
+        return self.loss3
+
+    def predict(self, images: torch.Tensor) -> torch.Tensor:
+        self.forward(images, None, None)
+        return self.logits
+
+    # ------------------------------------------------------------------------------------------
+    def _gp(self, g, y_raw, ql: _Lin, gelu: bool, R: int, out_planes, remap=(0, 0)) -> None:
+        """gradient planes of a plain Linear: g [* gelu'(y_raw)] -> hi/lo planes; bias grad = column sums."""
+        nblk = -(-R // self.rpb)
+        part = self.bias_part[:nblk * ql.N].view(nblk, ql.N)
+        ops.gp_planes(g, y_raw, None, None, False, gelu, R, ql.N, out_planes, part, self.rpb, remap[0], remap[1])
+        ops.colsum_reduce(part, nblk, ql.N, self._grad(ql.bias))
+
+    def _dgrad(self, ql: _Lin, gp, M: int, out) -> None:
+        # g[M, N] @ W[N, K]: the weight planes as they lie ([contraction N][K]) are the MN-major B operand
+        ops.gemm(Op.full(gp), Op.full(ql.planes, mn_major=True), M, ql.K, ql.N, PAIRS_FP32, out=out)
+
+    def _wgrad(self, ql: _Lin, gp, x_planes, kdim: int) -> None:
+        s = self._splits[(ql.N, ql.K)]
+        if s > 1:
+            ops.gemm(Op.full(gp, mn_major=True), Op.full(x_planes, mn_major=True), ql.N, ql.K, kdim, PAIRS_FP32, splits=s,
+                     workspace=self.ws)
+        else:
+            ops.gemm(Op.full(gp, mn_major=True), Op.full(x_planes, mn_major=True), ql.N, ql.K, kdim, PAIRS_FP32,
+                     out=self.ws[:ql.N * ql.K].view(ql.N, ql.K))
+        ops.splitk_reduce(self.ws, s, ql.N, ql.K, self._grad(ql.weight))
+
+    def backward(self, grads_final_from=None) -> None:
+        d, v = self.d, self.vit
+        B, T, D, F, M, L, H = d.B, d.T, d.D, d.F, d.M, d.L, d.H
+        BH = B * H
+        ops.head_bwd(self.g_logits, self.xn, v.head.weight.detach(), None, B, D, d.C, self.g_xn, self._grad(v.head.weight),
+                     self._grad(v.head.bias))
+        gx, gx2 = self.gx
+        gx.zero_()
+        ops.ln_bwd(self.g_xn, self.xcls, self.statsF[0], self.statsF[1], v.norm.weight.detach(), None, B, D, gx, self.ln_part,
+                   self.rpb, out_row_stride=T)
+        self._ln_param_grads(v.norm, -(-B // self.rpb))
+        nblk_ln = -(-M // self.rpb)
+        for l in range(L - 1, -1, -1):
+            blk, ql = v.blocks[l], self.lin[l]
+            # ---- MLP ----
+            self._gp(gx, None, ql["fc2"], False, M, self.gpD)
+            self._dgrad(ql["fc2"], self.gpD, M, self.g_big)
+            self._wgrad(ql["fc2"], self.gpD, self.gelp[l], M)
+            self._gp(self.g_big, self.f_raw[l], ql["fc1"], True, M, self.gpF)
+            self._dgrad(ql["fc1"], self.gpF, M, self.g_h)
+            self._wgrad(ql["fc1"], self.gpF, self.h2p[l], M)
+            ops.ln_bwd(self.g_h, self.x_mid[l], self.stats2[l][0], self.stats2[l][1], blk.norm2.weight.detach(), gx, M, D, gx2,
+                       self.ln_part, self.rpb)
+            self._ln_param_grads(blk.norm2, nblk_ln)
+            # ---- attention (unfused: probabilities saved as planes) ----
+            self._gp(gx2, None, ql["proj"], False, M, self.gpD)
+            self._dgrad(ql["proj"], self.gpD, M, self.g_o)
+            self._wgrad(ql["proj"], self.gpD, self.op[l], M)
+            ops.split_planes(self.g_o, self.g_op)
+            qkvp, Pp = self.qkvp[l], self.Pp[l]
+            ops.gemm(Op.tokens(self.g_op, B, T, 0, 64), Op.tokens(qkvp, B, T, 2 * D, 64), T, T, 64, PAIRS_FP32,
+                     out=Out.per_head(self.dP, BH, H, T, T), nbatch=BH, batch_inner=H)                      # dP = dO V^T
+            ops.attn_ds(Pp, self.dP, d.ldS, BH * T, T, d.attn_scale, self.dSp)
+            ops.gemm(Op.per_head(self.dSp, BH, H, T, T), Op.tokens(qkvp, B, T, D, 64, mn_major=True), T, 64, T, PAIRS_FP32,
+                     out=Out.tokens(self.g_qkv, B, T, 0, 64), nbatch=BH, batch_inner=H)                      # dQ = dS K
+            ops.gemm(Op.per_head(self.dSp, BH, H, T, T, mn_major=True), Op.tokens(qkvp, B, T, 0, 64, mn_major=True), T, 64, T,
+                     PAIRS_FP32, out=Out.tokens(self.g_qkv, B, T, D, 64), nbatch=BH, batch_inner=H)          # dK = dS^T Q
+            ops.gemm(Op.per_head(Pp, BH, H, T, T, mn_major=True), Op.tokens(self.g_op, B, T, 0, 64, mn_major=True), T, 64, T,
+                     PAIRS_FP32, out=Out.tokens(self.g_qkv, B, T, 2 * D, 64), nbatch=BH, batch_inner=H)      # dV = P^T dO
+            self._gp(self.g_qkv, None, ql["qkv"], False, M, self.gp3)
+            self._dgrad(ql["qkv"], self.gp3, M, self.g_h)
+            self._wgrad(ql["qkv"], self.gp3, self.h1p[l], M)
+            ops.ln_bwd(self.g_h, self.x_in[l], self.stats1[l][0], self.stats1[l][1], blk.norm1.weight.detach(), gx2, M, D, gx,
+                       self.ln_part, self.rpb)
+            self._ln_param_grads(blk.norm1, nblk_ln)
+            if grads_final_from is not None:
+                grads_final_from(min(self._goff[id(p)] for p in blk.parameters()))
+        # ---- embeddings ----
+        ops.colsum_rows(gx, B, T * D, T * D, self._grad(v.pos_embed))
+        ops.colsum_rows(gx, B, D, T * D, self._grad(v.cls_token))
+        self._gp(gx, None, self.conv, False, B * d.P, self.gpP, remap=(d.P, T))
+        self._wgrad(self.conv, self.gpP, self.img_planes, B * d.P)
+        if grads_final_from is not None:
+            grads_final_from(0)
+
+
+class PlainDistillStep:
+    """``loss3 = step(images, labels)``: teacher forward (side stream), plain student forward, KL + CE, backward -- the
+    reference's training iteration before QAT is enabled (ref qat_trainer.py:333-361 with qat_enabled == False, no AMP)."""
+
+    def __init__(self, student: nn.Module, teacher: nn.Module, batch: int, hparams: Dict,
+                 grad_buffer: Optional[torch.Tensor] = None):
+        self.student_engine = PlainStudentEngine(student, batch, hparams, grad_buffer=grad_buffer)
+        self.teacher_engine = TeacherEngine(teacher, batch)
+        self.grad_arena = self.student_engine.grad_arena
+        self._tstream = torch.cuda.Stream(device=self.student_engine.dev)
+        self._tdone = torch.cuda.Event()
+
+    def __call__(self, images: torch.Tensor, labels: torch.Tensor, grad_sync=None) -> torch.Tensor:
+        main = torch.cuda.current_stream()
+        if ops.profiling():
+            t_logits = self.teacher_engine.forward(images)
+            out3 = self.student_engine.forward(images, labels, t_logits)
+        else:
+            self._tstream.wait_stream(main)
+            with torch.cuda.stream(self._tstream):
+                t_logits = self.teacher_engine.forward(images)
+                self._tdone.record(self._tstream)
+            out3 = self.student_engine.forward(images, labels, t_logits, teacher_ready=self._tdone)
+        if grad_sync is None:
+            self.student_engine.backward()
+        else:
+            grad_sync.begin_step()
+            self.student_engine.backward(grads_final_from=grad_sync.grads_final_from)
+            grad_sync.end_step()
+        return out3
+
+    def predict(self, images: torch.Tensor) -> torch.Tensor:
+        return self.student_engine.predict(images)

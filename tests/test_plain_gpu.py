@@ -1,0 +1,90 @@
+"""GPU parity of the pre-QAT training step (qatvit_b200.plain.PlainDistillStep) against the reference
+path on CPU: the UNPREPARED QATWrapper student (ref/src/training/qat_trainer.py:333-361 before qat_start_epoch, no AMP) through
+stock fp32 autograd (oracle/vit_ref.py).  No fake-quant means no rounding chaos: loss, logits and every gradient must agree to
+1e-4 relative (north_star tolerance 1e-3)."""
+import copy
+
+import pytest
+import torch
+
+from parity_utils import rel_l2, rel_max
+
+pytestmark = pytest.mark.gpu
+
+
+def _models(sname, tname, img, seed=0):
+    from oracle import vit_ref as vr
+    torch.manual_seed(seed)
+    kw = dict(img_size=img) if img != 224 else {}
+    student = vr.qat_wrapper_cls(prefer_reference=False)(vr.create_model(sname, num_classes=10, **kw))
+    torch.manual_seed(seed + 1)
+    teacher = vr.create_model(tname, num_classes=10, **kw).eval()
+    with torch.no_grad():
+        teacher.head.weight.mul_(8.0)
+        for p in student.parameters():
+            if p.dim() == 1:
+                p.add_(0.02 * torch.randn_like(p))
+    for p in teacher.parameters():
+        p.requires_grad = False
+    return vr, student.train(), teacher
+
+
+@pytest.mark.parametrize("sname,tname,img,B", [("vit_test_tiny", "vit_test_teacher", 64, 4), ("vit_test_tiny", "vit_test_teacher", 96, 3),
+                                               ("vit_small_patch16_224", "vit_base_patch16_224", 224, 4)])
+def test_plain_step_matches_fp32_autograd(cuda_dev, sname, tname, img, B):
+    from qatvit_b200.plain import PlainDistillStep
+    vr, student, teacher = _models(sname, tname, img)
+    hp = dict(vr.DEFAULT_HPARAMS)
+    gpu_student = copy.deepcopy(student).to(cuda_dev)
+    step = PlainDistillStep(gpu_student, copy.deepcopy(teacher).to(cuda_dev), B, hp)
+    for it in range(2):
+        images, labels = vr.synthetic_batch(B, seed=3 + it, img=img)
+        out3 = step(images.to(cuda_dev), labels.to(cuda_dev))
+        torch.cuda.synchronize()
+        loss_ref, s_ref, t_ref = vr.distill_step(student, teacher, images, labels, None, hp, clip=False)
+        assert rel_max(step.teacher_engine.logits, t_ref) < 1e-4
+        assert rel_max(step.student_engine.logits, s_ref) < 1e-4
+        assert abs(float(out3[0]) - float(loss_ref)) <= 1e-5 * abs(float(loss_ref))
+        ref = dict(student.named_parameters())
+        for n, p in gpu_student.named_parameters():
+            assert rel_max(p.grad, ref[n].grad) < 1e-4 and rel_l2(p.grad, ref[n].grad) < 1e-4, (it, n, rel_max(p.grad, ref[n].grad))
+        student.zero_grad(set_to_none=True)
+    # forward only (validation loop)
+    images, _ = vr.synthetic_batch(B, seed=9, img=img)
+    with torch.no_grad():
+        want = student(images)
+    assert rel_max(step.predict(images.to(cuda_dev)), want) < 1e-4
+
+
+def test_plain_then_qat_handover(cuda_dev):
+    """The reference's schedule: plain epochs, then prepare_qat on the SAME parameters (ref qat_trainer.py:300-316).  Train two plain
+    steps with the fused optimizer, prepare, and run the QAT engine on the result: the hand-over keeps every parameter value."""
+    from torch.ao.quantization import get_default_qat_qconfig, prepare_qat
+    from qatvit_b200.engine import QATDistillStep
+    from qatvit_b200.optim import FusedClipAdamW
+    from qatvit_b200.plain import PlainDistillStep
+    vr, student, teacher = _models("vit_test_tiny", "vit_test_teacher", 64)
+    hp = dict(vr.DEFAULT_HPARAMS)
+    B = 4
+    s_gpu, t_gpu = copy.deepcopy(student).to(cuda_dev), copy.deepcopy(teacher).to(cuda_dev)
+    plain = PlainDistillStep(s_gpu, t_gpu, B, hp)
+    opt = FusedClipAdamW(s_gpu.parameters(), plain.grad_arena, lr=hp["lr"], weight_decay=hp["weight_decay"], max_norm=1.0)
+    before = {n: p.detach().clone() for n, p in s_gpu.named_parameters()}
+    for it in range(2):
+        images, labels = vr.synthetic_batch(B, seed=it, img=64)
+        plain(images.to(cuda_dev), labels.to(cuda_dev))
+        opt.step()
+    moved = sum(float((p.detach() - before[n]).abs().sum()) for n, p in s_gpu.named_parameters())
+    assert moved > 0
+    s_gpu.train()
+    s_gpu.qconfig = get_default_qat_qconfig("fbgemm")
+    prepared = prepare_qat(s_gpu, inplace=False).to(cuda_dev).train()
+    for (n, p), (n2, p2) in zip(s_gpu.named_parameters(), prepared.named_parameters()):
+        assert n == n2 and torch.equal(p, p2)
+    qat = QATDistillStep(prepared, t_gpu, B, hp)
+    images, labels = vr.synthetic_batch(B, seed=7, img=64)
+    out3 = qat(images.to(cuda_dev), labels.to(cuda_dev))
+    torch.cuda.synchronize()
+    assert torch.isfinite(out3).all()
+    with pytest.raises(RuntimeError, match="BEFORE prepare_qat"):
+        PlainDistillStep(prepared, t_gpu, B, hp)
