@@ -165,3 +165,37 @@ def test_predict_matches_reference_forward(cuda_dev, backend, ln_variant):
             assert torch.equal(gpu_sd[k].cpu(), ref_sd[k]), k
         elif k.endswith(("min_val", "max_val", "scale")):
             assert rel_max(gpu_sd[k].cpu(), ref_sd[k]) < 1e-6, k
+
+
+@pytest.mark.parametrize("sname,tname,img,B,steps", [("vit_test_tiny", "vit_test_teacher", 64, 4, 12),
+                                                     ("vit_small_patch16_224", "vit_base_patch16_224", 224, 8, 3)])
+def test_side_streams_change_nothing(cuda_dev, monkeypatch, sname, tname, img, B, steps):
+    """The teacher forward and the weight-gradient GEMMs run on side streams (event-ordered).  Every kernel is deterministic, so
+    a run with the overlap on must equal a run with everything on one stream BIT FOR BIT -- loss, every gradient and every
+    observer buffer, step after step with the optimizer in the loop (a missing wait shows up as a difference)."""
+    from qatvit_b200.engine import QATDistillStep
+    from qatvit_b200.optim import FusedClipAdamW
+    vr, prepared, teacher = build_models("fbgemm", sname, tname, img)
+    hp = dict(vr.DEFAULT_HPARAMS)
+    runs = []
+    for overlap in ("1", "0"):
+        monkeypatch.setenv("QV_OVERLAP_TEACHER", overlap)
+        monkeypatch.setenv("QV_OVERLAP_WGRAD", overlap)
+        student = copy.deepcopy(prepared).to(cuda_dev)
+        step = QATDistillStep(student, copy.deepcopy(teacher).to(cuda_dev), B, hp)
+        assert step.overlap_teacher == (overlap == "1") and (step.student_engine._wstream is not None) == (overlap == "1")
+        opt = FusedClipAdamW(student.parameters(), step.grad_arena, lr=1e-3, weight_decay=hp["weight_decay"], max_norm=1.0)
+        trace = []
+        for it in range(steps):
+            images, labels = vr.synthetic_batch(B, seed=100 + it, img=img)
+            out3 = step(images.to(cuda_dev), labels.to(cuda_dev))
+            trace.append((out3.clone(), step.grad_arena.clone()))
+            opt.step()
+        torch.cuda.synchronize()
+        runs.append((trace, {k: v.clone() for k, v in student.state_dict().items()}))
+    (ta, sa), (tb, sb) = runs
+    for it, ((la, ga), (lb, gb)) in enumerate(zip(ta, tb)):
+        assert torch.equal(la, lb), it
+        assert torch.equal(ga, gb), (it, int((ga != gb).sum()))
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
