@@ -124,6 +124,7 @@ qv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   uint64_t* p_ready = bars + 6;             // [2]
   uint64_t* o_full = bars + 8;              // [2]
   uint64_t* tmem_free = bars + 10;          // [2]
+  uint64_t* delta_ready = bars + 10; // [2] rows 128.. of delta (item parity) written by the output warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5;
@@ -387,8 +388,12 @@ int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap&
 // memory while the item's tiles are still in flight), so a chunk needs no row-wide reduction before it can be processed.
 // All second-stage products are TS-mode MMAs (A from TMEM); the same [tokens x 64] shared-memory tiles serve as K-major
 // operands of the first stage and MN-major operands of the second.
-// TMEM: buffer b in {0,1}: S_b [128 b, +64) | R_b [128 b + 64, +64) ;  ACC0 [256,320) (dQ / dV) ;  ACC1 [320,384) (dK).
-// Warps: 0 TMA, 1 MMA, 2-9 compute (two warps per TMEM lane quarter, one 32-column piece of the chunk each).
+// TMEM: buffer b in {0,1}: S_b [128 b, +64) | R_b [128 b + 64, +64) ;  accumulator set p in {0,1} (sub-pass parity):
+// ACC0 [256 + 128 p, +64) (dQ / dV), ACC1 [320 + 128 p, +64) (dK).
+// Warps: 0 TMA, 1 MMA, 2-5 CHUNK warps (one per TMEM lane quarter: S / dP chunk -> dz / P^T), 6-9 OUTPUT warps (one per lane
+// quarter: drain accumulator set p of sub-pass n -- mask, hi/lo split, column sums, staging, TMA -- while the chunk warps and
+// the tensor pipe are already in sub-pass n + 1; the chunk warps never touch an accumulator, so nothing on the MMA thread's
+// critical path waits for an output stage any more).
 // ====================================================================================================================
 // 28 KB tiles: 224 token rows x 64 bf16 (T <= 224; rows >= T zero-filled by TMA).  The second 128-row MMA tile reads 32 rows
 // past its end (the next tile's head): those lanes are tokens >= 224 > T, whose results are never stored.
@@ -396,7 +401,7 @@ constexpr int BW_TILE_ROWS = 224;
 constexpr int BW_TILE_BYTES = BW_TILE_ROWS * HD * 2;
 constexpr int BW_STAGE_BYTES = 8 * 2 * 4096;    // per compute warp: two 4 KB staging buffers (y tile in, gradient tile out)
 constexpr int BW_SMEM_BYTES = 5 * BW_TILE_BYTES + 4096 /*lse, delta*/ + BW_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr uint32_t BW_ACC0_COL = 256, BW_ACC1_COL = 320;
+constexpr uint32_t BW_ACC_COL = 256;             // accumulator set p (sub-pass parity): ACC0 at 256 + 128 p (dQ / dV), ACC1 64 further (dK)
 
 struct AttnBwdParams {
   int32_t B, T, H;
@@ -422,7 +427,7 @@ struct AttnBwdParams {
 };
 
 #ifdef QV_ATTN_DEBUG
-__device__ unsigned long long qv_dbg_buf[2][8192];
+__device__ unsigned long long qv_dbg_buf[3][8192];
 __device__ __forceinline__ void dbg_event(int who, int& n, int tag) {
   if (blockIdx.x == 0 && n < 8192) qv_dbg_buf[who][n++] = (static_cast<unsigned long long>(tag) << 48) | (clock64() & 0xffffffffffffULL);
 }
@@ -447,17 +452,18 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
   uint8_t* sDOh = sV + BW_TILE_BYTES;
   uint8_t* sDOl = sDOh + BW_TILE_BYTES;
   float* lse2_s = reinterpret_cast<float*>(sDOl + BW_TILE_BYTES);   // [256] lse * log2(e)
-  float* delta_s = lse2_s + 256;                                     // [256] (dO . O) / s
-  uint8_t* stage_s = reinterpret_cast<uint8_t*>(delta_s + 768);    // [8 warps][2][4 KB], 1024-byte aligned
+  float* delta_all = lse2_s + 256;                                   // [2 item parities][256] (dO . O) / s
+  uint8_t* stage_s = reinterpret_cast<uint8_t*>(lse2_s + 1024);     // [4 output warps][4][4 KB], 1024-byte aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(stage_s + BW_STAGE_BYTES);
   uint64_t* ld_full = bars + 0;
   uint64_t* ld_empty = bars + 1;
-  uint64_t* mma1_done = bars + 2;   // [2]
-  uint64_t* cmp_done = bars + 4;    // [2]
-  uint64_t* acc_done = bars + 6;
-  uint64_t* epi_done = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-  uint64_t* y_bar = bars + 9;       // [8 warps][2]: y tile landed in staging buffer k of compute warp w
+  uint64_t* mma1_done = bars + 2;    // [2] first-stage products of chunk buffer b landed in TMEM
+  uint64_t* cmp_done = bars + 4;     // [2] chunk warps have turned buffer b into dz / P^T
+  uint64_t* acc_done = bars + 6;     // [2] accumulator set p complete
+  uint64_t* epi_done = bars + 8;     // [2] accumulator set p drained by the output warps
+  uint64_t* delta_ready = bars + 10; // [2] rows 128.. of delta (item parity) written by the output warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* y_bar = bars + 13;       // [4 output warps][4]: y tile landed in staging buffer k
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -475,10 +481,11 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
     mbar_init(ld_empty, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&mma1_done[b], 1);
-      mbar_init(&cmp_done[b], 256);
+      mbar_init(&cmp_done[b], 128);
+      mbar_init(&acc_done[b], 1);
+      mbar_init(&epi_done[b], 128);
+      mbar_init(&delta_ready[b], 128);
     }
-    mbar_init(acc_done, 1);
-    mbar_init(epi_done, 256);
     if constexpr (FUSED) {
       prefetch_tensormap(&map_y);
       for (int w = 0; w < 16; ++w) mbar_init(&y_bar[w], 1);
@@ -491,6 +498,45 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+
+  // delta_i = (dO_i . O_i) / s for token rows [row_lo, row_lo + 128) of item (b, h) from global memory: 8 lanes per row, 8 columns
+  // each, 16 independent 16-byte loads in flight per lane; `w4` = this warp's index 0..3 inside its group of four.
+  auto delta_rows = [&](float* dst, int b, int h, int row_lo, int w4, float inv_s) {
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      uint4 oh[4], ol[4], dh[4], dl[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = row_lo + (half * 4 + u) * 16 + w4 * 4 + (lane >> 3);
+        if (r < p.T) {
+          const int64_t grow = static_cast<int64_t>(b) * p.T + r;
+          const int col = h * HD + (lane & 7) * 8;
+          oh[u] = __ldg(reinterpret_cast<const uint4*>(p.o_planes + grow * p.o_ld + col));
+          ol[u] = __ldg(reinterpret_cast<const uint4*>(p.o_planes + p.o_plane_stride + grow * p.o_ld + col));
+          dh[u] = __ldg(reinterpret_cast<const uint4*>(p.do_planes + grow * p.do_ld + col));
+          dl[u] = __ldg(reinterpret_cast<const uint4*>(p.do_planes + p.do_plane_stride + grow * p.do_ld + col));
+        } else {
+          oh[u] = ol[u] = dh[u] = dl[u] = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = row_lo + (half * 4 + u) * 16 + w4 * 4 + (lane >> 3);
+        const uint32_t ohw[4] = {oh[u].x, oh[u].y, oh[u].z, oh[u].w}, olw[4] = {ol[u].x, ol[u].y, ol[u].z, ol[u].w};
+        const uint32_t dhw[4] = {dh[u].x, dh[u].y, dh[u].z, dh[u].w}, dlw[4] = {dl[u].x, dl[u].y, dl[u].z, dl[u].w};
+        float dot = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          dot = fmaf(bf16lo_f(ohw[e]) + bf16lo_f(olw[e]), bf16lo_f(dhw[e]) + bf16lo_f(dlw[e]), dot);
+          dot = fmaf(bf16hi_f(ohw[e]) + bf16hi_f(olw[e]), bf16hi_f(dhw[e]) + bf16hi_f(dlw[e]), dot);
+        }
+        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+        if ((lane & 7) == 0) dst[r] = dot * inv_s;
+      }
+    }
+  };
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
@@ -547,11 +593,11 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         }
         __syncwarp();
       };
-      auto mma2 = [&](int sub, int c, uint32_t buf) {
+      auto mma2 = [&](int sub, int c, uint32_t buf, uint32_t aset) {
         const int ks = (c == nch - 1) ? (w_tail >> 4) : 4;
         const uint32_t S = tmem_base + buf * 128u, R = S + 64u;
         const uint64_t rows = static_cast<uint64_t>(c) * 512u;
-        const uint32_t acc0 = tmem_base + BW_ACC0_COL, acc1 = tmem_base + BW_ACC1_COL;
+        const uint32_t acc0 = tmem_base + BW_ACC_COL + aset * 128u, acc1 = acc0 + 64u;
         const bool pa = sub < mt;
         const uint64_t bK = mK + rows, bQ = mQ + rows, bDh = mDh + rows, bDl = mDl + rows;   // operands formed warp-uniformly
         const uint32_t first0 = c > 0 ? 1u : 0u;
@@ -601,14 +647,15 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
             DBG(0, 3);
             mbar_wait(&cmp_done[st & 1], (st >> 1) & 1);
             DBG(0, 4);
-            if (c == 0) mbar_wait(epi_done, (nsp & 1) ^ 1);              // accumulators of the previous sub-pass drained
+            // accumulator set nsp & 1 was last used by sub-pass nsp - 2: the output warps must have drained it
+            if (c == 0) mbar_wait(&epi_done[nsp & 1], ((nsp >> 1) & 1) ^ 1);
             tc_fence_after();
             DBG(0, 5);
-            mma2(sub, c, st & 1);
+            mma2(sub, c, st & 1, nsp & 1);
             __syncwarp();
             DBG(0, 6);
             if (c == nch - 1) {
-              if (elect_one()) umma_commit(acc_done);
+              if (elect_one()) umma_commit(&acc_done[nsp & 1]);
               __syncwarp();
               ++nsp;
             }
@@ -618,39 +665,123 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         __syncwarp();
       }
     }
-  } else {
-    // =============================== compute warps ===============================
-    const int cw = warp - 2;
+  } else if (warp < 6) {
+    // =============================== chunk warps (one per TMEM lane quarter) ===============================
     const int q = warp & 3;
-    const int par = cw >> 2;
+    const int w4 = warp - 2;
     const int row = q * 32 + lane;               // row inside the 128-row tile == TMEM lane
-    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t t0 = tmem_base + lane_addr;
+    const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const float s = p.qscale ? __ldg(p.qscale) : 1.0f;
     const float inv_s = 1.0f / s;
     const float c2 = p.scale * s * s * 1.4426950408889634f;
+    const int ctid = threadIdx.x - 64;           // 0..127
+    uint32_t st = 0;
+#ifdef QV_ATTN_DEBUG
+    int dbg_n = (threadIdx.x == 64) ? 0 : 8192;
+#endif
+    int local = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
+      const int b = item / p.H, h = item % p.H;
+      const float* lse_bh = p.lse + (static_cast<int64_t>(b) * p.H + h) * p.T;
+      float* delta_s = delta_all + (local & 1) * 256;
+      DBG(1, 10);
+      asm volatile("bar.sync 9, 128;" ::: "memory");            // previous item's pass B has finished reading lse2_s
+      lse2_s[ctid] = (ctid < p.T) ? __ldg(lse_bh + ctid) * 1.4426950408889634f : 0.0f;
+      lse2_s[128 + ctid] = (128 + ctid < p.T) ? __ldg(lse_bh + 128 + ctid) * 1.4426950408889634f : 0.0f;
+      delta_rows(delta_s, b, h, 0, w4, inv_s);                   // rows 0..127 (tile 0) from global memory while the tiles land;
+      asm volatile("bar.sync 9, 128;" ::: "memory");            // rows 128.. were written an item ahead by the output warps
+      DBG(1, 11);
+      bool have_hi = false;
+      for (int sub = 0; sub < nsub; ++sub) {
+        const bool pass_a = sub < mt;
+        const int tile = pass_a ? sub : sub - mt;
+        if (!have_hi && (sub > 0 || mt == 1)) {                  // anything past pass A / tile 0 touches rows >= 128
+          mbar_wait(&delta_ready[local & 1], (static_cast<uint32_t>(local) >> 1) & 1);
+          have_hi = true;
+        }
+        const int tok = tile * 128 + row;                         // query (pass A) / key (pass B) of this lane
+        const float Li = lse2_s[tok & 255], di = delta_s[tok & 255];
+        for (int c = 0; c < nch; ++c, ++st) {
+          const uint32_t buf = st & 1;
+          DBG(1, 12);
+          mbar_wait(&mma1_done[buf], (st >> 1) & 1);
+          tc_fence_after();
+          DBG(1, 13);
+#pragma unroll 1
+          for (int par = 0; par < 2; ++par) {
+            const uint32_t S = t0 + buf * 128u + par * 32u, R = S + 64u;
+            const int col0 = 64 * c + 32 * par;                   // first column (key in pass A, query in pass B) of this piece
+            if (col0 >= n_keys) break;
+            uint32_t sv[32], dv[32];
+            tmem_ld_32x32(S, sv);
+            tmem_ld_32x32(R, dv);
+            tmem_ld_wait();
+            const int nvalid = p.T - col0;
+            if (pass_a) {
+              uint32_t pk[32];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * j]), c2, -Li));
+                const float p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * j + 1]), c2, -Li));
+                const float z0 = (2 * j < nvalid) ? p0 * (__uint_as_float(dv[2 * j]) - di) : 0.f;
+                const float z1 = (2 * j + 1 < nvalid) ? p1 * (__uint_as_float(dv[2 * j + 1]) - di) : 0.f;
+                split_pack2(z0, z1, pk[j], pk[16 + j]);
+              }
+              tmem_st_32x32(R, pk);
+            } else {
+              uint32_t pp[32], pz[32];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float2 L = *reinterpret_cast<const float2*>(lse2_s + col0 + 2 * j);      // broadcast reads
+                const float2 dl = *reinterpret_cast<const float2*>(delta_s + col0 + 2 * j);
+                const float p0 = (2 * j < nvalid) ? ex2_approx(fmaf(__uint_as_float(sv[2 * j]), c2, -L.x)) : 0.f;
+                const float p1 = (2 * j + 1 < nvalid) ? ex2_approx(fmaf(__uint_as_float(sv[2 * j + 1]), c2, -L.y)) : 0.f;
+                const float z0 = (2 * j < nvalid) ? p0 * (__uint_as_float(dv[2 * j]) - dl.x) : 0.f;
+                const float z1 = (2 * j + 1 < nvalid) ? p1 * (__uint_as_float(dv[2 * j + 1]) - dl.y) : 0.f;
+                split_pack2(p0, p1, pp[j], pp[16 + j]);
+                split_pack2(z0, z1, pz[j], pz[16 + j]);
+              }
+              tmem_st_32x32(S, pp);
+              tmem_st_32x32(R, pz);
+            }
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&cmp_done[buf]);
+          DBG(1, 14);
+        }
+      }
+    }
+  } else {
+    // =============================== output warps (one per TMEM lane quarter) ===============================
+    // Drain accumulator set p of sub-pass n while the chunk warps and the tensor pipe are already in sub-pass n + 1.
+    // Per warp: 32 rows x 64 columns of dQ (pass A) or dV and dK (pass B), as 32 x 32 tiles through four 4 KB staging buffers.
+    const int q = warp & 3;
+    const int w4 = warp - 6;
+    const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const float s = p.qscale ? __ldg(p.qscale) : 1.0f;
+    const float inv_s = 1.0f / s;
     const float gscale = p.scale * s * s;        // dQ, dK factor (see header comment)
-    const int ctid = threadIdx.x - 64;           // 0..255
     QvQParams yq;
     if constexpr (FUSED) yq = qv_load_qparams(p.y_scale, p.y_zp, p.qmin, p.qmax);
     const int D3 = 3 * D;
-    // Output of one 32-row x 32-column block (this warp's TMEM lanes x its column half of the 64-wide accumulator), staged
-    // through shared memory so that global traffic is whole 128-byte lines moved by TMA: the y tile (FUSED: the qkv Linear's
-    // raw output under these gradients) comes IN through buffer k, the lanes take their rows to registers, and the finished
-    // tile (fp32, or bf16 hi/lo planes) leaves through the same buffer.  Rows >= T are zero-filled on load and clipped on
-    // store by the per-image tensor maps.
-    uint8_t* my_stage = stage_s + cw * 8192;
-    uint64_t* my_ybar = y_bar + cw * 2;
-    uint32_t yph0 = 0, yph1 = 0;
+    uint8_t* my_stage = stage_s + w4 * 16384;
+    uint64_t* my_ybar = y_bar + w4 * 4;
+    uint32_t yph = 0;                            // bit k: phase of my_ybar[k]
     auto request_y = [&](int k, int b, int tok0, int col) {       // lane 0, after tma_store_wait_read<0>()
       mbar_expect_tx(&my_ybar[k], 4096);
       tma_load_3d(my_stage + k * 4096, &map_y, &my_ybar[k], col, tok0, b);
     };
-    auto emit = [&](const uint32_t (&o)[32], int k, uint32_t yph, float mult, int b, int tok0, int col, int slab) {
+    // Output of one 32-row x 32-column block, staged through shared memory so that global traffic is whole 128-byte lines moved
+    // by TMA: the y tile (FUSED: the qkv Linear's raw output under these gradients) comes IN through buffer k, the lanes take
+    // their rows to registers, and the finished tile (fp32, or bf16 hi/lo planes) leaves through the same buffer.  Rows >= T
+    // are zero-filled on load and clipped on store by the per-image tensor maps.
+    auto emit = [&](const uint32_t (&o)[32], int k, float mult, int b, int tok0, int col, int slab) {
       uint8_t* buf = my_stage + k * 4096;
       const bool ok = tok0 + lane < p.T;
       if constexpr (FUSED) {
-        mbar_wait(&my_ybar[k], yph);
+        mbar_wait(&my_ybar[k], (yph >> k) & 1u);
+        yph ^= 1u << k;
         float4 yv[8];
         const uint32_t srow = smem_u32(buf) + lane * 128;
 #pragma unroll
@@ -714,140 +845,69 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         }
       }
     };
-    uint32_t st = 0, nsp = 0;
+    uint32_t nsp = 0;
 #ifdef QV_ATTN_DEBUG
-    int dbg_n = (threadIdx.x == 64) ? 0 : 8192;
+    int dbg_n = (threadIdx.x == 192) ? 0 : 8192;
 #endif
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+    int local = 0;
+    // rows 128.. of delta are this group's job, done ONE ITEM AHEAD (before the last output of the previous item) so that the
+    // chunk warps never wait for it; buffer (local & 1) was last read two items ago
+    if (static_cast<int>(blockIdx.x) < num_items) {
+      delta_rows(delta_all, blockIdx.x / p.H, blockIdx.x % p.H, 128, w4, inv_s);
+      mbar_arrive(&delta_ready[0]);
+    }
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
       const int b = item / p.H, h = item % p.H;
-      const float* lse_bh = p.lse + (static_cast<int64_t>(b) * p.H + h) * p.T;
-      DBG(1, 10);
-      asm volatile("bar.sync 9, 256;" ::: "memory");            // previous item has finished reading lse2_s / delta_s
-      lse2_s[ctid] = (ctid < p.T) ? __ldg(lse_bh + ctid) * 1.4426950408889634f : 0.0f;
-      // delta_i = (dO_i . O_i) / s from global memory (the item's tiles are still landing): 8 lanes per token row, 8 columns each
-#pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        uint4 oh[4], ol[4], dh[4], dl[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {                              // 16 independent 16-byte loads in flight per lane
-          const int r = (half * 4 + u) * 32 + cw * 4 + (lane >> 3);
-          if (r < p.T) {
-            const int64_t grow = static_cast<int64_t>(b) * p.T + r;
-            const int col = h * HD + (lane & 7) * 8;
-            oh[u] = __ldg(reinterpret_cast<const uint4*>(p.o_planes + grow * p.o_ld + col));
-            ol[u] = __ldg(reinterpret_cast<const uint4*>(p.o_planes + p.o_plane_stride + grow * p.o_ld + col));
-            dh[u] = __ldg(reinterpret_cast<const uint4*>(p.do_planes + grow * p.do_ld + col));
-            dl[u] = __ldg(reinterpret_cast<const uint4*>(p.do_planes + p.do_plane_stride + grow * p.do_ld + col));
-          } else {
-            oh[u] = ol[u] = dh[u] = dl[u] = make_uint4(0u, 0u, 0u, 0u);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int r = (half * 4 + u) * 32 + cw * 4 + (lane >> 3);
-          const uint32_t ohw[4] = {oh[u].x, oh[u].y, oh[u].z, oh[u].w}, olw[4] = {ol[u].x, ol[u].y, ol[u].z, ol[u].w};
-          const uint32_t dhw[4] = {dh[u].x, dh[u].y, dh[u].z, dh[u].w}, dlw[4] = {dl[u].x, dl[u].y, dl[u].z, dl[u].w};
-          float dot = 0.f;
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            dot = fmaf(bf16lo_f(ohw[e]) + bf16lo_f(olw[e]), bf16lo_f(dhw[e]) + bf16lo_f(dlw[e]), dot);
-            dot = fmaf(bf16hi_f(ohw[e]) + bf16hi_f(olw[e]), bf16hi_f(dhw[e]) + bf16hi_f(dlw[e]), dot);
-          }
-          dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-          dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-          dot += __shfl_xor_sync(0xffffffffu, dot, 4);
-          if ((lane & 7) == 0) delta_s[r] = dot * inv_s;
-        }
-      }
-      asm volatile("bar.sync 9, 256;" ::: "memory");            // lse2_s and delta_s complete for every token
-      DBG(1, 11);
       for (int sub = 0; sub < nsub; ++sub, ++nsp) {
         const bool pass_a = sub < mt;
         const int tile = pass_a ? sub : sub - mt;
-        const int tok = tile * 128 + row;                         // query (pass A) / key (pass B) of this lane
-        const float Li = lse2_s[tok & 255], di = delta_s[tok & 255];
         const int tok0 = tile * 128 + q * 32;                     // first token of this warp's 32-row slab
-        const int ccol = h * HD + par * 32;
+        if (sub == nsub - 1 && item + static_cast<int>(gridDim.x) < num_items) {
+          const int nitem = item + gridDim.x;
+          delta_rows(delta_all + ((local + 1) & 1) * 256, nitem / p.H, nitem % p.H, 128, w4, inv_s);
+          mbar_arrive(&delta_ready[(local + 1) & 1]);
+        }
+        const int slab = (b * mt + tile) * 4 + q;
+        const int col_h = h * HD;
+        const uint32_t aset = nsp & 1;
         if (lane == 0) {
           tma_store_wait_read<0>();                               // the previous sub-pass's tiles have left the staging buffers
-          if constexpr (FUSED) {                                  // y tiles under this sub-pass's outputs: in flight during the chunks
-            request_y(0, b, tok0, (pass_a ? 0 : 2 * D) + ccol);
-            if (!pass_a) request_y(1, b, tok0, D + ccol);
+          if constexpr (FUSED) {                                  // y tiles under this sub-pass's outputs
+            request_y(0, b, tok0, (pass_a ? 0 : 2 * D) + col_h);
+            request_y(1, b, tok0, (pass_a ? 0 : 2 * D) + col_h + 32);
+            if (!pass_a) {
+              request_y(2, b, tok0, D + col_h);
+              request_y(3, b, tok0, D + col_h + 32);
+            }
           }
         }
         __syncwarp();
-        for (int c = 0; c < nch; ++c, ++st) {
-          const uint32_t buf = st & 1;
-          const uint32_t S = t0 + buf * 128u + par * 32u, R = S + 64u;
-          const int col0 = 64 * c + 32 * par;                     // first column (key in pass A, query in pass B) of this piece
-          DBG(1, 12);
-          mbar_wait(&mma1_done[buf], (st >> 1) & 1);
-          tc_fence_after();
-          DBG(1, 13);
-          if (col0 < n_keys) {
-            uint32_t sv[32], dv[32];
-            tmem_ld_32x32(S, sv);
-            tmem_ld_32x32(R, dv);
-            tmem_ld_wait();
-            const int nvalid = p.T - col0;
-            if (pass_a) {
-              uint32_t pk[32];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * j]), c2, -Li));
-                const float p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * j + 1]), c2, -Li));
-                const float z0 = (2 * j < nvalid) ? p0 * (__uint_as_float(dv[2 * j]) - di) : 0.f;
-                const float z1 = (2 * j + 1 < nvalid) ? p1 * (__uint_as_float(dv[2 * j + 1]) - di) : 0.f;
-                split_pack2(z0, z1, pk[j], pk[16 + j]);
-              }
-              tmem_st_32x32(R, pk);
-            } else {
-              uint32_t pp[32], pz[32];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float2 L = *reinterpret_cast<const float2*>(lse2_s + col0 + 2 * j);      // broadcast reads
-                const float2 dl = *reinterpret_cast<const float2*>(delta_s + col0 + 2 * j);
-                const float p0 = (2 * j < nvalid) ? ex2_approx(fmaf(__uint_as_float(sv[2 * j]), c2, -L.x)) : 0.f;
-                const float p1 = (2 * j + 1 < nvalid) ? ex2_approx(fmaf(__uint_as_float(sv[2 * j + 1]), c2, -L.y)) : 0.f;
-                const float z0 = (2 * j < nvalid) ? p0 * (__uint_as_float(dv[2 * j]) - dl.x) : 0.f;
-                const float z1 = (2 * j + 1 < nvalid) ? p1 * (__uint_as_float(dv[2 * j + 1]) - dl.y) : 0.f;
-                split_pack2(p0, p1, pp[j], pp[16 + j]);
-                split_pack2(z0, z1, pz[j], pz[16 + j]);
-              }
-              tmem_st_32x32(S, pp);
-              tmem_st_32x32(R, pz);
-            }
-            tmem_st_wait();
-          }
-          tc_fence_before();
-          mbar_arrive(&cmp_done[buf]);
-          DBG(1, 14);
-        }
-        // ---- sub-pass output: this warp stores columns par*32 .. par*32+31 of its 32 rows ----
-        const int slab = (b * mt + tile) * 4 + q;
-        mbar_wait(acc_done, nsp & 1);
+        mbar_wait(&acc_done[aset], (nsp >> 1) & 1);
         tc_fence_after();
-        DBG(1, 15);
+        DBG(2, 15);
+        const uint32_t acc0 = t0 + BW_ACC_COL + aset * 128u;
         uint32_t o[32];
-        tmem_ld_32x32(t0 + BW_ACC0_COL + par * 32, o);
+        tmem_ld_32x32(acc0, o);
+        tmem_ld_wait();
+        emit(o, 0, pass_a ? gscale : 1.0f, b, tok0, (pass_a ? 0 : 2 * D) + col_h, slab);               // dQ | dV, columns 0..31
+        tmem_ld_32x32(acc0 + 32u, o);
         tmem_ld_wait();
         if (pass_a) {
           tc_fence_before();
-          mbar_arrive(epi_done);
-          emit(o, 0, yph0, gscale, b, tok0, ccol, slab);                             // dQ
-          yph0 ^= 1;
-        } else {
-          uint32_t o2[32];
-          tmem_ld_32x32(t0 + BW_ACC1_COL + par * 32, o2);
+          mbar_arrive(&epi_done[aset]);
+        }
+        emit(o, 1, pass_a ? gscale : 1.0f, b, tok0, (pass_a ? 0 : 2 * D) + col_h + 32, slab);          // columns 32..63
+        if (!pass_a) {
+          tmem_ld_32x32(acc0 + 64u, o);
+          tmem_ld_wait();
+          emit(o, 2, gscale, b, tok0, D + col_h, slab);                                                 // dK, columns 0..31
+          tmem_ld_32x32(acc0 + 96u, o);
           tmem_ld_wait();
           tc_fence_before();
-          mbar_arrive(epi_done);
-          emit(o, 0, yph0, 1.0f, b, tok0, 2 * D + ccol, slab);                       // dV
-          emit(o2, 1, yph1, gscale, b, tok0, D + ccol, slab);                        // dK
-          yph0 ^= 1;
-          yph1 ^= 1;
+          mbar_arrive(&epi_done[aset]);
+          emit(o, 3, gscale, b, tok0, D + col_h + 32, slab);                                            // dK, columns 32..63
         }
-        DBG(1, 16);
+        DBG(2, 16);
       }
     }
     if (lane == 0) tma_store_wait_read<0>();
@@ -999,7 +1059,7 @@ extern "C" int qv_attn_bwd_gp(const uint16_t* qkv_codes, int64_t ld, const float
 }
 
 #ifdef QV_ATTN_DEBUG
-extern "C" int qv_debug_read(unsigned long long* host_out) {   // host_out: [2][8192]
-  return cudaMemcpyFromSymbol(host_out, qv_dbg_buf, sizeof(unsigned long long) * 2 * 8192) == cudaSuccess ? 0 : -1;
+extern "C" int qv_debug_read(unsigned long long* host_out) {   // host_out: [3][8192]
+  return cudaMemcpyFromSymbol(host_out, qv_dbg_buf, sizeof(unsigned long long) * 3 * 8192) == cudaSuccess ? 0 : -1;
 }
 #endif

@@ -13,7 +13,7 @@ from qatvit_b200 import _lib, ops  # noqa: E402
 
 TAGS = {1: "mma: wait ld_full", 2: "mma: ld_full ok", 3: "mma: wait cmp_done", 4: "mma: cmp_done ok", 5: "mma: epi ok, issue MMA2",
         6: "mma: MMA2 issued", 10: "cmp: item start", 11: "cmp: delta done", 12: "cmp: wait mma1_done", 13: "cmp: mma1_done ok",
-        14: "cmp: chunk done", 15: "cmp: acc_done ok", 16: "cmp: sub-pass out done"}
+        14: "cmp: chunk done", 15: "out: acc_done ok", 16: "out: sub-pass out done"}
 
 
 def main():
@@ -42,11 +42,11 @@ def main():
         ops.attn_bwd(cp, s, out, dOp, lse, B, T, H, 0.125, g_qkv)
     torch.cuda.synchronize()
     L = _lib.lib()
-    buf = (ctypes.c_ulonglong * (2 * 8192))()
+    buf = (ctypes.c_ulonglong * (3 * 8192))()
     L.qv_debug_read.restype = ctypes.c_int
     assert L.qv_debug_read(buf) == 0
     ev = []
-    for who in range(2):
+    for who in range(3):
         for i in range(8192):
             v = buf[who * 8192 + i]
             if v == 0:
