@@ -1,6 +1,6 @@
 """Debug helper (GPU): per-parameter gradient errors of the fused step vs the CPU reference + phase timings."""
 import copy, sys, time, os
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 t0 = time.time()
 import torch

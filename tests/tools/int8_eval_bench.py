@@ -1,7 +1,7 @@
 """GPU probe for BASELINE.json configs[4]: converted int8 ViT-S/16 student (stock convert() of a QAT-trained student) evaluated on
 synthetic 224x224 batches -- our executor (qatvit_b200.int8.ConvertedStudent: tcgen05 kind::i8 linears + fp32 glue) against the
 CPU path with stock torch.ops.quantized kernels (oracle/int8_ref.py, the same float glue) on a bounded sample.
-Usage: python tools/int8_eval_bench.py [batch]      -> one JSON line"""
+Usage: python tests/tools/int8_eval_bench.py [batch]      -> one JSON line"""
 import copy
 import json
 import os
@@ -9,7 +9,7 @@ import sys
 import time
 import warnings
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 import bench  # noqa: E402

@@ -2,13 +2,13 @@
 ViT-B/16 teacher + ViT-S/16 student prepared by stock prepare_qat (fbgemm qconfig), the reference loop body
 (oracle.vit_ref.distill_step = ref/src/training/qat_trainer.py:337-361) under eager autograd, ATen CUDA kernels (cuBLAS fp32
 SGEMM with TF32 off, SDPA, FusedObsFakeQuant).  Prints one JSON line.  Test/measurement infrastructure only.
-Usage (GPU box): python tools/torch_cuda_baseline.py [batch]"""
+Usage (GPU box): python tests/tools/torch_cuda_baseline.py [batch]"""
 import json
 import os
 import sys
 import warnings
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 from oracle import vit_ref as vr  # noqa: E402
