@@ -55,7 +55,10 @@ int qv_fq_apply(const float* x, int64_t n, const float* scale, const int32_t* ze
                 const int64_t* fake_quant_enabled, int32_t qmin, int32_t qmax, float* y, uint8_t* mask,
                 void* stream);
 
-/* Grouped per-channel weight fake-quant: every weight of the model in ONE launch (same arithmetic as qv_fq_weight with
+/* Replaces: the `self.weight_fake_quant(self.weight)` call inside every torch.ao.nn.qat.Linear / Conv2d forward
+ * (torch/ao/nn/qat/modules/linear.py:50-51, conv.py:55-56 -> fake_quantize.py:423-438), 49 per student forward
+ * (ref/src/training/qat_trainer.py:341, `student_out = ddp_model(images)`).
+ * Grouped per-channel weight fake-quant: every weight of the model in ONE launch (same arithmetic as qv_fq_weight with
  * per_channel = 1; outputs codes, codes_t and mask are all required).  `descs` is a DEVICE array of n_desc descriptors sorted by
  * block_start; weight i owns blocks [block_start_i, block_start_i + ceil(rows_i / 16)), total_blocks in all; rows must be
  * 16-byte aligned (cols % 4 == 0) and rows_i % 8 == 0 keeps the transposed stores aligned; max_cols = the largest cols. */
@@ -188,7 +191,9 @@ int qv_ln_bwd(const float* g_h, const float* x, const float* mean, const float* 
               const float* g_res, int64_t R, int32_t D, int64_t out_row_stride, float* g_x, float* partials,
               int32_t rows_per_block, const float* h_raw, const float* h_scale, const int32_t* h_zp, int32_t qmin, int32_t qmax,
               void* stream);
-/* qv_ln_bwd (out_row_stride 1) that also emits the gradient planes of the Linear whose fake-quantised output gp_y was added
+/* Replaces (inside `loss.backward()`, ref qat_trainer.py:357): NativeLayerNormBackward0 of timm Block.norm1 / norm2 + the residual
+ * AddBackward0 + FusedMovingAvgObsFqHelperBackward0 / bias reduction of the Linear feeding that residual (attn.proj, mlp.fc2).
+ * qv_ln_bwd (out_row_stride 1) that also emits the gradient planes of the Linear whose fake-quantised output gp_y was added
  * into the residual stream this LayerNorm reads (attn.proj for norm2, the previous block's mlp.fc2 for norm1):
  * gp_out = hi/lo planes [2][R][D] of g_x * STEmask(gp_y) * gp_wscale[col]; gp_partials (may be NULL) fp32
  * [ceil(R/rows_per_block)][D]: per-block column sums of g_x * mask (that Linear's bias grad; reduce with qv_colsum_reduce). */
@@ -245,7 +250,10 @@ int qv_attn_fwd(const uint16_t* qkv_planes, int32_t n_planes, int64_t plane_stri
 int qv_attn_bwd(const uint16_t* qkv_codes, int64_t ld, const float* qscale, const uint16_t* o_planes, int64_t o_plane_stride,
                 int64_t o_ld, const uint16_t* do_planes, int64_t do_plane_stride, int64_t do_ld, const float* lse, int32_t B,
                 int32_t T, int32_t H, float scale, float* g_qkv, void* stream);
-/* qv_attn_bwd with the qkv Linear's backward prologue (qv_gp_planes) fused into its output stage: instead of fp32 dQ | dK | dV,
+/* Replaces (inside `loss.backward()`, ref/src/training/qat_trainer.py:357): ScaledDotProductAttention backward of timm
+ * Attention.forward + FusedMovingAvgObsFqHelperBackward0 of the qkv output hook (torch/ao/quantization/quantize.py:150-152) + the
+ * bias reduction of the qkv AddmmBackward0.
+ * qv_attn_bwd with the qkv Linear's backward prologue (qv_gp_planes) fused into its output stage: instead of fp32 dQ | dK | dV,
  * writes gp = g * STEmask(y_raw) * w_scale[col] as bf16 hi/lo planes [2][B*T][3*H*64] (the A operand of the qkv dgrad / wgrad
  * GEMMs) and colsum fp32 [B * ceil(T/128) * 4][3*H*64]: per 32-token slab column sums of g * mask (bias-grad partials, reduce
  * with qv_colsum_reduce).  y_raw: the qkv Linear's raw output fp32 [B*T][3*H*64]; (y_scale, y_zp, qmin, qmax): its output
