@@ -191,7 +191,7 @@ int qv_ln_bwd(const float* g_h, const float* x, const float* mean, const float* 
               const float* g_res, int64_t R, int32_t D, int64_t out_row_stride, float* g_x, float* partials,
               int32_t rows_per_block, const float* h_raw, const float* h_scale, const int32_t* h_zp, int32_t qmin, int32_t qmax,
               void* stream);
-/* Replaces (inside `loss.backward()`, ref qat_trainer.py:357): NativeLayerNormBackward0 of timm Block.norm1 / norm2 + the residual
+/* Replaces (inside `loss.backward()`, ref qat_trainer.py:359): NativeLayerNormBackward0 of timm Block.norm1 / norm2 + the residual
  * AddBackward0 + FusedMovingAvgObsFqHelperBackward0 / bias reduction of the Linear feeding that residual (attn.proj, mlp.fc2).
  * qv_ln_bwd (out_row_stride 1) that also emits the gradient planes of the Linear whose fake-quantised output gp_y was added
  * into the residual stream this LayerNorm reads (attn.proj for norm2, the previous block's mlp.fc2 for norm1):
@@ -250,7 +250,7 @@ int qv_attn_fwd(const uint16_t* qkv_planes, int32_t n_planes, int64_t plane_stri
 int qv_attn_bwd(const uint16_t* qkv_codes, int64_t ld, const float* qscale, const uint16_t* o_planes, int64_t o_plane_stride,
                 int64_t o_ld, const uint16_t* do_planes, int64_t do_plane_stride, int64_t do_ld, const float* lse, int32_t B,
                 int32_t T, int32_t H, float scale, float* g_qkv, void* stream);
-/* Replaces (inside `loss.backward()`, ref/src/training/qat_trainer.py:357): ScaledDotProductAttention backward of timm
+/* Replaces (inside `loss.backward()`, ref/src/training/qat_trainer.py:359): ScaledDotProductAttention backward of timm
  * Attention.forward + FusedMovingAvgObsFqHelperBackward0 of the qkv output hook (torch/ao/quantization/quantize.py:150-152) + the
  * bias reduction of the qkv AddmmBackward0.
  * qv_attn_bwd with the qkv Linear's backward prologue (qv_gp_planes) fused into its output stage: instead of fp32 dQ | dK | dV,
