@@ -57,7 +57,8 @@ def test_attn_fwd_integer_codes(cuda_dev, B, H, T):
     assert _rel(got, o_ref) < 1e-4
 
 
-@pytest.mark.parametrize("B,H,T", [(3, 6, 197), (4, 2, 17), (2, 3, 37), (1, 1, 128), (2, 2, 129), (150, 2, 33)])
+@pytest.mark.parametrize("B,H,T", [(3, 6, 197), (4, 2, 17), (2, 3, 37), (1, 1, 128), (2, 2, 129), (150, 2, 33), (2, 2, 224), (1, 3, 209),
+                                   (2, 1, 64), (3, 1, 65), (1, 2, 1)])
 def test_attn_bwd_integer_codes(cuda_dev, B, H, T):
     """fused backward (recomputed P from codes + lse) vs fp64 autograd of softmax(QK^T/8)V."""
     from qatvit_b200 import ops
@@ -81,5 +82,9 @@ def test_attn_bwd_integer_codes(cuda_dev, B, H, T):
     o = torch.softmax((xv[0] @ xv[1].transpose(-1, -2)) * 0.125, dim=-1) @ xv[2]
     o.permute(0, 2, 1, 3).reshape(B * T, D).backward(dO.double())
     ref = x.grad
+    # T = 1: softmax of one key is constant, dQ = dK = 0 exactly -> measure every block against the whole gradient's scale
+    floor = float(ref.abs().max())
     for blk, name in enumerate(("dQ", "dK", "dV")):
-        assert _rel(g_qkv[:, blk * D:(blk + 1) * D], ref[:, blk * D:(blk + 1) * D]) < 1e-4, name
+        a, b = g_qkv[:, blk * D:(blk + 1) * D], ref[:, blk * D:(blk + 1) * D]
+        err = float((a.double().cpu() - b).abs().max()) / max(float(b.abs().max()), 1e-3 * floor)
+        assert err < 1e-4 if T > 1 else err < 1e-1, name
