@@ -27,7 +27,7 @@ extern "C" {
 #define QV_ERR_UNSUPPORTED (-3)
 
 /* ---- library ------------------------------------------------------------------------------- */
-int qv_version(void);                 /* ABI version, currently 1 */
+int qv_version(void);                 /* ABI version, currently 2 */
 const char* qv_last_error(void);      /* thread-local message of the last failing call */
 int qv_device_sm_count(void);         /* SMs of the current device, <0 on error (no device) */
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
@@ -87,6 +87,10 @@ int qv_fq_bwd(const float* gy, const uint8_t* mask, int64_t n, float* gx, void* 
 
 /* fp32 -> bf16 hi/lo planes (x ~= hi + lo, |err| <= 2^-17 |x|): how fp32 operands reach the bf16 tensor cores. */
 int qv_split_planes(const float* x, int64_t n, uint16_t* hi, uint16_t* lo, void* stream);
+/* fp32 [rows, cols] (cols % 64 == 0) -> the "mixed" GEMM operand format (qv_gemm_args.mix): region0 = fp16(x * 2^s) [rows][cols];
+ * region1 (rows * cols * 2 bytes): per row and 64-column block 64 fp8 of the value, then 64 e5m2 of the fp16 rounding residual.
+ * kind 0 = activation scales (A operand), 1 = weight scales (B operand; the frozen teacher's nn.Linear weights, split once). */
+int qv_split_planes_mix(const float* x, int64_t rows, int64_t cols, int32_t kind, uint16_t* region0, uint16_t* region1, void* stream);
 
 /* ---- distillation loss (replaces ref/src/training/qat_trainer.py:343-349) ---------------------
  * loss = alpha*T^2*KL(softmax(t/T) || softmax(s/T))_batchmean + (1-alpha)*CE_labelsmooth(s, y).
@@ -161,6 +165,14 @@ typedef struct qv_gemm_args {
   const int64_t* obs_enabled; const int64_t* obs_fq_enabled;
   float obs_c; int32_t obs_qmin, obs_qmax, obs_symmetric;
   uint32_t* obs_ticket;
+  /* mix != 0 (needs a_planes = b_planes = 2, K-major operands, K % 64 == 0, no split-K): both operands are in the "mixed"
+   * format written by qv_split_planes_mix / out_kind = 2 / the plane_fmt = 1 producers: region 0 (plane 0) holds fp16(x * 2^s),
+   * region 1 (plane 1, same byte size) holds per 64-column block 64 fp8 of the value then 64 fp8 (e5m2) of the fp16 rounding
+   * residual.  The product is fp16.fp16 + hi8.lo8 + lo8.hi8 in ONE fp32 accumulator (kind::f16 + 2 x kind::f8f6f4 at twice the
+   * rate: the cost of two bf16 passes instead of three, same ~2^-16 accuracy); the kernel rescales by 2^-14 before the epilogue.
+   * A must be an activation-kind tensor and B a weight-kind one.  out_kind = 2: like out_kind = 1, but the output planes are
+   * written in the mixed activation format (the next mixed GEMM's A operand). */
+  int32_t mix;
 } qv_gemm_args;
 int qv_gemm_bf16(const qv_gemm_args* args, void* stream);
 
@@ -178,11 +190,12 @@ int qv_splitk_reduce(const float* workspace, int32_t splits, int64_t M, int64_t 
 /* x_out = x_in + FQ(y_raw) ; h = LayerNorm(x_out)*gamma+beta.  Row r reads input row r*in_row_stride.  Any of
  * x_in / y_raw / x_out / h_planes (bf16 [2][R][D]) / h_f32 / mean / rstd may be NULL; y_scale NULL = no fake-quant.
  * minmax (uint32[2], may be NULL): ordered min / max of h merged atomically -- the output observer of an OBSERVED LayerNorm
- * (plain nn.LayerNorm under prepare_qat), phase 1. */
+ * (plain nn.LayerNorm under prepare_qat), phase 1.
+ * plane_fmt: 0 = h_planes are bf16 hi/lo planes; 1 = the mixed fp16 + fp8 operand format (qv_split_planes_mix, activation kind). */
 int qv_resid_ln_fwd(const float* x_in, const float* y_raw, const float* y_scale, const int32_t* y_zp, int32_t qmin,
                     int32_t qmax, const float* gamma, const float* beta, float eps, int64_t R, int32_t D,
                     int64_t in_row_stride, float* x_out, uint16_t* h_planes, int64_t plane_stride, float* h_f32,
-                    float* mean, float* rstd, uint32_t* minmax, void* stream);
+                    float* mean, float* rstd, uint32_t* minmax, int32_t plane_fmt, void* stream);
 /* g_x[r*out_row_stride] = g_res[r] + LayerNormBackward(g_h, x, mean, rstd, gamma)[r]; partials: fp32
  * [ceil(R/rows_per_block)][2][D] per-block dgamma / dbeta sums (reduce with qv_colsum_reduce).
  * h_raw (may be NULL): the raw LayerNorm output of an observed LayerNorm; g_h then passes the STE mask of its fake-quant
@@ -238,10 +251,11 @@ int qv_attn_ds(const uint16_t* P, int64_t ldP, int64_t p_plane_stride, const flo
  *   passed as device scalars: logits *= (*qk_scale)^2, output *= *v_scale (either may be NULL).
  * out_planes: bf16 hi/lo planes [2][B*T][out_ld]; head h fills columns h*64..h*64+63 (the proj GEMM's A operand);
  * out_f32: fp32 [B*T][H*64] copy of the output (either output may be NULL, not both).
- * lse (may be NULL): fp32 [B*H*T] natural-log logsumexp of the scaled logits (saved for a recomputing backward). */
+ * lse (may be NULL): fp32 [B*H*T] natural-log logsumexp of the scaled logits (saved for a recomputing backward).
+ * out_fmt: 0 = out_planes are bf16 hi/lo planes; 1 = the mixed fp16 + fp8 operand format (activation kind; out_ld % 64 == 0). */
 int qv_attn_fwd(const uint16_t* qkv_planes, int32_t n_planes, int64_t plane_stride, int64_t ld, int32_t B, int32_t T,
                 int32_t H, float scale, const float* qk_scale, const float* v_scale, uint16_t* out_planes,
-                int64_t out_plane_stride, int64_t out_ld, float* out_f32, float* lse, void* stream);
+                int64_t out_plane_stride, int64_t out_ld, float* out_f32, float* lse, int32_t out_fmt, void* stream);
 /* Fused attention backward for integer-code operands (the QAT student; autograd of F.scaled_dot_product_attention):
  * recomputes P from the codes and the forward's lse on the tensor cores and writes dQ | dK | dV (gradients w.r.t. the
  * fake-quantised q, k, v = s * codes) into g_qkv fp32 [B*T][3*H*64].  qkv_codes: ONE bf16 plane [B*T][ld]; o_planes: the

@@ -69,6 +69,7 @@ class GemmArgs(ctypes.Structure):
         ("obs_enabled", c_void_p), ("obs_fq_enabled", c_void_p),
         ("obs_c", c_float), ("obs_qmin", c_int32), ("obs_qmax", c_int32), ("obs_symmetric", c_int32),
         ("obs_ticket", c_void_p),
+        ("mix", c_int32),
     ]
 
 
@@ -87,12 +88,13 @@ _SIGNATURES = {
     "qv_fq_weight_grouped": (c_int, [_P, c_int32, c_int32, c_int32, c_float, c_int32, c_int32, c_int32, _P]),
     "qv_fq_bwd": (c_int, [_P, _P, c_int64, _P, _P]),
     "qv_split_planes": (c_int, [_P, c_int64, _P, _P, _P]),
+    "qv_split_planes_mix": (c_int, [_P, c_int64, c_int64, c_int32, _P, _P, _P]),
     "qv_kd_ce_loss": (c_int, [_P, _P, _P, c_int32, c_int32, c_float, c_float, c_float, _P, _P, c_int32, c_int32,
                               _P, _P, _P]),
     "qv_gemm_bf16": (c_int, [POINTER(GemmArgs), _P]),
     "qv_splitk_reduce": (c_int, [_P, c_int32, c_int64, c_int64, _P, _P, _P, _P, c_int32, _P]),
     "qv_resid_ln_fwd": (c_int, [_P, _P, _P, _P, c_int32, c_int32, _P, _P, c_float, c_int64, c_int32, c_int64, _P, _P,
-                                c_int64, _P, _P, _P, _P, _P]),
+                                c_int64, _P, _P, _P, _P, c_int32, _P]),
     "qv_ln_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int32, c_int64, _P, _P, c_int32, _P, _P, _P, c_int32, c_int32, _P]),
     "qv_ln_bwd_gp": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int32, _P, _P, c_int32, _P, _P, _P, c_int32, c_int32,
                              _P, _P, _P, c_int32, c_int32, _P, _P, c_int64, _P, _P]),
@@ -106,7 +108,7 @@ _SIGNATURES = {
     "qv_softmax_planes": (c_int, [_P, c_int64, c_int64, c_int32, c_float, _P, c_int64, c_int64, _P]),
     "qv_attn_ds": (c_int, [_P, c_int64, c_int64, _P, c_int64, c_int64, c_int32, c_float, _P, c_int64, c_int64, _P]),
     "qv_attn_fwd": (c_int, [_P, c_int32, c_int64, c_int64, c_int32, c_int32, c_int32, c_float, _P, _P, _P, c_int64, c_int64,
-                            _P, _P, _P]),
+                            _P, _P, c_int32, _P]),
     "qv_attn_bwd": (c_int, [_P, c_int64, _P, _P, c_int64, c_int64, _P, c_int64, c_int64, _P, c_int32, c_int32, c_int32, c_float,
                             _P, _P]),
     "qv_attn_bwd_gp": (c_int, [_P, c_int64, _P, _P, c_int64, c_int64, _P, c_int64, c_int64, _P, c_int32, c_int32, c_int32,

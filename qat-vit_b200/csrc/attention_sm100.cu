@@ -62,6 +62,7 @@ struct AttnParams {
   __nv_bfloat16* out;    // [2][B*T][out_ld] hi/lo planes; head h writes columns h*64 .. h*64+63 (may be null)
   int64_t out_plane_stride, out_ld;
   float* out_f32;        // optional fp32 copy of the output, [B*T][H*64]
+  int32_t out_fmt;       // 0 = bf16 hi/lo planes, 1 = mixed fp16 + fp8 planes (the teacher's proj operand)
   float* lse;            // optional [B*H*T]: scale' * rowmax + ln(rowsum)   (natural-log logsumexp of the scaled logits)
 };
 
@@ -323,6 +324,20 @@ qv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
           if (p.out) {
             __nv_bfloat16* dst_hi = p.out + row * p.out_ld + h * HD;
             __nv_bfloat16* dst_lo = dst_hi + p.out_plane_stride;
+            if (p.out_fmt == 1) {      // a head's 64 columns are exactly one block of the mixed format: 64 hi8 | 64 lo8
+              uint8_t* row1 = reinterpret_cast<uint8_t*>(dst_lo);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                uint32_t h16[4], ph[4], pl[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  h16[e] = qv_mix_split2<QV_MIX_ACT>(__uint_as_float(o[8 * j + 2 * e]) * inv, __uint_as_float(o[8 * j + 2 * e + 1]) * inv,
+                                                     ph[e], pl[e]);
+                *reinterpret_cast<uint4*>(dst_hi + 8 * j) = make_uint4(h16[0], h16[1], h16[2], h16[3]);
+                *reinterpret_cast<uint2*>(row1 + 8 * j) = make_uint2(ph[0] | (ph[1] << 16), ph[2] | (ph[3] << 16));
+                *reinterpret_cast<uint2*>(row1 + 64 + 8 * j) = make_uint2(pl[0] | (pl[1] << 16), pl[2] | (pl[3] << 16));
+              }
+            } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               uint32_t hi[4], lo[4];
@@ -331,6 +346,7 @@ qv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 split_pack2(__uint_as_float(o[8 * j + 2 * e]) * inv, __uint_as_float(o[8 * j + 2 * e + 1]) * inv, hi[e], lo[e]);
               *reinterpret_cast<uint4*>(dst_hi + 8 * j) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
               *reinterpret_cast<uint4*>(dst_lo + 8 * j) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
             }
           }
           if (p.out_f32) {
@@ -926,8 +942,10 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
 extern "C" int qv_attn_fwd(const uint16_t* qkv_planes, int32_t n_planes, int64_t plane_stride, int64_t ld, int32_t B,
                            int32_t T, int32_t H, float scale, const float* qk_scale, const float* v_scale,
                            uint16_t* out_planes, int64_t out_plane_stride, int64_t out_ld, float* out_f32, float* lse,
-                           void* stream) {
+                           int32_t out_fmt, void* stream) {
   QV_REQUIRE(qkv_planes && (out_planes || out_f32) && B > 0 && T > 0 && H > 0, QV_ERR_INVALID, "bad attn_fwd arguments");
+  QV_REQUIRE(out_fmt == 0 || (out_fmt == 1 && out_planes && out_ld % 64 == 0), QV_ERR_INVALID,
+             "out_fmt must be 0 (bf16 hi/lo) or 1 (mixed fp16 + fp8 planes, row pitch a multiple of 64)");
   QV_REQUIRE(n_planes == 1 || n_planes == 2, QV_ERR_INVALID, "n_planes must be 1 (integer codes) or 2 (fp32 hi/lo)");
   QV_REQUIRE(T <= 224, QV_ERR_UNSUPPORTED, "fused attention holds all keys in one tile: T <= 224 (got %d)", T);
   QV_REQUIRE(ld >= 3LL * H * HD, QV_ERR_INVALID, "qkv row pitch must cover Q | K | V (3 * H * 64 columns)");
@@ -949,6 +967,7 @@ extern "C" int qv_attn_fwd(const uint16_t* qkv_planes, int32_t n_planes, int64_t
   ap.out_ld = out_ld;
   ap.out_f32 = out_f32;
   ap.lse = lse;
+  ap.out_fmt = out_fmt;
   // one tensor, three box shapes: per-image matrices [T rows, ld cols]; rows >= T are zero-filled by TMA
   qv_operand op;
   memset(&op, 0, sizeof(op));

@@ -49,7 +49,7 @@ int qv_num_sms() {
   return cached_sms;
 }
 
-extern "C" int qv_version(void) { return 1; }
+extern "C" int qv_version(void) { return 2; }
 extern "C" const char* qv_last_error(void) { return g_err; }
 extern "C" int qv_device_sm_count(void) {
   int n = qv_num_sms();

@@ -38,73 +38,98 @@ __device__ __forceinline__ void store_planes4(__nv_bfloat16* hi, __nv_bfloat16* 
 
 // ------------------------------------------------------------------------------------------------
 // x_out = x_in + FQ(y_raw);  h = LayerNorm(x_out) -> bf16 hi/lo planes (and/or fp32);  one warp per row.
-// VPL = float4 vectors per lane (D = 128 * VPL).
+// VPL = float4 vectors per lane (D = 128 * VPL).  Persistent: the grid is a fixed number of blocks per SM, a warp
+// walks rows warp_id, warp_id + n_warps, ... and issues the NEXT row's loads before it reduces the current one, so
+// every warp always has a full row (2 x VPL x 512 B) in flight while it computes.
 // ------------------------------------------------------------------------------------------------
 template <int VPL>
-__global__ void __launch_bounds__(256) resid_ln_fwd_kernel(const float* __restrict__ x_in, const float* __restrict__ y_raw,
-                                                           const float* y_scale, const int32_t* y_zp, int qmin, int qmax,
-                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                           float eps, int64_t R, int64_t in_row_stride,
-                                                           float* __restrict__ x_out, __nv_bfloat16* __restrict__ h_planes,
-                                                           int64_t plane_stride, float* __restrict__ h_f32,
-                                                           float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                                                           uint32_t* minmax) {
+__device__ __forceinline__ void resid_ln_load(const float* __restrict__ x_in, const float* __restrict__ y_raw, int64_t src, int lane,
+                                              float4 (&xa)[VPL], float4 (&ya)[VPL]) {
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    xa[i] = x_in ? __ldg(reinterpret_cast<const float4*>(x_in + src + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (y_raw) ya[i] = __ldg(reinterpret_cast<const float4*>(y_raw + src + c));
+  }
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(256, (VPL <= 4 ? 3 : 2)) resid_ln_fwd_kernel(
+    const float* __restrict__ x_in, const float* __restrict__ y_raw, const float* y_scale, const int32_t* y_zp, int qmin, int qmax,
+    const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int64_t R, int64_t in_row_stride,
+    float* __restrict__ x_out, __nv_bfloat16* __restrict__ h_planes, int64_t plane_stride, float* __restrict__ h_f32,
+    float* __restrict__ mean_out, float* __restrict__ rstd_out, uint32_t* minmax, int plane_fmt) {
   constexpr int D = 128 * VPL;
   const int lane = threadIdx.x & 31;
-  const int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t n_warps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
   __shared__ float s_mn[8], s_mx[8];
   float omn = INFINITY, omx = -INFINITY;
-  if (r < R) {
   const OptQ oq = load_optq(y_scale, y_zp, qmin, qmax);
-  const int64_t src = r * in_row_stride * D;
-  float4 v[VPL];
+  float4 xa[VPL], ya[VPL];
+  if (r < R) resid_ln_load<VPL>(x_in, y_raw, r * in_row_stride * D, lane, xa, ya);
+  while (r < R) {
+    const int64_t rn = r + n_warps;
+    float4 v[VPL];
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int c = (i * 32 + lane) * 4;
-    float4 a = x_in ? __ldg(reinterpret_cast<const float4*>(x_in + src + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    if (y_raw) {
-      float4 y = __ldg(reinterpret_cast<const float4*>(y_raw + src + c));
-      if (oq.on) {
-        y.x = qv_fq(y.x, oq.q, nullptr, nullptr);
-        y.y = qv_fq(y.y, oq.q, nullptr, nullptr);
-        y.z = qv_fq(y.z, oq.q, nullptr, nullptr);
-        y.w = qv_fq(y.w, oq.q, nullptr, nullptr);
+    for (int i = 0; i < VPL; ++i) {
+      float4 a = xa[i];
+      if (y_raw) {
+        float4 y = ya[i];
+        if (oq.on) {
+          y.x = qv_fq(y.x, oq.q, nullptr, nullptr);
+          y.y = qv_fq(y.y, oq.q, nullptr, nullptr);
+          y.z = qv_fq(y.z, oq.q, nullptr, nullptr);
+          y.w = qv_fq(y.w, oq.q, nullptr, nullptr);
+        }
+        a.x += y.x; a.y += y.y; a.z += y.z; a.w += y.w;
       }
-      a.x += y.x; a.y += y.y; a.z += y.z; a.w += y.w;
+      v[i] = a;
     }
-    v[i] = a;
-  }
-  float s = 0.f;
+    if (rn < R) resid_ln_load<VPL>(x_in, y_raw, rn * in_row_stride * D, lane, xa, ya);   // next row in flight
+    float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-  const float mean = qv_warp_sum(s) * (1.0f / D);
-  float ss = 0.f;
+    for (int i = 0; i < VPL; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = qv_warp_sum(s) * (1.0f / D);
+    float ss = 0.f;
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-    ss += (a * a + b * b) + (c * c + d * d);
-  }
-  const float var = qv_warp_sum(ss) * (1.0f / D);
-  const float rstd = rsqrtf(var + eps);
-  if (lane == 0) {
-    if (mean_out) mean_out[r] = mean;
-    if (rstd_out) rstd_out[r] = rstd;
-  }
+    for (int i = 0; i < VPL; ++i) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      ss += (a * a + b * b) + (c * c + d * d);
+    }
+    const float var = qv_warp_sum(ss) * (1.0f / D);
+    const float rstd = rsqrtf(var + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[r] = mean;
+      if (rstd_out) rstd_out[r] = rstd;
+    }
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int c = (i * 32 + lane) * 4;
-    if (x_out) *reinterpret_cast<float4*>(x_out + r * D + c) = v[i];
-    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
-    const float o0 = (v[i].x - mean) * rstd * g.x + b.x;
-    const float o1 = (v[i].y - mean) * rstd * g.y + b.y;
-    const float o2 = (v[i].z - mean) * rstd * g.z + b.z;
-    const float o3 = (v[i].w - mean) * rstd * g.w + b.w;
-    if (h_planes) store_planes4(h_planes, h_planes + plane_stride, r * D + c, o0, o1, o2, o3);
-    if (h_f32) *reinterpret_cast<float4*>(h_f32 + r * D + c) = make_float4(o0, o1, o2, o3);
-    omn = fminf(omn, fminf(fminf(o0, o1), fminf(o2, o3)));
-    omx = fmaxf(omx, fmaxf(fmaxf(o0, o1), fmaxf(o2, o3)));
-  }
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (x_out) *reinterpret_cast<float4*>(x_out + r * D + c) = v[i];
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+      const float o0 = (v[i].x - mean) * rstd * g.x + b.x;
+      const float o1 = (v[i].y - mean) * rstd * g.y + b.y;
+      const float o2 = (v[i].z - mean) * rstd * g.z + b.z;
+      const float o3 = (v[i].w - mean) * rstd * g.w + b.w;
+      if (h_planes) {
+        if (plane_fmt == 1) {           // mixed operand format: fp16 | per 64-column block 64 hi8 + 64 lo8 (qv_common.cuh)
+          uint32_t ph0, pl0, ph1, pl1;
+          const uint32_t h0 = qv_mix_split2<QV_MIX_ACT>(o0, o1, ph0, pl0), h1 = qv_mix_split2<QV_MIX_ACT>(o2, o3, ph1, pl1);
+          *reinterpret_cast<uint2*>(h_planes + r * D + c) = make_uint2(h0, h1);
+          uint8_t* row1 = reinterpret_cast<uint8_t*>(h_planes + plane_stride + r * D) + (c >> 6) * 128 + (c & 63);
+          *reinterpret_cast<uint32_t*>(row1) = ph0 | (ph1 << 16);
+          *reinterpret_cast<uint32_t*>(row1 + 64) = pl0 | (pl1 << 16);
+        } else {
+          store_planes4(h_planes, h_planes + plane_stride, r * D + c, o0, o1, o2, o3);
+        }
+      }
+      if (h_f32) *reinterpret_cast<float4*>(h_f32 + r * D + c) = make_float4(o0, o1, o2, o3);
+      omn = fminf(omn, fminf(fminf(o0, o1), fminf(o2, o3)));
+      omx = fmaxf(omx, fmaxf(fmaxf(o0, o1), fmaxf(o2, o3)));
+    }
+    r = rn;
   }
   if (minmax) {                       // observed-LayerNorm variant: min / max of the LN output, one atomic pair per block
     omn = qv_warp_min(omn);
@@ -687,19 +712,22 @@ inline int ew_blocks(int64_t n_items, int per_sm = 8) {
 extern "C" int qv_resid_ln_fwd(const float* x_in, const float* y_raw, const float* y_scale, const int32_t* y_zp,
                                int32_t qmin, int32_t qmax, const float* gamma, const float* beta, float eps, int64_t R,
                                int32_t D, int64_t in_row_stride, float* x_out, uint16_t* h_planes, int64_t plane_stride,
-                               float* h_f32, float* mean, float* rstd, uint32_t* minmax, void* stream) {
+                               float* h_f32, float* mean, float* rstd, uint32_t* minmax, int32_t plane_fmt, void* stream) {
   QV_REQUIRE((x_in || y_raw) && gamma && beta && R > 0, QV_ERR_INVALID, "bad resid_ln_fwd arguments");
+  QV_REQUIRE(plane_fmt == 0 || plane_fmt == 1, QV_ERR_INVALID, "plane_fmt must be 0 (bf16 hi/lo) or 1 (mixed fp16 + fp8)");
   QV_REQUIRE(D % 128 == 0 && D >= 128 && D <= 1024, QV_ERR_UNSUPPORTED, "LayerNorm width must be a multiple of 128 <= 1024 (got %d)", D);
   QV_REQUIRE((y_scale == nullptr) == (y_zp == nullptr), QV_ERR_INVALID, "y_scale and y_zp go together");
   QV_NEED_GPU();
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int rows_per_block = 8;
-  const unsigned grid = static_cast<unsigned>((R + rows_per_block - 1) / rows_per_block);
+  const int rows_per_block = 8;                       // one warp per row, a warp walks rows n_warps apart
+  const int64_t blocks_needed = (R + rows_per_block - 1) / rows_per_block;
+  const int64_t resident = static_cast<int64_t>(qv_num_sms()) * (D <= 512 ? 3 : 2);
+  const unsigned grid = static_cast<unsigned>(blocks_needed < resident ? blocks_needed : resident);
   __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(h_planes);
   if (in_row_stride < 1) in_row_stride = 1;
 #define LAUNCH(V)                                                                                                        \
   resid_ln_fwd_kernel<V><<<grid, 256, 0, st>>>(x_in, y_raw, y_scale, y_zp, qmin, qmax, gamma, beta, eps, R, in_row_stride, \
-                                               x_out, hp, plane_stride, h_f32, mean, rstd, minmax)
+                                               x_out, hp, plane_stride, h_f32, mean, rstd, minmax, plane_fmt)
   switch (D / 128) {
     case 1: LAUNCH(1); break;
     case 2: LAUNCH(2); break;

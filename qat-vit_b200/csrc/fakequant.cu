@@ -219,6 +219,31 @@ __global__ void __launch_bounds__(256) qv_split_planes_kernel(const float* __res
   }
 }
 
+// ---------------- fp32 -> mixed planes (fp16 | fp8 hi / residual blocks; see qv_common.cuh) ----------------
+// one thread = 8 consecutive columns of one row
+template <int KIND>
+__global__ void __launch_bounds__(256) qv_split_planes_mix_kernel(const float* __restrict__ x, int64_t rows, int64_t cols,
+                                                                  uint8_t* __restrict__ r0, uint8_t* __restrict__ r1) {
+  const int64_t groups_per_row = cols >> 3;
+  const int64_t total = rows * groups_per_row;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total; i += stride) {
+    const int64_t r = i / groups_per_row, c = (i - r * groups_per_row) << 3;
+    const float4 va = __ldg(reinterpret_cast<const float4*>(x + r * cols + c));
+    const float4 vb = __ldg(reinterpret_cast<const float4*>(x + r * cols + c + 4));
+    uint32_t ph[4], pl[4];
+    uint4 h16;
+    h16.x = qv_mix_split2<KIND>(va.x, va.y, ph[0], pl[0]);
+    h16.y = qv_mix_split2<KIND>(va.z, va.w, ph[1], pl[1]);
+    h16.z = qv_mix_split2<KIND>(vb.x, vb.y, ph[2], pl[2]);
+    h16.w = qv_mix_split2<KIND>(vb.z, vb.w, ph[3], pl[3]);
+    *reinterpret_cast<uint4*>(r0 + (r * cols + c) * 2) = h16;
+    uint8_t* row1 = r1 + r * cols * 2 + (c >> 6) * 128 + (c & 63);
+    *reinterpret_cast<uint2*>(row1) = make_uint2(ph[0] | (ph[1] << 16), ph[2] | (ph[3] << 16));
+    *reinterpret_cast<uint2*>(row1 + 64) = make_uint2(pl[0] | (pl[1] << 16), pl[2] | (pl[3] << 16));
+  }
+}
+
 inline int ew_blocks(int64_t n4) {
   const int sms = qv_num_sms();
   int64_t b = (n4 + 255) / 256;
@@ -444,4 +469,23 @@ extern "C" int qv_split_planes(const float* x, int64_t n, uint16_t* hi, uint16_t
   qv_split_planes_kernel<<<ew_blocks(n >> 2), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       x, n, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo));
   return qv_check_launch("qv_split_planes");
+}
+
+extern "C" int qv_split_planes_mix(const float* x, int64_t rows, int64_t cols, int32_t kind, uint16_t* region0, uint16_t* region1,
+                                   void* stream) {
+  QV_REQUIRE(rows >= 0 && cols >= 0 && (kind == QV_MIX_ACT || kind == QV_MIX_WGT), QV_ERR_INVALID, "bad split_planes_mix arguments");
+  if (rows == 0 || cols == 0) return QV_OK;
+  QV_REQUIRE(cols % 64 == 0, QV_ERR_UNSUPPORTED, "mixed planes need a multiple of 64 columns (got %lld)", (long long)cols);
+  QV_REQUIRE(x && region0 && region1 && qv_aligned16(x) && qv_aligned16(region0) && qv_aligned16(region1), QV_ERR_INVALID,
+             "split_planes_mix pointers must be 16-byte aligned");
+  QV_REQUIRE(qv_num_sms() > 0, QV_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  const int blocks = ew_blocks(rows * (cols >> 3));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (kind == QV_MIX_ACT)
+    qv_split_planes_mix_kernel<QV_MIX_ACT><<<blocks, 256, 0, st>>>(x, rows, cols, reinterpret_cast<uint8_t*>(region0),
+                                                                   reinterpret_cast<uint8_t*>(region1));
+  else
+    qv_split_planes_mix_kernel<QV_MIX_WGT><<<blocks, 256, 0, st>>>(x, rows, cols, reinterpret_cast<uint8_t*>(region0),
+                                                                   reinterpret_cast<uint8_t*>(region1));
+  return qv_check_launch("qv_split_planes_mix");
 }

@@ -56,6 +56,8 @@ struct GemmKParams {
   int32_t b_c2_outer, b_c2_inner, b_col0, b_col_inner;
   int32_t o_c2_outer, o_c2_inner, o_col0, o_col_inner;
   int32_t act;            // 0 = none, 1 = exact-erf GELU (applied after scale / bias)
+  float acc_scale;        // accumulator pre-scale (1, or 2^-14 for the fp16 + fp8 "mixed" operand format)
+  int32_t out_fmt;        // EPI 1: 0 = bf16 hi/lo planes, 1 = mixed planes (fp16 hi | e5m2 hi8 / lo8 blocks)
   // EPI 2 ("gradient planes"): gq = acc * [gelu'(FQ(y))] * STEmask(y), planes = split(gq * col_scale[n]), column sums of gq
   const float* ep_raw;    // y: raw output [M, N] of the Linear whose output fake-quant the gradient passes through
   int64_t ep_raw_ld;
@@ -103,11 +105,12 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 // EPI = 2: dgrad producing the NEXT layer's gradient planes: the accumulator (dL/d FQ(y) or dL/d GELU(FQ(y))) is multiplied by
 // gelu'(FQ(y)) -- a 256-entry table over the integer codes, built per CTA -- and the STE mask recomputed from the raw y tile,
 // folded with the per-channel weight scale and written as hi/lo planes; bias-grad column sums leave as per-slab partials.
-template <int BN, int NA, int NB, bool A_MN, bool B_MN, int EPI>
+template <int BN, int NA, int NB, bool A_MN, bool B_MN, int EPI, int MIX>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_o, const __grid_constant__ CUtensorMap map_y, const GemmKParams p) {
   using C = Cfg<BN, NA, NB, EPI>;
+  static_assert(!MIX || (NA == 2 && NB == 2 && !A_MN && !B_MN), "mixed operands: two K-major regions per operand");
   constexpr int EPI_WARP_BYTES = C::EPI_WARP_BYTES;
   constexpr int EPI_BYTES = C::EPI_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -220,6 +223,7 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // operands in uniform registers; under an `if (lane == 0)` region every tcgen05.mma paid an R2UR + ELECT waterfall loop
     // (~90 cycles of issue per instruction -- as long as a 128 x 192 x 16 MMA takes to execute).
     {
+      static_assert(!MIX, "the mixed operand format is issued by the single-lane issuer only");
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
       constexpr uint32_t a_lbo = A_MN ? 8192u : 16u, b_lbo = B_MN ? 8192u : 16u;
       constexpr uint32_t a_kadv = A_MN ? (UMMA_K * 128u) : (UMMA_K * 2u);   // bytes per 16-deep k step
@@ -301,6 +305,27 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint32_t sb = sa + NA * A_PLANE_BYTES;
+          if constexpr (MIX) {
+            // region 0 of each operand: fp16 (x 2^5 / x 2^9); region 1: per 64-deep k-block a 128-byte row = 64 fp8 of the
+            // value (hi8) then 64 fp8 of the fp16 rounding residual (lo8).  fp32-grade product = hi16.hi16 (4 x K16, kind::f16)
+            // + hi8.lo8 + lo8.hi8 (2 x K32 each, kind::f8f6f4 at twice the rate), every term scaled by 2^14 into ONE accumulator.
+            constexpr uint32_t idesc16 = umma_idesc_f16(BM, BN);
+            constexpr uint32_t idesc_hl = umma_idesc_f8(BM, BN, 1u, 1u);    // A hi8 e5m2 x B lo8 e5m2
+            constexpr uint32_t idesc_lh = umma_idesc_f8(BM, BN, 1u, 0u);    // A lo8 e5m2 x B hi8 e4m3
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t da = umma_smem_desc(sa + k * 32u, 16u, 1024u);
+              const uint64_t db = umma_smem_desc(sb + k * 32u, 16u, 1024u);
+              umma_bf16(d_tmem, da, db, idesc16, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            const uint32_t sa8 = sa + A_PLANE_BYTES, sb8 = sb + C::B_PLANE_BYTES;
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+              umma_f8(d_tmem, umma_smem_desc(sa8 + k * 32u, 16u, 1024u), umma_smem_desc(sb8 + 64u + k * 32u, 16u, 1024u), idesc_hl, 1u);
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+              umma_f8(d_tmem, umma_smem_desc(sa8 + 64u + k * 32u, 16u, 1024u), umma_smem_desc(sb8 + k * 32u, 16u, 1024u), idesc_lh, 1u);
+          } else {
 #pragma unroll
           for (int pr = 0; pr < C::NPAIRS; ++pr) {
             // pair order: (0,0) [,(0,1)] [,(1,0)]  -- for NB == 1 the second pair is (1,0)
@@ -312,6 +337,7 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               const uint64_t db = umma_smem_desc(sb + pb * C::B_PLANE_BYTES + k * b_kadv, b_lbo, 1024u);
               umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || pr > 0 || k > 0) ? 1u : 0u);
             }
+          }
           }
           umma_commit(&empty_bar[stage]);       // frees this smem stage once the MMAs have read it
           GDBG(1, 14);
@@ -509,7 +535,7 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int64_t n = n0 + lane;
             float m_ = 1.0f, b_ = 0.0f;
             if (n < p.N) {
-              m_ = alpha;
+              m_ = alpha * p.acc_scale;
               if (p.col_scale) m_ *= __ldg(p.col_scale + n);
               if (p.col_rscale) m_ = __fdiv_rn(m_, __ldg(p.col_rscale + n));
               if (p.bias) b_ = __ldg(p.bias + n);
@@ -561,10 +587,31 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               ba = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 8 * j));
               bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 8 * j + 4));
             }
-            float a[8] = {__uint_as_float(rr[8 * j]) + ba.x,     __uint_as_float(rr[8 * j + 1]) + ba.y,
-                          __uint_as_float(rr[8 * j + 2]) + ba.z, __uint_as_float(rr[8 * j + 3]) + ba.w,
-                          __uint_as_float(rr[8 * j + 4]) + bb.x, __uint_as_float(rr[8 * j + 5]) + bb.y,
-                          __uint_as_float(rr[8 * j + 6]) + bb.z, __uint_as_float(rr[8 * j + 7]) + bb.w};
+            const float as = p.acc_scale;
+            float a[8] = {__uint_as_float(rr[8 * j]) * as + ba.x,     __uint_as_float(rr[8 * j + 1]) * as + ba.y,
+                          __uint_as_float(rr[8 * j + 2]) * as + ba.z, __uint_as_float(rr[8 * j + 3]) * as + ba.w,
+                          __uint_as_float(rr[8 * j + 4]) * as + bb.x, __uint_as_float(rr[8 * j + 5]) * as + bb.y,
+                          __uint_as_float(rr[8 * j + 6]) * as + bb.z, __uint_as_float(rr[8 * j + 7]) * as + bb.w};
+            if (p.out_fmt == 1) {                                 // mixed planes: the next GEMM's fp16 + fp8 operand
+              uint32_t h16[4], h8[2], l8[2];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float a0 = a[2 * e], a1 = a[2 * e + 1];
+                if (p.act == 1) { a0 = gelu_erf(a0); a1 = gelu_erf(a1); }
+                uint32_t ph, pl;
+                h16[e] = qv_mix_split2<QV_MIX_ACT>(a0, a1, ph, pl);
+                if (e & 1) { h8[e >> 1] |= ph << 16; l8[e >> 1] |= pl << 16; }
+                else { h8[e >> 1] = ph; l8[e >> 1] = pl; }
+              }
+              const uint32_t swz = static_cast<uint32_t>(lane & 7);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow_hi + ((static_cast<uint32_t>(j) ^ swz) << 4)),
+                           "r"(h16[0]), "r"(h16[1]), "r"(h16[2]), "r"(h16[3]) : "memory");
+              // region 1 row: bytes [0, 64) = hi8 of the 64 columns, [64, 128) = lo8; 8 columns = 8 bytes at 8 j
+              const uint32_t c8 = static_cast<uint32_t>(j >> 1), o8 = static_cast<uint32_t>(j & 1) << 3;
+              asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(srow_lo + ((c8 ^ swz) << 4) + o8), "r"(h8[0]), "r"(h8[1]) : "memory");
+              asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(srow_lo + (((c8 + 4u) ^ swz) << 4) + o8), "r"(l8[0]), "r"(l8[1]) : "memory");
+              continue;
+            }
             uint32_t hi[4], lo[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -649,18 +696,18 @@ __global__ void qv_splitk_reduce_kernel(const float* __restrict__ ws, int splits
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <int BN, int NA, int NB, bool A_MN, bool B_MN, int EPI = 0>
+template <int BN, int NA, int NB, bool A_MN, bool B_MN, int EPI = 0, int MIX = 0>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const GemmKParams& kp, int grid,
            cudaStream_t st, const CUtensorMap* my = nullptr) {
   using C = Cfg<BN, NA, NB, EPI>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(qv_gemm_kernel<BN, NA, NB, A_MN, B_MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    attr_err = cudaFuncSetAttribute(qv_gemm_kernel<BN, NA, NB, A_MN, B_MN, EPI, MIX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     C::SMEM_BYTES);
   });
   QV_REQUIRE(attr_err == cudaSuccess, QV_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
-  qv_gemm_kernel<BN, NA, NB, A_MN, B_MN, EPI><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mb, mo, my ? *my : mo, kp);
+  qv_gemm_kernel<BN, NA, NB, A_MN, B_MN, EPI, MIX><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mb, mo, my ? *my : mo, kp);
   return qv_check_launch("qv_gemm_bf16");
 }
 
@@ -704,11 +751,16 @@ extern "C" int qv_gemm_bf16(const qv_gemm_args* a, void* stream) {
   const int nbatch = a->nbatch > 1 ? a->nbatch : 1;
   QV_REQUIRE(!(splits > 1 && nbatch > 1), QV_ERR_UNSUPPORTED, "split-K and batching are mutually exclusive");
   QV_REQUIRE(qv_num_sms() > 0, QV_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
-  const bool planes_out = a->out_kind == 1;
+  const bool mix = a->mix != 0;
+  const bool planes_out = a->out_kind == 1 || a->out_kind == 2;
   int BN = a->tile_n > 0 ? a->tile_n : pick_bn(a->N);
   if (planes_out && a->tile_n <= 0 && BN < 128) BN = 128;      // plane output is instantiated for 128 / 192 wide tiles
   QV_REQUIRE(BN == 64 || BN == 128 || BN == 192, QV_ERR_UNSUPPORTED, "tile_n must be 64, 128 or 192");
-  QV_REQUIRE(a->out_kind == 0 || a->out_kind == 1, QV_ERR_INVALID, "out_kind must be 0 (fp32) or 1 (bf16 hi/lo planes)");
+  QV_REQUIRE(a->out_kind >= 0 && a->out_kind <= 2, QV_ERR_INVALID, "out_kind must be 0 (fp32), 1 (bf16 hi/lo planes) or 2 (mixed planes)");
+  if (mix)
+    QV_REQUIRE(a->a_planes == 2 && a->b_planes == 2 && !a->a.mn_major && !a->b.mn_major && splits == 1 && a->K % 64 == 0 &&
+                   a->act != 2, QV_ERR_UNSUPPORTED,
+               "mixed (fp16 + fp8) operands: unsplit K-major (2,2)-region GEMMs with K a multiple of 64 only");
   QV_REQUIRE(a->act == 0 || ((a->act == 1 || a->act == 2) && planes_out), QV_ERR_UNSUPPORTED,
              "act = GELU / gradient-planes epilogue needs out_kind = 1 (plane output)");
   const bool grad_epi = a->act == 2;
@@ -785,6 +837,8 @@ extern "C" int qv_gemm_bf16(const qv_gemm_args* a, void* stream) {
   kp.b_c2_outer = a->b.c2_outer; kp.b_c2_inner = a->b.c2_inner; kp.b_col0 = a->b.col0; kp.b_col_inner = a->b.col_inner;
   kp.o_c2_outer = a->out.c2_outer; kp.o_c2_inner = a->out.c2_inner; kp.o_col0 = a->out.col0; kp.o_col_inner = a->out.col_inner;
   kp.act = a->act;
+  kp.acc_scale = mix ? QV_MIX_ACC_SCALE : 1.0f;
+  kp.out_fmt = a->out_kind == 2 ? 1 : 0;
   kp.ep_raw = a->ep_raw; kp.ep_raw_ld = a->ep_raw_ld; kp.ep_scale = a->ep_scale; kp.ep_zp = a->ep_zp;
   kp.ep_qmin = a->ep_qmin; kp.ep_qmax = a->ep_qmax; kp.ep_gelu = a->ep_gelu; kp.ep_colsum = a->ep_colsum;
   if (a->obs_ticket) {
@@ -805,6 +859,15 @@ extern "C" int qv_gemm_bf16(const qv_gemm_args* a, void* stream) {
   if (grad_epi) {
     if (BN == 128) return launch<128, 2, 1, false, false, 2>(ma, mb, mo, kp, grid, st, &my);
     return launch<192, 2, 1, false, false, 2>(ma, mb, mo, kp, grid, st, &my);
+  }
+  if (mix) {
+    if (planes_out) {
+      if (BN == 128) return launch<128, 2, 2, false, false, 1, 1>(ma, mb, mo, kp, grid, st);
+      return launch<192, 2, 2, false, false, 1, 1>(ma, mb, mo, kp, grid, st);
+    }
+    if (BN == 64) return launch<64, 2, 2, false, false, 0, 1>(ma, mb, mo, kp, grid, st);
+    if (BN == 128) return launch<128, 2, 2, false, false, 0, 1>(ma, mb, mo, kp, grid, st);
+    return launch<192, 2, 2, false, false, 0, 1>(ma, mb, mo, kp, grid, st);
   }
   if (planes_out) {
     if (a->b_planes == 1) {

@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <stdint.h>
 #include <math.h>
 
@@ -104,6 +106,35 @@ __device__ __forceinline__ float qv_warp_colsum32(float (&v)[32], int lane) {
 __device__ __forceinline__ void qv_split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(x);
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+// ------------------------------------------------------------------------------------------------
+// "mixed" operand format of the frozen teacher's Linears: an fp32 value x is carried as
+//   region 0: fp16(x * 2^S16)                                        (11 significant bits)
+//   region 1: per 64-column block one 128-byte row = 64 x hi8 = fp8(x * 2^SH8), then 64 x lo8 = e5m2 of the fp16 rounding
+//             residual (x * 2^S16 - fp16(..)) * 2^SL8
+// so that  A.W = [A16.W16 + hi8(A).lo8(W) + lo8(A).hi8(W)] * 2^-14  to ~2^-16 per product: the two cross terms are 2^-12 of the
+// main one and only need fp8 precision, which the tensor cores run at twice the fp16 rate (three bf16 hi/lo passes -> the
+// cost of two).  The scales are fixed powers of two (no per-tensor statistics): e5m2 spans the whole fp16 range.
+//   activations: S16 = 5, hi8 = e5m2(x * 2^-2), lo8 = e5m2(res * 2^5)   (residual scale 2^10 relative to x)
+//   weights    : S16 = 9, hi8 = e4m3(x * 2^4),  lo8 = e5m2(res * 2^7)   (2^16 relative to x)
+// Every product term carries 2^14: 5 + 9 = -2 + 16 = 10 + 4.
+// ------------------------------------------------------------------------------------------------
+#define QV_MIX_ACT 0
+#define QV_MIX_WGT 1
+#define QV_MIX_ACC_SCALE 6.103515625e-05f     /* 2^-14 */
+// returns the packed fp16 pair (a0 low half, a1 high half); ph / pl = packed hi8 / lo8 pairs (a0 low byte)
+template <int KIND>
+__device__ __forceinline__ uint32_t qv_mix_split2(float a0, float a1, uint32_t& ph, uint32_t& pl) {
+  constexpr float S16 = KIND == QV_MIX_ACT ? 32.f : 512.f;
+  constexpr float SH8 = KIND == QV_MIX_ACT ? 0.25f : 16.f;
+  constexpr float SL8 = KIND == QV_MIX_ACT ? 32.f : 128.f;
+  const float s0 = fminf(fmaxf(a0 * S16, -65504.f), 65504.f), s1 = fminf(fmaxf(a1 * S16, -65504.f), 65504.f);
+  const __half2 h = __floats2half2_rn(s0, s1);
+  const float2 hf = __half22float2(h);
+  ph = __nv_cvt_float2_to_fp8x2(make_float2(a0 * SH8, a1 * SH8), __NV_SATFINITE, KIND == QV_MIX_ACT ? __NV_E5M2 : __NV_E4M3);
+  pl = __nv_cvt_float2_to_fp8x2(make_float2((s0 - hf.x) * SL8, (s1 - hf.y) * SL8), __NV_SATFINITE, __NV_E5M2);
+  return *reinterpret_cast<const uint32_t*>(&h);
 }
 
 __device__ __forceinline__ float qv_warp_sum(float v) {

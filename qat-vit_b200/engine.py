@@ -189,10 +189,14 @@ def _attention_forward(d: _ViTDims, qkvp: torch.Tensor, S: torch.Tensor, Pp: tor
 
 
 class TeacherEngine:
-    """Frozen fp32 ViT forward (ref qat_trainer.py:337-338) on the tcgen05 GEMMs: weights and activations as bf16
-    hi/lo planes, three MMAs per product (hi*hi + hi*lo + lo*hi), fp32 accumulation."""
+    """Frozen fp32 ViT forward (ref qat_trainer.py:337-338) on the tcgen05 GEMMs, fp32 accumulation.  The block Linears
+    take their operands in the mixed format (fp16 value + fp8 copies of the value and of the fp16 rounding residual): one
+    kind::f16 product plus two kind::f8f6f4 cross terms at twice the rate -- fp32-grade (~2^-16 per product) for the cost of
+    two bf16 passes instead of three.  ``mixed=False`` (or QV_TEACHER_MIX=0) keeps bf16 hi/lo planes and three MMAs per product
+    (hi*hi + hi*lo + lo*hi) everywhere; the patch embedding always does."""
 
-    def __init__(self, vit: nn.Module, batch: int):
+    def __init__(self, vit: nn.Module, batch: int, mixed: Optional[bool] = None):
+        import os
         self.vit = vit
         dev = next(vit.parameters()).device
         if dev.type != "cuda":
@@ -202,19 +206,23 @@ class TeacherEngine:
         M, D, F = d.M, d.D, d.F
         bf, f32 = torch.bfloat16, torch.float32
 
-        def planes_of(w: torch.Tensor) -> torch.Tensor:
+        if mixed is None:
+            mixed = os.environ.get("QV_TEACHER_MIX", "1") != "0"
+        self.mixed = mx = bool(mixed) and D % 64 == 0 and F % 64 == 0
+
+        def planes_of(w: torch.Tensor, mix: bool = False) -> torch.Tensor:
             w2 = w.detach().reshape(w.shape[0], -1).contiguous()
-            return ops.split_planes(w2)
+            return ops.split_planes_mix(w2, weight=True) if mix else ops.split_planes(w2)
 
         self.w_conv = planes_of(vit.patch_embed.proj.weight)
         self.blocks = []
         for blk in vit.blocks:
             self.blocks.append(dict(
                 n1=(blk.norm1.weight.detach(), blk.norm1.bias.detach()), n2=(blk.norm2.weight.detach(), blk.norm2.bias.detach()),
-                qkv=(planes_of(blk.attn.qkv.weight), blk.attn.qkv.bias.detach()),
-                proj=(planes_of(blk.attn.proj.weight), blk.attn.proj.bias.detach()),
-                fc1=(planes_of(blk.mlp.fc1.weight), blk.mlp.fc1.bias.detach()),
-                fc2=(planes_of(blk.mlp.fc2.weight), blk.mlp.fc2.bias.detach())))
+                qkv=(planes_of(blk.attn.qkv.weight, mx), blk.attn.qkv.bias.detach()),
+                proj=(planes_of(blk.attn.proj.weight, mx), blk.attn.proj.bias.detach()),
+                fc1=(planes_of(blk.mlp.fc1.weight, mx), blk.mlp.fc1.bias.detach()),
+                fc2=(planes_of(blk.mlp.fc2.weight, mx), blk.mlp.fc2.bias.detach())))
         e = lambda *s, dt=f32: torch.empty(*s, dtype=dt, device=dev)  # noqa: E731
         self.img_planes = e(2, d.B * d.P, d.Kc, dt=bf)
         self.p_raw = e(d.B * d.P, D)
@@ -231,6 +239,7 @@ class TeacherEngine:
     def forward(self, images: torch.Tensor) -> torch.Tensor:
         d, v = self.d, self.vit
         B, T, D, F, M = d.B, d.T, d.D, d.F, d.M
+        mx = self.mixed
         if tuple(images.shape) != (B, d.in_ch, d.HW, d.HW):
             raise RuntimeError(f"teacher engine built for batch {B}, got {tuple(images.shape)}")
         ops.im2col_fq(images, None, B, d.in_ch, d.HW, d.ps, self.img_planes)
@@ -243,26 +252,27 @@ class TeacherEngine:
         for li, blk in enumerate(self.blocks):
             g, b = blk["n1"]
             if li == 0:
-                ops.resid_ln_fwd(x_in, None, None, g, b, d.eps, M, D, h_planes=self.hp)
+                ops.resid_ln_fwd(x_in, None, None, g, b, d.eps, M, D, h_planes=self.hp, planes_mix=mx)
             else:
-                ops.resid_ln_fwd(x_in, y_prev, None, g, b, d.eps, M, D, x_out=self.x[cur ^ 1], h_planes=self.hp)
+                ops.resid_ln_fwd(x_in, y_prev, None, g, b, d.eps, M, D, x_out=self.x[cur ^ 1], h_planes=self.hp, planes_mix=mx)
                 cur ^= 1
                 x_in = self.x[cur]
             w, bias = blk["qkv"]
             # no observer sits between the teacher's Linears: epilogues emit the next operand's bf16 planes directly
-            ops.gemm(Op.full(self.hp), Op.full(w), M, 3 * D, D, PAIRS_FP32, bias=bias, out_planes=self.qkvp)
-            # fused softmax attention: scores / probabilities stay in tensor memory, output lands as proj's A planes
-            ops.attn_fwd(self.qkvp, B, T, d.H, d.attn_scale, self.op)
+            ops.gemm(Op.full(self.hp), Op.full(w), M, 3 * D, D, PAIRS_FP32, bias=bias, out_planes=self.qkvp, mix=mx)
+            # fused softmax attention (bf16 hi/lo q, k, v): scores / probabilities stay in tensor memory, output lands as proj's
+            # A operand
+            ops.attn_fwd(self.qkvp, B, T, d.H, d.attn_scale, self.op, out_mix=mx)
             w, bias = blk["proj"]
-            ops.gemm(Op.full(self.op), Op.full(w), M, D, D, PAIRS_FP32, out=self.y, bias=bias)
+            ops.gemm(Op.full(self.op), Op.full(w), M, D, D, PAIRS_FP32, out=self.y, bias=bias, mix=mx)
             g, b = blk["n2"]
-            ops.resid_ln_fwd(x_in, self.y, None, g, b, d.eps, M, D, x_out=self.x[cur ^ 1], h_planes=self.hp)
+            ops.resid_ln_fwd(x_in, self.y, None, g, b, d.eps, M, D, x_out=self.x[cur ^ 1], h_planes=self.hp, planes_mix=mx)
             cur ^= 1
             x_in = self.x[cur]
             w, bias = blk["fc1"]
-            ops.gemm(Op.full(self.hp), Op.full(w), M, F, D, PAIRS_FP32, bias=bias, out_planes=self.fp, gelu=True)
+            ops.gemm(Op.full(self.hp), Op.full(w), M, F, D, PAIRS_FP32, bias=bias, out_planes=self.fp, gelu=True, mix=mx, out_mix=mx)
             w, bias = blk["fc2"]
-            ops.gemm(Op.full(self.fp), Op.full(w), M, D, F, PAIRS_FP32, out=self.y, bias=bias)
+            ops.gemm(Op.full(self.fp), Op.full(w), M, D, F, PAIRS_FP32, out=self.y, bias=bias, mix=mx)
             y_prev = self.y
         ops.resid_ln_fwd(x_in, y_prev, None, v.norm.weight.detach(), v.norm.bias.detach(), d.eps, B, D, in_row_stride=T,
                          h_f32=self.xn)

@@ -139,6 +139,17 @@ def split_planes(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.T
     return out
 
 
+def split_planes_mix(x: torch.Tensor, weight: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 [rows, cols] -> the mixed GEMM operand format as a 2-byte-element stack [2, rows, cols]: region 0 = fp16(x * 2^s),
+    region 1 = per 64-column block 64 fp8 of the value + 64 e5m2 of the fp16 rounding residual (qv_split_planes_mix)."""
+    rows, cols = x.shape
+    if out is None:
+        out = torch.empty((2, rows, cols), dtype=torch.bfloat16, device=x.device)
+    check(_lib.lib().qv_split_planes_mix(_p(x, torch.float32, "x"), rows, cols, int(bool(weight)), _p(out[0], torch.bfloat16),
+                                         _p(out[1], torch.bfloat16), _stream()), "split_planes_mix")
+    return out
+
+
 def kd_ce_loss(s_raw, t, labels, T, alpha, eps, s_scale=None, s_zp=None, qmin=0, qmax=255, want_grad=True, out3=None,
                grad=None):
     B, C = s_raw.shape
@@ -241,8 +252,10 @@ PAIRS_FP32 = (2, 2)          # both fp32 as hi/lo: A0*B0 + A0*B1 + A1*B0 (lo*lo 
 def gemm(a: Op, b: Op, M: int, N: int, K: int, planes: Tuple[int, int], *, out=None, col_scale=None, col_rscale=None,
          alpha=None, bias=None, minmax=None, splits: int = 1, workspace: Optional[torch.Tensor] = None, nbatch: int = 1,
          batch_inner: int = 1, tile_n: int = 0, out_planes: Optional[torch.Tensor] = None, gelu: bool = False,
-         grad_of=None, observer=None):
+         grad_of=None, observer=None, mix: bool = False, out_mix: bool = False):
     """D[M,N] = sum_pairs A[pa] @ B[pb]^T on tcgen05 (include/qatvit_b200.h: qv_gemm_bf16).
+    mix: both operands are in the mixed fp16 + fp8 format (split_planes_mix / out_mix producers); out_mix: out_planes is
+    written in the mixed activation format instead of bf16 hi/lo.
     out: an ``Out`` descriptor, a 2-D fp32 tensor, or None (allocated).
     out_planes: bf16 [2, M, N] -- write [GELU](D) as hi/lo planes straight from the epilogue instead of fp32.
     grad_of = (y_raw [M,N], (scale, zp, qmin, qmax), gelu: bool, colsum [ceil(M/32), N] | None): with out_planes, the
@@ -260,7 +273,7 @@ def gemm(a: Op, b: Op, M: int, N: int, K: int, planes: Tuple[int, int], *, out=N
             raise RuntimeError("qatvit_b200: out_planes must be a CUDA bf16 [2, M, N] plane stack (no CPU fallback)")
         o = args.out
         o.ptr, o.ld, o.rows, o.cols, o.nb, o.batch_stride = out_planes.data_ptr(), out_planes.stride(1), M, N, 1, 0
-        args.out_kind, args.act, args.out_plane_stride = 1, int(bool(gelu)), out_planes.stride(0)
+        args.out_kind, args.act, args.out_plane_stride = (2 if out_mix else 1), int(bool(gelu)), out_planes.stride(0)
         if grad_of is not None:
             y_raw, fq, g_gelu, colsum = grad_of
             if y_raw.dtype != torch.float32 or not y_raw.is_cuda or y_raw.dim() != 2 or y_raw.stride(1) != 1:
@@ -299,6 +312,7 @@ def gemm(a: Op, b: Op, M: int, N: int, K: int, planes: Tuple[int, int], *, out=N
     args.splits = splits
     args.nbatch, args.batch_inner = nbatch, batch_inner
     args.tile_n = tile_n
+    args.mix = int(bool(mix))
     check(_lib.lib().qv_gemm_bf16(ctypes.byref(args), _stream()), "gemm_bf16")
     return ret
 
@@ -315,15 +329,16 @@ def launch_count() -> int:
 
 
 def resid_ln_fwd(x_in, y_raw, fq, gamma, beta, eps, R, D, *, in_row_stride=1, x_out=None, h_planes=None, h_f32=None,
-                 mean=None, rstd=None, minmax=None):
-    """x_out = x_in + FQ(y_raw); h = LN(x_out).  fq = (scale, zero_point, qmin, qmax) or None."""
+                 mean=None, rstd=None, minmax=None, planes_mix=False):
+    """x_out = x_in + FQ(y_raw); h = LN(x_out).  fq = (scale, zero_point, qmin, qmax) or None.
+    planes_mix: h_planes in the mixed fp16 + fp8 operand format instead of bf16 hi/lo."""
     sc, zp, qmin, qmax = fq if fq is not None else (None, None, 0, 0)
     check(_lib.lib().qv_resid_ln_fwd(_p(x_in, torch.float32), _p(y_raw, torch.float32), _p(sc, torch.float32),
                                      _p(zp, torch.int32), qmin, qmax, _p(gamma, torch.float32), _p(beta, torch.float32),
                                      float(eps), R, D, in_row_stride, _p(x_out, torch.float32),
                                      _p(h_planes, torch.bfloat16), 0 if h_planes is None else h_planes.stride(0),
                                      _p(h_f32, torch.float32), _p(mean, torch.float32), _p(rstd, torch.float32),
-                                     _p(minmax, torch.int32), _stream()), "resid_ln_fwd")
+                                     _p(minmax, torch.int32), int(bool(planes_mix)), _stream()), "resid_ln_fwd")
 
 
 def ln_bwd(g_h, x, mean, rstd, gamma, g_res, R, D, g_x, partials, rows_per_block, out_row_stride=1, h_raw=None, h_fq=None,
@@ -406,7 +421,7 @@ def attn_ds(P_planes, dP, lddP, rows, T, scale, dS_planes):
                                 dS_planes.stride(1), dS_planes.stride(0), _stream()), "attn_ds")
 
 
-def attn_fwd(qkv_planes, B, T, H, scale, out_planes, qk_scale=None, v_scale=None, lse=None, out_f32=None):
+def attn_fwd(qkv_planes, B, T, H, scale, out_planes, qk_scale=None, v_scale=None, lse=None, out_f32=None, out_mix=False):
     """Fused softmax(Q K^T * scale) V per (image, head): qkv_planes bf16 [1 or 2, B*T, 3*H*64] -> out_planes bf16
     [2, B*T, H*64] (include/qatvit_b200.h: qv_attn_fwd)."""
     if qkv_planes.dim() != 3 or qkv_planes.stride(2) != 1 or (out_planes is not None and (out_planes.dim() != 3 or out_planes.stride(2) != 1)):
@@ -415,7 +430,8 @@ def attn_fwd(qkv_planes, B, T, H, scale, out_planes, qk_scale=None, v_scale=None
     check(_lib.lib().qv_attn_fwd(_p(qkv_planes, torch.bfloat16, "qkv_planes"), qkv_planes.shape[0], qkv_planes.stride(0),
                                  qkv_planes.stride(1), B, T, H, float(scale), _p(qk_scale, torch.float32),
                                  _p(v_scale, torch.float32), _p(out_planes, torch.bfloat16, "out_planes"), ops_, opl,
-                                 _p(out_f32, torch.float32, "out_f32"), _p(lse, torch.float32), _stream()), "attn_fwd")
+                                 _p(out_f32, torch.float32, "out_f32"), _p(lse, torch.float32), int(bool(out_mix)), _stream()),
+          "attn_fwd")
     return out_planes if out_planes is not None else out_f32
 
 
