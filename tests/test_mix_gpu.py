@@ -43,7 +43,8 @@ def test_split_planes_mix_roundtrip(cuda_dev, rows, cols, mag, weight):
     big = xd.abs() > (2.0 ** -5 if weight else 2.0 ** -11)
     if weight:
         big &= xd.abs() <= 28.0          # e4m3(w * 16) saturates at 448 (the cross term then under-corrects; |w| > 28 is no ViT weight)
-    assert float(((h8 - xd).abs() / xd.abs().clamp_min(1e-30))[big].max()) <= (2.0 ** -4 if weight else 2.0 ** -3) * 1.001
+    if bool(big.any()):
+        assert float(((h8 - xd).abs() / xd.abs().clamp_min(1e-30))[big].max()) <= (2.0 ** -4 if weight else 2.0 ** -3) * 1.001
 
 
 def test_split_planes_mix_rejects_bad_shapes(cuda_dev):
