@@ -598,7 +598,7 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 float a0 = a[2 * e], a1 = a[2 * e + 1];
-                if (p.act == 1) { a0 = gelu_erf(a0); a1 = gelu_erf(a1); }
+                if (p.act == 1) { a0 = qv_gelu_fast(a0); a1 = qv_gelu_fast(a1); }
                 uint32_t ph, pl;
                 h16[e] = qv_mix_split2<QV_MIX_ACT>(a0, a1, ph, pl);
                 if (e & 1) { h8[e >> 1] |= ph << 16; l8[e >> 1] |= pl << 16; }

@@ -786,10 +786,10 @@ class QATDistillStep:
 
     def __init__(self, student: nn.Module, teacher: nn.Module, batch: int, hparams: Dict,
                  grad_buffer: Optional[torch.Tensor] = None, fused_attention: Optional[bool] = None, fused_gp: bool = True,
-                 overlap_teacher: Optional[bool] = None):
+                 overlap_teacher: Optional[bool] = None, teacher_mixed: Optional[bool] = None):
         self.student_engine = StudentEngine(student, batch, hparams, grad_buffer=grad_buffer, fused_attention=fused_attention,
                                             fused_gp=fused_gp)
-        self.teacher_engine = TeacherEngine(teacher, batch)
+        self.teacher_engine = TeacherEngine(teacher, batch, mixed=teacher_mixed)
         self.grad_arena = self.student_engine.grad_arena
         # The frozen teacher's forward (ref qat_trainer.py:337-338) is independent of the student's until the loss: it runs on a
         # second stream, so each stream's kernel-boundary bubbles (tails of persistent kernels, small reduces / observer updates)

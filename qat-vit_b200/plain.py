@@ -271,9 +271,9 @@ class PlainDistillStep:
     reference's training iteration before QAT is enabled (ref qat_trainer.py:333-361 with qat_enabled == False, no AMP)."""
 
     def __init__(self, student: nn.Module, teacher: nn.Module, batch: int, hparams: Dict,
-                 grad_buffer: Optional[torch.Tensor] = None):
+                 grad_buffer: Optional[torch.Tensor] = None, teacher_mixed: Optional[bool] = None):
         self.student_engine = PlainStudentEngine(student, batch, hparams, grad_buffer=grad_buffer)
-        self.teacher_engine = TeacherEngine(teacher, batch)
+        self.teacher_engine = TeacherEngine(teacher, batch, mixed=teacher_mixed)
         self.grad_arena = self.student_engine.grad_arena
         self._tstream = torch.cuda.Stream(device=self.student_engine.dev)
         self._tdone = torch.cuda.Event()

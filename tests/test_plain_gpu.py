@@ -29,14 +29,21 @@ def _models(sname, tname, img, seed=0):
     return vr, student.train(), teacher
 
 
-@pytest.mark.parametrize("sname,tname,img,B", [("vit_test_tiny", "vit_test_teacher", 64, 4), ("vit_test_tiny", "vit_test_teacher", 96, 3),
-                                               ("vit_small_patch16_224", "vit_base_patch16_224", 224, 4)])
-def test_plain_step_matches_fp32_autograd(cuda_dev, sname, tname, img, B):
+@pytest.mark.parametrize("sname,tname,img,B,mixed", [("vit_test_tiny", "vit_test_teacher", 64, 4, True),
+                                                     ("vit_test_tiny", "vit_test_teacher", 96, 3, False),
+                                                     ("vit_small_patch16_224", "vit_base_patch16_224", 224, 4, False),
+                                                     ("vit_small_patch16_224", "vit_base_patch16_224", 224, 4, True)])
+def test_plain_step_matches_fp32_autograd(cuda_dev, sname, tname, img, B, mixed):
+    """mixed: the teacher's Linears in the fp16 + fp8 operand format (default) -- its logits carry ~2e-5 instead of ~5e-6, which the
+    KD term (p_s - p_t) amplifies to ~1e-4 on the gradients at ViT-B depth: tolerance 3e-4 there (north_star: 1e-3), 1e-4 with the
+    three-pass bf16 teacher."""
     from qatvit_b200.plain import PlainDistillStep
     vr, student, teacher = _models(sname, tname, img)
     hp = dict(vr.DEFAULT_HPARAMS)
     gpu_student = copy.deepcopy(student).to(cuda_dev)
-    step = PlainDistillStep(gpu_student, copy.deepcopy(teacher).to(cuda_dev), B, hp)
+    step = PlainDistillStep(gpu_student, copy.deepcopy(teacher).to(cuda_dev), B, hp, teacher_mixed=mixed)
+    assert step.teacher_engine.mixed == mixed
+    gtol = 3e-4 if mixed else 1e-4
     for it in range(2):
         images, labels = vr.synthetic_batch(B, seed=3 + it, img=img)
         out3 = step(images.to(cuda_dev), labels.to(cuda_dev))
@@ -44,10 +51,10 @@ def test_plain_step_matches_fp32_autograd(cuda_dev, sname, tname, img, B):
         loss_ref, s_ref, t_ref = vr.distill_step(student, teacher, images, labels, None, hp, clip=False)
         assert rel_max(step.teacher_engine.logits, t_ref) < 1e-4
         assert rel_max(step.student_engine.logits, s_ref) < 1e-4
-        assert abs(float(out3[0]) - float(loss_ref)) <= 1e-5 * abs(float(loss_ref))
+        assert abs(float(out3[0]) - float(loss_ref)) <= 1e-4 * abs(float(loss_ref))      # teacher logits carry ~2e-5 (mixed fp16 + fp8 Linears)
         ref = dict(student.named_parameters())
         for n, p in gpu_student.named_parameters():
-            assert rel_max(p.grad, ref[n].grad) < 1e-4 and rel_l2(p.grad, ref[n].grad) < 1e-4, (it, n, rel_max(p.grad, ref[n].grad))
+            assert rel_max(p.grad, ref[n].grad) < gtol and rel_l2(p.grad, ref[n].grad) < gtol, (it, n, rel_max(p.grad, ref[n].grad))
         student.zero_grad(set_to_none=True)
     # forward only (validation loop)
     images, _ = vr.synthetic_batch(B, seed=9, img=img)

@@ -22,7 +22,7 @@ CASES = {
 def decode_mix(planes, weight=False):
     import torch
     rows, cols = planes.shape[1], planes.shape[2]
-    s16, sh8, sl8 = (512.0, 16.0, 128.0) if weight else (32.0, 0.25, 32.0)
+    s16, sh8, sl8 = 128.0, 128.0, 1.0
     h16 = planes[0].view(torch.float16).double()
     b = planes[1].view(torch.uint8).reshape(rows, cols // 64, 2, 64)
     h8 = b[:, :, 0, :].contiguous().view(torch.float8_e4m3fn if weight else torch.float8_e5m2).double().reshape(rows, cols)
