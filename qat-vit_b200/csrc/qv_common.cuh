@@ -139,12 +139,14 @@ __device__ __forceinline__ uint32_t qv_mix_split2(float a0, float a1, uint32_t& 
 // t = 1 / (1 + p z);  x >= 0: gelu = x (1 - erfc / 2),  x < 0: gelu = x erfc / 2 (no cancellation in the tail).
 __device__ __forceinline__ float qv_gelu_fast(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float pl = fmaf(1.061405429f, t, -1.453152027f);
-  pl = fmaf(pl, t, 1.421413741f);
-  pl = fmaf(pl, t, -0.284496736f);
-  pl = fmaf(pl, t, 0.254829592f);
-  const float half_erfc = 0.5f * pl * t * exp2f(z * z * -1.4426950408889634f);
+  float t, e;                                               // raw MUFU ops: 1 + p z >= 1 and e^{-z^2} may flush to zero
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+  float pl = fmaf(1.061405429f * 0.5f, t, -1.453152027f * 0.5f);
+  pl = fmaf(pl, t, 1.421413741f * 0.5f);
+  pl = fmaf(pl, t, -0.284496736f * 0.5f);
+  pl = fmaf(pl, t, 0.254829592f * 0.5f);
+  const float half_erfc = pl * t * e;
   return x * (x >= 0.f ? 1.0f - half_erfc : half_erfc);
 }
 
