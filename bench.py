@@ -133,7 +133,7 @@ def run_reference(args):
                                    "per step on the host CPU", "qconfig": "fbgemm"},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # --------------------------------------------------------------------------------------------------------------------
@@ -385,9 +385,18 @@ def run_ours(args):
     }
     if cpu_base is not None:
         line["cpu_baseline"] = cpu_base
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_OUT = None
+
+
+def _emit(line):
+    out = _OUT if _OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -405,6 +414,12 @@ def main():
                          "BASELINE metric, a side measurement of SURVEY.md section 8f item 3")
     ap.add_argument("--torch-optimizer", action="store_true", help="torch AdamW + clip on the arena instead of qv_clip_adamw")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: libraries that write to fd 1 from C (NCCL prints "NCCL version ..." there on some
+    # boxes) are sent to stderr; the line itself goes to a private duplicate of the original stdout.
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
