@@ -1,7 +1,7 @@
 """Converted int8 student executor (BASELINE.json configs[4]; SURVEY.md §8 a12, §8c "config 5 oracle").
 
 Input: the module stock ``convert()`` returns for the trained student (ref/src/training/qat_trainer.py:377-388), or its
-``state_dict()`` (= best_converted.pth) together with the float student it was converted from.  Every converted
+``state_dict()`` (= best_converted.pth, read directly by ``ConvertedStudent.from_state_dict``).  Every converted
 ``nnq.Linear`` / ``nnq.Conv2d`` runs as ``qv_int8_linear`` (tcgen05 kind::i8, requantising epilogue) and is bit-identical
 to ``torch.ops.quantized.linear`` on identical quint8 inputs (tests/test_int8_gpu.py).
 
@@ -13,6 +13,7 @@ its codes directly; every other quantized module quantises its fp32 input per te
 """
 from __future__ import annotations
 
+import re
 from typing import Dict
 
 import torch
@@ -49,50 +50,115 @@ def _unpack_linear(mod) -> tuple:
     return w, b
 
 
-class ConvertedStudent:
-    """Runs the converted QATWrapper student on one GPU.  ``forward(images) -> fp32 logits [B, classes]``."""
+def _spec_from_module(converted: nn.Module) -> dict:
+    """Operands of the module stock ``convert()`` returns (ref qat_trainer.py:377-379)."""
+    vit = converted.model
+    if type(vit.blocks[0].norm1).__module__.startswith("torch.ao.nn.quantized"):
+        raise NotImplementedError("quantized LayerNorm (observed nn.LayerNorm variant) is not supported by the int8 executor")
+    pe = vit.patch_embed
+    conv = pe.proj
 
-    def __init__(self, converted: nn.Module, batch: int, device):
+    def lin(mod):
+        w, b = _unpack_linear(mod)
+        return (w, b, mod.scale, mod.zero_point)
+
+    blocks = []
+    for blk in vit.blocks:
+        blocks.append({"qkv": lin(blk.attn.qkv), "proj": lin(blk.attn.proj), "fc1": lin(blk.mlp.fc1), "fc2": lin(blk.mlp.fc2),
+                       "n1": (blk.norm1.weight, blk.norm1.bias), "n2": (blk.norm2.weight, blk.norm2.bias)})
+    return dict(in_scale=converted.quant.scale, in_zp=converted.quant.zero_point,
+                conv=(conv.weight(), conv.bias(), conv.scale, conv.zero_point), ps=conv.kernel_size[0], HW=pe.img_size[0],
+                blocks=blocks, head=lin(vit.head), norm=(vit.norm.weight, vit.norm.bias), cls=vit.cls_token, pos=vit.pos_embed,
+                H=vit.blocks[0].attn.num_heads, eps=float(vit.blocks[0].norm1.eps), attn_scale=float(vit.blocks[0].attn.scale))
+
+
+def _spec_from_state_dict(sd: dict, num_heads=None, eps: float = 1e-6) -> dict:
+    """Operands straight from ``converted.state_dict()`` -- the file the reference writes as best_converted.pth
+    (ref qat_trainer.py:386-388; key layout SURVEY.md §3.4): ``quant.{scale,zero_point}``,
+    ``model.patch_embed.proj.{weight (qint8 tensor),bias,scale,zero_point}``, per Linear ``<name>.{scale,zero_point}`` and
+    ``<name>._packed_params._packed_params`` = ``(qint8 weight, fp32 bias)``, plus the float LayerNorm / cls / pos tensors.
+    The head count and LayerNorm eps are module attributes, not tensors: timm's ViTs use 64-wide heads and eps 1e-6
+    (SURVEY.md App. B); pass ``num_heads`` / ``eps`` for anything else."""
+    missing = [k for k in ("quant.scale", "quant.zero_point", "model.cls_token", "model.pos_embed",
+                           "model.patch_embed.proj.weight", "model.head._packed_params._packed_params") if k not in sd]
+    if missing:
+        raise KeyError(f"not a converted QATWrapper state_dict (best_converted.pth): missing {missing}")
+    if "model.blocks.0.norm1.scale" in sd:
+        raise NotImplementedError("quantized LayerNorm (observed nn.LayerNorm variant) is not supported by the int8 executor")
+
+    def lin(prefix):
+        w, b = sd[prefix + "._packed_params._packed_params"]
+        return (w, b, float(sd[prefix + ".scale"]), int(sd[prefix + ".zero_point"]))
+
+    depth = 1 + max(int(m.group(1)) for m in (re.match(r"model\.blocks\.(\d+)\.", k) for k in sd) if m)
+    blocks = []
+    for i in range(depth):
+        p = f"model.blocks.{i}."
+        blocks.append({"qkv": lin(p + "attn.qkv"), "proj": lin(p + "attn.proj"), "fc1": lin(p + "mlp.fc1"), "fc2": lin(p + "mlp.fc2"),
+                       "n1": (sd[p + "norm1.weight"], sd[p + "norm1.bias"]), "n2": (sd[p + "norm2.weight"], sd[p + "norm2.bias"])})
+    cw = sd["model.patch_embed.proj.weight"]
+    D, ps = int(cw.shape[0]), int(cw.shape[-1])
+    T = int(sd["model.pos_embed"].shape[1])
+    side = int(round((T - 1) ** 0.5))
+    if side * side != T - 1:
+        raise ValueError(f"pos_embed holds {T} tokens: not a square patch grid + cls token")
+    H = int(num_heads) if num_heads is not None else max(D // 64, 1)
+    if D % H:
+        raise ValueError(f"embed dim {D} is not divisible by {H} heads")
+    return dict(in_scale=sd["quant.scale"], in_zp=sd["quant.zero_point"],
+                conv=(cw, sd.get("model.patch_embed.proj.bias"), float(sd["model.patch_embed.proj.scale"]),
+                      int(sd["model.patch_embed.proj.zero_point"])), ps=ps, HW=side * ps,
+                blocks=blocks, head=lin("model.head"), norm=(sd["model.norm.weight"], sd["model.norm.bias"]),
+                cls=sd["model.cls_token"], pos=sd["model.pos_embed"], H=H, eps=float(eps), attn_scale=float(D // H) ** -0.5)
+
+
+class ConvertedStudent:
+    """Runs the converted QATWrapper student on one GPU.  ``forward(images) -> fp32 logits [B, classes]``.
+
+    ``ConvertedStudent(converted_module, batch, device)`` takes the module stock ``convert()`` returns;
+    ``ConvertedStudent.from_state_dict(path_or_dict, batch, device)`` reads best_converted.pth directly (no module tree)."""
+
+    @classmethod
+    def from_state_dict(cls, state_dict, batch: int, device, num_heads=None, eps: float = 1e-6):
+        if not isinstance(state_dict, dict):
+            state_dict = torch.load(state_dict, map_location="cpu", weights_only=False)   # packed params are (qtensor, bias) tuples
+        return cls(_spec_from_state_dict(state_dict, num_heads, eps), batch, device)
+
+    def __init__(self, converted, batch: int, device):
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError("qatvit_b200: the converted executor needs a CUDA device (there is no CPU fallback)")
-        vit = converted.model
-        if type(vit.blocks[0].norm1).__module__.startswith("torch.ao.nn.quantized"):
-            raise NotImplementedError("quantized LayerNorm (observed nn.LayerNorm variant) is not supported by the int8 executor")
+        spec = converted if isinstance(converted, dict) else _spec_from_module(converted)
         self.dev = dev
         self.B = batch
-        pe = vit.patch_embed
-        self.D = vit.embed_dim
-        self.H = vit.blocks[0].attn.num_heads
-        self.ps = pe.proj.kernel_size[0]
-        self.HW = pe.img_size[0]
-        self.P = pe.num_patches
+        self.D = int(spec["pos"].shape[-1])
+        self.H = int(spec["H"])
+        self.ps = int(spec["ps"])
+        self.HW = int(spec["HW"])
+        self.P = (self.HW // self.ps) ** 2
         self.T = self.P + 1
-        self.L = len(vit.blocks)
-        self.eps = float(vit.blocks[0].norm1.eps)
-        self.attn_scale = float(vit.blocks[0].attn.scale)
+        self.L = len(spec["blocks"])
+        self.eps = float(spec["eps"])
+        self.attn_scale = float(spec["attn_scale"])
         B, T, D, P = batch, self.T, self.D, self.P
         M = B * T
         f32 = dict(dtype=torch.float32, device=dev)
         # nnq.Quantize (from QuantStub): static input qparams
-        self.in_scale = converted.quant.scale.detach().reshape(1).to(**f32)
-        self.in_zp = converted.quant.zero_point.detach().reshape(1).to(torch.int32).to(dev)
-        conv = pe.proj
-        self.conv = _QLin(conv.weight(), conv.bias(), conv.scale, conv.zero_point, dev)
+        self.in_scale = spec["in_scale"].detach().reshape(1).to(**f32)
+        self.in_zp = spec["in_zp"].detach().reshape(1).to(torch.int32).to(dev)
+        self.conv = _QLin(*spec["conv"], dev)
         self.blocks = []
-        for blk in vit.blocks:
+        for blk in spec["blocks"]:
             d: Dict[str, object] = {}
-            for name, mod in (("qkv", blk.attn.qkv), ("proj", blk.attn.proj), ("fc1", blk.mlp.fc1), ("fc2", blk.mlp.fc2)):
-                w, b = _unpack_linear(mod)
-                d[name] = _QLin(w, b, mod.scale, mod.zero_point, dev)
-            d["n1"] = (blk.norm1.weight.detach().to(**f32), blk.norm1.bias.detach().to(**f32))
-            d["n2"] = (blk.norm2.weight.detach().to(**f32), blk.norm2.bias.detach().to(**f32))
+            for name in ("qkv", "proj", "fc1", "fc2"):
+                d[name] = _QLin(*blk[name], dev)
+            d["n1"] = tuple(t.detach().to(**f32) for t in blk["n1"])
+            d["n2"] = tuple(t.detach().to(**f32) for t in blk["n2"])
             self.blocks.append(d)
-        w, b = _unpack_linear(vit.head)
-        self.head = _QLin(w, b, vit.head.scale, vit.head.zero_point, dev)
-        self.norm = (vit.norm.weight.detach().to(**f32), vit.norm.bias.detach().to(**f32))
-        self.cls = vit.cls_token.detach().reshape(-1).to(**f32)
-        self.pos = vit.pos_embed.detach().reshape(T, D).to(**f32)
+        self.head = _QLin(*spec["head"], dev)
+        self.norm = tuple(t.detach().to(**f32) for t in spec["norm"])
+        self.cls = spec["cls"].detach().reshape(-1).to(**f32)
+        self.pos = spec["pos"].detach().reshape(T, D).to(**f32)
         self.F = self.blocks[0]["fc1"].N
         self.C = self.head.N
         F = self.F

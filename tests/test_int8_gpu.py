@@ -148,3 +148,18 @@ def test_converted_student_per_layer_and_end_to_end(cuda_dev, backend, sname, im
     diff = logits.cpu() - ref_logits
     assert float(diff.abs().max()) <= 6.0 * step + 1e-6
     assert float(diff.norm() / ref_logits.norm()) < 8e-2
+
+
+def test_best_converted_pth_reader_runs_identically(cuda_dev, tmp_path):
+    """ConvertedStudent.from_state_dict(best_converted.pth) == ConvertedStudent(converted module): same operands, same
+    kernels, bit-identical logits (the stock file format of ref qat_trainer.py:386-388 is all the executor needs)."""
+    from qatvit_b200.int8 import ConvertedStudent
+    conv, images = _converted("fbgemm", "vit_test_tiny", "vit_test_teacher", 64, 4)
+    path = tmp_path / "best_converted.pth"
+    torch.save(conv.state_dict(), path)
+    a = ConvertedStudent(conv, 4, cuda_dev)
+    b = ConvertedStudent.from_state_dict(str(path), 4, cuda_dev)
+    la = a(images.to(cuda_dev)).clone()
+    lb = b(images.to(cuda_dev)).clone()
+    torch.cuda.synchronize()
+    assert torch.isfinite(la).all() and torch.equal(la, lb)
