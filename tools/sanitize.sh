@@ -1,5 +1,7 @@
 #!/bin/bash
 # compute-sanitizer pass over the op-level GPU tests (mandatory for hand-written mbarrier / TMA / tcgen05 code).
+# NOTE (round 1): this pool answers `compute-sanitizer is closed on this pool` (exit 86) -- the out-of-bounds check that
+# runs here is tests/test_guard_bands_gpu.py (guard bands around every engine buffer).  Kept for pools where the tool is open.
 # Run under gpurun, one GPU:   gpurun --timeout 1500 -- 'bash tools/sanitize.sh'
 # Small-shape op tests only (the sanitizer serialises kernels and slows them 20-100x); each tool writes
 # gpurun_out/sanitize_<tool>.log, a line "ERROR SUMMARY: 0 errors" at its end is the pass criterion.
