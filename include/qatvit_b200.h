@@ -32,6 +32,8 @@ const char* qv_last_error(void);      /* thread-local message of the last failin
 int qv_device_sm_count(void);         /* SMs of the current device, <0 on error (no device) */
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
 int64_t qv_launch_count(void);
+/* how many of those were CTA-pair GEMMs (tcgen05 cta_group::2, clusters of two CTAs; see qv_gemm_bf16) */
+int64_t qv_gemm_pair_launches(void);
 
 /* ---- observer + fake-quant (replaces torch.fused_moving_avg_obs_fake_quant,
  *      torch/ao/quantization/fake_quantize.py:423-438, called by the hooks prepare_qat installs:

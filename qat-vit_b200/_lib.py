@@ -79,6 +79,7 @@ _SIGNATURES = {
     "qv_last_error": (c_char_p, []),
     "qv_device_sm_count": (c_int, []),
     "qv_launch_count": (c_int64, []),
+    "qv_gemm_pair_launches": (c_int64, []),
     "qv_minmax_reset": (c_int, [_P, c_int, _P]),
     "qv_minmax_accumulate": (c_int, [_P, c_int64, _P, _P]),
     "qv_obs_update": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_float, c_int32, c_int32, c_int32, _P]),

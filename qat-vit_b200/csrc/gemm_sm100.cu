@@ -19,6 +19,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <atomic>
 #include <mutex>
 
 #include "qv_common.cuh"
@@ -41,6 +42,9 @@ constexpr int A_PLANE_BYTES = BM * BK * 2;
 constexpr int epi_warp_bytes(int epi) { return (epi == 2 ? 3 : epi == 1 ? 2 : 1) * 32 * 128; }   // EPI 2: y tile x2 + planes
 constexpr int epi_terms_bytes(int epi) { return epi >= 1 ? 0 : 8 * 2 * 32 * 4; }   // per-warp [mult][bias] column terms
 constexpr int SMEM_LIMIT = 232448;             // 227 KB
+#ifndef QV_GEMM_PAIR_DEFAULT
+#define QV_GEMM_PAIR_DEFAULT 0                 // bit 0: mixed-format (teacher) GEMMs, bit 1: bf16-plane GEMMs, bit 2: gradient-planes dgrad
+#endif
 
 struct GemmKParams {
   int64_t M, N;
@@ -74,9 +78,10 @@ struct GemmKParams {
   uint32_t* obs_ticket;
 };
 
-template <int BN, int NA, int NB, int EPI = 0>
+template <int BN, int NA, int NB, int EPI = 0, int CG = 1>
 struct Cfg {
-  static constexpr int B_PLANE_BYTES = BN * BK * 2;
+  // CG = 2 (CTA pair, tcgen05 cta_group::2): a 256 x BN tile per pair; each CTA stages its 128 rows of A and BN / 2 rows of B
+  static constexpr int B_PLANE_BYTES = (BN / CG) * BK * 2;
   static constexpr int STAGE_BYTES = NA * A_PLANE_BYTES + NB * B_PLANE_BYTES;
   static constexpr int EPI_WARP_BYTES = epi_warp_bytes(EPI);
   static constexpr int EPI_BYTES = 8 * EPI_WARP_BYTES + epi_terms_bytes(EPI);
@@ -88,6 +93,7 @@ struct Cfg {
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN must be a multiple of 32 up to 256");
   static_assert(EPI == 0 || BN % 64 == 0, "plane output works on 64-column chunks");
+  static_assert(CG == 1 || (CG == 2 && BN % 16 == 0 && B_PLANE_BYTES % 1024 == 0), "CTA pair: N a multiple of 16, 1 KB aligned half tiles");
 };
 
 #ifdef QV_ATTN_DEBUG      // timeline-instrumented build (make debug): clock64 events of CTA 0, read back with qv_gemm_debug_read
@@ -106,12 +112,19 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 // EPI = 2: dgrad producing the NEXT layer's gradient planes: the accumulator (dL/d FQ(y) or dL/d GELU(FQ(y))) is multiplied by
 // gelu'(FQ(y)) -- a 256-entry table over the integer codes, built per CTA -- and the STE mask recomputed from the raw y tile,
 // folded with the per-channel weight scale and written as hi/lo planes; bias-grad column sums leave as per-slab partials.
-template <int BN, int NA, int NB, bool A_MN, bool B_MN, int EPI, int MIX>
+template <int BN, int NA, int NB, bool A_MN, bool B_MN, int EPI, int MIX, int CG = 1>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_o, const __grid_constant__ CUtensorMap map_y, const GemmKParams p) {
-  using C = Cfg<BN, NA, NB, EPI>;
+  using C = Cfg<BN, NA, NB, EPI, CG>;
   static_assert(!MIX || (NA == 2 && NB == 2 && !A_MN && !B_MN), "mixed operands: two K-major regions per operand");
+  static_assert(CG == 1 || (!A_MN && !B_MN), "CTA pairs: K-major operands only");
+  // CTA pair (CG = 2, launched as clusters of 2): p.tiles_m counts 256-row tiles; CTA `rank` owns rows [rank * 128, +128) of
+  // the pair's tile and loads the B rows [rank * BN / 2, +BN / 2); rank 0 issues the MMAs for both.
+  const int rank = (CG == 2) ? static_cast<int>(cluster_ctarank()) : 0;
+  const int item0 = static_cast<int>(blockIdx.x) / CG, item_step = static_cast<int>(gridDim.x) / CG;
+  auto m_of = [&](int item) { return ((item / p.tiles_n) % p.tiles_m) * CG + rank; };
+  if constexpr (CG == 2) cluster_sync_all();        // both CTAs of the pair are resident before anything crosses over
   constexpr int EPI_WARP_BYTES = C::EPI_WARP_BYTES;
   constexpr int EPI_BYTES = C::EPI_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -148,7 +161,7 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
-      mbar_init(&tmem_empty[b], 256);
+      mbar_init(&tmem_empty[b], 256 * CG);          // every epilogue thread of the pair arrives on the leader's barrier
     }
     if constexpr (EPI == 2) {
       prefetch_tensormap(&map_y);
@@ -156,11 +169,20 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  if (warp == 1) {
+    if constexpr (CG == 2) tmem_alloc_pair(tmem_slot, C::TMEM_COLS);
+    else tmem_alloc(tmem_slot, C::TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();        // barrier inits of both CTAs are visible cluster-wide
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // epilogue threads release an accumulator buffer on the LEADER's barrier (the only CTA whose MMA thread waits on it)
+  auto tmem_empty_arrive = [&](int buf) {
+    if constexpr (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[buf]), 0));
+    else mbar_arrive(&tmem_empty[buf]);
+  };
 
   const int num_items = p.tiles_m * p.tiles_n * (p.nbatch > 1 ? p.nbatch : p.splits);
 
@@ -172,9 +194,9 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #ifdef QV_ATTN_DEBUG
       int gdbg_n = 0;
 #endif
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      for (int item = item0; item < num_items; item += item_step) {
         const int n_blk = item % p.tiles_n;
-        const int m_blk = (item / p.tiles_n) % p.tiles_m;
+        const int m_blk = m_of(item);
         const int outer = item / (p.tiles_n * p.tiles_m);
         const int z = p.nbatch > 1 ? 0 : outer;
         const int bt = p.nbatch > 1 ? outer : 0;
@@ -187,9 +209,22 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           GDBG(0, 1);
           mbar_wait(&empty_bar[stage], phase ^ 1);
           GDBG(0, 2);
-          mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + NA * A_PLANE_BYTES;
+          if constexpr (CG == 2) {
+            // both CTAs' bytes complete on the leader's full barrier (its MMA thread is the only consumer)
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+            const uint32_t lead_bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+#pragma unroll
+            for (int pa = 0; pa < NA; ++pa)
+              tma_load_4d_pair(sa + pa * A_PLANE_BYTES, &map_a, lead_bar, a_col + kb * BK, m_blk * BM, a_c2, pa);
+#pragma unroll
+            for (int pb = 0; pb < NB; ++pb)
+              tma_load_4d_pair(sb + pb * C::B_PLANE_BYTES, &map_b, lead_bar, b_col + kb * BK, n_blk * BN + rank * (BN / 2), b_c2, pb);
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
 #pragma unroll
           for (int pa = 0; pa < NA; ++pa) {
             if (!A_MN) {
@@ -224,7 +259,7 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // operands in uniform registers; under an `if (lane == 0)` region every tcgen05.mma paid an R2UR + ELECT waterfall loop
     // (~90 cycles of issue per instruction -- as long as a 128 x 192 x 16 MMA takes to execute).
     {
-      static_assert(!MIX, "the mixed operand format is issued by the single-lane issuer only");
+      static_assert(!MIX && CG == 1, "the mixed operand format and CTA pairs are issued by the single-lane issuer only");
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
       constexpr uint32_t a_lbo = A_MN ? 8192u : 16u, b_lbo = B_MN ? 8192u : 16u;
       constexpr uint32_t a_kadv = A_MN ? (UMMA_K * 128u) : (UMMA_K * 2u);   // bytes per 16-deep k step
@@ -277,18 +312,28 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // R2UR/ELECT waterfall in the attention kernels, where N = 64 instructions are issue-bound -- measured 3-4 % SLOWER here:
     // a 128 x 192 x 16 MMA executes for as long as its issue sequence takes, and 32 polling lanes steal issue slots from the
     // two epilogue warps sharing the sub-partition.)
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN, A_MN, B_MN);
       constexpr uint32_t a_lbo = A_MN ? 8192u : 16u, b_lbo = B_MN ? 8192u : 16u;
       constexpr uint32_t a_kadv = A_MN ? (UMMA_K * 128u) : (UMMA_K * 2u);   // bytes per 16-deep k step
       constexpr uint32_t b_kadv = B_MN ? (UMMA_K * 128u) : (UMMA_K * 2u);
+      // CG = 2: one instruction drives both SMs (M = 256); descriptors are offsets valid in BOTH CTAs' shared memory
+      auto mma16 = [](uint32_t d, uint64_t da, uint64_t db, uint32_t id, uint32_t acc) {
+        if constexpr (CG == 2) umma_bf16_pair(d, da, db, id, acc); else umma_bf16(d, da, db, id, acc);
+      };
+      auto mma8 = [](uint32_t d, uint64_t da, uint64_t db, uint32_t id, uint32_t acc) {
+        if constexpr (CG == 2) umma_f8_pair(d, da, db, id, acc); else umma_f8(d, da, db, id, acc);
+      };
+      auto commit = [](uint64_t* bar) {
+        if constexpr (CG == 2) umma_commit_pair(bar); else umma_commit(bar);
+      };
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
 #ifdef QV_ATTN_DEBUG
       int gdbg_n = 0;
 #endif
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
+      for (int item = item0; item < num_items; item += item_step, ++local) {
         const int z = p.nbatch > 1 ? 0 : item / (p.tiles_n * p.tiles_m);
         const int kb0 = z * p.kb_per_split;
         const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
@@ -310,22 +355,22 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             // region 0 of each operand: fp16 (x 2^5 / x 2^9); region 1: per 64-deep k-block a 128-byte row = 64 fp8 of the
             // value (hi8) then 64 fp8 of the fp16 rounding residual (lo8).  fp32-grade product = hi16.hi16 (4 x K16, kind::f16)
             // + hi8.lo8 + lo8.hi8 (2 x K32 each, kind::f8f6f4 at twice the rate), every term scaled by 2^14 into ONE accumulator.
-            constexpr uint32_t idesc16 = umma_idesc_f16(BM, BN);
-            constexpr uint32_t idesc_hl = umma_idesc_f8(BM, BN, 1u, 1u);    // A hi8 e5m2 x B lo8 e5m2
-            constexpr uint32_t idesc_lh = umma_idesc_f8(BM, BN, 1u, 0u);    // A lo8 e5m2 x B hi8 e4m3
+            constexpr uint32_t idesc16 = umma_idesc_f16(BM * CG, BN);
+            constexpr uint32_t idesc_hl = umma_idesc_f8(BM * CG, BN, 1u, 1u);    // A hi8 e5m2 x B lo8 e5m2
+            constexpr uint32_t idesc_lh = umma_idesc_f8(BM * CG, BN, 1u, 0u);    // A lo8 e5m2 x B hi8 e4m3
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t da = umma_smem_desc(sa + k * 32u, 16u, 1024u);
               const uint64_t db = umma_smem_desc(sb + k * 32u, 16u, 1024u);
-              umma_bf16(d_tmem, da, db, idesc16, (kb > kb0 || k > 0) ? 1u : 0u);
+              mma16(d_tmem, da, db, idesc16, (kb > kb0 || k > 0) ? 1u : 0u);
             }
             const uint32_t sa8 = sa + A_PLANE_BYTES, sb8 = sb + C::B_PLANE_BYTES;
 #pragma unroll
             for (int k = 0; k < 2; ++k)
-              umma_f8(d_tmem, umma_smem_desc(sa8 + k * 32u, 16u, 1024u), umma_smem_desc(sb8 + 64u + k * 32u, 16u, 1024u), idesc_hl, 1u);
+              mma8(d_tmem, umma_smem_desc(sa8 + k * 32u, 16u, 1024u), umma_smem_desc(sb8 + 64u + k * 32u, 16u, 1024u), idesc_hl, 1u);
 #pragma unroll
             for (int k = 0; k < 2; ++k)
-              umma_f8(d_tmem, umma_smem_desc(sa8 + 64u + k * 32u, 16u, 1024u), umma_smem_desc(sb8 + k * 32u, 16u, 1024u), idesc_lh, 1u);
+              mma8(d_tmem, umma_smem_desc(sa8 + 64u + k * 32u, 16u, 1024u), umma_smem_desc(sb8 + k * 32u, 16u, 1024u), idesc_lh, 1u);
           } else {
 #pragma unroll
           for (int pr = 0; pr < C::NPAIRS; ++pr) {
@@ -336,15 +381,15 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t da = umma_smem_desc(sa + pa * A_PLANE_BYTES + k * a_kadv, a_lbo, 1024u);
               const uint64_t db = umma_smem_desc(sb + pb * C::B_PLANE_BYTES + k * b_kadv, b_lbo, 1024u);
-              umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || pr > 0 || k > 0) ? 1u : 0u);
+              mma16(d_tmem, da, db, idesc, (kb > kb0 || pr > 0 || k > 0) ? 1u : 0u);
             }
           }
           }
-          umma_commit(&empty_bar[stage]);       // frees this smem stage once the MMAs have read it
+          commit(&empty_bar[stage]);            // frees this smem stage (in both CTAs of a pair) once the MMAs have read it
           GDBG(1, 14);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[buf]);           // accumulator complete -> epilogue
+        commit(&tmem_full[buf]);                // accumulator complete -> epilogue (of both CTAs of a pair)
       }
     }
 #endif
@@ -373,16 +418,16 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const bool use_lut = p.ep_gelu != 0;
       auto issue_raw = [&](int item, int u, uint32_t slot) {      // lane 0 only
         const int n_blk = item % p.tiles_n;
-        const int m_blk = (item / p.tiles_n) % p.tiles_m;
+        const int m_blk = m_of(item);
         mbar_expect_tx(my_bar, 4096);
         tma_load_3d(my_raw + slot * 4096u, &map_y, my_bar, n_blk * BN + u * 32, m_blk * BM + q * 32, 0);
       };
       uint32_t raw_phase = 0;             // also the slot of the tile being waited for (loads alternate slots)
       int local = 0;
-      if (static_cast<int>(blockIdx.x) < num_items && lane == 0) issue_raw(blockIdx.x, par, 0);
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
+      if (item0 < num_items && lane == 0) issue_raw(item0, par, 0);
+      for (int item = item0; item < num_items; item += item_step, ++local) {
         const int n_blk = item % p.tiles_n;
-        const int m_blk = (item / p.tiles_n) % p.tiles_m;
+        const int m_blk = m_of(item);
         const int buf = local & 1;
         const uint32_t use = static_cast<uint32_t>(local >> 1);
         const int row0 = m_blk * BM + q * 32;
@@ -407,7 +452,7 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const bool last = u + 2 >= NU;
           if (lane == 0) {
             if (!last) issue_raw(item, u + 2, raw_phase);
-            else if (item + static_cast<int>(gridDim.x) < num_items) issue_raw(item + gridDim.x, par, raw_phase);
+            else if (item + item_step < num_items) issue_raw(item + item_step, par, raw_phase);
           }
           if (!acc_ready) {
             mbar_wait(&tmem_full[buf], use & 1);
@@ -419,7 +464,7 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           tmem_ld_wait();
           if (last) {                                             // this warp's last TMEM read of the buffer
             tc_fence_before();
-            mbar_arrive(&tmem_empty[buf]);
+            tmem_empty_arrive(buf);
           }
           const int64_t n0 = static_cast<int64_t>(n_blk) * BN + u * 32;
           if (n0 >= p.N || static_cast<int64_t>(row0) >= p.M) continue;          // warp-uniform
@@ -493,9 +538,9 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #ifdef QV_ATTN_DEBUG
     int gdbg_n = (threadIdx.x == 64) ? 0 : 4096;
 #endif
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
+    for (int item = item0; item < num_items; item += item_step, ++local) {
       const int n_blk = item % p.tiles_n;
-      const int m_blk = (item / p.tiles_n) % p.tiles_m;
+      const int m_blk = m_of(item);
       const int outer = item / (p.tiles_n * p.tiles_m);
       const int bt = p.nbatch > 1 ? outer : 0;
       const int bo = bt / p.batch_inner, bi = bt % p.batch_inner;
@@ -524,7 +569,7 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           tmem_ld_cols<CW>(t_base + (ch + 2) * CW, nxt);
         } else {                                                // this warp's last chunk is in registers
           tc_fence_before();
-          mbar_arrive(&tmem_empty[buf]);
+          tmem_empty_arrive(buf);
           GDBG(2, 22);
         }
         const int64_t n0 = static_cast<int64_t>(n_blk) * BN + c0;
@@ -667,10 +712,13 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
 
   tc_fence_before();
-  __syncthreads();
+  __syncwarp();
+  if constexpr (CG == 2) cluster_sync_all();   // no MMA still reads the peer's tiles, no arrive is in flight to a CTA that exits
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if constexpr (CG == 2) tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
+    else tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -697,19 +745,45 @@ __global__ void qv_splitk_reduce_kernel(const float* __restrict__ ws, int splits
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <int BN, int NA, int NB, bool A_MN, bool B_MN, int EPI = 0, int MIX = 0>
+std::atomic<int64_t> g_pair_launches{0};       // qv_gemm_pair_launches(): GEMMs launched as CTA pairs
+
+template <int BN, int NA, int NB, bool A_MN, bool B_MN, int EPI = 0, int MIX = 0, int CG = 1>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const GemmKParams& kp, int grid,
            cudaStream_t st, const CUtensorMap* my = nullptr) {
-  using C = Cfg<BN, NA, NB, EPI>;
+  using C = Cfg<BN, NA, NB, EPI, CG>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(qv_gemm_kernel<BN, NA, NB, A_MN, B_MN, EPI, MIX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    attr_err = cudaFuncSetAttribute(qv_gemm_kernel<BN, NA, NB, A_MN, B_MN, EPI, MIX, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     C::SMEM_BYTES);
   });
   QV_REQUIRE(attr_err == cudaSuccess, QV_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
-  qv_gemm_kernel<BN, NA, NB, A_MN, B_MN, EPI, MIX><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mb, mo, my ? *my : mo, kp);
+  if constexpr (CG == 2) {       // CTA pairs: clusters of two CTAs (the two SMs of a TPC)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid), 1, 1);
+    cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, qv_gemm_kernel<BN, NA, NB, A_MN, B_MN, EPI, MIX, CG>, ma, mb, mo, my ? *my : mo, kp);
+    QV_REQUIRE(e == cudaSuccess, QV_ERR_CUDA, "cudaLaunchKernelEx(cluster 2): %s", cudaGetErrorString(e));
+    g_pair_launches.fetch_add(1, std::memory_order_relaxed);
+  } else {
+    qv_gemm_kernel<BN, NA, NB, A_MN, B_MN, EPI, MIX, CG><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mb, mo, my ? *my : mo, kp);
+  }
   return qv_check_launch("qv_gemm_bf16");
+}
+
+// CTA pairs (cta_group::2) for the big K-major GEMMs: QV_GEMM_PAIR=0 switches them off (A/B measurement)
+int pair_mode() {
+  const char* e = getenv("QV_GEMM_PAIR");     // read per launch: tests flip it inside one process
+  return e ? atoi(e) : QV_GEMM_PAIR_DEFAULT;
 }
 
 template <int BN, int NA, int NB>
@@ -790,10 +864,17 @@ extern "C" int qv_gemm_bf16(const qv_gemm_args* a, void* stream) {
                "plane output takes a bias term only (no scale / alpha / observer)");
     QV_REQUIRE(!a->bias || qv_aligned16(a->bias), QV_ERR_INVALID, "plane output needs a 16-byte aligned bias");
   }
+  // CTA pairs: unsplit, unbatched K-major GEMMs on 192-wide tiles with at least one 256-row tile per SM pair
+  // (teacher Linears, student forward / dgrad, dgrad + gradient planes); everything else stays one CTA per tile.
+  const int sms_all = qv_num_sms();
+  const bool pair = pair_mode() != 0 && BN == 192 && splits == 1 && nbatch == 1 && !a->a.mn_major && !a->b.mn_major &&
+                    a->a_planes == 2 && (mix || planes_out || grad_epi || a->b_planes == 1 || a->b_planes == 2) &&
+                    a->M >= 256LL * (sms_all / 2) && (pair_mode() & (mix ? 1 : grad_epi ? 4 : 2)) != 0;
+  const int CGh = pair ? 2 : 1;
   CUtensorMap ma, mb, mo, my;
   int rc = make_map(&ma, a->a, a->a_planes, a->a.mn_major ? 64 : BM);
   if (rc) return rc;
-  rc = make_map(&mb, a->b, a->b_planes, a->b.mn_major ? 64 : BN);
+  rc = make_map(&mb, a->b, a->b_planes, a->b.mn_major ? 64 : BN / CGh);
   if (rc) return rc;
   if (splits > 1) {
     QV_REQUIRE(a->workspace != nullptr, QV_ERR_INVALID, "split-K needs a workspace");
@@ -822,7 +903,7 @@ extern "C" int qv_gemm_bf16(const qv_gemm_args* a, void* stream) {
   kp.M = a->M;
   kp.N = a->N;
   kp.kblocks = static_cast<int32_t>((a->K + BK - 1) / BK);
-  kp.tiles_m = static_cast<int32_t>((a->M + BM - 1) / BM);
+  kp.tiles_m = static_cast<int32_t>((a->M + BM * CGh - 1) / (BM * CGh));
   kp.tiles_n = static_cast<int32_t>((a->N + BN - 1) / BN);
   int sp = splits > kp.kblocks ? kp.kblocks : splits;
   kp.kb_per_split = (kp.kblocks + sp - 1) / sp;
@@ -857,29 +938,39 @@ extern "C" int qv_gemm_bf16(const qv_gemm_args* a, void* stream) {
   const int64_t items = static_cast<int64_t>(kp.tiles_m) * kp.tiles_n * (nbatch > 1 ? nbatch : kp.splits);
   QV_REQUIRE(items < (1LL << 31), QV_ERR_UNSUPPORTED, "too many tiles");
   const int sms = qv_num_sms();
-  const int grid = static_cast<int>(items < sms ? items : sms);
+  const int units = sms / CGh;                                   // CTAs, or CTA pairs
+  const int grid = static_cast<int>(items < units ? items : units) * CGh;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool amn = a->a.mn_major != 0, bmn = a->b.mn_major != 0;
   if (grad_epi) {
+    if (pair) return launch<192, 2, 1, false, false, 2, 0, 2>(ma, mb, mo, kp, grid, st, &my);
     if (BN == 128) return launch<128, 2, 1, false, false, 2>(ma, mb, mo, kp, grid, st, &my);
     return launch<192, 2, 1, false, false, 2>(ma, mb, mo, kp, grid, st, &my);
   }
   if (mix) {
     if (planes_out) {
+      if (pair) return launch<192, 2, 2, false, false, 1, 1, 2>(ma, mb, mo, kp, grid, st);
       if (BN == 128) return launch<128, 2, 2, false, false, 1, 1>(ma, mb, mo, kp, grid, st);
       return launch<192, 2, 2, false, false, 1, 1>(ma, mb, mo, kp, grid, st);
     }
+    if (pair) return launch<192, 2, 2, false, false, 0, 1, 2>(ma, mb, mo, kp, grid, st);
     if (BN == 64) return launch<64, 2, 2, false, false, 0, 1>(ma, mb, mo, kp, grid, st);
     if (BN == 128) return launch<128, 2, 2, false, false, 0, 1>(ma, mb, mo, kp, grid, st);
     return launch<192, 2, 2, false, false, 0, 1>(ma, mb, mo, kp, grid, st);
   }
   if (planes_out) {
     if (a->b_planes == 1) {
+      if (pair) return launch<192, 2, 1, false, false, 1, 0, 2>(ma, mb, mo, kp, grid, st);
       if (BN == 128) return launch<128, 2, 1, false, false, 1>(ma, mb, mo, kp, grid, st);
       return launch<192, 2, 1, false, false, 1>(ma, mb, mo, kp, grid, st);
     }
+    if (pair) return launch<192, 2, 2, false, false, 1, 0, 2>(ma, mb, mo, kp, grid, st);
     if (BN == 128) return launch<128, 2, 2, false, false, 1>(ma, mb, mo, kp, grid, st);
     return launch<192, 2, 2, false, false, 1>(ma, mb, mo, kp, grid, st);
+  }
+  if (pair) {
+    if (a->b_planes == 1) return launch<192, 2, 1, false, false, 0, 0, 2>(ma, mb, mo, kp, grid, st);
+    return launch<192, 2, 2, false, false, 0, 0, 2>(ma, mb, mo, kp, grid, st);
   }
   switch (BN) {
     case 64: return launch_planes<64>(a->a_planes, a->b_planes, amn, bmn, ma, mb, mo, kp, grid, st);
@@ -887,6 +978,8 @@ extern "C" int qv_gemm_bf16(const qv_gemm_args* a, void* stream) {
     default: return launch_planes<192>(a->a_planes, a->b_planes, amn, bmn, ma, mb, mo, kp, grid, st);
   }
 }
+
+extern "C" int64_t qv_gemm_pair_launches(void) { return g_pair_launches.load(std::memory_order_relaxed); }
 
 extern "C" int qv_splitk_reduce(const float* workspace, int32_t splits, int64_t M, int64_t N, const float* row_rscale,
                                 const float* alpha, const uint8_t* mask, float* out, int32_t accumulate, void* stream) {

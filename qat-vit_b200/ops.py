@@ -328,6 +328,11 @@ def launch_count() -> int:
     return int(_lib.lib().qv_launch_count())
 
 
+def gemm_pair_launches() -> int:
+    """GEMM launches that ran as CTA pairs (cta_group::2) so far in this process."""
+    return int(_lib.lib().qv_gemm_pair_launches())
+
+
 def resid_ln_fwd(x_in, y_raw, fq, gamma, beta, eps, R, D, *, in_row_stride=1, x_out=None, h_planes=None, h_f32=None,
                  mean=None, rstd=None, minmax=None, planes_mix=False):
     """x_out = x_in + FQ(y_raw); h = LN(x_out).  fq = (scale, zero_point, qmin, qmax) or None.
