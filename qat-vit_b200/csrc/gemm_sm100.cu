@@ -43,7 +43,10 @@ constexpr int epi_warp_bytes(int epi) { return (epi == 2 ? 3 : epi == 1 ? 2 : 1)
 constexpr int epi_terms_bytes(int epi) { return epi >= 1 ? 0 : 8 * 2 * 32 * 4; }   // per-warp [mult][bias] column terms
 constexpr int SMEM_LIMIT = 232448;             // 227 KB
 #ifndef QV_GEMM_PAIR_DEFAULT
-#define QV_GEMM_PAIR_DEFAULT 0                 // bit 0: mixed-format (teacher) GEMMs, bit 1: bf16-plane GEMMs, bit 2: gradient-planes dgrad
+// bit 0: mixed-format (teacher) GEMMs with fp32 output, bit 4: ... with plane output, bit 1: (2,2) bf16 hi/lo plane GEMMs,
+// bit 2: gradient-planes dgrad, bit 3: (2,1) GEMMs, bit 5: 256-wide tiles for the mixed-format pairs.
+// The (2,1) student GEMMs are MMA-bound with one CTA per tile already (56 KB per k-block against 8 MMAs) and gain nothing.
+#define QV_GEMM_PAIR_DEFAULT 51
 #endif
 
 struct GemmKParams {
@@ -78,15 +81,19 @@ struct GemmKParams {
   uint32_t* obs_ticket;
 };
 
-template <int BN, int NA, int NB, int EPI = 0, int CG = 1>
+// SPLIT (mixed-format CTA pairs): one pipeline stage holds ONE region of a k-block -- the fp16 planes of A and B, or their fp8
+// value / residual planes.  The fp16 product needs only the first, the two fp8 cross terms only the second, so the stages are
+// half as large, twice as many fit (5-6 instead of 2-3) and each is released as soon as its four MMAs have read it.
+template <int BN, int NA, int NB, int EPI = 0, int CG = 1, bool SPLIT = false>
 struct Cfg {
   // CG = 2 (CTA pair, tcgen05 cta_group::2): a 256 x BN tile per pair; each CTA stages its 128 rows of A and BN / 2 rows of B
   static constexpr int B_PLANE_BYTES = (BN / CG) * BK * 2;
-  static constexpr int STAGE_BYTES = NA * A_PLANE_BYTES + NB * B_PLANE_BYTES;
+  static constexpr int STAGE_BYTES = SPLIT ? (A_PLANE_BYTES + B_PLANE_BYTES) : (NA * A_PLANE_BYTES + NB * B_PLANE_BYTES);
+  static_assert(!SPLIT || (NA == 2 && NB == 2), "region-split stages: two regions per operand");
   static constexpr int EPI_WARP_BYTES = epi_warp_bytes(EPI);
   static constexpr int EPI_BYTES = 8 * EPI_WARP_BYTES + epi_terms_bytes(EPI);
   static constexpr int MAX_STAGES = (SMEM_LIMIT - 1024 - 256 - EPI_BYTES) / STAGE_BYTES;
-  static constexpr int STAGES = MAX_STAGES > 6 ? 6 : MAX_STAGES;
+  static constexpr int STAGES = MAX_STAGES > 6 ? 6 : MAX_STAGES;       // barrier block holds 2 x 6 + 13 words
   static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int NPAIRS = (NA == 2 && NB == 2) ? 3 : NA * NB;   // (hi,hi) (hi,lo) (lo,hi): lo*lo is dropped
@@ -116,7 +123,8 @@ template <int BN, int NA, int NB, bool A_MN, bool B_MN, int EPI, int MIX, int CG
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_o, const __grid_constant__ CUtensorMap map_y, const GemmKParams p) {
-  using C = Cfg<BN, NA, NB, EPI, CG>;
+  constexpr bool SPLIT = MIX != 0 && CG == 2;
+  using C = Cfg<BN, NA, NB, EPI, CG, SPLIT>;
   static_assert(!MIX || (NA == 2 && NB == 2 && !A_MN && !B_MN), "mixed operands: two K-major regions per operand");
   static_assert(CG == 1 || (!A_MN && !B_MN), "CTA pairs: K-major operands only");
   // CTA pair (CG = 2, launched as clusters of 2): p.tiles_m counts 256-row tiles; CTA `rank` owns rows [rank * 128, +128) of
@@ -211,7 +219,22 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           GDBG(0, 2);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + NA * A_PLANE_BYTES;
-          if constexpr (CG == 2) {
+          if constexpr (SPLIT) {
+            // region r of this k-block -> its own stage: [A region r: 128 rows][B region r: BN / 2 rows]
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+              if (r == 1) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                sa = smem + stage * C::STAGE_BYTES;
+              }
+              if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+              const uint32_t lead_bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+              tma_load_4d_pair(sa, &map_a, lead_bar, a_col + kb * BK, m_blk * BM, a_c2, r);
+              tma_load_4d_pair(sa + A_PLANE_BYTES, &map_b, lead_bar, b_col + kb * BK, n_blk * BN + rank * (BN / 2), b_c2, r);
+              if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            }
+            continue;
+          } else if constexpr (CG == 2) {
             // both CTAs' bytes complete on the leader's full barrier (its MMA thread is the only consumer)
             if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
             const uint32_t lead_bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
@@ -351,7 +374,28 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint32_t sb = sa + NA * A_PLANE_BYTES;
-          if constexpr (MIX) {
+          if constexpr (SPLIT) {
+            // stage = fp16 region: the main product; next stage = fp8 region: the two cross terms (see the MIX branch below)
+            constexpr uint32_t idesc16 = umma_idesc_f16(BM * CG, BN);
+            constexpr uint32_t idesc_hl = umma_idesc_f8(BM * CG, BN, 1u, 1u);
+            constexpr uint32_t idesc_lh = umma_idesc_f8(BM * CG, BN, 1u, 0u);
+            const uint32_t sb0 = sa + A_PLANE_BYTES;
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              mma16(d_tmem, umma_smem_desc(sa + k * 32u, 16u, 1024u), umma_smem_desc(sb0 + k * 32u, 16u, 1024u), idesc16,
+                    (kb > kb0 || k > 0) ? 1u : 0u);
+            commit(&empty_bar[stage]);
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa8 = smem_u32(smem + stage * C::STAGE_BYTES), sb8 = sa8 + A_PLANE_BYTES;
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+              mma8(d_tmem, umma_smem_desc(sa8 + k * 32u, 16u, 1024u), umma_smem_desc(sb8 + 64u + k * 32u, 16u, 1024u), idesc_hl, 1u);
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+              mma8(d_tmem, umma_smem_desc(sa8 + 64u + k * 32u, 16u, 1024u), umma_smem_desc(sb8 + k * 32u, 16u, 1024u), idesc_lh, 1u);
+          } else if constexpr (MIX) {
             // region 0 of each operand: fp16 (x 2^5 / x 2^9); region 1: per 64-deep k-block a 128-byte row = 64 fp8 of the
             // value (hi8) then 64 fp8 of the fp16 rounding residual (lo8).  fp32-grade product = hi16.hi16 (4 x K16, kind::f16)
             // + hi8.lo8 + lo8.hi8 (2 x K32 each, kind::f8f6f4 at twice the rate), every term scaled by 2^14 into ONE accumulator.
@@ -750,7 +794,7 @@ std::atomic<int64_t> g_pair_launches{0};       // qv_gemm_pair_launches(): GEMMs
 template <int BN, int NA, int NB, bool A_MN, bool B_MN, int EPI = 0, int MIX = 0, int CG = 1>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const GemmKParams& kp, int grid,
            cudaStream_t st, const CUtensorMap* my = nullptr) {
-  using C = Cfg<BN, NA, NB, EPI, CG>;
+  using C = Cfg<BN, NA, NB, EPI, CG, (MIX != 0 && CG == 2)>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
@@ -869,8 +913,12 @@ extern "C" int qv_gemm_bf16(const qv_gemm_args* a, void* stream) {
   const int sms_all = qv_num_sms();
   const bool pair = pair_mode() != 0 && BN == 192 && splits == 1 && nbatch == 1 && !a->a.mn_major && !a->b.mn_major &&
                     a->a_planes == 2 && (mix || planes_out || grad_epi || a->b_planes == 1 || a->b_planes == 2) &&
-                    a->M >= 256LL * (sms_all / 2) && (pair_mode() & (mix ? 1 : grad_epi ? 4 : 2)) != 0;
+                    a->M >= 256LL * (sms_all / 2) && (pair_mode() & (mix ? (planes_out ? 16 : 1) : grad_epi ? 4 : a->b_planes == 2 ? 2 : 8)) != 0;
   const int CGh = pair ? 2 : 1;
+  // mixed-format pairs on 256-wide tiles (bit 5): 64 KB into each SM per k-block for 128 x 256 outputs (1 000 clk at 64 B/clk
+  // against 1 024 clk of MMA), 4 / 8 epilogue chunks split evenly over the two warps of a lane quarter (192: 3 chunks, 2 + 1),
+  // and 197 x N / 256 pair tiles fill 74 pairs in whole waves at the bench shapes
+  if (pair && mix && a->tile_n <= 0 && a->N % 256 == 0 && (pair_mode() & 32) != 0) BN = 256;
   CUtensorMap ma, mb, mo, my;
   int rc = make_map(&ma, a->a, a->a_planes, a->a.mn_major ? 64 : BM);
   if (rc) return rc;
@@ -949,10 +997,12 @@ extern "C" int qv_gemm_bf16(const qv_gemm_args* a, void* stream) {
   }
   if (mix) {
     if (planes_out) {
+      if (pair && BN == 256) return launch<256, 2, 2, false, false, 1, 1, 2>(ma, mb, mo, kp, grid, st);
       if (pair) return launch<192, 2, 2, false, false, 1, 1, 2>(ma, mb, mo, kp, grid, st);
       if (BN == 128) return launch<128, 2, 2, false, false, 1, 1>(ma, mb, mo, kp, grid, st);
       return launch<192, 2, 2, false, false, 1, 1>(ma, mb, mo, kp, grid, st);
     }
+    if (pair && BN == 256) return launch<256, 2, 2, false, false, 0, 1, 2>(ma, mb, mo, kp, grid, st);
     if (pair) return launch<192, 2, 2, false, false, 0, 1, 2>(ma, mb, mo, kp, grid, st);
     if (BN == 64) return launch<64, 2, 2, false, false, 0, 1>(ma, mb, mo, kp, grid, st);
     if (BN == 128) return launch<128, 2, 2, false, false, 0, 1>(ma, mb, mo, kp, grid, st);

@@ -3,7 +3,9 @@ and HALF of the B tile) against the one-CTA-per-tile kernel on identical operand
 along K, same epilogue code: the outputs must be bit-identical -- fp32, bf16 hi/lo planes, mixed planes, the gradient-planes
 epilogue with its bias-grad slab sums and the fused observer update.  M is chosen ragged against the 256-row pair tile
 (the last pair's second CTA is entirely out of range) and large enough for the pair path to be taken (>= 256 x 74 rows).
-QV_GEMM_PAIR (bit 0 mixed-format GEMMs, bit 1 bf16-plane GEMMs, bit 2 gradient-planes dgrad) is read per launch."""
+QV_GEMM_PAIR (bit 0 mixed-format GEMMs with fp32 output, bit 4 with plane output, bit 1 (2,2) bf16-plane GEMMs, bit 2 gradient-planes
+dgrad, bit 3 (2,1) GEMMs) is
+read per launch."""
 import os
 
 import pytest
@@ -37,7 +39,7 @@ def _both(fn):
         ref = fn()
         torch.cuda.synchronize()
         assert ops.gemm_pair_launches() == n0                 # one CTA per tile
-    with pair_mode(7):
+    with pair_mode(63):
         got = fn()
         torch.cuda.synchronize()
         assert ops.gemm_pair_launches() == n0 + 1             # the pair kernel really ran
@@ -160,7 +162,7 @@ def test_pair_is_deterministic_over_many_launches(cuda_dev):
     a = (torch.randn(M, K, generator=g) * 1.3).to(cuda_dev)
     w = (torch.randn(N, K, generator=g) * 0.02).to(cuda_dev)
     am, wm = ops.split_planes_mix(a), ops.split_planes_mix(w, weight=True)
-    with pair_mode(7):
+    with pair_mode(63):
         outs = [ops.gemm(Op.full(am), Op.full(wm), M, N, K, PAIRS_FP32, mix=True) for _ in range(30)]
         torch.cuda.synchronize()
     assert all(torch.equal(o, outs[0]) for o in outs[1:])
