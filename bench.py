@@ -329,6 +329,9 @@ def run_ours(args):
             traffic = json.load(f).get(top)
     how = (f"tcgen05.mma kind::f16 bf16 hi/lo planes x{PASSES.get(top, 1)}" if not (t_mixed and top == "gemm[teacher linear]") else
            "tcgen05.mma kind::f16 on fp16 values + 2 x kind::f8f6f4 cross terms on fp8 value / residual copies = 2 bf16-pass equivalents")
+    pairs = ops.gemm_pair_launches() > 0 and top == "gemm[teacher linear]"
+    if pairs:
+        how += "; CTA pairs (tcgen05 cta_group::2: 256 x 256 tile per SM pair, each SM stages 128 rows of A + half of B)"
     roofline = {"kernel": f"qv_gemm_kernel, {top} ({tv['count']} launches/step, {how}, fp32 accumulate in TMEM)",
                 "bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["tf_sustained"], "traffic": traffic,

@@ -176,6 +176,11 @@ typedef struct qv_gemm_args {
    * written in the mixed activation format (the next mixed GEMM's A operand). */
   int32_t mix;
 } qv_gemm_args;
+/* Scheduling (no ABI surface): unsplit, unbatched K-major GEMMs with M >= 256 x (SMs / 2) run as CTA PAIRS -- clusters of two
+ * CTAs on the two SMs of a TPC computing one 256 x tile_n tile with tcgen05 cta_group::2, each SM staging 128 rows of A and
+ * half of the B tile (the 4-byte-per-element operand formats are otherwise bound by the L2 -> SM fill rate, not the tensor
+ * pipe).  Results are bit-identical to one CTA per tile.  Environment variable QV_GEMM_PAIR (bit mask, default 51; 0 = off)
+ * selects the GEMM kinds; qv_gemm_pair_launches() counts them.  DESIGN.md section 3. */
 int qv_gemm_bf16(const qv_gemm_args* args, void* stream);
 
 /* out[M,N] (+)= sum_z workspace[z][M][N] * (row_rscale ? 1/row_rscale[m] : 1) * (alpha ? *alpha : 1)
