@@ -22,20 +22,35 @@ def main():
     torch.manual_seed(0)
     a = torch.randn(M, K, device=dev)
     b = torch.randint(-128, 128, (N, K), device=dev).float() if pb == 1 else torch.randn(N, K, device=dev)
-    ap = ops.split_planes(a) if pa == 2 else a.bfloat16()[None].contiguous()
-    bp = ops.split_planes(b) if pb == 2 else b.bfloat16()[None].contiguous()
+    mix = os.environ.get("QV_TL_MIX", "0") != "0"           # teacher format: fp16 + fp8 planes (QV_GEMM_PAIR picks pairs / tile width)
+    planes_out = os.environ.get("QV_TL_PLANES", "0") != "0"  # plane-output epilogue (+ GELU, mixed planes) instead of fp32
+    if mix:
+        b = b * 0.02
+        ap, bp = ops.split_planes_mix(a), ops.split_planes_mix(b, weight=True)
+    else:
+        ap = ops.split_planes(a) if pa == 2 else a.bfloat16()[None].contiguous()
+        bp = ops.split_planes(b) if pb == 2 else b.bfloat16()[None].contiguous()
     cs = torch.rand(N, device=dev) + 0.5
     bias = torch.randn(N, device=dev)
     mm = ops.new_minmax(dev)
     out = torch.empty(M, N, device=dev)
+    outp = torch.empty(2, M, N, dtype=torch.bfloat16, device=dev) if planes_out else None
     L = _lib.lib()
+
+    def run():
+        if mix and planes_out:
+            ops.gemm(Op.full(ap), Op.full(bp), M, N, K, (2, 2), bias=bias, out_planes=outp, gelu=True, mix=True, out_mix=True)
+        elif mix:
+            ops.gemm(Op.full(ap), Op.full(bp), M, N, K, (2, 2), out=out, bias=bias, mix=True)
+        else:
+            ops.gemm(Op.full(ap), Op.full(bp), M, N, K, (pa, pb), out=out, col_scale=cs, bias=bias, minmax=mm)
     for _ in range(3):
-        ops.gemm(Op.full(ap), Op.full(bp), M, N, K, (pa, pb), out=out, col_scale=cs, bias=bias, minmax=mm)
+        run()
     torch.cuda.synchronize()
     L.qv_gemm_debug_clear()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
-    ops.gemm(Op.full(ap), Op.full(bp), M, N, K, (pa, pb), out=out, col_scale=cs, bias=bias, minmax=mm)
+    run()
     e.record()
     torch.cuda.synchronize()
     print(f"kernel {s.elapsed_time(e) * 1e3:.1f} us")
@@ -62,6 +77,7 @@ def main():
             if tag == b_ and a_ in open_:
                 waits[TAGS[a_]] = waits.get(TAGS[a_], 0) + (t - open_.pop(a_))
     total = ev[-1][0] - t0
+    print(f"pair launches so far: {ops.gemm_pair_launches()}")
     print(f"CTA 0 timeline: {total / 1.9e3:.1f} us, {sum(1 for x in ev if x[1] == 21)} tiles")
     for k, v in waits.items():
         print(f"  {k:24s} {v / 1.9e3:8.1f} us  ({100.0 * v / total:5.1f} %)")
