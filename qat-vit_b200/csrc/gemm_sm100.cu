@@ -44,10 +44,8 @@ constexpr int epi_terms_bytes(int epi) { return epi >= 1 ? 0 : 8 * 2 * 32 * 4; }
 constexpr int SMEM_LIMIT = 232448;             // 227 KB
 #ifndef QV_GEMM_PAIR_DEFAULT
 // bit 0: mixed-format (teacher) GEMMs with fp32 output, bit 4: ... with plane output, bit 1: (2,2) bf16 hi/lo plane GEMMs,
-// bit 2: gradient-planes dgrad, bit 3: (2,1) GEMMs, bit 5: 256-wide tiles for the mixed-format pairs, bit 6 (only in the
-// `make prefetch` build, -DQV_GEMM_L2_PREFETCH; not yet measured): the producer prefetches the A tiles 6 k-blocks ahead into L2 -- the
-// timeline of a pair GEMM shows the MMA thread waiting 21 % of the time on `full` barriers while the producer waits 13 % on `empty` ones:
-// latency, A is a first-touch DRAM read.
+// bit 2: gradient-planes dgrad, bit 3: (2,1) GEMMs, bit 5: 256-wide tiles for the mixed-format pairs.  (Tried and dropped: the producer prefetching
+// the A tiles 6 k-blocks ahead into L2 with cp.async.bulk.prefetch.tensor -- isolated qkv 280 -> 305 us, fc2 353 -> 376 us.)
 // The (2,1) student GEMMs are MMA-bound with one CTA per tile already (56 KB per k-block against 8 MMAs) and gain nothing.
 #define QV_GEMM_PAIR_DEFAULT 51
 #endif
@@ -82,11 +80,6 @@ struct GemmKParams {
   const int64_t* obs_enabled; const int64_t* obs_fq_enabled;
   float obs_c; int32_t obs_qmin, obs_qmax, obs_symmetric;
   uint32_t* obs_ticket;
-#ifdef QV_GEMM_L2_PREFETCH   // experimental build (make prefetch), not yet measured
-  // CTA pairs: the producer prefetches the A tile of the k-block `l2_ahead` steps ahead of the one it loads into L2 (0 = off):
-  // activations are first-touch DRAM reads, and 5 stages of 32 KB cover an L2 hit, not a DRAM miss
-  int32_t l2_ahead;
-#endif
 };
 
 // SPLIT (mixed-format CTA pairs): one pipeline stage holds ONE region of a k-block -- the fp16 planes of A and B, or their fp8
@@ -210,19 +203,6 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #ifdef QV_ATTN_DEBUG
       int gdbg_n = 0;
 #endif
-#ifdef QV_GEMM_L2_PREFETCH
-      // rolling L2 prefetch cursor (pairs: unsplit, unbatched), `l2_ahead` k-blocks ahead of the load cursor
-      int pf_item = item0, pf_kb = 0;
-      auto prefetch_step = [&]() {
-        if (pf_item >= num_items) return;
-#pragma unroll
-        for (int pa = 0; pa < NA; ++pa) tma_prefetch_l2_4d(&map_a, p.a_col0 + pf_kb * BK, m_of(pf_item) * BM, 0, pa);
-        if (++pf_kb == p.kblocks) { pf_kb = 0; pf_item += item_step; }
-      };
-      if constexpr (CG == 2) {
-        for (int i = 0; i < p.l2_ahead; ++i) prefetch_step();
-      }
-#endif
       for (int item = item0; item < num_items; item += item_step) {
         const int n_blk = item % p.tiles_n;
         const int m_blk = m_of(item);
@@ -240,11 +220,6 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           GDBG(0, 2);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + NA * A_PLANE_BYTES;
-#ifdef QV_GEMM_L2_PREFETCH
-          if constexpr (CG == 2) {
-            if (p.l2_ahead > 0) prefetch_step();
-          }
-#endif
           if constexpr (SPLIT) {
             // region r of this k-block -> its own stage: [A region r: 128 rows][B region r: BN / 2 rows]
 #pragma unroll
@@ -1000,9 +975,6 @@ extern "C" int qv_gemm_bf16(const qv_gemm_args* a, void* stream) {
   kp.act = a->act;
   kp.acc_scale = mix ? QV_MIX_ACC_SCALE : 1.0f;
   kp.out_fmt = a->out_kind == 2 ? 1 : 0;
-#ifdef QV_GEMM_L2_PREFETCH
-  kp.l2_ahead = (pair && (pair_mode() & 64) != 0) ? 6 : 0;       // bit 6: rolling L2 prefetch of A
-#endif
   kp.ep_raw = a->ep_raw; kp.ep_raw_ld = a->ep_raw_ld; kp.ep_scale = a->ep_scale; kp.ep_zp = a->ep_zp;
   kp.ep_qmin = a->ep_qmin; kp.ep_qmax = a->ep_qmax; kp.ep_gelu = a->ep_gelu; kp.ep_colsum = a->ep_colsum;
   if (a->obs_ticket) {
