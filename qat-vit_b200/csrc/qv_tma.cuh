@@ -53,7 +53,9 @@ inline int make_map(CUtensorMap* m, const qv_operand& op, int planes, int box_ro
 
 
 // fp32 output [nb][rows][ld] as a 3-D tensor (cols, rows, nb); store box = (32 cols = 128 B, 32 rows, 1), 128B swizzle.
-inline int make_out_map(CUtensorMap* m, float* ptr, int64_t cols, int64_t rows, int64_t ld, int64_t nb, int64_t bstride) {
+// box_cols = 16: 64-byte rows, 64B swizzle (the slim fp32 epilogue of the experimental QV_GEMM_SLIM_EPI build stores 16-column halves)
+inline int make_out_map(CUtensorMap* m, float* ptr, int64_t cols, int64_t rows, int64_t ld, int64_t nb, int64_t bstride,
+                        int box_cols = 32) {
   EncodeTiledFn enc = get_encode();
   QV_REQUIRE(enc != nullptr, QV_ERR_CUDA, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
   QV_REQUIRE(ptr && qv_aligned16(ptr), QV_ERR_INVALID, "gemm output base must be a 16-byte aligned device pointer");
@@ -64,10 +66,11 @@ inline int make_out_map(CUtensorMap* m, float* ptr, int64_t cols, int64_t rows, 
   QV_REQUIRE(bstride % 4 == 0, QV_ERR_INVALID, "gemm output batch stride must be a multiple of 4 floats");
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(nb)};
   cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 4, static_cast<cuuint64_t>(bstride) * 4};
-  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(box_cols), 32, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   box_cols == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   QV_REQUIRE(r == CUDA_SUCCESS, QV_ERR_CUDA, "cuTensorMapEncodeTiled(output) failed (%d)", (int)r);
   return 0;
 }
