@@ -39,14 +39,7 @@ constexpr int A_PLANE_BYTES = BM * BK * 2;
 // epilogue staging per warp: 32-row x 128-byte buffers.  fp32 output: one buffer per 32-column chunk; bf16 hi/lo plane
 // output: a hi and a lo buffer per 64-column chunk.  Two warps alternate on each TMEM lane quarter, so per-warp single
 // buffering already overlaps one warp's TMA store with the other's math.
-#ifdef QV_GEMM_SLIM_EPI
-// EXPERIMENTAL build (make slim; not yet run on a GPU): half-size epilogue staging so that the CTA-pair kernels get a SIXTH 32 KB stage
-// in flight (their stage round trip, not bandwidth, bounds them: DESIGN.md section 7).  fp32 output: two 16-column halves through one
-// 2 KB buffer; plane output: the hi plane, then -- from registers -- the lo plane through one 4 KB buffer.  Same values, same bits.
-constexpr int epi_warp_bytes(int epi) { return epi == 2 ? 3 * 4096 : epi == 1 ? 4096 : 2048; }
-#else
 constexpr int epi_warp_bytes(int epi) { return (epi == 2 ? 3 : epi == 1 ? 2 : 1) * 32 * 128; }   // EPI 2: y tile x2 + planes
-#endif
 constexpr int epi_terms_bytes(int epi) { return epi >= 1 ? 0 : 8 * 2 * 32 * 4; }   // per-warp [mult][bias] column terms
 constexpr int SMEM_LIMIT = 232448;             // 227 KB
 #ifndef QV_GEMM_PAIR_DEFAULT
@@ -647,11 +640,7 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         if constexpr (EPI == 0) {
           const int ncols = static_cast<int>(min(static_cast<int64_t>(32), p.N - n0));   // valid columns of this chunk
-#ifdef QV_GEMM_SLIM_EPI
-          const uint32_t srow = smem_u32(my_epi) + lane * 64;
-#else
           const uint32_t srow = smem_u32(my_epi) + lane * 128;
-#endif
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float4 v = make_float4(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1]), __uint_as_float(rr[4 * j + 2]),
@@ -670,28 +659,6 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 mx = fmaxf(mx, fmaxf(fmaxf(hi0, hi1), fmaxf(hi2, hi3)));
               }
             }
-#ifdef QV_GEMM_SLIM_EPI
-            // 64B-swizzled 2 KB staging, one 16-column half at a time: 16-byte chunk c of row `lane` lives at chunk c ^ ((lane >> 1) & 3)
-            if (j == 4) {                                         // first half is staged: store it, then reuse the buffer
-              fence_proxy_async_smem();
-              __syncwarp();
-              if (lane == 0) {
-                tma_store_3d(&map_o, my_epi, o_col + static_cast<int>(n0), row0, o_c2);
-                tma_store_commit();
-                tma_store_wait_read<0>();
-              }
-              __syncwarp();
-            }
-            const uint32_t addr = srow + (static_cast<uint32_t>((j & 3) ^ ((lane >> 1) & 3)) << 4);
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            if (n0 + 16 < p.N) tma_store_3d(&map_o, my_epi, o_col + static_cast<int>(n0) + 16, row0, o_c2);
-            tma_store_commit();
-          }
-#else
             // 128B-swizzled staging: 16-byte chunk j of row `lane` lives at chunk (j ^ (lane & 7))
             const uint32_t addr = srow + (static_cast<uint32_t>(j ^ (lane & 7)) << 4);
             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
@@ -702,15 +669,9 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tma_store_3d(&map_o, my_epi, o_col + static_cast<int>(n0), row0, o_c2);
             tma_store_commit();
           }
-#endif
         } else {
           // bf16 hi/lo plane output: 64 columns -> one 32-row x 128-byte hi box and one lo box
-#ifdef QV_GEMM_SLIM_EPI
-          const uint32_t srow_hi = smem_u32(my_epi) + lane * 128, srow_lo = srow_hi;   // one buffer: hi plane first, then lo
-          uint32_t keep[32];                                                            // the lo plane's words wait in registers
-#else
           const uint32_t srow_hi = smem_u32(my_epi) + lane * 128, srow_lo = srow_hi + 4096;
-#endif
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             // plane output takes bias only (checked on the host); every lane reads the same 32 bytes: broadcast LDG.128
@@ -738,14 +699,10 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               const uint32_t swz = static_cast<uint32_t>(lane & 7);
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow_hi + ((static_cast<uint32_t>(j) ^ swz) << 4)),
                            "r"(h16[0]), "r"(h16[1]), "r"(h16[2]), "r"(h16[3]) : "memory");
-#ifdef QV_GEMM_SLIM_EPI
-              keep[4 * j] = h8[0]; keep[4 * j + 1] = h8[1]; keep[4 * j + 2] = l8[0]; keep[4 * j + 3] = l8[1];
-#else
               // region 1 row: bytes [0, 64) = hi8 of the 64 columns, [64, 128) = lo8; 8 columns = 8 bytes at 8 j
               const uint32_t c8 = static_cast<uint32_t>(j >> 1), o8 = static_cast<uint32_t>(j & 1) << 3;
               asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(srow_lo + ((c8 ^ swz) << 4) + o8), "r"(h8[0]), "r"(h8[1]) : "memory");
               asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(srow_lo + (((c8 + 4u) ^ swz) << 4) + o8), "r"(l8[0]), "r"(l8[1]) : "memory");
-#endif
               continue;
             }
             uint32_t hi[4], lo[4];
@@ -764,48 +721,16 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint32_t sw = (static_cast<uint32_t>(j ^ (lane & 7)) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow_hi + sw), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]),
                          "r"(hi[3]) : "memory");
-#ifdef QV_GEMM_SLIM_EPI
-            keep[4 * j] = lo[0]; keep[4 * j + 1] = lo[1]; keep[4 * j + 2] = lo[2]; keep[4 * j + 3] = lo[3];
-#else
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow_lo + sw), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]),
                          "r"(lo[3]) : "memory");
-#endif
           }
           fence_proxy_async_smem();
           __syncwarp();
-#ifdef QV_GEMM_SLIM_EPI
-          if (lane == 0) {
-            tma_store_4d(&map_o, my_epi, o_col + static_cast<int>(n0), row0, o_c2, 0);      // hi plane / region 0
-            tma_store_commit();
-            tma_store_wait_read<0>();                                                         // ... has left the buffer
-          }
-          __syncwarp();
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (p.out_fmt == 1) {
-              const uint32_t swz = static_cast<uint32_t>(lane & 7);
-              const uint32_t c8 = static_cast<uint32_t>(j >> 1), o8 = static_cast<uint32_t>(j & 1) << 3;
-              asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(srow_lo + ((c8 ^ swz) << 4) + o8), "r"(keep[4 * j]), "r"(keep[4 * j + 1]) : "memory");
-              asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(srow_lo + (((c8 + 4u) ^ swz) << 4) + o8), "r"(keep[4 * j + 2]), "r"(keep[4 * j + 3]) : "memory");
-            } else {
-              const uint32_t sw = (static_cast<uint32_t>(j ^ (lane & 7)) << 4);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow_lo + sw), "r"(keep[4 * j]), "r"(keep[4 * j + 1]),
-                           "r"(keep[4 * j + 2]), "r"(keep[4 * j + 3]) : "memory");
-            }
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_4d(&map_o, my_epi, o_col + static_cast<int>(n0), row0, o_c2, 1);      // lo plane / region 1
-            tma_store_commit();
-          }
-#else
           if (lane == 0) {
             tma_store_4d(&map_o, my_epi, o_col + static_cast<int>(n0), row0, o_c2, 0);
             tma_store_4d(&map_o, my_epi + 4096, o_col + static_cast<int>(n0), row0, o_c2, 1);
             tma_store_commit();
           }
-#endif
         }
       }
     }
@@ -1005,11 +930,7 @@ extern "C" int qv_gemm_bf16(const qv_gemm_args* a, void* stream) {
   if (splits > 1) {
     QV_REQUIRE(a->workspace != nullptr, QV_ERR_INVALID, "split-K needs a workspace");
     QV_REQUIRE(a->N % 4 == 0, QV_ERR_UNSUPPORTED, "split-K needs N to be a multiple of 4");
-#ifdef QV_GEMM_SLIM_EPI
-    rc = make_out_map(&mo, a->workspace, a->N, a->M, a->N, splits, a->M * a->N, 16);
-#else
     rc = make_out_map(&mo, a->workspace, a->N, a->M, a->N, splits, a->M * a->N);
-#endif
   } else {
     const qv_out& o = a->out;
     QV_REQUIRE(o.ptr != nullptr, QV_ERR_INVALID, "null output");
@@ -1024,11 +945,7 @@ extern "C" int qv_gemm_bf16(const qv_gemm_args* a, void* stream) {
     } else if (planes_out)
       rc = make_out_planes_map(&mo, o.ptr, o.cols, o.rows, o.ld, o.nb, o.batch_stride, a->out_plane_stride);
     else
-#ifdef QV_GEMM_SLIM_EPI
-      rc = make_out_map(&mo, o.ptr, o.cols, o.rows, o.ld, o.nb, o.batch_stride, 16);
-#else
       rc = make_out_map(&mo, o.ptr, o.cols, o.rows, o.ld, o.nb, o.batch_stride);
-#endif
   }
   if (rc) return rc;
 

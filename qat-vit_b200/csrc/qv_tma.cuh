@@ -53,7 +53,7 @@ inline int make_map(CUtensorMap* m, const qv_operand& op, int planes, int box_ro
 
 
 // fp32 output [nb][rows][ld] as a 3-D tensor (cols, rows, nb); store box = (32 cols = 128 B, 32 rows, 1), 128B swizzle.
-// box_cols = 16: 64-byte rows, 64B swizzle (the slim fp32 epilogue of the experimental QV_GEMM_SLIM_EPI build stores 16-column halves)
+// box_cols = 16: 64-byte rows, 64B swizzle
 inline int make_out_map(CUtensorMap* m, float* ptr, int64_t cols, int64_t rows, int64_t ld, int64_t nb, int64_t bstride,
                         int box_cols = 32) {
   EncodeTiledFn enc = get_encode();
