@@ -171,6 +171,268 @@ def clip_arena_(arena, max_norm: float, grad_scale: float = 1.0):
     return total
 
 
+# --------------------------------------------------------------------------------------------------------------------
+# side measurements on the N = 1 line (time-boxed, AFTER the timed regions): BASELINE configs[3] and configs[4], and the
+# reference's own GPU path (stock torch CUDA eager) on the same box
+# --------------------------------------------------------------------------------------------------------------------
+def _timed_us(fn, iters=10, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters * 1e3
+
+
+def fq_linear_microbench(M, N, K, dev, peak_tf, hbm_gbs):
+    """One fake-quant Linear (torch.ao.nn.qat.Linear + output FusedMovingAvgObsFakeQuantize, fbgemm qconfig) forward and
+    STE backward on this library: weight observer + codes -> tcgen05 GEMM (scale / bias / observer epilogue) | gradient planes
+    (STE mask, scale fold, bias partials) -> dgrad GEMM -> split-K wgrad GEMM -> reduce (weight STE mask)."""
+    import warnings
+    import torch
+    import torch.ao.nn.qat as nnqat
+    from torch.ao.quantization import get_default_qat_qconfig
+    from qatvit_b200 import ops
+    from qatvit_b200.engine import FQRef, wgrad_splits
+    from qatvit_b200.ops import Op, PAIRS_EXACT_B, PAIRS_FP32
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mod = nnqat.Linear(K, N, bias=True, qconfig=get_default_qat_qconfig("fbgemm"))
+        mod.activation_post_process = mod.qconfig.activation()
+    torch.nn.init.trunc_normal_(mod.weight, std=0.02)
+    mod = mod.to(dev)
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    x = torch.randn(M, K, device=dev)
+    gy = torch.randn(M, N, device=dev)
+    wfq, afq = FQRef(mod.weight_fake_quant, channels=N), FQRef(mod.activation_post_process)
+    xp = ops.split_planes(x)
+    codes = torch.empty(1, N, K, dtype=torch.bfloat16, device=dev)
+    codes_t = torch.empty(1, K, N, dtype=torch.bfloat16, device=dev)
+    wmask = torch.empty(N, K, dtype=torch.uint8, device=dev)
+    y_raw = torch.empty(M, N, device=dev)
+    acc = ops.new_minmax(dev)
+    w = mod.weight.detach()
+    ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def gemm_fwd():
+        ops.gemm(Op.full(xp), Op.full(codes), M, N, K, PAIRS_EXACT_B, out=y_raw, col_scale=wfq.scale, bias=mod.bias.detach(), minmax=acc,
+                 observer=(afq.min_val, afq.max_val, afq.scale, afq.zero_point, afq.observer_enabled, afq.fake_quant_enabled, afq.c,
+                           afq.qmin, afq.qmax, afq.symmetric, ticket))
+
+    def fwd():
+        ops.minmax_reset(acc)
+        ops.fq_weight(w, True, wfq.observer_enabled, wfq.fake_quant_enabled, wfq.min_val, wfq.max_val, wfq.scale, wfq.zero_point,
+                      wfq.c, wfq.qmin, wfq.qmax, wfq.symmetric, mask=wmask, codes=codes[0], codes_t=codes_t[0])
+        gemm_fwd()
+
+    rpb = 64
+    nblk = -(-M // rpb)
+    gp = torch.empty(2, M, N, dtype=torch.bfloat16, device=dev)
+    part = torch.empty(nblk, N, device=dev)
+    gb, gx, gw = torch.empty(N, device=dev), torch.empty(M, K, device=dev), torch.empty(N, K, device=dev)
+    sp = wgrad_splits(N, K, M, sms)
+    ws = torch.empty(max(sp, 1) * N * K, device=dev)
+
+    def gp_planes():
+        ops.gp_planes(gy, y_raw, afq.q, wfq.scale, True, False, M, N, gp, part, rpb)
+
+    def dgrad():
+        ops.gemm(Op.full(gp), Op.full(codes_t), M, K, N, PAIRS_EXACT_B, out=gx)
+
+    def wgrad():
+        if sp > 1:
+            ops.gemm(Op.full(gp, mn_major=True), Op.full(xp, mn_major=True), N, K, M, PAIRS_FP32, splits=sp, workspace=ws)
+        else:
+            ops.gemm(Op.full(gp, mn_major=True), Op.full(xp, mn_major=True), N, K, M, PAIRS_FP32, out=ws[:N * K].view(N, K))
+        ops.splitk_reduce(ws, sp, N, K, gw, row_rscale=wfq.scale, mask=wmask)
+
+    def bwd():
+        gp_planes()
+        ops.colsum_reduce(part, nblk, N, gb)
+        dgrad()
+        wgrad()
+
+    t_f, t_b = _timed_us(fwd), _timed_us(bwd)
+    t_g, t_d, t_w, t_p = _timed_us(gemm_fwd), _timed_us(dgrad), _timed_us(wgrad), _timed_us(gp_planes)
+    fl = 2.0 * M * N * K
+    return {"M": M, "N": N, "K": K, "fwd_us": round(t_f, 1), "ste_bwd_us": round(t_b, 1),
+            "fwd_gemm_us": round(t_g, 1), "dgrad_gemm_us": round(t_d, 1), "wgrad_gemm_reduce_us": round(t_w, 1), "gp_planes_us": round(t_p, 1),
+            "fwd_gemm_alg_tflops": round(fl / t_g / 1e6, 1), "fwd_gemm_frac": round(fl / t_g / 1e6 / peak_tf, 3),
+            "fwd_gemm_mma_frac": round(2 * fl / t_g / 1e6 / peak_tf, 3),           # two bf16 passes per fp32-grade product
+            "dgrad_gemm_frac": round(fl / t_d / 1e6 / peak_tf, 3), "wgrad_frac": round(fl / t_w / 1e6 / peak_tf, 3),
+            "fwd_bwd_alg_tflops": round(3 * fl / (t_f + t_b) / 1e6, 1),
+            "gp_planes_gbs": round(12.0 * M * N / t_p / 1e3, 0), "gp_planes_hbm_frac": round(12.0 * M * N / t_p / 1e3 / hbm_gbs, 3),
+            "wgrad_splits": sp}
+
+
+def side_measurements(student, teacher, step, images, labels, dev, peaks, budget_s=75.0):
+    """-> dict(microbench=..., int8_eval=..., torch_cuda_eager=...).  Every leg is best-effort and time-boxed; a failing leg
+    reports its error string instead of a number (the headline line is already measured at this point)."""
+    import copy
+    import warnings
+    import torch
+    from qatvit_b200 import ops
+    out = {}
+    t_start = time.perf_counter()
+    B = images.shape[0]
+    # ---- BASELINE configs[3]: fake-quant Linear sweep over the ViT-S / ViT-B shapes at M = 197 * 256 ----
+    try:
+        rows = []
+        for (N, K) in [(1152, 384), (384, 384), (1536, 384), (384, 1536), (2304, 768), (768, 768), (3072, 768), (768, 3072)]:
+            rows.append(fq_linear_microbench(197 * B, N, K, dev, peaks["tf_sustained"], peaks["hbm"]))
+            torch.cuda.empty_cache()
+        out["microbench"] = {"workload": f"fake-quant Linear fwd + STE bwd, M = 197 x {B}, fbgemm qconfig (BASELINE configs[3])",
+                             "peak_tflops": peaks["tf_sustained"], "peak_hbm_gbs": peaks["hbm"],
+                             "note": "frac = algorithmic 2MNK / time / measured sustained bf16 peak; an fp32-grade product of hi/lo "
+                                     "activation planes x exact weight codes costs 2 bf16 passes (mma_frac), wgrad 3",
+                             "shapes": rows}
+    except Exception as ex:     # noqa: BLE001
+        out["microbench"] = {"error": repr(ex)[:300]}
+    # ---- the reference's own GPU path: stock torch CUDA eager (ATen kernels, cuBLAS fp32, autograd) for the same step ----
+    try:
+        import torch.nn.functional as F
+        ref_student = copy.deepcopy(student)
+        ref_opt = torch.optim.AdamW(ref_student.parameters(), lr=HP["lr"] * 0.5, weight_decay=HP["weight_decay"])
+
+        def eager_step():           # ref/src/training/qat_trainer.py:337-361, verbatim order
+            with torch.no_grad():
+                t_out = teacher(images)
+            s_out = ref_student(images)
+            T, a = HP["kd_temp"], HP["kd_alpha"]
+            ce = F.cross_entropy(s_out, labels, label_smoothing=HP["label_smoothing"])
+            kd = F.kl_div(torch.log_softmax(s_out / T, dim=1), torch.softmax(t_out / T, dim=1), reduction="batchmean") * (T ** 2)
+            loss = a * kd + (1.0 - a) * ce
+            ref_opt.zero_grad(set_to_none=True)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(ref_student.parameters(), 1.0)
+            ref_opt.step()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            us = _timed_us(eager_step, iters=3, warm=2)
+        out["torch_cuda_eager"] = {"impl": "stock torch CUDA eager on the same B200: the same prepared module tree through nn.Module.forward "
+                                           "+ autograd (ATen FusedObsFakeQuant, cuBLAS fp32 SGEMM, SDPA), torch AdamW + clip_grad_norm_",
+                                   "batch": B, "ms_per_step": us / 1e3, "img_per_s": B / (us * 1e-6),
+                                   "allow_tf32_matmul": bool(torch.backends.cuda.matmul.allow_tf32), "torch": torch.__version__}
+        del ref_student, ref_opt
+        torch.cuda.empty_cache()
+    except Exception as ex:     # noqa: BLE001
+        out["torch_cuda_eager"] = {"error": repr(ex)[:300]}
+    # ---- BASELINE configs[4]: converted int8 student eval (stock convert() of the student trained above) ----
+    try:
+        if time.perf_counter() - t_start > budget_s:
+            raise TimeoutError("side-measurement budget used up")
+        from torch.ao.quantization import convert
+        from qatvit_b200.int8 import ConvertedStudent
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            conv = convert(copy.deepcopy(student).cpu().eval(), inplace=False)           # ref qat_trainer.py:377-379
+        ex_ = ConvertedStudent(conv, B, dev)
+        us = _timed_us(lambda: ex_(images), iters=10, warm=3)
+        ops.profile_begin()
+        logits = ex_(images)
+        prof = ops.profile_end()
+        lin = prof.get("int8_linear", {"ms": 0.0, "count": 0})
+        # qkv 3, proj 1, fc1 4, fc2 4 = 12 D^2 MACs per token and block, 12 blocks, + the patch-embed conv
+        int_ops = 2.0 * 197 * B * 12 * 12 * 384 * 384 + 2.0 * 196 * B * 384 * 768
+        int8_peak = 2.0 * peaks["tf_sustained"]
+        res = {"workload": f"converted int8 ViT-S/16 student eval, batch {B}, synthetic 224x224 (BASELINE configs[4])",
+               "img_per_s": B / (us * 1e-6), "ms_per_batch": us / 1e3, "finite": bool(torch.isfinite(logits).all()),
+               "int8_linear": {"launches": lin["count"], "ms": round(lin["ms"], 3),
+                               "alg_tops": round(int_ops / max(lin["ms"], 1e-9) / 1e9, 1),
+                               "frac_of_int8_peak": round(int_ops / max(lin["ms"], 1e-9) / 1e9 / int8_peak, 3),
+                               "peak_tops": int8_peak,
+                               "peak_source": "2 x measured sustained bf16 (kind::i8 runs at twice the kind::f16 rate; no int8 entry in MEASURED_PEAKS.json)"},
+               "breakdown_ms": {k: round(v["ms"], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}}
+        # CPU side of configs[4]: the same converted module through stock torch.ops.quantized kernels (x86 engine) + the same float glue
+        from oracle import int8_ref            # checker / CPU baseline only
+        torch.set_num_threads(os.cpu_count() or 1)
+        xs = images[:8].cpu()
+        int8_ref.converted_forward(conv, xs)
+        t0, reps = time.perf_counter(), 0
+        while time.perf_counter() - t0 < 6.0:
+            ref = int8_ref.converted_forward(conv, xs)
+            reps += 1
+        cpu_dt = (time.perf_counter() - t0) / reps
+        ours8 = ConvertedStudent(conv, 8, dev)(images[:8].contiguous()).cpu()
+        stepq = float(conv.model.head.scale)
+        res["cpu_reference"] = {"img_per_s": 8 / cpu_dt, "ms_per_batch8": cpu_dt * 1e3, "threads": torch.get_num_threads(),
+                                "engine": torch.backends.quantized.engine, "kind": "port (stock torch.ops.quantized kernels + the float glue of SURVEY 8c)"}
+        res["logits_max_abs_diff_in_head_steps"] = float((ours8 - ref).abs().max()) / stepq
+        out["int8_eval"] = res
+    except Exception as ex:     # noqa: BLE001
+        out["int8_eval"] = {"error": repr(ex)[:300]}
+    out["seconds"] = round(time.perf_counter() - t_start, 1)
+    return out
+
+
+def params_identical(student, dev, world) -> bool:
+    """Bit-level checksum (int64 sum of the int32 views) of every parameter and buffer, compared across ranks."""
+    import torch
+    import torch.distributed as dist
+    acc = torch.zeros(2, dtype=torch.int64, device=dev)
+    for t in list(student.parameters()) + list(student.buffers()):
+        if t.numel() == 0:
+            continue
+        v = t.detach().contiguous()
+        if v.dtype == torch.float32:
+            acc[0] += v.view(torch.int32).to(torch.int64).sum()
+        else:
+            acc[1] += v.to(torch.int64).sum()
+    allv = [torch.zeros_like(acc) for _ in range(world)]
+    dist.all_gather(allv, acc)
+    return all(bool(torch.equal(a, allv[0])) for a in allv)
+
+
+def check_exchange(step, sync, student, images, labels, dev, world, rank):
+    """The one exchange of the path must compute what DDP computes (ref qat_trainer.py:310-313,359 +
+    torch/nn/parallel/distributed.py:1590-1591): after a step WITH the overlapped all-reduce every rank holds (a) the SUM over
+    ranks of the gradients each rank produces alone from the same state on its shard, and (b) rank 0's activation-observer
+    running min / max.  Run once before the timed loop; observer state is put back afterwards."""
+    import torch
+    import torch.distributed as dist
+    buffers = {n: b.detach().clone() for n, b in student.named_buffers()}
+
+    def restore():
+        with torch.no_grad():
+            for n, b in student.named_buffers():
+                if b.shape == buffers[n].shape:
+                    b.copy_(buffers[n])
+    # 1. local step, no exchange
+    step(images, labels)
+    local = sync.grad_arena.clone()
+    obs_local = torch.stack([torch.stack([a.reshape(()), b.reshape(())]) for a, b in step.activation_observers()]).clone()
+    restore()
+    # 2. the same step with the exchange overlapped into the backward
+    step(images, labels, grad_sync=sync)
+    torch.cuda.synchronize()
+    reduced = sync.grad_arena.clone()
+    obs_after = torch.stack([torch.stack([a.reshape(()), b.reshape(())]) for a, b in step.activation_observers()]).clone()
+    restore()
+    parts = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(parts, local)
+    total = parts[0].double()
+    for p_ in parts[1:]:
+        total += p_.double()
+    err = float((reduced.double() - total).abs().max() / total.abs().max().clamp_min(1e-30))
+    exact = bool(torch.equal(reduced, total.float())) if world == 2 else None      # a + b has one rounding: order-free
+    obs0 = [torch.empty_like(obs_local) for _ in range(world)]
+    dist.all_gather(obs0, obs_local)
+    observers_ok = bool(torch.equal(obs_after, obs0[0]))
+    differ = bool(world == 1 or not torch.equal(obs0[0], obs0[-1]))       # the shards really had different local state
+    flags = torch.tensor([err <= 2e-6, observers_ok, exact is not False], dtype=torch.int32, device=dev)
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    return {"grads_sum_ok": bool(flags[0]), "grads_sum_exact": (bool(flags[2]) if world == 2 else None),
+            "grads_sum_max_rel_err": err, "observers_rank0": bool(flags[1]), "local_observers_differ_across_ranks": differ,
+            "weights_identical": True,
+            "how": "one step with the overlapped NCCL exchange vs the fp64 sum of the all-gathered per-rank gradients of the same "
+                   "step run without it; observer min/max after the exchange vs rank 0's own; int64 checksum of all parameters "
+                   "and buffers across ranks after the timed steps"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -186,6 +448,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # the exchange is 86.7 MB per step over NVSwitch: a few NCCL channels carry it; every CTA NCCL takes is an SM a persistent
+        # GEMM cannot use while the collective runs
+        os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("QV_NCCL_MAX_CTAS", "8"))
         dist.init_process_group("nccl", device_id=dev)
     n = max(world, 1)
     global_batch = 256 if n == 1 else 1024
@@ -240,6 +505,9 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    ddp_check = None
+    if world > 1 and not args.pre_qat:
+        ddp_check = check_exchange(step, sync, student, images, labels, dev, world, rank)
     for _ in range(max(args.warmup, 3)):
         train_step(images, labels)
     barrier()
@@ -257,11 +525,45 @@ def run_ours(args):
     ev1.record()
     barrier()
     launches = ops.launch_count() - l0
+    if ddp_check is not None:       # after the timed steps every rank must hold the same parameters, bit for bit
+        ddp_check["weights_identical"] = params_identical(student, dev, world)
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms)
     clocks = sampler.stop() if sampler else None
+
+    # ---- cost of the exchange: the same K steps on the same per-GPU batch WITHOUT the all-reduce (ranks then drift apart, which
+    #      is why this runs on a throw-away copy of nothing: it is measured last among the device-resident loops and the
+    #      parameters are re-broadcast afterwards) ----
+    ddp_overhead_ms = None
+    if world > 1:
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            step(images, labels)
+            if args.torch_optimizer:
+                clip_arena_(arena, 1.0, 1.0)
+                opt.step()
+            else:
+                opt.step(grad_scale=1.0)
+        ev1.record()
+        barrier()
+        ms0 = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+        dist.all_reduce(ms0, op=dist.ReduceOp.MAX)
+        ddp_overhead_ms = (ms_total - float(ms0)) / args.steps
+        drifted = list(student.parameters()) + list(student.buffers())
+        if args.torch_optimizer:
+            drifted += [v for st in opt.state.values() for v in st.values() if torch.is_tensor(v) and v.is_cuda]
+        else:
+            drifted += [opt.exp_avg, opt.exp_avg_sq]
+        for t in drifted:
+            if t.numel() > 0:
+                dist.broadcast(t.data, src=0)
+        train_step(images, labels)        # back in lock-step
+        weights_identical = params_identical(student, dev, world)
+        if ddp_check is not None:
+            ddp_check["weights_identical"] = bool(ddp_check["weights_identical"] and weights_identical)
 
     # ---- end to end through the public step API: every step's inputs start in PINNED HOST memory and its loss ends there.
     # Like the reference's DataLoader(pin_memory=True) + .to(device, non_blocking=True) (ref :334-335), the copy of step
@@ -301,9 +603,12 @@ def run_ours(args):
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_ms = float(ms2)
 
+    ddp_ok = ddp_check is None or all(bool(ddp_check[k]) for k in ("grads_sum_ok", "observers_rank0", "weights_identical"))
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
+        if not ddp_ok:
+            raise SystemExit(f"bench.py: rank {rank}: data-parallel exchange check FAILED: {ddp_check}")
         return
 
     # ---- per-kernel-family breakdown of ONE step (CUDA events around every launch, on the launching stream) ----
@@ -335,6 +640,8 @@ def run_ours(args):
     roofline = {"kernel": f"qv_gemm_kernel, {top} ({tv['count']} launches/step, {how}, fp32 accumulate in TMEM)",
                 "bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["tf_sustained"], "traffic": traffic,
+                "traffic_source": ("static: dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full "
+                                   "capture listed in profiles/ncu_traffic.json (not measured in this run)") if traffic else None,
                 "peak_source": peaks["src"] + ", bf16 dense sustained (kernel timed inside a long step)",
                 "avg_launch_us": tv["ms"] * 1e3 / tv["count"], "share_of_step_kernel_time": tv["ms"] / max(step_kernel_ms, 1e-9),
                 "mma_passes": PASSES.get(top, 1), "achieved_mma": achieved * PASSES.get(top, 1),
@@ -342,8 +649,10 @@ def run_ours(args):
                 "note": "achieved = ALGORITHMIC fp32 FLOPs (2MNK per Linear) / CUDA-event time of this family's launches in one "
                         "step; an fp32-exact product costs `mma_passes` bf16-equivalent tensor-core passes (north_star parity: 1e-3 on "
                         "fp32 logits; the mixed format's two fp8 cross terms run at twice the rate and count as one), so frac <= "
-                        "1/mma_passes; achieved_mma / frac_mma count every pass issued.  Launches are timed inside the overlapped step "
-                        "(other streams share the SMs and the 1 kW power budget)",
+                        "1/mma_passes; achieved_mma / frac_mma count every pass issued.  The breakdown is taken in ONE extra step with every "
+                        "launch on one stream (CUDA events around each launch need that: the timed steps overlap the teacher forward and the "
+                        "weight-gradient GEMMs on side streams), so a family's ms here is its serialised time under the step's power budget and "
+                        "the families sum to more than ms_per_step",
                 "families": {k: {"ms": round(v["ms"], 3), "launches": v["count"],
                                  "alg_tflops": round(v["work"] / (v["ms"] * 1e-3) / 1e12, 1)} for k, v in gemm_fams.items()},
                 "breakdown_ms": {k: round(v["ms"], 3) for k, v in fam}}
@@ -359,6 +668,9 @@ def run_ours(args):
     cpu_base = None
     if n == 1 and not args.no_cpu_baseline:
         cpu_base, _ = cpu_reference_rate(steps=1000, warmup=2, budget_s=18.0)
+    side = None
+    if n == 1 and not args.no_side and not args.pre_qat:
+        side = side_measurements(student, teacher, step, images, labels, dev, peaks)
 
     value = global_batch * args.steps / (ms_total * 1e-3)
     e2e_value = global_batch * args.steps / (e2e_ms * 1e-3)
@@ -373,7 +685,10 @@ def run_ours(args):
                    "ViT-B/16 teacher -> ViT-S/16 QAT student distillation step (KL+CE), batch 256, 1x B200"
                    if n == 1 else f"same distillation step data-parallel, global batch 1024 at {n} B200 with NCCL gradient allreduce",
                    "global_batch": global_batch, "per_gpu_batch": batch, "qconfig": "fbgemm", "layernorm": args.ln_variant, "image": "3x224x224",
-                   "parallelism": f"dp{n}", "l2": "per-step working set (~20 GB of activations) >> 126 MB L2; no flush needed",
+                   "parallelism": f"dp{n}",
+                   "scaling_note": "N = 1 runs BASELINE configs[1] (batch 256 on one GPU); N = 2 / 4 / 8 run configs[2] (global batch 1024 "
+                                   "split 512 / 256 / 128 per GPU: strong scaling among themselves; N = 4 has the per-GPU work of N = 1)",
+                   "l2": "per-step working set (~20 GB of activations) >> 126 MB L2; no flush needed",
                    "optimizer": "torch AdamW + clip-norm on the flat gradient arena" if args.torch_optimizer else
                                 "fused clip-norm + AdamW on flat arenas (qv_clip_adamw, 2 launches)",
                    "attention": "fused tcgen05 (integer-code student fwd+bwd, hi/lo teacher fwd)",
@@ -390,9 +705,20 @@ def run_ours(args):
     }
     if cpu_base is not None:
         line["cpu_baseline"] = cpu_base
+    if side is not None:
+        line.update({k: v for k, v in side.items() if k != "seconds"})
+        line["side_measurements_s"] = side["seconds"]
+    if ddp_check is not None:
+        line["ddp_check"] = ddp_check
+    if ddp_overhead_ms is not None:
+        line["ddp_overhead_ms"] = ddp_overhead_ms
+        line["ddp_overhead_note"] = ("ms_per_step minus the same K steps on the same per-GPU batch without the gradient exchange "
+                                     "(max over ranks both)")
     _emit(line)
     if world > 1:
         dist.destroy_process_group()
+    if not ddp_ok:
+        raise SystemExit(f"bench.py: data-parallel exchange check FAILED: {ddp_check}")
 
 
 _OUT = None
@@ -411,6 +737,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-side", action="store_true", help="skip the N = 1 side measurements (microbench, int8_eval, torch_cuda_eager)")
     ap.add_argument("--ln-variant", default="subclass", choices=["subclass", "plain"],
                     help="timm LayerNorm flavour: 'subclass' (timm.layers.LayerNorm, not observed: 101 fake-quant modules, the "
                          "primary target) or 'plain' (nn.LayerNorm, observed by prepare_qat: 126) -- SURVEY.md section 0.6")

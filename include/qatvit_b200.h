@@ -27,13 +27,17 @@ extern "C" {
 #define QV_ERR_UNSUPPORTED (-3)
 
 /* ---- library ------------------------------------------------------------------------------- */
-int qv_version(void);                 /* ABI version, currently 2 */
+int qv_version(void);                 /* ABI version, currently 3 */
 const char* qv_last_error(void);      /* thread-local message of the last failing call */
 int qv_device_sm_count(void);         /* SMs of the current device, <0 on error (no device) */
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
 int64_t qv_launch_count(void);
 /* how many of those were CTA-pair GEMMs (tcgen05 cta_group::2, clusters of two CTAs; see qv_gemm_bf16) */
 int64_t qv_gemm_pair_launches(void);
+/* Stream-ordered clear of `bytes` bytes (cudaMemsetAsync): the engine's only whole-buffer initialisation -- the residual-stream
+ * gradient whose non-cls rows are zero after the final LayerNorm's backward (ref: autograd's zero-filled SelectBackward0 of
+ * `x[:, 0]` in timm VisionTransformer.forward_head). */
+int qv_zero(void* ptr, int64_t bytes, void* stream);
 
 /* ---- observer + fake-quant (replaces torch.fused_moving_avg_obs_fake_quant,
  *      torch/ao/quantization/fake_quantize.py:423-438, called by the hooks prepare_qat installs:
@@ -77,12 +81,14 @@ int qv_fq_weight_grouped(const qv_fqw_desc* descs_device, int32_t n_desc, int32_
  * internal phases) min/max -> EMA -> qparams -> fake-quant of W[rows, cols].
  * Outputs (each may be NULL): y fp32 [rows,cols]; mask uint8; codes bf16 [rows,cols] holding the
  * centred integer code (q - zp), exact in bf16; codes_t bf16 [cols,rows] (transposed copy).
- * scratch: uint32[2] (only used when per_channel == 0). */
+ * scratch: uint32[2] (only used when per_channel == 0).
+ * scale_vec (may be NULL): fp32 [rows] <- the scale applied to each row (the per-tensor scale broadcast, or a copy of the
+ * per-channel scales): the per-output-channel vector the GEMM epilogues and gradient-plane kernels take. */
 int qv_fq_weight(const float* w, int64_t rows, int64_t cols, int32_t per_channel,
                  const int64_t* observer_enabled, const int64_t* fake_quant_enabled, float* min_val,
                  float* max_val, float* scale, int32_t* zero_point, float averaging_const, int32_t qmin,
                  int32_t qmax, int32_t symmetric, float* y, uint8_t* mask, uint16_t* codes, uint16_t* codes_t,
-                 uint32_t* scratch, void* stream);
+                 uint32_t* scratch, float* scale_vec, void* stream);
 
 /* STE backward gx = gy * mask (FusedMovingAvgObsFqHelperBackward0). */
 int qv_fq_bwd(const float* gy, const uint8_t* mask, int64_t n, float* gx, void* stream);
@@ -175,6 +181,10 @@ typedef struct qv_gemm_args {
    * A must be an activation-kind tensor and B a weight-kind one.  out_kind = 2: like out_kind = 1, but the output planes are
    * written in the mixed activation format (the next mixed GEMM's A operand). */
   int32_t mix;
+  /* out_kind = 2 only (may be NULL): range guard of the mixed activation format.  When an output value leaves the format's range
+   * (|x| > 448: its fp8 e5m2 copy saturates) the kernel ORs sat_bit into *sat_flag (device int32; one atomic per warp, only
+   * then).  The host checks the flag and routes that tensor to bf16 hi/lo planes (qatvit_b200/engine.py TeacherEngine). */
+  int32_t* sat_flag; int32_t sat_bit;
 } qv_gemm_args;
 /* Scheduling (no ABI surface): unsplit, unbatched K-major GEMMs with M >= 256 x (SMs / 2) run as CTA PAIRS -- clusters of two
  * CTAs on the two SMs of a TPC computing one 256 x tile_n tile with tcgen05 cta_group::2, each SM staging 128 rows of A and
@@ -198,11 +208,13 @@ int qv_splitk_reduce(const float* workspace, int32_t splits, int64_t M, int64_t 
  * x_in / y_raw / x_out / h_planes (bf16 [2][R][D]) / h_f32 / mean / rstd may be NULL; y_scale NULL = no fake-quant.
  * minmax (uint32[2], may be NULL): ordered min / max of h merged atomically -- the output observer of an OBSERVED LayerNorm
  * (plain nn.LayerNorm under prepare_qat), phase 1.
- * plane_fmt: 0 = h_planes are bf16 hi/lo planes; 1 = the mixed fp16 + fp8 operand format (qv_split_planes_mix, activation kind). */
+ * plane_fmt: 0 = h_planes are bf16 hi/lo planes; 1 = the mixed fp16 + fp8 operand format (qv_split_planes_mix, activation kind).
+ * sat_flag / sat_bit (plane_fmt 1, may be NULL): range guard of the mixed format, see qv_gemm_args.sat_flag. */
 int qv_resid_ln_fwd(const float* x_in, const float* y_raw, const float* y_scale, const int32_t* y_zp, int32_t qmin,
                     int32_t qmax, const float* gamma, const float* beta, float eps, int64_t R, int32_t D,
                     int64_t in_row_stride, float* x_out, uint16_t* h_planes, int64_t plane_stride, float* h_f32,
-                    float* mean, float* rstd, uint32_t* minmax, int32_t plane_fmt, void* stream);
+                    float* mean, float* rstd, uint32_t* minmax, int32_t plane_fmt, int32_t* sat_flag, int32_t sat_bit,
+                    void* stream);
 /* g_x[r*out_row_stride] = g_res[r] + LayerNormBackward(g_h, x, mean, rstd, gamma)[r]; partials: fp32
  * [ceil(R/rows_per_block)][2][D] per-block dgamma / dbeta sums (reduce with qv_colsum_reduce).
  * h_raw (may be NULL): the raw LayerNorm output of an observed LayerNorm; g_h then passes the STE mask of its fake-quant
@@ -259,10 +271,12 @@ int qv_attn_ds(const uint16_t* P, int64_t ldP, int64_t p_plane_stride, const flo
  * out_planes: bf16 hi/lo planes [2][B*T][out_ld]; head h fills columns h*64..h*64+63 (the proj GEMM's A operand);
  * out_f32: fp32 [B*T][H*64] copy of the output (either output may be NULL, not both).
  * lse (may be NULL): fp32 [B*H*T] natural-log logsumexp of the scaled logits (saved for a recomputing backward).
- * out_fmt: 0 = out_planes are bf16 hi/lo planes; 1 = the mixed fp16 + fp8 operand format (activation kind; out_ld % 64 == 0). */
+ * out_fmt: 0 = out_planes are bf16 hi/lo planes; 1 = the mixed fp16 + fp8 operand format (activation kind; out_ld % 64 == 0).
+ * sat_flag / sat_bit (out_fmt 1, may be NULL): range guard of the mixed format, see qv_gemm_args.sat_flag. */
 int qv_attn_fwd(const uint16_t* qkv_planes, int32_t n_planes, int64_t plane_stride, int64_t ld, int32_t B, int32_t T,
                 int32_t H, float scale, const float* qk_scale, const float* v_scale, uint16_t* out_planes,
-                int64_t out_plane_stride, int64_t out_ld, float* out_f32, float* lse, int32_t out_fmt, void* stream);
+                int64_t out_plane_stride, int64_t out_ld, float* out_f32, float* lse, int32_t out_fmt, int32_t* sat_flag,
+                int32_t sat_bit, void* stream);
 /* Fused attention backward for integer-code operands (the QAT student; autograd of F.scaled_dot_product_attention):
  * recomputes P from the codes and the forward's lse on the tensor cores and writes dQ | dK | dV (gradients w.r.t. the
  * fake-quantised q, k, v = s * codes) into g_qkv fp32 [B*T][3*H*64].  qkv_codes: ONE bf16 plane [B*T][ld]; o_planes: the

@@ -70,6 +70,7 @@ class GemmArgs(ctypes.Structure):
         ("obs_c", c_float), ("obs_qmin", c_int32), ("obs_qmax", c_int32), ("obs_symmetric", c_int32),
         ("obs_ticket", c_void_p),
         ("mix", c_int32),
+        ("sat_flag", c_void_p), ("sat_bit", c_int32),
     ]
 
 
@@ -80,12 +81,13 @@ _SIGNATURES = {
     "qv_device_sm_count": (c_int, []),
     "qv_launch_count": (c_int64, []),
     "qv_gemm_pair_launches": (c_int64, []),
+    "qv_zero": (c_int, [_P, c_int64, _P]),
     "qv_minmax_reset": (c_int, [_P, c_int, _P]),
     "qv_minmax_accumulate": (c_int, [_P, c_int64, _P, _P]),
     "qv_obs_update": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_float, c_int32, c_int32, c_int32, _P]),
     "qv_fq_apply": (c_int, [_P, c_int64, _P, _P, _P, c_int32, c_int32, _P, _P, _P]),
     "qv_fq_weight": (c_int, [_P, c_int64, c_int64, c_int32, _P, _P, _P, _P, _P, _P, c_float, c_int32, c_int32,
-                             c_int32, _P, _P, _P, _P, _P, _P]),
+                             c_int32, _P, _P, _P, _P, _P, _P, _P]),
     "qv_fq_weight_grouped": (c_int, [_P, c_int32, c_int32, c_int32, c_float, c_int32, c_int32, c_int32, _P]),
     "qv_fq_bwd": (c_int, [_P, _P, c_int64, _P, _P]),
     "qv_split_planes": (c_int, [_P, c_int64, _P, _P, _P]),
@@ -95,7 +97,7 @@ _SIGNATURES = {
     "qv_gemm_bf16": (c_int, [POINTER(GemmArgs), _P]),
     "qv_splitk_reduce": (c_int, [_P, c_int32, c_int64, c_int64, _P, _P, _P, _P, c_int32, _P]),
     "qv_resid_ln_fwd": (c_int, [_P, _P, _P, _P, c_int32, c_int32, _P, _P, c_float, c_int64, c_int32, c_int64, _P, _P,
-                                c_int64, _P, _P, _P, _P, c_int32, _P]),
+                                c_int64, _P, _P, _P, _P, c_int32, _P, c_int32, _P]),
     "qv_ln_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int32, c_int64, _P, _P, c_int32, _P, _P, _P, c_int32, c_int32, _P]),
     "qv_ln_bwd_gp": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int32, _P, _P, c_int32, _P, _P, _P, c_int32, c_int32,
                              _P, _P, _P, c_int32, c_int32, _P, _P, c_int64, _P, _P]),
@@ -109,7 +111,7 @@ _SIGNATURES = {
     "qv_softmax_planes": (c_int, [_P, c_int64, c_int64, c_int32, c_float, _P, c_int64, c_int64, _P]),
     "qv_attn_ds": (c_int, [_P, c_int64, c_int64, _P, c_int64, c_int64, c_int32, c_float, _P, c_int64, c_int64, _P]),
     "qv_attn_fwd": (c_int, [_P, c_int32, c_int64, c_int64, c_int32, c_int32, c_int32, c_float, _P, _P, _P, c_int64, c_int64,
-                            _P, _P, c_int32, _P]),
+                            _P, _P, c_int32, _P, c_int32, _P]),
     "qv_attn_bwd": (c_int, [_P, c_int64, _P, _P, c_int64, c_int64, _P, c_int64, c_int64, _P, c_int32, c_int32, c_int32, c_float,
                             _P, _P]),
     "qv_attn_bwd_gp": (c_int, [_P, c_int64, _P, _P, c_int64, c_int64, _P, c_int64, c_int64, _P, c_int32, c_int32, c_int32,

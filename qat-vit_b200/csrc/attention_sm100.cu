@@ -64,6 +64,8 @@ struct AttnParams {
   float* out_f32;        // optional fp32 copy of the output, [B*T][H*64]
   int32_t out_fmt;       // 0 = bf16 hi/lo planes, 1 = mixed fp16 + fp8 planes (the teacher's proj operand)
   float* lse;            // optional [B*H*T]: scale' * rowmax + ln(rowsum)   (natural-log logsumexp of the scaled logits)
+  int32_t* sat_flag;     // out_fmt 1: OR sat_bit into *sat_flag when an output leaves the mixed format's range (may be null)
+  int32_t sat_bit;
 };
 
 // A operand from TMEM (TS form): D[tmem] (+)= A[tmem] * B[smem desc]
@@ -265,6 +267,7 @@ qv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       if (p.qk_scale) { const float s = __ldg(p.qk_scale); sc *= s * s; }
       if (p.v_scale) vs = __ldg(p.v_scale);
       const float c2 = sc * 1.4426950408889634f;  // logits -> base-2 exponent
+      float amax = 0.f;                           // mixed plane output: largest |value| written by this thread
       int local = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
         const int b = item / p.H, h = item % p.H;
@@ -330,9 +333,11 @@ qv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
               for (int j = 0; j < 8; ++j) {
                 uint32_t h16[4], ph[4], pl[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                  h16[e] = qv_mix_split2<QV_MIX_ACT>(__uint_as_float(o[8 * j + 2 * e]) * inv, __uint_as_float(o[8 * j + 2 * e + 1]) * inv,
-                                                     ph[e], pl[e]);
+                for (int e = 0; e < 4; ++e) {
+                  const float a0 = __uint_as_float(o[8 * j + 2 * e]) * inv, a1 = __uint_as_float(o[8 * j + 2 * e + 1]) * inv;
+                  amax = fmaxf(amax, fmaxf(fabsf(a0), fabsf(a1)));
+                  h16[e] = qv_mix_split2<QV_MIX_ACT>(a0, a1, ph[e], pl[e]);
+                }
                 *reinterpret_cast<uint4*>(dst_hi + 8 * j) = make_uint4(h16[0], h16[1], h16[2], h16[3]);
                 *reinterpret_cast<uint2*>(row1 + 8 * j) = make_uint2(ph[0] | (ph[1] << 16), ph[2] | (ph[3] << 16));
                 *reinterpret_cast<uint2*>(row1 + 64 + 8 * j) = make_uint2(pl[0] | (pl[1] << 16), pl[2] | (pl[3] << 16));
@@ -359,6 +364,7 @@ qv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
           if (p.lse) p.lse[(static_cast<int64_t>(b) * p.H + h) * p.T + t] = mx * sc + logf(sum);
         }
       }
+      if (p.sat_flag && __any_sync(0xffffffffu, amax > QV_MIX_ACT_MAX) && lane == 0) atomicOr(p.sat_flag, p.sat_bit);
     }
   }
 
@@ -942,7 +948,7 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
 extern "C" int qv_attn_fwd(const uint16_t* qkv_planes, int32_t n_planes, int64_t plane_stride, int64_t ld, int32_t B,
                            int32_t T, int32_t H, float scale, const float* qk_scale, const float* v_scale,
                            uint16_t* out_planes, int64_t out_plane_stride, int64_t out_ld, float* out_f32, float* lse,
-                           int32_t out_fmt, void* stream) {
+                           int32_t out_fmt, int32_t* sat_flag, int32_t sat_bit, void* stream) {
   QV_REQUIRE(qkv_planes && (out_planes || out_f32) && B > 0 && T > 0 && H > 0, QV_ERR_INVALID, "bad attn_fwd arguments");
   QV_REQUIRE(out_fmt == 0 || (out_fmt == 1 && out_planes && out_ld % 64 == 0), QV_ERR_INVALID,
              "out_fmt must be 0 (bf16 hi/lo) or 1 (mixed fp16 + fp8 planes, row pitch a multiple of 64)");
@@ -968,6 +974,8 @@ extern "C" int qv_attn_fwd(const uint16_t* qkv_planes, int32_t n_planes, int64_t
   ap.out_f32 = out_f32;
   ap.lse = lse;
   ap.out_fmt = out_fmt;
+  ap.sat_flag = out_fmt == 1 ? sat_flag : nullptr;
+  ap.sat_bit = sat_bit;
   // one tensor, three box shapes: per-image matrices [T rows, ld cols]; rows >= T are zero-filled by TMA
   qv_operand op;
   memset(&op, 0, sizeof(op));

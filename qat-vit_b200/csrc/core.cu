@@ -49,7 +49,7 @@ int qv_num_sms() {
   return cached_sms;
 }
 
-extern "C" int qv_version(void) { return 2; }
+extern "C" int qv_version(void) { return 3; }
 extern "C" const char* qv_last_error(void) { return g_err; }
 extern "C" int qv_device_sm_count(void) {
   int n = qv_num_sms();
@@ -57,3 +57,11 @@ extern "C" int qv_device_sm_count(void) {
   return n;
 }
 extern "C" int64_t qv_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int qv_zero(void* ptr, int64_t bytes, void* stream) {
+  QV_REQUIRE(ptr != nullptr && bytes >= 0, QV_ERR_INVALID, "bad qv_zero arguments");
+  QV_REQUIRE(qv_num_sms() > 0, QV_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  cudaError_t e = cudaMemsetAsync(ptr, 0, static_cast<size_t>(bytes), static_cast<cudaStream_t>(stream));
+  QV_REQUIRE(e == cudaSuccess, QV_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+  return QV_OK;
+}

@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(256, (VPL <= 4 ? 3 : 2)) resid_ln_fwd_kernel(
     const float* __restrict__ x_in, const float* __restrict__ y_raw, const float* y_scale, const int32_t* y_zp, int qmin, int qmax,
     const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int64_t R, int64_t in_row_stride,
     float* __restrict__ x_out, __nv_bfloat16* __restrict__ h_planes, int64_t plane_stride, float* __restrict__ h_f32,
-    float* __restrict__ mean_out, float* __restrict__ rstd_out, uint32_t* minmax, int plane_fmt) {
+    float* __restrict__ mean_out, float* __restrict__ rstd_out, uint32_t* minmax, int plane_fmt, int32_t* sat_flag, int32_t sat_bit) {
   constexpr int D = 128 * VPL;
   const int lane = threadIdx.x & 31;
   const int64_t n_warps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
@@ -130,6 +130,10 @@ __global__ void __launch_bounds__(256, (VPL <= 4 ? 3 : 2)) resid_ln_fwd_kernel(
       omx = fmaxf(omx, fmaxf(fmaxf(o0, o1), fmaxf(o2, o3)));
     }
     r = rn;
+  }
+  if (sat_flag && plane_fmt == 1) {   // mixed format range guard: |h| beyond what fp8 e5m2(h * 2^7) holds -> raise the caller's flag
+    const bool over = fmaxf(-omn, omx) > QV_MIX_ACT_MAX;
+    if (__any_sync(0xffffffffu, over) && lane == 0) atomicOr(sat_flag, sat_bit);
   }
   if (minmax) {                       // observed-LayerNorm variant: min / max of the LN output, one atomic pair per block
     omn = qv_warp_min(omn);
@@ -712,7 +716,8 @@ inline int ew_blocks(int64_t n_items, int per_sm = 8) {
 extern "C" int qv_resid_ln_fwd(const float* x_in, const float* y_raw, const float* y_scale, const int32_t* y_zp,
                                int32_t qmin, int32_t qmax, const float* gamma, const float* beta, float eps, int64_t R,
                                int32_t D, int64_t in_row_stride, float* x_out, uint16_t* h_planes, int64_t plane_stride,
-                               float* h_f32, float* mean, float* rstd, uint32_t* minmax, int32_t plane_fmt, void* stream) {
+                               float* h_f32, float* mean, float* rstd, uint32_t* minmax, int32_t plane_fmt, int32_t* sat_flag,
+                               int32_t sat_bit, void* stream) {
   QV_REQUIRE((x_in || y_raw) && gamma && beta && R > 0, QV_ERR_INVALID, "bad resid_ln_fwd arguments");
   QV_REQUIRE(plane_fmt == 0 || plane_fmt == 1, QV_ERR_INVALID, "plane_fmt must be 0 (bf16 hi/lo) or 1 (mixed fp16 + fp8)");
   QV_REQUIRE(D % 128 == 0 && D >= 128 && D <= 1024, QV_ERR_UNSUPPORTED, "LayerNorm width must be a multiple of 128 <= 1024 (got %d)", D);
@@ -727,7 +732,7 @@ extern "C" int qv_resid_ln_fwd(const float* x_in, const float* y_raw, const floa
   if (in_row_stride < 1) in_row_stride = 1;
 #define LAUNCH(V)                                                                                                        \
   resid_ln_fwd_kernel<V><<<grid, 256, 0, st>>>(x_in, y_raw, y_scale, y_zp, qmin, qmax, gamma, beta, eps, R, in_row_stride, \
-                                               x_out, hp, plane_stride, h_f32, mean, rstd, minmax, plane_fmt)
+                                               x_out, hp, plane_stride, h_f32, mean, rstd, minmax, plane_fmt, sat_flag, sat_bit)
   switch (D / 128) {
     case 1: LAUNCH(1); break;
     case 2: LAUNCH(2); break;

@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(128) qv_fq_weight_kernel(const float* __restri
                                                            float* max_val, float* scale, int32_t* zp, float c, int qmin,
                                                            int qmax, int symmetric, float* __restrict__ y,
                                                            uint8_t* __restrict__ mask, __nv_bfloat16* __restrict__ codes,
-                                                           __nv_bfloat16* __restrict__ codes_t) {
+                                                           __nv_bfloat16* __restrict__ codes_t, float* __restrict__ scale_vec) {
   const int64_t r = blockIdx.x;
   const float* wr = w + r * cols;
   __shared__ float s_scale;
@@ -178,6 +178,7 @@ __global__ void __launch_bounds__(128) qv_fq_weight_kernel(const float* __restri
     if (threadIdx.x == 0) { s_scale = scale[0]; s_zp = zp[0]; }
   }
   __syncthreads();
+  if (scale_vec && threadIdx.x == 0) scale_vec[r] = s_scale;      // per-row copy of the scale in use (GEMM epilogue vector)
   QvQParams q;
   q.scale = s_scale;
   q.inv = __fdiv_rn(1.0f, q.scale);
@@ -429,7 +430,7 @@ extern "C" int qv_fq_weight(const float* w, int64_t rows, int64_t cols, int32_t 
                             const int64_t* observer_enabled, const int64_t* fake_quant_enabled, float* min_val,
                             float* max_val, float* scale, int32_t* zero_point, float averaging_const, int32_t qmin,
                             int32_t qmax, int32_t symmetric, float* y, uint8_t* mask, uint16_t* codes, uint16_t* codes_t,
-                            uint32_t* scratch, void* stream) {
+                            uint32_t* scratch, float* scale_vec, void* stream) {
   QV_REQUIRE(w && rows > 0 && cols > 0, QV_ERR_INVALID, "bad weight shape");
   QV_REQUIRE(observer_enabled && fake_quant_enabled && min_val && max_val && scale && zero_point, QV_ERR_INVALID,
              "null observer state pointer");
@@ -441,7 +442,7 @@ extern "C" int qv_fq_weight(const float* w, int64_t rows, int64_t cols, int32_t 
     qv_fq_weight_kernel<true><<<static_cast<unsigned>(rows), 128, 0, st>>>(w, rows, cols, observer_enabled,
                                                                           fake_quant_enabled, min_val, max_val, scale,
                                                                           zero_point, averaging_const, qmin, qmax,
-                                                                          symmetric, y, mask, c, ct);
+                                                                          symmetric, y, mask, c, ct, scale_vec);
     return qv_check_launch("qv_fq_weight");
   }
   QV_REQUIRE(scratch != nullptr, QV_ERR_INVALID, "per-tensor weight fake-quant needs a uint32[2] scratch");
@@ -455,7 +456,7 @@ extern "C" int qv_fq_weight(const float* w, int64_t rows, int64_t cols, int32_t 
   qv_fq_weight_kernel<false><<<static_cast<unsigned>(rows), 128, 0, st>>>(w, rows, cols, observer_enabled,
                                                                          fake_quant_enabled, min_val, max_val, scale,
                                                                          zero_point, averaging_const, qmin, qmax,
-                                                                         symmetric, y, mask, c, ct);
+                                                                         symmetric, y, mask, c, ct, scale_vec);
   return qv_check_launch("qv_fq_weight");
 }
 

@@ -80,6 +80,8 @@ struct GemmKParams {
   const int64_t* obs_enabled; const int64_t* obs_fq_enabled;
   float obs_c; int32_t obs_qmin, obs_qmax, obs_symmetric;
   uint32_t* obs_ticket;
+  int32_t* sat_flag;      // EPI 1, out_fmt 1: OR sat_bit into *sat_flag when an output leaves the mixed format's range
+  int32_t sat_bit;
 };
 
 // SPLIT (mixed-format CTA pairs): one pipeline stage holds ONE region of a k-block -- the fp16 planes of A and B, or their fp8
@@ -579,6 +581,7 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint8_t* my_epi = smem_epi + ew * EPI_WARP_BYTES;
     float* my_terms = reinterpret_cast<float*>(smem_epi + 8 * EPI_WARP_BYTES) + ew * 64;   // EPI 0: [mult 32][bias 32]
     float mn = INFINITY, mx = -INFINITY;
+    float amax = 0.f;                            // mixed plane output: largest |value| this thread has written
     const float alpha = p.alpha ? __ldg(p.alpha) : 1.0f;
     const bool raw = p.splits > 1;
     int local = 0;
@@ -691,6 +694,7 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               for (int e = 0; e < 4; ++e) {
                 float a0 = a[2 * e], a1 = a[2 * e + 1];
                 if (p.act == 1) { a0 = qv_gelu_fast(a0); a1 = qv_gelu_fast(a1); }
+                amax = fmaxf(amax, fmaxf(fabsf(a0), fabsf(a1)));
                 uint32_t ph, pl;
                 h16[e] = qv_mix_split2<QV_MIX_ACT>(a0, a1, ph, pl);
                 if (e & 1) { h8[e >> 1] |= ph << 16; l8[e >> 1] |= pl << 16; }
@@ -735,6 +739,9 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
     if (lane == 0) tma_store_wait_read<0>();
+    if constexpr (EPI == 1) {
+      if (p.sat_flag && __any_sync(0xffffffffu, amax > QV_MIX_ACT_MAX) && lane == 0) atomicOr(p.sat_flag, p.sat_bit);
+    }
     if (p.minmax && !raw) {
       mn = qv_warp_min(mn);
       mx = qv_warp_max(mx);
@@ -986,6 +993,8 @@ extern "C" int qv_gemm_bf16(const qv_gemm_args* a, void* stream) {
     kp.obs_c = a->obs_c; kp.obs_qmin = a->obs_qmin; kp.obs_qmax = a->obs_qmax; kp.obs_symmetric = a->obs_symmetric;
     kp.obs_ticket = a->obs_ticket;
   }
+  kp.sat_flag = (a->out_kind == 2) ? a->sat_flag : nullptr;
+  kp.sat_bit = a->sat_bit;
   const int64_t items = static_cast<int64_t>(kp.tiles_m) * kp.tiles_n * (nbatch > 1 ? nbatch : kp.splits);
   QV_REQUIRE(items < (1LL << 31), QV_ERR_UNSUPPORTED, "too many tiles");
   const int sms = qv_num_sms();

@@ -122,6 +122,11 @@ __device__ __forceinline__ void qv_split_bf16(float x, __nv_bfloat16& hi, __nv_b
 #define QV_MIX_WGT 1
 #define QV_MIX_SCALE 128.0f
 #define QV_MIX_ACC_SCALE 6.103515625e-05f     /* 2^-14 */
+// Range of the format: the e5m2 copy of an activation saturates at 57344 / 2^7 = 448 (its fp16 part at 511.75), the e4m3 copy
+// of a weight at 448 / 2^7 = 3.5.  Producers of mixed ACTIVATION planes take an optional (flag, bit) pair and OR the bit into
+// the flag when a value leaves the range (one atomic per warp, only then); the host routes that tensor to bf16 hi/lo planes.
+#define QV_MIX_ACT_MAX 448.0f
+#define QV_MIX_WGT_MAX 3.5f
 // returns the packed fp16 pair (a0 low half, a1 high half); ph / pl = packed hi8 / lo8 pairs (a0 low byte)
 template <int KIND>
 __device__ __forceinline__ uint32_t qv_mix_split2(float a0, float a1, uint32_t& ph, uint32_t& pl) {

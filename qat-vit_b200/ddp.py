@@ -30,12 +30,31 @@ class GradSync:
         self.bucket_elems = max(1, bucket_bytes // 4)
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.rehomed = False
 
-    def bind_observers(self, observers: Sequence[Tuple[torch.Tensor, torch.Tensor]]) -> None:
+    def bind_observers(self, observers: Sequence[Tuple[torch.Tensor, torch.Tensor]], rehome: Optional[bool] = None) -> None:
+        """observers: the (min_val, max_val) buffers of the activation fake-quant modules, in a fixed order.
+        rehome (default: on for CUDA): move the storage of every buffer INTO the tail of the flat buffer (the module keeps the
+        same tensor objects -- names, state_dict keys and values unchanged; ``t.data`` becomes a view of the tail), so that
+        packing rank 0's state and adopting it after the all-reduce cost no launch at all: the kernels that update the
+        running ranges write straight into the exchange buffer.  Do not deep-copy / ``.to()`` the model afterwards."""
         observers = list(observers)
         if 2 * len(observers) != self.n_tail:
             raise ValueError(f"expected {self.n_tail // 2} observers, got {len(observers)}")
         self.observers = observers
+        if rehome is None:
+            rehome = self.flat.is_cuda
+        self.rehomed = bool(rehome) and len(observers) > 0
+        if self.rehomed:
+            t = self.tail
+            with torch.no_grad():
+                for i, (mn, mx) in enumerate(observers):
+                    for j, buf in enumerate((mn, mx)):
+                        if buf.numel() != 1 or buf.dtype != t.dtype:
+                            raise ValueError("activation observers are per-tensor fp32 scalars")
+                        slot = t[2 * i + j:2 * i + j + 1]
+                        slot.copy_(buf.reshape(1))
+                        buf.data = slot.view(buf.shape)
 
     @property
     def grad_arena(self) -> torch.Tensor:
@@ -46,10 +65,19 @@ class GradSync:
         return self.flat[self.n_grad:]
 
     def pack_observers(self) -> None:
+        """Rank 0 contributes its running min / max, every other rank zeros: after the SUM everyone holds rank 0's state."""
         if self.n_tail == 0:
             return
         if len(self.observers) * 2 != self.n_tail:
             raise RuntimeError("GradSync.bind_observers() has not been called")
+        if self.rehomed:
+            if self.rank != 0:          # the local ranges are dead after the forward: clear them in place (one memset)
+                if self.flat.is_cuda:
+                    from . import ops
+                    ops.zero_(self.tail)
+                else:
+                    self.tail.zero_()
+            return
         if self.rank == 0:
             vals = [t.reshape(1) for pair in self.observers for t in pair]
             torch.cat(vals, out=self.tail)
@@ -57,7 +85,7 @@ class GradSync:
             self.tail.zero_()
 
     def unpack_observers(self) -> None:
-        if self.n_tail == 0 or self.world == 1:
+        if self.n_tail == 0 or self.world == 1 or self.rehomed:
             return
         t = self.tail
         for i, (mn, mx) in enumerate(self.observers):
@@ -94,10 +122,13 @@ class GradSync:
         self.unpack_observers()
 
     # ---- overlapped mode: the engine reports, layer by layer, how much of the arena is final -------------------------
-    def begin_step(self, min_bucket_bytes: int = 4 << 20) -> None:
+    def begin_step(self, min_bucket_bytes: Optional[int] = None) -> None:
         """Call before backward.  Gradients are produced from the END of the arena (head, last block, ...) towards its start
         (embeddings), like DDP's reverse-order buckets (torch/nn/parallel/distributed.py:831-833): ``grads_final_from(lo)``
         all-reduces the newly completed suffix asynchronously so the transfer overlaps the remaining backward GEMMs."""
+        if min_bucket_bytes is None:
+            import os
+            min_bucket_bytes = int(float(os.environ.get("QV_DDP_BUCKET_MB", "25")) * (1 << 20))
         self._hi = self.flat.numel()
         self._works = []
         self._min_bucket = max(1, min_bucket_bytes // 4)

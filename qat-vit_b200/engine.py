@@ -99,15 +99,15 @@ class _QLinear:
     def quantize_weight(self) -> None:
         f = self.wfq
         w = self.weight.detach()
+        # per-tensor weights (qnnpack qconfig): the kernel also writes the scale broadcast over the output channels
+        sv = None if f.per_channel else self.wscale_vec
         if self.small:
             ops.fq_weight(w, f.per_channel, f.observer_enabled, f.fake_quant_enabled, f.min_val, f.max_val, f.scale,
-                          f.zero_point, f.c, f.qmin, f.qmax, f.symmetric, y=self.wq, mask=self.wmask, scratch=self.scratch)
+                          f.zero_point, f.c, f.qmin, f.qmax, f.symmetric, y=self.wq, mask=self.wmask, scratch=self.scratch, scale_vec=sv)
         else:
             ops.fq_weight(w, f.per_channel, f.observer_enabled, f.fake_quant_enabled, f.min_val, f.max_val, f.scale,
                           f.zero_point, f.c, f.qmin, f.qmax, f.symmetric, mask=self.wmask, codes=self.codes[0],
-                          codes_t=self.codes_t[0], scratch=self.scratch)
-        if not f.per_channel:
-            self.wscale_vec.copy_(f.scale.expand(self.N))
+                          codes_t=self.codes_t[0], scratch=self.scratch, scale_vec=sv)
 
 
 def gemm_tile_n(N: int) -> int:
@@ -147,8 +147,50 @@ def wgrad_splits(n_out: int, k_in: int, tokens: int, sms: int) -> int:
     return _splits_for(tiles, -(-tokens // 64), sms)
 
 
+def _is_identity(m) -> bool:
+    return m is None or isinstance(m, nn.Identity) or (isinstance(m, nn.Dropout) and m.p == 0.0)
+
+
+def _check_supported_vit(vit: nn.Module) -> None:
+    """The engines execute ONE function: the timm VisionTransformer of SURVEY.md App. B (what ``timm.create_model`` returns for
+    vit_small/base_patch16_224 with default arguments, ref model_registry.py:167-172,228-233).  ``create_student`` /
+    ``create_teacher`` forward **kwargs to timm, so other variants are reachable: refuse them instead of silently computing a
+    different function than the module tree."""
+    bad = []
+    for name in ("norm_pre", "patch_drop", "fc_norm", "pos_drop", "head_drop"):
+        if hasattr(vit, name) and not _is_identity(getattr(vit, name)):
+            bad.append(name)
+    if getattr(vit, "global_pool", "token") != "token":
+        bad.append(f"global_pool={vit.global_pool!r}")
+    if getattr(vit, "num_prefix_tokens", 1) != 1 or getattr(vit, "reg_token", None) is not None:
+        bad.append("prefix / register tokens")
+    if getattr(vit, "no_embed_class", False):
+        bad.append("no_embed_class")
+    if hasattr(vit.patch_embed, "norm") and not _is_identity(vit.patch_embed.norm):
+        bad.append("patch_embed.norm")
+    for i, blk in enumerate(vit.blocks):
+        for name in ("ls1", "ls2", "drop_path1", "drop_path2"):
+            if hasattr(blk, name) and not _is_identity(getattr(blk, name)):
+                bad.append(f"blocks.{i}.{name}")
+        for name in ("q_norm", "k_norm", "norm", "attn_drop", "proj_drop"):
+            if hasattr(blk.attn, name) and not _is_identity(getattr(blk.attn, name)):
+                bad.append(f"blocks.{i}.attn.{name}")
+        for name in ("drop1", "drop2", "norm"):
+            if hasattr(blk.mlp, name) and not _is_identity(getattr(blk.mlp, name)):
+                bad.append(f"blocks.{i}.mlp.{name}")
+        act = getattr(blk.mlp, "act", None)
+        if act is not None and not (isinstance(act, nn.GELU) and getattr(act, "approximate", "none") == "none"):
+            bad.append(f"blocks.{i}.mlp.act={type(act).__name__}")
+        if blk.attn.qkv.bias is None or blk.attn.proj.bias is None or blk.mlp.fc1.bias is None or blk.mlp.fc2.bias is None:
+            bad.append(f"blocks.{i}: Linear without bias")
+    if bad:
+        raise NotImplementedError("qatvit_b200: this VisionTransformer variant is not on the fused path (the engine would compute a "
+                                  "different function than the module tree): " + ", ".join(bad[:8]))
+
+
 class _ViTDims:
     def __init__(self, vit: nn.Module, batch: int):
+        _check_supported_vit(vit)
         pe = vit.patch_embed
         self.B = batch
         self.D = vit.embed_dim
@@ -173,6 +215,68 @@ class _ViTDims:
         self.eps = float(vit.blocks[0].norm1.eps)
         self.attn_scale = float(vit.blocks[0].attn.scale)
 
+    def with_batch(self, b: int) -> "_ViTDims":
+        import copy
+        d = copy.copy(self)
+        d.B, d.M = b, b * self.T
+        return d
+
+
+class _BatchBuffers:
+    """Activation / scratch buffers of an engine: allocated ONCE for the construction batch B and, for a smaller batch b (the
+    ragged last batch of an epoch -- the reference's DataLoaders have no drop_last, ref qat_trainer.py:227-254: 50 000 % 256 = 80
+    train, 10 000 % 256 = 16 eval images), re-viewed as the CONTIGUOUS tensors an engine built for b would own (same storage, first
+    numel(b) elements).  Kernels take their row counts at launch and TMA clips ragged tiles, so an engine built for B and fed b
+    images computes bit for bit what an engine built for b computes (tests/test_partial_batch_gpu.py).  Views are cached per b:
+    nothing is allocated and nothing synchronises after the first step of a given size."""
+
+    def _bb_init(self, dev, dims: _ViTDims) -> None:
+        self._bb_dev, self._bb_dims = dev, dims
+        self._bb_specs, self._bb_full, self._bb_views = {}, {}, {}
+        self._bb_cur = dims.B
+
+    def _bb_add(self, name: str, shape_fn, dtype=torch.float32, count: Optional[int] = None, zero: bool = False) -> None:
+        shape = tuple(int(x) for x in shape_fn(self._bb_dims))
+        alloc = torch.zeros if zero else torch.empty
+        full = [alloc(shape, dtype=dtype, device=self._bb_dev) for _ in range(count or 1)]
+        self._bb_specs[name] = (shape_fn, count, zero)
+        self._bb_full[name] = full
+        setattr(self, name, full if count else full[0])
+
+    def _bb_bind(self, b: int) -> None:
+        """Point every registered buffer attribute (and self.d) at its batch-b view."""
+        if b == self._bb_cur:
+            return
+        views = self._bb_views.get(b)
+        if views is None:
+            d = self._bb_dims.with_batch(b)
+            views = {"d": d}
+            for name, (shape_fn, count, _) in self._bb_specs.items():
+                shape = tuple(int(x) for x in shape_fn(d))
+                n = math.prod(shape)
+                vs = [f.view(-1)[:n].view(shape) for f in self._bb_full[name]]
+                views[name] = vs if count else vs[0]
+            self._bb_views[b] = views
+        for name, v in views.items():
+            setattr(self, name, v)
+        for name, (_, _, zero) in self._bb_specs.items():
+            if zero:        # padded buffers whose padding must read as zero: the layout changed, so clear them (fallback paths only)
+                for t in self._bb_full[name]:
+                    t.zero_()
+        self._bb_cur = b
+        self._bb_on_bind(b)
+
+    def _bb_on_bind(self, b: int) -> None:
+        pass
+
+    def _bb_check(self, images: torch.Tensor, what: str) -> int:
+        d0 = self._bb_dims
+        b = int(images.shape[0]) if images.dim() == 4 else -1
+        if images.dim() != 4 or tuple(images.shape[1:]) != (d0.in_ch, d0.HW, d0.HW) or not (1 <= b <= d0.B):
+            raise RuntimeError(f"{what} engine built for batch {d0.B} of {d0.in_ch}x{d0.HW}x{d0.HW} images (any batch 1..{d0.B} "
+                               f"is accepted), got {tuple(images.shape)}")
+        return b
+
 
 def _attention_forward(d: _ViTDims, qkvp: torch.Tensor, S: torch.Tensor, Pp: torch.Tensor, o: torch.Tensor) -> None:
     """softmax(Q K^T / 8) V per (image, head) as two batched tcgen05 GEMMs + one row-softmax kernel
@@ -188,12 +292,22 @@ def _attention_forward(d: _ViTDims, qkvp: torch.Tensor, S: torch.Tensor, Pp: tor
     ops.gemm(p_op, v_op, T, 64, T, PAIRS_FP32, out=Out.tokens(o, B, T, 0, 64), nbatch=BH, batch_inner=H)
 
 
-class TeacherEngine:
+class TeacherEngine(_BatchBuffers):
     """Frozen fp32 ViT forward (ref qat_trainer.py:337-338) on the tcgen05 GEMMs, fp32 accumulation.  The block Linears
     take their operands in the mixed format (fp16 value + fp8 copies of the value and of the fp16 rounding residual): one
     kind::f16 product plus two kind::f8f6f4 cross terms at twice the rate -- fp32-grade (~2^-16 per product) for the cost of
     two bf16 passes instead of three.  ``mixed=False`` (or QV_TEACHER_MIX=0) keeps bf16 hi/lo planes and three MMAs per product
-    (hi*hi + hi*lo + lo*hi) everywhere; the patch embedding always does."""
+    (hi*hi + hi*lo + lo*hi) everywhere; the patch embedding always does.
+
+    Range guard of the mixed format (one fixed 2^7 scale: activations saturate at |x| = 448, weights at |w| = 3.5 --
+    csrc/qv_common.cuh).  Per Linear and per block: (a) a weight with max |w| >= 3.5 is routed to the three-pass path when the
+    engine is built; (b) every producer of a mixed ACTIVATION tensor (LayerNorm, attention output, fc1 + GELU epilogue) raises a
+    device flag bit when a value leaves the range; the flags are copied to pinned host memory after every forward (no sync) and
+    looked at when the NEXT forward starts: that Linear then moves to bf16 hi/lo planes for good (``saturation_events``), with a
+    RuntimeWarning.  ``calibrate(images)`` does the same synchronously -- call it once on a representative batch before training
+    so that no step ever runs with a clamped activation (a fine-tuned in21k ViT-B has outlier channels a random-init one lacks)."""
+
+    SITES = ("qkv", "proj", "fc1", "fc2")
 
     def __init__(self, vit: nn.Module, batch: int, mixed: Optional[bool] = None):
         import os
@@ -203,45 +317,112 @@ class TeacherEngine:
             raise RuntimeError("qatvit_b200: the teacher must live on a CUDA device (there is no CPU fallback)")
         self.dev = dev
         d = self.d = _ViTDims(vit, batch)
-        M, D, F = d.M, d.D, d.F
+        D, F = d.D, d.F
         bf, f32 = torch.bfloat16, torch.float32
 
         if mixed is None:
             mixed = os.environ.get("QV_TEACHER_MIX", "1") != "0"
-        self.mixed = mx = bool(mixed) and D % 64 == 0 and F % 64 == 0
+        self.mixed = bool(mixed) and D % 64 == 0 and F % 64 == 0
+        self.saturation_events: List[str] = []        # "blocks.3.fc2: activation |x| > 448" ... (what left the mixed format, and why)
 
-        def planes_of(w: torch.Tensor, mix: bool = False) -> torch.Tensor:
-            w2 = w.detach().reshape(w.shape[0], -1).contiguous()
-            return ops.split_planes_mix(w2, weight=True) if mix else ops.split_planes(w2)
-
-        self.w_conv = planes_of(vit.patch_embed.proj.weight)
+        self.w_conv = ops.split_planes(vit.patch_embed.proj.weight.detach().reshape(D, -1).contiguous())
         self.blocks = []
-        for blk in vit.blocks:
-            self.blocks.append(dict(
-                n1=(blk.norm1.weight.detach(), blk.norm1.bias.detach()), n2=(blk.norm2.weight.detach(), blk.norm2.bias.detach()),
-                qkv=(planes_of(blk.attn.qkv.weight, mx), blk.attn.qkv.bias.detach()),
-                proj=(planes_of(blk.attn.proj.weight, mx), blk.attn.proj.bias.detach()),
-                fc1=(planes_of(blk.mlp.fc1.weight, mx), blk.mlp.fc1.bias.detach()),
-                fc2=(planes_of(blk.mlp.fc2.weight, mx), blk.mlp.fc2.bias.detach())))
-        e = lambda *s, dt=f32: torch.empty(*s, dtype=dt, device=dev)  # noqa: E731
-        self.img_planes = e(2, d.B * d.P, d.Kc, dt=bf)
-        self.p_raw = e(d.B * d.P, D)
-        self.x = [e(M, D), e(M, D)]
-        self.hp = e(2, M, D, dt=bf)
-        self.qkvp = e(2, M, 3 * D, dt=bf)
-        self.op = e(2, M, D, dt=bf)
-        self.y = e(M, D)
-        self.fp = e(2, M, F, dt=bf)
-        self.xn = e(d.B, D)
-        self.logits = e(d.B, d.C)
+        self.mix: List[Dict[str, bool]] = []          # per block and Linear: operands in the mixed format?
+        for li, blk in enumerate(vit.blocks):
+            lin = dict(qkv=blk.attn.qkv, proj=blk.attn.proj, fc1=blk.mlp.fc1, fc2=blk.mlp.fc2)
+            entry = dict(n1=(blk.norm1.weight.detach(), blk.norm1.bias.detach()), n2=(blk.norm2.weight.detach(), blk.norm2.bias.detach()))
+            mix = {}
+            for name, m in lin.items():
+                w2 = m.weight.detach().reshape(m.weight.shape[0], -1).contiguous()
+                ok = self.mixed
+                if ok and not bool(w2.abs().max() < 3.5):           # build time, once: e4m3(w * 2^7) would saturate (or w is not finite)
+                    ok = False
+                    self.saturation_events.append(f"blocks.{li}.{name}: weight max |w| >= 3.5")
+                mix[name] = ok
+                entry[name] = [ops.split_planes_mix(w2, weight=True) if ok else ops.split_planes(w2), m.bias.detach(), m]
+            self.blocks.append(entry)
+            self.mix.append(mix)
+        # range guard of the activation producers: one int32 word per site, bit l = block l
+        if d.L > 31:
+            raise NotImplementedError("the mixed-format range guard keeps one flag bit per block: depth <= 31")
+        self.sat = torch.zeros(len(self.SITES), dtype=torch.int32, device=dev)
+        self._sat_of = [self.sat[i:i + 1] for i in range(len(self.SITES))]
+        self._sat_host = torch.zeros(len(self.SITES), dtype=torch.int32).pin_memory()
+        self._sat_event = torch.cuda.Event()
+        self._sat_pending = False
+        self._bb_init(dev, d)
+        add = self._bb_add
+        add("img_planes", lambda d: (2, d.B * d.P, d.Kc), bf)
+        add("p_raw", lambda d: (d.B * d.P, d.D))
+        add("x", lambda d: (d.M, d.D), count=2)
+        add("hp", lambda d: (2, d.M, d.D), bf)
+        add("qkvp", lambda d: (2, d.M, 3 * d.D), bf)
+        add("op", lambda d: (2, d.M, d.D), bf)
+        add("y", lambda d: (d.M, d.D))
+        add("fp", lambda d: (2, d.M, d.F), bf)
+        add("xn", lambda d: (d.B, d.D))
+        add("logits", lambda d: (d.B, d.C))
+
+    # ---- range guard ------------------------------------------------------------------------------
+    def _demote(self, li: int, site: str, why: str) -> None:
+        """Linear `site` of block li leaves the mixed format: weight re-split as bf16 hi/lo planes, producers follow self.mix."""
+        if not self.mix[li][site]:
+            return
+        import warnings
+        ent = self.blocks[li][site]
+        m = ent[2]
+        ent[0] = ops.split_planes(m.weight.detach().reshape(m.weight.shape[0], -1).contiguous())
+        self.mix[li][site] = False
+        msg = f"blocks.{li}.{site}: {why}"
+        self.saturation_events.append(msg)
+        warnings.warn("qatvit_b200 teacher: " + msg + " -- this Linear now runs on bf16 hi/lo planes (three MMA passes)", RuntimeWarning)
+
+    def _apply_flags(self, words) -> bool:
+        hit = False
+        for si, site in enumerate(self.SITES):
+            w = int(words[si])
+            for li in range(self.d.L):
+                if w >> li & 1 and self.mix[li][site]:
+                    self._demote(li, site, "activation |x| > 448 (outside the mixed fp16 + fp8 format)")
+                    hit = True
+        return hit
+
+    def poll_saturation(self, wait: bool = False) -> bool:
+        """Look at the flags of the last forward whose copy has arrived (wait=True: synchronise on it).  True if a Linear was
+        demoted.  Called at the start of every forward; never blocks unless asked to."""
+        if not self._sat_pending:
+            return False
+        if wait:
+            self._sat_event.synchronize()
+        elif not self._sat_event.query():
+            return False
+        self._sat_pending = False
+        words = self._sat_host.tolist()
+        if not any(words):
+            return False
+        hit = self._apply_flags(words)
+        ops.zero_(self.sat)
+        return hit
+
+    @torch.no_grad()
+    def calibrate(self, images: torch.Tensor, max_rounds: int = 4) -> List[str]:
+        """Run the forward on `images` until no activation leaves the mixed format (each round demotes the Linears whose input
+        saturated).  Synchronises; call once before training.  Returns saturation_events."""
+        for _ in range(max_rounds):
+            self.forward(images)
+            if not self.poll_saturation(wait=True):
+                break
+        return self.saturation_events
 
     @torch.no_grad()
     def forward(self, images: torch.Tensor) -> torch.Tensor:
-        d, v = self.d, self.vit
+        v = self.vit
+        b = self._bb_check(images, "teacher")
+        self._bb_bind(b)
+        self.poll_saturation()
+        d = self.d
         B, T, D, F, M = d.B, d.T, d.D, d.F, d.M
-        mx = self.mixed
-        if tuple(images.shape) != (B, d.in_ch, d.HW, d.HW):
-            raise RuntimeError(f"teacher engine built for batch {B}, got {tuple(images.shape)}")
+        any_mix = False
         ops.im2col_fq(images, None, B, d.in_ch, d.HW, d.ps, self.img_planes)
         ops.gemm(Op.full(self.img_planes), Op.full(self.w_conv), B * d.P, D, d.Kc, PAIRS_FP32, out=self.p_raw,
                  bias=v.patch_embed.proj.bias.detach())
@@ -250,37 +431,46 @@ class TeacherEngine:
         cur = 0
         x_in, y_prev = self.x[0], None
         for li, blk in enumerate(self.blocks):
-            g, b = blk["n1"]
+            mx, bit = self.mix[li], 1 << li
+            any_mix = any_mix or any(mx.values())
+            g, b_ = blk["n1"]
             if li == 0:
-                ops.resid_ln_fwd(x_in, None, None, g, b, d.eps, M, D, h_planes=self.hp, planes_mix=mx)
+                ops.resid_ln_fwd(x_in, None, None, g, b_, d.eps, M, D, h_planes=self.hp, planes_mix=mx["qkv"], sat=(self._sat_of[0], bit))
             else:
-                ops.resid_ln_fwd(x_in, y_prev, None, g, b, d.eps, M, D, x_out=self.x[cur ^ 1], h_planes=self.hp, planes_mix=mx)
+                ops.resid_ln_fwd(x_in, y_prev, None, g, b_, d.eps, M, D, x_out=self.x[cur ^ 1], h_planes=self.hp,
+                                 planes_mix=mx["qkv"], sat=(self._sat_of[0], bit))
                 cur ^= 1
                 x_in = self.x[cur]
-            w, bias = blk["qkv"]
+            w, bias, _ = blk["qkv"]
             # no observer sits between the teacher's Linears: epilogues emit the next operand's bf16 planes directly
-            ops.gemm(Op.full(self.hp), Op.full(w), M, 3 * D, D, PAIRS_FP32, bias=bias, out_planes=self.qkvp, mix=mx)
+            ops.gemm(Op.full(self.hp), Op.full(w), M, 3 * D, D, PAIRS_FP32, bias=bias, out_planes=self.qkvp, mix=mx["qkv"])
             # fused softmax attention (bf16 hi/lo q, k, v): scores / probabilities stay in tensor memory, output lands as proj's
             # A operand
-            ops.attn_fwd(self.qkvp, B, T, d.H, d.attn_scale, self.op, out_mix=mx)
-            w, bias = blk["proj"]
-            ops.gemm(Op.full(self.op), Op.full(w), M, D, D, PAIRS_FP32, out=self.y, bias=bias, mix=mx)
-            g, b = blk["n2"]
-            ops.resid_ln_fwd(x_in, self.y, None, g, b, d.eps, M, D, x_out=self.x[cur ^ 1], h_planes=self.hp, planes_mix=mx)
+            ops.attn_fwd(self.qkvp, B, T, d.H, d.attn_scale, self.op, out_mix=mx["proj"], sat=(self._sat_of[1], bit))
+            w, bias, _ = blk["proj"]
+            ops.gemm(Op.full(self.op), Op.full(w), M, D, D, PAIRS_FP32, out=self.y, bias=bias, mix=mx["proj"])
+            g, b_ = blk["n2"]
+            ops.resid_ln_fwd(x_in, self.y, None, g, b_, d.eps, M, D, x_out=self.x[cur ^ 1], h_planes=self.hp, planes_mix=mx["fc1"],
+                             sat=(self._sat_of[2], bit))
             cur ^= 1
             x_in = self.x[cur]
-            w, bias = blk["fc1"]
-            ops.gemm(Op.full(self.hp), Op.full(w), M, F, D, PAIRS_FP32, bias=bias, out_planes=self.fp, gelu=True, mix=mx, out_mix=mx)
-            w, bias = blk["fc2"]
-            ops.gemm(Op.full(self.fp), Op.full(w), M, D, F, PAIRS_FP32, out=self.y, bias=bias, mix=mx)
+            w, bias, _ = blk["fc1"]
+            ops.gemm(Op.full(self.hp), Op.full(w), M, F, D, PAIRS_FP32, bias=bias, out_planes=self.fp, gelu=True, mix=mx["fc1"],
+                     out_mix=mx["fc2"], sat=(self._sat_of[3], bit))
+            w, bias, _ = blk["fc2"]
+            ops.gemm(Op.full(self.fp), Op.full(w), M, D, F, PAIRS_FP32, out=self.y, bias=bias, mix=mx["fc2"])
             y_prev = self.y
         ops.resid_ln_fwd(x_in, y_prev, None, v.norm.weight.detach(), v.norm.bias.detach(), d.eps, B, D, in_row_stride=T,
                          h_f32=self.xn)
         ops.head_fwd(self.xn, v.head.weight.detach(), v.head.bias.detach(), B, D, d.C, self.logits)
+        if any_mix and not self._sat_pending:
+            self._sat_host.copy_(self.sat, non_blocking=True)     # 16 bytes D2H on this stream; read when the next forward starts
+            self._sat_event.record()
+            self._sat_pending = True
         return self.logits
 
 
-class StudentEngine:
+class StudentEngine(_BatchBuffers):
     """Forward + hand-written backward of the prepared (torch.ao eager-mode QAT) ``QATWrapper`` student."""
 
     def __init__(self, student: nn.Module, batch: int, hparams: Dict, grad_buffer: Optional[torch.Tensor] = None,
@@ -339,8 +529,6 @@ class StudentEngine:
             for blk in vit.blocks:
                 self.ln_fq += [FQRef(blk.norm1.activation_post_process), FQRef(blk.norm2.activation_post_process)]
             self.ln_fq.append(FQRef(vit.norm.activation_post_process))
-            if not all(int(f.fake_quant_enabled.item()) != 0 for f in self.ln_fq):
-                raise NotImplementedError("observed LayerNorm with fake-quant disabled is not on the fused path")
 
         # ---- flat gradient arena (the buffer a DDP-style all-reduce runs over) ----
         self.params = [p for p in student.parameters() if p.requires_grad]
@@ -368,10 +556,20 @@ class StudentEngine:
 
         # Fused attention works on the integer codes of the fake-quantised q, k, v (FQ(x) = code * scale): one exact bf16
         # plane instead of hi/lo planes, scores never leave tensor memory, backward recomputes P from the saved logsumexp.
-        # It needs fake-quant to be ON for every qkv output observer (the reference never turns it off); the flags are read
-        # once here -- if any is off, fall back to the unfused hi/lo-plane kernels.
+        # fused_attention=False keeps the unfused batched-GEMM kernels (scores / probabilities as planes in HBM): the parity
+        # reference for the fused ones.
+        # Every consumer applies the producer's fake-quant ON LOAD and every GEMM consumes weight CODES: that is the arithmetic of
+        # fake_quant_enabled == 1, the only state the reference ever runs in (it never calls disable_fake_quant).  The flags are
+        # read once here; a model with fake-quant switched off on any module is refused instead of silently computing
+        # something else (the module-level install() path honours the flags per call).
+        fq_off = [n for n, m in student.named_modules() if hasattr(m, "fake_quant_enabled") and hasattr(m, "observer_enabled")
+                  and int(m.fake_quant_enabled.item()) == 0]
+        if fq_off:
+            raise NotImplementedError("qatvit_b200: fake-quant is disabled on " + ", ".join(fq_off[:4]) + (" ..." if len(fq_off) > 4 else "")
+                                      + ": the fused engine implements fake_quant_enabled == 1 only (use qatvit_b200.dropin.install() "
+                                      "for models with fake-quant switched off)")
         if fused_attention is None:
-            fused_attention = all(int(ql["qkv"].afq.fake_quant_enabled.item()) != 0 for ql in self.lin)
+            fused_attention = True
         self.fused_attn = bool(fused_attention)
         # The backward prologue of every block Linear (gradient x STE mask of its output fake-quant [x gelu'] x weight scale ->
         # bf16 planes, bias-grad partial sums; qv_gp_planes) runs inside the kernel that PRODUCES the gradient: the fc2 dgrad
@@ -383,78 +581,99 @@ class StudentEngine:
         self._w_ready = {k: torch.cuda.Event() for k in ("fc2", "fc1", "proj", "qkv", "conv")}
         self._w_done = {k: torch.cuda.Event() for k in ("fc2", "fc1", "proj", "qkv", "conv")}
         self._w_pending = set()
+        self._pub_event = torch.cuda.Event()
 
-        # ---- forward activations (saved for backward) ----
-        self.img_codes = e(1, B * d.P, d.Kc, dt=bf)
-        self.p_raw = e(B * d.P, D)
-        self.x_in = [e(M, D) for _ in range(L)]
-        self.x_mid = [e(M, D) for _ in range(L)]
+        # ---- forward activations (saved for backward) and backward scratch: registered with _BatchBuffers so that a smaller
+        #      batch (the ragged tail of an epoch) re-views the same storage ----
+        self._bb_init(dev, d)
+        add = self._bb_add
+        lo, fa, fgp = self.ln_obs, self.fused_attn, self.fused_gp
+        add("img_codes", lambda d: (1, d.B * d.P, d.Kc), bf)
+        add("p_raw", lambda d: (d.B * d.P, d.D))
+        add("x_in", lambda d: (d.M, d.D), count=L)
+        add("x_mid", lambda d: (d.M, d.D), count=L)
         # A operand of qkv / fc1: LayerNorm output as hi/lo planes, or (observed LN) one plane of codes + the raw output
-        npl = 1 if self.ln_obs else 2
-        self.h1p = [e(npl, M, D, dt=bf) for _ in range(L)]
-        self.h2p = [e(npl, M, D, dt=bf) for _ in range(L)]
-        if self.ln_obs:
-            self.h1_raw = [e(M, D) for _ in range(L)]
-            self.h2_raw = [e(M, D) for _ in range(L)]
-            self.hN_raw = e(M, D)
-            self.xn_raw = e(B, D)
-            self.xn_mask = e(B, D, dt=torch.uint8)
-        self.qkv_raw = [e(M, 3 * D) for _ in range(L)]
-        if self.fused_attn:
-            self.qkvc = [e(1, M, 3 * D, dt=bf) for _ in range(L)]
-            self.lse = [e(B * d.H * T) for _ in range(L)]
+        npl = 1 if lo else 2
+        add("h1p", lambda d: (npl, d.M, d.D), bf, count=L)
+        add("h2p", lambda d: (npl, d.M, d.D), bf, count=L)
+        if lo:
+            add("h1_raw", lambda d: (d.M, d.D), count=L)
+            add("h2_raw", lambda d: (d.M, d.D), count=L)
+            add("hN_raw", lambda d: (d.M, d.D))
+            add("xn_raw", lambda d: (d.B, d.D))
+            add("xn_mask", lambda d: (d.B, d.D), torch.uint8)
+        add("qkv_raw", lambda d: (d.M, 3 * d.D), count=L)
+        if fa:
+            add("qkvc", lambda d: (1, d.M, 3 * d.D), bf, count=L)
+            add("lse", lambda d: (d.B * d.H * d.T,), count=L)
         else:
-            self.qkvp = [e(2, M, 3 * D, dt=bf) for _ in range(L)]
-            self.Pp = [torch.zeros(2, B * d.H * T, d.ldP, dtype=bf, device=dev) for _ in range(L)]
-        self.op = [e(2, M, D, dt=bf) for _ in range(L)]
-        self.a_raw = [e(M, D) for _ in range(L)]
-        self.f_raw = [e(M, F) for _ in range(L)]
-        self.gelp = [e(2, M, F, dt=bf) for _ in range(L)]
-        self.m_raw = [e(M, D) for _ in range(L)]
-        self.stats1 = [(e(M), e(M)) for _ in range(L)]
-        self.stats2 = [(e(M), e(M)) for _ in range(L)]
-        if not self.fused_attn:
-            self.S = e(B * d.H * T, d.ldS)
-            self.o = e(M, D)
-        self.xcls = e(B, D)
-        self.xn = e(B, D)
-        self.statsF = (e(B), e(B))
-        self.logits_raw = e(B, d.C)
+            add("qkvp", lambda d: (2, d.M, 3 * d.D), bf, count=L)
+            add("Pp", lambda d: (2, d.B * d.H * d.T, d.ldP), bf, count=L, zero=True)
+        add("op", lambda d: (2, d.M, d.D), bf, count=L)
+        add("a_raw", lambda d: (d.M, d.D), count=L)
+        add("f_raw", lambda d: (d.M, d.F), count=L)
+        add("gelp", lambda d: (2, d.M, d.F), bf, count=L)
+        add("m_raw", lambda d: (d.M, d.D), count=L)
+        for nm in ("st1m", "st1r", "st2m", "st2r"):       # LayerNorm mean / rstd per row (norm1, norm2)
+            add(nm, lambda d: (d.M,), count=L)
+        if not fa:
+            add("S", lambda d: (d.B * d.H * d.T, d.ldS))
+            add("o", lambda d: (d.M, d.D))
+        add("xcls", lambda d: (d.B, d.D))
+        add("xn", lambda d: (d.B, d.D))
+        add("stFm", lambda d: (d.B,))
+        add("stFr", lambda d: (d.B,))
+        add("logits_raw", lambda d: (d.B, d.C))
+        add("g_logits", lambda d: (d.B, d.C))
         self.loss3 = e(3)
-        self.g_logits = e(B, d.C)
 
         # ---- backward scratch ----
-        self.gx = [e(M, D), e(M, D)]
-        self.g_xn = e(B, D)
-        self.gpD = e(2, M, D, dt=bf)         # fc2's gradient planes
-        self.gpDp = e(2, M, D, dt=bf)        # proj's (separate, so a weight-gradient GEMM on the side stream can still read one
-        self.gpF = e(2, M, F, dt=bf)         #         while the main chain already writes the other)
-        self.gp3 = e(2, M, 3 * D, dt=bf)
-        self.gpP = e(2, B * d.P, D, dt=bf)
-        if not self.fused_gp:
-            self.g_big = e(M, F)
-        self.g_h = e(M, D)
-        self.g_op = e(2, M, D, dt=bf)
-        if not (self.fused_gp and self.fused_attn):
-            self.g_qkv = e(M, 3 * D)
-        if not self.fused_attn:
-            self.g_o = e(M, D)
-            self.dP = e(B * d.H * T, d.ldS)
-            self.dSp = torch.zeros(2, B * d.H * T, d.ldP, dtype=bf, device=dev)
+        add("gx", lambda d: (d.M, d.D), count=2)
+        add("g_xn", lambda d: (d.B, d.D))
+        add("gpD", lambda d: (2, d.M, d.D), bf)          # fc2's gradient planes
+        add("gpDp", lambda d: (2, d.M, d.D), bf)         # proj's (separate, so a weight-gradient GEMM on the side stream can still
+        add("gpF", lambda d: (2, d.M, d.F), bf)          #         read one while the main chain already writes the other)
+        add("gp3", lambda d: (2, d.M, 3 * d.D), bf)
+        add("gpP", lambda d: (2, d.B * d.P, d.D), bf)
+        if not fgp:
+            add("g_big", lambda d: (d.M, d.F))
+        add("g_h", lambda d: (d.M, d.D))
+        add("g_op", lambda d: (2, d.M, d.D), bf)
+        if not (fgp and fa):
+            add("g_qkv", lambda d: (d.M, 3 * d.D))
+        if not fa:
+            add("g_o", lambda d: (d.M, d.D))
+            add("dP", lambda d: (d.B * d.H * d.T, d.ldS))
+            add("dSp", lambda d: (2, d.B * d.H * d.T, d.ldP), bf, zero=True)
         import os
         self.rpb_gp = 64
         self.rpb_ln = int(os.environ.get("QV_RPB_LN", "64"))
         # bias-grad partial sums: standalone gp_planes [M/64][N]; GEMM epilogue [M/32][F]; attention backward [B*mt*4][3D]
-        self.slabs_attn = B * (-(-T // 128)) * 4
-        self.bias_part = e(max(-(-M // self.rpb_gp) * max(F, 3 * D), -(-M // 32) * F, self.slabs_attn * 3 * D))
+        # (sized for the construction batch; a smaller batch uses a prefix)
+        slabs_full = B * (-(-T // 128)) * 4
+        self.bias_part = e(max(-(-M // self.rpb_gp) * max(F, 3 * D), -(-M // 32) * F, slabs_full * 3 * D))
         self.ln_part = e(-(-M // self.rpb_ln), 2, D)
-        max_ws = 0
-        self._splits = {}
-        for (n, k, kdim) in [(3 * D, D, M), (D, D, M), (F, D, M), (D, F, M), (D, d.Kc, B * d.P)]:
-            s = wgrad_splits(n, k, kdim, self.sms)
-            self._splits[(n, k)] = s
-            max_ws = max(max_ws, s * n * k)
+        # split-K factors of the weight-gradient GEMMs depend on the token count: one table per batch size 1..B, and a
+        # workspace that holds the largest of them (so that b images on an engine built for B split exactly like an engine
+        # built for b -- bit-identical sums)
+        self._splits_by_b, max_ws = {}, 0
+        for bb in range(1, B + 1):
+            tab = {}
+            for (n, k, kdim) in [(3 * D, D, bb * T), (D, D, bb * T), (F, D, bb * T), (D, F, bb * T), (D, d.Kc, bb * d.P)]:
+                sp = wgrad_splits(n, k, kdim, self.sms)
+                tab[(n, k)] = sp
+                max_ws = max(max_ws, sp * n * k)
+            self._splits_by_b[bb] = tab
         self.ws = e(max_ws)
+        self._bb_on_bind(B)
+
+    def _bb_on_bind(self, b: int) -> None:
+        d = self.d
+        self._splits = self._splits_by_b[b]
+        self.slabs_attn = b * (-(-d.T // 128)) * 4
+        self.stats1 = list(zip(self.st1m, self.st1r))
+        self.stats2 = list(zip(self.st2m, self.st2r))
+        self.statsF = (self.stFm, self.stFr)
 
     # ------------------------------------------------------------------------------------------
     def attach_grads(self) -> None:
@@ -541,10 +760,13 @@ class StudentEngine:
                 teacher_ready=None) -> Optional[torch.Tensor]:
         """teacher_ready: optional CUDA event; the current stream waits for it right before the loss (the teacher forward may
         then run concurrently on another stream).  labels = None: stop after the head (predict)."""
+        self._bb_bind(self._bb_check(images, "student"))          # any batch 1..B: the ragged tail of an epoch re-views the buffers
         d, v = self.d, self.vit
         B, T, D, F, M, L = d.B, d.T, d.D, d.F, d.M, d.L
-        if tuple(images.shape) != (B, d.in_ch, d.HW, d.HW):
-            raise RuntimeError(f"student engine built for batch {B}, got {tuple(images.shape)}")
+        if labels is not None and (labels.dim() != 1 or labels.shape[0] != B):
+            raise RuntimeError(f"labels must be a [batch] int64 tensor matching the {B} images, got {tuple(labels.shape)}")
+        if teacher_logits is not None and tuple(teacher_logits.shape) != (B, d.C):
+            raise RuntimeError(f"teacher logits must be [{B}, {d.C}], got {tuple(teacher_logits.shape)}")
         ops.minmax_reset(self.acc)
         self.quantize_weights()
         # input fake-quant (QuantStub hook) fused into im2col; patch-embed conv as an exact-integer GEMM
@@ -627,6 +849,20 @@ class StudentEngine:
             torch.cuda.current_stream().wait_event(self._w_done[key])
             self._w_pending.discard(key)
 
+    def _publish(self, grads_final_from, lo: int) -> None:
+        """Every gradient with arena offset >= lo has been ENQUEUED: hand the suffix to the exchange (ddp.GradSync) without making
+        the main chain wait for the weight-gradient side stream.  The collective is issued from the side stream's context after
+        that stream has caught up with the main one (bias / LayerNorm gradients are written there), so it is ordered after both,
+        while the main stream runs on into the next block."""
+        ws = self._wstream
+        if ws is None or not self._w_pending:
+            return grads_final_from(lo)
+        main = torch.cuda.current_stream()
+        self._pub_event.record(main)
+        with torch.cuda.stream(ws):
+            ws.wait_event(self._pub_event)
+            grads_final_from(lo)
+
     def _w_join(self) -> None:
         """Every weight gradient issued so far is complete (before gradients are declared final / the optimizer runs)."""
         if self._w_pending:
@@ -666,7 +902,7 @@ class StudentEngine:
         if self.ln_obs:     # STE mask of the final norm's output fake-quant
             ops.fq_bwd(self.g_xn, self.xn_mask, gx=self.g_xn)
         gx, gx2 = self.gx
-        gx.zero_()
+        ops.zero_(gx)                  # only the cls rows carry a gradient out of the final norm (x[:, 0]); the rest is zero
         nblk_ln = -(-B // self.rpb_ln)
         ops.ln_bwd(self.g_xn, self.xcls, self.statsF[0], self.statsF[1], v.norm.weight.detach(), None, B, D, gx, self.ln_part,
                    self.rpb_ln, out_row_stride=T)
@@ -768,8 +1004,7 @@ class StudentEngine:
             if gp_fc2 is not None:
                 ops.colsum_reduce(part, nblk_gp, D, self._grad(self.lin[l - 1]["fc2"].bias))
             if grads_final_from is not None:
-                self._w_join()
-                grads_final_from(self._block_lo[l])
+                self._publish(grads_final_from, self._block_lo[l])
         # ---- embeddings: pos_embed, cls_token, patch-embed conv ----
         ops.colsum_rows(gx, B, T * D, T * D, self._grad(v.pos_embed))
         ops.colsum_rows(gx, B, D, T * D, self._grad(v.cls_token))
@@ -803,6 +1038,9 @@ class QATDistillStep:
 
     def __call__(self, images: torch.Tensor, labels: torch.Tensor, grad_sync=None) -> torch.Tensor:
         """grad_sync: a ddp.GradSync whose buffer holds the gradient arena -- its all-reduce then overlaps the backward."""
+        # optimizer.zero_grad(set_to_none=True) -- every iteration of the reference loop, ref qat_trainer.py:351 -- drops the
+        # .grad views into the arena: put them back (152 pointer assignments, no launch, no sync)
+        self.student_engine.attach_grads()
         if self.overlap_teacher and not ops.profiling():
             main = torch.cuda.current_stream()
             self._tstream.wait_stream(main)                      # images are ready; the previous step's loss has read the logits

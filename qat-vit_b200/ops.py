@@ -71,7 +71,7 @@ def fq_apply(x, scale, zero_point, fake_quant_enabled, qmin, qmax, y=None, mask=
 
 
 def fq_weight(w, per_channel, observer_enabled, fake_quant_enabled, min_val, max_val, scale, zero_point,
-              averaging_const, qmin, qmax, symmetric, y=None, mask=None, codes=None, codes_t=None, scratch=None):
+              averaging_const, qmin, qmax, symmetric, y=None, mask=None, codes=None, codes_t=None, scratch=None, scale_vec=None):
     rows = w.shape[0]
     cols = w.numel() // rows
     check(_lib.lib().qv_fq_weight(_p(w, torch.float32, "w"), rows, cols, int(bool(per_channel)),
@@ -81,7 +81,8 @@ def fq_weight(w, per_channel, observer_enabled, fake_quant_enabled, min_val, max
                                   float(averaging_const), int(qmin), int(qmax), int(bool(symmetric)),
                                   _p(y, torch.float32, "y"), _p(mask, torch.uint8, "mask"),
                                   _p(codes, torch.bfloat16, "codes"), _p(codes_t, torch.bfloat16, "codes_t"),
-                                  _p(scratch, torch.int32, "scratch"), _stream()), "fq_weight")
+                                  _p(scratch, torch.int32, "scratch"), _p(scale_vec, torch.float32, "scale_vec"), _stream()),
+          "fq_weight")
 
 
 FQW_ROWS = 16      # output channels per block of qv_fq_weight_grouped (csrc/fakequant.cu)
@@ -252,7 +253,7 @@ PAIRS_FP32 = (2, 2)          # both fp32 as hi/lo: A0*B0 + A0*B1 + A1*B0 (lo*lo 
 def gemm(a: Op, b: Op, M: int, N: int, K: int, planes: Tuple[int, int], *, out=None, col_scale=None, col_rscale=None,
          alpha=None, bias=None, minmax=None, splits: int = 1, workspace: Optional[torch.Tensor] = None, nbatch: int = 1,
          batch_inner: int = 1, tile_n: int = 0, out_planes: Optional[torch.Tensor] = None, gelu: bool = False,
-         grad_of=None, observer=None, mix: bool = False, out_mix: bool = False):
+         grad_of=None, observer=None, mix: bool = False, out_mix: bool = False, sat=None):
     """D[M,N] = sum_pairs A[pa] @ B[pb]^T on tcgen05 (include/qatvit_b200.h: qv_gemm_bf16).
     mix: both operands are in the mixed fp16 + fp8 format (split_planes_mix / out_mix producers); out_mix: out_planes is
     written in the mixed activation format instead of bf16 hi/lo.
@@ -313,6 +314,9 @@ def gemm(a: Op, b: Op, M: int, N: int, K: int, planes: Tuple[int, int], *, out=N
     args.nbatch, args.batch_inner = nbatch, batch_inner
     args.tile_n = tile_n
     args.mix = int(bool(mix))
+    if sat is not None and out_mix:
+        sat_p, args.sat_bit = _sat(sat)
+        args.sat_flag = sat_p.value
     check(_lib.lib().qv_gemm_bf16(ctypes.byref(args), _stream()), "gemm_bf16")
     return ret
 
@@ -333,17 +337,34 @@ def gemm_pair_launches() -> int:
     return int(_lib.lib().qv_gemm_pair_launches())
 
 
+def _sat(sat):
+    """(flag tensor int32[1], bit) -> ctypes pair for the mixed-format range guard; None -> (NULL, 0)."""
+    if sat is None:
+        return _NULL, 0
+    flag, bit = sat
+    if flag.dtype != torch.int32 or not flag.is_cuda or flag.numel() != 1:
+        raise RuntimeError("qatvit_b200: the saturation flag must be a CUDA int32 scalar")
+    return ctypes.c_void_p(flag.data_ptr()), int(bit)
+
+
+def zero_(t: torch.Tensor) -> torch.Tensor:
+    """Stream-ordered clear of a contiguous CUDA tensor (qv_zero)."""
+    check(_lib.lib().qv_zero(_p(t, None, "tensor"), t.numel() * t.element_size(), _stream()), "zero")
+    return t
+
+
 def resid_ln_fwd(x_in, y_raw, fq, gamma, beta, eps, R, D, *, in_row_stride=1, x_out=None, h_planes=None, h_f32=None,
-                 mean=None, rstd=None, minmax=None, planes_mix=False):
+                 mean=None, rstd=None, minmax=None, planes_mix=False, sat=None):
     """x_out = x_in + FQ(y_raw); h = LN(x_out).  fq = (scale, zero_point, qmin, qmax) or None.
-    planes_mix: h_planes in the mixed fp16 + fp8 operand format instead of bf16 hi/lo."""
+    planes_mix: h_planes in the mixed fp16 + fp8 operand format instead of bf16 hi/lo; sat = (flag, bit): its range guard."""
     sc, zp, qmin, qmax = fq if fq is not None else (None, None, 0, 0)
+    sat_p, sat_b = _sat(sat if planes_mix else None)
     check(_lib.lib().qv_resid_ln_fwd(_p(x_in, torch.float32), _p(y_raw, torch.float32), _p(sc, torch.float32),
                                      _p(zp, torch.int32), qmin, qmax, _p(gamma, torch.float32), _p(beta, torch.float32),
                                      float(eps), R, D, in_row_stride, _p(x_out, torch.float32),
                                      _p(h_planes, torch.bfloat16), 0 if h_planes is None else h_planes.stride(0),
                                      _p(h_f32, torch.float32), _p(mean, torch.float32), _p(rstd, torch.float32),
-                                     _p(minmax, torch.int32), int(bool(planes_mix)), _stream()), "resid_ln_fwd")
+                                     _p(minmax, torch.int32), int(bool(planes_mix)), sat_p, sat_b, _stream()), "resid_ln_fwd")
 
 
 def ln_bwd(g_h, x, mean, rstd, gamma, g_res, R, D, g_x, partials, rows_per_block, out_row_stride=1, h_raw=None, h_fq=None,
@@ -426,17 +447,19 @@ def attn_ds(P_planes, dP, lddP, rows, T, scale, dS_planes):
                                 dS_planes.stride(1), dS_planes.stride(0), _stream()), "attn_ds")
 
 
-def attn_fwd(qkv_planes, B, T, H, scale, out_planes, qk_scale=None, v_scale=None, lse=None, out_f32=None, out_mix=False):
+def attn_fwd(qkv_planes, B, T, H, scale, out_planes, qk_scale=None, v_scale=None, lse=None, out_f32=None, out_mix=False,
+             sat=None):
     """Fused softmax(Q K^T * scale) V per (image, head): qkv_planes bf16 [1 or 2, B*T, 3*H*64] -> out_planes bf16
     [2, B*T, H*64] (include/qatvit_b200.h: qv_attn_fwd)."""
     if qkv_planes.dim() != 3 or qkv_planes.stride(2) != 1 or (out_planes is not None and (out_planes.dim() != 3 or out_planes.stride(2) != 1)):
         raise RuntimeError("qatvit_b200: attn_fwd takes [planes, tokens, cols] plane stacks")
     ops_, opl = (out_planes.stride(0), out_planes.stride(1)) if out_planes is not None else (0, 0)
+    sat_p, sat_b = _sat(sat if out_mix else None)
     check(_lib.lib().qv_attn_fwd(_p(qkv_planes, torch.bfloat16, "qkv_planes"), qkv_planes.shape[0], qkv_planes.stride(0),
                                  qkv_planes.stride(1), B, T, H, float(scale), _p(qk_scale, torch.float32),
                                  _p(v_scale, torch.float32), _p(out_planes, torch.bfloat16, "out_planes"), ops_, opl,
-                                 _p(out_f32, torch.float32, "out_f32"), _p(lse, torch.float32), int(bool(out_mix)), _stream()),
-          "attn_fwd")
+                                 _p(out_f32, torch.float32, "out_f32"), _p(lse, torch.float32), int(bool(out_mix)), sat_p, sat_b,
+                                 _stream()), "attn_fwd")
     return out_planes if out_planes is not None else out_f32
 
 
@@ -589,7 +612,7 @@ def _wrap(name, fn, tag_fn=None):
     return inner
 
 
-for _nm in ("minmax_reset", "minmax_accumulate", "obs_update", "fq_apply", "fq_weight", "fq_weight_grouped", "fq_bwd", "split_planes",
+for _nm in ("zero_", "minmax_reset", "minmax_accumulate", "obs_update", "fq_apply", "fq_weight", "fq_weight_grouped", "fq_bwd", "split_planes",
            "kd_ce_loss", "splitk_reduce", "colsum_reduce", "colsum_rows",
            "embed_fwd", "im2col_fq", "softmax_planes", "attn_ds", "head_fwd", "head_bwd", "attn_fwd", "attn_bwd", "attn_bwd_gp",
            "int8_linear", "quantize_u8", "qparams_from_minmax", "im2col_u8", "gelu_minmax"):

@@ -18,7 +18,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .engine import TeacherEngine, _ViTDims, _attention_forward, _round_up, wgrad_splits
+from .engine import TeacherEngine, _BatchBuffers, _ViTDims, _attention_forward, wgrad_splits
 from .ops import Op, Out, PAIRS_FP32
 
 
@@ -36,7 +36,7 @@ class _Lin:
         ops.split_planes(self.weight.detach().reshape(self.N, self.K), self.planes)
 
 
-class PlainStudentEngine:
+class PlainStudentEngine(_BatchBuffers):
     """Forward + hand-written backward of the unprepared ``QATWrapper`` student (no fake-quant anywhere)."""
 
     def __init__(self, student: nn.Module, batch: int, hparams: Dict, grad_buffer: Optional[torch.Tensor] = None):
@@ -74,52 +74,67 @@ class PlainStudentEngine:
             self._goff[id(p)] = off
             off += p.numel()
         self.attach_grads()
-        # ---- forward activations (saved for backward) ----
-        self.img_planes = e(2, B * d.P, d.Kc, dt=bf)
-        self.p_raw = e(B * d.P, D)
-        self.x_in = [e(M, D) for _ in range(L)]
-        self.x_mid = [e(M, D) for _ in range(L)]
-        self.h1p = [e(2, M, D, dt=bf) for _ in range(L)]
-        self.h2p = [e(2, M, D, dt=bf) for _ in range(L)]
-        self.qkvp = [e(2, M, 3 * D, dt=bf) for _ in range(L)]
-        self.Pp = [torch.zeros(2, B * d.H * T, d.ldP, dtype=bf, device=dev) for _ in range(L)]
-        self.op = [e(2, M, D, dt=bf) for _ in range(L)]
-        self.a_raw = e(M, D)
-        self.f_raw = [e(M, F) for _ in range(L)]
-        self.gelp = [e(2, M, F, dt=bf) for _ in range(L)]
-        self.m_raw = e(M, D)
-        self.stats1 = [(e(M), e(M)) for _ in range(L)]
-        self.stats2 = [(e(M), e(M)) for _ in range(L)]
-        self.S = e(B * d.H * T, d.ldS)
-        self.o = e(M, D)
-        self.xcls, self.xn = e(B, D), e(B, D)
-        self.statsF = (e(B), e(B))
-        self.logits = e(B, d.C)
+        # ---- forward activations (saved for backward) and backward scratch (re-viewed for a smaller batch: engine._BatchBuffers) ----
+        self._bb_init(dev, d)
+        add = self._bb_add
+        add("img_planes", lambda d: (2, d.B * d.P, d.Kc), bf)
+        add("p_raw", lambda d: (d.B * d.P, d.D))
+        add("x_in", lambda d: (d.M, d.D), count=L)
+        add("x_mid", lambda d: (d.M, d.D), count=L)
+        add("h1p", lambda d: (2, d.M, d.D), bf, count=L)
+        add("h2p", lambda d: (2, d.M, d.D), bf, count=L)
+        add("qkvp", lambda d: (2, d.M, 3 * d.D), bf, count=L)
+        add("Pp", lambda d: (2, d.B * d.H * d.T, d.ldP), bf, count=L, zero=True)
+        add("op", lambda d: (2, d.M, d.D), bf, count=L)
+        add("a_raw", lambda d: (d.M, d.D))
+        add("f_raw", lambda d: (d.M, d.F), count=L)
+        add("gelp", lambda d: (2, d.M, d.F), bf, count=L)
+        add("m_raw", lambda d: (d.M, d.D))
+        for nm in ("st1m", "st1r", "st2m", "st2r"):
+            add(nm, lambda d: (d.M,), count=L)
+        add("S", lambda d: (d.B * d.H * d.T, d.ldS))
+        add("o", lambda d: (d.M, d.D))
+        add("xcls", lambda d: (d.B, d.D))
+        add("xn", lambda d: (d.B, d.D))
+        add("stFm", lambda d: (d.B,))
+        add("stFr", lambda d: (d.B,))
+        add("logits", lambda d: (d.B, d.C))
+        add("g_logits", lambda d: (d.B, d.C))
         self.loss3 = e(3)
-        self.g_logits = e(B, d.C)
         # ---- backward scratch ----
-        self.gx = [e(M, D), e(M, D)]
-        self.g_xn = e(B, D)
-        self.gpD = e(2, M, D, dt=bf)
-        self.gpF = e(2, M, F, dt=bf)
-        self.gp3 = e(2, M, 3 * D, dt=bf)
-        self.gpP = e(2, B * d.P, D, dt=bf)
-        self.g_big = e(M, F)
-        self.g_h = e(M, D)
-        self.g_o = e(M, D)
-        self.g_op = e(2, M, D, dt=bf)
-        self.g_qkv = e(M, 3 * D)
-        self.dP = e(B * d.H * T, d.ldS)
-        self.dSp = torch.zeros(2, B * d.H * T, d.ldP, dtype=bf, device=dev)
+        add("gx", lambda d: (d.M, d.D), count=2)
+        add("g_xn", lambda d: (d.B, d.D))
+        add("gpD", lambda d: (2, d.M, d.D), bf)
+        add("gpF", lambda d: (2, d.M, d.F), bf)
+        add("gp3", lambda d: (2, d.M, 3 * d.D), bf)
+        add("gpP", lambda d: (2, d.B * d.P, d.D), bf)
+        add("g_big", lambda d: (d.M, d.F))
+        add("g_h", lambda d: (d.M, d.D))
+        add("g_o", lambda d: (d.M, d.D))
+        add("g_op", lambda d: (2, d.M, d.D), bf)
+        add("g_qkv", lambda d: (d.M, 3 * d.D))
+        add("dP", lambda d: (d.B * d.H * d.T, d.ldS))
+        add("dSp", lambda d: (2, d.B * d.H * d.T, d.ldP), bf, zero=True)
         self.rpb = 64
         self.bias_part = e(-(-M // self.rpb) * max(F, 3 * D))
         self.ln_part = e(-(-M // self.rpb), 2, D)
-        self._splits, max_ws = {}, 0
-        for (n, k, kdim) in [(3 * D, D, M), (D, D, M), (F, D, M), (D, F, M), (D, d.Kc, B * d.P)]:
-            s = wgrad_splits(n, k, kdim, self.sms)
-            self._splits[(n, k)] = s
-            max_ws = max(max_ws, s * n * k)
+        self._ln_tmp = e(2 * D)
+        self._splits_by_b, max_ws = {}, 0
+        for bb in range(1, B + 1):
+            tab = {}
+            for (n, k, kdim) in [(3 * D, D, bb * T), (D, D, bb * T), (F, D, bb * T), (D, F, bb * T), (D, d.Kc, bb * d.P)]:
+                sp = wgrad_splits(n, k, kdim, self.sms)
+                tab[(n, k)] = sp
+                max_ws = max(max_ws, sp * n * k)
+            self._splits_by_b[bb] = tab
         self.ws = e(max_ws)
+        self._bb_on_bind(B)
+
+    def _bb_on_bind(self, b: int) -> None:
+        self._splits = self._splits_by_b[b]
+        self.stats1 = list(zip(self.st1m, self.st1r))
+        self.stats2 = list(zip(self.st2m, self.st2r))
+        self.statsF = (self.stFm, self.stFr)
 
     # ------------------------------------------------------------------------------------------
     def attach_grads(self) -> None:
@@ -132,7 +147,11 @@ class PlainStudentEngine:
 
     def _ln_param_grads(self, norm: nn.Module, nblk: int) -> None:
         D = self.d.D
-        tmp = torch.empty(2 * D, device=self.dev)
+        gw, gb = self._goff[id(norm.weight)], self._goff[id(norm.bias)]
+        if gb == gw + D:        # weight and bias gradients are neighbours in the arena: one reduce writes both
+            ops.colsum_reduce(self.ln_part, nblk, 2 * D, self.grad_arena[gw:gw + 2 * D])
+            return
+        tmp = self._ln_tmp
         ops.colsum_reduce(self.ln_part, nblk, 2 * D, tmp)
         self._grad(norm.weight).copy_(tmp[:D])
         self._grad(norm.bias).copy_(tmp[D:])
@@ -143,10 +162,9 @@ class PlainStudentEngine:
 
     def forward(self, images: torch.Tensor, labels: Optional[torch.Tensor], teacher_logits: Optional[torch.Tensor],
                 teacher_ready=None) -> Optional[torch.Tensor]:
+        self._bb_bind(self._bb_check(images, "student"))
         d, v = self.d, self.vit
         B, T, D, F, M, L = d.B, d.T, d.D, d.F, d.M, d.L
-        if tuple(images.shape) != (B, d.in_ch, d.HW, d.HW):
-            raise RuntimeError(f"student engine built for batch {B}, got {tuple(images.shape)}")
         for ql in self.all_linears:
             ql.split()
         ops.im2col_fq(images, None, B, d.in_ch, d.HW, d.ps, self.img_planes)
@@ -217,7 +235,7 @@ class PlainStudentEngine:
         ops.head_bwd(self.g_logits, self.xn, v.head.weight.detach(), None, B, D, d.C, self.g_xn, self._grad(v.head.weight),
                      self._grad(v.head.bias))
         gx, gx2 = self.gx
-        gx.zero_()
+        ops.zero_(gx)
         ops.ln_bwd(self.g_xn, self.xcls, self.statsF[0], self.statsF[1], v.norm.weight.detach(), None, B, D, gx, self.ln_part,
                    self.rpb, out_row_stride=T)
         self._ln_param_grads(v.norm, -(-B // self.rpb))
@@ -280,6 +298,7 @@ class PlainDistillStep:
 
     def __call__(self, images: torch.Tensor, labels: torch.Tensor, grad_sync=None) -> torch.Tensor:
         main = torch.cuda.current_stream()
+        self.student_engine.attach_grads()       # optimizer.zero_grad(set_to_none=True) drops the arena views (ref :351)
         if ops.profiling():
             t_logits = self.teacher_engine.forward(images)
             out3 = self.student_engine.forward(images, labels, t_logits)

@@ -40,37 +40,51 @@ def build_models(backend, student_name, teacher_name, img, seed=0, ln_variant="s
     return vr, prepared, teacher
 
 
-def engine_raw_tensors(se):
-    """name of each activation fake-quant module of the prepared student -> the engine's raw input for it (CPU)."""
+def engine_raw_tensors(se, lazy=False):
+    """name of each activation fake-quant module of the prepared student -> the engine's raw input for it (CPU).
+    lazy=True: values are zero-argument callables that copy the tensor off the device when the hook needs it (batch 256:
+    8 GB of raw tensors would otherwise sit in host memory at once)."""
     d = se.d
     B, T, D, P = d.B, d.T, d.D, d.P
     G = int(round(P ** 0.5))
-    forced = {"model.patch_embed.proj.activation_post_process":
-              se.p_raw.view(B, P, D).transpose(1, 2).reshape(B, D, G, G).cpu(),
-              "model.head.activation_post_process": se.logits_raw.cpu()}
+    get = {"model.patch_embed.proj.activation_post_process":
+           lambda: se.p_raw.view(B, P, D).transpose(1, 2).reshape(B, D, G, G).cpu(),
+           "model.head.activation_post_process": lambda: se.logits_raw.cpu()}
+
+    def tok(t):
+        return lambda: t.view(B, T, -1).cpu()
     for i in range(d.L):
         pre = f"model.blocks.{i}."
-        forced[pre + "attn.qkv.activation_post_process"] = se.qkv_raw[i].view(B, T, -1).cpu()
-        forced[pre + "attn.proj.activation_post_process"] = se.a_raw[i].view(B, T, -1).cpu()
-        forced[pre + "mlp.fc1.activation_post_process"] = se.f_raw[i].view(B, T, -1).cpu()
-        forced[pre + "mlp.fc2.activation_post_process"] = se.m_raw[i].view(B, T, -1).cpu()
+        get[pre + "attn.qkv.activation_post_process"] = tok(se.qkv_raw[i])
+        get[pre + "attn.proj.activation_post_process"] = tok(se.a_raw[i])
+        get[pre + "mlp.fc1.activation_post_process"] = tok(se.f_raw[i])
+        get[pre + "mlp.fc2.activation_post_process"] = tok(se.m_raw[i])
         if se.ln_obs:
-            forced[pre + "norm1.activation_post_process"] = se.h1_raw[i].view(B, T, -1).cpu()
-            forced[pre + "norm2.activation_post_process"] = se.h2_raw[i].view(B, T, -1).cpu()
+            get[pre + "norm1.activation_post_process"] = tok(se.h1_raw[i])
+            get[pre + "norm2.activation_post_process"] = tok(se.h2_raw[i])
     if se.ln_obs:
-        forced["model.norm.activation_post_process"] = se.hN_raw.view(B, T, -1).cpu()
-    return forced
+        get["model.norm.activation_post_process"] = tok(se.hN_raw)
+    return get if lazy else {k: f() for k, f in get.items()}
 
 
-def install_forcing_hooks(ref_model, forced, stage_err):
+def install_forcing_hooks(ref_model, forced, stage_err, keep_ref_codes=None):
+    """Pre-hooks on the activation fake-quant modules of the CPU reference: the module sees OUR raw tensor, value-exact
+    (`ours + (x - x.detach())`: the bracket is exactly zero, so the forward value is `ours` bit for bit while the gradient still
+    flows into the reference's own x) -- every observer and every integer code of the reference is then decided on the very
+    tensor our kernels saw, which is what lets the observer state be compared with torch.equal.
+    keep_ref_codes: optional dict filled with name -> (input tensor as forced, module) for code-level comparisons."""
     handles = []
 
     def mk(name):
         def pre_hook(mod, inp):
             x = inp[0]
             ours = forced[name]
+            if callable(ours):
+                ours = ours()
             stage_err[name] = rel_l2(x, ours)
-            return (x + (ours - x).detach(),)
+            if keep_ref_codes is not None:
+                keep_ref_codes[name] = ours
+            return (ours + (x - x.detach()),)
         return pre_hook
     for name, m in ref_model.named_modules():
         if name in forced:

@@ -11,7 +11,7 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, async_op, q):
+def _worker(rank, world, port, async_op, q, rehome=False):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -21,7 +21,10 @@ def _worker(rank, world, port, async_op, q):
     torch.manual_seed(100 + rank)
     obs = [(torch.tensor(float(-1 - rank - i)), torch.tensor(float(1 + rank + i))) for i in range(5)]
     gs = GradSync(1000, len(obs), device="cpu", bucket_bytes=1024)      # several buckets
-    gs.bind_observers(obs)
+    gs.bind_observers(obs, rehome=rehome)
+    if rehome:       # the observer buffers now live in the tail of the exchange buffer: same objects, same values
+        assert all(a.data_ptr() >= gs.tail.data_ptr() for a, _ in obs)
+        assert [(float(a), float(b)) for a, b in obs] == [(float(-1 - rank - i), float(1 + rank + i)) for i in range(5)]
     g = torch.randn(1000)
     gs.grad_arena.copy_(g)
     if async_op == "overlapped":        # layer-by-layer suffixes, as the engine's backward reports them
@@ -54,3 +57,22 @@ def test_gradient_sum_and_rank0_observer_state(async_op):
     for rank, _, reduced, obs in res:
         assert torch.allclose(reduced, total, atol=1e-6)                  # SUM; the 1/world is applied in the clip pass
         assert obs == [(float(-1 - i), float(1 + i)) for i in range(5)]   # everyone ends with rank 0's running min/max
+
+
+def test_rehomed_observers_need_no_pack_or_unpack():
+    """bind_observers(rehome=True): the running min / max buffers ARE the tail of the exchange buffer -- rank != 0 clears them
+    before the exchange, nothing is copied afterwards, and every rank still ends with rank 0's state."""
+    world, port = 2, 31500 + os.getpid() % 2000
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, "overlapped", q, True)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    total = res[0][1] + res[1][1]
+    for rank, _, reduced, obs in res:
+        assert torch.allclose(reduced, total, atol=1e-6)
+        assert obs == [(float(-1 - i), float(1 + i)) for i in range(5)]

@@ -1,7 +1,11 @@
-"""BASELINE.json configs[1] at FULL size (ViT-B/16 teacher -> ViT-S/16 QAT student, batch 256, 224x224) through size-independent
-properties -- the CPU oracle cannot run this size in test time, so: determinism (two runs from the same state are bit-identical),
-conservation laws of the loss gradient, the bias-gradient = column-sum identity, fake-quant idempotence on a full activation
-tensor, and agreement of the big step with the same images run as two half batches wherever the arithmetic is batch-local."""
+"""BASELINE.json configs[1] at FULL size (ViT-B/16 teacher -> ViT-S/16 QAT student, batch 256, 224x224).
+
+Against the oracle where the CPU can follow in seconds: the teacher's logits on the first 8 images of the 256-image batch vs the
+CPU fp32 teacher on those images (the teacher is batch-local), and a FORWARD-ONLY forced-parity pass of the student at batch
+256 (every stage, the fake-quantised logits and every observer buffer; the CTA-pair GEMMs, taken only for M >= 18 944 rows,
+are thereby compared with the oracle inside the engine).  Through size-independent properties for the full step: determinism
+(two runs from the same state are bit-identical), conservation laws of the loss gradient, the bias-gradient = column-sum
+identity, fake-quant idempotence on a full activation tensor, batch-locality of the teacher."""
 import copy
 import os
 import sys
@@ -97,3 +101,66 @@ def test_full_size_teacher_is_batch_local(cuda_dev, big):
     hi = half.forward(big["images"][B // 2:].contiguous()).clone()
     torch.cuda.synchronize()
     assert torch.equal(full, torch.cat([lo, hi]))
+
+
+def _oracle_teacher(big):
+    """The CPU side: oracle/vit_ref.py's restated timm ViT-B (stock ATen ops) holding the bench teacher's weights."""
+    from oracle import vit_ref as vr
+    ref = vr.create_model("vit_base_patch16_224", num_classes=10).eval()
+    ref.load_state_dict({k: v.detach().cpu() for k, v in big["teacher"].state_dict().items()})
+    return ref
+
+
+def test_full_size_teacher_rows_match_cpu_fp32(cuda_dev, big):
+    """Rows 0..7 of the batch-256 teacher logits (mixed-format CTA-pair GEMMs at M = 50 432) vs the CPU fp32 teacher on those 8
+    images: north_star tolerance 1e-3 relative, expected ~1e-4."""
+    from parity_utils import rel_max
+    from qatvit_b200.engine import TeacherEngine
+    from qatvit_b200 import ops
+    n0 = ops.gemm_pair_launches()
+    eng = TeacherEngine(big["teacher"], big["B"])
+    full = eng.forward(big["images"]).clone()
+    torch.cuda.synchronize()
+    assert ops.gemm_pair_launches() > n0                       # this size really takes the cta_group::2 kernels
+    assert eng.saturation_events == []
+    with torch.no_grad():
+        ref = _oracle_teacher(big)(big["images"][:8].cpu())
+    err = rel_max(full[:8], ref)
+    assert err < 1e-3, err
+    print(f"teacher B=256 rows 0..7 vs CPU fp32: rel_max {err:.2e}")
+
+
+def test_full_size_student_forward_forced_parity(cuda_dev, big):
+    """Forward of the prepared student at batch 256 vs the reference path on the host CPU (stock prepare_qat + live ATen ops,
+    oracle/vit_ref.py) with our raw tensors forced value-exactly into every activation fake-quant: stage error < 1e-4,
+    fake-quantised logits < 1e-5, and EVERY observer buffer (weights and activations: running min / max, scale, zero_point)
+    bit for bit."""
+    from parity_utils import engine_raw_tensors, install_forcing_hooks, rel_max
+    from oracle import vit_ref as vr
+    B = big["B"]
+    s = copy.deepcopy(big["student"])
+    sd0 = {k: v.detach().cpu().clone() for k, v in s.state_dict().items()}        # before the engine resizes per-channel buffers
+    ref = vr.enable_qat(vr.make_student(prefer_reference=False), "fbgemm")
+    ref.load_state_dict(sd0)
+    step = big["Step"](s, big["teacher"], B, big["hp"])
+    y = step.predict(big["images"]).clone()
+    torch.cuda.synchronize()
+    stage_err = {}
+    handles = install_forcing_hooks(ref, engine_raw_tensors(step.student_engine, lazy=True), stage_err)
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        y_ref = ref(big["images"].cpu())
+    for h in handles:
+        h.remove()
+    worst = max(stage_err, key=stage_err.get)
+    assert len(stage_err) == 50 and stage_err[worst] < 1e-4, (worst, stage_err[worst])
+    assert rel_max(y, y_ref) < 1e-5
+    ref_sd, gpu_sd = ref.state_dict(), s.state_dict()
+    assert list(ref_sd.keys()) == list(gpu_sd.keys())
+    n_obs = 0
+    for k in ref_sd:
+        if k.endswith(("min_val", "max_val", "scale", "zero_point")):
+            assert torch.equal(gpu_sd[k].cpu(), ref_sd[k]), k
+            n_obs += 1
+    assert n_obs == 4 * 101
+    print(f"student B=256 forward forced parity: worst stage {worst} {stage_err[worst]:.2e}, {n_obs} observer buffers bit-exact")
