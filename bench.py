@@ -370,20 +370,24 @@ def side_measurements(student, teacher, step, images, labels, dev, peaks, budget
 
 
 def params_identical(student, dev, world) -> bool:
-    """Bit-level checksum (int64 sum of the int32 views) of every parameter and buffer, compared across ranks."""
+    """Bit-level checksums (int64 sum of the int32 views, one per tensor) of everything data parallelism keeps identical across
+    ranks after a step: every parameter, every weight-observer buffer (derived from identical weights) and the activation
+    observers' running min / max (rank 0's, exchanged).  The activation fake-quants' scale / zero_point are NOT in the list: each
+    rank recomputes them inside its own forward from the running range AND its local batch (under DDP likewise: rank 0's copy is
+    broadcast at the start of the next forward and recomputed before use, torch/nn/parallel/distributed.py:1590-1591)."""
     import torch
     import torch.distributed as dist
-    acc = torch.zeros(2, dtype=torch.int64, device=dev)
-    for t in list(student.parameters()) + list(student.buffers()):
-        if t.numel() == 0:
-            continue
+    tensors = [p_ for _, p_ in student.named_parameters()]
+    for name, b in student.named_buffers():
+        local = name.endswith(("scale", "zero_point")) and "weight_fake_quant" not in name
+        if not local and b.numel() > 0:
+            tensors.append(b)
+    sums = torch.zeros(len(tensors), dtype=torch.int64, device=dev)
+    for i, t in enumerate(tensors):
         v = t.detach().contiguous()
-        if v.dtype == torch.float32:
-            acc[0] += v.view(torch.int32).to(torch.int64).sum()
-        else:
-            acc[1] += v.to(torch.int64).sum()
-    allv = [torch.zeros_like(acc) for _ in range(world)]
-    dist.all_gather(allv, acc)
+        sums[i] = (v.view(torch.int32) if v.dtype == torch.float32 else v).to(torch.int64).sum()
+    allv = [torch.zeros_like(sums) for _ in range(world)]
+    dist.all_gather(allv, sums)
     return all(bool(torch.equal(a, allv[0])) for a in allv)
 
 

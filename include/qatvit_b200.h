@@ -90,6 +90,19 @@ int qv_fq_weight(const float* w, int64_t rows, int64_t cols, int32_t per_channel
                  int32_t qmax, int32_t symmetric, float* y, uint8_t* mask, uint16_t* codes, uint16_t* codes_t,
                  uint32_t* scratch, float* scale_vec, void* stream);
 
+/* Learnable per-channel fake-quant (replaces torch._fake_quantize_learnable_per_channel_affine and its autograd node, called by
+ * torch/ao/quantization/_learnable_fake_quantize.py:158-196; channel axis 0 of x[rows][cols], scale / zero_point fp32 [rows]).
+ * OPT-IN: the reference has no learnable scale (its scale / zero_point are buffers); nothing on the default
+ * path calls these.  forward: zr = clamp(rint(zero_point)), y = (clamp(zr + rint(x / scale)) - zr) * scale.
+ * backward (north_star kernel 2, "the per-channel scale gradient done as a warp-shuffle reduction"): dx = gy * [in range];
+ * dscale[r] / dzero_point[r] = per-channel sums of ATen's per-element terms times grad_factor (oracle/fq_oracle.c
+ * qo_fq_learnable_bwd), one warp per channel, shuffle butterfly, deterministic.  dx / dscale / dzero_point may each be NULL. */
+int qv_fq_learnable_fwd(const float* x, int64_t rows, int64_t cols, const float* scale, const float* zero_point,
+                        int32_t qmin, int32_t qmax, float* y, void* stream);
+int qv_fq_learnable_bwd(const float* gy, const float* x, int64_t rows, int64_t cols, const float* scale,
+                        const float* zero_point, int32_t qmin, int32_t qmax, float grad_factor, float* dx, float* dscale,
+                        float* dzero_point, void* stream);
+
 /* STE backward gx = gy * mask (FusedMovingAvgObsFqHelperBackward0). */
 int qv_fq_bwd(const float* gy, const uint8_t* mask, int64_t n, float* gx, void* stream);
 

@@ -131,17 +131,18 @@ def fq_learnable_fwd(x: np.ndarray, scale: np.ndarray, zero_point: np.ndarray, q
 
 def fq_learnable_bwd(gy: np.ndarray, x: np.ndarray, scale: np.ndarray, zero_point: np.ndarray, qmin: int, qmax: int,
                      grad_factor: float):
-    """-> (dx fp32, dscale float64 [C], dzero_point float64 [C]) of the learnable per-channel fake-quant (qo_fq_learnable_bwd)."""
+    """-> (dx fp32, dscale float64 [C], dzero_point float64 [C], magnitude float64 [C]) of the learnable per-channel
+    fake-quant (qo_fq_learnable_bwd).  magnitude = sum |g| (|xq - zr| + 1) grad_factor: what fp32 rounding acts on (see the C file)."""
     gy = np.ascontiguousarray(gy, np.float32)
     x = np.ascontiguousarray(x, np.float32)
     scale = np.ascontiguousarray(scale, np.float32)
     zero_point = np.ascontiguousarray(zero_point, np.float32)
     C = x.shape[0]
     dx = np.empty_like(x)
-    ds, dz = np.zeros(C, np.float64), np.zeros(C, np.float64)
+    ds, dz, da = np.zeros(C, np.float64), np.zeros(C, np.float64), np.zeros(C, np.float64)
     lib().qo_fq_learnable_bwd(_p(gy), _p(x), ctypes.c_int64(C), ctypes.c_int64(x.size // max(C, 1)), _p(scale), _p(zero_point),
-                              int(qmin), int(qmax), ctypes.c_float(grad_factor), _p(dx), _p(ds), _p(dz))
-    return dx, ds, dz
+                              int(qmin), int(qmax), ctypes.c_float(grad_factor), _p(dx), _p(ds), _p(dz), _p(da))
+    return dx, ds, dz, da
 
 
 def distill_loss(s: np.ndarray, t: np.ndarray, labels: np.ndarray, T: float, alpha: float, eps: float):

@@ -90,6 +90,8 @@ _SIGNATURES = {
                              c_int32, _P, _P, _P, _P, _P, _P, _P]),
     "qv_fq_weight_grouped": (c_int, [_P, c_int32, c_int32, c_int32, c_float, c_int32, c_int32, c_int32, _P]),
     "qv_fq_bwd": (c_int, [_P, _P, c_int64, _P, _P]),
+    "qv_fq_learnable_fwd": (c_int, [_P, c_int64, c_int64, _P, _P, c_int32, c_int32, _P, _P]),
+    "qv_fq_learnable_bwd": (c_int, [_P, _P, c_int64, c_int64, _P, _P, c_int32, c_int32, c_float, _P, _P, _P, _P]),
     "qv_split_planes": (c_int, [_P, c_int64, _P, _P, _P]),
     "qv_split_planes_mix": (c_int, [_P, c_int64, c_int64, c_int32, _P, _P, _P]),
     "qv_kd_ce_loss": (c_int, [_P, _P, _P, c_int32, c_int32, c_float, c_float, c_float, _P, _P, c_int32, c_int32,

@@ -8,6 +8,7 @@
 //   q = rint(x * (1/s)) + zp, clamp, (q - zp) * s.
 #include <stdio.h>
 
+#include <algorithm>
 #include <mutex>
 
 #include "qv_common.cuh"
@@ -458,6 +459,150 @@ extern "C" int qv_fq_weight(const float* w, int64_t rows, int64_t cols, int32_t 
                                                                          zero_point, averaging_const, qmin, qmax,
                                                                          symmetric, y, mask, c, ct, scale_vec);
   return qv_check_launch("qv_fq_weight");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Learnable per-channel fake-quant (torch._fake_quantize_learnable_per_channel_affine, channel axis 0 of x[rows][cols]): the
+// op behind torch/ao/quantization/_learnable_fake_quantize.py:158-196.  Not on the reference's path (its scales are buffers,
+// SURVEY.md 0.10) -- the opt-in counterpart of north_star's "per-channel scale gradient done as a warp-shuffle reduction".
+// Arithmetic: oracle/fq_oracle.c qo_fq_learnable_fwd / _bwd (note the backward rounds AFTER adding the zero point, the forward
+// before: they differ on ties, as in ATen).  One WARP per channel: lanes stride the row with 16-byte loads, per-lane partial sums
+// in a fixed order, then an xor-shuffle butterfly -- no atomics, no second pass, bit-reproducible run to run.
+// ------------------------------------------------------------------------------------------------
+struct QvLearnQ { float s, inv, zr, qmin, qmax; };
+__device__ __forceinline__ QvLearnQ qv_learn_q(const float* scale, const float* zp, int64_t r, int qmin, int qmax) {
+  QvLearnQ q;
+  q.s = __ldg(scale + r);
+  q.inv = __fdiv_rn(1.0f, q.s);
+  q.qmin = (float)qmin;
+  q.qmax = (float)qmax;
+  q.zr = fminf(fmaxf(rintf(__ldg(zp + r)), q.qmin), q.qmax);
+  return q;
+}
+__device__ __forceinline__ float qv_learn_fwd1(float x, const QvLearnQ& q) {
+  const float v = fminf(fmaxf(__fadd_rn(q.zr, rintf(__fmul_rn(x, q.inv))), q.qmin), q.qmax);
+  return __fmul_rn(__fsub_rn(v, q.zr), q.s);
+}
+// one element of the backward: returns dx; adds this element's terms to ds / dz
+__device__ __forceinline__ float qv_learn_bwd1(float g, float x, const QvLearnQ& q, float gf, float& ds, float& dz) {
+  const float xq = rintf(__fadd_rn(q.zr, __fmul_rn(x, q.inv)));
+  const bool in = (xq >= q.qmin) && (xq <= q.qmax);
+  if (in) {
+    const float xfq = __fmul_rn(__fsub_rn(xq, q.zr), q.s);
+    ds += __fmul_rn(__fmul_rn(__fmul_rn(g, __fsub_rn(xfq, x)), q.inv), gf);
+  } else {
+    const float edge = __fsub_rn(xq < q.qmin ? q.qmin : q.qmax, q.zr);
+    ds += __fmul_rn(__fmul_rn(g, edge), gf);
+    dz += __fmul_rn(__fmul_rn(__fmul_rn(g, -1.0f), q.s), gf);
+  }
+  return in ? g : 0.0f;
+}
+
+__global__ void __launch_bounds__(256) qv_fq_learnable_fwd_kernel(const float* __restrict__ x, int64_t rows, int64_t cols,
+                                                                  const float* __restrict__ scale, const float* __restrict__ zp,
+                                                                  int qmin, int qmax, float* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const bool vec = (cols & 3) == 0;
+  for (int64_t r = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) {
+    const QvLearnQ q = qv_learn_q(scale, zp, r, qmin, qmax);
+    const float* xr = x + r * cols;
+    float* yr = y + r * cols;
+    if (vec) {
+      for (int64_t i = lane; i < (cols >> 2); i += 32) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(xr) + i);
+        reinterpret_cast<float4*>(yr)[i] = make_float4(qv_learn_fwd1(v.x, q), qv_learn_fwd1(v.y, q), qv_learn_fwd1(v.z, q),
+                                                       qv_learn_fwd1(v.w, q));
+      }
+    } else {
+      for (int64_t i = lane; i < cols; i += 32) yr[i] = qv_learn_fwd1(__ldg(xr + i), q);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) qv_fq_learnable_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x,
+                                                                  int64_t rows, int64_t cols, const float* __restrict__ scale,
+                                                                  const float* __restrict__ zp, int qmin, int qmax, float gf,
+                                                                  float* __restrict__ dx, float* __restrict__ dscale,
+                                                                  float* __restrict__ dzp) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const bool vec = (cols & 3) == 0;
+  for (int64_t r = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) {
+    const QvLearnQ q = qv_learn_q(scale, zp, r, qmin, qmax);
+    const float* xr = x + r * cols;
+    const float* gr = gy + r * cols;
+    float* dr = dx ? dx + r * cols : nullptr;
+    float ds = 0.f, dz = 0.f;
+    if (vec) {
+      const int64_t n4 = cols >> 2;
+      for (int64_t i = lane; i < n4; i += 64) {          // two independent 16-byte load pairs in flight per lane
+        const bool two = i + 32 < n4;
+        const float4 xa = __ldg(reinterpret_cast<const float4*>(xr) + i);
+        const float4 ga = __ldg(reinterpret_cast<const float4*>(gr) + i);
+        float4 xb = make_float4(0.f, 0.f, 0.f, 0.f), gb = xb;
+        if (two) {
+          xb = __ldg(reinterpret_cast<const float4*>(xr) + i + 32);
+          gb = __ldg(reinterpret_cast<const float4*>(gr) + i + 32);
+        }
+        float4 o;
+        o.x = qv_learn_bwd1(ga.x, xa.x, q, gf, ds, dz);
+        o.y = qv_learn_bwd1(ga.y, xa.y, q, gf, ds, dz);
+        o.z = qv_learn_bwd1(ga.z, xa.z, q, gf, ds, dz);
+        o.w = qv_learn_bwd1(ga.w, xa.w, q, gf, ds, dz);
+        if (dr) reinterpret_cast<float4*>(dr)[i] = o;
+        if (two) {
+          o.x = qv_learn_bwd1(gb.x, xb.x, q, gf, ds, dz);
+          o.y = qv_learn_bwd1(gb.y, xb.y, q, gf, ds, dz);
+          o.z = qv_learn_bwd1(gb.z, xb.z, q, gf, ds, dz);
+          o.w = qv_learn_bwd1(gb.w, xb.w, q, gf, ds, dz);
+          if (dr) reinterpret_cast<float4*>(dr)[i + 32] = o;
+        }
+      }
+    } else {
+      for (int64_t i = lane; i < cols; i += 32) {
+        const float o = qv_learn_bwd1(__ldg(gr + i), __ldg(xr + i), q, gf, ds, dz);
+        if (dr) dr[i] = o;
+      }
+    }
+    ds = qv_warp_sum(ds);
+    dz = qv_warp_sum(dz);
+    if (lane == 0) {
+      if (dscale) dscale[r] = ds;
+      if (dzp) dzp[r] = dz;
+    }
+  }
+}
+
+extern "C" int qv_fq_learnable_fwd(const float* x, int64_t rows, int64_t cols, const float* scale, const float* zero_point,
+                                   int32_t qmin, int32_t qmax, float* y, void* stream) {
+  QV_REQUIRE(rows >= 0 && cols >= 0 && qmin < qmax, QV_ERR_INVALID, "bad fq_learnable_fwd arguments");
+  if (rows == 0 || cols == 0) return QV_OK;
+  QV_REQUIRE(x && y && scale && zero_point, QV_ERR_INVALID, "null pointer");
+  QV_REQUIRE((cols & 3) != 0 || (qv_aligned16(x) && qv_aligned16(y)), QV_ERR_INVALID, "x / y must be 16-byte aligned");
+  const int sms = qv_num_sms();
+  QV_REQUIRE(sms > 0, QV_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  const int64_t blocks = std::min<int64_t>((rows + 7) / 8, static_cast<int64_t>(sms) * 8);
+  qv_fq_learnable_fwd_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, rows, cols, scale, zero_point, qmin, qmax, y);
+  return qv_check_launch("qv_fq_learnable_fwd");
+}
+
+extern "C" int qv_fq_learnable_bwd(const float* gy, const float* x, int64_t rows, int64_t cols, const float* scale,
+                                   const float* zero_point, int32_t qmin, int32_t qmax, float grad_factor, float* dx,
+                                   float* dscale, float* dzero_point, void* stream) {
+  QV_REQUIRE(rows >= 0 && cols >= 0 && qmin < qmax, QV_ERR_INVALID, "bad fq_learnable_bwd arguments");
+  if (rows == 0) return QV_OK;
+  QV_REQUIRE(scale && zero_point && (dx || dscale || dzero_point), QV_ERR_INVALID, "null pointer");
+  QV_REQUIRE(cols == 0 || (gy && x), QV_ERR_INVALID, "null pointer");
+  QV_REQUIRE((cols & 3) != 0 || (qv_aligned16(gy) && qv_aligned16(x) && qv_aligned16(dx)), QV_ERR_INVALID,
+             "gy / x / dx must be 16-byte aligned");
+  const int sms = qv_num_sms();
+  QV_REQUIRE(sms > 0, QV_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  const int64_t blocks = std::min<int64_t>((rows + 3) / 4, static_cast<int64_t>(sms) * 16);
+  qv_fq_learnable_bwd_kernel<<<static_cast<unsigned>(blocks), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      gy, x, rows, cols, scale, zero_point, qmin, qmax, grad_factor, dx, dscale, dzero_point);
+  return qv_check_launch("qv_fq_learnable_bwd");
 }
 
 extern "C" int qv_split_planes(const float* x, int64_t n, uint16_t* hi, uint16_t* lo, void* stream) {

@@ -72,6 +72,39 @@ def _fq_forward(self, X):
     return _ORIG["fq"](self, X)
 
 
+class _LearnableFakeQuantFn(torch.autograd.Function):
+    """torch._fake_quantize_learnable_per_channel_affine for channel axis 0: y, STE dx and the per-channel scale / zero-point
+    gradients (warp-shuffle reduction, qv_fq_learnable_bwd)."""
+
+    @staticmethod
+    def forward(ctx, x, scale, zero_point, qmin, qmax, grad_factor):
+        xc, sc, zc = x.contiguous(), scale.contiguous(), zero_point.contiguous()
+        ctx.save_for_backward(xc, sc, zc)
+        ctx.q = (qmin, qmax, grad_factor)
+        return ops.fq_learnable_fwd(xc, sc, zc, qmin, qmax)
+
+    @staticmethod
+    def backward(ctx, gy):
+        xc, sc, zc = ctx.saved_tensors
+        qmin, qmax, gf = ctx.q
+        dx, ds, dz = ops.fq_learnable_bwd(gy.contiguous(), xc, sc, zc, qmin, qmax, gf)
+        return dx, ds, dz, None, None, None
+
+
+def _learnable_fq_forward(self, X):
+    """_LearnableFakeQuantize.forward (torch/ao/quantization/_learnable_fake_quantize.py:158-196) with the per-channel op on our
+    kernels; every other branch (static observation, per-tensor, other axes, CPU) stays stock."""
+    per_channel = self.qscheme in (torch.per_channel_symmetric, torch.per_channel_affine)
+    if not (X.is_cuda and X.dtype == torch.float32 and X.numel() > 0 and per_channel and self.ch_axis == 0
+            and int(self.static_enabled[0]) != 1 and int(self.fake_quant_enabled[0]) == 1):
+        return _ORIG["learnable_fq"](self, X)
+    self.scale.data.clamp_(min=self.eps.item())
+    if self.qscheme == torch.per_channel_symmetric:
+        self.zero_point.data.zero_()
+    grad_factor = 1.0 / (X.numel() * self.quant_max) ** 0.5 if self.use_grad_scaling else 1.0
+    return _LearnableFakeQuantFn.apply(X, self.scale, self.zero_point, self.quant_min, self.quant_max, grad_factor)
+
+
 def _gemm_friendly(M: int, N: int, K: int) -> bool:
     return K % 8 == 0 and N % 32 == 0 and M > 0
 
@@ -169,11 +202,17 @@ def distill_loss(student_out: torch.Tensor, teacher_out: torch.Tensor, labels: t
                                 float(label_smoothing))
 
 
-def install() -> None:
-    """Patch the torch.ao module classes in place (idempotent).  Module TYPES stay exactly the stock ones."""
+def install(learnable: bool = False) -> None:
+    """Patch the torch.ao module classes in place (idempotent).  Module TYPES stay exactly the stock ones.
+    learnable=True (default OFF: the reference has no learnable scale) also routes
+    ``_LearnableFakeQuantize.forward`` (per-channel, axis 0) to qv_fq_learnable_fwd / _bwd."""
     from torch.ao.quantization.fake_quantize import FusedMovingAvgObsFakeQuantize
     import torch.ao.nn.qat as nnqat
-    if _ORIG:
+    if learnable and "learnable_fq" not in _ORIG:
+        from torch.ao.quantization._learnable_fake_quantize import _LearnableFakeQuantize
+        _ORIG["learnable_fq"] = _LearnableFakeQuantize.forward
+        _LearnableFakeQuantize.forward = _learnable_fq_forward
+    if "fq" in _ORIG:
         return
     _ORIG["fq"] = FusedMovingAvgObsFakeQuantize.forward
     _ORIG["linear"] = nnqat.Linear.forward
@@ -184,7 +223,10 @@ def install() -> None:
 def uninstall() -> None:
     from torch.ao.quantization.fake_quantize import FusedMovingAvgObsFakeQuantize
     import torch.ao.nn.qat as nnqat
-    if not _ORIG:
+    if "learnable_fq" in _ORIG:
+        from torch.ao.quantization._learnable_fake_quantize import _LearnableFakeQuantize
+        _LearnableFakeQuantize.forward = _ORIG.pop("learnable_fq")
+    if "fq" not in _ORIG:
         return
     FusedMovingAvgObsFakeQuantize.forward = _ORIG.pop("fq")
     nnqat.Linear.forward = _ORIG.pop("linear")

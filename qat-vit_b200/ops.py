@@ -131,6 +131,31 @@ def fq_bwd(gy, mask, gx=None):
     return gx
 
 
+def fq_learnable_fwd(x, scale, zero_point, qmin, qmax, y=None):
+    """Learnable per-channel fake-quant forward, channel axis 0 (include/qatvit_b200.h: qv_fq_learnable_fwd)."""
+    rows = x.shape[0]
+    if y is None:
+        y = torch.empty_like(x)
+    check(_lib.lib().qv_fq_learnable_fwd(_p(x, torch.float32, "x"), rows, x.numel() // max(rows, 1), _p(scale, torch.float32, "scale"),
+                                         _p(zero_point, torch.float32, "zero_point"), int(qmin), int(qmax),
+                                         _p(y, torch.float32, "y"), _stream()), "fq_learnable_fwd")
+    return y
+
+
+def fq_learnable_bwd(gy, x, scale, zero_point, qmin, qmax, grad_factor, want_dx=True):
+    """-> (dx, dscale[rows], dzero_point[rows]): STE gradient and the per-channel scale / zero-point gradients (one warp per
+    channel, shuffle reduction; qv_fq_learnable_bwd)."""
+    rows = x.shape[0]
+    dx = torch.empty_like(x) if want_dx else None
+    ds = torch.empty(rows, dtype=torch.float32, device=x.device)
+    dz = torch.empty(rows, dtype=torch.float32, device=x.device)
+    check(_lib.lib().qv_fq_learnable_bwd(_p(gy, torch.float32, "gy"), _p(x, torch.float32, "x"), rows, x.numel() // max(rows, 1),
+                                         _p(scale, torch.float32, "scale"), _p(zero_point, torch.float32, "zero_point"),
+                                         int(qmin), int(qmax), float(grad_factor), _p(dx, torch.float32, "dx"),
+                                         _p(ds, torch.float32), _p(dz, torch.float32), _stream()), "fq_learnable_bwd")
+    return dx, ds, dz
+
+
 def split_planes(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """fp32 [..] -> bf16 [2, ..] (hi, lo)."""
     if out is None:
@@ -612,7 +637,7 @@ def _wrap(name, fn, tag_fn=None):
     return inner
 
 
-for _nm in ("zero_", "minmax_reset", "minmax_accumulate", "obs_update", "fq_apply", "fq_weight", "fq_weight_grouped", "fq_bwd", "split_planes",
+for _nm in ("zero_", "minmax_reset", "minmax_accumulate", "obs_update", "fq_apply", "fq_weight", "fq_weight_grouped", "fq_bwd", "fq_learnable_fwd", "fq_learnable_bwd", "split_planes",
            "kd_ce_loss", "splitk_reduce", "colsum_reduce", "colsum_rows",
            "embed_fwd", "im2col_fq", "softmax_planes", "attn_ds", "head_fwd", "head_bwd", "attn_fwd", "attn_bwd", "attn_bwd_gp",
            "int8_linear", "quantize_u8", "qparams_from_minmax", "im2col_u8", "gelu_minmax"):
