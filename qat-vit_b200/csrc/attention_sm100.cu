@@ -33,7 +33,7 @@ using namespace qvptx;
 
 namespace {
 
-constexpr int AT_THREADS = 320;
+constexpr int AT_THREADS = 576;                // forward: warp 0 TMA, warp 1 MMA, warps 2-17 softmax / output (two per row)
 constexpr int HD = 64;                       // head dim
 constexpr int Q_TILE_BYTES = 128 * HD * 2;   // 16 KB: 128 query rows x 64 bf16
 constexpr int K_PLANE_BYTES = 224 * HD * 2;  // 28 KB: up to 224 keys x 64 bf16
@@ -47,7 +47,9 @@ struct AttnCfg {
   static constexpr int Q_BYTES = NPL * 2 * Q_TILE_BYTES;
   static constexpr int K_BYTES = NPL * K_PLANE_BYTES;
   static constexpr int V_BYTES = NPL * V_PLANE_BYTES;
-  static constexpr int SMEM_BYTES = Q_BYTES + K_BYTES + V_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int STAGE_BYTES = 16 * 2048;           // per softmax warp: 32 rows x 64 B, the output transpose
+  static constexpr int SMEM_BYTES = Q_BYTES + K_BYTES + V_BYTES + 8192 /*row max / exponent / sum exchange*/ + STAGE_BYTES + 1024 /*align slack*/ +
+                                    256 /*barriers*/;
   static constexpr int NPAIRS_S = (NPL == 2) ? 3 : 1;    // (hi,hi) (hi,lo) (lo,hi)  |  codes x codes
   static constexpr int NPAIRS_PV = (NPL == 2) ? 3 : 2;   // P is always hi/lo;  V hi/lo or exact codes
 };
@@ -93,6 +95,72 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// 32 lanes x 16 consecutive columns (one 16-key piece: the register budget of the two-warps-per-lane-quarter layouts)
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
+// Packed fp32 pairs (FFMA2 / FADD2 / FMUL2: one issue slot for two elements -- the chunk / softmax warps are issue- and
+// latency-bound, not pipe-bound).  Same IEEE round-to-nearest results as the scalar forms, element by element.
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_pack_u(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_sub(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// (a0, a1) -> bf16 hi pair + bf16 pair of the exact residuals (same values as split_pack2; the residual is one packed subtract)
+__device__ __forceinline__ void split_pack2_f2(uint64_t a, uint32_t& hi, uint32_t& lo) {
+  float a0, a1;
+  f2_unpack(a, a0, a1);
+  const __nv_bfloat162 h2 = __floats2bfloat162_rn(a0, a1);
+  hi = *reinterpret_cast<const uint32_t*>(&h2);
+  float r0, r1;
+  f2_unpack(f2_sub(a, f2_pack_u(hi << 16, hi & 0xffff0000u)), r0, r1);
+  const __nv_bfloat162 l2 = __floats2bfloat162_rn(r0, r1);
+  lo = *reinterpret_cast<const uint32_t*>(&l2);
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -108,6 +176,108 @@ __device__ __forceinline__ void split_pack2(float a0, float a1, uint32_t& hi, ui
   lo = *reinterpret_cast<const uint32_t*>(&l2);
 }
 
+#ifdef QV_ATTN_DEBUG
+__device__ unsigned long long qv_dbg_buf[3][8192];
+__device__ __forceinline__ void dbg_event(int who, int& n, int tag) {
+  if (blockIdx.x == 0 && n < 8192) qv_dbg_buf[who][n++] = (static_cast<unsigned long long>(tag) << 48) | (clock64() & 0xffffffffffffULL);
+}
+#define DBG(who, tag) dbg_event(who, dbg_n, tag)
+#else
+#define DBG(who, tag)
+#endif
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+// Softmax of one 16-key unit for one query row (TMEM lane): 16 fp32 logits (already in registers) in, un-normalised
+// probabilities 2^(s * c2 - r) out IN PLACE as bf16 pairs [hi 8 words | lo 8 words] (the A operand of the P V product: each
+// 16-key k-step reads 8 consecutive columns).  c2p = (scale * log2 e) twice, nrp = -r twice (r: the row's reference exponent);
+// returns the two partial sums packed.
+template <bool MASKED>
+__device__ __forceinline__ uint64_t fw_softmax_unit(uint32_t taddr, const uint32_t (&sv)[16], uint64_t c2p, uint64_t nrp,
+                                                    uint64_t sum2, int nvalid) {
+  uint32_t pk[16];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float e0, e1;
+    f2_unpack(f2_fma(f2_pack_u(sv[2 * j], sv[2 * j + 1]), c2p, nrp), e0, e1);
+    e0 = ex2_approx(e0);
+    e1 = ex2_approx(e1);
+    if constexpr (MASKED) {
+      e0 = (2 * j < nvalid) ? e0 : 0.f;
+      e1 = (2 * j + 1 < nvalid) ? e1 : 0.f;
+    }
+    const uint64_t e = f2_pack(e0, e1);
+    sum2 = f2_add(sum2, e);
+    split_pack2_f2(e, pk[j], pk[8 + j]);
+  }
+  tmem_st_32x16(taddr, pk);
+  return sum2;
+}
+// max of a unit's valid logits
+__device__ __forceinline__ float fw_unit_max(const uint32_t (&sv)[16], int nvalid) {
+  float m0 = -INFINITY, m1 = -INFINITY;
+  if (nvalid >= 16) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      m0 = fmax3(m0, __uint_as_float(sv[4 * j]), __uint_as_float(sv[4 * j + 1]));
+      m1 = fmax3(m1, __uint_as_float(sv[4 * j + 2]), __uint_as_float(sv[4 * j + 3]));
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) m0 = (j < nvalid) ? fmaxf(m0, __uint_as_float(sv[j])) : m0;
+  }
+  return fmaxf(m0, m1);
+}
+// RARE PATH: multiply the probabilities already written for units [u0, u1) of this lane's row by f, an exact power of two <= 1
+// (the row's reference exponent moved up): hi and lo bf16 parts scale exactly (underflow flushes towards zero, as it should).
+__device__ __noinline__ void fw_rescale_units(uint32_t s_tmem, int u0, int u1, float f) {
+  for (int u = u0; u < u1; ++u) {
+    uint32_t w[16];
+    tmem_ld_32x16(s_tmem + u * 16, w);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(w[j] << 16) * f, __uint_as_float(w[j] & 0xffff0000u) * f);
+      w[j] = *reinterpret_cast<const uint32_t*>(&h2);
+    }
+    tmem_st_32x16(s_tmem + u * 16, w);
+  }
+  tmem_st_wait();
+}
+
+// Each lane of a warp holds NCH 16-byte chunks (NCH * 16 contiguous bytes) of ITS OWN row; the 32 rows are `row_pitch` bytes
+// apart in global memory.  Written straight from the registers, one store instruction would touch 32 different 128-byte lines
+// (one LSU wavefront per lane: the forward's output phase was bound by exactly that).  Instead the tile goes through a 2 KB
+// swizzled shared-memory buffer and leaves row-run by row-run: a store instruction then covers 32 / NCH rows x (NCH * 16) bytes.
+// `base` = global address of the warp's first row's run; rows >= n_rows are skipped.  Whole warp calls; NCH = 2 or 4.
+template <int NCH>
+__device__ __forceinline__ void warp_store_row_runs(uint8_t* stage, int lane, const uint4 (&v)[NCH], uint8_t* base, int64_t row_pitch,
+                                                    int n_rows) {
+  const uint32_t sbase = smem_u32(stage);
+  __syncwarp();                                             // the previous pass through this buffer has been read out
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const uint32_t pos = static_cast<uint32_t>(c ^ ((lane >> 1) & (NCH - 1)));
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + lane * (NCH * 16) + pos * 16), "r"(v[c].x), "r"(v[c].y),
+                 "r"(v[c].z), "r"(v[c].w) : "memory");
+  }
+  __syncwarp();
+  constexpr int RPI = 32 / NCH;                             // rows per instruction
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    const int r = k * RPI + lane / NCH, c = lane % NCH;
+    const uint32_t pos = static_cast<uint32_t>(c ^ ((r >> 1) & (NCH - 1)));
+    uint4 w;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w)
+                 : "r"(sbase + r * (NCH * 16) + pos * 16) : "memory");
+    if (r < n_rows) *reinterpret_cast<uint4*>(base + r * row_pitch + c * 16) = w;
+  }
+}
+
 template <int NPL>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 qv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
@@ -118,7 +288,9 @@ qv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   uint8_t* sQ = smem;                       // [NPL][2 tiles][128 x 64]
   uint8_t* sK = sQ + C::Q_BYTES;            // [NPL][224 x 64]
   uint8_t* sV = sK + C::K_BYTES;            // [NPL][4 boxes][64 keys x 64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + C::V_BYTES);
+  float* xchg = reinterpret_cast<float*>(sV + C::V_BYTES);      // [3 kinds: first-unit max, reference exponent, sum][2 tiles][2 key halves][128 rows]
+  uint8_t* stage_all = reinterpret_cast<uint8_t*>(xchg + 2048); // [16 softmax warps][2 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_all + C::STAGE_BYTES);
   uint64_t* qk_full = bars + 0;
   uint64_t* qk_empty = bars + 1;
   uint64_t* v_full = bars + 2;
@@ -127,7 +299,6 @@ qv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   uint64_t* p_ready = bars + 6;             // [2]
   uint64_t* o_full = bars + 8;              // [2]
   uint64_t* tmem_free = bars + 10;          // [2]
-  uint64_t* delta_ready = bars + 10; // [2] rows 128.. of delta (item parity) written by the output warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5;
@@ -148,9 +319,9 @@ qv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     mbar_init(v_empty, 1);
     for (int g = 0; g < 2; ++g) {
       mbar_init(&s_full[g], 1);
-      mbar_init(&p_ready[g], 128);
+      mbar_init(&p_ready[g], 256);
       mbar_init(&o_full[g], 1);
-      mbar_init(&tmem_free[g], 128);
+      mbar_init(&tmem_free[g], 256);
     }
     fence_barrier_init();
   }
@@ -196,15 +367,21 @@ qv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       const uint64_t dK0 = umma_smem_desc(smem_u32(sK), 16u, 1024u);
       const uint64_t dV0 = umma_smem_desc(smem_u32(sV), 8192u, 1024u);        // MN-major V boxes
       int local = 0;
+#ifdef QV_ATTN_DEBUG
+      int dbg_n = 0;
+#endif
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
         const uint32_t ph = static_cast<uint32_t>(local & 1);
-        // TMEM of the previous item fully drained by both softmax groups
-        mbar_wait(&tmem_free[0], ph ^ 1);
-        if (mt == 2) mbar_wait(&tmem_free[1], ph ^ 1);
+        DBG(0, 21);
         mbar_wait(qk_full, ph);
-        tc_fence_after();
-        // ---- S_g = Q_g K^T ----
+        DBG(0, 22);
+        // ---- S_g = Q_g K^T (tile g's TMEM region must have been drained: O1 lives inside S0's columns) ----
         for (int g = 0; g < mt; ++g) {
+          if (g == 0) {
+            mbar_wait(&tmem_free[0], ph ^ 1);
+            if (mt == 2) mbar_wait(&tmem_free[1], ph ^ 1);
+          }
+          tc_fence_after();
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(g * S_COLS);
           if (elect_one()) {
 #pragma unroll
@@ -222,12 +399,15 @@ qv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         }
         if (elect_one()) umma_commit(qk_empty);  // Q / K smem may be refilled once the score MMAs have read it
         __syncwarp();
+        DBG(0, 23);
         // ---- O_g = P_g V ----
         mbar_wait(v_full, ph);
         for (int g = 0; g < mt; ++g) {
           mbar_wait(&p_ready[g], ph);
+          DBG(0, 24 + 3 * g);
           if (g == 1) mbar_wait(&o_full[0], ph);   // O1 lives in [0,64): P0 must have been consumed by the PV0 MMAs
           tc_fence_after();
+          DBG(0, 25 + 3 * g);
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(g == 0 ? O0_COL : 0);
           const uint32_t p_tmem = tmem_base + static_cast<uint32_t>(g * S_COLS);
           if (elect_one()) {
@@ -238,8 +418,8 @@ qv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
               const int pb = (NPL == 2) ? (pr == 1 ? 1 : 0) : 0;
               const uint64_t dv = dV0 + static_cast<uint64_t>(pb * 4 * (V_BOX_BYTES >> 4));
               for (int kk = 0; kk < ksteps_pv; ++kk) {
-                // 16 keys of P: 8 TMEM columns inside the 32-column chunk kk/2 -- [hi even | hi odd | lo even | lo odd]
-                const uint32_t a_tmem = p_tmem + static_cast<uint32_t>((kk >> 1) * 32 + pa * 16 + (kk & 1) * 8);
+                // 16 keys of P = 16 TMEM columns: [hi pairs 8 | lo pairs 8]
+                const uint32_t a_tmem = p_tmem + static_cast<uint32_t>(kk * 16 + pa * 8);
                 // key step kk: box kk/4 (8 KB each), 2048 bytes per step inside the box -> contiguous: kk * 2048 bytes
                 umma_bf16_ts(d_tmem, a_tmem, dv + static_cast<uint64_t>(kk) * 128u, idesc_pv, (pr > 0 || kk > 0) ? 1u : 0u);
               }
@@ -247,122 +427,189 @@ qv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             umma_commit(&o_full[g]);
           }
           __syncwarp();
+          DBG(0, 26 + 3 * g);
         }
         if (elect_one()) umma_commit(v_empty);
         __syncwarp();
       }
     }
   } else {
-    // =============================== softmax + output (one thread per query row) ===============================
-    const int g = (warp - 2) >> 2;               // query tile of this warp group
+    // =============================== softmax + output: TWO threads per query row ===============================
+    // Warp (g, q, hf): query tile g, TMEM lane quarter q (= warp id mod 4, the hardware's access rule), key half hf.  The two
+    // warps of a (g, q) pair split the row's keys in 16-key units (7 + 6 of 13 at T = 197) and its 64 output columns in halves;
+    // row max and row sum cross between them through shared memory and a 64-thread named barrier.  Four softmax warps per
+    // scheduler partition instead of two: the phase was latency-bound (issue slots 36 % busy, tensor pipe 15 %).
+    const int j4 = (warp - 2) >> 2;              // 0..3
+    const int g = j4 >> 1;                       // query tile
+    const int hf = j4 & 1;                       // key half / output column half
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
     if (g < mt) {
       const int row_in_tile = q * 32 + lane;
+      const bool warp_has_rows = g * 128 + q * 32 < p.T;          // else: all 32 rows are padding -- only keep the barrier protocol
       const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
       const uint32_t s_tmem = tmem_base + lane_addr + static_cast<uint32_t>(g * S_COLS);
-      const uint32_t o_tmem = tmem_base + lane_addr + static_cast<uint32_t>(g == 0 ? O0_COL : 0);
-      const int nch = (n_keys + 31) >> 5;        // 32-column chunks (the tail chunk may hold 16 stale columns: masked)
+      const uint32_t o_tmem = tmem_base + lane_addr + static_cast<uint32_t>(g == 0 ? O0_COL : 0) + static_cast<uint32_t>(hf * 32);
+      const int nu = n_keys >> 4;                // 16-key units
+      const int u_lo = hf == 0 ? 0 : (nu + 1) >> 1, u_hi = hf == 0 ? (nu + 1) >> 1 : nu;
+      float* x_max = xchg + (g * 2 + hf) * 128 + row_in_tile;      // mine; the partner's is 128 floats away
+      float* x_sum = x_max + 1024;                                 // x_max + 512: the reference exponents
+      const int partner = (hf == 0) ? 128 : -128;
+      const int bar_id = 1 + g * 4 + q;
+      uint8_t* my_stage = stage_all + (warp - 2) * 2048;
       float sc = p.scale;
       float vs = 1.0f;
       if (p.qk_scale) { const float s = __ldg(p.qk_scale); sc *= s * s; }
       if (p.v_scale) vs = __ldg(p.v_scale);
       const float c2 = sc * 1.4426950408889634f;  // logits -> base-2 exponent
+      const uint64_t c2p = f2_pack(c2, c2);
       float amax = 0.f;                           // mixed plane output: largest |value| written by this thread
       int local = 0;
+#ifdef QV_ATTN_DEBUG
+      int dbg_n = (threadIdx.x == 128 || threadIdx.x == 384) ? 0 : 8192;     // warp 4 = (g 0, q 0, hf 0); warp 12 = (g 1, q 0, hf 0)
+      const int dbg_who = threadIdx.x == 128 ? 1 : 2;
+#endif
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
         const int b = item / p.H, h = item % p.H;
         const uint32_t ph = static_cast<uint32_t>(local & 1);
+        DBG(dbg_who, 30);
         mbar_wait(&s_full[g], ph);
         tc_fence_after();
-        uint32_t rr[32], nxt[32];
-        // ---- pass 1: row max over the T valid keys ----
-        float mx = -INFINITY;
-        tmem_ld_32x32(s_tmem, nxt);
-#pragma unroll 1
-        for (int c = 0; c < nch; ++c) {
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) rr[j] = nxt[j];
-          if (c + 1 < nch) tmem_ld_32x32(s_tmem + (c + 1) * 32, nxt);
-          const int nvalid = p.T - c * 32;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) mx = (j < nvalid) ? fmaxf(mx, __uint_as_float(rr[j])) : mx;
-        }
-        // ---- pass 2: e = exp2((s - max) * c2); row sum; P hi/lo written in place ----
-        const float mxc = mx * c2;
-        float sum = 0.f;
-        tmem_ld_32x32(s_tmem, nxt);
-#pragma unroll 1
-        for (int c = 0; c < nch; ++c) {
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) rr[j] = nxt[j];
-          if (c + 1 < nch) tmem_ld_32x32(s_tmem + (c + 1) * 32, nxt);
-          const int nvalid = p.T - c * 32;
-          uint32_t pk[32];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float e0 = (2 * j < nvalid) ? ex2_approx(fmaf(__uint_as_float(rr[2 * j]), c2, -mxc)) : 0.f;
-            const float e1 = (2 * j + 1 < nvalid) ? ex2_approx(fmaf(__uint_as_float(rr[2 * j + 1]), c2, -mxc)) : 0.f;
-            sum += e0 + e1;
-            split_pack2(e0, e1, pk[j], pk[16 + j]);   // keys 32c+2j, +1: hi pairs in words 0..15, lo pairs in 16..31
+        DBG(dbg_who, 31);
+        // ---- ONE pass over the scores (TMEM reads, 64 B/clk per SM, bound this phase: a separate max pass read every score
+        // twice).  P_j = 2^(s_j c2 - r) for a per-row reference exponent r -- ANY r gives the same normalised result as long as
+        // nothing overflows, so r = ceil(c2 * max over the first 16-key unit of both halves) (exchanged), and a later unit whose
+        // maximum exceeds r by more than 2^64 moves r up by an integer: what that lane has already written is rescaled by the
+        // exact power of two (rare: it needs a key > 44 nats above the best of 32 sampled keys).  The halves reconcile their r
+        // the same way before P is released.  lse = r ln 2 + ln(sum). ----
+        float r = -INFINITY, sum = 0.f;            // r in log2 units, integer-valued
+        if (warp_has_rows) {
+          uint32_t sv[16];
+          float m0 = -INFINITY;
+          if (u_lo < u_hi) {
+            tmem_ld_32x16(s_tmem + u_lo * 16, sv);
+            tmem_ld_wait();
+            m0 = fw_unit_max(sv, p.T - u_lo * 16);
           }
-          tmem_st_32x32(s_tmem + c * 32, pk);
+          *x_max = m0;
+          asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+          r = ceilf(fmaxf(m0, x_max[partner]) * c2);
+          DBG(dbg_who, 32);
+          uint64_t sum2 = 0ull;
+#pragma unroll 1
+          for (int u = u_lo; u < u_hi; ++u) {
+            const int nvalid = p.T - u * 16;
+            if (u > u_lo) {
+              tmem_ld_32x16(s_tmem + u * 16, sv);
+              tmem_ld_wait();
+              const float need = fmaf(fw_unit_max(sv, nvalid), c2, -r);
+              if (__any_sync(0xffffffffu, need > 64.f)) {              // rare: re-base this lane's row
+                const float r_new = need > 64.f ? r + ceilf(need) : r;
+                const float f = ex2_approx(r - r_new);                    // exact: integer argument (1.0 for untouched lanes)
+                fw_rescale_units(s_tmem, u_lo, u, f);
+                sum2 = f2_mul(sum2, f2_pack(f, f));
+                r = r_new;
+              }
+            }
+            const float nr = -r;
+            if (nvalid >= 16) sum2 = fw_softmax_unit<false>(s_tmem + u * 16, sv, c2p, f2_pack(nr, nr), sum2, nvalid);
+            else sum2 = fw_softmax_unit<true>(s_tmem + u * 16, sv, c2p, f2_pack(nr, nr), sum2, nvalid);
+          }
+          float s0, s1;
+          f2_unpack(sum2, s0, s1);
+          sum = s0 + s1;
+          x_max[512] = r;                                               // third exchange array: [1024, 1536)
+          *x_sum = sum;
+          asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+          const float r_p = x_max[512 + partner], sum_p = x_sum[partner];
+          const float R = fmaxf(r, r_p);
+          const float f = ex2_approx(r - R), f_p = ex2_approx(r_p - R);   // exact powers of two; 2^-inf = 0 for an empty half
+          if (__any_sync(0xffffffffu, f != 1.0f) && u_lo < u_hi) fw_rescale_units(s_tmem, u_lo, u_hi, f);
+          sum = sum * f + sum_p * f_p;
+          r = R;
+          tmem_st_wait();
         }
-        tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&p_ready[g]);
-        // ---- output: O / rowsum (* s) -> bf16 hi/lo planes ----
+        DBG(dbg_who, 33);
+        // ---- output: O / rowsum (* s) -> bf16 hi/lo planes, this thread's 32 of the 64 columns ----
         mbar_wait(&o_full[g], ph);
         tc_fence_after();
-        uint32_t o[64];
-        tmem_ld_32x64(o_tmem, o);
-        tmem_ld_wait();
+        DBG(dbg_who, 34);
+        uint32_t o[32];
+        if (warp_has_rows) {
+          tmem_ld_32x32(o_tmem, o);
+          tmem_ld_wait();
+        }
         tc_fence_before();
         mbar_arrive(&tmem_free[g]);
+        DBG(dbg_who, 36);
         const int t = g * 128 + row_in_tile;
-        if (t < p.T) {
-          const float inv = vs / sum;
-          const int64_t row = static_cast<int64_t>(b) * p.T + t;
+        if (warp_has_rows) {
+          // rows of this warp: t0w .. t0w + 31, the first n_rows of them real
+          const int t0w = g * 128 + q * 32;
+          const int n_rows = min(32, p.T - t0w);
+          const float inv = vs / sum;                               // padded rows: finite garbage, never stored
+          const int64_t row0 = static_cast<int64_t>(b) * p.T + t0w;
           if (p.out) {
-            __nv_bfloat16* dst_hi = p.out + row * p.out_ld + h * HD;
-            __nv_bfloat16* dst_lo = dst_hi + p.out_plane_stride;
+            uint8_t* hi0 = reinterpret_cast<uint8_t*>(p.out + row0 * p.out_ld + h * HD);            // plane 0, this head, row t0w
+            uint8_t* lo0 = hi0 + p.out_plane_stride * 2;
+            const int64_t pitch = p.out_ld * 2;
             if (p.out_fmt == 1) {      // a head's 64 columns are exactly one block of the mixed format: 64 hi8 | 64 lo8
-              uint8_t* row1 = reinterpret_cast<uint8_t*>(dst_lo);
+              uint4 h16v[4], h8v[2], l8v[2];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                uint32_t h16[4], ph[4], pl[4];
+              for (int j = 0; j < 4; ++j) {
+                uint32_t h16[4], ph8[4], pl8[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const float a0 = __uint_as_float(o[8 * j + 2 * e]) * inv, a1 = __uint_as_float(o[8 * j + 2 * e + 1]) * inv;
-                  amax = fmaxf(amax, fmaxf(fabsf(a0), fabsf(a1)));
-                  h16[e] = qv_mix_split2<QV_MIX_ACT>(a0, a1, ph[e], pl[e]);
+                  if (t < p.T) amax = fmaxf(amax, fmaxf(fabsf(a0), fabsf(a1)));
+                  h16[e] = qv_mix_split2<QV_MIX_ACT>(a0, a1, ph8[e], pl8[e]);
                 }
-                *reinterpret_cast<uint4*>(dst_hi + 8 * j) = make_uint4(h16[0], h16[1], h16[2], h16[3]);
-                *reinterpret_cast<uint2*>(row1 + 8 * j) = make_uint2(ph[0] | (ph[1] << 16), ph[2] | (ph[3] << 16));
-                *reinterpret_cast<uint2*>(row1 + 64 + 8 * j) = make_uint2(pl[0] | (pl[1] << 16), pl[2] | (pl[3] << 16));
+                h16v[j] = make_uint4(h16[0], h16[1], h16[2], h16[3]);
+                const uint32_t w0 = ph8[0] | (ph8[1] << 16), w1 = ph8[2] | (ph8[3] << 16);
+                const uint32_t x0 = pl8[0] | (pl8[1] << 16), x1 = pl8[2] | (pl8[3] << 16);
+                if (j & 1) { h8v[j >> 1].z = w0; h8v[j >> 1].w = w1; l8v[j >> 1].z = x0; l8v[j >> 1].w = x1; }
+                else { h8v[j >> 1].x = w0; h8v[j >> 1].y = w1; l8v[j >> 1].x = x0; l8v[j >> 1].y = x1; }
               }
+              warp_store_row_runs<4>(my_stage, lane, h16v, hi0 + hf * 64, pitch, n_rows);
+              warp_store_row_runs<2>(my_stage, lane, h8v, lo0 + hf * 32, pitch, n_rows);
+              warp_store_row_runs<2>(my_stage, lane, l8v, lo0 + 64 + hf * 32, pitch, n_rows);
             } else {
+              uint4 hv[4], lv[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              uint32_t hi[4], lo[4];
+              for (int j = 0; j < 4; ++j) {
+                uint32_t hi[4], lo[4];
 #pragma unroll
-              for (int e = 0; e < 4; ++e)
-                split_pack2(__uint_as_float(o[8 * j + 2 * e]) * inv, __uint_as_float(o[8 * j + 2 * e + 1]) * inv, hi[e], lo[e]);
-              *reinterpret_cast<uint4*>(dst_hi + 8 * j) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-              *reinterpret_cast<uint4*>(dst_lo + 8 * j) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            }
+                for (int e = 0; e < 4; ++e)
+                  split_pack2(__uint_as_float(o[8 * j + 2 * e]) * inv, __uint_as_float(o[8 * j + 2 * e + 1]) * inv, hi[e], lo[e]);
+                hv[j] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                lv[j] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              }
+              DBG(dbg_who, 37);
+              warp_store_row_runs<4>(my_stage, lane, hv, hi0 + hf * 64, pitch, n_rows);
+              DBG(dbg_who, 38);
+              warp_store_row_runs<4>(my_stage, lane, lv, lo0 + hf * 64, pitch, n_rows);
+              DBG(dbg_who, 39);
             }
           }
           if (p.out_f32) {
-            float* dst = p.out_f32 + row * (static_cast<int64_t>(p.H) * HD) + h * HD;
+            uint8_t* f0 = reinterpret_cast<uint8_t*>(p.out_f32 + row0 * (static_cast<int64_t>(p.H) * HD) + h * HD + hf * 32);
+            const int64_t pitch = static_cast<int64_t>(p.H) * HD * 4;
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(__uint_as_float(o[4 * j]) * inv, __uint_as_float(o[4 * j + 1]) * inv,
-                                                                    __uint_as_float(o[4 * j + 2]) * inv, __uint_as_float(o[4 * j + 3]) * inv);
+            for (int half = 0; half < 2; ++half) {
+              uint4 fv[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int k = 16 * half + 4 * j;
+                fv[j] = make_uint4(__float_as_uint(__uint_as_float(o[k]) * inv), __float_as_uint(__uint_as_float(o[k + 1]) * inv),
+                                   __float_as_uint(__uint_as_float(o[k + 2]) * inv), __float_as_uint(__uint_as_float(o[k + 3]) * inv));
+              }
+              warp_store_row_runs<4>(my_stage, lane, fv, f0 + half * 64, pitch, n_rows);
+            }
           }
-          if (p.lse) p.lse[(static_cast<int64_t>(b) * p.H + h) * p.T + t] = mx * sc + logf(sum);
+          if (p.lse && hf == 0 && t < p.T) p.lse[(static_cast<int64_t>(b) * p.H + h) * p.T + t] = r * 0.69314718055994531f + logf(sum);
         }
+        DBG(dbg_who, 35);
       }
       if (p.sat_flag && __any_sync(0xffffffffu, amax > QV_MIX_ACT_MAX) && lane == 0) atomicOr(p.sat_flag, p.sat_bit);
     }
@@ -423,6 +670,7 @@ constexpr int BW_TILE_ROWS = 224;
 constexpr int BW_TILE_BYTES = BW_TILE_ROWS * HD * 2;
 constexpr int BW_STAGE_BYTES = 8 * 2 * 4096;    // per compute warp: two 4 KB staging buffers (y tile in, gradient tile out)
 constexpr int BW_SMEM_BYTES = 5 * BW_TILE_BYTES + 4096 /*lse, delta*/ + BW_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int BW_THREADS = 576;                  // warps: 0 TMA, 1 MMA, 2-9 chunk, 10-17 output (two of each per TMEM lane quarter)
 constexpr uint32_t BW_ACC_COL = 256;             // accumulator set p (sub-pass parity): ACC0 at 256 + 128 p (dQ / dV), ACC1 64 further (dK)
 
 struct AttnBwdParams {
@@ -448,21 +696,54 @@ struct AttnBwdParams {
   float* colsum;            // [B * m_tiles * 4][3*D]
 };
 
-#ifdef QV_ATTN_DEBUG
-__device__ unsigned long long qv_dbg_buf[3][8192];
-__device__ __forceinline__ void dbg_event(int who, int& n, int tag) {
-  if (blockIdx.x == 0 && n < 8192) qv_dbg_buf[who][n++] = (static_cast<unsigned long long>(tag) << 48) | (clock64() & 0xffffffffffffULL);
-}
-#define DBG(who, tag) dbg_event(who, dbg_n, tag)
-#else
-#define DBG(who, tag)
-#endif
 
 __device__ __forceinline__ float bf16lo_f(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16hi_f(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
+// One 16-column piece of a chunk for one TMEM lane (row): S / dP in, dz (pass A) or P^T and dz^T (pass B) out, in place, as
+// bf16 pairs [hi 8 words | lo 8 words].  nLp / ndp: this row's -lse*log2e and -delta (pass A, packed twice); lse_sa / delta_sa:
+// shared-memory addresses of the 16 columns' -lse*log2e and -delta (pass B, broadcast reads).  MASKED: the piece straddles T.
+template <bool PASS_A, bool MASKED>
+__device__ __forceinline__ void bw_chunk_piece(uint32_t S, uint32_t R, uint64_t c2p, uint64_t nLp, uint64_t ndp,
+                                               uint32_t lse_sa, uint32_t delta_sa, int nvalid) {
+  uint32_t sv[16], dv[16];
+  tmem_ld_32x16(S, sv);
+  tmem_ld_32x16(R, dv);
+  uint64_t nL[8], nd[8];
+  if constexpr (!PASS_A) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(nL[2 * i]), "=l"(nL[2 * i + 1]) : "r"(lse_sa + 16 * i));
+      asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(nd[2 * i]), "=l"(nd[2 * i + 1]) : "r"(delta_sa + 16 * i));
+    }
+  }
+  tmem_ld_wait();
+  uint32_t pz[16], pp[16];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float e0, e1;
+    f2_unpack(f2_fma(f2_pack_u(sv[2 * j], sv[2 * j + 1]), c2p, PASS_A ? nLp : nL[j]), e0, e1);
+    float p0 = ex2_approx(e0), p1 = ex2_approx(e1);
+    if constexpr (MASKED && !PASS_A) {
+      p0 = (2 * j < nvalid) ? p0 : 0.f;
+      p1 = (2 * j + 1 < nvalid) ? p1 : 0.f;
+    }
+    const uint64_t pr = f2_pack(p0, p1);
+    uint64_t z = f2_mul(pr, f2_add(f2_pack_u(dv[2 * j], dv[2 * j + 1]), PASS_A ? ndp : nd[j]));
+    if constexpr (MASKED && PASS_A) {
+      float z0, z1;
+      f2_unpack(z, z0, z1);
+      z = f2_pack((2 * j < nvalid) ? z0 : 0.f, (2 * j + 1 < nvalid) ? z1 : 0.f);
+    }
+    split_pack2_f2(z, pz[j], pz[8 + j]);
+    if constexpr (!PASS_A) split_pack2_f2(pr, pp[j], pp[8 + j]);
+  }
+  if constexpr (!PASS_A) tmem_st_32x16(S, pp);
+  tmem_st_32x16(R, pz);
+}
+
 template <bool FUSED>
-__global__ void __launch_bounds__(AT_THREADS, 1)
+__global__ void __launch_bounds__(BW_THREADS, 1)
 qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
                    const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_o,
                    const AttnBwdParams p) {
@@ -473,9 +754,9 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
   uint8_t* sV = sK + BW_TILE_BYTES;
   uint8_t* sDOh = sV + BW_TILE_BYTES;
   uint8_t* sDOl = sDOh + BW_TILE_BYTES;
-  float* lse2_s = reinterpret_cast<float*>(sDOl + BW_TILE_BYTES);   // [256] lse * log2(e)
-  float* delta_all = lse2_s + 256;                                   // [2 item parities][256] (dO . O) / s
-  uint8_t* stage_s = reinterpret_cast<uint8_t*>(lse2_s + 1024);     // [4 output warps][4][4 KB], 1024-byte aligned
+  float* lse2_s = reinterpret_cast<float*>(sDOl + BW_TILE_BYTES);   // [256] -lse * log2(e)   (negated: the packed fma adds it)
+  float* delta_all = lse2_s + 256;                                   // [2 item parities][256] -(dO . O) / s  (negated likewise)
+  uint8_t* stage_s = reinterpret_cast<uint8_t*>(lse2_s + 1024);     // [8 output warps][2][4 KB], 1024-byte aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(stage_s + BW_STAGE_BYTES);
   uint64_t* ld_full = bars + 0;
   uint64_t* ld_empty = bars + 1;
@@ -483,9 +764,8 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
   uint64_t* cmp_done = bars + 4;     // [2] chunk warps have turned buffer b into dz / P^T
   uint64_t* acc_done = bars + 6;     // [2] accumulator set p complete
   uint64_t* epi_done = bars + 8;     // [2] accumulator set p drained by the output warps
-  uint64_t* delta_ready = bars + 10; // [2] rows 128.. of delta (item parity) written by the output warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
-  uint64_t* y_bar = bars + 13;       // [4 output warps][4]: y tile landed in staging buffer k
+  uint64_t* y_bar = bars + 13;       // [8 output warps][2]: y tile landed in staging buffer k
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -503,14 +783,13 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
     mbar_init(ld_empty, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&mma1_done[b], 1);
-      mbar_init(&cmp_done[b], 128);
+      mbar_init(&cmp_done[b], 256);
       mbar_init(&acc_done[b], 1);
-      mbar_init(&epi_done[b], 128);
-      mbar_init(&delta_ready[b], 128);
+      mbar_init(&epi_done[b], 256);
     }
     if constexpr (FUSED) {
       prefetch_tensormap(&map_y);
-      for (int w = 0; w < 16; ++w) mbar_init(&y_bar[w], 1);
+      for (int w = 0; w < 16; ++w) mbar_init(&y_bar[w], 1);      // [8 output warps][2]
     }
     prefetch_tensormap(&map_o);
     fence_barrier_init();
@@ -521,11 +800,12 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // delta_i = (dO_i . O_i) / s for token rows [row_lo, row_lo + 128) of item (b, h) from global memory: 8 lanes per row, 8 columns
-  // each, 16 independent 16-byte loads in flight per lane; `w4` = this warp's index 0..3 inside its group of four.
-  auto delta_rows = [&](float* dst, int b, int h, int row_lo, int w4, float inv_s) {
+  // dst[r] = -(dO_r . O_r) / s for token rows of [row_lo, row_lo + 128) of item (b, h) from global memory: 8 lanes per row, 8
+  // columns each, 16 independent 16-byte loads in flight per lane; `w4` = this warp's index 0..3 inside its group of four; the
+  // group covers the 64-row halves [half_lo, half_hi) of the range (chunk warps: one half per group of four; output warps: both).
+  auto delta_rows = [&](float* dst, int b, int h, int row_lo, int w4, float inv_s, int half_lo, int half_hi) {
 #pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
+    for (int half = half_lo; half < half_hi; ++half) {
       uint4 oh[4], ol[4], dh[4], dl[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -555,7 +835,7 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         dot += __shfl_xor_sync(0xffffffffu, dot, 1);
         dot += __shfl_xor_sync(0xffffffffu, dot, 2);
         dot += __shfl_xor_sync(0xffffffffu, dot, 4);
-        if ((lane & 7) == 0) dst[r] = dot * inv_s;
+        if ((lane & 7) == 0) dst[r] = -dot * inv_s;
       }
     }
   };
@@ -573,6 +853,18 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         tma_load_4d(sV, &map_qkv, ld_full, 2 * D + h * HD, 0, b, 0);
         tma_load_4d(sDOh, &map_do, ld_full, h * HD, 0, b, 0);
         tma_load_4d(sDOl, &map_do, ld_full, h * HD, 0, b, 1);
+        // The tiles are single-buffered (140 KB of the 227 KB), so the next item's loads start only when this item's last MMA
+        // has read them -- and every CTA reaches that point together (20 MB in one burst).  Pull the next item's tiles into L2
+        // now, while this item computes: the real loads then hit L2.
+        const int nitem = item + static_cast<int>(gridDim.x);
+        if (nitem < num_items) {
+          const int nb = nitem / p.H, nh = nitem % p.H;
+          tma_prefetch_l2_4d(&map_qkv, nh * HD, 0, nb, 0);
+          tma_prefetch_l2_4d(&map_qkv, D + nh * HD, 0, nb, 0);
+          tma_prefetch_l2_4d(&map_qkv, 2 * D + nh * HD, 0, nb, 0);
+          tma_prefetch_l2_4d(&map_do, nh * HD, 0, nb, 0);
+          tma_prefetch_l2_4d(&map_do, nh * HD, 0, nb, 1);
+        }
       }
     }
   } else if (warp == 1) {
@@ -628,22 +920,22 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
               if (kk < ks) {
-                const uint32_t off = static_cast<uint32_t>((kk >> 1) * 32 + (kk & 1) * 8);
+                const uint32_t off = static_cast<uint32_t>(kk * 16);     // 16 keys = 16 columns: [hi pairs 8 | lo pairs 8]
                 umma_bf16_ts(acc0, R + off, bK + 128 * kk, idesc_ts, kk > 0 ? 1u : first0);
-                umma_bf16_ts(acc0, R + off + 16, bK + 128 * kk, idesc_ts, 1u);
+                umma_bf16_ts(acc0, R + off + 8, bK + 128 * kk, idesc_ts, 1u);
               }
             }
           } else {                                                       // dV and dK chains interleaved (independent tiles)
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
               if (kk < ks) {
-                const uint32_t off = static_cast<uint32_t>((kk >> 1) * 32 + (kk & 1) * 8);
+                const uint32_t off = static_cast<uint32_t>(kk * 16);
                 const uint32_t first = kk > 0 ? 1u : first0;
                 umma_bf16_ts(acc0, S + off, bDh + 128 * kk, idesc_ts, first);            // dV += P^T dO : (hi,hi)
                 umma_bf16_ts(acc1, R + off, bQ + 128 * kk, idesc_ts, first);             // dK += dz^T Q : hi
                 umma_bf16_ts(acc0, S + off, bDl + 128 * kk, idesc_ts, 1u);               //               (hi,lo)
-                umma_bf16_ts(acc1, R + off + 16, bQ + 128 * kk, idesc_ts, 1u);           //                lo
-                umma_bf16_ts(acc0, S + off + 16, bDh + 128 * kk, idesc_ts, 1u);          //               (lo,hi)
+                umma_bf16_ts(acc1, R + off + 8, bQ + 128 * kk, idesc_ts, 1u);            //                lo
+                umma_bf16_ts(acc0, S + off + 8, bDh + 128 * kk, idesc_ts, 1u);           //               (lo,hi)
               }
             }
           }
@@ -687,16 +979,21 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         __syncwarp();
       }
     }
-  } else if (warp < 6) {
-    // =============================== chunk warps (one per TMEM lane quarter) ===============================
+  } else if (warp < 10) {
+    // =============================== chunk warps (TWO per TMEM lane quarter) ===============================
+    // Warps 2-5 convert columns [0, 32) of every 64-column chunk, warps 6-9 columns [32, 64): each scheduler partition
+    // then holds two chunk warps (one alone sat at IPC ~0.25, latency-bound -- the chunk math was the critical path of an
+    // item: 28 us against 9.6 us of MMA work).  A 32-column half goes through the registers as two 16-column pieces
+    // (tcgen05.ld / st .x16) with packed-pair fp32 math; validity masks only in a piece that straddles T.
     const int q = warp & 3;
-    const int w4 = warp - 2;
+    const int hf = (warp - 2) >> 2;              // which 32-column half of a chunk
     const int row = q * 32 + lane;               // row inside the 128-row tile == TMEM lane
-    const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(hf * 32);
     const float s = p.qscale ? __ldg(p.qscale) : 1.0f;
     const float inv_s = 1.0f / s;
     const float c2 = p.scale * s * s * 1.4426950408889634f;
-    const int ctid = threadIdx.x - 64;           // 0..127
+    const uint64_t c2p = f2_pack(c2, c2);
+    const int ctid = threadIdx.x - 64;           // 0..255
     uint32_t st = 0;
 #ifdef QV_ATTN_DEBUG
     int dbg_n = (threadIdx.x == 64) ? 0 : 8192;
@@ -706,23 +1003,19 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
       const int b = item / p.H, h = item % p.H;
       const float* lse_bh = p.lse + (static_cast<int64_t>(b) * p.H + h) * p.T;
       float* delta_s = delta_all + (local & 1) * 256;
+      const uint32_t lse_s32 = smem_u32(lse2_s), delta_s32 = smem_u32(delta_s);
       DBG(1, 10);
-      asm volatile("bar.sync 9, 128;" ::: "memory");            // previous item's pass B has finished reading lse2_s
-      lse2_s[ctid] = (ctid < p.T) ? __ldg(lse_bh + ctid) * 1.4426950408889634f : 0.0f;
-      lse2_s[128 + ctid] = (128 + ctid < p.T) ? __ldg(lse_bh + 128 + ctid) * 1.4426950408889634f : 0.0f;
-      delta_rows(delta_s, b, h, 0, w4, inv_s);                   // rows 0..127 (tile 0) from global memory while the tiles land;
-      asm volatile("bar.sync 9, 128;" ::: "memory");            // rows 128.. were written an item ahead by the output warps
+      asm volatile("bar.sync 9, 256;" ::: "memory");            // previous item's pass B has finished reading lse2_s
+      lse2_s[ctid] = (ctid < p.T) ? -__ldg(lse_bh + ctid) * 1.4426950408889634f : 0.0f;
+      delta_rows(delta_s, b, h, hf * 128, q, inv_s, 0, 2);       // all 256 rows, 32 per warp, from global memory while the tiles land
+      asm volatile("bar.sync 9, 256;" ::: "memory");
       DBG(1, 11);
-      bool have_hi = false;
       for (int sub = 0; sub < nsub; ++sub) {
         const bool pass_a = sub < mt;
         const int tile = pass_a ? sub : sub - mt;
-        if (!have_hi && (sub > 0 || mt == 1)) {                  // anything past pass A / tile 0 touches rows >= 128
-          mbar_wait(&delta_ready[local & 1], (static_cast<uint32_t>(local) >> 1) & 1);
-          have_hi = true;
-        }
         const int tok = tile * 128 + row;                         // query (pass A) / key (pass B) of this lane
-        const float Li = lse2_s[tok & 255], di = delta_s[tok & 255];
+        const float nLi = lse2_s[tok & 255], ndi = delta_s[tok & 255];
+        const uint64_t nLp = f2_pack(nLi, nLi), ndp = f2_pack(ndi, ndi);
         for (int c = 0; c < nch; ++c, ++st) {
           const uint32_t buf = st & 1;
           DBG(1, 12);
@@ -730,41 +1023,18 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
           tc_fence_after();
           DBG(1, 13);
 #pragma unroll 1
-          for (int par = 0; par < 2; ++par) {
-            const uint32_t S = t0 + buf * 128u + par * 32u, R = S + 64u;
-            const int col0 = 64 * c + 32 * par;                   // first column (key in pass A, query in pass B) of this piece
+          for (int u = 0; u < 2; ++u) {
+            const int col0 = 64 * c + 32 * hf + 16 * u;           // first column (key in pass A, query in pass B) of this piece
             if (col0 >= n_keys) break;
-            uint32_t sv[32], dv[32];
-            tmem_ld_32x32(S, sv);
-            tmem_ld_32x32(R, dv);
-            tmem_ld_wait();
+            const uint32_t S = t0 + buf * 128u + static_cast<uint32_t>(u * 16), R = S + 64u;
             const int nvalid = p.T - col0;
+            const uint32_t lse_sa = lse_s32 + static_cast<uint32_t>(col0) * 4u, delta_sa = delta_s32 + static_cast<uint32_t>(col0) * 4u;
             if (pass_a) {
-              uint32_t pk[32];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * j]), c2, -Li));
-                const float p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * j + 1]), c2, -Li));
-                const float z0 = (2 * j < nvalid) ? p0 * (__uint_as_float(dv[2 * j]) - di) : 0.f;
-                const float z1 = (2 * j + 1 < nvalid) ? p1 * (__uint_as_float(dv[2 * j + 1]) - di) : 0.f;
-                split_pack2(z0, z1, pk[j], pk[16 + j]);
-              }
-              tmem_st_32x32(R, pk);
+              if (nvalid >= 16) bw_chunk_piece<true, false>(S, R, c2p, nLp, ndp, lse_sa, delta_sa, nvalid);
+              else bw_chunk_piece<true, true>(S, R, c2p, nLp, ndp, lse_sa, delta_sa, nvalid);
             } else {
-              uint32_t pp[32], pz[32];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float2 L = *reinterpret_cast<const float2*>(lse2_s + col0 + 2 * j);      // broadcast reads
-                const float2 dl = *reinterpret_cast<const float2*>(delta_s + col0 + 2 * j);
-                const float p0 = (2 * j < nvalid) ? ex2_approx(fmaf(__uint_as_float(sv[2 * j]), c2, -L.x)) : 0.f;
-                const float p1 = (2 * j + 1 < nvalid) ? ex2_approx(fmaf(__uint_as_float(sv[2 * j + 1]), c2, -L.y)) : 0.f;
-                const float z0 = (2 * j < nvalid) ? p0 * (__uint_as_float(dv[2 * j]) - dl.x) : 0.f;
-                const float z1 = (2 * j + 1 < nvalid) ? p1 * (__uint_as_float(dv[2 * j + 1]) - dl.y) : 0.f;
-                split_pack2(p0, p1, pp[j], pp[16 + j]);
-                split_pack2(z0, z1, pz[j], pz[16 + j]);
-              }
-              tmem_st_32x32(S, pp);
-              tmem_st_32x32(R, pz);
+              if (nvalid >= 16) bw_chunk_piece<false, false>(S, R, c2p, nLp, ndp, lse_sa, delta_sa, nvalid);
+              else bw_chunk_piece<false, true>(S, R, c2p, nLp, ndp, lse_sa, delta_sa, nvalid);
             }
           }
           tmem_st_wait();
@@ -779,16 +1049,16 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
     // Drain accumulator set p of sub-pass n while the chunk warps and the tensor pipe are already in sub-pass n + 1.
     // Per warp: 32 rows x 64 columns of dQ (pass A) or dV and dK (pass B), as 32 x 32 tiles through four 4 KB staging buffers.
     const int q = warp & 3;
-    const int w4 = warp - 6;
-    const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const int wo = warp - 10;                    // 0..7
+    const int ch = wo >> 2;                      // which 32-column half of every 64-column accumulator this warp drains
+    const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(ch * 32);
     const float s = p.qscale ? __ldg(p.qscale) : 1.0f;
-    const float inv_s = 1.0f / s;
     const float gscale = p.scale * s * s;        // dQ, dK factor (see header comment)
     QvQParams yq;
     if constexpr (FUSED) yq = qv_load_qparams(p.y_scale, p.y_zp, p.qmin, p.qmax);
     const int D3 = 3 * D;
-    uint8_t* my_stage = stage_s + w4 * 16384;
-    uint64_t* my_ybar = y_bar + w4 * 4;
+    uint8_t* my_stage = stage_s + wo * 8192;
+    uint64_t* my_ybar = y_bar + wo * 2;
     uint32_t yph = 0;                            // bit k: phase of my_ybar[k]
     auto request_y = [&](int k, int b, int tok0, int col) {       // lane 0, after tma_store_wait_read<0>()
       mbar_expect_tx(&my_ybar[k], 4096);
@@ -869,38 +1139,23 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
     };
     uint32_t nsp = 0;
 #ifdef QV_ATTN_DEBUG
-    int dbg_n = (threadIdx.x == 192) ? 0 : 8192;
+    int dbg_n = (threadIdx.x == 320) ? 0 : 8192;
 #endif
     int local = 0;
-    // rows 128.. of delta are this group's job, done ONE ITEM AHEAD (before the last output of the previous item) so that the
-    // chunk warps never wait for it; buffer (local & 1) was last read two items ago
-    if (static_cast<int>(blockIdx.x) < num_items) {
-      delta_rows(delta_all, blockIdx.x / p.H, blockIdx.x % p.H, 128, w4, inv_s);
-      mbar_arrive(&delta_ready[0]);
-    }
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
       const int b = item / p.H, h = item % p.H;
       for (int sub = 0; sub < nsub; ++sub, ++nsp) {
         const bool pass_a = sub < mt;
         const int tile = pass_a ? sub : sub - mt;
         const int tok0 = tile * 128 + q * 32;                     // first token of this warp's 32-row slab
-        if (sub == nsub - 1 && item + static_cast<int>(gridDim.x) < num_items) {
-          const int nitem = item + gridDim.x;
-          delta_rows(delta_all + ((local + 1) & 1) * 256, nitem / p.H, nitem % p.H, 128, w4, inv_s);
-          mbar_arrive(&delta_ready[(local + 1) & 1]);
-        }
         const int slab = (b * mt + tile) * 4 + q;
-        const int col_h = h * HD;
+        const int col_h = h * HD + ch * 32;                       // this warp's 32 columns of the head
         const uint32_t aset = nsp & 1;
         if (lane == 0) {
           tma_store_wait_read<0>();                               // the previous sub-pass's tiles have left the staging buffers
           if constexpr (FUSED) {                                  // y tiles under this sub-pass's outputs
             request_y(0, b, tok0, (pass_a ? 0 : 2 * D) + col_h);
-            request_y(1, b, tok0, (pass_a ? 0 : 2 * D) + col_h + 32);
-            if (!pass_a) {
-              request_y(2, b, tok0, D + col_h);
-              request_y(3, b, tok0, D + col_h + 32);
-            }
+            if (!pass_a) request_y(1, b, tok0, D + col_h);
           }
         }
         __syncwarp();
@@ -911,23 +1166,17 @@ qv_attn_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         uint32_t o[32];
         tmem_ld_32x32(acc0, o);
         tmem_ld_wait();
-        emit(o, 0, pass_a ? gscale : 1.0f, b, tok0, (pass_a ? 0 : 2 * D) + col_h, slab);               // dQ | dV, columns 0..31
-        tmem_ld_32x32(acc0 + 32u, o);
-        tmem_ld_wait();
         if (pass_a) {
           tc_fence_before();
           mbar_arrive(&epi_done[aset]);
         }
-        emit(o, 1, pass_a ? gscale : 1.0f, b, tok0, (pass_a ? 0 : 2 * D) + col_h + 32, slab);          // columns 32..63
+        emit(o, 0, pass_a ? gscale : 1.0f, b, tok0, (pass_a ? 0 : 2 * D) + col_h, slab);               // dQ | dV
         if (!pass_a) {
           tmem_ld_32x32(acc0 + 64u, o);
           tmem_ld_wait();
-          emit(o, 2, gscale, b, tok0, D + col_h, slab);                                                 // dK, columns 0..31
-          tmem_ld_32x32(acc0 + 96u, o);
-          tmem_ld_wait();
           tc_fence_before();
           mbar_arrive(&epi_done[aset]);
-          emit(o, 3, gscale, b, tok0, D + col_h + 32, slab);                                            // dK, columns 32..63
+          emit(o, 1, gscale, b, tok0, D + col_h, slab);                                                 // dK
         }
         DBG(2, 16);
       }
@@ -953,6 +1202,7 @@ extern "C" int qv_attn_fwd(const uint16_t* qkv_planes, int32_t n_planes, int64_t
   QV_REQUIRE(out_fmt == 0 || (out_fmt == 1 && out_planes && out_ld % 64 == 0), QV_ERR_INVALID,
              "out_fmt must be 0 (bf16 hi/lo) or 1 (mixed fp16 + fp8 planes, row pitch a multiple of 64)");
   QV_REQUIRE(n_planes == 1 || n_planes == 2, QV_ERR_INVALID, "n_planes must be 1 (integer codes) or 2 (fp32 hi/lo)");
+  QV_REQUIRE(scale > 0.f, QV_ERR_INVALID, "the softmax scale must be positive (the row reference exponent is a maximum)");
   QV_REQUIRE(T <= 224, QV_ERR_UNSUPPORTED, "fused attention holds all keys in one tile: T <= 224 (got %d)", T);
   QV_REQUIRE(ld >= 3LL * H * HD, QV_ERR_INVALID, "qkv row pitch must cover Q | K | V (3 * H * 64 columns)");
   QV_REQUIRE(!out_planes || (out_ld >= static_cast<int64_t>(H) * HD && out_ld % 8 == 0 && out_plane_stride % 8 == 0 &&
@@ -1054,8 +1304,8 @@ int attn_bwd_impl(const uint16_t* qkv_codes, int64_t ld, const float* qscale, co
   const int items = B * H;
   const int sms = qv_num_sms();
   const int grid = items < sms ? items : sms;
-  if (fused) qv_attn_bwd_kernel<true><<<grid, AT_THREADS, BW_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(mq, md, my, mo, ap);
-  else qv_attn_bwd_kernel<false><<<grid, AT_THREADS, BW_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(mq, md, my, mo, ap);
+  if (fused) qv_attn_bwd_kernel<true><<<grid, BW_THREADS, BW_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(mq, md, my, mo, ap);
+  else qv_attn_bwd_kernel<false><<<grid, BW_THREADS, BW_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(mq, md, my, mo, ap);
   return qv_check_launch("qv_attn_bwd");
 }
 }  // namespace

@@ -82,6 +82,13 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* map, uin
       : "memory");
 }
 
+// Tile prefetch into L2 (no smem destination, no barrier): the tile's lines are pulled from HBM ahead of the real load
+__device__ __forceinline__ void tma_prefetch_l2_4d(const void* map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
 // TMA store smem -> global (bulk async group), 3-D coordinates (col, row, batch); clips out-of-range rows/cols
 __device__ __forceinline__ void tma_store_3d(const void* map, const void* smem_src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
