@@ -11,6 +11,14 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _free_port() -> int:
+    """A TCP port nobody listens on right now (a pid-derived guess collided with other listeners on busy hosts)."""
+    import socket
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
 def _worker(rank, world, port, async_op, q, rehome=False):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -43,7 +51,7 @@ def _worker(rank, world, port, async_op, q, rehome=False):
 
 @pytest.mark.parametrize("async_op", [False, True, "overlapped"])
 def test_gradient_sum_and_rank0_observer_state(async_op):
-    world, port = 2, 29000 + os.getpid() % 2000 + [False, True, "overlapped"].index(async_op)
+    world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, world, port, async_op, q)) for r in range(world)]
@@ -62,7 +70,7 @@ def test_gradient_sum_and_rank0_observer_state(async_op):
 def test_rehomed_observers_need_no_pack_or_unpack():
     """bind_observers(rehome=True): the running min / max buffers ARE the tail of the exchange buffer -- rank != 0 clears them
     before the exchange, nothing is copied afterwards, and every rank still ends with rank 0's state."""
-    world, port = 2, 31500 + os.getpid() % 2000
+    world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, world, port, "overlapped", q, True)) for r in range(world)]
