@@ -462,8 +462,10 @@ def run_ours(args):
 
     student, teacher = build_models(batch, dev, ln_variant=args.ln_variant, prepare=not args.pre_qat)
     if args.pre_qat:
+        import functools
         from qatvit_b200.plain import PlainDistillStep
-        QATDistillStep = PlainDistillStep          # noqa: N806 -- same call surface; no observers to synchronise
+        # same call surface; no observers to synchronise.  --amp: one bf16 pass per product (the reference's optional --amp epochs)
+        QATDistillStep = functools.partial(PlainDistillStep, amp=True) if args.amp else PlainDistillStep          # noqa: N806
     sync = None
     if world > 1:
         from qatvit_b200.ddp import GradSync
@@ -681,10 +683,13 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": n, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32 (tcgen05: bf16 hi/lo planes, teacher Linears fp16 + fp8 cross terms; fp32 accumulate; integer fake-quant codes exact)",
+        "dtype": ("bf16 student operands, one tcgen05 pass per product, fp32 accumulate (pre-QAT --amp variant); teacher f32-grade"
+                  if (args.pre_qat and args.amp) else
+                  "f32 (tcgen05: bf16 hi/lo planes, teacher Linears fp16 + fp8 cross terms; fp32 accumulate; integer fake-quant codes exact)"),
         "data": "synthetic",
         "config": {"workload": ("PRE-QAT epoch variant (student not yet prepared, no fake-quant; ref qat_trainer.py:333-361 before "
-                                "qat_start_epoch): ViT-B/16 teacher -> ViT-S/16 student distillation step, batch 256, 1x B200")
+                                "qat_start_epoch" + (", --amp: one bf16 tensor-core pass per student product" if args.amp else "") +
+                                "): ViT-B/16 teacher -> ViT-S/16 student distillation step, batch 256, 1x B200")
                    if (n == 1 and args.pre_qat) else
                    "ViT-B/16 teacher -> ViT-S/16 QAT student distillation step (KL+CE), batch 256, 1x B200"
                    if n == 1 else f"same distillation step data-parallel, global batch 1024 at {n} B200 with NCCL gradient allreduce",
@@ -748,6 +753,7 @@ def main():
     ap.add_argument("--pre-qat", action="store_true",
                     help="time the pre-QAT epoch step instead (unprepared student, qatvit_b200.plain.PlainDistillStep) -- not the "
                          "BASELINE metric, a side measurement of SURVEY.md section 8f item 3")
+    ap.add_argument("--amp", action="store_true", help="with --pre-qat: the half-precision variant (PlainDistillStep(amp=True))")
     ap.add_argument("--torch-optimizer", action="store_true", help="torch AdamW + clip on the arena instead of qv_clip_adamw")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: libraries that write to fd 1 from C (NCCL prints "NCCL version ..." there on some

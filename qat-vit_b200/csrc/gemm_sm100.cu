@@ -911,8 +911,8 @@ extern "C" int qv_gemm_bf16(const qv_gemm_args* a, void* stream) {
     if (a->tile_n <= 0 && BN < 128) BN = 128;
     QV_REQUIRE(BN >= 128, QV_ERR_UNSUPPORTED, "gradient-planes epilogue needs tile_n 128 / 192");
   } else if (planes_out) {
-    QV_REQUIRE(splits == 1 && a->a_planes == 2 && !a->a.mn_major && !a->b.mn_major && BN >= 128, QV_ERR_UNSUPPORTED,
-               "plane output is instantiated for unsplit K-major (2,1)- and (2,2)-plane GEMMs with tile_n 128/192");
+    QV_REQUIRE(splits == 1 && (a->a_planes == 2 || a->b_planes == 1) && !a->a.mn_major && !a->b.mn_major && BN >= 128, QV_ERR_UNSUPPORTED,
+               "plane output is instantiated for unsplit K-major (2,1)-, (2,2)- and (1,1)-plane GEMMs with tile_n 128/192");
     QV_REQUIRE(a->N % 64 == 0, QV_ERR_UNSUPPORTED, "plane output needs N to be a multiple of 64");
     QV_REQUIRE(!a->col_scale && !a->col_rscale && !a->alpha && !a->minmax, QV_ERR_UNSUPPORTED,
                "plane output takes a bias term only (no scale / alpha / observer)");
@@ -1021,6 +1021,10 @@ extern "C" int qv_gemm_bf16(const qv_gemm_args* a, void* stream) {
     return launch<192, 2, 2, false, false, 0, 1>(ma, mb, mo, kp, grid, st);
   }
   if (planes_out) {
+    if (a->a_planes == 1) {      // single-pass (half-precision, pre-QAT --amp variant) GEMM whose output is the next operand
+      if (BN == 128) return launch<128, 1, 1, false, false, 1>(ma, mb, mo, kp, grid, st);
+      return launch<192, 1, 1, false, false, 1>(ma, mb, mo, kp, grid, st);
+    }
     if (a->b_planes == 1) {
       if (pair) return launch<192, 2, 1, false, false, 1, 0, 2>(ma, mb, mo, kp, grid, st);
       if (BN == 128) return launch<128, 2, 1, false, false, 1>(ma, mb, mo, kp, grid, st);

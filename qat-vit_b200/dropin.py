@@ -4,7 +4,8 @@ attributes, buffers, hooks or state_dict keys -- so ``QATWrapper``, the qconfig 
 ``convert()`` flow are untouched.  It replaces
 
 * ``FusedMovingAvgObsFakeQuantize.forward``      (torch/ao/quantization/fake_quantize.py:423-438)
-* ``torch.ao.nn.qat.Linear.forward``             (torch/ao/nn/qat/modules/linear.py:50-51)
+* ``torch.ao.nn.qat.Linear.forward``             (torch/ao/nn/qat/modules/linear.py:50-51; the 10-class head included)
+* ``torch.ao.nn.qat.Conv2d.forward``             (torch/ao/nn/qat/modules/conv.py:55-56; the patch embedding, as im2col + GEMM)
 * the inline loss of the hot loop -> ``distill_loss`` (ref qat_trainer.py:343-349)
 
 with ``torch.autograd.Function``s whose forward/backward are C-ABI calls (observer state is mutated in the modules' own
@@ -23,6 +24,9 @@ from .ops import Op, PAIRS_EXACT_B, PAIRS_FP32
 
 _ORIG = {}
 _INF = float("inf")
+# which route each patched module call took since install() (tests assert that the reference's prepared student leaves nothing
+# on the stock F.linear / cuDNN route)
+stats = {"linear_gemm": 0, "linear_small": 0, "linear_stock": 0, "conv_gemm": 0, "conv_stock": 0}
 
 
 def _ensure_per_channel_state(mod, channels: int) -> None:
@@ -34,36 +38,57 @@ def _ensure_per_channel_state(mod, channels: int) -> None:
         mod.zero_point.resize_(channels).fill_(0)
 
 
+def _dense_view(x: torch.Tensor):
+    """(contiguous tensor holding x's elements, restore) -- per-tensor fake-quant is elementwise, so a channels_last 4-D tensor
+    (what the patch-embedding drop-in returns) is processed in its own memory order instead of being copied to NCHW."""
+    if x.is_contiguous():
+        return x, None
+    if x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last):
+        return x.permute(0, 2, 3, 1), (0, 3, 1, 2)
+    return x.contiguous(), None
+
+
 class _FakeQuantFn(torch.autograd.Function):
     """y = fused observer + fake-quant of x; backward = STE mask."""
 
     @staticmethod
     def forward(ctx, x, mod):
         obs = mod.activation_post_process
-        xc = x.contiguous()
-        y = torch.empty_like(xc)
-        mask = torch.empty(xc.shape, dtype=torch.uint8, device=xc.device)
         if mod.is_per_channel:
             if mod.ch_axis != 0:
                 raise NotImplementedError("qatvit_b200: per-channel fake-quant is implemented for ch_axis 0 (weights)")
+            xc, perm = x.contiguous(), None
+            y = torch.empty_like(xc)
+            mask = torch.empty(xc.shape, dtype=torch.uint8, device=xc.device)
             C = xc.shape[0]
             _ensure_per_channel_state(mod, C)
             ops.fq_weight(xc, True, mod.observer_enabled, mod.fake_quant_enabled, obs.min_val, obs.max_val, mod.scale,
                           mod.zero_point, obs.averaging_constant, obs.quant_min, obs.quant_max, mod.is_symmetric_quant,
                           y=y, mask=mask)
         else:
-            acc = ops.new_minmax(xc.device)
+            xc, perm = _dense_view(x)
+            y = torch.empty_like(xc)
+            mask = torch.empty(xc.shape, dtype=torch.uint8, device=xc.device)
+            acc = mod.__dict__.get("_qv_acc")
+            if acc is None or acc.device != xc.device:
+                acc = mod.__dict__["_qv_acc"] = ops.new_minmax(xc.device)
+            else:
+                ops.minmax_reset(acc)
             ops.minmax_accumulate(xc, acc)
             ops.obs_update(acc, mod.observer_enabled, mod.fake_quant_enabled, obs.min_val, obs.max_val, mod.scale,
                            mod.zero_point, obs.averaging_constant, obs.quant_min, obs.quant_max, mod.is_symmetric_quant)
             ops.fq_apply(xc, mod.scale, mod.zero_point, mod.fake_quant_enabled, obs.quant_min, obs.quant_max, y=y, mask=mask)
         ctx.save_for_backward(mask)
-        return y
+        ctx.perm = perm
+        return y if perm is None else y.permute(*perm)
 
     @staticmethod
     def backward(ctx, gy):
         (mask,) = ctx.saved_tensors
-        return ops.fq_bwd(gy.contiguous(), mask), None
+        if ctx.perm is None:
+            return ops.fq_bwd(gy.contiguous(), mask), None
+        g = ops.fq_bwd(gy.permute(0, 2, 3, 1).contiguous(), mask)       # mask is in channels_last order
+        return g.permute(*ctx.perm), None
 
 
 def _fq_forward(self, X):
@@ -109,75 +134,247 @@ def _gemm_friendly(M: int, N: int, K: int) -> bool:
     return K % 8 == 0 and N % 32 == 0 and M > 0
 
 
+def _flag(t: torch.Tensor, owner) -> int:
+    """int(t[0]) of an enable flag that lives on the device, WITHOUT a sync per call: the value is cached on the owning module
+    and re-read only when the buffer was modified in place (``_version`` moves on ``t[0] = 0``, ``copy_``, load_state_dict) or
+    replaced (``.to()``)."""
+    key = (t.data_ptr(), t._version)
+    c = owner.__dict__.get("_qv_flag")
+    if c is None or c[0] != key:
+        c = (key, int(t.reshape(-1)[0].item()))
+        owner.__dict__["_qv_flag"] = c
+    return c[1]
+
+
+class _WeightCache:
+    """Per-module scratch for everything that is a function of the WEIGHT only (codes, transposed codes, STE mask, the
+    fake-quantised fp32 copy of a small weight, split-K workspace): allocated once, overwritten by every forward -- the stock
+    module re-runs weight_fake_quant per call too, and so do we (the observer's EMA needs it), but without a cudaMalloc-class
+    call or a memset launch per step.  Buffers a pending backward still needs are never overwritten: a second forward before
+    the first one's backward (weight sharing, two passes per step) gets fresh tensors instead (``pending``)."""
+
+    def __init__(self):
+        self.key, self.bufs, self.pending, self.ws = None, None, 0, None
+
+    def __deepcopy__(self, memo):
+        return _WeightCache()
+
+    def get(self, N: int, K: int, dev, small: bool, fresh: bool):
+        key = (N, K, dev, small)
+        if fresh or self.key != key or self.bufs is None:
+            b = dict(wmask=torch.empty(N, K, dtype=torch.uint8, device=dev), scratch=torch.zeros(2, dtype=torch.int32, device=dev),
+                     scale_vec=torch.empty(N, dtype=torch.float32, device=dev))
+            if small:
+                b["wq"] = torch.empty(N, K, dtype=torch.float32, device=dev)
+            else:
+                b["codes"] = torch.empty(1, N, K, dtype=torch.bfloat16, device=dev)
+                b["codes_t"] = torch.empty(1, K, N, dtype=torch.bfloat16, device=dev)
+            if fresh:
+                return b
+            self.key, self.bufs = key, b
+        return self.bufs
+
+    def workspace(self, n: int, dev) -> torch.Tensor:
+        if self.ws is None or self.ws.numel() < n or self.ws.device != dev:
+            self.ws = torch.empty(n, dtype=torch.float32, device=dev)
+        return self.ws
+
+
+def _cache(mod) -> _WeightCache:
+    c = mod.__dict__.get("_qv_cache")
+    if c is None:
+        c = mod.__dict__["_qv_cache"] = _WeightCache()
+    return c
+
+
+def _quantize_weight(mod, w2: torch.Tensor, small: bool, track: bool):
+    """weight_fake_quant(weight) on our kernel: observer EMA + qparams in the module's own buffers, STE mask, and either the
+    integer codes (both orientations, the tensor-core operands) or the fake-quantised fp32 weight (small Linears)."""
+    wfq = mod.weight_fake_quant
+    obs = wfq.activation_post_process
+    N, K = w2.shape
+    per_channel = bool(wfq.is_per_channel)
+    if per_channel:
+        _ensure_per_channel_state(wfq, N)
+    cache = _cache(mod)
+    b = cache.get(N, K, w2.device, small, fresh=track and cache.pending > 0)
+    if small:
+        ops.fq_weight(w2, per_channel, wfq.observer_enabled, wfq.fake_quant_enabled, obs.min_val, obs.max_val, wfq.scale,
+                      wfq.zero_point, obs.averaging_constant, obs.quant_min, obs.quant_max, wfq.is_symmetric_quant,
+                      y=b["wq"], mask=b["wmask"], scratch=b["scratch"])
+    else:
+        ops.fq_weight(w2, per_channel, wfq.observer_enabled, wfq.fake_quant_enabled, obs.min_val, obs.max_val, wfq.scale,
+                      wfq.zero_point, obs.averaging_constant, obs.quant_min, obs.quant_max, wfq.is_symmetric_quant,
+                      mask=b["wmask"], codes=b["codes"][0], codes_t=b["codes_t"][0], scratch=b["scratch"], scale_vec=b["scale_vec"])
+    if track:
+        cache.pending += 1
+    return b, cache
+
+
+def _codes_linear_fwd(xp: torch.Tensor, M: int, N: int, K: int, b: dict, bias) -> torch.Tensor:
+    out = torch.empty(M, N, dtype=torch.float32, device=xp.device)
+    ops.gemm(Op.full(xp), Op.full(b["codes"]), M, N, K, PAIRS_EXACT_B, out=out, col_scale=b["scale_vec"],
+             bias=None if bias is None else bias.detach())
+    return out
+
+
+def _codes_linear_bwd(g2: torch.Tensor, xp: torch.Tensor, b: dict, cache: _WeightCache, M: int, N: int, K: int, has_bias: bool,
+                      need_gx: bool):
+    """dgrad / split-K wgrad of y = x (codes * scale)^T + bias; the weight STE mask and 1/scale are applied in the reduce."""
+    dev = g2.device
+    rpb = 64
+    nblk = -(-M // rpb)
+    gp = torch.empty(2, M, N, dtype=torch.bfloat16, device=dev)
+    part = torch.empty(nblk, N, dtype=torch.float32, device=dev)
+    ops.gp_planes(g2, None, None, b["scale_vec"], True, False, M, N, gp, part, rpb)
+    gb = None
+    if has_bias:
+        gb = torch.empty(N, dtype=torch.float32, device=dev)
+        ops.colsum_reduce(part, nblk, N, gb)
+    gx = None
+    if need_gx:
+        gx = torch.empty(M, K, dtype=torch.float32, device=dev)
+        ops.gemm(Op.full(gp), Op.full(b["codes_t"]), M, K, N, PAIRS_EXACT_B, out=gx)
+    from .engine import wgrad_splits
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    s = wgrad_splits(N, K, M, sms)
+    ws = cache.workspace(s * N * K, dev)
+    gw = torch.empty(N, K, dtype=torch.float32, device=dev)
+    if s > 1:
+        ops.gemm(Op.full(gp, mn_major=True), Op.full(xp, mn_major=True), N, K, M, PAIRS_FP32, splits=s, workspace=ws)
+    else:
+        ops.gemm(Op.full(gp, mn_major=True), Op.full(xp, mn_major=True), N, K, M, PAIRS_FP32, out=ws[:N * K].view(N, K))
+    ops.splitk_reduce(ws, s, N, K, gw, row_rscale=b["scale_vec"], mask=b["wmask"])
+    cache.pending = max(0, cache.pending - 1)
+    return gx, gw, gb
+
+
 class _QATLinearFn(torch.autograd.Function):
     """F.linear(x, fake_quant(W), b): weight observer + codes, tcgen05 GEMM with the scale in the epilogue; backward =
     dgrad / split-K wgrad on the same tensor-core kernel, weight STE mask applied in the reduce."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, mod):
-        wfq = mod.weight_fake_quant
-        obs = wfq.activation_post_process
         N, K = weight.shape
         x2 = x.reshape(-1, K).contiguous()
         M = x2.shape[0]
-        dev = x.device
-        per_channel = bool(wfq.is_per_channel)
-        if per_channel:
-            _ensure_per_channel_state(wfq, N)
-        codes = torch.empty(1, N, K, dtype=torch.bfloat16, device=dev)
-        codes_t = torch.empty(1, K, N, dtype=torch.bfloat16, device=dev)
-        wmask = torch.empty(N, K, dtype=torch.uint8, device=dev)
-        scratch = torch.zeros(2, dtype=torch.int32, device=dev)
-        ops.fq_weight(weight.detach().contiguous(), per_channel, wfq.observer_enabled, wfq.fake_quant_enabled, obs.min_val,
-                      obs.max_val, wfq.scale, wfq.zero_point, obs.averaging_constant, obs.quant_min, obs.quant_max,
-                      wfq.is_symmetric_quant, mask=wmask, codes=codes[0], codes_t=codes_t[0], scratch=scratch)
-        scale_vec = wfq.scale if per_channel else wfq.scale.expand(N).contiguous()
+        track = torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad)
+        b, cache = _quantize_weight(mod, weight.detach().contiguous(), small=False, track=track)
         xp = ops.split_planes(x2)
-        out = torch.empty(M, N, dtype=torch.float32, device=dev)
-        ops.gemm(Op.full(xp), Op.full(codes), M, N, K, PAIRS_EXACT_B, out=out, col_scale=scale_vec,
-                 bias=None if bias is None else bias.detach())
-        ctx.save_for_backward(xp, codes_t, wmask, scale_vec.clone())
+        out = _codes_linear_fwd(xp, M, N, K, b, bias)
+        ctx.saved = (xp, b, cache)
         ctx.shape = (x.shape, M, N, K, bias is not None)
         return out.reshape(*x.shape[:-1], N)
 
     @staticmethod
     def backward(ctx, gy):
-        xp, codes_t, wmask, scale_vec = ctx.saved_tensors
+        xp, b, cache = ctx.saved
+        xshape, M, N, K, has_bias = ctx.shape
+        gx, gw, gb = _codes_linear_bwd(gy.reshape(M, N).contiguous(), xp, b, cache, M, N, K, has_bias, ctx.needs_input_grad[0])
+        return (None if gx is None else gx.reshape(xshape)), gw, gb, None
+
+
+class _SmallLinearFn(torch.autograd.Function):
+    """Linears the tensor-core kernel does not take (the 10-class head: N = 10): one warp per output in fp32 FMA order, on the
+    fake-quantised fp32 weight; backward = the same small kernel the fused engine uses (qv_head_fwd / qv_head_bwd)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, mod):
+        N, K = weight.shape
+        x2 = x.reshape(-1, K).contiguous()
+        M = x2.shape[0]
+        track = torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad)
+        b, cache = _quantize_weight(mod, weight.detach().contiguous(), small=True, track=track)
+        out = torch.empty(M, N, dtype=torch.float32, device=x.device)
+        ops.head_fwd(x2, b["wq"], None if bias is None else bias.detach(), M, K, N, out)
+        ctx.saved = (x2, b, cache)
+        ctx.shape = (x.shape, M, N, K, bias is not None)
+        return out.reshape(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, b, cache = ctx.saved
         xshape, M, N, K, has_bias = ctx.shape
         dev = gy.device
-        g2 = gy.reshape(M, N).contiguous()
-        rpb = 64
-        nblk = -(-M // rpb)
-        gp = torch.empty(2, M, N, dtype=torch.bfloat16, device=dev)
-        part = torch.empty(nblk, N, dtype=torch.float32, device=dev)
-        ops.gp_planes(g2, None, None, scale_vec, True, False, M, N, gp, part, rpb)
-        gb = None
-        if has_bias:
-            gb = torch.empty(N, dtype=torch.float32, device=dev)
-            ops.colsum_reduce(part, nblk, N, gb)
         gx = torch.empty(M, K, dtype=torch.float32, device=dev)
-        ops.gemm(Op.full(gp), Op.full(codes_t), M, K, N, PAIRS_EXACT_B, out=gx)
-        from .engine import wgrad_splits
-        sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        s = wgrad_splits(N, K, M, sms)
         gw = torch.empty(N, K, dtype=torch.float32, device=dev)
-        if s > 1:
-            ws = ops.gemm(Op.full(gp, mn_major=True), Op.full(xp, mn_major=True), N, K, M, PAIRS_FP32, splits=s)
-        else:
-            ws = ops.gemm(Op.full(gp, mn_major=True), Op.full(xp, mn_major=True), N, K, M, PAIRS_FP32)
-        ops.splitk_reduce(ws, s, N, K, gw, row_rscale=scale_vec, mask=wmask)
-        return gx.reshape(xshape), gw, gb, None
+        gb = torch.empty(N, dtype=torch.float32, device=dev)
+        ops.head_bwd(gy.reshape(M, N).contiguous(), x2, b["wq"], b["wmask"], M, K, N, gx, gw, gb)
+        cache.pending = max(0, cache.pending - 1)
+        return gx.reshape(xshape), gw, (gb if has_bias else None), None
+
+
+_SMALL_MAX_ROWS = 4096       # qv_head_bwd walks the batch serially per weight element: keep it to head-sized problems
+
+
+def _is_fused_fq(m) -> bool:
+    return type(m).__name__ == "FusedMovingAvgObsFakeQuantize"
 
 
 def _qat_linear_forward(self, input):
-    if input.is_cuda and input.dtype == torch.float32 and self.weight.dtype == torch.float32:
+    if input.is_cuda and input.dtype == torch.float32 and self.weight.dtype == torch.float32 and _is_fused_fq(self.weight_fake_quant) \
+            and input.numel() > 0 and _flag(self.weight_fake_quant.fake_quant_enabled, self.weight_fake_quant) == 1:
         N, K = self.weight.shape
         M = input.numel() // max(K, 1)
-        if _gemm_friendly(M, N, K) and type(self.weight_fake_quant).__name__ == "FusedMovingAvgObsFakeQuantize":
+        if _gemm_friendly(M, N, K):
+            stats["linear_gemm"] += 1
             return _QATLinearFn.apply(input, self.weight, self.bias, self)
-    # shapes the tensor-core kernel does not take (e.g. the 10-class head): fake-quant still runs on our kernels through
-    # the patched FusedMovingAvgObsFakeQuantize.forward; the tiny matmul stays in ATen
+        if M <= _SMALL_MAX_ROWS and N <= 1024:
+            stats["linear_small"] += 1
+            return _SmallLinearFn.apply(input, self.weight, self.bias, self)
+    stats["linear_stock"] += int(input.is_cuda)      # CPU tensors are the oracle path, not a missed route
+    # fake-quant switched off (weights are then not integer codes), exotic fake-quant classes, huge odd shapes: the stock
+    # composition -- the fake-quant itself still runs on our kernels through the patched FusedMovingAvgObsFakeQuantize.forward
     return F.linear(input, self.weight_fake_quant(self.weight), self.bias)
+
+
+class _QATConv2dFn(torch.autograd.Function):
+    """Patch-embedding convolution (kernel == stride, no padding / dilation / groups: timm PatchEmbed.proj, the only conv of the
+    reference path) as im2col + the fake-quant Linear GEMM above.  Output is the NCHW view of the [B * patches, N] GEMM result
+    (channels_last memory), so timm's flatten(2).transpose(1, 2) that follows is a view again."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, mod):
+        B, C, H, W = x.shape
+        N = weight.shape[0]
+        ps = weight.shape[2]
+        K = C * ps * ps
+        P = (H // ps) * (W // ps)
+        M = B * P
+        track = torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad)
+        b, cache = _quantize_weight(mod, weight.detach().reshape(N, K).contiguous(), small=False, track=track)
+        xp = torch.empty(2, M, K, dtype=torch.bfloat16, device=x.device)
+        ops.im2col_fq(x.contiguous(), None, B, C, H, ps, xp)
+        out = _codes_linear_fwd(xp, M, N, K, b, bias)
+        ctx.saved = (xp, b, cache)
+        ctx.shape = (x.shape, weight.shape, M, N, K, ps, bias is not None)
+        return out.view(B, H // ps, W // ps, N).permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, gy):
+        xp, b, cache = ctx.saved
+        xshape, wshape, M, N, K, ps, has_bias = ctx.shape
+        B, C, H, W = xshape
+        g2 = gy.permute(0, 2, 3, 1).reshape(M, N).contiguous()       # a view when gy arrives in the layout we produced
+        gx, gw, gb = _codes_linear_bwd(g2, xp, b, cache, M, N, K, has_bias, ctx.needs_input_grad[0])
+        if gx is not None:   # col2im of non-overlapping patches is a permutation (the input of the reference's patch embedding
+            # is the fake-quantised image and needs no gradient: this branch only serves other callers)
+            gx = gx.view(B, H // ps, W // ps, C, ps, ps).permute(0, 3, 1, 4, 2, 5).reshape(B, C, H, W)
+        return gx, gw.view(wshape), gb, None
+
+
+def _qat_conv2d_forward(self, input):
+    w = self.weight
+    if (input.is_cuda and input.dtype == torch.float32 and w.dtype == torch.float32 and input.dim() == 4 and input.numel() > 0
+            and _is_fused_fq(self.weight_fake_quant) and self.groups == 1 and tuple(self.dilation) == (1, 1)
+            and tuple(self.padding) == (0, 0) and self.padding_mode == "zeros" and w.shape[2] == w.shape[3]
+            and tuple(self.stride) == (w.shape[2], w.shape[3]) and input.shape[2] == input.shape[3]
+            and input.shape[2] % w.shape[2] == 0 and _gemm_friendly(1, w.shape[0], w.shape[1] * w.shape[2] * w.shape[3])
+            and _flag(self.weight_fake_quant.fake_quant_enabled, self.weight_fake_quant) == 1):
+        stats["conv_gemm"] += 1
+        return _QATConv2dFn.apply(input, w, self.bias, self)
+    stats["conv_stock"] += int(input.is_cuda)
+    return _ORIG["conv2d"](self, input)          # any other convolution: stock (cuDNN) path, fake-quant on our kernels
 
 
 class _DistillLossFn(torch.autograd.Function):
@@ -216,8 +413,10 @@ def install(learnable: bool = False) -> None:
         return
     _ORIG["fq"] = FusedMovingAvgObsFakeQuantize.forward
     _ORIG["linear"] = nnqat.Linear.forward
+    _ORIG["conv2d"] = nnqat.Conv2d.forward
     FusedMovingAvgObsFakeQuantize.forward = _fq_forward
     nnqat.Linear.forward = _qat_linear_forward
+    nnqat.Conv2d.forward = _qat_conv2d_forward
 
 
 def uninstall() -> None:
@@ -230,3 +429,4 @@ def uninstall() -> None:
         return
     FusedMovingAvgObsFakeQuantize.forward = _ORIG.pop("fq")
     nnqat.Linear.forward = _ORIG.pop("linear")
+    nnqat.Conv2d.forward = _ORIG.pop("conv2d")

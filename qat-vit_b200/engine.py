@@ -278,18 +278,18 @@ class _BatchBuffers:
         return b
 
 
-def _attention_forward(d: _ViTDims, qkvp: torch.Tensor, S: torch.Tensor, Pp: torch.Tensor, o: torch.Tensor) -> None:
+def _attention_forward(d: _ViTDims, qkvp: torch.Tensor, S: torch.Tensor, Pp: torch.Tensor, o: torch.Tensor, pairs=PAIRS_FP32) -> None:
     """softmax(Q K^T / 8) V per (image, head) as two batched tcgen05 GEMMs + one row-softmax kernel
     (replaces F.scaled_dot_product_attention in timm Attention.forward)."""
     B, H, T, D = d.B, d.H, d.T, d.D
     BH = B * H
     q_op = Op.tokens(qkvp, B, T, 0, 64)
     k_op = Op.tokens(qkvp, B, T, D, 64)
-    ops.gemm(q_op, k_op, T, T, 64, PAIRS_FP32, out=Out.per_head(S, BH, H, T, T), nbatch=BH, batch_inner=H)
+    ops.gemm(q_op, k_op, T, T, 64, pairs, out=Out.per_head(S, BH, H, T, T), nbatch=BH, batch_inner=H)
     ops.softmax_planes(S, d.ldS, BH * T, T, d.attn_scale, Pp)
     p_op = Op.per_head(Pp, BH, H, T, T)
     v_op = Op.tokens(qkvp, B, T, 2 * D, 64, mn_major=True)
-    ops.gemm(p_op, v_op, T, 64, T, PAIRS_FP32, out=Out.tokens(o, B, T, 0, 64), nbatch=BH, batch_inner=H)
+    ops.gemm(p_op, v_op, T, 64, T, pairs, out=Out.tokens(o, B, T, 0, 64), nbatch=BH, batch_inner=H)
 
 
 class TeacherEngine(_BatchBuffers):

@@ -3,8 +3,10 @@
 Quant/DeQuant stubs, plain nn.Linear / nn.Conv2d, no fake-quant) against the same frozen teacher with the same KL + CE loss.
 
 ``PlainDistillStep`` is that step on the tcgen05 GEMM family: every fp32 tensor that feeds a GEMM travels as bf16 hi/lo planes,
-three MMAs per product, fp32 accumulation (fp32-grade results, ~2^-16 relative) -- the reference's non-AMP arithmetic; its
-``--amp`` variant (fp16 autocast + GradScaler) is reproduced to fp16 accuracy, not bit for bit.  Weights are re-split into planes
+three MMAs per product, fp32 accumulation (fp32-grade results, ~2^-16 relative) -- the reference's non-AMP arithmetic.  Its
+optional ``--amp`` variant (fp16 autocast + GradScaler around the student, ref :286,340,353-357) has a half-precision counterpart
+here: ``PlainDistillStep(..., amp=True)`` runs ONE bf16 pass per product (a third of the tensor work; the teacher stays fp32-grade
+as in the reference, where it runs outside the autocast region).  Weights are re-split into planes
 every step (they change every step); dgrad reads the same [N, K] planes as an MN-major operand, so no transposed copy exists.
 Attention uses the unfused kernels (scores / probabilities as planes in HBM, saved for backward): the fused integer-code
 kernels need fake-quantised q, k, v.  Gradients land in one flat arena exactly like the QAT engine's, so the optimizer and the
@@ -19,7 +21,7 @@ import torch.nn as nn
 
 from . import ops
 from .engine import TeacherEngine, _BatchBuffers, _ViTDims, _attention_forward, wgrad_splits
-from .ops import Op, Out, PAIRS_FP32
+from .ops import Op, Out, PAIRS_FP32, PAIRS_SINGLE
 
 
 class _Lin:
@@ -39,7 +41,15 @@ class _Lin:
 class PlainStudentEngine(_BatchBuffers):
     """Forward + hand-written backward of the unprepared ``QATWrapper`` student (no fake-quant anywhere)."""
 
-    def __init__(self, student: nn.Module, batch: int, hparams: Dict, grad_buffer: Optional[torch.Tensor] = None):
+    def __init__(self, student: nn.Module, batch: int, hparams: Dict, grad_buffer: Optional[torch.Tensor] = None,
+                 amp: bool = False):
+        # amp: the half-precision variant of the pre-QAT step (the reference's optional --amp: fp16 autocast + GradScaler around
+        # the student forward / loss, ref qat_trainer.py:286,340,353-357).  Here: ONE tensor-core pass per product on the bf16
+        # hi planes of both operands (the lo planes are simply not read), fp32 accumulation and fp32 outputs, LayerNorm /
+        # softmax / loss in fp32 as under autocast.  bf16 keeps the fp32 exponent range, so no loss scaling is needed; operand
+        # rounding is 2^-9 (fp16 autocast: 2^-11) -- reduced-precision by design, checked against the fp32 reference to 3e-2.
+        self.amp = bool(amp)
+        self.pairs = PAIRS_SINGLE if self.amp else PAIRS_FP32
         for m in student.modules():
             if type(m).__name__ == "FusedMovingAvgObsFakeQuantize":
                 raise RuntimeError("qatvit_b200: PlainStudentEngine takes the student BEFORE prepare_qat (use QATDistillStep after)")
@@ -157,7 +167,7 @@ class PlainStudentEngine(_BatchBuffers):
         self._grad(norm.bias).copy_(tmp[D:])
 
     def _fwd(self, ql: _Lin, a_planes, M, out=None, out_planes=None) -> None:
-        ops.gemm(Op.full(a_planes), Op.full(ql.planes), M, ql.N, ql.K, PAIRS_FP32, out=out, out_planes=out_planes,
+        ops.gemm(Op.full(a_planes), Op.full(ql.planes), M, ql.N, ql.K, self.pairs, out=out, out_planes=out_planes,
                  bias=ql.bias.detach())
 
     def forward(self, images: torch.Tensor, labels: Optional[torch.Tensor], teacher_logits: Optional[torch.Tensor],
@@ -176,7 +186,7 @@ class PlainStudentEngine(_BatchBuffers):
                 ops.resid_ln_fwd(self.x_in[0], None, None, blk.norm1.weight.detach(), blk.norm1.bias.detach(), d.eps, M, D,
                                  h_planes=self.h1p[0], mean=self.stats1[0][0], rstd=self.stats1[0][1])
             self._fwd(ql["qkv"], self.h1p[l], M, out_planes=self.qkvp[l])
-            _attention_forward(d, self.qkvp[l], self.S, self.Pp[l], self.o)
+            _attention_forward(d, self.qkvp[l], self.S, self.Pp[l], self.o, pairs=self.pairs)
             ops.split_planes(self.o, self.op[l])
             self._fwd(ql["proj"], self.op[l], M, out=self.a_raw)
             ops.resid_ln_fwd(self.x_in[l], self.a_raw, None, blk.norm2.weight.detach(), blk.norm2.bias.detach(), d.eps, M, D,
@@ -216,15 +226,15 @@ class PlainStudentEngine(_BatchBuffers):
 
     def _dgrad(self, ql: _Lin, gp, M: int, out) -> None:
         # g[M, N] @ W[N, K]: the weight planes as they lie ([contraction N][K]) are the MN-major B operand
-        ops.gemm(Op.full(gp), Op.full(ql.planes, mn_major=True), M, ql.K, ql.N, PAIRS_FP32, out=out)
+        ops.gemm(Op.full(gp), Op.full(ql.planes, mn_major=True), M, ql.K, ql.N, self.pairs, out=out)
 
     def _wgrad(self, ql: _Lin, gp, x_planes, kdim: int) -> None:
         s = self._splits[(ql.N, ql.K)]
         if s > 1:
-            ops.gemm(Op.full(gp, mn_major=True), Op.full(x_planes, mn_major=True), ql.N, ql.K, kdim, PAIRS_FP32, splits=s,
+            ops.gemm(Op.full(gp, mn_major=True), Op.full(x_planes, mn_major=True), ql.N, ql.K, kdim, self.pairs, splits=s,
                      workspace=self.ws)
         else:
-            ops.gemm(Op.full(gp, mn_major=True), Op.full(x_planes, mn_major=True), ql.N, ql.K, kdim, PAIRS_FP32,
+            ops.gemm(Op.full(gp, mn_major=True), Op.full(x_planes, mn_major=True), ql.N, ql.K, kdim, self.pairs,
                      out=self.ws[:ql.N * ql.K].view(ql.N, ql.K))
         ops.splitk_reduce(self.ws, s, ql.N, ql.K, self._grad(ql.weight))
 
@@ -258,15 +268,15 @@ class PlainStudentEngine(_BatchBuffers):
             self._wgrad(ql["proj"], self.gpD, self.op[l], M)
             ops.split_planes(self.g_o, self.g_op)
             qkvp, Pp = self.qkvp[l], self.Pp[l]
-            ops.gemm(Op.tokens(self.g_op, B, T, 0, 64), Op.tokens(qkvp, B, T, 2 * D, 64), T, T, 64, PAIRS_FP32,
+            ops.gemm(Op.tokens(self.g_op, B, T, 0, 64), Op.tokens(qkvp, B, T, 2 * D, 64), T, T, 64, self.pairs,
                      out=Out.per_head(self.dP, BH, H, T, T), nbatch=BH, batch_inner=H)                      # dP = dO V^T
             ops.attn_ds(Pp, self.dP, d.ldS, BH * T, T, d.attn_scale, self.dSp)
-            ops.gemm(Op.per_head(self.dSp, BH, H, T, T), Op.tokens(qkvp, B, T, D, 64, mn_major=True), T, 64, T, PAIRS_FP32,
+            ops.gemm(Op.per_head(self.dSp, BH, H, T, T), Op.tokens(qkvp, B, T, D, 64, mn_major=True), T, 64, T, self.pairs,
                      out=Out.tokens(self.g_qkv, B, T, 0, 64), nbatch=BH, batch_inner=H)                      # dQ = dS K
             ops.gemm(Op.per_head(self.dSp, BH, H, T, T, mn_major=True), Op.tokens(qkvp, B, T, 0, 64, mn_major=True), T, 64, T,
-                     PAIRS_FP32, out=Out.tokens(self.g_qkv, B, T, D, 64), nbatch=BH, batch_inner=H)          # dK = dS^T Q
+                     self.pairs, out=Out.tokens(self.g_qkv, B, T, D, 64), nbatch=BH, batch_inner=H)          # dK = dS^T Q
             ops.gemm(Op.per_head(Pp, BH, H, T, T, mn_major=True), Op.tokens(self.g_op, B, T, 0, 64, mn_major=True), T, 64, T,
-                     PAIRS_FP32, out=Out.tokens(self.g_qkv, B, T, 2 * D, 64), nbatch=BH, batch_inner=H)      # dV = P^T dO
+                     self.pairs, out=Out.tokens(self.g_qkv, B, T, 2 * D, 64), nbatch=BH, batch_inner=H)      # dV = P^T dO
             self._gp(self.g_qkv, None, ql["qkv"], False, M, self.gp3)
             self._dgrad(ql["qkv"], self.gp3, M, self.g_h)
             self._wgrad(ql["qkv"], self.gp3, self.h1p[l], M)
@@ -289,8 +299,8 @@ class PlainDistillStep:
     reference's training iteration before QAT is enabled (ref qat_trainer.py:333-361 with qat_enabled == False, no AMP)."""
 
     def __init__(self, student: nn.Module, teacher: nn.Module, batch: int, hparams: Dict,
-                 grad_buffer: Optional[torch.Tensor] = None, teacher_mixed: Optional[bool] = None):
-        self.student_engine = PlainStudentEngine(student, batch, hparams, grad_buffer=grad_buffer)
+                 grad_buffer: Optional[torch.Tensor] = None, teacher_mixed: Optional[bool] = None, amp: bool = False):
+        self.student_engine = PlainStudentEngine(student, batch, hparams, grad_buffer=grad_buffer, amp=amp)
         self.teacher_engine = TeacherEngine(teacher, batch, mixed=teacher_mixed)
         self.grad_arena = self.student_engine.grad_arena
         self._tstream = torch.cuda.Stream(device=self.student_engine.dev)

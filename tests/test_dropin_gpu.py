@@ -91,6 +91,107 @@ def test_qat_linear_module(cuda_dev, installed, backend, shape):
             gpu_mod.weight.add_(delta.to(cuda_dev))
 
 
+@pytest.mark.parametrize("backend", ["fbgemm", "qnnpack"])
+def test_qat_conv2d_patch_embedding_module(cuda_dev, installed, backend):
+    """nnqat.Conv2d with kernel == stride (timm PatchEmbed.proj, ref model_registry.py:167-172 -> torch/ao/nn/qat/modules/conv.py:55-56)
+    as im2col + the fake-quant GEMM: y, all three gradients and the weight observer vs the stock module on CPU."""
+    import torch.ao.nn.qat as nnqat
+    torch.manual_seed(1)
+    cpu_mod = nnqat.Conv2d(3, 64, kernel_size=16, stride=16, bias=True, qconfig=_qconfig(backend))
+    gpu_mod = copy.deepcopy(cpu_mod).to(cuda_dev)
+    n0 = dict(installed.stats)
+    for it in range(2):
+        x = torch.randn(4, 3, 64, 64) * (1.0 + it)
+        gy = torch.randn(4, 64, 4, 4)
+        xc = x.clone().requires_grad_(True)
+        xg = x.to(cuda_dev).requires_grad_(True)
+        yc, yg = cpu_mod(xc), gpu_mod(xg)
+        assert yg.shape == yc.shape
+        yc.backward(gy)
+        yg.backward(gy.to(cuda_dev))
+        assert rel_max(yg, yc) < 1e-4
+        assert rel_max(xg.grad, xc.grad) < 1e-4
+        assert rel_max(gpu_mod.weight.grad, cpu_mod.weight.grad) < 1e-4
+        assert rel_max(gpu_mod.bias.grad, cpu_mod.bias.grad) < 1e-4
+        assert torch.equal(gpu_mod.weight.grad.cpu() == 0, cpu_mod.weight.grad == 0)
+        for k, v in cpu_mod.weight_fake_quant.state_dict().items():
+            assert torch.equal(gpu_mod.weight_fake_quant.state_dict()[k].cpu(), v), k
+        cpu_mod.zero_grad(set_to_none=True)
+        gpu_mod.zero_grad(set_to_none=True)
+    assert installed.stats["conv_gemm"] - n0["conv_gemm"] == 2 and installed.stats["conv_stock"] == n0["conv_stock"]
+    # a convolution that is not a patch embedding keeps the stock route (still fake-quantised by our kernel)
+    other = nnqat.Conv2d(3, 32, kernel_size=3, stride=1, padding=1, qconfig=_qconfig(backend)).to(cuda_dev)
+    other(torch.randn(2, 3, 8, 8, device=cuda_dev))
+    assert installed.stats["conv_stock"] == n0["conv_stock"] + 1
+
+
+@pytest.mark.parametrize("backend", ["fbgemm", "qnnpack"])
+@pytest.mark.parametrize("B", [8, 256])
+def test_qat_small_linear_head_module(cuda_dev, installed, backend, B):
+    """The 10-class head (N = 10 is not a tensor-core tile): fake-quantised fp32 weight + the small-Linear kernels."""
+    import torch.ao.nn.qat as nnqat
+    torch.manual_seed(2)
+    cpu_mod = nnqat.Linear(384, 10, bias=True, qconfig=_qconfig(backend))
+    gpu_mod = copy.deepcopy(cpu_mod).to(cuda_dev)
+    n0 = dict(installed.stats)
+    for it in range(2):
+        x = torch.randn(B, 384) * (1.0 + it)
+        gy = torch.randn(B, 10)
+        xc = x.clone().requires_grad_(True)
+        xg = x.to(cuda_dev).requires_grad_(True)
+        yc, yg = cpu_mod(xc), gpu_mod(xg)
+        yc.backward(gy)
+        yg.backward(gy.to(cuda_dev))
+        assert rel_max(yg, yc) < 1e-5
+        assert rel_max(xg.grad, xc.grad) < 1e-5
+        assert rel_max(gpu_mod.weight.grad, cpu_mod.weight.grad) < 1e-5
+        assert rel_max(gpu_mod.bias.grad, cpu_mod.bias.grad) < 1e-5
+        assert torch.equal(gpu_mod.weight.grad.cpu() == 0, cpu_mod.weight.grad == 0)
+        for k, v in cpu_mod.weight_fake_quant.state_dict().items():
+            assert torch.equal(gpu_mod.weight_fake_quant.state_dict()[k].cpu(), v), k
+        cpu_mod.zero_grad(set_to_none=True)
+        gpu_mod.zero_grad(set_to_none=True)
+    assert installed.stats["linear_small"] - n0["linear_small"] == 2 and installed.stats["linear_stock"] == n0["linear_stock"]
+
+
+def test_fake_quant_disabled_and_reused_modules(cuda_dev, installed):
+    """(a) torch.ao.quantization.disable_fake_quant: weights are then not integer codes -- the drop-in must notice the flag
+    (cached, re-read when the buffer changes) and compute x W^T with the RAW weight like the stock module; (b) a module
+    applied twice before backward (weight sharing) must not have the first call's saved operands overwritten by the second."""
+    import torch.ao.nn.qat as nnqat
+    from torch.ao.quantization import disable_fake_quant, enable_fake_quant
+    torch.manual_seed(3)
+    cpu_mod = nnqat.Linear(64, 96, bias=True, qconfig=_qconfig("fbgemm"))
+    gpu_mod = copy.deepcopy(cpu_mod).to(cuda_dev)
+    x = torch.randn(5, 7, 64)
+    for step in range(3):
+        if step == 1:
+            cpu_mod.apply(disable_fake_quant)
+            gpu_mod.apply(disable_fake_quant)
+        if step == 2:
+            cpu_mod.apply(enable_fake_quant)
+            gpu_mod.apply(enable_fake_quant)
+        n0 = dict(installed.stats)
+        yc, yg = cpu_mod(x), gpu_mod(x.to(cuda_dev))
+        assert rel_max(yg, yc) < 1e-4, step
+        took_stock = installed.stats["linear_stock"] - n0["linear_stock"]
+        assert took_stock == (1 if step == 1 else 0)
+        if step == 1:       # raw weights: the result must differ from the fake-quantised one by more than the tolerance
+            w = cpu_mod.weight.detach()
+            assert rel_max(yc, torch.nn.functional.linear(x, w, cpu_mod.bias.detach())) < 1e-6
+    # (b) y = f(f(x)) with one module (square so that it composes)
+    torch.manual_seed(4)
+    cpu_sq = nnqat.Linear(64, 64, bias=True, qconfig=_qconfig("fbgemm"))
+    gpu_sq = copy.deepcopy(cpu_sq).to(cuda_dev)
+    xc = torch.randn(33, 64, requires_grad=True)
+    xg = xc.detach().to(cuda_dev).requires_grad_(True)
+    cpu_sq(cpu_sq(xc)).square().sum().backward()
+    gpu_sq(gpu_sq(xg)).square().sum().backward()
+    assert rel_max(xg.grad, xc.grad) < 2e-4
+    assert rel_max(gpu_sq.weight.grad, cpu_sq.weight.grad) < 2e-4
+    assert rel_max(gpu_sq.bias.grad, cpu_sq.bias.grad) < 2e-4
+
+
 @pytest.mark.parametrize("B,C", [(256, 10), (8, 10), (5, 1000)])
 def test_distill_loss_dropin(cuda_dev, installed, B, C):
     from oracle import vit_ref as vr
@@ -121,9 +222,15 @@ def test_reference_loop_body_with_dropins(cuda_dev, installed):
     gpu_student = copy.deepcopy(prepared).to(cuda_dev)
     gpu_teacher = copy.deepcopy(teacher).to(cuda_dev)
     n0 = ops.launch_count()
+    st0 = dict(installed.stats)
     l_gpu, s_gpu, _ = vr.distill_step(gpu_student, gpu_teacher, images.to(cuda_dev), labels.to(cuda_dev), None, hp, clip=False)
     torch.cuda.synchronize()
     assert ops.launch_count() - n0 > 100            # the sm_100a kernels ran, not ATen's
+    st = {k: installed.stats[k] - st0[k] for k in st0}
+    # every fake-quant module of the prepared student took a native route: block Linears on the tensor-core GEMM, the patch
+    # embedding as im2col + GEMM, the 10-class head on the small-Linear kernels -- nothing left on cuDNN / cuBLAS
+    assert st["linear_stock"] == 0 and st["conv_stock"] == 0, st
+    assert st["conv_gemm"] == 1 and st["linear_small"] == 1 and st["linear_gemm"] == 4 * len(prepared.model.blocks), st
     l_cpu, s_cpu, _ = vr.distill_step(prepared, teacher, images, labels, None, hp, clip=False)
     assert abs(float(l_gpu) - float(l_cpu)) < 2e-2 * abs(float(l_cpu))
     g_cpu = torch.cat([p.grad.flatten() for p in prepared.parameters()])

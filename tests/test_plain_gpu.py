@@ -63,6 +63,41 @@ def test_plain_step_matches_fp32_autograd(cuda_dev, sname, tname, img, B, mixed)
     assert rel_max(step.predict(images.to(cuda_dev)), want) < 1e-4
 
 
+@pytest.mark.parametrize("sname,tname,img,B", [("vit_test_tiny", "vit_test_teacher", 64, 4),
+                                               ("vit_small_patch16_224", "vit_base_patch16_224", 224, 4)])
+def test_plain_step_amp_variant(cuda_dev, sname, tname, img, B):
+    """amp=True: the half-precision counterpart of the reference's optional --amp (fp16 autocast + GradScaler around the student,
+    ref qat_trainer.py:286,340,353-357): ONE bf16 tensor-core pass per product (operands rounded to 2^-9, fp32 accumulate, fp32
+    LayerNorm / softmax / loss).  Reduced precision by design, so the bar is NOT the 1e-3 of the fp32 path: loss within 1e-2 and
+    every gradient within 5e-2 (L2) of the fp32 CPU reference -- and the result must DIFFER from the fp32-grade step (the
+    single-pass path really ran).  The teacher stays fp32-grade: the reference runs it outside the autocast region."""
+    from qatvit_b200 import ops
+    from qatvit_b200.plain import PlainDistillStep
+    vr, student, teacher = _models(sname, tname, img)
+    hp = dict(vr.DEFAULT_HPARAMS)
+    gpu_student = copy.deepcopy(student).to(cuda_dev)
+    gpu_teacher = copy.deepcopy(teacher).to(cuda_dev)
+    step = PlainDistillStep(gpu_student, gpu_teacher, B, hp, amp=True)
+    assert step.student_engine.amp
+    images, labels = vr.synthetic_batch(B, seed=3, img=img)
+    out3 = step(images.to(cuda_dev), labels.to(cuda_dev))
+    torch.cuda.synchronize()
+    loss_ref, s_ref, t_ref = vr.distill_step(student, teacher, images, labels, None, hp, clip=False)
+    assert rel_max(step.teacher_engine.logits, t_ref) < 1e-4                  # the teacher is not under autocast
+    assert 1e-6 < rel_l2(step.student_engine.logits, s_ref) < 2e-2
+    assert abs(float(out3[0]) - float(loss_ref)) <= 1e-2 * abs(float(loss_ref))
+    ref = dict(student.named_parameters())
+    worst = 0.0
+    for n, p in gpu_student.named_parameters():
+        assert torch.isfinite(p.grad).all(), n
+        worst = max(worst, rel_l2(p.grad, ref[n].grad))
+    assert 1e-5 < worst < 5e-2, worst
+    # the same engine object also serves validation
+    with torch.no_grad():
+        want = student(images)
+    assert rel_l2(step.predict(images.to(cuda_dev)), want) < 2e-2
+
+
 def test_plain_then_qat_handover(cuda_dev):
     """The reference's schedule: plain epochs, then prepare_qat on the SAME parameters (ref qat_trainer.py:300-316).  Train two plain
     steps with the fused optimizer, prepare, and run the QAT engine on the result: the hand-over keeps every parameter value."""
