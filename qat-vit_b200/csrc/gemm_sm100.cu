@@ -153,12 +153,24 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  __shared__ float gelu_lut[EPI == 2 ? 256 : 1];
+  // EPI 2: FQ(y) takes at most qmax - qmin + 1 <= 256 distinct values, so  gelu'(FQ(y)) * STEmask(y)  is ONE table lookup on the
+  // code clamped to [qmin - 1, qmax + 1]: entry 0 and the last entry are the two out-of-range sides (mask = 0), entry k + 1 is
+  // gelu'((qmin + k - zp) * scale) -- or 1 without GELU.  Same expression per code as the elementwise kernels -> same bits.
+  // The table is kept in 8 interleaved copies (entry k, copy r at word 8 k + r; lane L reads copy L & 7): the codes of a warp's 32
+  // rows are data-dependent, and with ONE copy the gather cost ~6 shared-memory wavefronts per load (ncu: 63 % of the kernel's
+  // shared-load wavefronts were bank conflicts, LSU data pipe 69 % busy = the limiter); with 8 copies only lanes L, L + 8, L + 16,
+  // L + 24 can still collide.
+  constexpr int LUT_COPIES = 8;
+  __shared__ float gelu_lut[EPI == 2 ? 260 * LUT_COPIES : 1];
   if constexpr (EPI == 2) {
-    if (p.ep_gelu) {     // FQ(y) takes at most qmax - qmin + 1 <= 256 distinct values: gelu'(FQ(y)) by table lookup on the code
-      const QvQParams yq = qv_load_qparams(p.ep_scale, p.ep_zp, p.ep_qmin, p.ep_qmax);
-      for (int k = threadIdx.x; k <= p.ep_qmax - p.ep_qmin && k < 256; k += NUM_THREADS)
-        gelu_lut[k] = qv_gelu_grad(__fmul_rn(__fsub_rn(static_cast<float>(p.ep_qmin + k), yq.zp), yq.scale));
+    const QvQParams yq = qv_load_qparams(p.ep_scale, p.ep_zp, p.ep_qmin, p.ep_qmax);
+    const int ncodes = p.ep_qmax - p.ep_qmin + 1;
+    for (int k = threadIdx.x; k < ncodes + 2 && k < 260; k += NUM_THREADS) {
+      float v = 0.f;
+      if (k >= 1 && k <= ncodes)
+        v = p.ep_gelu ? qv_gelu_grad(__fmul_rn(__fsub_rn(static_cast<float>(p.ep_qmin + k - 1), yq.zp), yq.scale)) : 1.0f;
+#pragma unroll
+      for (int r = 0; r < LUT_COPIES; ++r) gelu_lut[k * LUT_COPIES + r] = v;
     }
   }
 
@@ -464,7 +476,10 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       uint8_t* my_out = my_raw + 8192;                            // 2 KB hi + 2 KB lo: 32 rows x 64 B, 64B swizzle
       uint64_t* my_bar = &raw_bar[ew];
       const QvQParams yq = qv_load_qparams(p.ep_scale, p.ep_zp, p.ep_qmin, p.ep_qmax);
-      const bool use_lut = p.ep_gelu != 0;
+      // clamp bounds in the magic domain (exact: small integers added to 1.5 * 2^23) and the table base folded with the bits of the
+      // lower bound (index 0), all modulo 2^32
+      const float t_lo = 12582912.0f + (yq.qmin - 1.0f - yq.zp), t_hi = 12582912.0f + (yq.qmax + 1.0f - yq.zp);
+      const uint32_t lut_off = smem_u32(gelu_lut) + static_cast<uint32_t>(lane & 7) * 4u - (__float_as_uint(t_lo) << 5);
       auto issue_raw = [&](int item, int u, uint32_t slot) {      // lane 0 only
         const int n_blk = item % p.tiles_n;
         const int m_blk = m_of(item);
@@ -473,6 +488,9 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       };
       uint32_t raw_phase = 0;             // also the slot of the tile being waited for (loads alternate slots)
       int local = 0;
+#ifdef QV_ATTN_DEBUG
+      int gdbg_n = (threadIdx.x == 64) ? 0 : 4096;
+#endif
       if (item0 < num_items && lane == 0) issue_raw(item0, par, 0);
       for (int item = item0; item < num_items; item += item_step, ++local) {
         const int n_blk = item % p.tiles_n;
@@ -485,7 +503,9 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll 1
         for (int u = par; u < NU; u += 2) {
           // ---- this unit's y values: smem -> registers, then hand the buffer to the next unit's load ----
+          GDBG(2, 30);
           mbar_wait(my_bar, raw_phase);
+          GDBG(2, 31);
           float4 yv[8];
           {
             const uint32_t srow = smem_u32(my_raw) + raw_phase * 4096u + lane * 128;
@@ -503,14 +523,26 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (!last) issue_raw(item, u + 2, raw_phase);
             else if (item + item_step < num_items) issue_raw(item + item_step, par, raw_phase);
           }
+          // this unit's 32 weight scales (every lane the same 128 bytes: broadcast loads), issued before the accumulator wait
+          float4 csv[8];
+          {
+            const int64_t n0s = static_cast<int64_t>(n_blk) * BN + u * 32;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              csv[j] = (p.col_scale && n0s < p.N) ? __ldg(reinterpret_cast<const float4*>(p.col_scale + n0s + 4 * j))     // N % 64 == 0: whole units
+                                                  : make_float4(1.f, 1.f, 1.f, 1.f);
+          }
           if (!acc_ready) {
+            GDBG(2, 20);
             mbar_wait(&tmem_full[buf], use & 1);
+            GDBG(2, 21);
             tc_fence_after();
             acc_ready = true;
           }
           uint32_t rr[32];
           tmem_ld_cols<32>(t_base + u * 32, rr);
           tmem_ld_wait();
+          GDBG(2, 32);
           if (last) {                                             // this warp's last TMEM read of the buffer
             tc_fence_before();
             tmem_empty_arrive(buf);
@@ -519,29 +551,37 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (n0 >= p.N || static_cast<int64_t>(row0) >= p.M) continue;          // warp-uniform
           if (lane == 0) tma_store_wait_read<0>();                // previous planes have left the staging buffer
           __syncwarp();
-          float gq[32];
+          GDBG(2, 33);
+          // Per element (8 instructions + the operand split; was 24): t = y * inv + 1.5 * 2^23 is the magic-number round-to-nearest-
+          // even (exact for |y * inv| < 2^22, still far out of range beyond; no FRND): its mantissa IS rint(y * inv), so the code is
+          // clamped in that domain -- [qmin - 1 - zp, qmax + 1 - zp] + 1.5 * 2^23, floats compare like the integers they hold -- and
+          // the clamped float's BITS, shifted left by 5 (modulo 2^32) plus a constant, are the address of the table entry (8 copies x
+          // 4 bytes per code; no F2I, no subtract).  The table holds gelu' * STE mask, so there is no compare / select either.
           const uint32_t srow_hi = smem_u32(my_out) + lane * 64, srow_lo = srow_hi + 2048;
+          // column-sum scratch: the y slot this unit has just emptied (its next TMA refill is two units away)
+          const uint32_t cs_row = smem_u32(my_raw) + (raw_phase ^ 1u) * 4096u + lane * 128;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {                           // 8 columns per step
-            float4 sa = make_float4(1.f, 1.f, 1.f, 1.f), sb = sa;
-            if (p.col_scale) {
-              sa = __ldg(reinterpret_cast<const float4*>(p.col_scale + n0 + 8 * j));
-              sb = __ldg(reinterpret_cast<const float4*>(p.col_scale + n0 + 8 * j + 4));
-            }
+            const float4 sa = csv[2 * j], sb = csv[2 * j + 1];
             const float4 ya = yv[2 * j], yb = yv[2 * j + 1];
             const float yy[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
             const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
-            float a[8];
+            float a[8], gq[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              const float r = __fadd_rn(rintf(__fmul_rn(yy[e], yq.inv)), yq.zp);
-              const float c = fminf(fmaxf(r, yq.qmin), yq.qmax);
-              const bool in = (yq.qmin <= r) && (r <= yq.qmax);
-              float f = __uint_as_float(rr[8 * j + e]);
-              if (use_lut) f *= gelu_lut[static_cast<int>(c - yq.qmin)];
-              f = in ? f : 0.f;
-              gq[8 * j + e] = f;
-              a[e] = f * sc[e];
+              const float t = __fadd_rn(__fmul_rn(yy[e], yq.inv), 12582912.0f);
+              const float tc = fminf(fmaxf(t, t_lo), t_hi);
+              float l;
+              asm("ld.shared.f32 %0, [%1];" : "=f"(l) : "r"((__float_as_uint(tc) << 5) + lut_off));
+              const float f = __uint_as_float(rr[8 * j + e]) * l;
+              gq[e] = f;
+              a[e] = __fmaf_rn(f, sc[e], 0.0f);       // + 0: a masked element (f = -0 for a negative accumulator) leaves as +0, like the select did
+            }
+            if (p.ep_colsum) {
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cs_row + (static_cast<uint32_t>((2 * j) ^ (lane & 7)) << 4)),
+                           "f"(gq[0]), "f"(gq[1]), "f"(gq[2]), "f"(gq[3]) : "memory");
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cs_row + (static_cast<uint32_t>((2 * j + 1) ^ (lane & 7)) << 4)),
+                           "f"(gq[4]), "f"(gq[5]), "f"(gq[6]), "f"(gq[7]) : "memory");
             }
             uint32_t hi[4], lo[4];
 #pragma unroll
@@ -568,10 +608,23 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tma_store_4d(&map_o, my_out + 2048, static_cast<int>(n0), row0, 0, 1);
             tma_store_commit();
           }
+          GDBG(2, 34);
           if (p.ep_colsum) {
-            const float cs = qv_warp_colsum32(gq, lane);
+            // bias-grad partial of column `lane` over this slab's 32 rows: read the fp32 tile back column-wise (row i keeps its
+            // 16-byte chunk k at k ^ (i & 7): the 32 lanes of one load hit 32 different banks), summed in row order -> deterministic
+            const uint32_t cs_base = smem_u32(my_raw) + (raw_phase ^ 1u) * 4096u + static_cast<uint32_t>(lane & 3) * 4u;
+            const uint32_t ck = static_cast<uint32_t>(lane >> 2);
+            float c4[4] = {0.f, 0.f, 0.f, 0.f};             // four interleaved partial sums (fixed order): no 32-deep dependent chain
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float t;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(cs_base + i * 128 + ((ck ^ static_cast<uint32_t>(i & 7)) << 4)) : "memory");
+              c4[i & 3] += t;
+            }
+            const float cs = (c4[0] + c4[1]) + (c4[2] + c4[3]);
             p.ep_colsum[(static_cast<int64_t>(m_blk) * 4 + q) * p.N + n0 + lane] = cs;
           }
+          GDBG(2, 35);
         }
       }
       if (lane == 0) tma_store_wait_read<0>();

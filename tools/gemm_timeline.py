@@ -12,7 +12,8 @@ import qatvit_b200  # noqa: E402,F401
 from qatvit_b200 import _lib, ops  # noqa: E402
 from qatvit_b200.ops import Op  # noqa: E402
 
-TAGS = {1: "tma: wait empty", 2: "tma: empty ok", 10: "mma: wait tmem_empty", 11: "mma: tmem_empty ok", 12: "mma: wait full",
+TAGS = {1: "tma: wait empty", 2: "tma: empty ok", 30: "epi2: wait raw y", 31: "epi2: raw y ok", 32: "epi2: acc in regs", 33: "epi2: staging free", 34: "epi2: planes stored",
+        35: "epi2: colsum done", 10: "mma: wait tmem_empty", 11: "mma: tmem_empty ok", 12: "mma: wait full",
         13: "mma: full ok", 14: "mma: issued", 20: "epi: wait tmem_full", 21: "epi: tmem_full ok", 22: "epi: tmem released"}
 
 
@@ -37,8 +38,17 @@ def main():
     outp = torch.empty(2, M, N, dtype=torch.bfloat16, device=dev) if planes_out else None
     L = _lib.lib()
 
+    grad_epi = os.environ.get("QV_TL_GRADEPI", "0") != "0"    # fc2 dgrad + fc1 gradient-planes epilogue (EPI 2)
+    if grad_epi:
+        y_raw = torch.randn(M, N, device=dev)
+        gsc, gzp = torch.tensor([0.05], device=dev), torch.tensor([64], dtype=torch.int32, device=dev)
+        gpo = torch.empty(2, M, N, dtype=torch.bfloat16, device=dev)
+        part = torch.empty(-(-M // 32), N, device=dev)
+
     def run():
-        if mix and planes_out:
+        if grad_epi:
+            ops.gemm(Op.full(ap), Op.full(bp), M, N, K, (pa, pb), out_planes=gpo, col_scale=cs, grad_of=(y_raw, (gsc, gzp, 0, 127), True, part))
+        elif mix and planes_out:
             ops.gemm(Op.full(ap), Op.full(bp), M, N, K, (2, 2), bias=bias, out_planes=outp, gelu=True, mix=True, out_mix=True)
         elif mix:
             ops.gemm(Op.full(ap), Op.full(bp), M, N, K, (2, 2), out=out, bias=bias, mix=True)
@@ -69,7 +79,7 @@ def main():
     # aggregate waiting time per role
     waits = {}
     open_ = {}
-    pairs = {1: 2, 10: 11, 12: 13, 20: 21}
+    pairs = {1: 2, 10: 11, 12: 13, 20: 21, 30: 31}
     for t, tag, who in ev:
         if tag in pairs:
             open_[tag] = t
