@@ -12,7 +12,8 @@
 // bit-identical to the fbgemm / x86 engines of the reference (tests/test_int8_gpu.py; oracle: oracle/fq_oracle.c qo_int8_linear).
 //
 // Structure: persistent 128 x BN tiles; warp 0 TMA producer (128-byte rows of 128 int8, 128B swizzle, OOB zero fill),
-// warp 1 MMA issuer (4 x K=32 steps per stage, double-buffered TMEM accumulators), warps 2-5 requantising epilogue.
+// warp 1 MMA issuer (4 x K=32 steps per stage, double-buffered TMEM accumulators), warps 2-9 requantising epilogue (two per
+// TMEM lane quarter on alternate 32-column chunks; the per-column terms of a chunk are staged once in shared memory).
 #include <cuda.h>
 #include <stdio.h>
 #include <string.h>
@@ -28,15 +29,17 @@ namespace {
 constexpr int I8_BM = 128;
 constexpr int I8_BK = 128;          // 128 int8 = one 128-byte swizzle row
 constexpr int I8_UMMA_K = 32;
-constexpr int I8_THREADS = 192;
+constexpr int I8_THREADS = 320;        // TMA warp, MMA warp, 8 requantising warps (two per TMEM lane quarter)
+constexpr int I8_STAGE_OUT_BYTES = 8 * (4096 + 1024);   // per epilogue warp: 32 x 32 fp32 (128B swizzle) + 32 x 32 uint8 output staging
+constexpr int I8_TERM_BYTES = 8 * 3 * 32 * 4;   // per epilogue warp: [add int32 x 32][bias term x 32][multiplier x 32] of the chunk's columns
 constexpr int I8_A_BYTES = I8_BM * I8_BK;
 
 template <int BN>
 struct I8Cfg {
   static constexpr int B_BYTES = BN * I8_BK;
   static constexpr int STAGE_BYTES = I8_A_BYTES + B_BYTES;
-  static constexpr int STAGES = 6;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int STAGES = 5;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + I8_STAGE_OUT_BYTES + I8_TERM_BYTES + 1024 + 256;
   static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : 256;
 };
 
@@ -54,6 +57,7 @@ struct I8Params {
   int32_t bias_int;       // 0: float bias added to float(acc) (x86 / fbgemm); 1: bias pre-quantised to int32 (qnnpack)
   uint8_t* qy;            // [M,N] quint8 codes (may be null)
   float* y;               // [M,N] dequantised (q_y - z_y) * s_y (may be null)
+  int32_t tma_y, tma_q;   // outputs leave through shared-memory staging + TMA stores (full 128-byte lines) when their pitch allows
 };
 
 __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -77,13 +81,22 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* map, uin
                : "memory");
 }
 
+__device__ __forceinline__ void tma_store_2d(const void* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+
 template <int BN>
 __global__ void __launch_bounds__(I8_THREADS, 1)
-qv_int8_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const I8Params p) {
+qv_int8_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                      const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_q, const I8Params p) {
   using C = I8Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint8_t* smem_out = smem + C::STAGES * C::STAGE_BYTES;          // 1 KB aligned: STAGE_BYTES is a multiple of 1024
+  uint8_t* smem_terms = smem_out + I8_STAGE_OUT_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_terms + I8_TERM_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + C::STAGES;
   uint64_t* tmem_full = bars + 2 * C::STAGES;
@@ -94,8 +107,10 @@ qv_int8_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   if (threadIdx.x == 0) {
     prefetch_tensormap(&map_a);
     prefetch_tensormap(&map_b);
+    if (p.tma_y) prefetch_tensormap(&map_y);
+    if (p.tma_q) prefetch_tensormap(&map_q);
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 256); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
@@ -151,11 +166,25 @@ qv_int8_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     }
   } else {
     // =============================== requantising epilogue ===============================
+    // A K = 384 tile is 12 MMAs (~1.2 k clk at the int8 rate): the epilogue, not the tensor pipe, bounds this kernel, so it runs
+    // on 8 warps, fetches the per-column terms as broadcast LDS.128 (they were three shuffles per ELEMENT) and rounds with the
+    // magic-number add (round-to-nearest-even like nearbyintf, exact for |v| < 2^22 and clamped the same beyond).
+    const int ew = warp - 2;
     const int q = warp & 3;
+    const int par = ew >> 2;
     const float sx = __ldg(p.sx);
     const int32_t zx = __ldg(p.zx);
     const float zyf = static_cast<float>(p.zy);
+    const float rint_c = 12582912.0f - zyf;                  // (v + 1.5 * 2^23) - rint_c = rint(v) + z_y
     const bool vec_ok = (p.N % 16 == 0);
+    int32_t* t_add = reinterpret_cast<int32_t*>(smem_terms) + ew * 96;
+    float* t_badd = reinterpret_cast<float*>(t_add + 32);
+    float* t_mult = t_badd + 32;
+    // Row-per-lane registers written straight to global memory touch 32 different lines per store instruction (one 16-byte
+    // piece of a sector each: the LSU, not HBM, bounded the kernel): outputs go through swizzled staging and leave as TMA boxes.
+    uint8_t* st_y = smem_out + ew * (4096 + 1024);
+    uint8_t* st_q = st_y + 4096;
+    const bool any_tma = p.tma_y || p.tma_q;
     int local = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
       const int n_blk = item % p.tiles_n, m_blk = item / p.tiles_n;
@@ -165,21 +194,15 @@ qv_int8_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       const int64_t row = static_cast<int64_t>(m_blk) * I8_BM + q * 32 + lane;
       const bool row_ok = row < p.M;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = par * 32; c0 < BN; c0 += 64) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN + c0), r);
-        tmem_ld_wait();
-        if (c0 + 32 >= BN) {
-          tc_fence_before();
-          mbar_arrive(&tmem_empty[buf]);
-        }
         const int64_t n0 = static_cast<int64_t>(n_blk) * BN + c0;
-        if (n0 >= p.N) continue;
-        // per-column terms: lane j owns column n0 + j
-        int32_t my_add = 0;          // - z_x * sum_k q_w  (+ rint(b / (s_x s_w)) in qnnpack mode)
-        float my_badd = 0.f;         // b / (s_x s_w)  (x86 / fbgemm mode)
-        float my_mult = 0.f;         // s_x s_w / s_y
+        // per-column terms while the TMEM load is in flight: lane j owns column n0 + j
         {
+          int32_t my_add = 0;          // - z_x * sum_k q_w  (+ rint(b / (s_x s_w)) in qnnpack mode)
+          float my_badd = 0.f;         // b / (s_x s_w)  (x86 / fbgemm mode)
+          float my_mult = 0.f;         // s_x s_w / s_y
           const int64_t n = n0 + lane;
           if (n < p.N) {
             const float bs = __fmul_rn(sx, __ldg(p.sw + (p.per_channel ? n : 0)));
@@ -191,25 +214,68 @@ qv_int8_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
               else my_badd = bq;
             }
           }
+          __syncwarp();                // the previous chunk's reads of this warp's term buffer are done
+          t_add[lane] = my_add;
+          t_badd[lane] = my_badd;
+          t_mult[lane] = my_mult;
+          __syncwarp();
         }
+        tmem_ld_wait();
+        if (c0 + 64 >= BN) {           // this warp's last chunk of the tile is in registers
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[buf]);
+        }
+        if (n0 >= p.N) continue;
         const int ncols = static_cast<int>(min(static_cast<int64_t>(32), p.N - n0));
         uint32_t packed[8];
         float deq[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int32_t add_j = __shfl_sync(0xffffffffu, my_add, j);
-          const float mult_j = __shfl_sync(0xffffffffu, my_mult, j);
-          const float badd_j = __shfl_sync(0xffffffffu, my_badd, j);
-          const int32_t acc = static_cast<int32_t>(r[j]) + add_j;
-          float f = __fadd_rn(nearbyintf(__fmul_rn(__fadd_rn(static_cast<float>(acc), badd_j), mult_j)), zyf);
-          f = fminf(fmaxf(f, 0.0f), 255.0f);
-          const uint32_t code = static_cast<uint32_t>(f);
-          deq[j] = __fmul_rn(__fsub_rn(f, zyf), p.sy);
-          if ((j & 3) == 0) packed[j >> 2] = code;
-          else packed[j >> 2] |= code << (8 * (j & 3));
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const int4 a4 = *reinterpret_cast<const int4*>(t_add + 4 * j4);
+          const float4 b4 = *reinterpret_cast<const float4*>(t_badd + 4 * j4);
+          const float4 m4 = *reinterpret_cast<const float4*>(t_mult + 4 * j4);
+          const int32_t aj[4] = {a4.x, a4.y, a4.z, a4.w};
+          const float bj[4] = {b4.x, b4.y, b4.z, b4.w};
+          const float mj[4] = {m4.x, m4.y, m4.z, m4.w};
+          uint32_t w = 0;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int32_t acc = static_cast<int32_t>(r[4 * j4 + e]) + aj[e];
+            const float v = __fmul_rn(__fadd_rn(static_cast<float>(acc), bj[e]), mj[e]);
+            float f = __fsub_rn(__fadd_rn(v, 12582912.0f), rint_c);
+            f = fminf(fmaxf(f, 0.0f), 255.0f);
+            w |= static_cast<uint32_t>(f) << (8 * e);
+            deq[4 * j4 + e] = __fmul_rn(__fsub_rn(f, zyf), p.sy);
+          }
+          packed[j4] = w;
+        }
+        const int row0 = m_blk * I8_BM + q * 32;
+        if (static_cast<int64_t>(row0) >= p.M) continue;          // warp-uniform: the whole slab is padding
+        if (any_tma) {
+          if (lane == 0) tma_store_wait_read<0>();                // the previous chunk's boxes have left the staging buffers
+          __syncwarp();
+          if (p.tma_q && p.qy) {                                  // 32 rows x 32 bytes, linear
+            const uint32_t a = smem_u32(st_q) + lane * 32;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(packed[0]), "r"(packed[1]), "r"(packed[2]), "r"(packed[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + 16), "r"(packed[4]), "r"(packed[5]), "r"(packed[6]), "r"(packed[7]) : "memory");
+          }
+          if (p.tma_y && p.y) {                                   // 32 rows x 128 bytes, 16-byte chunk j of row r at j ^ (r & 7)
+            const uint32_t a = smem_u32(st_y) + lane * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a + (static_cast<uint32_t>(j ^ (lane & 7)) << 4)), "f"(deq[4 * j]),
+                           "f"(deq[4 * j + 1]), "f"(deq[4 * j + 2]), "f"(deq[4 * j + 3]) : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (p.tma_q && p.qy) tma_store_2d(&map_q, st_q, static_cast<int>(n0), row0);
+            if (p.tma_y && p.y) tma_store_3d(&map_y, st_y, static_cast<int>(n0), row0, 0);
+            tma_store_commit();
+          }
         }
         if (!row_ok) continue;
-        if (p.qy) {
+        if (p.qy && !p.tma_q) {
           uint8_t* dst = p.qy + row * p.N + n0;
           if (vec_ok && ncols == 32) {
             *reinterpret_cast<uint4*>(dst) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
@@ -220,7 +286,7 @@ qv_int8_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
               if (j < ncols) dst[j] = static_cast<uint8_t>((packed[j >> 2] >> (8 * (j & 3))) & 0xffu);
           }
         }
-        if (p.y) {
+        if (p.y && !p.tma_y) {
           float* dst = p.y + row * p.N + n0;
           if (p.N % 4 == 0 && ncols == 32) {
 #pragma unroll
@@ -234,6 +300,7 @@ qv_int8_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         }
       }
     }
+    if (any_tma && lane == 0) tma_store_wait_read<0>();
   }
 
   tc_fence_before();
@@ -261,8 +328,23 @@ int make_map_i8(CUtensorMap* m, const void* ptr, int64_t rows, int64_t K, int bo
   return 0;
 }
 
+// quint8 output [rows][N] as a 2-D tensor (N, rows); store box = (32 bytes, 32 rows), no swizzle
+int make_map_q_out(CUtensorMap* m, uint8_t* ptr, int64_t rows, int64_t N) {
+  EncodeTiledFn enc = get_encode();
+  QV_REQUIRE(enc != nullptr, QV_ERR_CUDA, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(N)};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  QV_REQUIRE(r == CUDA_SUCCESS, QV_ERR_CUDA, "cuTensorMapEncodeTiled(quint8 output) failed (%d)", (int)r);
+  return 0;
+}
+
 template <int BN>
-int launch_i8(const CUtensorMap& ma, const CUtensorMap& mb, const I8Params& kp, int grid, cudaStream_t st) {
+int launch_i8(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& my, const CUtensorMap& mq, const I8Params& kp, int grid,
+              cudaStream_t st) {
   using C = I8Cfg<BN>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
@@ -270,7 +352,7 @@ int launch_i8(const CUtensorMap& ma, const CUtensorMap& mb, const I8Params& kp, 
     attr_err = cudaFuncSetAttribute(qv_int8_linear_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
   });
   QV_REQUIRE(attr_err == cudaSuccess, QV_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
-  qv_int8_linear_kernel<BN><<<grid, I8_THREADS, C::SMEM_BYTES, st>>>(ma, mb, kp);
+  qv_int8_linear_kernel<BN><<<grid, I8_THREADS, C::SMEM_BYTES, st>>>(ma, mb, my, mq, kp);
   return qv_check_launch("qv_int8_linear");
 }
 
@@ -336,12 +418,24 @@ extern "C" int qv_int8_linear(const uint8_t* qx, int64_t M, int64_t K, const flo
   kp.tiles_n = static_cast<int32_t>((N + BN - 1) / BN);
   kp.sx = sx; kp.zx = zx; kp.sw = sw; kp.per_channel = per_channel; kp.wsum = wsum; kp.bias = bias;
   kp.sy = sy; kp.zy = zy; kp.bias_int = bias_int; kp.qy = qy; kp.y = y;
+  // TMA-stored outputs need 16-byte aligned bases and row pitches (N % 4 floats / N % 16 bytes); the 10-class head keeps plain stores
+  CUtensorMap my = ma, mq = ma;
+  kp.tma_y = (y && N % 4 == 0 && qv_aligned16(y)) ? 1 : 0;
+  kp.tma_q = (qy && N % 16 == 0 && qv_aligned16(qy)) ? 1 : 0;
+  if (kp.tma_y) {
+    rc = make_out_map(&my, y, N, M, N, 1, 0);
+    if (rc) return rc;
+  }
+  if (kp.tma_q) {
+    rc = make_map_q_out(&mq, qy, M, N);
+    if (rc) return rc;
+  }
   const int64_t items = static_cast<int64_t>(kp.tiles_m) * kp.tiles_n;
   const int sms = qv_num_sms();
   const int grid = static_cast<int>(items < sms ? items : sms);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (BN == 64) return launch_i8<64>(ma, mb, kp, grid, st);
-  return launch_i8<128>(ma, mb, kp, grid, st);
+  if (BN == 64) return launch_i8<64>(ma, mb, my, mq, kp, grid, st);
+  return launch_i8<128>(ma, mb, my, mq, kp, grid, st);
 }
 
 extern "C" int qv_quantize_u8(const float* x, int64_t n, const float* scale, const int32_t* zero_point, uint8_t* q, void* stream) {
