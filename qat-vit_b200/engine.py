@@ -647,12 +647,16 @@ class StudentEngine(_BatchBuffers):
             add("dSp", lambda d: (2, d.B * d.H * d.T, d.ldP), bf, zero=True)
         import os
         self.rpb_gp = 64
-        self.rpb_ln = int(os.environ.get("QV_RPB_LN", "64"))
+        # token rows per block of the LayerNorm backward: by default ONE full wave of 2 blocks per SM (788 blocks of 64 rows ran
+        # 2.66 waves at batch 256: 4 700 -> 5 080 GB/s with 171 rows per block); a function of the CURRENT batch so that b images on
+        # an engine built for B reduce in the same order as on an engine built for b.  QV_RPB_LN=<n> pins it (A/B).
+        self._rpb_ln_env = int(os.environ.get("QV_RPB_LN", "0"))
+        self.rpb_ln = self._rpb_ln_for(M)
         # bias-grad partial sums: standalone gp_planes [M/64][N]; GEMM epilogue [M/32][F]; attention backward [B*mt*4][3D]
         # (sized for the construction batch; a smaller batch uses a prefix)
         slabs_full = B * (-(-T // 128)) * 4
-        self.bias_part = e(max(-(-M // self.rpb_gp) * max(F, 3 * D), -(-M // 32) * F, slabs_full * 3 * D))
-        self.ln_part = e(-(-M // self.rpb_ln), 2, D)
+        self.bias_part = e(max(-(-M // self.rpb_gp) * max(F, 3 * D), -(-M // 32) * F, slabs_full * 3 * D, -(-M // 8) * D))
+        self.ln_part = e(max(-(-(bb * T) // self._rpb_ln_for(bb * T)) for bb in range(1, B + 1)), 2, D)
         # split-K factors of the weight-gradient GEMMs depend on the token count: one table per batch size 1..B, and a
         # workspace that holds the largest of them (so that b images on an engine built for B split exactly like an engine
         # built for b -- bit-identical sums)
@@ -667,8 +671,14 @@ class StudentEngine(_BatchBuffers):
         self.ws = e(max_ws)
         self._bb_on_bind(B)
 
+    def _rpb_ln_for(self, rows: int) -> int:
+        if self._rpb_ln_env > 0:
+            return self._rpb_ln_env
+        return max(8, -(-rows // (2 * self.sms)))
+
     def _bb_on_bind(self, b: int) -> None:
         d = self.d
+        self.rpb_ln = self._rpb_ln_for(b * d.T)
         self._splits = self._splits_by_b[b]
         self.slabs_attn = b * (-(-d.T // 128)) * 4
         self.stats1 = list(zip(self.st1m, self.st1r))
