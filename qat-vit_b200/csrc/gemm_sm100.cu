@@ -34,12 +34,18 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;            // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 320;           // TMA warp, MMA warp, 8 epilogue warps
+// Threads: TMA warp, MMA warp, then the epilogue warps.  The plane-output epilogue (EPI 1: bias [+ GELU] + operand split, 13-23
+// instructions per element with MUFU / conversion chains) is LATENCY-bound with two warps per scheduler -- ncu: issue slots 40 %,
+// tensor pipe 57 % on the teacher's fc1, where a 256 x 256 pair tile's 12 k-blocks of MMAs are shorter than its epilogue -- so it runs on
+// 16 warps (four per TMEM lane quarter and scheduler) over 32-column chunks; the lighter fp32 epilogue keeps 8.
+__host__ __device__ constexpr int epi_warps(int epi) { return epi == 1 ? 16 : 8; }
+__host__ __device__ constexpr int num_threads(int epi) { return 64 + 32 * epi_warps(epi); }
 constexpr int A_PLANE_BYTES = BM * BK * 2;
 // epilogue staging per warp: 32-row x 128-byte buffers.  fp32 output: one buffer per 32-column chunk; bf16 hi/lo plane
 // output: a hi and a lo buffer per 64-column chunk.  Two warps alternate on each TMEM lane quarter, so per-warp single
 // buffering already overlaps one warp's TMA store with the other's math.
-constexpr int epi_warp_bytes(int epi) { return (epi == 2 ? 3 : epi == 1 ? 2 : 1) * 32 * 128; }   // EPI 2: y tile x2 + planes
+// EPI 0: 32 x 32 fp32;  EPI 1: 32 rows x 32 columns of both planes (2 x 2 KB: bf16 hi | lo, or fp16 | hi8 + lo8);  EPI 2: y tile x2 + planes
+constexpr int epi_warp_bytes(int epi) { return (epi == 2 ? 3 : 1) * 32 * 128; }
 constexpr int epi_terms_bytes(int epi) { return epi >= 1 ? 0 : 8 * 2 * 32 * 4; }   // per-warp [mult][bias] column terms
 constexpr int SMEM_LIMIT = 232448;             // 227 KB
 #ifndef QV_GEMM_PAIR_DEFAULT
@@ -94,7 +100,7 @@ struct Cfg {
   static constexpr int STAGE_BYTES = SPLIT ? (A_PLANE_BYTES + B_PLANE_BYTES) : (NA * A_PLANE_BYTES + NB * B_PLANE_BYTES);
   static_assert(!SPLIT || (NA == 2 && NB == 2), "region-split stages: two regions per operand");
   static constexpr int EPI_WARP_BYTES = epi_warp_bytes(EPI);
-  static constexpr int EPI_BYTES = 8 * EPI_WARP_BYTES + epi_terms_bytes(EPI);
+  static constexpr int EPI_BYTES = epi_warps(EPI) * EPI_WARP_BYTES + epi_terms_bytes(EPI);
   static constexpr int MAX_STAGES = (SMEM_LIMIT - 1024 - 256 - EPI_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = MAX_STAGES > 6 ? 6 : MAX_STAGES;       // barrier block holds 2 x 6 + 13 words
   static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
@@ -123,7 +129,7 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 // gelu'(FQ(y)) -- a 256-entry table over the integer codes, built per CTA -- and the STE mask recomputed from the raw y tile,
 // folded with the per-channel weight scale and written as hi/lo planes; bias-grad column sums leave as per-slab partials.
 template <int BN, int NA, int NB, bool A_MN, bool B_MN, int EPI, int MIX, int CG = 1>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(num_threads(EPI), 1)
 qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_o, const __grid_constant__ CUtensorMap map_y, const GemmKParams p) {
   constexpr bool SPLIT = MIX != 0 && CG == 2;
@@ -165,7 +171,7 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if constexpr (EPI == 2) {
     const QvQParams yq = qv_load_qparams(p.ep_scale, p.ep_zp, p.ep_qmin, p.ep_qmax);
     const int ncodes = p.ep_qmax - p.ep_qmin + 1;
-    for (int k = threadIdx.x; k < ncodes + 2 && k < 260; k += NUM_THREADS) {
+    for (int k = threadIdx.x; k < ncodes + 2 && k < 260; k += num_threads(EPI)) {
       float v = 0.f;
       if (k >= 1 && k <= ncodes)
         v = p.ep_gelu ? qv_gelu_grad(__fmul_rn(__fsub_rn(static_cast<float>(p.ep_qmin + k - 1), yq.zp), yq.scale)) : 1.0f;
@@ -184,7 +190,7 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
-      mbar_init(&tmem_empty[b], 256 * CG);          // every epilogue thread of the pair arrives on the leader's barrier
+      mbar_init(&tmem_empty[b], epi_warps(EPI) * 32 * CG);   // every epilogue thread of the pair arrives on the leader's barrier
     }
     if constexpr (EPI == 2) {
       prefetch_tensormap(&map_y);
@@ -290,24 +296,38 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-#ifdef QV_GEMM_UNIFORM_ISSUE
+#ifndef QV_GEMM_SINGLE_LANE_ISSUE
     // =============================== MMA issuer ===============================
     // The whole warp walks the tile / k-block schedule (barrier waits included) and ONE elected lane issues the MMAs and
     // commits.  With warp-uniform control flow and descriptors formed as "stage base + compile-time offset", ptxas keeps the
-    // operands in uniform registers; under an `if (lane == 0)` region every tcgen05.mma paid an R2UR + ELECT waterfall loop
-    // (~90 cycles of issue per instruction -- as long as a 128 x 192 x 16 MMA takes to execute).
-    {
-      static_assert(!MIX && CG == 1, "the mixed operand format and CTA pairs are issued by the single-lane issuer only");
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+    // operands in uniform registers: ~4 instructions per tcgen05.mma.  Under an `if (lane == 0)` region every MMA costs ~21
+    // (descriptor arithmetic in vector registers + an ELECT / 5 x R2UR waterfall loop): ~210 instructions per k-block on ONE
+    // thread, as long as the k-block's 8 MMAs take to execute -- and that thread shares its scheduler with the epilogue warps of
+    // TMEM lane quarter 1, so a heavy epilogue (GELU + operand split) slows the MMA stream itself (timeline: the issuing thread's
+    // busy time grows from 212 to 279 us on the teacher's fc1 when the epilogue changes from fp32 to GELU + mixed planes, while it
+    // waits for tmem_empty only 1 %).
+    if (rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN, A_MN, B_MN);
       constexpr uint32_t a_lbo = A_MN ? 8192u : 16u, b_lbo = B_MN ? 8192u : 16u;
       constexpr uint32_t a_kadv = A_MN ? (UMMA_K * 128u) : (UMMA_K * 2u);   // bytes per 16-deep k step
       constexpr uint32_t b_kadv = B_MN ? (UMMA_K * 128u) : (UMMA_K * 2u);
-      const uint64_t desc_a0 = umma_smem_desc(smem_u32(smem), a_lbo, 1024u);                          // stage 0, plane 0
-      const uint64_t desc_b0 = umma_smem_desc(smem_u32(smem) + NA * A_PLANE_BYTES, b_lbo, 1024u);
+      auto mma16 = [](uint32_t d, uint64_t da, uint64_t db, uint32_t id, uint32_t acc) {
+        if constexpr (CG == 2) umma_bf16_pair(d, da, db, id, acc); else umma_bf16(d, da, db, id, acc);
+      };
+      auto mma8 = [](uint32_t d, uint64_t da, uint64_t db, uint32_t id, uint32_t acc) {
+        if constexpr (CG == 2) umma_f8_pair(d, da, db, id, acc); else umma_f8(d, da, db, id, acc);
+      };
+      auto commit = [](uint64_t* bar) {
+        if constexpr (CG == 2) umma_commit_pair(bar); else umma_commit(bar);
+      };
+      // descriptors of stage 0 (low 14 bits of the 64-bit descriptor = byte address >> 4: a stage / plane / k step is an ADD)
+      const uint64_t dA0 = umma_smem_desc(smem_u32(smem), a_lbo, 1024u);
+      const uint64_t dB0 = umma_smem_desc(smem_u32(smem), b_lbo, 1024u);
+      const uint64_t dK0 = umma_smem_desc(smem_u32(smem), 16u, 1024u);       // K-major (mixed / split paths)
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
+      for (int item = item0; item < num_items; item += item_step, ++local) {
         const int z = p.nbatch > 1 ? 0 : item / (p.tiles_n * p.tiles_m);
         const int kb0 = z * p.kb_per_split;
         const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
@@ -319,37 +339,79 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t sa = desc_a0 + static_cast<uint64_t>(stage) * (C::STAGE_BYTES >> 4);
-          const uint64_t sb = desc_b0 + static_cast<uint64_t>(stage) * (C::STAGE_BYTES >> 4);
+          const uint64_t so = static_cast<uint64_t>(static_cast<uint32_t>(stage) * static_cast<uint32_t>(C::STAGE_BYTES >> 4));
           const uint32_t first = (kb > kb0) ? 1u : 0u;
-          if (elect_one()) {
+          if constexpr (SPLIT) {
+            // stage = fp16 region: the main product; next stage = fp8 region: the two cross terms
+            constexpr uint32_t idesc16 = umma_idesc_f16(BM * CG, BN);
+            constexpr uint32_t idesc_hl = umma_idesc_f8(BM * CG, BN, 1u, 1u);
+            constexpr uint32_t idesc_lh = umma_idesc_f8(BM * CG, BN, 1u, 0u);
+            if (elect_one()) {
+              const uint64_t da = dK0 + so, db = da + (A_PLANE_BYTES >> 4);
 #pragma unroll
-            for (int pr = 0; pr < C::NPAIRS; ++pr) {
-              // pair order: (0,0) [,(0,1)] [,(1,0)]  -- for NB == 1 the second pair is (1,0)
-              const int pa = (NB == 1) ? pr : (pr == 2 ? 1 : 0);
-              const int pb = (NB == 1) ? 0 : (pr == 1 ? 1 : 0);
-#pragma unroll
-              for (int k = 0; k < BK / UMMA_K; ++k) {
-                const uint64_t da = sa + ((pa * A_PLANE_BYTES + k * a_kadv) >> 4);
-                const uint64_t db = sb + ((pb * C::B_PLANE_BYTES + k * b_kadv) >> 4);
-                umma_bf16(d_tmem, da, db, idesc, (pr > 0 || k > 0) ? 1u : first);
-              }
+              for (int k = 0; k < BK / UMMA_K; ++k) mma16(d_tmem, da + 2 * k, db + 2 * k, idesc16, k > 0 ? 1u : first);
+              commit(&empty_bar[stage]);
             }
-            umma_commit(&empty_bar[stage]);     // frees this smem stage once the MMAs have read it
+            __syncwarp();
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint64_t so8 = static_cast<uint64_t>(static_cast<uint32_t>(stage) * static_cast<uint32_t>(C::STAGE_BYTES >> 4));
+            if (elect_one()) {
+              const uint64_t da = dK0 + so8, db = da + (A_PLANE_BYTES >> 4);
+#pragma unroll
+              for (int k = 0; k < 2; ++k) mma8(d_tmem, da + 2 * k, db + 4 + 2 * k, idesc_hl, 1u);          // A hi8 x B lo8 (64 bytes on)
+#pragma unroll
+              for (int k = 0; k < 2; ++k) mma8(d_tmem, da + 4 + 2 * k, db + 2 * k, idesc_lh, 1u);          // A lo8 x B hi8
+              commit(&empty_bar[stage]);
+            }
+            __syncwarp();
+          } else if constexpr (MIX) {
+            constexpr uint32_t idesc16 = umma_idesc_f16(BM * CG, BN);
+            constexpr uint32_t idesc_hl = umma_idesc_f8(BM * CG, BN, 1u, 1u);    // A hi8 e5m2 x B lo8 e5m2
+            constexpr uint32_t idesc_lh = umma_idesc_f8(BM * CG, BN, 1u, 0u);    // A lo8 e5m2 x B hi8 e4m3
+            if (elect_one()) {
+              const uint64_t da = dK0 + so, db = da + ((NA * A_PLANE_BYTES) >> 4);
+              const uint64_t da8 = da + (A_PLANE_BYTES >> 4), db8 = db + (C::B_PLANE_BYTES >> 4);
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k) mma16(d_tmem, da + 2 * k, db + 2 * k, idesc16, k > 0 ? 1u : first);
+#pragma unroll
+              for (int k = 0; k < 2; ++k) mma8(d_tmem, da8 + 2 * k, db8 + 4 + 2 * k, idesc_hl, 1u);
+#pragma unroll
+              for (int k = 0; k < 2; ++k) mma8(d_tmem, da8 + 4 + 2 * k, db8 + 2 * k, idesc_lh, 1u);
+              commit(&empty_bar[stage]);     // frees this smem stage (in both CTAs of a pair) once the MMAs have read it
+            }
+            __syncwarp();
+          } else {
+            if (elect_one()) {
+              const uint64_t sa = dA0 + so, sb = dB0 + so + ((NA * A_PLANE_BYTES) >> 4);
+#pragma unroll
+              for (int pr = 0; pr < C::NPAIRS; ++pr) {
+                // pair order: (0,0) [,(0,1)] [,(1,0)]  -- for NB == 1 the second pair is (1,0)
+                const int pa = (NB == 1) ? pr : (pr == 2 ? 1 : 0);
+                const int pb = (NB == 1) ? 0 : (pr == 1 ? 1 : 0);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                  const uint64_t da = sa + ((pa * A_PLANE_BYTES + k * a_kadv) >> 4);
+                  const uint64_t db = sb + ((pb * C::B_PLANE_BYTES + k * b_kadv) >> 4);
+                  mma16(d_tmem, da, db, idesc, (pr > 0 || k > 0) ? 1u : first);
+                }
+              }
+              commit(&empty_bar[stage]);
+            }
+            __syncwarp();
           }
-          __syncwarp();
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        if (elect_one()) umma_commit(&tmem_full[buf]);   // accumulator complete -> epilogue
+        if (elect_one()) commit(&tmem_full[buf]);        // accumulator complete -> epilogue (of both CTAs of a pair)
         __syncwarp();
       }
     }
 #else
-    // =============================== MMA issuer ===============================
-    // (A whole-warp walk with an elected issuing lane -- which keeps operands in uniform registers and removed a per-MMA
-    // R2UR/ELECT waterfall in the attention kernels, where N = 64 instructions are issue-bound -- measured 3-4 % SLOWER here:
-    // a 128 x 192 x 16 MMA executes for as long as its issue sequence takes, and 32 polling lanes steal issue slots from the
-    // two epilogue warps sharing the sub-partition.)
+    // =============================== MMA issuer (A/B build: make alt) ===============================
+    // One thread walks the schedule and issues: the default until round 2.  Every tcgen05.mma then pays descriptor arithmetic in
+    // vector registers + an ELECT / R2UR waterfall (~21 instructions); measured against the warp-uniform issuer above on the teacher
+    // shapes: fc1 + GELU + mixed planes 451 vs 425 us, fp32 output 378 vs 367 us (profiles/r02_summary.md).
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN, A_MN, B_MN);
       constexpr uint32_t a_lbo = A_MN ? 8192u : 16u, b_lbo = B_MN ? 8192u : 16u;
@@ -628,13 +690,139 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       }
       if (lane == 0) tma_store_wait_read<0>();
+    } else if constexpr (EPI == 1) {
+    // ---- plane output (the next GEMM's operand), 16 warps: warp (q, par) takes the 32-column chunks ch = par, par + 4, ... of its
+    // TMEM lane quarter.  Per chunk: tcgen05.ld (the next chunk's load already in flight) -> bias [-> GELU] -> operand split ->
+    // 64B-swizzled staging -> TMA stores (hi / lo plane, or fp16 region + the block's hi8 and lo8 byte runs).
+    constexpr int NCHUNK = BN / 32;
+    static_assert(NCHUNK >= 4, "every one of the four warps of a lane quarter needs a chunk (it arrives on tmem_empty once per tile)");
+    const int par4 = ew >> 2;
+    uint8_t* my_epi = smem_epi + ew * EPI_WARP_BYTES;
+    __half2 amax2 = __floats2half2_rn(0.f, 0.f);  // mixed plane output: largest |fp16 image| (value x 2^7) this thread has written
+    int local = 0;
+#ifdef QV_ATTN_DEBUG
+    int gdbg_n = (threadIdx.x == 64) ? 0 : 4096;
+#endif
+    for (int item = item0; item < num_items; item += item_step, ++local) {
+      const int n_blk = item % p.tiles_n;
+      const int m_blk = m_of(item);
+      const int outer = item / (p.tiles_n * p.tiles_m);
+      const int bt = p.nbatch > 1 ? outer : 0;
+      const int bo = bt / p.batch_inner, bi = bt % p.batch_inner;
+      const int o_c2 = bo * p.o_c2_outer + bi * p.o_c2_inner;
+      const int o_col = p.o_col0 + bi * p.o_col_inner;
+      const int buf = local & 1;
+      const uint32_t use = static_cast<uint32_t>(local >> 1);
+      GDBG(2, 20);
+      mbar_wait(&tmem_full[buf], use & 1);
+      GDBG(2, 21);
+      tc_fence_after();
+      const int row0 = m_blk * BM + q * 32;
+      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN);
+      uint32_t rr[32], nxt[32];
+      tmem_ld_cols<32>(t_base + par4 * 32, nxt);
+#pragma unroll 1
+      for (int ch = par4; ch < NCHUNK; ch += 4) {
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) rr[j] = nxt[j];
+        if (ch + 4 < NCHUNK) {
+          tmem_ld_cols<32>(t_base + (ch + 4) * 32, nxt);
+        } else {                                                // this warp's last chunk is in registers
+          tc_fence_before();
+          tmem_empty_arrive(buf);
+          GDBG(2, 22);
+        }
+        const int64_t n0 = static_cast<int64_t>(n_blk) * BN + ch * 32;
+        if (n0 >= p.N || static_cast<int64_t>(row0) >= p.M) continue;      // warp-uniform: nothing to store
+        if (lane == 0) tma_store_wait_read<0>();                // this warp's previous stores have read the staging buffer
+        __syncwarp();
+        const uint32_t srow0 = smem_u32(my_epi) + lane * 64;    // region 0 / hi plane: 32 rows x 64 bytes, 64B swizzle
+        const uint32_t swz = static_cast<uint32_t>((lane >> 1) & 3);
+        uint32_t h8w[8], l8w[8];                                // mixed: this row's 32 hi8 / lo8 bytes
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {                           // 8 columns per step
+          // plane output takes bias only (checked on the host); every lane reads the same 32 bytes: broadcast LDG.128
+          float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba;
+          if (p.bias) {
+            ba = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 8 * j));
+            bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 8 * j + 4));
+          }
+          const float as = p.acc_scale;
+          float a[8] = {__uint_as_float(rr[8 * j]) * as + ba.x,     __uint_as_float(rr[8 * j + 1]) * as + ba.y,
+                        __uint_as_float(rr[8 * j + 2]) * as + ba.z, __uint_as_float(rr[8 * j + 3]) * as + ba.w,
+                        __uint_as_float(rr[8 * j + 4]) * as + bb.x, __uint_as_float(rr[8 * j + 5]) * as + bb.y,
+                        __uint_as_float(rr[8 * j + 6]) * as + bb.z, __uint_as_float(rr[8 * j + 7]) * as + bb.w};
+          const uint32_t sw = (static_cast<uint32_t>(j) ^ swz) << 4;
+          if (p.out_fmt == 1) {                                 // mixed planes: the next GEMM's fp16 + fp8 operand
+            uint32_t h16[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const uint64_t x2 = qv2_pack(a[2 * e], a[2 * e + 1]);
+              const uint64_t s2 = (p.act == 1) ? qv_gelu128_pair(x2) : qv2_mul(x2, qv2_pack(QV_MIX_SCALE, QV_MIX_SCALE));
+              uint32_t ph, pl;
+              h16[e] = qv_mix_split2_scaled<QV_MIX_ACT>(s2, ph, pl);
+              const __half2 ah = __habs2(*reinterpret_cast<const __half2*>(&h16[e]));      // range guard on the fp16 image (x 2^7)
+              amax2 = __hmax2(amax2, ah);
+              if (e & 1) { h8w[2 * j + (e >> 1)] |= ph << 16; l8w[2 * j + (e >> 1)] |= pl << 16; }
+              else { h8w[2 * j + (e >> 1)] = ph; l8w[2 * j + (e >> 1)] = pl; }
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow0 + sw), "r"(h16[0]), "r"(h16[1]), "r"(h16[2]), "r"(h16[3]) : "memory");
+            continue;
+          }
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float a0 = a[2 * e], a1 = a[2 * e + 1];
+            if (p.act == 1) { a0 = gelu_erf(a0); a1 = gelu_erf(a1); }
+            // packed split: one F2FP for the hi pair, exact residuals, one F2FP for the lo pair
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(a0, a1);
+            const uint32_t hbits = *reinterpret_cast<const uint32_t*>(&h2);
+            const float r0 = a0 - __uint_as_float(hbits << 16), r1 = a1 - __uint_as_float(hbits & 0xffff0000u);
+            const __nv_bfloat162 l2 = __floats2bfloat162_rn(r0, r1);
+            hi[e] = hbits;
+            lo[e] = *reinterpret_cast<const uint32_t*>(&l2);
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow0 + sw), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow0 + 2048 + sw), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+        }
+        if (p.out_fmt == 1) {
+          // region 1 of this 64-column block is one 128-byte line per row = 64 hi8 | 64 lo8; this chunk is its half (ch & 1):
+          // two 32-row x 32-byte tiles (linear), stored as 16-element boxes of the bf16-typed tensor
+          const uint32_t r1 = smem_u32(my_epi) + 2048 + lane * 32;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(r1), "r"(h8w[0]), "r"(h8w[1]), "r"(h8w[2]), "r"(h8w[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(r1 + 16), "r"(h8w[4]), "r"(h8w[5]), "r"(h8w[6]), "r"(h8w[7]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(r1 + 1024), "r"(l8w[0]), "r"(l8w[1]), "r"(l8w[2]), "r"(l8w[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(r1 + 1040), "r"(l8w[4]), "r"(l8w[5]), "r"(l8w[6]), "r"(l8w[7]) : "memory");
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          const int c = o_col + static_cast<int>(n0);
+          tma_store_4d(&map_o, my_epi, c, row0, o_c2, 0);
+          if (p.out_fmt == 1) {
+            const int blk = c & ~63, half = (c >> 5) & 1;
+            tma_store_4d(&map_y, my_epi + 2048, blk + 16 * half, row0, o_c2, 1);
+            tma_store_4d(&map_y, my_epi + 3072, blk + 32 + 16 * half, row0, o_c2, 1);
+          } else {
+            tma_store_4d(&map_o, my_epi + 2048, c, row0, o_c2, 1);
+          }
+          tma_store_commit();
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait_read<0>();
+    {
+      // the fp16 image saturates at 65504 >= 448 * 2^7 = 57344, so a clamped value still trips the guard
+      const float amax = fmaxf(__low2float(amax2), __high2float(amax2)) * (1.0f / QV_MIX_SCALE);
+      if (p.sat_flag && __any_sync(0xffffffffu, amax > QV_MIX_ACT_MAX) && lane == 0) atomicOr(p.sat_flag, p.sat_bit);
+    }
     } else {
-    constexpr int CW = (EPI == 1) ? 64 : 32;     // columns per chunk (one 128-byte row of fp32 / of each bf16 plane)
+    constexpr int CW = 32;                       // EPI 0: columns per chunk (one 128-byte row of fp32)
     constexpr int NCHUNK = BN / CW;
     uint8_t* my_epi = smem_epi + ew * EPI_WARP_BYTES;
     float* my_terms = reinterpret_cast<float*>(smem_epi + 8 * EPI_WARP_BYTES) + ew * 64;   // EPI 0: [mult 32][bias 32]
     float mn = INFINITY, mx = -INFINITY;
-    float amax = 0.f;                            // mixed plane output: largest |value| this thread has written
     const float alpha = p.alpha ? __ldg(p.alpha) : 1.0f;
     const bool raw = p.splits > 1;
     int local = 0;
@@ -725,76 +913,10 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tma_store_3d(&map_o, my_epi, o_col + static_cast<int>(n0), row0, o_c2);
             tma_store_commit();
           }
-        } else {
-          // bf16 hi/lo plane output: 64 columns -> one 32-row x 128-byte hi box and one lo box
-          const uint32_t srow_hi = smem_u32(my_epi) + lane * 128, srow_lo = srow_hi + 4096;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            // plane output takes bias only (checked on the host); every lane reads the same 32 bytes: broadcast LDG.128
-            float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba;
-            if (p.bias) {
-              ba = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 8 * j));
-              bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 8 * j + 4));
-            }
-            const float as = p.acc_scale;
-            float a[8] = {__uint_as_float(rr[8 * j]) * as + ba.x,     __uint_as_float(rr[8 * j + 1]) * as + ba.y,
-                          __uint_as_float(rr[8 * j + 2]) * as + ba.z, __uint_as_float(rr[8 * j + 3]) * as + ba.w,
-                          __uint_as_float(rr[8 * j + 4]) * as + bb.x, __uint_as_float(rr[8 * j + 5]) * as + bb.y,
-                          __uint_as_float(rr[8 * j + 6]) * as + bb.z, __uint_as_float(rr[8 * j + 7]) * as + bb.w};
-            if (p.out_fmt == 1) {                                 // mixed planes: the next GEMM's fp16 + fp8 operand
-              uint32_t h16[4], h8[2], l8[2];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float a0 = a[2 * e], a1 = a[2 * e + 1];
-                if (p.act == 1) { a0 = qv_gelu_fast(a0); a1 = qv_gelu_fast(a1); }
-                amax = fmaxf(amax, fmaxf(fabsf(a0), fabsf(a1)));
-                uint32_t ph, pl;
-                h16[e] = qv_mix_split2<QV_MIX_ACT>(a0, a1, ph, pl);
-                if (e & 1) { h8[e >> 1] |= ph << 16; l8[e >> 1] |= pl << 16; }
-                else { h8[e >> 1] = ph; l8[e >> 1] = pl; }
-              }
-              const uint32_t swz = static_cast<uint32_t>(lane & 7);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow_hi + ((static_cast<uint32_t>(j) ^ swz) << 4)),
-                           "r"(h16[0]), "r"(h16[1]), "r"(h16[2]), "r"(h16[3]) : "memory");
-              // region 1 row: bytes [0, 64) = hi8 of the 64 columns, [64, 128) = lo8; 8 columns = 8 bytes at 8 j
-              const uint32_t c8 = static_cast<uint32_t>(j >> 1), o8 = static_cast<uint32_t>(j & 1) << 3;
-              asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(srow_lo + ((c8 ^ swz) << 4) + o8), "r"(h8[0]), "r"(h8[1]) : "memory");
-              asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(srow_lo + (((c8 + 4u) ^ swz) << 4) + o8), "r"(l8[0]), "r"(l8[1]) : "memory");
-              continue;
-            }
-            uint32_t hi[4], lo[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float a0 = a[2 * e], a1 = a[2 * e + 1];
-              if (p.act == 1) { a0 = gelu_erf(a0); a1 = gelu_erf(a1); }
-              // packed split: one F2FP for the hi pair, exact residuals, one F2FP for the lo pair
-              const __nv_bfloat162 h2 = __floats2bfloat162_rn(a0, a1);
-              const uint32_t hbits = *reinterpret_cast<const uint32_t*>(&h2);
-              const float r0 = a0 - __uint_as_float(hbits << 16), r1 = a1 - __uint_as_float(hbits & 0xffff0000u);
-              const __nv_bfloat162 l2 = __floats2bfloat162_rn(r0, r1);
-              hi[e] = hbits;
-              lo[e] = *reinterpret_cast<const uint32_t*>(&l2);
-            }
-            const uint32_t sw = (static_cast<uint32_t>(j ^ (lane & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow_hi + sw), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]),
-                         "r"(hi[3]) : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow_lo + sw), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]),
-                         "r"(lo[3]) : "memory");
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_4d(&map_o, my_epi, o_col + static_cast<int>(n0), row0, o_c2, 0);
-            tma_store_4d(&map_o, my_epi + 4096, o_col + static_cast<int>(n0), row0, o_c2, 1);
-            tma_store_commit();
-          }
         }
       }
     }
     if (lane == 0) tma_store_wait_read<0>();
-    if constexpr (EPI == 1) {
-      if (p.sat_flag && __any_sync(0xffffffffu, amax > QV_MIX_ACT_MAX) && lane == 0) atomicOr(p.sat_flag, p.sat_bit);
-    }
     if (p.minmax && !raw) {
       mn = qv_warp_min(mn);
       mx = qv_warp_max(mx);
@@ -868,7 +990,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, 
   if constexpr (CG == 2) {       // CTA pairs: clusters of two CTAs (the two SMs of a TPC)
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(static_cast<unsigned>(grid), 1, 1);
-    cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+    cfg.blockDim = dim3(num_threads(EPI), 1, 1);
     cfg.dynamicSmemBytes = C::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -882,7 +1004,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, 
     QV_REQUIRE(e == cudaSuccess, QV_ERR_CUDA, "cudaLaunchKernelEx(cluster 2): %s", cudaGetErrorString(e));
     g_pair_launches.fetch_add(1, std::memory_order_relaxed);
   } else {
-    qv_gemm_kernel<BN, NA, NB, A_MN, B_MN, EPI, MIX, CG><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mb, mo, my ? *my : mo, kp);
+    qv_gemm_kernel<BN, NA, NB, A_MN, B_MN, EPI, MIX, CG><<<grid, num_threads(EPI), C::SMEM_BYTES, st>>>(ma, mb, mo, my ? *my : mo, kp);
   }
   return qv_check_launch("qv_gemm_bf16");
 }
@@ -1002,9 +1124,12 @@ extern "C" int qv_gemm_bf16(const qv_gemm_args* a, void* stream) {
       if (rc) return rc;
       // the raw y tile comes in through the fp32 store-map geometry used as a load map: box = 32 cols x 32 rows, 128B swizzle
       rc = make_out_map(&my, const_cast<float*>(a->ep_raw), a->N, a->M, a->ep_raw_ld, 1, 0);
-    } else if (planes_out)
-      rc = make_out_planes_map(&mo, o.ptr, o.cols, o.rows, o.ld, o.nb, o.batch_stride, a->out_plane_stride);
-    else
+    } else if (planes_out) {
+      rc = make_out_planes_map(&mo, o.ptr, o.cols, o.rows, o.ld, o.nb, o.batch_stride, a->out_plane_stride, 32);
+      if (rc) return rc;
+      // mixed planes: region 1 leaves as 32-byte runs (a 32-column chunk's hi8 / lo8 bytes) = 16-element boxes of the bf16-typed tensor
+      rc = make_out_planes_map(&my, o.ptr, o.cols, o.rows, o.ld, o.nb, o.batch_stride, a->out_plane_stride, 16);
+    } else
       rc = make_out_map(&mo, o.ptr, o.cols, o.rows, o.ld, o.nb, o.batch_stride);
   }
   if (rc) return rc;
@@ -1062,10 +1187,10 @@ extern "C" int qv_gemm_bf16(const qv_gemm_args* a, void* stream) {
   }
   if (mix) {
     if (planes_out) {
-      if (pair && BN == 256) return launch<256, 2, 2, false, false, 1, 1, 2>(ma, mb, mo, kp, grid, st);
-      if (pair) return launch<192, 2, 2, false, false, 1, 1, 2>(ma, mb, mo, kp, grid, st);
-      if (BN == 128) return launch<128, 2, 2, false, false, 1, 1>(ma, mb, mo, kp, grid, st);
-      return launch<192, 2, 2, false, false, 1, 1>(ma, mb, mo, kp, grid, st);
+      if (pair && BN == 256) return launch<256, 2, 2, false, false, 1, 1, 2>(ma, mb, mo, kp, grid, st, &my);
+      if (pair) return launch<192, 2, 2, false, false, 1, 1, 2>(ma, mb, mo, kp, grid, st, &my);
+      if (BN == 128) return launch<128, 2, 2, false, false, 1, 1>(ma, mb, mo, kp, grid, st, &my);
+      return launch<192, 2, 2, false, false, 1, 1>(ma, mb, mo, kp, grid, st, &my);
     }
     if (pair && BN == 256) return launch<256, 2, 2, false, false, 0, 1, 2>(ma, mb, mo, kp, grid, st);
     if (pair) return launch<192, 2, 2, false, false, 0, 1, 2>(ma, mb, mo, kp, grid, st);
@@ -1075,17 +1200,17 @@ extern "C" int qv_gemm_bf16(const qv_gemm_args* a, void* stream) {
   }
   if (planes_out) {
     if (a->a_planes == 1) {      // single-pass (half-precision, pre-QAT --amp variant) GEMM whose output is the next operand
-      if (BN == 128) return launch<128, 1, 1, false, false, 1>(ma, mb, mo, kp, grid, st);
-      return launch<192, 1, 1, false, false, 1>(ma, mb, mo, kp, grid, st);
+      if (BN == 128) return launch<128, 1, 1, false, false, 1>(ma, mb, mo, kp, grid, st, &my);
+      return launch<192, 1, 1, false, false, 1>(ma, mb, mo, kp, grid, st, &my);
     }
     if (a->b_planes == 1) {
-      if (pair) return launch<192, 2, 1, false, false, 1, 0, 2>(ma, mb, mo, kp, grid, st);
-      if (BN == 128) return launch<128, 2, 1, false, false, 1>(ma, mb, mo, kp, grid, st);
-      return launch<192, 2, 1, false, false, 1>(ma, mb, mo, kp, grid, st);
+      if (pair) return launch<192, 2, 1, false, false, 1, 0, 2>(ma, mb, mo, kp, grid, st, &my);
+      if (BN == 128) return launch<128, 2, 1, false, false, 1>(ma, mb, mo, kp, grid, st, &my);
+      return launch<192, 2, 1, false, false, 1>(ma, mb, mo, kp, grid, st, &my);
     }
-    if (pair) return launch<192, 2, 2, false, false, 1, 0, 2>(ma, mb, mo, kp, grid, st);
-    if (BN == 128) return launch<128, 2, 2, false, false, 1>(ma, mb, mo, kp, grid, st);
-    return launch<192, 2, 2, false, false, 1>(ma, mb, mo, kp, grid, st);
+    if (pair) return launch<192, 2, 2, false, false, 1, 0, 2>(ma, mb, mo, kp, grid, st, &my);
+    if (BN == 128) return launch<128, 2, 2, false, false, 1>(ma, mb, mo, kp, grid, st, &my);
+    return launch<192, 2, 2, false, false, 1>(ma, mb, mo, kp, grid, st, &my);
   }
   if (pair) {
     if (a->b_planes == 1) return launch<192, 2, 1, false, false, 0, 0, 2>(ma, mb, mo, kp, grid, st);

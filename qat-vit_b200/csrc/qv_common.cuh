@@ -155,6 +155,67 @@ __device__ __forceinline__ float qv_gelu_fast(float x) {
   return x * (x >= 0.f ? 1.0f - half_erfc : half_erfc);
 }
 
+// ---- the same GELU + mixed-format split on PAIRS, for the teacher's fc1 epilogue (gemm_sm100.cu, EPI 1, out_fmt 1) ----
+// The epilogue warps of that kernel are bound by the FP32 pipe's issue rate (~25 instructions per element against a 12-k-block
+// tile of MMAs), so the pair form uses packed fma / mul (one issue slot for two elements), folds every constant factor (the
+// format's x 128, the 1/2 of erfc / 2, |x| = |z| / c) into the polynomial's coefficients, takes gelu = relu(x) - |x| erfc / 2
+// (no compare / select / 1 - ...), and forms the fp16 rounding residual with ONE mixed-precision fma per element.
+__device__ __forceinline__ uint64_t qv2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void qv2_unpack(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t qv2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t qv2_mul(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// (x0, x1) -> 2^7 * gelu(x0), 2^7 * gelu(x1)  (same approximation as qv_gelu_fast: Abramowitz-Stegun 7.1.26, MUFU rcp / ex2)
+__device__ __forceinline__ uint64_t qv_gelu128_pair(uint64_t x2) {
+  constexpr float C = 0.8493218002880191f;            // sqrt(log2 e) / sqrt 2:  (C x)^2 = x^2 log2(e) / 2
+  constexpr float P = 0.3275911f / 1.2011224087864498f;
+  constexpr float K = -64.0f / C;                     // - 2^7 / 2 / C: the polynomial then yields -2^7 |x| erfc(|x| / sqrt 2) / 2 per |z|
+  float x0, x1, z0, z1, e0, e1, d0, d1, t0, t1;
+  qv2_unpack(x2, x0, x1);
+  const uint64_t z2 = qv2_mul(x2, qv2_pack(C, C));
+  const uint64_t zz2 = qv2_mul(z2, z2);
+  qv2_unpack(z2, z0, z1);
+  qv2_unpack(zz2, e0, e1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(-e0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(-e1));
+  const uint64_t az2 = qv2_pack(fabsf(z0), fabsf(z1));
+  qv2_unpack(qv2_fma(az2, qv2_pack(P, P), qv2_pack(1.0f, 1.0f)), d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  const uint64_t t2 = qv2_pack(t0, t1);
+  uint64_t pl = qv2_fma(qv2_pack(K * 1.061405429f, K * 1.061405429f), t2, qv2_pack(K * -1.453152027f, K * -1.453152027f));
+  pl = qv2_fma(pl, t2, qv2_pack(K * 1.421413741f, K * 1.421413741f));
+  pl = qv2_fma(pl, t2, qv2_pack(K * -0.284496736f, K * -0.284496736f));
+  pl = qv2_fma(pl, t2, qv2_pack(K * 0.254829592f, K * 0.254829592f));
+  const uint64_t u2 = qv2_mul(qv2_mul(qv2_mul(pl, t2), qv2_pack(e0, e1)), az2);      // - 2^7 |x| erfc / 2
+  return qv2_fma(qv2_pack(fmaxf(x0, 0.f), fmaxf(x1, 0.f)), qv2_pack(QV_MIX_SCALE, QV_MIX_SCALE), u2);
+}
+// split of an ALREADY SCALED pair (s = x * 2^7): packed fp16 pair returned, ph / pl = packed hi8 / lo8 pairs (element 0 low byte)
+template <int KIND>
+__device__ __forceinline__ uint32_t qv_mix_split2_scaled(uint64_t s2, uint32_t& ph, uint32_t& pl) {
+  float s0, s1, r0, r1;
+  qv2_unpack(s2, s0, s1);
+  uint32_t h;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(s1), "f"(s0));
+  const unsigned short h0 = static_cast<unsigned short>(h & 0xffffu), h1 = static_cast<unsigned short>(h >> 16), m1 = 0xBC00;   // -1.0
+  asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(r0) : "h"(h0), "h"(m1), "f"(s0));      // s - fp16(s), exact
+  asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(r1) : "h"(h1), "h"(m1), "f"(s1));
+  ph = __nv_cvt_float2_to_fp8x2(make_float2(s0, s1), __NV_SATFINITE, KIND == QV_MIX_ACT ? __NV_E5M2 : __NV_E4M3);
+  pl = __nv_cvt_float2_to_fp8x2(make_float2(r0, r1), __NV_SATFINITE, __NV_E5M2);
+  return h;
+}
+
 __device__ __forceinline__ float qv_warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

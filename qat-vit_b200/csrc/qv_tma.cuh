@@ -76,7 +76,8 @@ inline int make_out_map(CUtensorMap* m, float* ptr, int64_t cols, int64_t rows, 
 }
 
 // bf16 hi/lo plane output [2][nb][rows][ld] as a 4-D tensor (cols, rows, nb, plane); store box = (64 cols = 128 B, 32 rows).
-// box_cols = 32: 64-byte rows, 64B swizzle (the gradient-planes epilogue works in 32-column units).
+// box_cols = 32: 64-byte rows, 64B swizzle (the plane-output and gradient-planes epilogues work in 32-column units);
+// box_cols = 16: 32-byte rows, no swizzle (the hi8 / lo8 byte runs of the mixed format's region 1).
 inline int make_out_planes_map(CUtensorMap* m, void* ptr, int64_t cols, int64_t rows, int64_t ld, int64_t nb, int64_t bstride,
                         int64_t pstride, int box_cols = 64) {
   EncodeTiledFn enc = get_encode();
@@ -94,8 +95,8 @@ inline int make_out_planes_map(CUtensorMap* m, void* ptr, int64_t cols, int64_t 
   cuuint32_t box[4] = {static_cast<cuuint32_t>(box_cols), 32, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   box_cols == 16 ? CU_TENSOR_MAP_SWIZZLE_NONE : box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   QV_REQUIRE(r == CUDA_SUCCESS, QV_ERR_CUDA, "cuTensorMapEncodeTiled(plane output) failed (%d)", (int)r);
   return 0;
 }
