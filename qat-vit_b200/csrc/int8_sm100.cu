@@ -137,8 +137,11 @@ qv_int8_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // whole warp walks the schedule, one elected lane issues: descriptors stay in uniform registers (a 128 x BN x 32 int8 MMA
+    // executes in ~64 clk, far less than the ~21-instruction ELECT / R2UR sequence a single issuing thread pays per MMA)
+    {
       constexpr uint32_t idesc = umma_idesc_u8s8(I8_BM, BN);
+      const uint64_t d0 = umma_smem_desc(smem_u32(smem), 16u, 1024u);
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
@@ -150,18 +153,18 @@ qv_int8_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         for (int kb = 0; kb < p.kblocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
-          const uint32_t sb = sa + I8_A_BYTES;
+          if (elect_one()) {
+            const uint64_t da = d0 + static_cast<uint64_t>(static_cast<uint32_t>(stage) * static_cast<uint32_t>(C::STAGE_BYTES >> 4));
+            const uint64_t db = da + (I8_A_BYTES >> 4);
 #pragma unroll
-          for (int k = 0; k < I8_BK / I8_UMMA_K; ++k) {
-            const uint64_t da = umma_smem_desc(sa + k * I8_UMMA_K, 16u, 1024u);
-            const uint64_t db = umma_smem_desc(sb + k * I8_UMMA_K, 16u, 1024u);
-            umma_i8(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < I8_BK / I8_UMMA_K; ++k) umma_i8(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit(&empty_bar[stage]);
           }
-          umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[buf]);
+        if (elect_one()) umma_commit(&tmem_full[buf]);
+        __syncwarp();
       }
     }
   } else {
