@@ -50,10 +50,11 @@ constexpr int epi_terms_bytes(int epi) { return epi >= 1 ? 0 : 8 * 2 * 32 * 4; }
 constexpr int SMEM_LIMIT = 232448;             // 227 KB
 #ifndef QV_GEMM_PAIR_DEFAULT
 // bit 0: mixed-format (teacher) GEMMs with fp32 output, bit 4: ... with plane output, bit 1: (2,2) bf16 hi/lo plane GEMMs,
-// bit 2: gradient-planes dgrad, bit 3: (2,1) GEMMs, bit 5: 256-wide tiles for the mixed-format pairs.  (Tried and dropped: the producer prefetching
+// bit 2: gradient-planes dgrad, bit 3: every (2,1) GEMM, bit 5: 256-wide tiles for the mixed-format pairs, bit 6: the (2,1) GEMMs with
+// plane output or K >= 1024.  (Tried and dropped: the producer prefetching
 // the A tiles 6 k-blocks ahead into L2 with cp.async.bulk.prefetch.tensor -- isolated qkv 280 -> 305 us, fc2 353 -> 376 us.)
 // The (2,1) student GEMMs are MMA-bound with one CTA per tile already (56 KB per k-block against 8 MMAs) and gain nothing.
-#define QV_GEMM_PAIR_DEFAULT 51
+#define QV_GEMM_PAIR_DEFAULT 115
 #endif
 
 struct GemmKParams {
@@ -1098,7 +1099,11 @@ extern "C" int qv_gemm_bf16(const qv_gemm_args* a, void* stream) {
   const int sms_all = qv_num_sms();
   const bool pair = pair_mode() != 0 && BN == 192 && splits == 1 && nbatch == 1 && !a->a.mn_major && !a->b.mn_major &&
                     a->a_planes == 2 && (mix || planes_out || grad_epi || a->b_planes == 1 || a->b_planes == 2) &&
-                    a->M >= 256LL * (sms_all / 2) && (pair_mode() & (mix ? (planes_out ? 16 : 1) : grad_epi ? 4 : a->b_planes == 2 ? 2 : 8)) != 0;
+                    a->M >= 256LL * (sms_all / 2) &&
+                    ((pair_mode() & (mix ? (planes_out ? 16 : 1) : grad_epi ? 4 : a->b_planes == 2 ? 2 : 8)) != 0 ||
+                     // bit 6: the (2,1) student GEMMs that gain from pairing -- plane output (proj dgrad: 56 -> 46 us) and long K
+                     // (>= 16 k-blocks: 1-2 %); the K = 384 forward shapes lose 5-10 % as pairs (6 k-blocks per tile)
+                     ((pair_mode() & 64) != 0 && !mix && !grad_epi && a->b_planes == 1 && (planes_out || a->K >= 1024)));
   const int CGh = pair ? 2 : 1;
   // mixed-format pairs on 256-wide tiles (bit 5): 64 KB into each SM per k-block for 128 x 256 outputs (1 000 clk at 64 B/clk
   // against 1 024 clk of MMA), 4 / 8 epilogue chunks split evenly over the two warps of a lane quarter (192: 3 chunks, 2 + 1),
