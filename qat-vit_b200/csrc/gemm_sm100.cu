@@ -218,11 +218,15 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
-    if (lane == 0) {
+    // Like the MMA issuer below, the whole warp walks the schedule and ONE elected lane issues the loads: coordinates, shared-memory
+    // addresses and barrier addresses then live in uniform registers.  As a single thread (`if (lane == 0)`) every TMA instruction
+    // paid a vector-to-uniform waterfall, and the timeline showed the producer BUSY 87 % of a teacher GEMM while the MMA side waited
+    // for operands 21 % of it: the loads were late because their issue was slow, not because memory was.
+    {
       int stage = 0;
       uint32_t phase = 0;
 #ifdef QV_ATTN_DEBUG
-      int gdbg_n = 0;
+      int gdbg_n = (lane == 0) ? 0 : 4096;
 #endif
       for (int item = item0; item < num_items; item += item_step) {
         const int n_blk = item % p.tiles_n;
@@ -249,49 +253,58 @@ qv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 sa = smem + stage * C::STAGE_BYTES;
               }
-              if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
-              const uint32_t lead_bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
-              tma_load_4d_pair(sa, &map_a, lead_bar, a_col + kb * BK, m_blk * BM, a_c2, r);
-              tma_load_4d_pair(sa + A_PLANE_BYTES, &map_b, lead_bar, b_col + kb * BK, n_blk * BN + rank * (BN / 2), b_c2, r);
+              if (elect_one()) {
+                if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+                const uint32_t lead_bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+                tma_load_4d_pair(sa, &map_a, lead_bar, a_col + kb * BK, m_blk * BM, a_c2, r);
+                tma_load_4d_pair(sa + A_PLANE_BYTES, &map_b, lead_bar, b_col + kb * BK, n_blk * BN + rank * (BN / 2), b_c2, r);
+              }
+              __syncwarp();
               if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
             continue;
           } else if constexpr (CG == 2) {
-            // both CTAs' bytes complete on the leader's full barrier (its MMA thread is the only consumer)
-            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
-            const uint32_t lead_bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            // both CTAs' bytes complete on the leader's full barrier (its MMA warp is the only consumer)
+            if (elect_one()) {
+              if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+              const uint32_t lead_bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
 #pragma unroll
-            for (int pa = 0; pa < NA; ++pa)
-              tma_load_4d_pair(sa + pa * A_PLANE_BYTES, &map_a, lead_bar, a_col + kb * BK, m_blk * BM, a_c2, pa);
+              for (int pa = 0; pa < NA; ++pa)
+                tma_load_4d_pair(sa + pa * A_PLANE_BYTES, &map_a, lead_bar, a_col + kb * BK, m_blk * BM, a_c2, pa);
 #pragma unroll
-            for (int pb = 0; pb < NB; ++pb)
-              tma_load_4d_pair(sb + pb * C::B_PLANE_BYTES, &map_b, lead_bar, b_col + kb * BK, n_blk * BN + rank * (BN / 2), b_c2, pb);
+              for (int pb = 0; pb < NB; ++pb)
+                tma_load_4d_pair(sb + pb * C::B_PLANE_BYTES, &map_b, lead_bar, b_col + kb * BK, n_blk * BN + rank * (BN / 2), b_c2, pb);
+            }
+            __syncwarp();
             if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             continue;
           }
-          mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          if (elect_one()) {
+            mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
 #pragma unroll
-          for (int pa = 0; pa < NA; ++pa) {
-            if (!A_MN) {
-              tma_load_4d(sa + pa * A_PLANE_BYTES, &map_a, &full_bar[stage], a_col + kb * BK, m_blk * BM, a_c2, pa);
-            } else {
+            for (int pa = 0; pa < NA; ++pa) {
+              if (!A_MN) {
+                tma_load_4d(sa + pa * A_PLANE_BYTES, &map_a, &full_bar[stage], a_col + kb * BK, m_blk * BM, a_c2, pa);
+              } else {
 #pragma unroll
-              for (int j = 0; j < BM / 64; ++j)
-                tma_load_4d(sa + pa * A_PLANE_BYTES + j * 8192, &map_a, &full_bar[stage], a_col + m_blk * BM + j * 64,
-                            kb * BK, a_c2, pa);
+                for (int j = 0; j < BM / 64; ++j)
+                  tma_load_4d(sa + pa * A_PLANE_BYTES + j * 8192, &map_a, &full_bar[stage], a_col + m_blk * BM + j * 64,
+                              kb * BK, a_c2, pa);
+              }
+            }
+#pragma unroll
+            for (int pb = 0; pb < NB; ++pb) {
+              if (!B_MN) {
+                tma_load_4d(sb + pb * C::B_PLANE_BYTES, &map_b, &full_bar[stage], b_col + kb * BK, n_blk * BN, b_c2, pb);
+              } else {
+#pragma unroll
+                for (int j = 0; j < BN / 64; ++j)
+                  tma_load_4d(sb + pb * C::B_PLANE_BYTES + j * 8192, &map_b, &full_bar[stage], b_col + n_blk * BN + j * 64,
+                              kb * BK, b_c2, pb);
+              }
             }
           }
-#pragma unroll
-          for (int pb = 0; pb < NB; ++pb) {
-            if (!B_MN) {
-              tma_load_4d(sb + pb * C::B_PLANE_BYTES, &map_b, &full_bar[stage], b_col + kb * BK, n_blk * BN, b_c2, pb);
-            } else {
-#pragma unroll
-              for (int j = 0; j < BN / 64; ++j)
-                tma_load_4d(sb + pb * C::B_PLANE_BYTES + j * 8192, &map_b, &full_bar[stage], b_col + n_blk * BN + j * 64,
-                            kb * BK, b_c2, pb);
-            }
-          }
+          __syncwarp();
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
