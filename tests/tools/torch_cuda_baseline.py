@@ -2,7 +2,9 @@
 ViT-B/16 teacher + ViT-S/16 student prepared by stock prepare_qat (fbgemm qconfig), the reference loop body
 (oracle.vit_ref.distill_step = ref/src/training/qat_trainer.py:337-361) under eager autograd, ATen CUDA kernels (cuBLAS fp32
 SGEMM with TF32 off, SDPA, FusedObsFakeQuant).  Prints one JSON line.  Test/measurement infrastructure only.
-Usage (GPU box): python tests/tools/torch_cuda_baseline.py [batch]"""
+Usage (GPU box): python tests/tools/torch_cuda_baseline.py [batch] [dropin]
+`dropin`: the SAME unmodified loop body after qatvit_b200.dropin.install() -- the module-level integration: the
+teacher stays stock torch CUDA, every fake-quant module / nnqat.Linear / nnqat.Conv2d of the student runs on the sm_100a kernels."""
 import json
 import os
 import sys
@@ -15,6 +17,11 @@ from oracle import vit_ref as vr  # noqa: E402
 
 warnings.simplefilter("ignore")
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+DROPIN = len(sys.argv) > 2 and sys.argv[2] == "dropin"
+if DROPIN:
+    import qatvit_b200  # noqa: F401
+    from qatvit_b200 import dropin
+    dropin.install()
 dev = torch.device("cuda", 0)
 hp = dict(vr.DEFAULT_HPARAMS)
 student = vr.enable_qat(vr.make_student(prefer_reference=False), "fbgemm").to(dev).train()
@@ -33,6 +40,7 @@ for _ in range(steps):
 e.record()
 torch.cuda.synchronize()
 ms = s.elapsed_time(e) / steps
-print(json.dumps({"impl": "stock torch CUDA eager (the reference's own GPU path)", "batch": B, "ms_per_step": ms, "img_per_s": B / ms * 1e3,
+print(json.dumps({"impl": ("reference loop body + qatvit_b200.dropin.install() (module-level drop-ins under stock autograd; teacher stock)" if DROPIN else
+                           "stock torch CUDA eager (the reference's own GPU path)"), "routes": (dict(dropin.stats) if DROPIN else None), "batch": B, "ms_per_step": ms, "img_per_s": B / ms * 1e3,
                   "allow_tf32_matmul": torch.backends.cuda.matmul.allow_tf32, "allow_tf32_cudnn": torch.backends.cudnn.allow_tf32,
                   "torch": torch.__version__, "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30}))
