@@ -458,6 +458,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     n = max(world, 1)
     global_batch = 256 if n == 1 else 1024
+    if os.environ.get("QV_BENCH_GLOBAL_BATCH"):      # experiments only (e.g. N = 2 with the per-GPU batch of N = 4); shows in config.global_batch
+        global_batch = int(os.environ["QV_BENCH_GLOBAL_BATCH"])
     batch = global_batch // n
 
     student, teacher = build_models(batch, dev, ln_variant=args.ln_variant, prepare=not args.pre_qat)
