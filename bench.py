@@ -96,13 +96,13 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the reference's own torch.ao CPU path (restated step over the live torch CPU ops)
 # --------------------------------------------------------------------------------------------------------------------
-def cpu_reference_rate(steps: int, warmup: int, batch: int = 8, budget_s: float = 25.0):
+def cpu_reference_rate(steps: int, warmup: int, batch: int = 8, budget_s: float = 25.0, qconfig: str = "fbgemm"):
     """img/s of the reference CPU path on a bounded sample: `steps` distill steps at batch 8 (BASELINE configs[0])."""
     import torch
     from oracle import vit_ref as vr     # checker / baseline only -- never on the product path
     torch.set_num_threads(os.cpu_count() or 1)
     hp = dict(vr.DEFAULT_HPARAMS)
-    student = vr.enable_qat(vr.make_student(prefer_reference=False), "fbgemm")
+    student = vr.enable_qat(vr.make_student(prefer_reference=False), qconfig)
     teacher = vr.make_teacher()
     opt = vr.make_optimizer(student.parameters(), hp, 0.5)
     images, labels = vr.synthetic_batch(batch, seed=0)
@@ -117,7 +117,7 @@ def cpu_reference_rate(steps: int, warmup: int, batch: int = 8, budget_s: float 
             break
     dt = time.perf_counter() - t0
     return dict(value=batch * done / dt, unit="img/s", cores=torch.get_num_threads(), kind="port",
-                sample=f"{done} full distill steps (ViT-B teacher fwd + ViT-S fbgemm-QAT student fwd/bwd + clip + AdamW) at "
+                sample=f"{done} full distill steps (ViT-B teacher fwd + ViT-S {qconfig}-QAT student fwd/bwd + clip + AdamW) at "
                        f"batch {batch}, fp32, stock torch {torch.__version__} CPU ops, {dt / done * 1e3:.0f} ms/step"), dt / done
 
 
@@ -125,12 +125,12 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base, ms = cpu_reference_rate(max(args.steps, 1), max(args.warmup, 0), budget_s=150.0)
+    base, ms = cpu_reference_rate(max(args.steps, 1), max(args.warmup, 0), budget_s=150.0, qconfig=args.qconfig)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "img/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "ViT-B/16 teacher -> ViT-S/16 QAT student distillation step (KL+CE), bounded sample: batch 8 "
-                                   "per step on the host CPU", "qconfig": "fbgemm"},
+                                   "per step on the host CPU", "qconfig": args.qconfig},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     _emit(line)
@@ -139,7 +139,7 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------------------------
 # this repo's arm
 # --------------------------------------------------------------------------------------------------------------------
-def build_models(batch, dev, seed=0, ln_variant="subclass", prepare=True):
+def build_models(batch, dev, seed=0, ln_variant="subclass", prepare=True, qconfig="fbgemm"):
     import warnings
     import torch
     from torch.ao.quantization import get_default_qat_qconfig, prepare_qat
@@ -156,7 +156,7 @@ def build_models(batch, dev, seed=0, ln_variant="subclass", prepare=True):
     # QAT enable block, ref qat_trainer.py:304-308 (fbgemm qconfig = per-channel symmetric weights: north_star)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        student.qconfig = get_default_qat_qconfig("fbgemm")
+        student.qconfig = get_default_qat_qconfig(qconfig)
         prepared = prepare_qat(student, inplace=False)
     return prepared.to(dev).train(), teacher.to(dev)
 
@@ -292,6 +292,25 @@ def side_measurements(student, teacher, step, images, labels, dev, peaks, budget
                              "shapes": rows}
     except Exception as ex:     # noqa: BLE001
         out["microbench"] = {"error": repr(ex)[:300]}
+    # ---- the KD + CE loss kernel is latency-bound on the workload's [B, 10] logits; its HBM fraction is reported on a
+    #      synthetic many-class sweep (grid form qv_kd_ce_loss_rows: 12 algorithmic bytes per logit -- s, t in, dL/ds out) ----
+    try:
+        rows = []
+        for (b, c) in [(B, 10), (16384, 1000), (65536, 1000)]:
+            g = torch.Generator(device=dev).manual_seed(3)
+            s_ = torch.randn(b, c, device=dev, generator=g) * 3
+            t_ = torch.randn(b, c, device=dev, generator=g) * 6
+            y_ = torch.randint(0, c, (b,), device=dev, generator=g)
+            o3, gr = torch.empty(3, device=dev), torch.empty_like(s_)
+            us = _timed_us(lambda: ops.kd_ce_loss(s_, t_, y_, HP["kd_temp"], HP["kd_alpha"], HP["label_smoothing"], out3=o3, grad=gr))
+            gbs = 12.0 * b * c / (us * 1e-6) / 1e9
+            rows.append({"B": b, "C": c, "us": round(us, 2), "kernel": "qv_kd_ce_loss_rows" if b * c >= (1 << 15) else "qv_kd_ce_loss (one block)",
+                         "GBps": round(gbs, 1), "frac_hbm": round(gbs / peaks["hbm"], 4), "finite": bool(torch.isfinite(o3).all())})
+            del s_, t_, y_, gr
+        out["kd_ce_sweep"] = {"workload": "KL + label-smoothed CE forward and dL/ds in one launch (ref qat_trainer.py:343-349)",
+                              "bytes_per_logit": 12, "peak_hbm_gbs": peaks["hbm"], "shapes": rows}
+    except Exception as ex:     # noqa: BLE001
+        out["kd_ce_sweep"] = {"error": repr(ex)[:300]}
     # ---- the reference's own GPU path: stock torch CUDA eager (ATen kernels, cuBLAS fp32, autograd) for the same step ----
     try:
         import torch.nn.functional as F
@@ -462,7 +481,7 @@ def run_ours(args):
         global_batch = int(os.environ["QV_BENCH_GLOBAL_BATCH"])
     batch = global_batch // n
 
-    student, teacher = build_models(batch, dev, ln_variant=args.ln_variant, prepare=not args.pre_qat)
+    student, teacher = build_models(batch, dev, ln_variant=args.ln_variant, prepare=not args.pre_qat, qconfig=args.qconfig)
     if args.pre_qat:
         import functools
         from qatvit_b200.plain import PlainDistillStep
@@ -675,7 +694,7 @@ def run_ours(args):
 
     cpu_base = None
     if n == 1 and not args.no_cpu_baseline:
-        cpu_base, _ = cpu_reference_rate(steps=1000, warmup=2, budget_s=18.0)
+        cpu_base, _ = cpu_reference_rate(steps=1000, warmup=2, budget_s=18.0, qconfig=args.qconfig)
     side = None
     if n == 1 and not args.no_side and not args.pre_qat:
         side = side_measurements(student, teacher, step, images, labels, dev, peaks)
@@ -695,7 +714,7 @@ def run_ours(args):
                    if (n == 1 and args.pre_qat) else
                    "ViT-B/16 teacher -> ViT-S/16 QAT student distillation step (KL+CE), batch 256, 1x B200"
                    if n == 1 else f"same distillation step data-parallel, global batch 1024 at {n} B200 with NCCL gradient allreduce",
-                   "global_batch": global_batch, "per_gpu_batch": batch, "qconfig": "fbgemm", "layernorm": args.ln_variant, "image": "3x224x224",
+                   "global_batch": global_batch, "per_gpu_batch": batch, "qconfig": args.qconfig, "layernorm": args.ln_variant, "image": "3x224x224",
                    "parallelism": f"dp{n}",
                    "scaling_note": "N = 1 runs BASELINE configs[1] (batch 256 on one GPU); N = 2 / 4 / 8 run configs[2] (global batch 1024 "
                                    "split 512 / 256 / 128 per GPU: strong scaling among themselves; N = 4 has the per-GPU work of N = 1)",
@@ -748,6 +767,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--qconfig", default="fbgemm", choices=["fbgemm", "qnnpack"],
+                    help="torch.ao QAT qconfig of the student: fbgemm (per-channel symmetric weights, activations 0..127; north_star, "
+                         "default) or qnnpack (per-tensor weights, activations 0..255; the reference script's own default)")
     ap.add_argument("--no-side", action="store_true", help="skip the N = 1 side measurements (microbench, int8_eval, torch_cuda_eager)")
     ap.add_argument("--ln-variant", default="subclass", choices=["subclass", "plain"],
                     help="timm LayerNorm flavour: 'subclass' (timm.layers.LayerNorm, not observed: 101 fake-quant modules, the "

@@ -121,6 +121,14 @@ int qv_split_planes_mix(const float* x, int64_t rows, int64_t cols, int32_t kind
 int qv_kd_ce_loss(const float* s_raw, const float* t, const int64_t* labels, int32_t B, int32_t C, float T,
                   float alpha, float eps, const float* s_scale, const int32_t* s_zp, int32_t qmin,
                   int32_t qmax, float* out3, float* grad, void* stream);
+/* The same loss for many classes / large batches (the reference's lines 343-349 are shape-agnostic; ImageNet-width heads): one warp
+ * per row over a persistent grid, 16-byte loads when C % 4 == 0, every element read from HBM once and its gradient written once
+ * (12 B per element), fixed-order (deterministic) reduction.  workspace: qv_kd_ce_rows_workspace_floats(B) floats owned by the
+ * caller, ZERO before the first use (the kernel leaves its ticket word zero again). */
+int64_t qv_kd_ce_rows_workspace_floats(int32_t B);
+int qv_kd_ce_loss_rows(const float* s_raw, const float* t, const int64_t* labels, int32_t B, int32_t C, float T,
+                       float alpha, float eps, const float* s_scale, const int32_t* s_zp, int32_t qmin,
+                       int32_t qmax, float* out3, float* grad, float* workspace, void* stream);
 
 /* ---- tcgen05 GEMM family (replaces F.linear inside torch.ao.nn.qat.Linear.forward,
  *      torch/ao/nn/qat/modules/linear.py:50-51, its autograd dgrad/wgrad, the teacher's nn.Linear, and --

@@ -96,6 +96,9 @@ _SIGNATURES = {
     "qv_split_planes_mix": (c_int, [_P, c_int64, c_int64, c_int32, _P, _P, _P]),
     "qv_kd_ce_loss": (c_int, [_P, _P, _P, c_int32, c_int32, c_float, c_float, c_float, _P, _P, c_int32, c_int32,
                               _P, _P, _P]),
+    "qv_kd_ce_rows_workspace_floats": (c_int64, [c_int32]),
+    "qv_kd_ce_loss_rows": (c_int, [_P, _P, _P, c_int32, c_int32, c_float, c_float, c_float, _P, _P, c_int32, c_int32,
+                                   _P, _P, _P, _P]),
     "qv_gemm_bf16": (c_int, [POINTER(GemmArgs), _P]),
     "qv_splitk_reduce": (c_int, [_P, c_int32, c_int64, c_int64, _P, _P, _P, _P, c_int32, _P]),
     "qv_resid_ln_fwd": (c_int, [_P, _P, _P, _P, c_int32, c_int32, _P, _P, c_float, c_int64, c_int32, c_int64, _P, _P,

@@ -176,13 +176,32 @@ def split_planes_mix(x: torch.Tensor, weight: bool = False, out: Optional[torch.
     return out
 
 
+_KD_ROWS_MIN_ELEMS = 1 << 15      # above this many logits the one-block kernel stops being latency-bound: use the grid form
+_kd_ws = {}                        # device -> zeroed workspace of the grid form (ticket word + per-block partial sums)
+
+
 def kd_ce_loss(s_raw, t, labels, T, alpha, eps, s_scale=None, s_zp=None, qmin=0, qmax=255, want_grad=True, out3=None,
-               grad=None):
+               grad=None, rows=None):
+    """KL + label-smoothed CE and dL/ds in one launch (ref qat_trainer.py:343-349).  rows: force (True) / forbid (False) the
+    grid form ``qv_kd_ce_loss_rows`` (default: by size -- the reference's [B, 10] logits take the one-block kernel)."""
     B, C = s_raw.shape
     if out3 is None:
         out3 = torch.empty(3, dtype=torch.float32, device=s_raw.device)
     if grad is None and want_grad:
         grad = torch.empty_like(s_raw)
+    if rows is None:
+        rows = B * C >= _KD_ROWS_MIN_ELEMS
+    if rows:
+        L = _lib.lib()
+        need = int(L.qv_kd_ce_rows_workspace_floats(B))
+        key = (s_raw.device, torch.cuda.current_stream(s_raw.device).cuda_stream)     # one workspace per stream: launches that may overlap never share a ticket
+        ws = _kd_ws.get(key)
+        if ws is None or ws.numel() < need:
+            ws = _kd_ws[key] = torch.zeros(max(need, 4096), dtype=torch.float32, device=s_raw.device)
+        check(L.qv_kd_ce_loss_rows(_p(s_raw, torch.float32, "s"), _p(t, torch.float32, "t"), _p(labels, torch.int64, "labels"),
+                                   B, C, float(T), float(alpha), float(eps), _p(s_scale, torch.float32), _p(s_zp, torch.int32),
+                                   int(qmin), int(qmax), _p(out3), _p(grad), _p(ws, torch.float32), _stream()), "kd_ce_loss_rows")
+        return out3, grad
     check(_lib.lib().qv_kd_ce_loss(_p(s_raw, torch.float32, "s"), _p(t, torch.float32, "t"),
                                    _p(labels, torch.int64, "labels"), B, C, float(T), float(alpha), float(eps),
                                    _p(s_scale, torch.float32), _p(s_zp, torch.int32), int(qmin), int(qmax),

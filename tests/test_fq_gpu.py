@@ -212,6 +212,44 @@ def test_kd_ce_loss(cuda_dev, B, C, fq):
     assert torch.allclose(grad.cpu(), sq.grad, rtol=1e-4, atol=1e-7)
 
 
+@pytest.mark.parametrize("B,C", [(513, 10), (300, 1000), (2048, 1002), (4096, 1000)])
+@pytest.mark.parametrize("fq", [False, True])
+def test_kd_ce_loss_rows(cuda_dev, B, C, fq):
+    """The grid form (qv_kd_ce_loss_rows: one warp per row, 16-byte loads when C % 4 == 0, scalar otherwise) against the same
+    CPU torch expression, launched three times on one workspace (the ticket word must come back to zero) with bit-identical
+    results (fixed-order reduction), and against the one-block kernel."""
+    from qatvit_b200 import ops
+    from oracle import vit_ref as vr
+    dev = cuda_dev
+    gen = torch.Generator().manual_seed(6)
+    s = torch.randn(B, C, generator=gen) * 3
+    t = torch.randn(B, C, generator=gen) * 6
+    y = torch.randint(0, C, (B,), generator=gen)
+    hp = dict(vr.DEFAULT_HPARAMS)
+    scale, zp = torch.tensor([0.0731]), torch.tensor([61], dtype=torch.int32)
+    sq = s.clone().requires_grad_(True)
+    s_in = torch.fake_quantize_per_tensor_affine(sq, 0.0731, 61, 0, 127) if fq else sq
+    loss, kd, ce = vr.distill_loss(s_in, t, y, hp)
+    loss.backward()
+    kw = dict(s_scale=scale.to(dev) if fq else None, s_zp=zp.to(dev) if fq else None, qmin=0, qmax=127)
+    args = (s.to(dev), t.to(dev), y.to(dev), hp["kd_temp"], hp["kd_alpha"], hp["label_smoothing"])
+    runs = []
+    for _ in range(3):
+        out3, grad = ops.kd_ce_loss(*args, rows=True, **kw)
+        runs.append((out3.clone(), grad.clone()))
+    torch.cuda.synchronize()
+    for o, g in runs[1:]:
+        assert torch.equal(o, runs[0][0]) and torch.equal(g, runs[0][1])
+    out3, grad = runs[0][0].cpu(), runs[0][1].cpu()
+    assert abs(out3[0] - loss.item()) <= 1e-5 * abs(loss.item())
+    assert abs(out3[1] - kd.item()) <= 1e-5 * abs(kd.item()) + 1e-7
+    assert abs(out3[2] - ce.item()) <= 1e-5 * abs(ce.item())
+    assert torch.allclose(grad, sq.grad, rtol=1e-4, atol=1e-7)
+    one3, one_grad = ops.kd_ce_loss(*args, rows=False, **kw)
+    assert torch.allclose(one3.cpu(), out3, rtol=2e-6, atol=0)
+    assert torch.allclose(one_grad.cpu(), grad, rtol=1e-5, atol=1e-9)     # same expression, different lane -> column assignment
+
+
 def test_weight_fq_grouped_bit_exact(cuda_dev):
     """qv_fq_weight_grouped: several per-channel weights (ViT-S shapes, a ragged row count and edge-case rows) in ONE launch,
     three EMA steps; state, fake-quantised values (codes * scale), STE mask and the transposed code plane must equal the live
