@@ -40,6 +40,38 @@ def test_attn_fwd_fp32_planes(cuda_dev, B, H, T):
     assert float((lse.double().cpu() - lse_ref.cpu()).abs().max()) < 1e-4
 
 
+@pytest.mark.parametrize("B,H,T,npl", [(80, 6, 197, 2), (100, 6, 197, 1), (400, 3, 37, 2), (333, 2, 129, 1)])
+def test_attn_fwd_many_items_per_cta(cuda_dev, B, H, T, npl):
+    """Several (image, head) items per CTA: the forward pipelines tiles ACROSS items (the next item's score tile is issued while
+    this item's other tile is still in its softmax / PV product; one output accumulator shared in turn).  Every item must still
+    equal the fp64 reference, and two runs must agree bit for bit (no race between an item's drain and the next item's MMAs)."""
+    from qatvit_b200 import ops
+    g = torch.Generator().manual_seed(B + 31 * H + T)
+    D = H * 64
+    if npl == 2:
+        qkv = (torch.randn(B * T, 3 * D, generator=g) * 1.5).to(cuda_dev)
+        planes, kw = ops.split_planes(qkv), {}
+    else:
+        sc = torch.tensor([0.0437], device=cuda_dev)
+        codes = torch.randint(-60, 68, (B * T, 3 * D), generator=g).float().to(cuda_dev)
+        qkv = codes * sc
+        planes, kw = codes.bfloat16()[None].contiguous(), dict(qk_scale=sc, v_scale=sc)
+    outs = []
+    for _ in range(2):
+        out = torch.full((2, B * T, D), float("nan"), dtype=torch.bfloat16, device=cuda_dev)
+        lse = torch.empty(B * H * T, device=cuda_dev)
+        ops.attn_fwd(planes, B, T, H, 0.125, out, lse=lse, **kw)
+        outs.append((out, lse))
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    o_ref, lse_ref = _ref(qkv, B, T, H, 0.125)
+    got = outs[0][0][0].double() + outs[0][0][1].double()
+    # per item, so that one wrong item cannot hide behind the global maximum
+    err = (got - o_ref).abs().view(B, T, H, 64).amax(dim=(1, 3)) / o_ref.abs().view(B, T, H, 64).amax(dim=(1, 3))
+    assert float(err.max()) < 1e-4, (int(err.argmax()) // H, int(err.argmax()) % H)
+    assert float((outs[0][1].double() - lse_ref).abs().max()) < 1e-4
+
+
 @pytest.mark.parametrize("B,H,T", [(3, 6, 197), (4, 2, 17), (2, 3, 37)])
 def test_attn_fwd_integer_codes(cuda_dev, B, H, T):
     """student operands: centred fake-quant codes (|c| <= 127 here) in ONE bf16 plane, scale as a device scalar."""

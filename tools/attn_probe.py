@@ -45,6 +45,14 @@ def main():
     items = B * H
     t = timeit(lambda: ops.attn_fwd(cp, B, T, H, 0.125, out, qk_scale=s, v_scale=s, lse=lse))
     print(f"attn_fwd (codes): {t:.1f} us, {t * 148 / items:.2f} us per item per SM")
+    # teacher form: fp32-grade hi/lo planes, 12 heads, mixed-format planes out (what TeacherEngine launches)
+    Ht = 12
+    Dt = Ht * 64
+    qkvp = ops.split_planes(torch.randn(B * T, 3 * Dt, device=dev) * 1.5)
+    out_t = torch.empty(2, B * T, Dt, dtype=torch.bfloat16, device=dev)
+    t = timeit(lambda: ops.attn_fwd(qkvp, B, T, Ht, 0.125, out_t))
+    print(f"attn_fwd (hi/lo planes, {Ht} heads): {t:.1f} us, {t * 148 / (B * Ht):.2f} us per item per SM")
+    del qkvp, out_t
     t = timeit(lambda: ops.attn_bwd(cp, s, out, dOp, lse, B, T, H, 0.125, g_qkv))
     print(f"attn_bwd: {t:.1f} us, {t * 148 / items:.2f} us per item per SM")
     t = timeit(lambda: ops.attn_bwd_gp(cp, s, out, dOp, lse, B, T, H, 0.125, y_raw, fq, wsc, planes, slab))
