@@ -47,7 +47,10 @@ struct AttnCfg {
   static constexpr int Q_BYTES = NPL * 2 * Q_TILE_BYTES;
   static constexpr int K_BYTES = NPL * K_PLANE_BYTES;
   static constexpr int V_BYTES = NPL * V_PLANE_BYTES;
-  static constexpr int STAGE_BYTES = 16 * 2048;           // per softmax warp: 32 rows x 64 B, the output transpose
+  // per softmax warp: the output staging the TMA stores read.  One 2 KB buffer (32 rows x 64 B) where shared memory is full
+  // (hi/lo operand planes: 224 KB), two for the one-plane code operands (hi and lo leave without an intermediate wait)
+  static constexpr int STAGE_PER_WARP = (NPL == 1) ? 4096 : 2048;
+  static constexpr int STAGE_BYTES = 16 * STAGE_PER_WARP;
   static constexpr int SMEM_BYTES = Q_BYTES + K_BYTES + V_BYTES + 8192 /*row max / exponent / sum exchange*/ + STAGE_BYTES + 1024 /*align slack*/ +
                                     256 /*barriers*/;
   static constexpr int NPAIRS_S = (NPL == 2) ? 3 : 1;    // (hi,hi) (hi,lo) (lo,hi)  |  codes x codes
@@ -278,10 +281,24 @@ __device__ __forceinline__ void warp_store_row_runs(uint8_t* stage, int lane, co
   }
 }
 
+// A warp's 32 rows x (NCH * 16) bytes (lane = row) written to a staging buffer in the layout a TMA store box expects: NCH = 4 ->
+// 64-byte rows under the 64B swizzle (16-byte chunk j of row r at j ^ ((r >> 1) & 3)); NCH = 2 -> plain 32-byte rows.
+template <int NCH>
+__device__ __forceinline__ void stage_rows_tma(uint8_t* stage, int lane, const uint4 (&v)[NCH]) {
+  const uint32_t sbase = smem_u32(stage) + static_cast<uint32_t>(lane) * (NCH * 16);
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const uint32_t pos = (NCH == 4) ? static_cast<uint32_t>(c ^ ((lane >> 1) & 3)) : static_cast<uint32_t>(c);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + pos * 16), "r"(v[c].x), "r"(v[c].y), "r"(v[c].z), "r"(v[c].w)
+                 : "memory");
+  }
+}
+
 template <int NPL>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 qv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
-                   const __grid_constant__ CUtensorMap map_v, const AttnParams p) {
+                   const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_o,
+                   const __grid_constant__ CUtensorMap map_o8, const AttnParams p) {
   using C = AttnCfg<NPL>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -313,6 +330,10 @@ qv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     prefetch_tensormap(&map_q);
     prefetch_tensormap(&map_k);
     prefetch_tensormap(&map_v);
+    if (p.out) {
+      prefetch_tensormap(&map_o);
+      prefetch_tensormap(&map_o8);
+    }
     mbar_init(qk_full, 1);
     mbar_init(qk_empty, 1);
     mbar_init(v_full, 1);
@@ -455,7 +476,8 @@ qv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       float* x_sum = x_max + 1024;                                 // x_max + 512: the reference exponents
       const int partner = (hf == 0) ? 128 : -128;
       const int bar_id = 1 + g * 4 + q;
-      uint8_t* my_stage = stage_all + (warp - 2) * 2048;
+      constexpr int SPW = C::STAGE_PER_WARP;
+      uint8_t* my_stage = stage_all + (warp - 2) * SPW;
       float sc = p.scale;
       float vs = 1.0f;
       if (p.qk_scale) { const float s = __ldg(p.qk_scale); sc *= s * s; }
@@ -551,9 +573,6 @@ qv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
           const float inv = vs / sum;                               // padded rows: finite garbage, never stored
           const int64_t row0 = static_cast<int64_t>(b) * p.T + t0w;
           if (p.out) {
-            uint8_t* hi0 = reinterpret_cast<uint8_t*>(p.out + row0 * p.out_ld + h * HD);            // plane 0, this head, row t0w
-            uint8_t* lo0 = hi0 + p.out_plane_stride * 2;
-            const int64_t pitch = p.out_ld * 2;
             if (p.out_fmt == 1) {      // a head's 64 columns are exactly one block of the mixed format: 64 hi8 | 64 lo8
               uint4 h16v[4], h8v[2], l8v[2];
 #pragma unroll
@@ -571,9 +590,39 @@ qv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 if (j & 1) { h8v[j >> 1].z = w0; h8v[j >> 1].w = w1; l8v[j >> 1].z = x0; l8v[j >> 1].w = x1; }
                 else { h8v[j >> 1].x = w0; h8v[j >> 1].y = w1; l8v[j >> 1].x = x0; l8v[j >> 1].y = x1; }
               }
-              warp_store_row_runs<4>(my_stage, lane, h16v, hi0 + hf * 64, pitch, n_rows);
-              warp_store_row_runs<2>(my_stage, lane, h8v, lo0 + hf * 32, pitch, n_rows);
-              warp_store_row_runs<2>(my_stage, lane, l8v, lo0 + 64 + hf * 32, pitch, n_rows);
+              // fp16 region: a 32-column box; region 1: this half's 32 hi8 and 32 lo8 bytes = two 16-"element" boxes of the block
+              const int col = h * HD + hf * 32, col8 = h * HD + hf * 16;
+              if (lane == 0) tma_store_wait_read<0>();            // the previous item's stores have read the staging buffer
+              __syncwarp();
+              stage_rows_tma<4>(my_stage, lane, h16v);
+              uint8_t* st8 = my_stage + (SPW >= 4096 ? 2048 : 0);
+              if constexpr (SPW >= 4096) {
+                stage_rows_tma<2>(st8, lane, h8v);
+                stage_rows_tma<2>(st8 + 1024, lane, l8v);
+              }
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_4d(&map_o, my_stage, col, t0w, b, 0);
+                if constexpr (SPW >= 4096) {
+                  tma_store_4d(&map_o8, st8, col8, t0w, b, 1);
+                  tma_store_4d(&map_o8, st8 + 1024, col8 + 32, t0w, b, 1);
+                }
+                tma_store_commit();
+                if constexpr (SPW < 4096) tma_store_wait_read<0>();
+              }
+              if constexpr (SPW < 4096) {
+                __syncwarp();
+                stage_rows_tma<2>(st8, lane, h8v);
+                stage_rows_tma<2>(st8 + 1024, lane, l8v);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                  tma_store_4d(&map_o8, st8, col8, t0w, b, 1);
+                  tma_store_4d(&map_o8, st8 + 1024, col8 + 32, t0w, b, 1);
+                  tma_store_commit();
+                }
+              }
             } else {
               uint4 hv[4], lv[4];
 #pragma unroll
@@ -586,13 +635,36 @@ qv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
                 lv[j] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
               }
               DBG(dbg_who, 37);
-              warp_store_row_runs<4>(my_stage, lane, hv, hi0 + hf * 64, pitch, n_rows);
+              const int col = h * HD + hf * 32;
+              if (lane == 0) tma_store_wait_read<0>();            // the previous item's stores have read the staging buffer
+              __syncwarp();
+              stage_rows_tma<4>(my_stage, lane, hv);
+              if constexpr (SPW >= 4096) stage_rows_tma<4>(my_stage + 2048, lane, lv);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_4d(&map_o, my_stage, col, t0w, b, 0);
+                if constexpr (SPW >= 4096) tma_store_4d(&map_o, my_stage + 2048, col, t0w, b, 1);
+                tma_store_commit();
+                if constexpr (SPW < 4096) tma_store_wait_read<0>();
+              }
               DBG(dbg_who, 38);
-              warp_store_row_runs<4>(my_stage, lane, lv, lo0 + hf * 64, pitch, n_rows);
+              if constexpr (SPW < 4096) {
+                __syncwarp();
+                stage_rows_tma<4>(my_stage, lane, lv);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                  tma_store_4d(&map_o, my_stage, col, t0w, b, 1);
+                  tma_store_commit();
+                }
+              }
               DBG(dbg_who, 39);
             }
           }
           if (p.out_f32) {
+            if (lane == 0) tma_store_wait_read<0>();              // the plane stores above read the same staging buffer
+            __syncwarp();
             uint8_t* f0 = reinterpret_cast<uint8_t*>(p.out_f32 + row0 * (static_cast<int64_t>(p.H) * HD) + h * HD + hf * 32);
             const int64_t pitch = static_cast<int64_t>(p.H) * HD * 4;
 #pragma unroll
@@ -612,6 +684,7 @@ qv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         DBG(dbg_who, 35);
       }
       if (p.sat_flag && __any_sync(0xffffffffu, amax > QV_MIX_ACT_MAX) && lane == 0) atomicOr(p.sat_flag, p.sat_bit);
+      if (lane == 0) tma_store_wait_read<0>();                    // staging buffers are read before the CTA's shared memory goes away
     }
   }
 
@@ -624,8 +697,8 @@ qv_attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
 }
 
 template <int NPL>
-int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& ap, int grid,
-                cudaStream_t st) {
+int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mo, const CUtensorMap& mo8,
+                const AttnParams& ap, int grid, cudaStream_t st) {
   using C = AttnCfg<NPL>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
@@ -633,7 +706,7 @@ int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap&
     attr_err = cudaFuncSetAttribute(qv_attn_fwd_kernel<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
   });
   QV_REQUIRE(attr_err == cudaSuccess, QV_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
-  qv_attn_fwd_kernel<NPL><<<grid, AT_THREADS, C::SMEM_BYTES, st>>>(mq, mk, mv, ap);
+  qv_attn_fwd_kernel<NPL><<<grid, AT_THREADS, C::SMEM_BYTES, st>>>(mq, mk, mv, mo, mo8, ap);
   return qv_check_launch("qv_attn_fwd");
 }
 
@@ -1238,12 +1311,21 @@ extern "C" int qv_attn_fwd(const uint16_t* qkv_planes, int32_t n_planes, int64_t
   if (rc) return rc;
   rc = make_map(&mv, op, n_planes, 64);
   if (rc) return rc;
+  // output planes as [plane][image][token][column]: a store box that runs past an image's last token is clipped by the descriptor
+  // (the second query tile's padding rows), 32-column boxes for the 2-byte planes, 16-"element" boxes for the mixed format's byte runs
+  CUtensorMap mo = mq, mo8 = mq;
+  if (out_planes) {
+    rc = make_out_planes_map(&mo, out_planes, static_cast<int64_t>(H) * HD, T, out_ld, B, static_cast<int64_t>(T) * out_ld, out_plane_stride, 32);
+    if (rc) return rc;
+    rc = make_out_planes_map(&mo8, out_planes, static_cast<int64_t>(H) * HD, T, out_ld, B, static_cast<int64_t>(T) * out_ld, out_plane_stride, 16);
+    if (rc) return rc;
+  }
   const int items = B * H;
   const int sms = qv_num_sms();
   const int grid = items < sms ? items : sms;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (n_planes == 2) return launch_attn<2>(mq, mk, mv, ap, grid, st);
-  return launch_attn<1>(mq, mk, mv, ap, grid, st);
+  if (n_planes == 2) return launch_attn<2>(mq, mk, mv, mo, mo8, ap, grid, st);
+  return launch_attn<1>(mq, mk, mv, mo, mo8, ap, grid, st);
 }
 
 namespace {
