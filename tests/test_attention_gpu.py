@@ -89,7 +89,7 @@ def test_attn_fwd_integer_codes(cuda_dev, B, H, T):
     assert _rel(got, o_ref) < 1e-4
 
 
-@pytest.mark.parametrize("B,H,T", [(3, 6, 197), (4, 2, 17), (2, 3, 37), (1, 1, 128), (2, 2, 129), (150, 2, 33), (2, 2, 224), (1, 3, 209),
+@pytest.mark.parametrize("B,H,T", [(3, 6, 197), (4, 2, 17), (2, 3, 37), (1, 1, 128), (2, 2, 129), (150, 2, 33), (100, 6, 197), (2, 2, 224), (1, 3, 209),
                                    (2, 1, 64), (3, 1, 65), (1, 2, 1)])
 def test_attn_bwd_integer_codes(cuda_dev, B, H, T):
     """fused backward (recomputed P from codes + lse) vs fp64 autograd of softmax(QK^T/8)V."""

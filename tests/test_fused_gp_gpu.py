@@ -17,7 +17,7 @@ def _rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
-@pytest.mark.parametrize("B,H,T", [(3, 6, 197), (4, 2, 17), (2, 3, 129), (150, 2, 33), (2, 2, 224), (1, 2, 64), (2, 1, 193)])
+@pytest.mark.parametrize("B,H,T", [(3, 6, 197), (4, 2, 17), (2, 3, 129), (150, 2, 33), (90, 6, 197), (2, 2, 224), (1, 2, 64), (2, 1, 193)])
 def test_attn_bwd_gp_matches_unfused(cuda_dev, B, H, T):
     from qatvit_b200 import ops
     dev = cuda_dev
