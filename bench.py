@@ -723,8 +723,8 @@ def run_ours(args):
                                 "fused clip-norm + AdamW on flat arenas (qv_clip_adamw, 2 launches)",
                    "attention": "fused tcgen05 (integer-code student fwd+bwd, hi/lo teacher fwd)",
                    "streams": "teacher forward and weight-gradient GEMMs on side streams (event-ordered)",
-                   "gemm_pairs": ("teacher Linears as CTA pairs (tcgen05 cta_group::2, QV_GEMM_PAIR="
-                                  + os.environ.get("QV_GEMM_PAIR", "default 51") + f"): {int(ops.gemm_pair_launches())} launches so far")},
+                   "gemm_pairs": ("teacher Linears and the student's plane-output / K >= 1024 GEMMs as CTA pairs (tcgen05 cta_group::2, QV_GEMM_PAIR="
+                                  + os.environ.get("QV_GEMM_PAIR", "default 115") + f"): {int(ops.gemm_pair_launches())} launches so far")},
         "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": host_images.numel() * 4 + host_labels.numel() * 8,
                 "d2h_bytes_per_step": 12, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
