@@ -358,8 +358,16 @@ def side_measurements(student, teacher, step, images, labels, dev, peaks, budget
         # qkv 3, proj 1, fc1 4, fc2 4 = 12 D^2 MACs per token and block, 12 blocks, + the patch-embed conv
         int_ops = 2.0 * 197 * B * 12 * 12 * 384 * 384 + 2.0 * 196 * B * 384 * 768
         int8_peak = 2.0 * peaks["tf_sustained"]
+        # the same executor with the first implementation of the float glue (fp32 tensors between the Linears), for comparison
+        ex_f = ConvertedStudent(conv, B, dev, compact=False)
+        us_f = _timed_us(lambda: ex_f(images), iters=5, warm=2)
+        del ex_f
         res = {"workload": f"converted int8 ViT-S/16 student eval, batch {B}, synthetic 224x224 (BASELINE configs[4])",
                "img_per_s": B / (us * 1e-6), "ms_per_batch": us / 1e3, "finite": bool(torch.isfinite(logits).all()),
+               "glue": ("compact: quint8 codes between a Linear and a consumer that works on codes (attention on one exact bf16 code "
+                        "plane, GELU + dynamic re-quantisation as table lookups), qparams folded into the quantising pass"
+                        if ex_.compact else "fp32 tensors between the Linears"),
+               "fp32_glue_ms_per_batch": us_f / 1e3,
                "int8_linear": {"launches": lin["count"], "ms": round(lin["ms"], 3),
                                "alg_tops": round(int_ops / max(lin["ms"], 1e-9) / 1e9, 1),
                                "frac_of_int8_peak": round(int_ops / max(lin["ms"], 1e-9) / 1e9 / int8_peak, 3),

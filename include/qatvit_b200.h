@@ -346,6 +346,21 @@ int qv_im2col_u8(const float* img, const float* scale, const int32_t* zp, int64_
                  uint8_t* out, void* stream);
 /* y = GELU_erf(x) in fp32, with the min / max of y merged into acc (may be NULL): the float glue between fc1 and fc2. */
 int qv_gelu_minmax(const float* x, int64_t n, float* y, uint32_t* acc, void* stream);
+/* Compact float glue of the converted student (same arithmetic as the fp32 glue above, on the Linear's quint8 OUTPUT codes:
+ * (q - z_y) * s_y is an integer code times one scale -- torch/ao/nn/quantized/modules/linear.py:187-190 returns exactly that
+ * quantized tensor; the reference's DeQuantStub / float modules then see its dequantised values):
+ *   qv_quantize_u8_dyn  = qv_qparams_from_minmax(acc, 0, 255) + qv_quantize_u8 in one launch (qparams also stored for the consumer);
+ *   qv_codes_from_u8    : codes[i] = bf16(q[i] - zero_point), the one-plane integer operand of qv_attn_fwd (n % 16 == 0);
+ *   qv_gelu_u8_minmax   : min / max of GELU_erf((q - zy) * sy) merged into acc (a 256-entry table of the qv_gelu_minmax values);
+ *   qv_gelu_u8_requant  : out = quantize_u8(GELU_erf((q - zy) * sy)) with the dynamic qparams of acc (a 256-byte code -> code
+ *                         table), qparams stored for the consuming Linear.  Bit-identical to qv_int8_linear(y) -> qv_gelu_minmax
+ *                         -> qv_qparams_from_minmax -> qv_quantize_u8 (tests/test_int8_gpu.py). */
+int qv_quantize_u8_dyn(const float* x, int64_t n, const uint32_t* acc, float* scale_out, int32_t* zero_point_out, uint8_t* q,
+                       void* stream);
+int qv_codes_from_u8(const uint8_t* q, int64_t n, int32_t zero_point, uint16_t* codes, void* stream);
+int qv_gelu_u8_minmax(const uint8_t* q, int64_t n, float sy, int32_t zy, uint32_t* acc, void* stream);
+int qv_gelu_u8_requant(const uint8_t* q, int64_t n, float sy, int32_t zy, const uint32_t* acc, float* scale_out,
+                       int32_t* zero_point_out, uint8_t* out, void* stream);
 
 /* ---- clip_grad_norm_ + AdamW on flat arenas (replaces ref/src/training/qat_trainer.py:360-361; torch.optim.AdamW foreach
  *      arithmetic, single parameter group) ----

@@ -388,14 +388,145 @@ __global__ void __launch_bounds__(256) quantize_u8_kernel(const float* __restric
 
 // Affine quint8 qparams from an observed min / max (torch/ao/quantization/observer.py:349-427, the convert-time Python
 // formula; also what the float-glue executor uses for dynamically quantised inputs): fp32 arithmetic.
-__global__ void qparams_from_minmax_kernel(const uint32_t* acc, int32_t qmin, int32_t qmax, float* scale, int32_t* zp) {
+__device__ __forceinline__ void qparams_affine(const uint32_t* acc, int32_t qmin, int32_t qmax, float& s, float& z) {
   const float mn = fminf(qv_ord2f(acc[0]), 0.0f), mx = fmaxf(qv_ord2f(acc[1]), 0.0f);
-  float s = __fdiv_rn(__fsub_rn(mx, mn), static_cast<float>(qmax - qmin));
+  s = __fdiv_rn(__fsub_rn(mx, mn), static_cast<float>(qmax - qmin));
   s = fmaxf(s, 1.1920928955078125e-07f);
-  float z = __fsub_rn(static_cast<float>(qmin), nearbyintf(__fdiv_rn(mn, s)));
+  z = __fsub_rn(static_cast<float>(qmin), nearbyintf(__fdiv_rn(mn, s)));
   z = fminf(fmaxf(z, static_cast<float>(qmin)), static_cast<float>(qmax));
+}
+
+__global__ void qparams_from_minmax_kernel(const uint32_t* acc, int32_t qmin, int32_t qmax, float* scale, int32_t* zp) {
+  float s, z;
+  qparams_affine(acc, qmin, qmax, s, z);
   *scale = s;
   *zp = static_cast<int32_t>(z);
+}
+
+__device__ __forceinline__ uint32_t quant4_u8(float a0, float a1, float a2, float a3, float inv, float z) {
+  const float a[4] = {a0, a1, a2, a3};
+  uint32_t w = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float f = __fadd_rn(nearbyintf(__fmul_rn(a[j], inv)), z);
+    f = fminf(fmaxf(f, 0.0f), 255.0f);
+    w |= static_cast<uint32_t>(f) << (8 * j);
+  }
+  return w;
+}
+
+// qv_qparams_from_minmax + qv_quantize_u8 in one launch: every block derives the dynamic (scale, zero point) from the finished
+// min / max accumulator itself (a dozen flops), block 0 publishes them for the int8 Linear that consumes the codes.
+__global__ void __launch_bounds__(256) quantize_u8_dyn_kernel(const float* __restrict__ x, int64_t n, const uint32_t* acc, float* scale_out,
+                                                              int32_t* zp_out, uint8_t* __restrict__ q) {
+  float s, z;
+  qparams_affine(acc, 0, 255, s, z);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *scale_out = s;
+    *zp_out = static_cast<int32_t>(z);
+  }
+  const float inv = __fdiv_rn(1.0f, s);
+  const int64_t n4 = n >> 2;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    reinterpret_cast<uint32_t*>(q)[i] = quant4_u8(v.x, v.y, v.z, v.w, inv, z);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (int64_t i = n4 * 4; i < n; ++i) {
+      float f = __fadd_rn(nearbyintf(__fmul_rn(x[i], inv)), z);
+      q[i] = static_cast<uint8_t>(fminf(fmaxf(f, 0.0f), 255.0f));
+    }
+}
+
+// The output of a converted Linear is (q - z_y) * s_y with q in 0..255: an integer code times ONE scale.  Consumers that can work on
+// codes take them instead of the dequantised fp32 tensor (1 byte instead of 4 out of the GEMM, no fp32 round trip):
+//   * attention: the centred codes q - z_y as ONE bf16 plane (|q - z_y| <= 255 is exact in bf16), s_y applied by the kernel --
+//     the operand format of the QAT student's fused attention (qv_attn_fwd with one plane);
+//   * GELU + dynamic re-quantisation (fc1 -> fc2): GELU((q - z_y) s_y) takes at most 256 values, so its min / max and the
+//     re-quantised codes are table lookups on q.  Every table entry is computed with the expressions of the elementwise path
+//     (qv_int8_linear's dequantisation, qv_gelu_minmax, qv_quantize_u8), so the codes are bit-identical to it.
+__global__ void __launch_bounds__(256) codes_from_u8_kernel(const uint8_t* __restrict__ q, int64_t n16, int32_t zp,
+                                                            __nv_bfloat16* __restrict__ out) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n16; i += stride) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(q) + i);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c0 = static_cast<int>((w[j >> 1] >> (16 * (j & 1))) & 0xffu) - zp;
+      const int c1 = static_cast<int>((w[j >> 1] >> (16 * (j & 1) + 8)) & 0xffu) - zp;
+      const __nv_bfloat162 b = __floats2bfloat162_rn(static_cast<float>(c0), static_cast<float>(c1));
+      o[j] = *reinterpret_cast<const uint32_t*>(&b);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out) + 2 * i;
+    dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+  }
+}
+
+__device__ __forceinline__ float gelu_of_code(int c, float zyf, float sy) {
+  return qv_gelu_fwd(__fmul_rn(__fsub_rn(static_cast<float>(c), zyf), sy));       // dequantise as qv_int8_linear does, then exact-erf GELU
+}
+
+// min / max of GELU(dequant(q)) merged into acc: one table lookup per element (blockDim.x == 256 == table size)
+__global__ void __launch_bounds__(256) gelu_u8_minmax_kernel(const uint8_t* __restrict__ q, int64_t n16, float sy, int32_t zy, uint32_t* acc) {
+  __shared__ float lut[256];
+  lut[threadIdx.x] = gelu_of_code(threadIdx.x, static_cast<float>(zy), sy);
+  __syncthreads();
+  float mn = INFINITY, mx = -INFINITY;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n16; i += stride) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(q) + i);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float g = lut[(w[j >> 2] >> (8 * (j & 3))) & 0xffu];
+      mn = fminf(mn, g);
+      mx = fmaxf(mx, g);
+    }
+  }
+  mn = qv_warp_min(mn);
+  mx = qv_warp_max(mx);
+  if ((threadIdx.x & 31) == 0 && mn <= mx) {
+    atomicMin(acc, qv_f2ord(mn));
+    atomicMax(acc + 1, qv_f2ord(mx));
+  }
+}
+
+// out = quantize_u8(GELU(dequant(q))) with the dynamic qparams of the finished accumulator: a 256-byte code -> code table
+__global__ void __launch_bounds__(256) gelu_u8_requant_kernel(const uint8_t* __restrict__ q, int64_t n16, float sy, int32_t zy,
+                                                              const uint32_t* acc, float* scale_out, int32_t* zp_out,
+                                                              uint8_t* __restrict__ out) {
+  __shared__ uint8_t lut[256];
+  float s, z;
+  qparams_affine(acc, 0, 255, s, z);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *scale_out = s;
+    *zp_out = static_cast<int32_t>(z);
+  }
+  {
+    const float inv = __fdiv_rn(1.0f, s);
+    float f = __fadd_rn(nearbyintf(__fmul_rn(gelu_of_code(threadIdx.x, static_cast<float>(zy), sy), inv)), z);
+    f = fminf(fmaxf(f, 0.0f), 255.0f);
+    lut[threadIdx.x] = static_cast<uint8_t>(f);
+  }
+  __syncthreads();
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n16; i += stride) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(q) + i);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint32_t r = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r |= static_cast<uint32_t>(lut[(w[k] >> (8 * j)) & 0xffu]) << (8 * j);
+      o[k] = r;
+    }
+    reinterpret_cast<uint4*>(out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
 }
 
 }  // namespace
@@ -459,4 +590,50 @@ extern "C" int qv_qparams_from_minmax(const uint32_t* acc, int32_t qmin, int32_t
   QV_REQUIRE(qv_num_sms() > 0, QV_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
   qparams_from_minmax_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(acc, qmin, qmax, scale, zero_point);
   return qv_check_launch("qv_qparams_from_minmax");
+}
+
+static int i8_ew_blocks(int64_t items) {
+  int64_t blocks = (items + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(qv_num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+extern "C" int qv_quantize_u8_dyn(const float* x, int64_t n, const uint32_t* acc, float* scale_out, int32_t* zero_point_out,
+                                  uint8_t* q, void* stream) {
+  QV_REQUIRE(x && acc && scale_out && zero_point_out && q && n > 0, QV_ERR_INVALID, "bad quantize_u8_dyn arguments");
+  QV_REQUIRE(qv_aligned16(x) && (reinterpret_cast<uintptr_t>(q) & 3u) == 0, QV_ERR_INVALID, "quantize_u8_dyn needs aligned buffers");
+  QV_REQUIRE(qv_num_sms() > 0, QV_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  quantize_u8_dyn_kernel<<<i8_ew_blocks(n >> 2), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, acc, scale_out, zero_point_out, q);
+  return qv_check_launch("qv_quantize_u8_dyn");
+}
+
+extern "C" int qv_codes_from_u8(const uint8_t* q, int64_t n, int32_t zero_point, uint16_t* codes, void* stream) {
+  QV_REQUIRE(q && codes && n > 0 && n % 16 == 0, QV_ERR_INVALID, "bad codes_from_u8 arguments (n must be a multiple of 16)");
+  QV_REQUIRE(zero_point >= 0 && zero_point <= 255, QV_ERR_INVALID, "codes_from_u8: quint8 zero point out of range");
+  QV_REQUIRE(qv_aligned16(q) && qv_aligned16(codes), QV_ERR_INVALID, "codes_from_u8 needs 16-byte aligned buffers");
+  QV_REQUIRE(qv_num_sms() > 0, QV_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  codes_from_u8_kernel<<<i8_ew_blocks(n >> 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      q, n >> 4, zero_point, reinterpret_cast<__nv_bfloat16*>(codes));
+  return qv_check_launch("qv_codes_from_u8");
+}
+
+extern "C" int qv_gelu_u8_minmax(const uint8_t* q, int64_t n, float sy, int32_t zy, uint32_t* acc, void* stream) {
+  QV_REQUIRE(q && acc && n > 0 && n % 16 == 0 && sy > 0.f, QV_ERR_INVALID, "bad gelu_u8_minmax arguments (n must be a multiple of 16)");
+  QV_REQUIRE(qv_aligned16(q), QV_ERR_INVALID, "gelu_u8_minmax needs a 16-byte aligned buffer");
+  QV_REQUIRE(qv_num_sms() > 0, QV_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  gelu_u8_minmax_kernel<<<i8_ew_blocks(n >> 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(q, n >> 4, sy, zy, acc);
+  return qv_check_launch("qv_gelu_u8_minmax");
+}
+
+extern "C" int qv_gelu_u8_requant(const uint8_t* q, int64_t n, float sy, int32_t zy, const uint32_t* acc, float* scale_out,
+                                  int32_t* zero_point_out, uint8_t* out, void* stream) {
+  QV_REQUIRE(q && acc && scale_out && zero_point_out && out && n > 0 && n % 16 == 0 && sy > 0.f, QV_ERR_INVALID,
+             "bad gelu_u8_requant arguments (n must be a multiple of 16)");
+  QV_REQUIRE(qv_aligned16(q) && qv_aligned16(out), QV_ERR_INVALID, "gelu_u8_requant needs 16-byte aligned buffers");
+  QV_REQUIRE(qv_num_sms() > 0, QV_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  gelu_u8_requant_kernel<<<i8_ew_blocks(n >> 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(q, n >> 4, sy, zy, acc, scale_out,
+                                                                                           zero_point_out, out);
+  return qv_check_launch("qv_gelu_u8_requant");
 }

@@ -10,6 +10,15 @@ SURVEY.md §0.9), so the glue between the quantized modules is OURS, defined in 
 stock ops by oracle/int8_ref.py: a quantized module whose producer is quantized (patch-embed conv <- QuantStub) consumes
 its codes directly; every other quantized module quantises its fp32 input per tensor with DYNAMIC affine quint8 qparams
 (min / max of the batch, Python-observer formula); cls / pos-embed / LayerNorm / attention / GELU / residuals are fp32.
+
+Two realisations of that glue, same arithmetic (``ConvertedStudent(..., compact=...)``):
+  * compact (default): a converted Linear's output is (q - z_y) * s_y -- an integer code times one scale -- so where the consumer
+    can work on codes the GEMM writes its quint8 codes (1 byte / element) instead of the dequantised fp32 tensor: attention takes
+    the centred codes as ONE exact bf16 plane (the QAT student's fused attention kernel, s_y applied inside), and GELU + the
+    dynamic re-quantisation between fc1 and fc2 are 256-entry table lookups on the codes (bit-identical codes: every table entry
+    is computed with the elementwise expressions); the qparams kernel is folded into the quantising pass.
+  * ``compact=False``: every Linear writes fp32, the glue runs elementwise on fp32 tensors (the first implementation; kept as the
+    parity reference of the compact path, tests/test_int8_gpu.py).
 """
 from __future__ import annotations
 
@@ -43,6 +52,7 @@ class _QLin:
         self.wsum = w.to(torch.int32).sum(1).to(torch.int32).contiguous().to(dev)      # one-time weight prep
         self.bias = None if bias is None else bias.detach().to(torch.float32).contiguous().to(dev)
         self.sy, self.zy = float(scale), int(zero_point)
+        self.sy_dev = torch.tensor([self.sy], dtype=torch.float32, device=dev)          # for kernels that take the scale by pointer
 
 
 def _unpack_linear(mod) -> tuple:
@@ -119,12 +129,12 @@ class ConvertedStudent:
     ``ConvertedStudent.from_state_dict(path_or_dict, batch, device)`` reads best_converted.pth directly (no module tree)."""
 
     @classmethod
-    def from_state_dict(cls, state_dict, batch: int, device, num_heads=None, eps: float = 1e-6):
+    def from_state_dict(cls, state_dict, batch: int, device, num_heads=None, eps: float = 1e-6, compact: bool = True):
         if not isinstance(state_dict, dict):
             state_dict = torch.load(state_dict, map_location="cpu", weights_only=False)   # packed params are (qtensor, bias) tuples
-        return cls(_spec_from_state_dict(state_dict, num_heads, eps), batch, device)
+        return cls(_spec_from_state_dict(state_dict, num_heads, eps), batch, device, compact=compact)
 
-    def __init__(self, converted, batch: int, device):
+    def __init__(self, converted, batch: int, device, compact: bool = True):
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError("qatvit_b200: the converted executor needs a CUDA device (there is no CPU fallback)")
@@ -168,12 +178,27 @@ class ConvertedStudent:
         self.x = [e(M, D), e(M, D)]
         self.h = e(M, D)
         self.qh = e(M, D, dt=torch.uint8)
-        self.qkv = e(M, 3 * D)
-        self.qkvp = e(2, M, 3 * D, dt=torch.bfloat16)
+        # the code-plane attention kernel is specialised for 64-wide heads; the table kernels move 16 codes per thread
+        # compact: True / False, or "attn" / "gelu" for one half only ("gelu" is bit-identical to False: the parity reference).
+        # The table kernels move 16 codes per thread.
+        if compact not in (True, False, "attn", "gelu"):
+            raise ValueError("compact must be True, False, 'attn' or 'gelu'")
+        self.c_attn = compact in (True, "attn") and (M * 3 * D) % 16 == 0
+        self.c_gelu = compact in (True, "gelu") and (M * F) % 16 == 0
+        self.compact = self.c_attn and self.c_gelu
+        if self.c_attn:
+            self.q_qkv = e(M, 3 * D, dt=torch.uint8)
+            self.qkv_codes = e(1, M, 3 * D, dt=torch.bfloat16)
+        else:
+            self.qkv = e(M, 3 * D)
+            self.qkvp = e(2, M, 3 * D, dt=torch.bfloat16)
+        if self.c_gelu:
+            self.q_f = e(M, F, dt=torch.uint8)
+        else:
+            self.f = e(M, F)
+            self.g = e(M, F)
         self.o = e(M, D)
         self.y = e(M, D)
-        self.f = e(M, F)
-        self.g = e(M, F)
         self.qg = e(M, F, dt=torch.uint8)
         self.xn = e(B, D)
         self.qxn = e(B, D, dt=torch.uint8)
@@ -189,12 +214,15 @@ class ConvertedStudent:
         if not have_minmax:
             ops.minmax_accumulate(x, acc)
         s, z = self.dyn_scale[slot:slot + 1], self.dyn_zp[slot:slot + 1]
-        ops.qparams_from_minmax(acc, 0, 255, s, z)
-        ops.quantize_u8(x, s, z, out)
+        if self.c_gelu:
+            ops.quantize_u8_dyn(x, acc, s, z, out)             # qparams from the finished accumulator + codes, one launch
+        else:
+            ops.qparams_from_minmax(acc, 0, 255, s, z)
+            ops.quantize_u8(x, s, z, out)
         return s, z
 
-    def _lin(self, ql: _QLin, qx, sx, zx, y):
-        ops.int8_linear(qx, sx, zx, ql.qw, ql.sw, ql.wsum, ql.bias, ql.sy, ql.zy, y=y)
+    def _lin(self, ql: _QLin, qx, sx, zx, y=None, qy=None):
+        ops.int8_linear(qx, sx, zx, ql.qw, ql.sw, ql.wsum, ql.bias, ql.sy, ql.zy, y=y, qy=qy)
 
     @torch.no_grad()
     def forward(self, images: torch.Tensor, trace=None) -> torch.Tensor:
@@ -221,9 +249,16 @@ class ConvertedStudent:
             s, z = self._dyn_quant(slot, self.h, self.qh, have_minmax=True); slot += 1
             if trace is not None:
                 trace[f"blocks.{li}.attn.qkv"] = (self.qh.clone(), s.clone(), z.clone())
-            self._lin(blk["qkv"], self.qh, s, z, self.qkv)
-            ops.split_planes(self.qkv, self.qkvp)
-            ops.attn_fwd(self.qkvp, B, T, H, self.attn_scale, None, out_f32=self.o)
+            if self.c_attn:
+                # q, k, v = (codes - z_y) * s_y: the centred codes are one exact bf16 plane, s_y is applied by the attention kernel
+                ql = blk["qkv"]
+                self._lin(ql, self.qh, s, z, qy=self.q_qkv)
+                ops.codes_from_u8(self.q_qkv, ql.zy, self.qkv_codes)
+                ops.attn_fwd(self.qkv_codes, B, T, H, self.attn_scale, None, qk_scale=ql.sy_dev, v_scale=ql.sy_dev, out_f32=self.o)
+            else:
+                self._lin(blk["qkv"], self.qh, s, z, self.qkv)
+                ops.split_planes(self.qkv, self.qkvp)
+                ops.attn_fwd(self.qkvp, B, T, H, self.attn_scale, None, out_f32=self.o)
             s, z = self._dyn_quant(slot, self.o, self.qh); slot += 1
             self._lin(blk["proj"], self.qh, s, z, self.y)
             g, b = blk["n2"]
@@ -231,9 +266,20 @@ class ConvertedStudent:
                              minmax=self.acc[slot])
             cur ^= 1
             s, z = self._dyn_quant(slot, self.h, self.qh, have_minmax=True); slot += 1
-            self._lin(blk["fc1"], self.qh, s, z, self.f)
-            ops.gelu_minmax(self.f, self.g, self.acc[slot])
-            s, z = self._dyn_quant(slot, self.g, self.qg, have_minmax=True); slot += 1
+            if self.c_gelu:
+                # GELU((q - z_y) s_y) takes <= 256 values: min / max and the re-quantised codes are table lookups on fc1's codes
+                ql = blk["fc1"]
+                self._lin(ql, self.qh, s, z, qy=self.q_f)
+                ops.gelu_u8_minmax(self.q_f, ql.sy, ql.zy, self.acc[slot])
+                s, z = self.dyn_scale[slot:slot + 1], self.dyn_zp[slot:slot + 1]
+                ops.gelu_u8_requant(self.q_f, ql.sy, ql.zy, self.acc[slot], s, z, self.qg)
+                slot += 1
+            else:
+                self._lin(blk["fc1"], self.qh, s, z, self.f)
+                ops.gelu_minmax(self.f, self.g, self.acc[slot])
+                s, z = self._dyn_quant(slot, self.g, self.qg, have_minmax=True); slot += 1
+            if trace is not None:
+                trace[f"blocks.{li}.mlp.fc2"] = (self.qg.clone(), s.clone(), z.clone())
             self._lin(blk["fc2"], self.qg, s, z, self.y)
             y_prev = self.y
         g, b = self.norm

@@ -578,6 +578,33 @@ def gelu_minmax(x, y, acc=None):
                                     _stream()), "gelu_minmax")
 
 
+def quantize_u8_dyn(x, acc, scale_out, zero_point_out, out):
+    """qparams_from_minmax(acc, 0, 255) + quantize_u8 in one launch; the qparams land in scale_out / zero_point_out."""
+    check(_lib.lib().qv_quantize_u8_dyn(_p(x, torch.float32, "x"), x.numel(), _p(acc, torch.int32, "acc"),
+                                        _p(scale_out, torch.float32, "scale_out"), _p(zero_point_out, torch.int32, "zero_point_out"),
+                                        _p(out, torch.uint8, "out"), _stream()), "quantize_u8_dyn")
+    return out
+
+
+def codes_from_u8(q, zero_point, codes):
+    """codes = bf16(q - zero_point): a converted Linear's quint8 output as the one-plane integer operand of attn_fwd."""
+    check(_lib.lib().qv_codes_from_u8(_p(q, torch.uint8, "q"), q.numel(), int(zero_point), _p(codes, torch.bfloat16, "codes"),
+                                      _stream()), "codes_from_u8")
+    return codes
+
+
+def gelu_u8_minmax(q, sy, zy, acc):
+    check(_lib.lib().qv_gelu_u8_minmax(_p(q, torch.uint8, "q"), q.numel(), float(sy), int(zy), _p(acc, torch.int32, "acc"),
+                                       _stream()), "gelu_u8_minmax")
+
+
+def gelu_u8_requant(q, sy, zy, acc, scale_out, zero_point_out, out):
+    check(_lib.lib().qv_gelu_u8_requant(_p(q, torch.uint8, "q"), q.numel(), float(sy), int(zy), _p(acc, torch.int32, "acc"),
+                                        _p(scale_out, torch.float32, "scale_out"), _p(zero_point_out, torch.int32, "zero_point_out"),
+                                        _p(out, torch.uint8, "out"), _stream()), "gelu_u8_requant")
+    return out
+
+
 def head_fwd(x, wq, bias, B, K, N, out, minmax=None):
     check(_lib.lib().qv_head_fwd(_p(x, torch.float32), _p(wq, torch.float32), _p(bias, torch.float32), B, K, N,
                                  _p(out, torch.float32), _p(minmax, torch.int32), _stream()), "head_fwd")
@@ -659,7 +686,8 @@ def _wrap(name, fn, tag_fn=None):
 for _nm in ("zero_", "minmax_reset", "minmax_accumulate", "obs_update", "fq_apply", "fq_weight", "fq_weight_grouped", "fq_bwd", "fq_learnable_fwd", "fq_learnable_bwd", "split_planes",
            "kd_ce_loss", "splitk_reduce", "colsum_reduce", "colsum_rows",
            "embed_fwd", "im2col_fq", "softmax_planes", "attn_ds", "head_fwd", "head_bwd", "attn_fwd", "attn_bwd", "attn_bwd_gp",
-           "int8_linear", "quantize_u8", "qparams_from_minmax", "im2col_u8", "gelu_minmax"):
+           "int8_linear", "quantize_u8", "qparams_from_minmax", "im2col_u8", "gelu_minmax", "quantize_u8_dyn", "codes_from_u8",
+           "gelu_u8_minmax", "gelu_u8_requant"):
     globals()[_nm] = _wrap(_nm, globals()[_nm])
 gemm = _wrap("gemm", gemm, _gemm_tag)
 act_planes = _wrap("act_planes", act_planes, _bytes_act_planes)

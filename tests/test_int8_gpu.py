@@ -87,6 +87,71 @@ def test_quantize_and_dynamic_qparams(cuda_dev, shape):
     q = ops.quantize_u8(xd, s, zp)
     ref = torch.quantize_per_tensor(x, s_ref, z_ref, torch.quint8).int_repr()
     assert torch.equal(q.cpu(), ref)
+    # the one-launch form (qparams from the accumulator + codes): same qparams, same codes
+    s2 = torch.empty(1, device=cuda_dev)
+    zp2 = torch.empty(1, dtype=torch.int32, device=cuda_dev)
+    q2 = ops.quantize_u8_dyn(xd, acc[0], s2, zp2, torch.empty(shape, dtype=torch.uint8, device=cuda_dev))
+    assert torch.equal(s2, s) and torch.equal(zp2, zp) and torch.equal(q2, q)
+
+
+@pytest.mark.parametrize("M,N,sy,zy", [(197 * 4, 1536, 0.0471, 117), (197 * 2, 1152, 0.31, 0), (64, 64, 1e-3, 255), (48, 16, 0.02, 64)])
+def test_compact_glue_on_codes_is_bit_identical_to_the_fp32_glue(cuda_dev, M, N, sy, zy):
+    """A converted Linear's output is (q - zy) * sy.  The compact glue works on q: centred codes for attention, table lookups
+    for GELU + dynamic re-quantisation.  Against the elementwise fp32 chain on the dequantised tensor (the values qv_int8_linear
+    writes as y, pinned to ref.dequantize() above): identical min / max, qparams and codes, bit for bit."""
+    from qatvit_b200 import ops
+    g = torch.Generator().manual_seed(M + N)
+    q = torch.randint(0, 256, (M, N), generator=g, dtype=torch.int32).to(torch.uint8)
+    q[0, :4] = torch.tensor([0, 255, zy, max(zy - 1, 0)], dtype=torch.uint8)         # the extreme codes are present
+    qd = q.to(cuda_dev)
+    y = ((qd.float() - float(zy)) * torch.tensor(sy, dtype=torch.float32, device=cuda_dev)).contiguous()   # = qv_int8_linear's y
+    # attention operand: one exact bf16 plane of centred codes, codes * sy == y
+    codes = ops.codes_from_u8(qd, zy, torch.empty(M, N, dtype=torch.bfloat16, device=cuda_dev))
+    assert torch.equal(codes.float(), qd.float() - float(zy))
+    assert torch.equal(codes.float() * torch.tensor(sy, dtype=torch.float32, device=cuda_dev), y)
+    # GELU + min / max + dynamic re-quantisation: fp32 chain ...
+    acc_a = ops.new_minmax(cuda_dev)
+    gy = torch.empty_like(y)
+    ops.gelu_minmax(y, gy, acc_a[0])
+    s_a = torch.empty(1, device=cuda_dev)
+    z_a = torch.empty(1, dtype=torch.int32, device=cuda_dev)
+    ops.qparams_from_minmax(acc_a[0], 0, 255, s_a, z_a)
+    q_a = ops.quantize_u8(gy, s_a, z_a)
+    # ... vs the tables on the codes
+    acc_b = ops.new_minmax(cuda_dev)
+    ops.gelu_u8_minmax(qd, sy, zy, acc_b[0])
+    s_b = torch.empty(1, device=cuda_dev)
+    z_b = torch.empty(1, dtype=torch.int32, device=cuda_dev)
+    q_b = ops.gelu_u8_requant(qd, sy, zy, acc_b[0], s_b, z_b, torch.empty(M, N, dtype=torch.uint8, device=cuda_dev))
+    torch.cuda.synchronize()
+    assert torch.equal(acc_a, acc_b)
+    assert torch.equal(s_a, s_b) and torch.equal(z_a, z_b)
+    assert torch.equal(q_a, q_b)
+    # and against torch on the CPU: GELU(erf) of the dequantised tensor, Python-observer qparams, quantize_per_tensor
+    # (CPU and GPU erf differ in the last bit on a few values, which can move a code by one)
+    from oracle import int8_ref
+    g_cpu = torch.nn.functional.gelu(y.cpu())
+    s_ref, z_ref = int8_ref.dynamic_qparams(g_cpu)
+    assert abs(float(s_b) - s_ref) <= 1e-6 * s_ref and int(z_b) == z_ref
+    d = (q_b.cpu().int() - torch.quantize_per_tensor(g_cpu, s_ref, z_ref, torch.quint8).int_repr().int()).abs()
+    assert int(d.max()) <= 1 and float((d > 0).float().mean()) < 1e-2
+
+
+def test_compact_glue_rejects_bad_arguments(cuda_dev):
+    from qatvit_b200 import ops
+    q = torch.zeros(3, 5, dtype=torch.uint8, device=cuda_dev)                  # 15 codes: not a multiple of 16
+    acc = ops.new_minmax(cuda_dev)
+    with pytest.raises(RuntimeError, match="multiple of 16"):
+        ops.codes_from_u8(q, 0, torch.empty(3, 5, dtype=torch.bfloat16, device=cuda_dev))
+    with pytest.raises(RuntimeError, match="multiple of 16"):
+        ops.gelu_u8_minmax(q, 0.1, 0, acc[0])
+    q16 = torch.zeros(4, 4, dtype=torch.uint8, device=cuda_dev)
+    with pytest.raises(RuntimeError, match="zero point"):
+        ops.codes_from_u8(q16, 256, torch.empty(4, 4, dtype=torch.bfloat16, device=cuda_dev))
+    with pytest.raises(RuntimeError):
+        ops.gelu_u8_minmax(q16, 0.0, 0, acc[0])                                # scale must be positive
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.codes_from_u8(q16.cpu(), 0, torch.empty(4, 4, dtype=torch.bfloat16, device=cuda_dev))
 
 
 def _converted(backend, sname, tname, img, B):
@@ -102,16 +167,18 @@ def _converted(backend, sname, tname, img, B):
     return conv, images
 
 
-@pytest.mark.parametrize("backend,sname,img,B", [("fbgemm", "vit_test_tiny", 64, 4), ("qnnpack", "vit_test_tiny", 64, 3),
-                                                 ("fbgemm", "vit_small_patch16_224", 224, 2)])
-def test_converted_student_per_layer_and_end_to_end(cuda_dev, backend, sname, img, B):
+@pytest.mark.parametrize("backend,sname,img,B,compact", [("fbgemm", "vit_test_tiny", 64, 4, True), ("qnnpack", "vit_test_tiny", 64, 3, True),
+                                                         ("fbgemm", "vit_small_patch16_224", 224, 2, True),
+                                                         ("fbgemm", "vit_test_tiny", 64, 4, False), ("qnnpack", "vit_test_tiny", 64, 3, "attn")])
+def test_converted_student_per_layer_and_end_to_end(cuda_dev, backend, sname, img, B, compact):
     from qatvit_b200 import ops
     from qatvit_b200.int8 import ConvertedStudent
     from oracle import int8_ref
     conv, images = _converted(backend, sname, "vit_test_teacher", img, B)
     trace = {}
     ref_logits = int8_ref.converted_forward(conv, images, trace)
-    ex = ConvertedStudent(conv, B, cuda_dev)
+    ex = ConvertedStudent(conv, B, cuda_dev, compact=compact)
+    assert (ex.c_attn, ex.c_gelu) == (compact in (True, "attn"), compact in (True, "gelu"))
     # tier 1: every quantized module, on the CPU run's own quint8 input, gives bit-identical codes
     qlins = {"head": ex.head}
     for i, blk in enumerate(ex.blocks):
@@ -148,6 +215,36 @@ def test_converted_student_per_layer_and_end_to_end(cuda_dev, backend, sname, im
     diff = logits.cpu() - ref_logits
     assert float(diff.abs().max()) <= 6.0 * step + 1e-6
     assert float(diff.norm() / ref_logits.norm()) < 8e-2
+
+
+def test_compact_glue_end_to_end_against_the_fp32_glue(cuda_dev):
+    """The same converted student through the two realisations of the float glue.  The table half (GELU + re-quantisation on
+    fc1's codes, qparams folded into the quantising pass) must reproduce the fp32 glue BIT FOR BIT, logits included; the
+    attention half computes softmax(QK^T)V from exact integer codes instead of fp32 hi/lo planes of the dequantised values
+    (products exact instead of ~2^-16 relative), so block 0's fc2 input may differ by a code on a few elements and the logits by
+    a few head quantisation steps -- the bound the CPU mirror is held to."""
+    from qatvit_b200.int8 import ConvertedStudent
+    conv, images = _converted("fbgemm", "vit_test_tiny", "vit_test_teacher", 64, 4)
+    x = images.to(cuda_dev)
+    runs = {}
+    for mode in (False, "gelu", True):
+        ex = ConvertedStudent(conv, 4, cuda_dev, compact=mode)
+        tr = {}
+        runs[mode] = (ex(x, tr).clone(), tr)
+    torch.cuda.synchronize()
+    base, tables, full = runs[False], runs["gelu"], runs[True]
+    assert torch.equal(base[0], tables[0])
+    for k in base[1]:
+        for a, b in zip(base[1][k], tables[1][k]):
+            assert torch.equal(a, b), k
+    qa, sa, za = base[1]["blocks.0.mlp.fc2"]
+    qb, sb, zb = full[1]["blocks.0.mlp.fc2"]
+    assert abs(float(sa) - float(sb)) <= 1e-5 * float(sa) and abs(int(za) - int(zb)) <= 1
+    d = (qa.int() - qb.int()).abs()
+    assert int(d.max()) <= 1 and float((d > 0).float().mean()) < 1e-2
+    step = conv.model.head.scale
+    diff = (full[0] - base[0]).cpu()
+    assert torch.isfinite(full[0]).all() and float(diff.abs().max()) <= 6.0 * step + 1e-6
 
 
 def test_best_converted_pth_reader_runs_identically(cuda_dev, tmp_path):
