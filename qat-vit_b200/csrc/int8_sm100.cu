@@ -30,16 +30,29 @@ constexpr int I8_BM = 128;
 constexpr int I8_BK = 128;          // 128 int8 = one 128-byte swizzle row
 constexpr int I8_UMMA_K = 32;
 constexpr int I8_THREADS = 320;        // TMA warp, MMA warp, 8 requantising warps (two per TMEM lane quarter)
-constexpr int I8_STAGE_OUT_BYTES = 8 * (4096 + 1024);   // per epilogue warp: 32 x 32 fp32 (128B swizzle) + 32 x 32 uint8 output staging
+// Output staging per epilogue warp: 8 KB.  One output kind requested (what the executor does): TWO buffers -- 2 x (32 x 32 fp32,
+// 128B swizzle) or 2 x (32 x 32 uint8) -- used alternately, so a chunk's staging writes never wait for the TMA store of the chunk
+// before it (with ONE buffer every chunk stalled for the full latency of the previous store: ~1.5 us per chunk, the tile time).
+// Both kinds requested: [fp32 4 KB][uint8 1 KB], single-buffered.
+constexpr int I8_STAGE_WARP_BYTES = 8192;
+constexpr int I8_STAGE_OUT_BYTES = 8 * I8_STAGE_WARP_BYTES;
 constexpr int I8_TERM_BYTES = 8 * 3 * 32 * 4;   // per epilogue warp: [add int32 x 32][bias term x 32][multiplier x 32] of the chunk's columns
+// The per-column requantisation terms depend on the column alone: for N <= I8_TABLE_N they are computed ONCE per CTA into a
+// shared-memory table when the kernel starts ([add][bias term][multiplier], each padded to a whole last tile), instead of once per
+// 32-column chunk of every tile (three dependent global loads and two IEEE divides on the critical path of a chunk whose tile has
+// only 12 MMAs in front of it).
+constexpr int I8_TABLE_N = 2048;
+constexpr int I8_TABLE_LEN = I8_TABLE_N + 128;
+constexpr int I8_TABLE_BYTES = 3 * I8_TABLE_LEN * 4;
 constexpr int I8_A_BYTES = I8_BM * I8_BK;
 
 template <int BN>
 struct I8Cfg {
   static constexpr int B_BYTES = BN * I8_BK;
   static constexpr int STAGE_BYTES = I8_A_BYTES + B_BYTES;
-  static constexpr int STAGES = 5;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + I8_STAGE_OUT_BYTES + I8_TERM_BYTES + 1024 + 256;
+  static constexpr int STAGES = 4;        // a K = 384 tile is 3 k-blocks, K = 1536 twelve: four 32 KB stages keep the producer ahead
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + I8_STAGE_OUT_BYTES + I8_TERM_BYTES + I8_TABLE_BYTES + 1024 + 256;
+  static_assert(SMEM_BYTES <= 232448, "int8 linear: shared memory over the 227 KB limit");
   static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : 256;
 };
 
@@ -87,7 +100,9 @@ __device__ __forceinline__ void tma_store_2d(const void* map, const void* smem_s
                : "memory");
 }
 
-template <int BN>
+// WANT_Y: the dequantised fp32 output is requested (codes optional); otherwise codes only -- the shape the compact executor uses
+// for qkv and fc1, with the rounding / clamp / pack done in the integer domain (no float -> int conversions on the XU pipe).
+template <int BN, bool WANT_Y>
 __global__ void __launch_bounds__(I8_THREADS, 1)
 qv_int8_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                       const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_q, const I8Params p) {
@@ -96,7 +111,10 @@ qv_int8_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_out = smem + C::STAGES * C::STAGE_BYTES;          // 1 KB aligned: STAGE_BYTES is a multiple of 1024
   uint8_t* smem_terms = smem_out + I8_STAGE_OUT_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_terms + I8_TERM_BYTES);
+  int32_t* tab_add = reinterpret_cast<int32_t*>(smem_terms + I8_TERM_BYTES);
+  float* tab_badd = reinterpret_cast<float*>(tab_add + I8_TABLE_LEN);
+  float* tab_mult = tab_badd + I8_TABLE_LEN;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_terms + I8_TERM_BYTES + I8_TABLE_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + C::STAGES;
   uint64_t* tmem_full = bars + 2 * C::STAGES;
@@ -114,6 +132,30 @@ qv_int8_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  const bool use_table = p.N <= I8_TABLE_N;
+  if (use_table) {
+    const float sx = __ldg(p.sx);
+    const int32_t zx = __ldg(p.zx);
+    const int n_pad = p.tiles_n * BN;                 // <= N + BN - 1 <= I8_TABLE_LEN
+    for (int n = threadIdx.x; n < n_pad; n += I8_THREADS) {
+      int32_t my_add = 0;          // - z_x * sum_k q_w  (+ rint(b / (s_x s_w)) in qnnpack mode)
+      float my_badd = 0.f;         // b / (s_x s_w)  (x86 / fbgemm mode)
+      float my_mult = 0.f;         // s_x s_w / s_y
+      if (n < p.N) {
+        const float bs = __fmul_rn(sx, __ldg(p.sw + (p.per_channel ? n : 0)));
+        my_mult = __fdiv_rn(bs, p.sy);
+        my_add = -zx * __ldg(p.wsum + n);
+        if (p.bias) {
+          const float bq = __fdiv_rn(__ldg(p.bias + n), bs);
+          if (p.bias_int) my_add += static_cast<int32_t>(nearbyintf(bq));
+          else my_badd = bq;
+        }
+      }
+      tab_add[n] = my_add;
+      tab_badd[n] = my_badd;
+      tab_mult[n] = my_mult;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -185,9 +227,11 @@ qv_int8_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     float* t_mult = t_badd + 32;
     // Row-per-lane registers written straight to global memory touch 32 different lines per store instruction (one 16-byte
     // piece of a sector each: the LSU, not HBM, bounded the kernel): outputs go through swizzled staging and leave as TMA boxes.
-    uint8_t* st_y = smem_out + ew * (4096 + 1024);
-    uint8_t* st_q = st_y + 4096;
+    uint8_t* st_base = smem_out + ew * I8_STAGE_WARP_BYTES;
     const bool any_tma = p.tma_y || p.tma_q;
+    const int32_t code_bias = p.zy - 0x4B400000;                      // (v + 1.5 * 2^23) as an integer -> rint(v) + z_y
+    const bool st_both = WANT_Y && (p.tma_y && p.y) && (p.tma_q && p.qy);       // both kinds staged: one buffer each, single-buffered
+    uint32_t st_ctr = 0;                                              // chunks this warp has staged so far
     int local = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
       const int n_blk = item % p.tiles_n, m_blk = item / p.tiles_n;
@@ -201,8 +245,12 @@ qv_int8_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN + c0), r);
         const int64_t n0 = static_cast<int64_t>(n_blk) * BN + c0;
-        // per-column terms while the TMEM load is in flight: lane j owns column n0 + j
-        {
+        // per-column terms: from the CTA's table, or (N > I8_TABLE_N) computed while the TMEM load is in flight: lane j owns column n0 + j
+        const int32_t* c_add = tab_add + n0;
+        const float* c_badd = tab_badd + n0;
+        const float* c_mult = tab_mult + n0;
+        if (!use_table) {
+          c_add = t_add; c_badd = t_badd; c_mult = t_mult;
           int32_t my_add = 0;          // - z_x * sum_k q_w  (+ rint(b / (s_x s_w)) in qnnpack mode)
           float my_badd = 0.f;         // b / (s_x s_w)  (x86 / fbgemm mode)
           float my_mult = 0.f;         // s_x s_w / s_y
@@ -234,35 +282,57 @@ qv_int8_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         float deq[32];
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-          const int4 a4 = *reinterpret_cast<const int4*>(t_add + 4 * j4);
-          const float4 b4 = *reinterpret_cast<const float4*>(t_badd + 4 * j4);
-          const float4 m4 = *reinterpret_cast<const float4*>(t_mult + 4 * j4);
+          const int4 a4 = *reinterpret_cast<const int4*>(c_add + 4 * j4);
+          const float4 b4 = *reinterpret_cast<const float4*>(c_badd + 4 * j4);
+          const float4 m4 = *reinterpret_cast<const float4*>(c_mult + 4 * j4);
           const int32_t aj[4] = {a4.x, a4.y, a4.z, a4.w};
           const float bj[4] = {b4.x, b4.y, b4.z, b4.w};
           const float mj[4] = {m4.x, m4.y, m4.z, m4.w};
           uint32_t w = 0;
+          if constexpr (WANT_Y) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int32_t acc = static_cast<int32_t>(r[4 * j4 + e]) + aj[e];
-            const float v = __fmul_rn(__fadd_rn(static_cast<float>(acc), bj[e]), mj[e]);
-            float f = __fsub_rn(__fadd_rn(v, 12582912.0f), rint_c);
-            f = fminf(fmaxf(f, 0.0f), 255.0f);
-            w |= static_cast<uint32_t>(f) << (8 * e);
-            deq[4 * j4 + e] = __fmul_rn(__fsub_rn(f, zyf), p.sy);
+            for (int e = 0; e < 4; ++e) {
+              const int32_t acc = static_cast<int32_t>(r[4 * j4 + e]) + aj[e];
+              const float v = __fmul_rn(__fadd_rn(static_cast<float>(acc), bj[e]), mj[e]);
+              float f = __fsub_rn(__fadd_rn(v, 12582912.0f), rint_c);
+              f = fminf(fmaxf(f, 0.0f), 255.0f);
+              w |= static_cast<uint32_t>(f) << (8 * e);
+              deq[4 * j4 + e] = __fmul_rn(__fsub_rn(f, zyf), p.sy);
+            }
+          } else {
+            // codes only: v + 1.5 * 2^23 holds rint(v) in its low mantissa bits (round-to-nearest-even, |v| < 2^22); the float's bit
+            // pattern is monotonic in v beyond that range too, so  bits - 0x4B400000 + z_y  clamped to [0, 255] as an INTEGER gives
+            // the same code as the float route above for every finite v; four clamped codes are gathered with byte permutes
+            int32_t c[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int32_t acc = static_cast<int32_t>(r[4 * j4 + e]) + aj[e];
+              const float v = __fmul_rn(__fadd_rn(static_cast<float>(acc), bj[e]), mj[e]);
+              const int32_t i = __float_as_int(__fadd_rn(v, 12582912.0f)) + code_bias;
+              c[e] = min(max(i, 0), 255);
+            }
+            w = __byte_perm(__byte_perm(c[0], c[1], 0x0040), __byte_perm(c[2], c[3], 0x0040), 0x5410);
           }
           packed[j4] = w;
         }
         const int row0 = m_blk * I8_BM + q * 32;
         if (static_cast<int64_t>(row0) >= p.M) continue;          // warp-uniform: the whole slab is padding
         if (any_tma) {
-          if (lane == 0) tma_store_wait_read<0>();                // the previous chunk's boxes have left the staging buffers
+          const uint32_t sb = st_both ? 0u : (st_ctr & 1u);
+          uint8_t* st_y = st_base + sb * 4096;
+          uint8_t* st_q = st_both ? st_base + 4096 : st_base + sb * 1024;
+          ++st_ctr;
+          if (lane == 0) {                                        // bulk groups retire in order: with two buffers the store of the
+            if (st_both) tma_store_wait_read<0>();                // chunk BEFORE the previous one has left the buffer reused now
+            else tma_store_wait_read<1>();
+          }
           __syncwarp();
           if (p.tma_q && p.qy) {                                  // 32 rows x 32 bytes, linear
             const uint32_t a = smem_u32(st_q) + lane * 32;
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(packed[0]), "r"(packed[1]), "r"(packed[2]), "r"(packed[3]) : "memory");
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + 16), "r"(packed[4]), "r"(packed[5]), "r"(packed[6]), "r"(packed[7]) : "memory");
           }
-          if (p.tma_y && p.y) {                                   // 32 rows x 128 bytes, 16-byte chunk j of row r at j ^ (r & 7)
+          if (WANT_Y && p.tma_y && p.y) {                         // 32 rows x 128 bytes, 16-byte chunk j of row r at j ^ (r & 7)
             const uint32_t a = smem_u32(st_y) + lane * 128;
 #pragma unroll
             for (int j = 0; j < 8; ++j)
@@ -273,7 +343,7 @@ qv_int8_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           __syncwarp();
           if (lane == 0) {
             if (p.tma_q && p.qy) tma_store_2d(&map_q, st_q, static_cast<int>(n0), row0);
-            if (p.tma_y && p.y) tma_store_3d(&map_y, st_y, static_cast<int>(n0), row0, 0);
+            if (WANT_Y && p.tma_y && p.y) tma_store_3d(&map_y, st_y, static_cast<int>(n0), row0, 0);
             tma_store_commit();
           }
         }
@@ -289,7 +359,7 @@ qv_int8_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
               if (j < ncols) dst[j] = static_cast<uint8_t>((packed[j >> 2] >> (8 * (j & 3))) & 0xffu);
           }
         }
-        if (p.y && !p.tma_y) {
+        if (WANT_Y && p.y && !p.tma_y) {
           float* dst = p.y + row * p.N + n0;
           if (p.N % 4 == 0 && ncols == 32) {
 #pragma unroll
@@ -345,17 +415,17 @@ int make_map_q_out(CUtensorMap* m, uint8_t* ptr, int64_t rows, int64_t N) {
   return 0;
 }
 
-template <int BN>
+template <int BN, bool WANT_Y>
 int launch_i8(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& my, const CUtensorMap& mq, const I8Params& kp, int grid,
               cudaStream_t st) {
   using C = I8Cfg<BN>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(qv_int8_linear_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    attr_err = cudaFuncSetAttribute(qv_int8_linear_kernel<BN, WANT_Y>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
   });
   QV_REQUIRE(attr_err == cudaSuccess, QV_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
-  qv_int8_linear_kernel<BN><<<grid, I8_THREADS, C::SMEM_BYTES, st>>>(ma, mb, my, mq, kp);
+  qv_int8_linear_kernel<BN, WANT_Y><<<grid, I8_THREADS, C::SMEM_BYTES, st>>>(ma, mb, my, mq, kp);
   return qv_check_launch("qv_int8_linear");
 }
 
@@ -568,8 +638,8 @@ extern "C" int qv_int8_linear(const uint8_t* qx, int64_t M, int64_t K, const flo
   const int sms = qv_num_sms();
   const int grid = static_cast<int>(items < sms ? items : sms);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (BN == 64) return launch_i8<64>(ma, mb, my, mq, kp, grid, st);
-  return launch_i8<128>(ma, mb, my, mq, kp, grid, st);
+  if (BN == 64) return y ? launch_i8<64, true>(ma, mb, my, mq, kp, grid, st) : launch_i8<64, false>(ma, mb, my, mq, kp, grid, st);
+  return y ? launch_i8<128, true>(ma, mb, my, mq, kp, grid, st) : launch_i8<128, false>(ma, mb, my, mq, kp, grid, st);
 }
 
 extern "C" int qv_quantize_u8(const float* x, int64_t n, const float* scale, const int32_t* zero_point, uint8_t* q, void* stream) {

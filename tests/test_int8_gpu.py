@@ -49,7 +49,8 @@ def test_int8_linear_golden_vectors(cuda_dev):
 
 
 @pytest.mark.parametrize("M,N,K", [(197 * 4, 1152, 384), (197 * 4, 384, 1536), (197 * 2, 1536, 384), (196 * 2, 384, 768),
-                                   (8, 10, 384), (130, 24, 96), (1, 16, 16), (300, 200, 144)])
+                                   (8, 10, 384), (130, 24, 96), (1, 16, 16), (300, 200, 144),
+                                   (200, 2304, 64)])          # N > 2048: per-chunk column terms instead of the per-CTA table
 @pytest.mark.parametrize("per_channel", [True, False])
 def test_int8_linear_vs_quantized_linear(cuda_dev, M, N, K, per_channel):
     g = torch.Generator().manual_seed(M + N + K)
