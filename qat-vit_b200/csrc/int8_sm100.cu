@@ -29,14 +29,17 @@ namespace {
 constexpr int I8_BM = 128;
 constexpr int I8_BK = 128;          // 128 int8 = one 128-byte swizzle row
 constexpr int I8_UMMA_K = 32;
-constexpr int I8_THREADS = 320;        // TMA warp, MMA warp, 8 requantising warps (two per TMEM lane quarter)
-// Output staging per epilogue warp: 8 KB.  One output kind requested (what the executor does): TWO buffers -- 2 x (32 x 32 fp32,
-// 128B swizzle) or 2 x (32 x 32 uint8) -- used alternately, so a chunk's staging writes never wait for the TMA store of the chunk
-// before it (with ONE buffer every chunk stalled for the full latency of the previous store: ~1.5 us per chunk, the tile time).
-// Both kinds requested: [fp32 4 KB][uint8 1 KB], single-buffered.
-constexpr int I8_STAGE_WARP_BYTES = 8192;
-constexpr int I8_STAGE_OUT_BYTES = 8 * I8_STAGE_WARP_BYTES;
-constexpr int I8_TERM_BYTES = 8 * 3 * 32 * 4;   // per epilogue warp: [add int32 x 32][bias term x 32][multiplier x 32] of the chunk's columns
+// TMA warp, MMA warp, 16 requantising warps: four per TMEM lane quarter (= per scheduler partition), one 32-column chunk of a
+// 128-wide tile each.  ncu on the 8-warp version: issue slots 44 % busy with stall reasons `wait` 1.5 and `long scoreboard` 1.1 per
+// issued instruction -- two warps per scheduler cannot hide the dependent-issue and TMEM / shared-memory latencies of a chunk.
+constexpr int I8_EPI_WARPS = 16;
+constexpr int I8_THREADS = 64 + 32 * I8_EPI_WARPS;
+// Output staging per epilogue warp: 4 KB = one 32 x 32 fp32 box (128B swizzle), or two alternating 32 x 32 uint8 boxes.  A warp
+// stages one chunk per tile, so the previous box has a whole tile time to leave before its buffer is written again.  When BOTH
+// output kinds are requested (tests only) the codes leave by plain stores.
+constexpr int I8_STAGE_WARP_BYTES = 4096;
+constexpr int I8_STAGE_OUT_BYTES = I8_EPI_WARPS * I8_STAGE_WARP_BYTES;
+constexpr int I8_TERM_BYTES = I8_EPI_WARPS * 3 * 32 * 4;   // per epilogue warp: [add int32 x 32][bias term x 32][multiplier x 32] of the chunk's columns
 // The per-column requantisation terms depend on the column alone: for N <= I8_TABLE_N they are computed ONCE per CTA into a
 // shared-memory table when the kernel starts ([add][bias term][multiplier], each padded to a whole last tile), instead of once per
 // 32-column chunk of every tile (three dependent global loads and two IEEE divides on the critical path of a chunk whose tile has
@@ -128,7 +131,7 @@ qv_int8_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     if (p.tma_y) prefetch_tensormap(&map_y);
     if (p.tma_q) prefetch_tensormap(&map_q);
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 256); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], I8_EPI_WARPS * 32); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
@@ -230,7 +233,6 @@ qv_int8_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     uint8_t* st_base = smem_out + ew * I8_STAGE_WARP_BYTES;
     const bool any_tma = p.tma_y || p.tma_q;
     const int32_t code_bias = p.zy - 0x4B400000;                      // (v + 1.5 * 2^23) as an integer -> rint(v) + z_y
-    const bool st_both = WANT_Y && (p.tma_y && p.y) && (p.tma_q && p.qy);       // both kinds staged: one buffer each, single-buffered
     uint32_t st_ctr = 0;                                              // chunks this warp has staged so far
     int local = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
@@ -240,8 +242,12 @@ qv_int8_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       tc_fence_after();
       const int64_t row = static_cast<int64_t>(m_blk) * I8_BM + q * 32 + lane;
       const bool row_ok = row < p.M;
+      if (par * 32 >= BN) {            // BN = 64: the third and fourth warp of a lane quarter have no chunk, only the hand-back
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[buf]);
+      }
 #pragma unroll 1
-      for (int c0 = par * 32; c0 < BN; c0 += 64) {
+      for (int c0 = par * 32; c0 < BN; c0 += 8 * I8_EPI_WARPS) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN + c0), r);
         const int64_t n0 = static_cast<int64_t>(n_blk) * BN + c0;
@@ -272,7 +278,7 @@ qv_int8_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           __syncwarp();
         }
         tmem_ld_wait();
-        if (c0 + 64 >= BN) {           // this warp's last chunk of the tile is in registers
+        if (c0 + 8 * I8_EPI_WARPS >= BN) {           // this warp's last chunk of the tile is in registers
           tc_fence_before();
           mbar_arrive(&tmem_empty[buf]);
         }
@@ -318,12 +324,12 @@ qv_int8_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         const int row0 = m_blk * I8_BM + q * 32;
         if (static_cast<int64_t>(row0) >= p.M) continue;          // warp-uniform: the whole slab is padding
         if (any_tma) {
-          const uint32_t sb = st_both ? 0u : (st_ctr & 1u);
-          uint8_t* st_y = st_base + sb * 4096;
-          uint8_t* st_q = st_both ? st_base + 4096 : st_base + sb * 1024;
+          const uint32_t sb = st_ctr & 1u;
+          uint8_t* st_y = st_base;
+          uint8_t* st_q = st_base + sb * 1024;
           ++st_ctr;
-          if (lane == 0) {                                        // bulk groups retire in order: with two buffers the store of the
-            if (st_both) tma_store_wait_read<0>();                // chunk BEFORE the previous one has left the buffer reused now
+          if (lane == 0) {                                        // bulk groups retire in order: with two code buffers the store of
+            if (WANT_Y) tma_store_wait_read<0>();                 // the chunk BEFORE the previous one has left the buffer reused now
             else tma_store_wait_read<1>();
           }
           __syncwarp();
@@ -625,7 +631,7 @@ extern "C" int qv_int8_linear(const uint8_t* qx, int64_t M, int64_t K, const flo
   // TMA-stored outputs need 16-byte aligned bases and row pitches (N % 4 floats / N % 16 bytes); the 10-class head keeps plain stores
   CUtensorMap my = ma, mq = ma;
   kp.tma_y = (y && N % 4 == 0 && qv_aligned16(y)) ? 1 : 0;
-  kp.tma_q = (qy && N % 16 == 0 && qv_aligned16(qy)) ? 1 : 0;
+  kp.tma_q = (qy && !y && N % 16 == 0 && qv_aligned16(qy)) ? 1 : 0;    // one staged output kind per launch (4 KB per warp)
   if (kp.tma_y) {
     rc = make_out_map(&my, y, N, M, N, 1, 0);
     if (rc) return rc;
