@@ -336,6 +336,11 @@ int qv_head_bwd(const float* g, const float* x, const float* wq, const uint8_t* 
 int qv_int8_linear(const uint8_t* qx, int64_t M, int64_t K, const float* sx, const int32_t* zx, const int8_t* qw, int64_t N,
                    const float* sw, int32_t per_channel, const int32_t* wsum, const float* bias, float sy, int32_t zy,
                    int32_t bias_int, uint8_t* qy, float* y, void* stream);
+/* Same product and requantisation; the output is the CENTRED code q_y - z_y as bf16 [M,N] (|q_y - z_y| <= 255 is exact): the
+ * one-plane integer operand qv_attn_fwd takes for q, k, v, with s_y passed to it as qk_scale / v_scale.  N % 8 == 0. */
+int qv_int8_linear_codes(const uint8_t* qx, int64_t M, int64_t K, const float* sx, const int32_t* zx, const int8_t* qw, int64_t N,
+                         const float* sw, int32_t per_channel, const int32_t* wsum, const float* bias, float sy, int32_t zy,
+                         int32_t bias_int, uint16_t* codes, void* stream);
 /* q = clamp(rint(x * (1/scale)) + zero_point, 0, 255) with device-scalar qparams (torch.quantize_per_tensor / nnq.Quantize). */
 int qv_quantize_u8(const float* x, int64_t n, const float* scale, const int32_t* zero_point, uint8_t* q, void* stream);
 /* Affine qparams from an ordered min/max accumulator (qv_minmax_accumulate), Python-observer formula

@@ -125,6 +125,7 @@ _SIGNATURES = {
                               c_int64, _P, c_int32, _P]),
     "qv_int8_linear": (c_int, [_P, c_int64, c_int64, _P, _P, _P, c_int64, _P, c_int32, _P, _P, c_float, c_int32, c_int32, _P, _P,
                                _P]),
+    "qv_int8_linear_codes": (c_int, [_P, c_int64, c_int64, _P, _P, _P, c_int64, _P, c_int32, _P, _P, c_float, c_int32, c_int32, _P, _P]),
     "qv_quantize_u8": (c_int, [_P, c_int64, _P, _P, _P, _P]),
     "qv_qparams_from_minmax": (c_int, [_P, c_int32, c_int32, _P, _P, _P]),
     "qv_im2col_u8": (c_int, [_P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P, _P]),

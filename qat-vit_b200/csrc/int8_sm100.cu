@@ -73,6 +73,7 @@ struct I8Params {
   int32_t bias_int;       // 0: float bias added to float(acc) (x86 / fbgemm); 1: bias pre-quantised to int32 (qnnpack)
   uint8_t* qy;            // [M,N] quint8 codes (may be null)
   float* y;               // [M,N] dequantised (q_y - z_y) * s_y (may be null)
+  uint16_t* codes16;      // [M,N] bf16(q_y - z_y): the one-plane integer operand of the fused attention (codes-only kernel, N % 8 == 0)
   int32_t tma_y, tma_q;   // outputs leave through shared-memory staging + TMA stores (full 128-byte lines) when their pitch allows
 };
 
@@ -129,7 +130,7 @@ qv_int8_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     prefetch_tensormap(&map_a);
     prefetch_tensormap(&map_b);
     if (p.tma_y) prefetch_tensormap(&map_y);
-    if (p.tma_q) prefetch_tensormap(&map_q);
+    if (p.tma_q || p.codes16) prefetch_tensormap(&map_q);
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], I8_EPI_WARPS * 32); }
     fence_barrier_init();
@@ -231,8 +232,9 @@ qv_int8_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     // Row-per-lane registers written straight to global memory touch 32 different lines per store instruction (one 16-byte
     // piece of a sector each: the LSU, not HBM, bounded the kernel): outputs go through swizzled staging and leave as TMA boxes.
     uint8_t* st_base = smem_out + ew * I8_STAGE_WARP_BYTES;
-    const bool any_tma = p.tma_y || p.tma_q;
+    const bool any_tma = p.tma_y || p.tma_q || (!WANT_Y && p.codes16 != nullptr);
     const int32_t code_bias = p.zy - 0x4B400000;                      // (v + 1.5 * 2^23) as an integer -> rint(v) + z_y
+    const bool codes16 = !WANT_Y && p.codes16 != nullptr;
     uint32_t st_ctr = 0;                                              // chunks this warp has staged so far
     int local = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
@@ -285,6 +287,7 @@ qv_int8_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         if (n0 >= p.N) continue;
         const int ncols = static_cast<int>(min(static_cast<int64_t>(32), p.N - n0));
         uint32_t packed[8];
+        uint32_t packed16[WANT_Y ? 1 : 16];
         float deq[32];
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
@@ -318,6 +321,12 @@ qv_int8_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
               c[e] = min(max(i, 0), 255);
             }
             w = __byte_perm(__byte_perm(c[0], c[1], 0x0040), __byte_perm(c[2], c[3], 0x0040), 0x5410);
+            if (codes16) {            // centred codes as bf16: |q - z_y| <= 255 is exact in 8 significant bits = the float's upper half
+              const uint32_t f0 = __float_as_uint(static_cast<float>(c[0] - p.zy)), f1 = __float_as_uint(static_cast<float>(c[1] - p.zy));
+              const uint32_t f2 = __float_as_uint(static_cast<float>(c[2] - p.zy)), f3 = __float_as_uint(static_cast<float>(c[3] - p.zy));
+              packed16[2 * j4] = __byte_perm(f0, f1, 0x7632);
+              packed16[2 * j4 + 1] = __byte_perm(f2, f3, 0x7632);
+            }
           }
           packed[j4] = w;
         }
@@ -333,7 +342,14 @@ qv_int8_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             else tma_store_wait_read<1>();
           }
           __syncwarp();
-          if (p.tma_q && p.qy) {                                  // 32 rows x 32 bytes, linear
+          if (!WANT_Y && codes16) {                               // 32 rows x 64 bytes (32 bf16), linear; two 2 KB buffers
+            st_q = st_base + sb * 2048;
+            const uint32_t a = smem_u32(st_q) + lane * 64;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + 16 * j), "r"(packed16[WANT_Y ? 0 : 4 * j]),
+                           "r"(packed16[WANT_Y ? 0 : 4 * j + 1]), "r"(packed16[WANT_Y ? 0 : 4 * j + 2]), "r"(packed16[WANT_Y ? 0 : 4 * j + 3]) : "memory");
+          } else if (p.tma_q && p.qy) {                           // 32 rows x 32 bytes, linear
             const uint32_t a = smem_u32(st_q) + lane * 32;
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(packed[0]), "r"(packed[1]), "r"(packed[2]), "r"(packed[3]) : "memory");
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + 16), "r"(packed[4]), "r"(packed[5]), "r"(packed[6]), "r"(packed[7]) : "memory");
@@ -348,7 +364,7 @@ qv_int8_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            if (p.tma_q && p.qy) tma_store_2d(&map_q, st_q, static_cast<int>(n0), row0);
+            if ((p.tma_q && p.qy) || codes16) tma_store_2d(&map_q, st_q, static_cast<int>(n0), row0);
             if (WANT_Y && p.tma_y && p.y) tma_store_3d(&map_y, st_y, static_cast<int>(n0), row0, 0);
             tma_store_commit();
           }
@@ -418,6 +434,20 @@ int make_map_q_out(CUtensorMap* m, uint8_t* ptr, int64_t rows, int64_t N) {
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   QV_REQUIRE(r == CUDA_SUCCESS, QV_ERR_CUDA, "cuTensorMapEncodeTiled(quint8 output) failed (%d)", (int)r);
+  return 0;
+}
+
+// bf16 code output [rows][N] as a 2-D tensor (N, rows); store box = (32 codes = 64 bytes, 32 rows), no swizzle
+int make_map_codes_out(CUtensorMap* m, uint16_t* ptr, int64_t rows, int64_t N) {
+  EncodeTiledFn enc = get_encode();
+  QV_REQUIRE(enc != nullptr, QV_ERR_CUDA, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(N) * 2};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  QV_REQUIRE(r == CUDA_SUCCESS, QV_ERR_CUDA, "cuTensorMapEncodeTiled(bf16 code output) failed (%d)", (int)r);
   return 0;
 }
 
@@ -607,12 +637,14 @@ __global__ void __launch_bounds__(256) gelu_u8_requant_kernel(const uint8_t* __r
 
 }  // namespace
 
-extern "C" int qv_int8_linear(const uint8_t* qx, int64_t M, int64_t K, const float* sx, const int32_t* zx, const int8_t* qw,
-                              int64_t N, const float* sw, int32_t per_channel, const int32_t* wsum, const float* bias, float sy,
-                              int32_t zy, int32_t bias_int, uint8_t* qy, float* y, void* stream) {
-  QV_REQUIRE(qx && qw && sx && zx && sw && wsum && (qy || y), QV_ERR_INVALID, "null pointer in int8_linear");
+static int int8_linear_impl(const uint8_t* qx, int64_t M, int64_t K, const float* sx, const int32_t* zx, const int8_t* qw,
+                            int64_t N, const float* sw, int32_t per_channel, const int32_t* wsum, const float* bias, float sy,
+                            int32_t zy, int32_t bias_int, uint8_t* qy, float* y, uint16_t* codes16, void* stream) {
+  QV_REQUIRE(qx && qw && sx && zx && sw && wsum && (qy || y || codes16), QV_ERR_INVALID, "null pointer in int8_linear");
   QV_REQUIRE(M > 0 && N > 0 && K > 0 && sy > 0.f, QV_ERR_INVALID, "bad int8_linear shape (M=%lld N=%lld K=%lld)", (long long)M,
              (long long)N, (long long)K);
+  QV_REQUIRE(!codes16 || (N % 8 == 0 && qv_aligned16(codes16) && zy >= 0 && zy <= 255), QV_ERR_INVALID,
+             "int8_linear_codes needs N %% 8 == 0, a 16-byte aligned output and a quint8 zero point");
   QV_REQUIRE(qv_num_sms() > 0, QV_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
   const int BN = N <= 64 ? 64 : 128;
   CUtensorMap ma, mb;
@@ -627,7 +659,7 @@ extern "C" int qv_int8_linear(const uint8_t* qx, int64_t M, int64_t K, const flo
   kp.tiles_m = static_cast<int32_t>((M + I8_BM - 1) / I8_BM);
   kp.tiles_n = static_cast<int32_t>((N + BN - 1) / BN);
   kp.sx = sx; kp.zx = zx; kp.sw = sw; kp.per_channel = per_channel; kp.wsum = wsum; kp.bias = bias;
-  kp.sy = sy; kp.zy = zy; kp.bias_int = bias_int; kp.qy = qy; kp.y = y;
+  kp.sy = sy; kp.zy = zy; kp.bias_int = bias_int; kp.qy = qy; kp.y = y; kp.codes16 = codes16;
   // TMA-stored outputs need 16-byte aligned bases and row pitches (N % 4 floats / N % 16 bytes); the 10-class head keeps plain stores
   CUtensorMap my = ma, mq = ma;
   kp.tma_y = (y && N % 4 == 0 && qv_aligned16(y)) ? 1 : 0;
@@ -636,7 +668,10 @@ extern "C" int qv_int8_linear(const uint8_t* qx, int64_t M, int64_t K, const flo
     rc = make_out_map(&my, y, N, M, N, 1, 0);
     if (rc) return rc;
   }
-  if (kp.tma_q) {
+  if (codes16) {
+    rc = make_map_codes_out(&mq, codes16, M, N);
+    if (rc) return rc;
+  } else if (kp.tma_q) {
     rc = make_map_q_out(&mq, qy, M, N);
     if (rc) return rc;
   }
@@ -646,6 +681,20 @@ extern "C" int qv_int8_linear(const uint8_t* qx, int64_t M, int64_t K, const flo
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (BN == 64) return y ? launch_i8<64, true>(ma, mb, my, mq, kp, grid, st) : launch_i8<64, false>(ma, mb, my, mq, kp, grid, st);
   return y ? launch_i8<128, true>(ma, mb, my, mq, kp, grid, st) : launch_i8<128, false>(ma, mb, my, mq, kp, grid, st);
+}
+
+extern "C" int qv_int8_linear(const uint8_t* qx, int64_t M, int64_t K, const float* sx, const int32_t* zx, const int8_t* qw,
+                              int64_t N, const float* sw, int32_t per_channel, const int32_t* wsum, const float* bias, float sy,
+                              int32_t zy, int32_t bias_int, uint8_t* qy, float* y, void* stream) {
+  QV_REQUIRE(qy || y, QV_ERR_INVALID, "null pointer in int8_linear");
+  return int8_linear_impl(qx, M, K, sx, zx, qw, N, sw, per_channel, wsum, bias, sy, zy, bias_int, qy, y, nullptr, stream);
+}
+
+extern "C" int qv_int8_linear_codes(const uint8_t* qx, int64_t M, int64_t K, const float* sx, const int32_t* zx, const int8_t* qw,
+                                    int64_t N, const float* sw, int32_t per_channel, const int32_t* wsum, const float* bias, float sy,
+                                    int32_t zy, int32_t bias_int, uint16_t* codes, void* stream) {
+  QV_REQUIRE(codes, QV_ERR_INVALID, "null pointer in int8_linear_codes");
+  return int8_linear_impl(qx, M, K, sx, zx, qw, N, sw, per_channel, wsum, bias, sy, zy, bias_int, nullptr, nullptr, codes, stream);
 }
 
 extern "C" int qv_quantize_u8(const float* x, int64_t n, const float* scale, const int32_t* zero_point, uint8_t* q, void* stream) {

@@ -13,8 +13,9 @@ its codes directly; every other quantized module quantises its fp32 input per te
 
 Two realisations of that glue, same arithmetic (``ConvertedStudent(..., compact=...)``):
   * compact (default): a converted Linear's output is (q - z_y) * s_y -- an integer code times one scale -- so where the consumer
-    can work on codes the GEMM writes its quint8 codes (1 byte / element) instead of the dequantised fp32 tensor: attention takes
-    the centred codes as ONE exact bf16 plane (the QAT student's fused attention kernel, s_y applied inside), and GELU + the
+    can work on codes the GEMM writes codes instead of the dequantised fp32 tensor: the qkv Linear emits the centred codes
+    q - z_y as ONE exact bf16 plane (qv_int8_linear_codes; the QAT student's fused attention kernel, s_y applied inside), fc1 emits
+    quint8 codes (1 byte / element), and GELU + the
     dynamic re-quantisation between fc1 and fc2 are 256-entry table lookups on the codes (bit-identical codes: every table entry
     is computed with the elementwise expressions); the qparams kernel is folded into the quantising pass.
   * ``compact=False``: every Linear writes fp32, the glue runs elementwise on fp32 tensors (the first implementation; kept as the
@@ -183,11 +184,10 @@ class ConvertedStudent:
         # The table kernels move 16 codes per thread.
         if compact not in (True, False, "attn", "gelu"):
             raise ValueError("compact must be True, False, 'attn' or 'gelu'")
-        self.c_attn = compact in (True, "attn") and (M * 3 * D) % 16 == 0
+        self.c_attn = compact in (True, "attn") and D % 8 == 0
         self.c_gelu = compact in (True, "gelu") and (M * F) % 16 == 0
         self.compact = self.c_attn and self.c_gelu
         if self.c_attn:
-            self.q_qkv = e(M, 3 * D, dt=torch.uint8)
             self.qkv_codes = e(1, M, 3 * D, dt=torch.bfloat16)
         else:
             self.qkv = e(M, 3 * D)
@@ -252,8 +252,7 @@ class ConvertedStudent:
             if self.c_attn:
                 # q, k, v = (codes - z_y) * s_y: the centred codes are one exact bf16 plane, s_y is applied by the attention kernel
                 ql = blk["qkv"]
-                self._lin(ql, self.qh, s, z, qy=self.q_qkv)
-                ops.codes_from_u8(self.q_qkv, ql.zy, self.qkv_codes)
+                ops.int8_linear_codes(self.qh, s, z, ql.qw, ql.sw, ql.wsum, ql.bias, ql.sy, ql.zy, self.qkv_codes)
                 ops.attn_fwd(self.qkv_codes, B, T, H, self.attn_scale, None, qk_scale=ql.sy_dev, v_scale=ql.sy_dev, out_f32=self.o)
             else:
                 self._lin(blk["qkv"], self.qh, s, z, self.qkv)

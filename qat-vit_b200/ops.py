@@ -555,6 +555,20 @@ def int8_linear(qx, sx, zx, qw, sw, wsum, bias, sy, zy, qy=None, y=None, engine=
     return qy if qy is not None else y
 
 
+def int8_linear_codes(qx, sx, zx, qw, sw, wsum, bias, sy, zy, codes, engine="x86"):
+    """quantized::linear whose output is the centred code q_y - zy as ONE bf16 plane (the integer operand of attn_fwd):
+    codes bf16 [M, N] or [1, M, N] (include/qatvit_b200.h: qv_int8_linear_codes)."""
+    M, K = qx.shape
+    N = qw.shape[0]
+    if codes.numel() != M * N:
+        raise RuntimeError("qatvit_b200: codes must hold M * N bf16 values")
+    check(_lib.lib().qv_int8_linear_codes(_p(qx, torch.uint8, "qx"), M, K, _p(sx, torch.float32, "sx"), _p(zx, torch.int32, "zx"),
+                                          _p(qw, torch.int8, "qw"), N, _p(sw, torch.float32, "sw"), int(sw.numel() > 1),
+                                          _p(wsum, torch.int32, "wsum"), _p(bias, torch.float32, "bias"), float(sy), int(zy),
+                                          int(engine == "qnnpack"), _p(codes, torch.bfloat16, "codes"), _stream()), "int8_linear_codes")
+    return codes
+
+
 def quantize_u8(x, scale, zero_point, out=None):
     if out is None:
         out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
@@ -620,6 +634,7 @@ def head_bwd(g, x, wq, wmask, B, K, N, gx, gw, gb, accumulate=False):
 # optional per-op CUDA-event profiling (bench.py's roofline section; off by default, zero overhead when off)
 # ------------------------------------------------------------------------------------------------
 _prof = None
+_prof_gc = True
 
 
 def _gemm_tag(args, kw):
@@ -687,7 +702,7 @@ for _nm in ("zero_", "minmax_reset", "minmax_accumulate", "obs_update", "fq_appl
            "kd_ce_loss", "splitk_reduce", "colsum_reduce", "colsum_rows",
            "embed_fwd", "im2col_fq", "softmax_planes", "attn_ds", "head_fwd", "head_bwd", "attn_fwd", "attn_bwd", "attn_bwd_gp",
            "int8_linear", "quantize_u8", "qparams_from_minmax", "im2col_u8", "gelu_minmax", "quantize_u8_dyn", "codes_from_u8",
-           "gelu_u8_minmax", "gelu_u8_requant"):
+           "gelu_u8_minmax", "gelu_u8_requant", "int8_linear_codes"):
     globals()[_nm] = _wrap(_nm, globals()[_nm])
 gemm = _wrap("gemm", gemm, _gemm_tag)
 act_planes = _wrap("act_planes", act_planes, _bytes_act_planes)
@@ -701,7 +716,14 @@ def profiling() -> bool:
 
 
 def profile_begin() -> None:
-    global _prof
+    """Start recording a CUDA-event pair around every op.  The cyclic garbage collector is paused until profile_end(): a
+    generation-2 collection landing between an op's two events (tens of ms with a model's worth of tensors alive) would be
+    charged to that op -- seen as a 35-45 ms `int8_linear` / `resid_ln_fwd` in tools/int8_quick.py."""
+    global _prof, _prof_gc
+    import gc
+    _prof_gc = gc.isenabled()
+    gc.collect()
+    gc.disable()
     _prof = []
 
 
@@ -709,6 +731,9 @@ def profile_end():
     """-> {tag: dict(count, ms, work)} with CUDA-event durations of every op since profile_begin()."""
     global _prof
     torch.cuda.synchronize()
+    if _prof_gc:
+        import gc
+        gc.enable()
     out = {}
     for tag, work, s, e in _prof:
         d = out.setdefault(tag, dict(count=0, ms=0.0, work=0.0))

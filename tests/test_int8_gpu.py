@@ -69,6 +69,17 @@ def test_int8_linear_vs_quantized_linear(cuda_dev, M, N, K, per_channel):
     qy, y = _run_ours(cuda_dev, qx.int_repr(), sx, zx, qw.int_repr(), sw, b, sy, zy)
     assert torch.equal(qy, ref.int_repr())
     assert torch.equal(y, ref.dequantize())
+    if N % 8 == 0:
+        # third output form: the centred codes q_y - z_y as one bf16 plane (the attention operand of the compact executor)
+        from qatvit_b200 import ops
+        dev = cuda_dev
+        qwd = qw.int_repr().to(torch.int8).contiguous().to(dev)
+        codes = ops.int8_linear_codes(qx.int_repr().contiguous().to(dev), torch.tensor([sx], dtype=torch.float32, device=dev),
+                                      torch.tensor([zx], dtype=torch.int32, device=dev), qwd, sw.to(torch.float32).contiguous().to(dev),
+                                      qw.int_repr().to(torch.int32).sum(1).to(torch.int32).contiguous().to(dev), b.to(dev), sy, zy,
+                                      torch.full((M, N), 7.0, dtype=torch.bfloat16, device=dev))
+        torch.cuda.synchronize()
+        assert torch.equal(codes.float().cpu(), ref.int_repr().float() - float(zy))
 
 
 @pytest.mark.parametrize("shape", [(4, 197, 384), (3, 5, 7), (1, 3, 64, 64)])
