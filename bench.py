@@ -354,7 +354,9 @@ def side_measurements(student, teacher, step, images, labels, dev, peaks, budget
         ops.profile_begin()
         logits = ex_(images)
         prof = ops.profile_end()
-        lin = prof.get("int8_linear", {"ms": 0.0, "count": 0})
+        # every converted Linear: the fp32 / quint8-output launches and the bf16-code-plane launches of the qkv Linears
+        lin = {"ms": sum(prof.get(k, {"ms": 0.0})["ms"] for k in ("int8_linear", "int8_linear_codes")),
+               "count": sum(prof.get(k, {"count": 0})["count"] for k in ("int8_linear", "int8_linear_codes"))}
         # qkv 3, proj 1, fc1 4, fc2 4 = 12 D^2 MACs per token and block, 12 blocks, + the patch-embed conv
         int_ops = 2.0 * 197 * B * 12 * 12 * 384 * 384 + 2.0 * 196 * B * 384 * 768
         int8_peak = 2.0 * peaks["tf_sustained"]
