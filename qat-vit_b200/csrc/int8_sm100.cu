@@ -12,8 +12,9 @@
 // bit-identical to the fbgemm / x86 engines of the reference (tests/test_int8_gpu.py; oracle: oracle/fq_oracle.c qo_int8_linear).
 //
 // Structure: persistent 128 x BN tiles; warp 0 TMA producer (128-byte rows of 128 int8, 128B swizzle, OOB zero fill),
-// warp 1 MMA issuer (4 x K=32 steps per stage, double-buffered TMEM accumulators), warps 2-9 requantising epilogue (two per
-// TMEM lane quarter on alternate 32-column chunks; the per-column terms of a chunk are staged once in shared memory).
+// warp 1 MMA issuer (4 x K=32 steps per stage, double-buffered TMEM accumulators), warps 2-17 requantising epilogue (four per
+// TMEM lane quarter, one 32-column chunk of a 128-wide tile each; the per-column terms of all N columns are computed once per CTA
+// into a shared-memory table).  Outputs: dequantised fp32, quint8 codes, or the centred codes as one bf16 plane.
 #include <cuda.h>
 #include <stdio.h>
 #include <string.h>
@@ -215,9 +216,9 @@ qv_int8_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     }
   } else {
     // =============================== requantising epilogue ===============================
-    // A K = 384 tile is 12 MMAs (~1.2 k clk at the int8 rate): the epilogue, not the tensor pipe, bounds this kernel, so it runs
-    // on 8 warps, fetches the per-column terms as broadcast LDS.128 (they were three shuffles per ELEMENT) and rounds with the
-    // magic-number add (round-to-nearest-even like nearbyintf, exact for |v| < 2^22 and clamped the same beyond).
+    // A K = 384 tile is 12 MMAs (~0.8 k clk at the int8 rate): the epilogue, not the tensor pipe, bounds this kernel, so it runs
+    // on 16 warps, fetches the per-column terms as broadcast 16-byte shared-memory loads (they were three shuffles per ELEMENT) and
+    // rounds with the magic-number add (round-to-nearest-even like nearbyintf, exact for |v| < 2^22 and clamped the same beyond).
     const int ew = warp - 2;
     const int q = warp & 3;
     const int par = ew >> 2;
