@@ -236,6 +236,7 @@ qv_int8_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     const bool any_tma = p.tma_y || p.tma_q || (!WANT_Y && p.codes16 != nullptr);
     const int32_t code_bias = p.zy - 0x4B400000;                      // (v + 1.5 * 2^23) as an integer -> rint(v) + z_y
     const bool codes16 = !WANT_Y && p.codes16 != nullptr;
+    const int32_t centre_bias = 0x4B400000 - p.zy;                    // bits(1.5 * 2^23 + (q - z_y)) = q + centre_bias for |q - z_y| <= 255
     uint32_t st_ctr = 0;                                              // chunks this warp has staged so far
     int local = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++local) {
@@ -323,8 +324,11 @@ qv_int8_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             }
             w = __byte_perm(__byte_perm(c[0], c[1], 0x0040), __byte_perm(c[2], c[3], 0x0040), 0x5410);
             if (codes16) {            // centred codes as bf16: |q - z_y| <= 255 is exact in 8 significant bits = the float's upper half
-              const uint32_t f0 = __float_as_uint(static_cast<float>(c[0] - p.zy)), f1 = __float_as_uint(static_cast<float>(c[1] - p.zy));
-              const uint32_t f2 = __float_as_uint(static_cast<float>(c[2] - p.zy)), f3 = __float_as_uint(static_cast<float>(c[3] - p.zy));
+              // int -> float without the XU pipe (ncu: 92 % busy with one I2F per element more): 1.5 * 2^23 + n as a bit pattern, minus 1.5 * 2^23
+              const uint32_t f0 = __float_as_uint(__fsub_rn(__int_as_float(c[0] + centre_bias), 12582912.0f));
+              const uint32_t f1 = __float_as_uint(__fsub_rn(__int_as_float(c[1] + centre_bias), 12582912.0f));
+              const uint32_t f2 = __float_as_uint(__fsub_rn(__int_as_float(c[2] + centre_bias), 12582912.0f));
+              const uint32_t f3 = __float_as_uint(__fsub_rn(__int_as_float(c[3] + centre_bias), 12582912.0f));
               packed16[2 * j4] = __byte_perm(f0, f1, 0x7632);
               packed16[2 * j4 + 1] = __byte_perm(f2, f3, 0x7632);
             }
