@@ -23,6 +23,7 @@ Two realisations of that glue, same arithmetic (``ConvertedStudent(..., compact=
 """
 from __future__ import annotations
 
+import math
 import re
 from typing import Dict
 
@@ -179,13 +180,12 @@ class ConvertedStudent:
         self.x = [e(M, D), e(M, D)]
         self.h = e(M, D)
         self.qh = e(M, D, dt=torch.uint8)
-        # the code-plane attention kernel is specialised for 64-wide heads; the table kernels move 16 codes per thread
         # compact: True / False, or "attn" / "gelu" for one half only ("gelu" is bit-identical to False: the parity reference).
         # The table kernels move 16 codes per thread.
         if compact not in (True, False, "attn", "gelu"):
             raise ValueError("compact must be True, False, 'attn' or 'gelu'")
         self.c_attn = compact in (True, "attn") and D % 8 == 0
-        self.c_gelu = compact in (True, "gelu") and (M * F) % 16 == 0
+        self.c_gelu = compact in (True, "gelu") and F % 16 == 0
         self.compact = self.c_attn and self.c_gelu
         if self.c_attn:
             self.qkv_codes = e(1, M, 3 * D, dt=torch.bfloat16)
@@ -203,10 +203,39 @@ class ConvertedStudent:
         self.xn = e(B, D)
         self.qxn = e(B, D, dt=torch.uint8)
         self.logits = e(B, self.C)
+        # Ragged last batch (the reference's eval DataLoader has no drop_last: 10 000 % 256 = 16 images, ref qat_trainer.py:237-254):
+        # every activation buffer is re-viewed as the CONTIGUOUS tensor an executor built for b images would own (same storage, first
+        # numel(b) elements); kernels take their row counts at launch, so b images on an executor built for B give bit for bit what
+        # an executor built for b gives.  Views are cached per b.
+        self._full = {k: v for k, v in vars(self).items()
+                      if torch.is_tensor(v) and k in ("q_img", "p", "h", "qh", "qkv_codes", "qkv", "qkvp", "q_f", "f", "g", "o", "y", "qg",
+                                                      "xn", "qxn", "logits")}
+        self._full["x0"], self._full["x1"] = self.x
+        self._views = {}
+        self._cur = batch
         n_dyn = 4 * self.L + 1
         self.acc = torch.empty(n_dyn, 2, dtype=torch.int32, device=dev)
         self.dyn_scale = e(n_dyn)
         self.dyn_zp = torch.empty(n_dyn, dtype=torch.int32, device=dev)
+
+    def _bind(self, b: int) -> None:
+        """Point every activation buffer attribute at its batch-b view."""
+        if b == self._cur:
+            return
+        views = self._views.get(b)
+        if views is None:
+            views = {}
+            for name, full in self._full.items():
+                shape = list(full.shape)
+                ax = 1 if full.dim() == 3 else 0                 # [planes, rows, cols] or [rows, cols]: rows scale with the batch
+                shape[ax] = shape[ax] * b // self.B
+                views[name] = full.view(-1)[:math.prod(shape)].view(shape)
+            self._views[b] = views
+        for name, v in views.items():
+            if name not in ("x0", "x1"):
+                setattr(self, name, v)
+        self.x = [views["x0"], views["x1"]]
+        self._cur = b
 
     def _dyn_quant(self, slot: int, x: torch.Tensor, out: torch.Tensor, have_minmax: bool = False):
         """dynamic per-tensor affine quint8 (0..255) of an fp32 tensor: min/max -> qparams -> codes, all on device."""
@@ -227,10 +256,13 @@ class ConvertedStudent:
     @torch.no_grad()
     def forward(self, images: torch.Tensor, trace=None) -> torch.Tensor:
         """trace (optional dict): name -> clone of the uint8 input codes of each quantized module (parity diagnostics)."""
-        B, T, D, P, H, F = self.B, self.T, self.D, self.P, self.H, self.F
+        T, D, P, H, F = self.T, self.D, self.P, self.H, self.F
+        B = int(images.shape[0]) if images.dim() == 4 else -1
+        if images.dim() != 4 or tuple(images.shape[1:]) != (3, self.HW, self.HW) or not (1 <= B <= self.B) or not images.is_cuda:
+            raise RuntimeError(f"converted executor built for CUDA batches of 1..{self.B} 3x{self.HW}x{self.HW} images, got "
+                               f"{tuple(images.shape)} on {images.device}")
+        self._bind(B)
         M = B * T
-        if tuple(images.shape) != (B, 3, self.HW, self.HW) or not images.is_cuda:
-            raise RuntimeError(f"converted executor built for CUDA batch {B}, got {tuple(images.shape)} on {images.device}")
         ops.minmax_reset(self.acc)
         ops.im2col_u8(images, self.in_scale, self.in_zp, B, 3, self.HW, self.ps, self.q_img)
         self._lin(self.conv, self.q_img, self.in_scale, self.in_zp, self.p)

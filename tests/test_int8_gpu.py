@@ -259,6 +259,29 @@ def test_compact_glue_end_to_end_against_the_fp32_glue(cuda_dev):
     assert torch.isfinite(full[0]).all() and float(diff.abs().max()) <= 6.0 * step + 1e-6
 
 
+@pytest.mark.parametrize("compact", [True, False])
+def test_converted_executor_takes_a_ragged_tail_batch(cuda_dev, compact):
+    """The reference's eval DataLoader has no drop_last (ref qat_trainer.py:237-254: 10 000 % 256 = 16): an executor built for B
+    images fed b < B must give, bit for bit, what an executor built for b gives -- then run the full batch again unchanged."""
+    from qatvit_b200.int8 import ConvertedStudent
+    conv, images = _converted("fbgemm", "vit_test_tiny", "vit_test_teacher", 64, 5)
+    x = images.to(cuda_dev)
+    big = ConvertedStudent(conv, 5, cuda_dev, compact=compact)
+    full_a = big(x).clone()
+    for b in (3, 1):
+        tail = big(x[:b].contiguous()).clone()
+        ref = ConvertedStudent(conv, b, cuda_dev, compact=compact)(x[:b].contiguous()).clone()
+        torch.cuda.synchronize()
+        assert tail.shape == (b, 10) and torch.equal(tail, ref), b
+    full_b = big(x).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(full_a, full_b)
+    for bad in (torch.zeros(6, 3, 64, 64, device=cuda_dev), torch.zeros(0, 3, 64, 64, device=cuda_dev),
+                torch.zeros(2, 3, 32, 32, device=cuda_dev), x[:2].cpu()):
+        with pytest.raises(RuntimeError, match="1..5"):
+            big(bad)
+
+
 def test_best_converted_pth_reader_runs_identically(cuda_dev, tmp_path):
     """ConvertedStudent.from_state_dict(best_converted.pth) == ConvertedStudent(converted module): same operands, same
     kernels, bit-identical logits (the stock file format of ref qat_trainer.py:386-388 is all the executor needs)."""
