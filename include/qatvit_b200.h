@@ -363,6 +363,11 @@ int qv_gelu_minmax(const float* x, int64_t n, float* y, uint32_t* acc, void* str
 int qv_quantize_u8_dyn(const float* x, int64_t n, const uint32_t* acc, float* scale_out, int32_t* zero_point_out, uint8_t* q,
                        void* stream);
 int qv_codes_from_u8(const uint8_t* q, int64_t n, int32_t zero_point, uint16_t* codes, void* stream);
+/* q = quantize_u8(LayerNorm(x) * gamma + beta) with the dynamic qparams of acc, the LayerNorm output recomputed from the row
+ * statistics qv_resid_ln_fwd saved (mean, rstd: fp32 [R]) instead of read back as fp32; x fp32 [R][D] is that call's x_out (or its
+ * x_in when there was no residual).  Bit-identical to qv_resid_ln_fwd(h_f32) -> qv_quantize_u8_dyn.  D as for qv_resid_ln_fwd. */
+int qv_ln_quantize_u8_dyn(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta, int64_t R,
+                          int32_t D, const uint32_t* acc, float* scale_out, int32_t* zero_point_out, uint8_t* q, void* stream);
 int qv_gelu_u8_minmax(const uint8_t* q, int64_t n, float sy, int32_t zy, uint32_t* acc, void* stream);
 int qv_gelu_u8_requant(const uint8_t* q, int64_t n, float sy, int32_t zy, const uint32_t* acc, float* scale_out,
                        int32_t* zero_point_out, uint8_t* out, void* stream);

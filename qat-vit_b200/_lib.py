@@ -134,6 +134,7 @@ _SIGNATURES = {
     "qv_gelu_minmax": (c_int, [_P, c_int64, _P, _P, _P]),
     "qv_quantize_u8_dyn": (c_int, [_P, c_int64, _P, _P, _P, _P, _P]),
     "qv_codes_from_u8": (c_int, [_P, c_int64, c_int32, _P, _P]),
+    "qv_ln_quantize_u8_dyn": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int32, _P, _P, _P, _P, _P]),
     "qv_gelu_u8_minmax": (c_int, [_P, c_int64, c_float, c_int32, _P, _P]),
     "qv_gelu_u8_requant": (c_int, [_P, c_int64, c_float, c_int32, _P, _P, _P, _P, _P]),
     "qv_head_fwd": (c_int, [_P, _P, _P, c_int32, c_int32, c_int32, _P, _P, _P]),

@@ -700,6 +700,54 @@ __global__ void __launch_bounds__(256) gelu_minmax_kernel(const float* __restric
   }
 }
 
+// Converted-student glue: q = quantize_u8(LayerNorm(x)) with the DYNAMIC qparams of the finished min / max accumulator, recomputing
+// the LayerNorm output from the row statistics resid_ln_fwd_kernel saved instead of reading an fp32 copy of it (4 B/elt read + 1 written
+// against 4 written + 4 read + 1 written).  Same arithmetic, operation for operation, as resid_ln_fwd_kernel's output expression
+// (v - mean) * rstd * gamma + beta (subtract, multiply, fused multiply-add) and as qv_qparams_from_minmax + qv_quantize_u8, so the
+// codes are bit-identical to the unfused chain (tests/test_int8_gpu.py).  One warp per row, persistent.
+template <int VPL>
+__global__ void __launch_bounds__(256) ln_quantize_u8_dyn_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                                                 const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, int64_t R, const uint32_t* acc,
+                                                                 float* scale_out, int32_t* zp_out, uint8_t* __restrict__ q) {
+  constexpr int D = 128 * VPL;
+  const int lane = threadIdx.x & 31;
+  // torch/ao/quantization/observer.py:349-427 (affine quint8, 0..255), fp32 arithmetic -- as qv_qparams_from_minmax
+  const float mn = fminf(qv_ord2f(acc[0]), 0.0f), mx = fmaxf(qv_ord2f(acc[1]), 0.0f);
+  float s = __fdiv_rn(__fsub_rn(mx, mn), 255.0f);
+  s = fmaxf(s, 1.1920928955078125e-07f);
+  float z = __fsub_rn(0.0f, nearbyintf(__fdiv_rn(mn, s)));
+  z = fminf(fmaxf(z, 0.0f), 255.0f);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *scale_out = s;
+    *zp_out = static_cast<int32_t>(z);
+  }
+  const float inv = __fdiv_rn(1.0f, s);
+  const int64_t n_warps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  for (int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5); r < R; r += n_warps) {
+    const float m = __ldg(mean + r), rs = __ldg(rstd + r);
+    float4 v[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(x + r * D + (i * 32 + lane) * 4));
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+      const float o[4] = {__fmaf_rn(__fmul_rn(__fsub_rn(v[i].x, m), rs), g.x, b.x), __fmaf_rn(__fmul_rn(__fsub_rn(v[i].y, m), rs), g.y, b.y),
+                          __fmaf_rn(__fmul_rn(__fsub_rn(v[i].z, m), rs), g.z, b.z), __fmaf_rn(__fmul_rn(__fsub_rn(v[i].w, m), rs), g.w, b.w)};
+      uint32_t w = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float f = __fadd_rn(nearbyintf(__fmul_rn(o[j], inv)), z);
+        f = fminf(fmaxf(f, 0.0f), 255.0f);
+        w |= static_cast<uint32_t>(f) << (8 * j);
+      }
+      *reinterpret_cast<uint32_t*>(q + r * D + c) = w;
+    }
+  }
+}
+
 inline int ew_blocks(int64_t n_items, int per_sm = 8) {
   const int sms = qv_num_sms();
   int64_t b = (n_items + 255) / 256;
@@ -922,4 +970,31 @@ extern "C" int qv_head_bwd(const float* g, const float* x, const float* wq, cons
   head_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       g, x, wq, wmask, B, K, N, gx, gw, gb, accumulate);
   return qv_check_launch("qv_head_bwd");
+}
+
+extern "C" int qv_ln_quantize_u8_dyn(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                                     int64_t R, int32_t D, const uint32_t* acc, float* scale_out, int32_t* zero_point_out, uint8_t* q,
+                                     void* stream) {
+  QV_REQUIRE(x && mean && rstd && gamma && beta && acc && scale_out && zero_point_out && q && R > 0, QV_ERR_INVALID,
+             "bad ln_quantize_u8_dyn arguments");
+  QV_REQUIRE(D % 128 == 0 && D >= 128 && D <= 1024, QV_ERR_UNSUPPORTED, "LayerNorm width must be a multiple of 128 <= 1024 (got %d)", D);
+  QV_REQUIRE(qv_aligned16(x) && qv_aligned16(gamma) && qv_aligned16(beta) && (reinterpret_cast<uintptr_t>(q) & 3u) == 0, QV_ERR_INVALID,
+             "ln_quantize_u8_dyn needs 16-byte aligned fp32 buffers and a 4-byte aligned code buffer");
+  QV_NEED_GPU();
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t blocks_needed = (R + 7) / 8;
+  const int64_t resident = static_cast<int64_t>(qv_num_sms()) * 4;
+  const unsigned grid = static_cast<unsigned>(blocks_needed < resident ? blocks_needed : resident);
+#define LAUNCH(V) ln_quantize_u8_dyn_kernel<V><<<grid, 256, 0, st>>>(x, mean, rstd, gamma, beta, R, acc, scale_out, zero_point_out, q)
+  switch (D / 128) {
+    case 1: LAUNCH(1); break;
+    case 2: LAUNCH(2); break;
+    case 3: LAUNCH(3); break;
+    case 4: LAUNCH(4); break;
+    case 6: LAUNCH(6); break;
+    case 8: LAUNCH(8); break;
+    default: return qv_set_error(QV_ERR_UNSUPPORTED, "LayerNorm width %d not instantiated", D);
+  }
+#undef LAUNCH
+  return qv_check_launch("qv_ln_quantize_u8_dyn");
 }

@@ -17,9 +17,11 @@ Two realisations of that glue, same arithmetic (``ConvertedStudent(..., compact=
     q - z_y as ONE exact bf16 plane (qv_int8_linear_codes; the QAT student's fused attention kernel, s_y applied inside), fc1 emits
     quint8 codes (1 byte / element), and GELU + the
     dynamic re-quantisation between fc1 and fc2 are 256-entry table lookups on the codes (bit-identical codes: every table entry
-    is computed with the elementwise expressions); the qparams kernel is folded into the quantising pass.
+    is computed with the elementwise expressions); the qparams kernel is folded into the quantising pass, and the LayerNorm
+    outputs are quantised from the saved row statistics instead of an fp32 copy (qv_ln_quantize_u8_dyn).
   * ``compact=False``: every Linear writes fp32, the glue runs elementwise on fp32 tensors (the first implementation; kept as the
-    parity reference of the compact path, tests/test_int8_gpu.py).
+    parity reference of the compact path, tests/test_int8_gpu.py).  ``compact={"gelu", "ln"}`` selects single features: those
+    two reproduce the fp32 glue bit for bit, "attn" (exact integer products) does not.
 """
 from __future__ import annotations
 
@@ -180,13 +182,23 @@ class ConvertedStudent:
         self.x = [e(M, D), e(M, D)]
         self.h = e(M, D)
         self.qh = e(M, D, dt=torch.uint8)
-        # compact: True / False, or "attn" / "gelu" for one half only ("gelu" is bit-identical to False: the parity reference).
-        # The table kernels move 16 codes per thread.
-        if compact not in (True, False, "attn", "gelu"):
-            raise ValueError("compact must be True, False, 'attn' or 'gelu'")
-        self.c_attn = compact in (True, "attn") and D % 8 == 0
-        self.c_gelu = compact in (True, "gelu") and F % 16 == 0
-        self.compact = self.c_attn and self.c_gelu
+        # compact: True (every feature) / False (none), one feature name, or a collection of names out of
+        #   "attn": qkv leaves its Linear as one bf16 code plane for the integer-code attention kernel (exact products: not
+        #           bit-identical to the fp32 glue, whose hi/lo products are ~2^-16 relative)
+        #   "gelu": GELU + re-quantisation between fc1 and fc2 as table lookups, qparams folded into the quantising passes
+        #   "ln"  : the LayerNorm outputs are quantised from the saved row statistics instead of an fp32 copy
+        # "gelu" and "ln" reproduce the fp32 glue bit for bit (the parity reference of the compact path).
+        feats = {True: {"attn", "gelu", "ln"}, False: set()}.get(compact) if isinstance(compact, bool) else \
+            ({compact} if isinstance(compact, str) else set(compact))
+        if not feats <= {"attn", "gelu", "ln"}:
+            raise ValueError("compact must be True, False, or a selection of 'attn', 'gelu', 'ln'")
+        self.c_attn = "attn" in feats and D % 8 == 0
+        self.c_gelu = "gelu" in feats and F % 16 == 0           # the table kernels move 16 codes per thread
+        self.c_ln = "ln" in feats and D % 128 == 0
+        self.compact = self.c_attn and self.c_gelu and self.c_ln
+        if self.c_ln:
+            self.ln_mean = e(M)
+            self.ln_rstd = e(M)
         if self.c_attn:
             self.qkv_codes = e(1, M, 3 * D, dt=torch.bfloat16)
         else:
@@ -209,7 +221,7 @@ class ConvertedStudent:
         # an executor built for b gives.  Views are cached per b.
         self._full = {k: v for k, v in vars(self).items()
                       if torch.is_tensor(v) and k in ("q_img", "p", "h", "qh", "qkv_codes", "qkv", "qkvp", "q_f", "f", "g", "o", "y", "qg",
-                                                      "xn", "qxn", "logits")}
+                                                      "xn", "qxn", "logits", "ln_mean", "ln_rstd")}
         self._full["x0"], self._full["x1"] = self.x
         self._views = {}
         self._cur = batch
@@ -250,6 +262,24 @@ class ConvertedStudent:
             ops.quantize_u8(x, s, z, out)
         return s, z
 
+    def _ln_quant(self, slot: int, cur: int, y_prev, gamma, beta, M: int):
+        """x <- x + y_prev (when given); qh <- dynamically quantised LayerNorm(x).  Returns (index of the current residual
+        buffer, scale, zero point)."""
+        D = self.D
+        fused = self.c_ln
+        out = dict(mean=self.ln_mean, rstd=self.ln_rstd) if fused else dict(h_f32=self.h)
+        if y_prev is None:
+            ops.resid_ln_fwd(self.x[cur], None, None, gamma, beta, self.eps, M, D, minmax=self.acc[slot], **out)
+        else:
+            ops.resid_ln_fwd(self.x[cur], y_prev, None, gamma, beta, self.eps, M, D, x_out=self.x[cur ^ 1], minmax=self.acc[slot], **out)
+            cur ^= 1
+        if fused:      # the LayerNorm output is recomputed from (x, mean, rstd) inside the quantising pass: no fp32 copy of it
+            s, z = self.dyn_scale[slot:slot + 1], self.dyn_zp[slot:slot + 1]
+            ops.ln_quantize_u8_dyn(self.x[cur], self.ln_mean, self.ln_rstd, gamma, beta, M, D, self.acc[slot], s, z, self.qh)
+        else:
+            s, z = self._dyn_quant(slot, self.h, self.qh, have_minmax=True)
+        return cur, s, z
+
     def _lin(self, ql: _QLin, qx, sx, zx, y=None, qy=None):
         ops.int8_linear(qx, sx, zx, ql.qw, ql.sw, ql.wsum, ql.bias, ql.sy, ql.zy, y=y, qy=qy)
 
@@ -272,13 +302,7 @@ class ConvertedStudent:
         y_prev = None
         for li, blk in enumerate(self.blocks):
             g, b = blk["n1"]
-            if y_prev is None:
-                ops.resid_ln_fwd(self.x[cur], None, None, g, b, self.eps, M, D, h_f32=self.h, minmax=self.acc[slot])
-            else:
-                ops.resid_ln_fwd(self.x[cur], y_prev, None, g, b, self.eps, M, D, x_out=self.x[cur ^ 1], h_f32=self.h,
-                                 minmax=self.acc[slot])
-                cur ^= 1
-            s, z = self._dyn_quant(slot, self.h, self.qh, have_minmax=True); slot += 1
+            cur, s, z = self._ln_quant(slot, cur, y_prev, g, b, M); slot += 1
             if trace is not None:
                 trace[f"blocks.{li}.attn.qkv"] = (self.qh.clone(), s.clone(), z.clone())
             if self.c_attn:
@@ -293,10 +317,7 @@ class ConvertedStudent:
             s, z = self._dyn_quant(slot, self.o, self.qh); slot += 1
             self._lin(blk["proj"], self.qh, s, z, self.y)
             g, b = blk["n2"]
-            ops.resid_ln_fwd(self.x[cur], self.y, None, g, b, self.eps, M, D, x_out=self.x[cur ^ 1], h_f32=self.h,
-                             minmax=self.acc[slot])
-            cur ^= 1
-            s, z = self._dyn_quant(slot, self.h, self.qh, have_minmax=True); slot += 1
+            cur, s, z = self._ln_quant(slot, cur, self.y, g, b, M); slot += 1
             if self.c_gelu:
                 # GELU((q - z_y) s_y) takes <= 256 values: min / max and the re-quantised codes are table lookups on fc1's codes
                 ql = blk["fc1"]

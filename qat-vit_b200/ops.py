@@ -600,6 +600,17 @@ def quantize_u8_dyn(x, acc, scale_out, zero_point_out, out):
     return out
 
 
+def ln_quantize_u8_dyn(x, mean, rstd, gamma, beta, R, D, acc, scale_out, zero_point_out, out):
+    """out = quantize_u8(LayerNorm(x)) with the dynamic qparams of acc, from the row statistics resid_ln_fwd saved
+    (include/qatvit_b200.h: qv_ln_quantize_u8_dyn); the qparams land in scale_out / zero_point_out."""
+    check(_lib.lib().qv_ln_quantize_u8_dyn(_p(x, torch.float32, "x"), _p(mean, torch.float32, "mean"), _p(rstd, torch.float32, "rstd"),
+                                           _p(gamma, torch.float32, "gamma"), _p(beta, torch.float32, "beta"), R, D,
+                                           _p(acc, torch.int32, "acc"), _p(scale_out, torch.float32, "scale_out"),
+                                           _p(zero_point_out, torch.int32, "zero_point_out"), _p(out, torch.uint8, "out"), _stream()),
+          "ln_quantize_u8_dyn")
+    return out
+
+
 def codes_from_u8(q, zero_point, codes):
     """codes = bf16(q - zero_point): a converted Linear's quint8 output as the one-plane integer operand of attn_fwd."""
     check(_lib.lib().qv_codes_from_u8(_p(q, torch.uint8, "q"), q.numel(), int(zero_point), _p(codes, torch.bfloat16, "codes"),
@@ -702,7 +713,7 @@ for _nm in ("zero_", "minmax_reset", "minmax_accumulate", "obs_update", "fq_appl
            "kd_ce_loss", "splitk_reduce", "colsum_reduce", "colsum_rows",
            "embed_fwd", "im2col_fq", "softmax_planes", "attn_ds", "head_fwd", "head_bwd", "attn_fwd", "attn_bwd", "attn_bwd_gp",
            "int8_linear", "quantize_u8", "qparams_from_minmax", "im2col_u8", "gelu_minmax", "quantize_u8_dyn", "codes_from_u8",
-           "gelu_u8_minmax", "gelu_u8_requant", "int8_linear_codes"):
+           "gelu_u8_minmax", "gelu_u8_requant", "int8_linear_codes", "ln_quantize_u8_dyn"):
     globals()[_nm] = _wrap(_nm, globals()[_nm])
 gemm = _wrap("gemm", gemm, _gemm_tag)
 act_planes = _wrap("act_planes", act_planes, _bytes_act_planes)

@@ -190,7 +190,7 @@ def test_converted_student_per_layer_and_end_to_end(cuda_dev, backend, sname, im
     trace = {}
     ref_logits = int8_ref.converted_forward(conv, images, trace)
     ex = ConvertedStudent(conv, B, cuda_dev, compact=compact)
-    assert (ex.c_attn, ex.c_gelu) == (compact in (True, "attn"), compact in (True, "gelu"))
+    assert (ex.c_attn, ex.c_gelu, ex.c_ln) == (compact in (True, "attn"), compact in (True, "gelu"), compact is True)
     # tier 1: every quantized module, on the CPU run's own quint8 input, gives bit-identical codes
     qlins = {"head": ex.head}
     for i, blk in enumerate(ex.blocks):
@@ -230,25 +230,29 @@ def test_converted_student_per_layer_and_end_to_end(cuda_dev, backend, sname, im
 
 
 def test_compact_glue_end_to_end_against_the_fp32_glue(cuda_dev):
-    """The same converted student through the two realisations of the float glue.  The table half (GELU + re-quantisation on
-    fc1's codes, qparams folded into the quantising pass) must reproduce the fp32 glue BIT FOR BIT, logits included; the
-    attention half computes softmax(QK^T)V from exact integer codes instead of fp32 hi/lo planes of the dequantised values
-    (products exact instead of ~2^-16 relative), so block 0's fc2 input may differ by a code on a few elements and the logits by
-    a few head quantisation steps -- the bound the CPU mirror is held to."""
+    """The same converted student through the realisations of the float glue.  The table half (GELU + re-quantisation on fc1's
+    codes, qparams folded into the quantising pass) and the LayerNorm half (codes from the saved row statistics instead of an fp32
+    copy of the LayerNorm output) must reproduce the fp32 glue BIT FOR BIT, logits and every dynamic (scale, zero point)
+    included; the attention half computes softmax(QK^T)V from exact integer codes instead of fp32 hi/lo planes of the
+    dequantised values (products exact instead of ~2^-16 relative), so block 0's fc2 input may differ by a code on a few elements
+    and the logits by a few head quantisation steps -- the bound the CPU mirror is held to."""
     from qatvit_b200.int8 import ConvertedStudent
     conv, images = _converted("fbgemm", "vit_test_tiny", "vit_test_teacher", 64, 4)
     x = images.to(cuda_dev)
     runs = {}
-    for mode in (False, "gelu", True):
+    for mode in (False, "gelu", "ln", ("gelu", "ln"), True):
         ex = ConvertedStudent(conv, 4, cuda_dev, compact=mode)
         tr = {}
-        runs[mode] = (ex(x, tr).clone(), tr)
+        runs[mode] = (ex(x, tr).clone(), tr, ex.dyn_scale.clone(), ex.dyn_zp.clone())
     torch.cuda.synchronize()
-    base, tables, full = runs[False], runs["gelu"], runs[True]
-    assert torch.equal(base[0], tables[0])
-    for k in base[1]:
-        for a, b in zip(base[1][k], tables[1][k]):
-            assert torch.equal(a, b), k
+    base, full = runs[False], runs[True]
+    for mode in ("gelu", "ln", ("gelu", "ln")):
+        other = runs[mode]
+        assert torch.equal(base[0], other[0]), mode
+        assert torch.equal(base[2], other[2]) and torch.equal(base[3], other[3]), mode
+        for k in base[1]:
+            for a, b in zip(base[1][k], other[1][k]):
+                assert torch.equal(a, b), (mode, k)
     qa, sa, za = base[1]["blocks.0.mlp.fc2"]
     qb, sb, zb = full[1]["blocks.0.mlp.fc2"]
     assert abs(float(sa) - float(sb)) <= 1e-5 * float(sa) and abs(int(za) - int(zb)) <= 1
@@ -257,6 +261,8 @@ def test_compact_glue_end_to_end_against_the_fp32_glue(cuda_dev):
     step = conv.model.head.scale
     diff = (full[0] - base[0]).cpu()
     assert torch.isfinite(full[0]).all() and float(diff.abs().max()) <= 6.0 * step + 1e-6
+    with pytest.raises(ValueError):
+        ConvertedStudent(conv, 4, cuda_dev, compact="planes")
 
 
 @pytest.mark.parametrize("compact", [True, False])

@@ -29,7 +29,7 @@ with warnings.catch_warnings():
     conv = convert(copy.deepcopy(student).cpu().eval(), inplace=False)
 torch.cuda.empty_cache()
 outs = {}
-for mode in (False, "gelu", "attn", True):
+for mode in (False, ("gelu", "ln"), "attn", True):
     ex = ConvertedStudent(conv, B, dev, compact=mode)
     for _ in range(3):
         ex(images)
@@ -50,5 +50,5 @@ for mode in (False, "gelu", "attn", True):
     del ex
     torch.cuda.empty_cache()
 stepq = float(conv.model.head.scale)
-print("logits: gelu == fp32 glue:", bool(torch.equal(outs[False], outs["gelu"])), "| full vs fp32 glue, max |diff| in head steps:",
+print("logits: gelu + ln == fp32 glue:", bool(torch.equal(outs[False], outs[("gelu", "ln")])), "| full vs fp32 glue, max |diff| in head steps:",
       float((outs[True] - outs[False]).abs().max()) / stepq)
